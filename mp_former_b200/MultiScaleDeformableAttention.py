@@ -1,0 +1,121 @@
+"""Drop-in for the reference's compiled extension module ``MultiScaleDeformableAttention``.
+
+The reference builds a pybind module of this name exporting ``ms_deform_attn_forward`` and
+``ms_deform_attn_backward`` (ref: mask2former/modeling/pixel_decoder/ops/src/vision.cpp:18-21,
+src/ms_deform_attn.h:25-66, setup.py:60).  This module exports the same two functions with the same
+positional signatures, argument meaning and error behaviour (RuntimeError on CPU tensors, on
+non-contiguous inputs and on batch % im2col_step != 0), implemented by the hand-written sm_100a
+kernels behind the C ABI in ``include/mpformer_b200.h``.
+
+    sys.modules["MultiScaleDeformableAttention"] = mp_former_b200.MultiScaleDeformableAttention
+
+makes the reference's own ``ops/functions/ms_deform_attn_func.py`` run on these kernels unchanged
+(see INTEGRATION.md).
+
+Extension to the reference signature: ``spatial_shapes`` may carry a Python attribute
+``_mpf_host_shapes`` (tuple of (H, W)); when present the launcher tiles queries spatially for L1
+locality.  Results do not depend on it.
+"""
+import torch
+
+from . import _lib
+
+_FLOATS = (torch.float32, torch.float64)
+
+
+def _host_shapes_array(spatial_shapes, host_shapes):
+    import ctypes
+    hs = host_shapes if host_shapes is not None else getattr(spatial_shapes, "_mpf_host_shapes", None)
+    if hs is None:
+        return None
+    flat = [int(v) for hw in hs for v in hw]
+    return (ctypes.c_int64 * len(flat))(*flat)
+
+
+def _check_inputs(named):
+    for name, t in named:
+        if not t.is_contiguous():
+            raise RuntimeError(f"{name} tensor has to be contiguous")
+    for name, t in named:
+        _lib.require_cuda(t, name)
+
+
+def _dims(value, spatial_shapes, sampling_loc, attn_weight, im2col_step):
+    if value.dim() != 4 or sampling_loc.dim() != 6 or attn_weight.dim() != 5:
+        raise RuntimeError("ms_deform_attn: expected value [N,S,M,D], sampling_loc [N,Lq,M,L,P,2], "
+                           "attn_weight [N,Lq,M,L,P]")
+    batch, spatial_size, num_heads, channels = value.shape
+    num_levels = spatial_shapes.shape[0]
+    num_query, num_point = sampling_loc.shape[1], sampling_loc.shape[4]
+    if tuple(sampling_loc.shape) != (batch, num_query, num_heads, num_levels, num_point, 2) or \
+            tuple(attn_weight.shape) != (batch, num_query, num_heads, num_levels, num_point):
+        raise RuntimeError("ms_deform_attn: inconsistent sampling_loc / attn_weight shapes")
+    if spatial_shapes.dtype != torch.int64:
+        raise RuntimeError("spatial_shapes / level_start_index must be int64 (as in the reference)")
+    step = min(batch, int(im2col_step))
+    if step <= 0 or batch % step != 0:
+        raise RuntimeError(f"batch({batch}) must divide im2col_step({step})")
+    if value.dtype not in _FLOATS or sampling_loc.dtype != value.dtype or attn_weight.dtype != value.dtype:
+        raise RuntimeError("ms_deform_attn supports float32/float64 with matching dtypes "
+                           f"(got {value.dtype}, {sampling_loc.dtype}, {attn_weight.dtype})")
+    return batch, spatial_size, num_heads, channels, num_levels, num_query, num_point
+
+
+def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                           im2col_step, host_shapes=None):
+    """ref: ops/src/ms_deform_attn.h:25-45 -> cuda/ms_deform_attn_cuda.cu:25-85.
+    Returns ``[N, Lq, M*D]`` (freshly allocated, same dtype/device as ``value``)."""
+    _check_inputs([("value", value), ("spatial_shapes", spatial_shapes),
+                   ("level_start_index", level_start_index), ("sampling_loc", sampling_loc),
+                   ("attn_weight", attn_weight)])
+    B, S, M, D, L, Lq, P = _dims(value, spatial_shapes, sampling_loc, attn_weight, im2col_step)
+    lib = _lib.load()
+    out = torch.empty((B, Lq, M * D), dtype=value.dtype, device=value.device)
+    with torch.cuda.device(value.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        if value.dtype == torch.float32:
+            hs = _host_shapes_array(spatial_shapes, host_shapes)
+            rc = lib.mpf_msda_forward_f32_ex(
+                value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                sampling_loc.data_ptr(), attn_weight.data_ptr(), B, S, M, D, L, Lq, P,
+                out.data_ptr(), hs, stream)
+        else:
+            rc = lib.mpf_msda_forward_f64(
+                value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                sampling_loc.data_ptr(), attn_weight.data_ptr(), B, S, M, D, L, Lq, P,
+                out.data_ptr(), stream)
+    _lib.check(rc, "ms_deform_attn_forward")
+    return out
+
+
+def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                            grad_output, im2col_step, host_shapes=None):
+    """ref: ops/src/ms_deform_attn.h:47-66 -> cuda/ms_deform_attn_cuda.cu:88-158.
+    Returns ``[grad_value, grad_sampling_loc, grad_attn_weight]``."""
+    _check_inputs([("value", value), ("spatial_shapes", spatial_shapes),
+                   ("level_start_index", level_start_index), ("sampling_loc", sampling_loc),
+                   ("attn_weight", attn_weight), ("grad_output", grad_output)])
+    B, S, M, D, L, Lq, P = _dims(value, spatial_shapes, sampling_loc, attn_weight, im2col_step)
+    if grad_output.dtype != value.dtype or grad_output.numel() != B * Lq * M * D:
+        raise RuntimeError("ms_deform_attn_backward: grad_output must be [N, Lq, M*D] of value's dtype")
+    lib = _lib.load()
+    grad_value = torch.empty_like(value)
+    grad_loc = torch.empty_like(sampling_loc)
+    grad_aw = torch.empty_like(attn_weight)
+    with torch.cuda.device(value.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        if value.dtype == torch.float32:
+            hs = _host_shapes_array(spatial_shapes, host_shapes)
+            rc = lib.mpf_msda_backward_f32_ex(
+                grad_output.data_ptr(), value.data_ptr(), spatial_shapes.data_ptr(),
+                level_start_index.data_ptr(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
+                B, S, M, D, L, Lq, P, grad_value.data_ptr(), grad_loc.data_ptr(),
+                grad_aw.data_ptr(), hs, stream)
+        else:
+            rc = lib.mpf_msda_backward_f64(
+                grad_output.data_ptr(), value.data_ptr(), spatial_shapes.data_ptr(),
+                level_start_index.data_ptr(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
+                B, S, M, D, L, Lq, P, grad_value.data_ptr(), grad_loc.data_ptr(),
+                grad_aw.data_ptr(), stream)
+    _lib.check(rc, "ms_deform_attn_backward")
+    return [grad_value, grad_loc, grad_aw]

@@ -1,0 +1,72 @@
+"""ctypes binding of the C-ABI shared library ``libmpformer_b200.so`` (see include/mpformer_b200.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` (plain ``nvcc -shared``; no torch headers).
+There is NO fallback: if the library is missing or a call fails, a ``RuntimeError`` is raised.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmpformer_b200.so")
+
+_c_int = ctypes.c_int
+_c_vp = ctypes.c_void_p
+
+# name -> (restype, argtypes).  Must list every symbol declared in include/mpformer_b200.h;
+# tests/test_abi.py parses the header and checks this table and the .so against it.
+_MSDA_FWD = [_c_vp] * 5 + [_c_int] * 7 + [_c_vp, _c_vp]
+_MSDA_FWD_EX = [_c_vp] * 5 + [_c_int] * 7 + [_c_vp, _c_vp, _c_vp]
+_MSDA_BWD = [_c_vp] * 6 + [_c_int] * 7 + [_c_vp] * 3 + [_c_vp]
+_MSDA_BWD_EX = [_c_vp] * 6 + [_c_int] * 7 + [_c_vp] * 3 + [_c_vp, _c_vp]
+
+SIGNATURES = {
+    "mpf_abi_version": (_c_int, []),
+    "mpf_last_error": (ctypes.c_char_p, []),
+    "mpf_launch_count": (ctypes.c_uint64, []),
+    "mpf_msda_forward_f32": (_c_int, _MSDA_FWD),
+    "mpf_msda_forward_f32_ex": (_c_int, _MSDA_FWD_EX),
+    "mpf_msda_forward_f64": (_c_int, _MSDA_FWD),
+    "mpf_msda_backward_f32": (_c_int, _MSDA_BWD),
+    "mpf_msda_backward_f32_ex": (_c_int, _MSDA_BWD_EX),
+    "mpf_msda_backward_f64": (_c_int, _MSDA_BWD),
+}
+
+_lib = None
+
+
+def load():
+    """Loads (once) and returns the ctypes handle; raises RuntimeError when the .so is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"mp_former_b200: native library not found at {LIB_PATH}. Build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). "
+            "There is no CPU / PyTorch fallback for this path."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError => stale .so; let it surface
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().mpf_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"mp_former_b200.{what} failed (code {rc}): {msg}")
+
+
+def launch_count():
+    return int(load().mpf_launch_count())
+
+
+def require_cuda(t, name):
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"mp_former_b200: `{name}` must be a CUDA tensor (got {t.device}); this path has no "
+            "CPU implementation (the reference op has none either: "
+            "ops/src/cpu/ms_deform_attn_cpu.cpp:22-45)")

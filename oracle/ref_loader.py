@@ -1,0 +1,197 @@
+"""TEST INFRASTRUCTURE ONLY -- never imported by the product path.
+
+Imports the UNMODIFIED reference modules of the hot path straight from
+``/root/reference`` so that golden vectors can be generated from the reference's own code
+(see ``tests/golden/make_golden.py``).  ``/root/reference`` exists only in the authoring
+container, never on the GPU box, so nothing that runs there may call :func:`load_reference`.
+
+Third-party packages the reference imports but that are absent here (detectron2, fvcore and the
+compiled ``MultiScaleDeformableAttention`` extension) are replaced by minimal stand-ins that keep
+the arithmetic identical:
+
+* ``detectron2.config.configurable``      -> identity decorator (we pass explicit kwargs)
+* ``detectron2.layers.Conv2d``            -> ``nn.Conv2d`` + optional ``norm`` / ``activation``
+  (same order as detectron2: conv -> norm -> activation)
+* ``detectron2.layers.get_norm("GN", c)`` -> ``nn.GroupNorm(32, c)``
+* ``fvcore.nn.weight_init.c2_xavier_fill``-> kaiming_uniform_(a=1), zero bias (init only; the
+  goldens overwrite every parameter with seeded values anyway)
+* ``MultiScaleDeformableAttention``       -> empty module; ``MSDeformAttn.forward`` then takes its
+  own ``except:`` branch into ``ms_deform_attn_core_pytorch``
+  (reference ``ops/modules/ms_deform_attn.py:116-121``), i.e. the reference's CPU path.
+"""
+import importlib
+import os
+import sys
+import types
+
+import torch
+from torch import nn
+
+REFERENCE_ROOT = os.environ.get("MPF_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "mask2former", "modeling"))
+
+
+class _Registry(dict):
+    def __init__(self, name="registry"):
+        super().__init__()
+        self._name = name
+
+    def register(self, obj=None):
+        if obj is None:
+            def deco(o):
+                self[o.__name__] = o
+                return o
+            return deco
+        self[obj.__name__] = obj
+        return obj
+
+    def get(self, name):
+        return self[name]
+
+
+class _Conv2d(nn.Conv2d):
+    """detectron2.layers.Conv2d stand-in: conv -> norm -> activation."""
+
+    def __init__(self, *args, **kwargs):
+        norm = kwargs.pop("norm", None)
+        activation = kwargs.pop("activation", None)
+        super().__init__(*args, **kwargs)
+        self.norm = norm
+        self.activation = activation
+
+    def forward(self, x):
+        x = super().forward(x)
+        if self.norm is not None:
+            x = self.norm(x)
+        if self.activation is not None:
+            x = self.activation(x)
+        return x
+
+
+class _ShapeSpec:
+    def __init__(self, channels=None, height=None, width=None, stride=None):
+        self.channels, self.height, self.width, self.stride = channels, height, width, stride
+
+
+def _get_norm(norm, out_channels):
+    if norm is None or norm == "":
+        return None
+    if callable(norm) and not isinstance(norm, str):
+        return norm(out_channels)
+    if norm == "GN":
+        return nn.GroupNorm(32, out_channels)
+    raise ValueError(f"stub get_norm: unsupported norm {norm!r}")
+
+
+def _configurable(init_func=None, *, from_config=None):
+    if init_func is not None:
+        return init_func
+
+    def deco(f):
+        return f
+    return deco
+
+
+def _c2_xavier_fill(module):
+    nn.init.kaiming_uniform_(module.weight, a=1)
+    if module.bias is not None:
+        nn.init.constant_(module.bias, 0)
+
+
+def _mod(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+def _pkg(name, path):
+    m = types.ModuleType(name)
+    m.__path__ = [path]
+    sys.modules[name] = m
+    return m
+
+
+_LOADED = None
+
+
+def load_reference():
+    """Returns a namespace with the reference's own classes/functions for the hot path."""
+    global _LOADED
+    if _LOADED is not None:
+        return _LOADED
+    if not reference_available():
+        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+
+    # ---- third-party stand-ins -------------------------------------------------------------
+    _mod("detectron2")
+    _mod("detectron2.config", configurable=_configurable)
+    _mod("detectron2.layers", Conv2d=_Conv2d, ShapeSpec=_ShapeSpec, get_norm=_get_norm)
+    _mod("detectron2.modeling", SEM_SEG_HEADS_REGISTRY=_Registry("SEM_SEG_HEADS"))
+    _mod("detectron2.utils")
+    _mod("detectron2.utils.registry", Registry=_Registry)
+    _mod("fvcore")
+    wi = _mod("fvcore.nn.weight_init", c2_xavier_fill=_c2_xavier_fill)
+    _mod("fvcore.nn", weight_init=wi)
+    _mod("MultiScaleDeformableAttention")  # empty: reference falls to its CPU path
+
+    # ---- package shells so mask2former/__init__.py (data, D2 engine) is NOT executed -------
+    base = os.path.join(REFERENCE_ROOT, "mask2former")
+    _pkg("mask2former", base)
+    _pkg("mask2former.modeling", os.path.join(base, "modeling"))
+    _pkg("mask2former.modeling.pixel_decoder", os.path.join(base, "modeling", "pixel_decoder"))
+    _pkg("mask2former.modeling.transformer_decoder",
+         os.path.join(base, "modeling", "transformer_decoder"))
+
+    ns = types.SimpleNamespace()
+    func = importlib.import_module(
+        "mask2former.modeling.pixel_decoder.ops.functions.ms_deform_attn_func")
+    ns.ms_deform_attn_core_pytorch = func.ms_deform_attn_core_pytorch
+    mods = importlib.import_module("mask2former.modeling.pixel_decoder.ops.modules.ms_deform_attn")
+    ns.MSDeformAttn = mods.MSDeformAttn
+    pd = importlib.import_module("mask2former.modeling.pixel_decoder.msdeformattn")
+    ns.MSDeformAttnPixelDecoder = pd.MSDeformAttnPixelDecoder
+    ns.MSDeformAttnTransformerEncoderOnly = pd.MSDeformAttnTransformerEncoderOnly
+    pe = importlib.import_module("mask2former.modeling.transformer_decoder.position_encoding")
+    ns.PositionEmbeddingSine = pe.PositionEmbeddingSine
+    td = importlib.import_module(
+        "mask2former.modeling.transformer_decoder.mask2former_transformer_decoder")
+    ns.MultiScaleMaskedTransformerDecoder = td.MultiScaleMaskedTransformerDecoder
+    ns.MultiScaleMaskedTransformerDecoderMaskDN = td.MultiScaleMaskedTransformerDecoderMaskDN
+    ns.CrossAttentionLayer = td.CrossAttentionLayer
+    ns.SelfAttentionLayer = td.SelfAttentionLayer
+    ns.FFNLayer = td.FFNLayer
+    ns.MLP = td.MLP
+    ns.ShapeSpec = _ShapeSpec
+    _LOADED = ns
+    return ns
+
+
+class cuda_is_identity:
+    """Context manager: the reference's DN preparation hard-codes ``.cuda()`` / ``.to('cuda')``
+    (reference mask2former_transformer_decoder.py:984-985,1029,1052).  To run it on CPU for golden
+    generation we make those calls no-ops.  Test-only monkeypatch."""
+
+    def __enter__(self):
+        self._cuda = torch.Tensor.cuda
+        self._to = torch.Tensor.to
+        torch.Tensor.cuda = lambda t, *a, **k: t
+        orig_to = self._to
+
+        def _to(t, *a, **k):
+            a = tuple(x for x in a if not (isinstance(x, str) and x.startswith("cuda")))
+            if isinstance(k.get("device"), str) and k["device"].startswith("cuda"):
+                k.pop("device")
+            if not a and not k:
+                return t
+            return orig_to(t, *a, **k)
+        torch.Tensor.to = _to
+        return self
+
+    def __exit__(self, *exc):
+        torch.Tensor.cuda = self._cuda
+        torch.Tensor.to = self._to
+        return False
