@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- img/s (forward+backward) of the MP-Former hot path on N B200s, one JSON line.
+
+A "step" is one forward+backward pass of the hot path (MSDeformAttn pixel decoder + masked-attention
+transformer decoder, MP-Former COCO-instance R50 head, DN/mask-piloted queries on) over one batch of
+synthetic 1024x1024 backbone features.  The backbone (upstream of the path) and the criterion
+(downstream) are outside the path: inputs are R50-shaped feature maps, the loss is a
+fixed linear functional of every prediction the head returns.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]           our arm
+  python bench.py --impl reference [...]                          CPU port of the reference path
+  torchrun --nproc-per-node N bench.py --gpus N ...               one rank per GPU (weak scaling)
+
+Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "images/sec fwd+bwd, MP-Former R50 head (MSDeformAttn pixel decoder + masked decoder), 1024x1024"
+UNIT = "img/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="images per GPU (weak scaling)")
+    ap.add_argument("--height", type=int, default=1024)
+    ap.add_argument("--width", type=int, default=1024)
+    ap.add_argument("--queries", type=int, default=100)
+    ap.add_argument("--no-dn", action="store_true", help="drop the mask-piloted (DN) query group")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"R50 feature maps {a.height}x{a.width} -> MSDeformAttnPixelDecoder(6 layers) + "
+            f"MultiScaleMaskedTransformerDecoderMaskDN(9 layers, {a.queries} queries, "
+            f"{'DN points' if not a.no_dn else 'no DN'}), fwd+bwd, linear pseudo-loss")
+
+
+def pseudo_loss(out):
+    terms = [out["pred_masks"].float().mean(), out["pred_logits"].float().mean()]
+    for a in out["aux_outputs"]:
+        terms += [a["pred_masks"].float().mean(), a["pred_logits"].float().mean()]
+    dn = out.get("dn_out")
+    if dn is not None:
+        terms += [dn["pred_masks"].float().mean(), dn["pred_logits"].float().mean()]
+        for a in dn["aux_outputs"]:
+            terms += [a["pred_masks"].float().mean(), a["pred_logits"].float().mean()]
+    return sum(terms)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's CPU path on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_port_step_fn(a):
+    """Returns (fn, sample_description): fn() runs ONE image fwd+bwd through the CPU oracle."""
+    import torch
+    from mp_former_b200 import workload
+    from oracle import torch_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    pd, dec = workload.build_head(num_queries=a.queries, device="cpu")
+    psd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in pd.state_dict().items()}
+    dsd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in dec.state_dict().items()}
+    feats = workload.synthetic_features(1, a.height, a.width)
+    dn = None if a.no_dn else {"tgt": workload.synthetic_targets(1, a.height, a.width), "scalar": 1,
+                               "noise_scale": 0.0}
+
+    def fn():
+        mf, _, ms = O.pixel_decoder_forward(psd, feats)
+        out = O.decoder_forward(dsd, ms, mf, num_queries=a.queries, dn_args=dn, dn_label_noise_ratio=0.2)
+        loss = pseudo_loss(out)
+        loss.backward()
+        for sd in (psd, dsd):
+            for v in sd.values():
+                v.grad = None
+        return float(loss)
+
+    return fn, "1 image (same shapes/config) fwd+bwd per step through oracle/torch_oracle.py on host cores"
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    fn, sample = cpu_port_step_fn(a)
+    for _ in range(min(a.warmup, 1)):
+        fn()
+    steps = a.steps
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        fn()
+        done += 1
+        if time.perf_counter() - t0 > 240:      # keep the whole arm within minutes
+            break
+    dt = time.perf_counter() - t0
+    v = done / dt
+    cores = os.cpu_count() or 1
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus,
+        "steps": done, "warmup": min(a.warmup, 1), "ms_per_step": dt / done * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "images_per_step": 1},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index, path):
+        self.path, self.proc, self.idx = path, None, gpu_index
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s in sm if s > 0.5 * max(sm)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    import mp_former_b200 as M
+    from mp_former_b200 import MultiScaleDeformableAttention as MSDA
+    from mp_former_b200 import _lib, workload
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (our arm) needs a GPU; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cuda.matmul.allow_tf32 = False          # fp32 path, like the reference's pixel decoder
+    torch.backends.cudnn.allow_tf32 = False
+
+    B = a.batch
+    pd, dec = workload.build_head(num_queries=a.queries, device=dev, seed=0)
+
+    class Head(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.pixel_decoder, self.predictor = pd, dec
+
+        def forward(self, feats, dn_args):
+            mf, _, ms = self.pixel_decoder.forward_features(feats)
+            return self.predictor(ms, mf, None, dn_args)
+
+    head = Head()
+    model = head
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(head, device_ids=[local], gradient_as_bucket_view=True)
+    params = [p for p in head.parameters()]
+    feats = workload.synthetic_features(B, a.height, a.width, seed=rank, device=dev)
+    dn_args = None
+    if not a.no_dn:
+        dn_args = {"tgt": workload.synthetic_targets(B, a.height, a.width, seed=rank, device=dev),
+                   "scalar": 1, "noise_scale": 0.0}
+
+    def step(f):
+        for p in params:
+            p.grad = None
+        out = model(f, dn_args)
+        loss = pseudo_loss(out)
+        loss.backward()
+        return loss
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        step(feats)
+    sync()
+
+    # ---- timed region: device-resident inputs ------------------------------------------------
+    sampler = ClockSampler(local, os.path.join(ROOT, "gpurun_out", f"clocks_rank{rank}.csv")) if rank == 0 else None
+    if sampler:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        sampler.start()
+    MSDA.profile_begin()
+    l0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    ev0.record()
+    for _ in range(a.steps):
+        step(feats)
+    ev1.record()
+    sync()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = _lib.launch_count() - l0
+    prof = MSDA.profile_end()
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = B * world * a.steps / (ms_total / 1e3)
+
+    # ---- e2e: host (pinned) inputs, H2D inside the timed region, loss read back ---------------
+    e2e = None
+    if not a.no_e2e:
+        host = workload.synthetic_features(B, a.height, a.width, seed=rank, device="cpu", pin=True)
+        h2d = sum(t_.numel() * t_.element_size() for t_ in host.values())
+
+        def e2e_step():
+            f = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+            return float(step(f).item())
+        e2e_step()
+        sync()
+        n_e2e = max(3, min(a.steps, 10))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_e2e):
+            e2e_step()
+        e1.record()
+        sync()
+        te = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": B * world * n_e2e / (float(te.item()) / 1e3), "unit": UNIT,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": n_e2e}
+
+    if rank == 0:
+        peaks = {}
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk):
+            peaks = json.load(open(pk))
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        # MSDeformAttn forward: algorithmic bytes per launch:
+        #   4 * (S*M*D + 2*Lq*M*L*P + Lq*M*L*P + Lq*M*D) per image
+        S = sum((a.height // s) * (a.width // s) for s in (32, 16, 8))
+        Mh, D, L, P = 8, 32, 3, 4
+        alg = 4 * (S * Mh * D + 2 * S * Mh * L * P + S * Mh * L * P + S * Mh * D) * B
+        fwd_ms = statistics.mean(prof["fwd_ms"]) if prof["fwd_ms"] else None
+        bwd_ms = statistics.mean(prof["bwd_ms"]) if prof["bwd_ms"] else None
+        roof = None
+        if fwd_ms:
+            ach = alg / (fwd_ms / 1e3) / 1e9
+            roof = {"kernel": "msda_fwd_vec_kernel<8>", "bound": "hbm", "achieved": ach, "peak": hbm,
+                    "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                    "algorithmic_bytes_per_launch": alg, "avg_launch_ms": fwd_ms,
+                    "launches_timed": len(prof["fwd_ms"]),
+                    "share_of_step": fwd_ms * len(prof["fwd_ms"]) / ms_total}
+            if bwd_ms:
+                alg_b = (4 * (S * Mh * D * 2 + 3 * S * Mh * L * P) + 4 * (S * Mh * D + 3 * S * Mh * L * P)) * B
+                roof["backward"] = {"kernel": "msda_bwd_vec_kernel<8>", "avg_launch_ms": bwd_ms,
+                                    "achieved": alg_b / (bwd_ms / 1e3) / 1e9,
+                                    "frac": alg_b / (bwd_ms / 1e3) / 1e9 / hbm,
+                                    "algorithmic_bytes_per_launch": alg_b,
+                                    "share_of_step": bwd_ms * len(prof["bwd_ms"]) / ms_total}
+        cpu = None
+        if not a.no_cpu_baseline and world == 1:
+            fn, sample = cpu_port_step_fn(a)
+            fn()
+            t0 = time.perf_counter()
+            n = 0
+            while n < 2 and time.perf_counter() - t0 < 60:
+                fn(); n += 1
+            dt = time.perf_counter() - t0
+            cpu = {"value": n / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                   "sample": sample + f" ({n} steps, {dt:.1f}s)"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": max(a.warmup, 3), "ms_per_step": ms_total / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "images_per_gpu": B, "global_batch": B * world,
+                       "parallelism": f"dp{world}" if world > 1 else "single",
+                       "l2": "inputs+activations per step (>2 GB) exceed the 126 MB L2; no explicit flush",
+                       "native_ops": sorted(M.ops.NATIVE_OPS), "tf32": False},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)

@@ -22,6 +22,41 @@ from . import _lib
 
 _FLOATS = (torch.float32, torch.float64)
 
+# Optional per-launch device timing (bench.py's roofline leg): CUDA events recorded on the launching
+# stream right around the C-ABI call.  Off by default.
+_PROFILE = None
+
+
+def profile_begin():
+    global _PROFILE
+    _PROFILE = {"fwd": [], "bwd": []}
+
+
+def profile_end():
+    """Returns {"fwd_ms": [...], "bwd_ms": [...]} and switches profiling off (synchronises)."""
+    global _PROFILE
+    p, _PROFILE = _PROFILE, None
+    torch.cuda.synchronize()
+    return {k + "_ms": [a.elapsed_time(b) for a, b in v] for k, v in (p or {"fwd": [], "bwd": []}).items()}
+
+
+class _Timed:
+    def __init__(self, kind):
+        self.kind = kind
+
+    def __enter__(self):
+        if _PROFILE is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _PROFILE is not None:
+            self.b.record()
+            _PROFILE[self.kind].append((self.a, self.b))
+        return False
+
 
 def _host_shapes_array(spatial_shapes, host_shapes):
     import ctypes
@@ -71,7 +106,7 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     B, S, M, D, L, Lq, P = _dims(value, spatial_shapes, sampling_loc, attn_weight, im2col_step)
     lib = _lib.load()
     out = torch.empty((B, Lq, M * D), dtype=value.dtype, device=value.device)
-    with torch.cuda.device(value.device):
+    with torch.cuda.device(value.device), _Timed("fwd"):
         stream = torch.cuda.current_stream().cuda_stream
         if value.dtype == torch.float32:
             hs = _host_shapes_array(spatial_shapes, host_shapes)
@@ -102,7 +137,7 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     grad_value = torch.empty_like(value)
     grad_loc = torch.empty_like(sampling_loc)
     grad_aw = torch.empty_like(attn_weight)
-    with torch.cuda.device(value.device):
+    with torch.cuda.device(value.device), _Timed("bwd"):
         stream = torch.cuda.current_stream().cuda_stream
         if value.dtype == torch.float32:
             hs = _host_shapes_array(spatial_shapes, host_shapes)

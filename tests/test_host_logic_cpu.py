@@ -1,0 +1,124 @@
+"""CPU checks of the host-side module logic (wiring, layouts, DN preparation, state-dict keys).
+
+The product has no CPU path.  To exercise the Python modules without a GPU, THIS TEST swaps the
+native MSDeformAttn op for the oracle and disables the CUDA-tensor guard -- a test-only monkeypatch;
+the kernels themselves are validated by the ``-m gpu`` tests on the B200 box."""
+import os
+
+import pytest
+import torch
+
+import cases
+import mp_former_b200 as M
+from mp_former_b200 import MultiScaleDeformableAttention as MSDA
+from mp_former_b200 import _lib
+from oracle import torch_oracle as O
+from test_oracle_vs_golden import (_cmp_out, close, decoder_template, load, pixel_decoder_template)
+
+
+@pytest.fixture()
+def cpu_ops(monkeypatch):
+    def fwd(value, shapes, lsi, loc, aw, step, host_shapes=None):
+        return O.msda_core(value, shapes, loc, aw)
+    monkeypatch.setattr(MSDA, "ms_deform_attn_forward", fwd)
+    monkeypatch.setattr(_lib, "require_cuda", lambda t, n: None)
+
+
+def build_pixel_decoder():
+    c = cases.PD_CFG
+    shape = {k: M.ShapeSpec(channels=c["channels"][k], stride=c["strides"][k]) for k in c["channels"]}
+    return M.MSDeformAttnPixelDecoder(
+        shape, transformer_dropout=0.0, transformer_nheads=c["nheads"],
+        transformer_dim_feedforward=c["dim_feedforward"], transformer_enc_layers=c["enc_layers"],
+        conv_dim=c["conv_dim"], mask_dim=c["mask_dim"], norm="GN",
+        transformer_in_features=["res3", "res4", "res5"], common_stride=4).eval()
+
+
+def build_decoder(cls=None, **kw):
+    d = cases.DEC_CFG
+    cls = cls or M.MultiScaleMaskedTransformerDecoderMaskDN
+    extra = dict(dn_mode="points", all_lys=True, dn_label_noise_ratio=-1.0) \
+        if cls is M.MultiScaleMaskedTransformerDecoderMaskDN else {}
+    extra.update(kw)
+    return cls(d["hidden_dim"], True, num_classes=d["num_classes"], hidden_dim=d["hidden_dim"],
+               num_queries=d["num_queries"], nheads=d["nheads"], dim_feedforward=d["dim_feedforward"],
+               dec_layers=d["dec_layers"], pre_norm=False, mask_dim=d["mask_dim"],
+               enforce_input_project=False, **extra).eval()
+
+
+def test_pixel_decoder_module_matches_reference_golden(golden_dir, cpu_ops):
+    G = load(golden_dir, "pixel_decoder.pt")
+    pd = build_pixel_decoder()
+    assert sorted(pd.state_dict().keys()) == G["keys"]
+    pd.load_state_dict(O.seeded_state_dict(pixel_decoder_template(), seed=41))
+    with torch.no_grad():
+        mf, enc0, ms = pd.forward_features(cases.pixel_decoder_features())
+    close(mf, G["mask_features"], 5e-5)
+    close(enc0, G["enc0"], 5e-5)
+    assert len(ms) == 3
+    for a, b in zip(ms, G["multi_scale"]):
+        close(a, b, 5e-5)
+
+
+@pytest.mark.parametrize("mode", ["plain", "dn", "dn2", "base"])
+def test_decoder_module_matches_reference_golden(golden_dir, cpu_ops, mode):
+    G = load(golden_dir, "decoder.pt")
+    sd = O.seeded_state_dict(decoder_template(), seed=51)
+    if mode == "base":
+        dec = build_decoder(M.MultiScaleMaskedTransformerDecoder)
+        sd = {k: v for k, v in sd.items() if not k.startswith("label_enc")}
+    else:
+        dec = build_decoder()
+        assert sorted(dec.state_dict().keys()) == G["keys"]
+    dec.load_state_dict(sd)
+    x, mf = cases.decoder_inputs()
+    dn_args = None
+    if mode in ("dn", "dn2"):
+        dn_args = {"tgt": cases.dn_targets(), "scalar": 1 if mode == "dn" else 2, "noise_scale": 0.0}
+    with torch.no_grad():
+        o = dec(x, mf, None, dn_args)
+    _cmp_out(o, G[mode], 5e-5)
+    if dn_args is not None:
+        assert o["dn_out"]["dn_args"] == G[mode]["dn"]["dn_args"]
+        _cmp_out(o["dn_out"], G[mode]["dn"], 5e-5)
+    else:
+        assert o["dn_out"] is None
+
+
+def test_dn_label_noise_and_empty_targets(cpu_ops):
+    dec = build_decoder(dn_label_noise_ratio=0.2)
+    x, mf = cases.decoder_inputs()
+    torch.manual_seed(0)
+    o = dec(x, mf, None, {"tgt": cases.dn_targets(), "scalar": 1, "noise_scale": 0.4})
+    assert o["dn_out"]["pred_masks"].shape[1] == 3
+    assert torch.isfinite(o["pred_masks"]).all() and torch.isfinite(o["dn_out"]["pred_masks"]).all()
+    empty = [{"labels": torch.zeros(0, dtype=torch.long), "masks": torch.zeros(0, 64, 64, dtype=torch.bool),
+              "boxes": torch.zeros(0, 4)} for _ in range(2)]
+    o = dec(x, mf, None, {"tgt": empty, "scalar": 1, "noise_scale": 0.0})
+    assert o["dn_out"] is None
+
+
+def test_static_query_checkpoint_migration():
+    dec = build_decoder()
+    sd = dec.state_dict()
+    old = {k.replace("query_feat", "static_query"): v for k, v in sd.items()}
+    dec2 = build_decoder()
+    meta = getattr(old, "_metadata", None)
+    dec2.load_state_dict(old)          # version-less checkpoint: static_query -> query_feat
+    assert torch.equal(dec2.query_feat.weight, dec.query_feat.weight)
+
+
+def test_cpu_tensors_are_rejected_loudly():
+    value, shapes, loc, aw = cases.msda_inputs("testpy")
+    st = torch.as_tensor(shapes, dtype=torch.long)
+    lsi = torch.tensor([0, 24])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        MSDA.ms_deform_attn_forward(value, st, lsi, loc, aw, 2)
+    with pytest.raises(RuntimeError, match="contiguous"):
+        MSDA.ms_deform_attn_forward(value.transpose(2, 3), st, lsi, loc, aw, 2)
+
+
+def test_registries_hold_reference_names():
+    assert "MSDeformAttnPixelDecoder" in M.SEM_SEG_HEADS_REGISTRY
+    assert "MultiScaleMaskedTransformerDecoder" in M.TRANSFORMER_DECODER_REGISTRY
+    assert "MultiScaleMaskedTransformerDecoderMaskDN" in M.TRANSFORMER_DECODER_REGISTRY
