@@ -106,6 +106,24 @@ int mpf_msda_backward_f64(const double* grad_out, const double* value,
                           int num_query, int num_point, double* grad_value,
                           double* grad_sampling_loc, double* grad_attn_weight, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * fp32-accurate tensor-core GEMM ("3xTF32", tcgen05 + TMA):
+ *   C[b] = A[b] * B[b]^T (+ bias[N]) (ReLU optional), A [batch,M,K], B [batch,N,K], K contiguous.
+ * B (the small operand: an nn.Linear weight [out,in] or the per-query mask embedding) is passed
+ * pre-split by mpf_split_tf32 (hi = rn_tf32(x), lo = rn_tf32(x - hi)).
+ * transpose_c == 0: C[b][m*ldc + n];  transpose_c != 0: C[b][n*ldc + m].
+ * Replaces the library calls at: ref decoder :1865 (einsum "bqc,bchw->bqhw" with mask_features kept
+ * channels-last: M = H*W, N = Q, K = C, transposed store), ref decoder :105-108 (K/V/Q in-projections
+ * of nn.MultiheadAttention), ref ops/modules/ms_deform_attn.py:98,102-103,124 and
+ * pixel_decoder/msdeformattn.py:116-120 (Linear layers of the encoder).
+ * Requirements: K % 32 == 0; A/B 16-byte aligned, lda/ldb/batch strides multiples of 4 elements.
+ * ------------------------------------------------------------------------------------------- */
+int mpf_split_tf32(const float* x, float* hi, float* lo, long long n, void* stream);
+int mpf_gemm_tf32x3(const float* A, long long lda, long long a_batch_stride, const float* B_hi,
+                    const float* B_lo, long long ldb, long long b_batch_stride, const float* bias,
+                    float* C, long long ldc, long long c_batch_stride, int batch, int M, int N, int K,
+                    int relu, int transpose_c, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,6 +29,10 @@ SIGNATURES = {
     "mpf_msda_backward_f32": (_c_int, _MSDA_BWD),
     "mpf_msda_backward_f32_ex": (_c_int, _MSDA_BWD_EX),
     "mpf_msda_backward_f64": (_c_int, _MSDA_BWD),
+    "mpf_split_tf32": (_c_int, [_c_vp, _c_vp, _c_vp, ctypes.c_longlong, _c_vp]),
+    "mpf_gemm_tf32x3": (_c_int, [_c_vp, ctypes.c_longlong, ctypes.c_longlong, _c_vp, _c_vp,
+                                 ctypes.c_longlong, ctypes.c_longlong, _c_vp, _c_vp, ctypes.c_longlong,
+                                 ctypes.c_longlong, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp]),
 }
 
 _lib = None

@@ -1,0 +1,392 @@
+// C[b] = A[b] * B[b]^T (+ bias) with fp32-accurate "3xTF32" arithmetic on the 5th-gen tensor cores.
+//
+//   A : [batch, M, K] fp32, K contiguous (activations / pixel features, channels-last)
+//   B : [batch, N, K] fp32, K contiguous (nn.Linear weight [out,in], or the per-query mask embedding)
+//       supplied PRE-SPLIT as B_hi, B_lo (mpf_split_tf32) because it is small and reused by every CTA
+//   C : row-major [batch, M, ldc] or transposed [batch, N, ldc_t] (used for the mask logits
+//       out[b,q,hw] = sum_c E[b,q,c] * F[b,hw,c], ref decoder :1865)
+//
+// Why 3xTF32: the path's contract is fp32 parity (1e-3) with the reference's fp32 cuBLAS results; a
+// single TF32 pass (10-bit mantissa) gives ~5e-3 absolute error at K = 256.  Each operand is written
+// as x = hi + lo with hi = rn_tf32(x), lo = rn_tf32(x - hi) (both exactly representable in TF32), and
+// D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi accumulates in fp32 in TMEM; the dropped lo*lo term is
+// ~2^-22 relative.
+//
+// Structure (one CTA per SM, persistent over output tiles, warp-specialised):
+//   warp 0      TMA producer: A tile (fp32), B_hi, B_lo tiles, SWIZZLE_128B, mbarrier complete_tx
+//   warps 8-11  splitters: rewrite the landed A tile in place as A_hi and write A_lo next to it
+//               (same swizzled positions), fence.proxy.async, arrive
+//   warp 1      MMA issuer: 3 x tcgen05.mma.kind::tf32 per 8-wide K step, accumulators in TMEM
+//               (double-buffered across tiles), tcgen05.commit frees the smem stage
+//   warps 4-7   epilogue: tcgen05.ld TMEM -> registers -> bias / ReLU -> global (row-major or
+//               transposed), overlapped with the next tile's main loop
+#include "mpf_common.cuh"
+#include "sm100_ptx.cuh"
+
+#include <mutex>
+
+namespace mpf {
+
+using namespace ptx;
+
+constexpr int kBM = 128;
+constexpr int kBK = 32;                       // 32 fp32 = 128 B = one swizzle row
+constexpr int kUmmaK = 8;                     // tf32: 32 bytes per MMA K step
+constexpr int kABytes = kBM * kBK * 4;        // 16 KiB
+constexpr int kGemmThreads = 384;
+
+struct GemmArgs {
+  float* C;
+  const float* bias;                          // [N] or null
+  long long c_batch_stride;                   // elements
+  long long ldc;                              // row stride of C (row-major: of M rows; transposed: of N rows)
+  int batch, M, N, K;
+  int tiles_m, tiles_n;
+  int relu;
+  int transpose_c;
+  int vec_store;                              // row-major float4 stores are legal
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kBBytes = BN * kBK * 4;
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kStages = (BN == 256) ? 2 : (BN == 128 ? 3 : 4);
+  static constexpr int kBarrierBytes = 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarrierBytes + 1024;  // + alignment slack
+  static constexpr int kTmemCols = 2 * BN;     // power of two >= 32 for BN in {64,128,256}
+};
+
+__device__ __forceinline__ float rn_tf32(float x) {
+  // round-to-nearest (ties away) to a 10-bit mantissa; result has its 13 low bits clear
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+                   const __grid_constant__ CUtensorMap tmBlo, const GemmArgs g) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+  uint64_t* full = bars;               // [S] TMA bytes landed
+  uint64_t* split = bars + S;          // [S] A_hi / A_lo written
+  uint64_t* empty = bars + 2 * S;      // [S] MMAs reading the stage retired
+  uint64_t* tfull = bars + 3 * S;      // [2] accumulator complete
+  uint64_t* tempty = bars + 3 * S + 2; // [2] accumulator drained by the epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmBhi);
+    prefetch_tmap(&tmBlo);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&split[s], 4);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = g.batch * g.tiles_m * g.tiles_n;
+  const int kblocks = g.K / kBK;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_t = tile % g.tiles_n;
+        const int rest = tile / g.tiles_n;
+        const int m_t = rest % g.tiles_m;
+        const int b = rest / g.tiles_m;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* st = smem + stage * Cfg::kStageBytes;
+          mbar_arrive_expect_tx(&full[stage], kABytes + 2 * Cfg::kBBytes);
+          tma_load_3d(st, &tmA, &full[stage], kb * kBK, m_t * kBM, b);
+          tma_load_3d(st + 2 * kABytes, &tmBhi, &full[stage], kb * kBK, n_t * BN, b);
+          tma_load_3d(st + 2 * kABytes + Cfg::kBBytes, &tmBlo, &full[stage], kb * kBK, n_t * BN, b);
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_tf32(kBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          mbar_wait(&split[stage], phase);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t a_lo = a_hi + kABytes;
+          const uint32_t b_hi = a_hi + 2 * kABytes;
+          const uint32_t b_lo = b_hi + Cfg::kBBytes;
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            const uint32_t ko = k * kUmmaK * 4;      // bytes along K inside the 128-B swizzle row
+            const uint64_t dah = smem_desc_sw128_kmajor(a_hi + ko), dal = smem_desc_sw128_kmajor(a_lo + ko);
+            const uint64_t dbh = smem_desc_sw128_kmajor(b_hi + ko), dbl = smem_desc_sw128_kmajor(b_lo + ko);
+            mma_tf32_ss(d_tmem, dal, dbh, idesc, (kb | k) ? 1u : 0u);
+            mma_tf32_ss(d_tmem, dah, dbl, idesc, 1u);
+            mma_tf32_ss(d_tmem, dah, dbh, idesc, 1u);
+          }
+          mma_commit(&empty[stage]);
+          if (kb == kblocks - 1) mma_commit(&tfull[acc]);
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 8) {
+    // ================= splitters (128 threads) =================
+    const int st_id = threadIdx.x - 256;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(&full[stage], phase);
+        uint8_t* a = smem + stage * Cfg::kStageBytes;
+#pragma unroll
+        for (int i = 0; i < kABytes / 16 / 128; ++i) {
+          const int off = (st_id + i * 128) * 16;
+          const float4 x = *reinterpret_cast<const float4*>(a + off);
+          float4 hi, lo;
+          hi.x = rn_tf32(x.x); hi.y = rn_tf32(x.y); hi.z = rn_tf32(x.z); hi.w = rn_tf32(x.w);
+          lo.x = rn_tf32(x.x - hi.x); lo.y = rn_tf32(x.y - hi.y);
+          lo.z = rn_tf32(x.z - hi.z); lo.w = rn_tf32(x.w - hi.w);
+          *reinterpret_cast<float4*>(a + off) = hi;
+          *reinterpret_cast<float4*>(a + kABytes + off) = lo;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&split[stage]);
+        if (++stage == S) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue (warps 4..7 -> TMEM lane groups 0..3) =================
+    const int ew = warp - 4;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_t = tile % g.tiles_n;
+      const int rest = tile / g.tiles_n;
+      const int m_t = rest % g.tiles_m;
+      const int b = rest / g.tiles_m;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_t * kBM + ew * 32 + lane;
+      const bool row_ok = row < g.M;
+      float* cb = g.C + static_cast<long long>(b) * g.c_batch_stride;
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n0 = n_t * BN + c * 32;
+        if (n0 >= g.N) break;
+        uint32_t v[32];
+        tmem_ld_32x32(t_addr + c * 32, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(v[j]);
+          if (g.bias != nullptr && n0 + j < g.N) x += __ldg(g.bias + n0 + j);
+          if (g.relu) x = fmaxf(x, 0.f);
+          f[j] = x;
+        }
+        if (g.transpose_c) {
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < g.N) cb[static_cast<long long>(n0 + j) * g.ldc + row] = f[j];
+          }
+        } else if (row_ok) {
+          float* dst = cb + static_cast<long long>(row) * g.ldc + n0;
+          if (g.vec_store && n0 + 32 <= g.N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < g.N) dst[j] = f[j];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long long n) {
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * 256) {
+    const float v = x[i];
+    const float h = rn_tf32(v);
+    hi[i] = h;
+    lo[i] = rn_tf32(v - h);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeFn get_encode() {
+  static EncodeFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(p);
+  });
+  return fn;
+}
+
+// 3-D fp32 tensor [batch, rows, K] (K contiguous), box [1, box_rows, 32], 128-byte swizzle.
+static int make_tmap(CUtensorMap* m, const float* base, int K, long long rows, int batch, long long ld,
+                     long long batch_stride, int box_rows) {
+  EncodeFn enc = get_encode();
+  if (enc == nullptr) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return MPF_ERR_UNSUPPORTED;
+  }
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(batch)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 4, static_cast<cuuint64_t>(batch_stride) * 4};
+  if (batch == 1) strides[1] = static_cast<cuuint64_t>(rows) * static_cast<cuuint64_t>(ld) * 4;
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d) for base=%p K=%d rows=%lld batch=%d ld=%lld", (int)r,
+              (const void*)base, K, rows, batch, ld);
+    return MPF_ERR_BAD_ARG;
+  }
+  return MPF_OK;
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tbh, const CUtensorMap& tbl, GemmArgs g,
+                       cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    MPF_CUDA_OK(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::kSmemBytes));
+    configured = true;
+  }
+  g.tiles_m = (g.M + kBM - 1) / kBM;
+  g.tiles_n = (g.N + BN - 1) / BN;
+  const long long tiles = static_cast<long long>(g.batch) * g.tiles_m * g.tiles_n;
+  const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
+  gemm_tf32x3_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tbh, tbl, g);
+  count_launch();
+  return finish_launch("gemm_tf32x3");
+}
+
+}  // namespace mpf
+
+extern "C" {
+
+int mpf_split_tf32(const float* x, float* hi, float* lo, long long n, void* stream) {
+  mpf::clear_error();
+  MPF_REQUIRE(x && hi && lo && n > 0, "split_tf32: bad arguments");
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  mpf::split_tf32_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, hi, lo, n);
+  mpf::count_launch();
+  return mpf::finish_launch("split_tf32");
+}
+
+int mpf_gemm_tf32x3(const float* A, long long lda, long long a_batch_stride, const float* B_hi,
+                    const float* B_lo, long long ldb, long long b_batch_stride, const float* bias, float* C,
+                    long long ldc, long long c_batch_stride, int batch, int M, int N, int K, int relu,
+                    int transpose_c, void* stream) {
+  using namespace mpf;
+  clear_error();
+  MPF_REQUIRE(A && B_hi && B_lo && C, "gemm_tf32x3: null pointer argument");
+  MPF_REQUIRE(batch > 0 && M > 0 && N > 0 && K > 0, "gemm_tf32x3: dimensions must be positive");
+  MPF_REQUIRE(K % kBK == 0, "gemm_tf32x3: K (%d) must be a multiple of %d", K, kBK);
+  MPF_REQUIRE(lda % 4 == 0 && ldb % 4 == 0 && a_batch_stride % 4 == 0 && b_batch_stride % 4 == 0 &&
+                  aligned16(A) && aligned16(B_hi) && aligned16(B_lo),
+              "gemm_tf32x3: A / B must be 16-byte aligned with row strides that are multiples of 4 elements");
+  MPF_REQUIRE(lda >= K && ldb >= K, "gemm_tf32x3: row strides must be >= K");
+  int bn = 64;
+  if (N > 64) {
+    const int waste128 = (N + 127) / 128 * 128 - N, waste256 = (N + 255) / 256 * 256 - N;
+    bn = (N <= 128 || waste128 < waste256) ? 128 : 256;
+  }
+  CUtensorMap ta, tbh, tbl;
+  int rc = make_tmap(&ta, A, K, M, batch, lda, a_batch_stride, kBM);
+  if (rc) return rc;
+  rc = make_tmap(&tbh, B_hi, K, N, batch, ldb, b_batch_stride, bn);
+  if (rc) return rc;
+  rc = make_tmap(&tbl, B_lo, K, N, batch, ldb, b_batch_stride, bn);
+  if (rc) return rc;
+  GemmArgs g;
+  g.C = C; g.bias = bias; g.c_batch_stride = c_batch_stride; g.ldc = ldc;
+  g.batch = batch; g.M = M; g.N = N; g.K = K; g.tiles_m = g.tiles_n = 0;
+  g.relu = relu; g.transpose_c = transpose_c;
+  g.vec_store = (!transpose_c && ldc % 4 == 0 && c_batch_stride % 4 == 0 && aligned16(C)) ? 1 : 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (bn == 64) return launch_gemm<64>(ta, tbh, tbl, g, st);
+  if (bn == 128) return launch_gemm<128>(ta, tbh, tbl, g, st);
+  return launch_gemm<256>(ta, tbh, tbl, g, st);
+}
+
+}  // extern "C"

@@ -29,6 +29,21 @@ from .position_encoding import PositionEmbeddingSine
 from .registry import configurable, register_pixel_decoder
 
 
+class fp32_math:
+    """Context manager: cuDNN / cuBLAS library calls inside run in true fp32 (TF32 off)."""
+
+    def __enter__(self):
+        self._c = torch.backends.cudnn.allow_tf32
+        self._m = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+
+    def __exit__(self, *exc):
+        torch.backends.cudnn.allow_tf32 = self._c
+        torch.backends.cuda.matmul.allow_tf32 = self._m
+        return False
+
+
 class ShapeSpec:
     """Minimal stand-in for detectron2.layers.ShapeSpec (only .channels / .stride are read)."""
 
@@ -256,8 +271,9 @@ class MSDeformAttnPixelDecoder(nn.Module):
 
     def forward_features(self, features):
         """features: dict name -> [B, C_f, H_f, W_f].  Runs in fp32 regardless of autocast (the
-        reference disables autocast here, msdeformattn.py:314,320)."""
-        with torch.autocast(device_type="cuda", enabled=False):
+        reference disables autocast here, msdeformattn.py:314,320) and with TF32 off for the
+        remaining library convolutions / GEMMs, so results keep fp32 parity with the reference."""
+        with torch.autocast(device_type="cuda", enabled=False), fp32_math():
             return self._forward_features(features)
 
     def _forward_features(self, features):

@@ -1,0 +1,67 @@
+"""-m gpu: the tcgen05 3xTF32 GEMM vs an fp64 reference.  Tolerance: |err| <= 2e-5 * sum_k|a||b|-scale,
+i.e. far inside the path's 1e-3 fp32 contract (a single TF32 pass would fail it)."""
+import pytest
+import torch
+
+from mp_former_b200 import native
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def ref64(a, b, bias=None, relu=False):
+    y = a.double() @ b.double().transpose(-1, -2)
+    if bias is not None:
+        y = y + bias.double()
+    return y.relu() if relu else y
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 64, 256), (256, 128, 256), (1000, 100, 256),
+                                   (4096, 288, 256), (300, 1024, 256), (777, 256, 1024), (128, 2048, 256),
+                                   (65536, 100, 256)])
+def test_gemm_matches_fp64(M, N, K):
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    a = torch.randn(M, K, device=DEV, generator=g)
+    b = torch.randn(N, K, device=DEV, generator=g) / K ** 0.5
+    bias = torch.randn(N, device=DEV, generator=g)
+    bh, bl = native.split_tf32(b)
+    assert torch.equal((bh.double() + bl.double()).float(), b) or (bh + bl - b).abs().max() < 1e-6 * b.abs().max()
+    for relu in (False, True):
+        y = native.gemm_tf32x3(a, bh, bl, bias, relu=relu)
+        r = ref64(a, b, bias, relu)
+        err = (y.double() - r).abs().max().item()
+        assert err < 2e-5, (M, N, K, relu, err)
+    yt = native.gemm_tf32x3(a, bh, bl, None, transpose_c=True)
+    assert yt.shape == (N, M)
+    assert (yt.double().t() - ref64(a, b)).abs().max().item() < 2e-5
+
+
+def test_batched_transposed_mask_logit_shape():
+    """mask logits: out[b,q,hw] = sum_c E[b,q,c] F[b,hw,c] (ref decoder :1865), F channels-last."""
+    B, Q, C, H, W = 3, 100, 256, 64, 64
+    g = torch.Generator(device=DEV).manual_seed(1)
+    E = torch.randn(B, Q, C, device=DEV, generator=g)
+    F_ = torch.randn(B, C, H, W, device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    eh, el = native.split_tf32(E)
+    a = F_.permute(0, 2, 3, 1).reshape(B, H * W, C)
+    assert a.is_contiguous()
+    out = native.gemm_tf32x3(a, eh, el, None, transpose_c=True).view(B, Q, H, W)
+    ref = torch.einsum("bqc,bchw->bqhw", E.double(), F_.double())
+    assert (out.double() - ref).abs().max().item() < 5e-5
+    # a single-pass TF32 product of the same operands is >10x less accurate (why 3xTF32 is used)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    tf32 = torch.einsum("bqc,bchw->bqhw", E, F_)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    assert (tf32.double() - ref).abs().max().item() > 10 * (out.double() - ref).abs().max().item()
+
+
+def test_strided_a_and_bad_args():
+    g = torch.Generator(device=DEV).manual_seed(2)
+    big = torch.randn(512, 512, device=DEV, generator=g)
+    a = big[:, :256]                                   # row stride 512, K = 256
+    b = torch.randn(96, 256, device=DEV, generator=g)
+    bh, bl = native.split_tf32(b)
+    y = native.gemm_tf32x3(a, bh, bl)
+    assert (y.double() - ref64(a, b)).abs().max().item() < 1e-4
+    with pytest.raises(RuntimeError, match="multiple of 32"):
+        native.gemm_tf32x3(torch.randn(8, 48, device=DEV), *native.split_tf32(torch.randn(8, 48, device=DEV)))
