@@ -124,6 +124,52 @@ int mpf_gemm_tf32x3(const float* A, long long lda, long long a_batch_stride, con
                     float* C, long long ldc, long long c_batch_stride, int batch, int M, int N, int K,
                     int relu, int transpose_c, void* stream);
 
+/* Extended form of mpf_gemm_tf32x3:  x = (A*B^T + bias + resid) * alpha, optional ReLU.
+ *   resid : optional addend with row stride resid_ld; output row r uses resid row (r % resid_rows)
+ *           (resid_rows == 0: row r) and only columns < resid_cols receive it (0 = all).  Used to add the
+ *           batch-independent term pos*Wk^T + bk to the key projection (K = (memory+pos) Wk^T + bk,
+ *           ref decoder :105-107) without materialising memory+pos.
+ *   C_lo  : if non-NULL the result is emitted pre-split for a following 3xTF32 consumer:
+ *           C = rn_tf32(x), C_lo = rn_tf32(x - C)  (same layout as C). */
+int mpf_gemm_tf32x3_ex(const float* A, long long lda, long long a_batch_stride, const float* B_hi,
+                       const float* B_lo, long long ldb, long long b_batch_stride, const float* bias,
+                       float* C, float* C_lo, long long ldc, long long c_batch_stride, const float* resid,
+                       long long resid_ld, int resid_rows, int resid_cols, float alpha, int batch, int M,
+                       int N, int K, int relu, int transpose_c, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Boolean stage of the prediction heads, bit-packed:
+ *   bits[row][j] bit i = ( sigmoid( bilinear_resize(logits[row], (h,w), align_corners=False) )[32j+i] < 0.5 )
+ * ref: transformer_decoder/mask2former_transformer_decoder.py:1869-1875 (F.interpolate, sigmoid, < 0.5;
+ * the reference then repeats the map over the 8 heads -- here one bit serves all heads).
+ *   logits [rows, H, W] fp32 with row stride `row_stride` elements; bits [rows, words_per_row] uint32,
+ *   1 = masked; keys >= h*w (padding up to 32*words_per_row) are set to 1.
+ * mpf_pack_bool_bits packs an existing bool map (uint8 0/1, [rows, n]) the same way (used for the
+ * mask-piloted GT masks, ref decoder :986, :1038-1039).
+ * ------------------------------------------------------------------------------------------- */
+int mpf_attn_mask_bits_f32(const float* logits, long long row_stride, int rows, int H, int W, int h, int w,
+                           uint32_t* bits, int words_per_row, void* stream);
+int mpf_pack_bool_bits(const uint8_t* src, int rows, int n, uint32_t* bits, int words_per_row,
+                       void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused masked multi-head cross-attention, forward (tcgen05 + TMA, 3xTF32):
+ *   out[b,q,h*32:(h+1)*32] = softmax_k( Q_h[b,q,:] . K_h[b,k,:]  (+ -inf where masked) ) V_h[b,k,:]
+ * ref: decoder :100-112 (nn.MultiheadAttention(query, key=memory+pos, value=memory, attn_mask)),
+ *      decoder :1780 (rows whose keys are all masked attend everywhere -> row_open).
+ *   q_hi/q_lo  [B, Qt, heads*32]  query projection, pre-scaled by log2(e)/sqrt(32), pre-split
+ *   k_hi/k_lo  [B, HW, heads*32]  key projection, pre-split
+ *   vt_hi/vt_lo[B, heads*32, HW]  value projection TRANSPOSED, pre-split
+ *   mask_bits  [B, Qt, mask_words] (mask_words >= 2*ceil(HW/64)), 1 = masked
+ *   row_open   [B, Qt] uint8, 1 = ignore the mask for this row (may be NULL)
+ *   out        [B, Qt, heads*32];  lse2 [B, heads, Qt] = log2-sum-exp2 of the scaled scores (may be NULL)
+ * Requirements: head_dim == 32, HW % 4 == 0.
+ * ------------------------------------------------------------------------------------------- */
+int mpf_masked_xattn_fwd_f32(const float* q_hi, const float* q_lo, const float* k_hi, const float* k_lo,
+                             const float* vt_hi, const float* vt_lo, const uint32_t* mask_bits,
+                             const uint8_t* row_open, float* out, float* lse2, int B, int Qt, int HW,
+                             int heads, int head_dim, int mask_words, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

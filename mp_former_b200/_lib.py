@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libmpformer_b200.so")
 
 _c_int = ctypes.c_int
 _c_vp = ctypes.c_void_p
+_c_ll = ctypes.c_longlong
 
 # name -> (restype, argtypes).  Must list every symbol declared in include/mpformer_b200.h;
 # tests/test_abi.py parses the header and checks this table and the .so against it.
@@ -33,6 +34,12 @@ SIGNATURES = {
     "mpf_gemm_tf32x3": (_c_int, [_c_vp, ctypes.c_longlong, ctypes.c_longlong, _c_vp, _c_vp,
                                  ctypes.c_longlong, ctypes.c_longlong, _c_vp, _c_vp, ctypes.c_longlong,
                                  ctypes.c_longlong, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp]),
+    "mpf_gemm_tf32x3_ex": (_c_int, [_c_vp, _c_ll, _c_ll, _c_vp, _c_vp, _c_ll, _c_ll, _c_vp, _c_vp, _c_vp,
+                                    _c_ll, _c_ll, _c_vp, _c_ll, _c_int, _c_int, ctypes.c_float,
+                                    _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp]),
+    "mpf_attn_mask_bits_f32": (_c_int, [_c_vp, _c_ll] + [_c_int] * 5 + [_c_vp, _c_int, _c_vp]),
+    "mpf_pack_bool_bits": (_c_int, [_c_vp, _c_int, _c_int, _c_vp, _c_int, _c_vp]),
+    "mpf_masked_xattn_fwd_f32": (_c_int, [_c_vp] * 10 + [_c_int] * 6 + [_c_vp]),
 }
 
 _lib = None

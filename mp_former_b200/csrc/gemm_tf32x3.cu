@@ -22,6 +22,7 @@
 //               transposed), overlapped with the next tile's main loop
 #include "mpf_common.cuh"
 #include "sm100_ptx.cuh"
+#include "tmap.cuh"
 
 #include <mutex>
 
@@ -45,6 +46,11 @@ struct GemmArgs {
   int relu;
   int transpose_c;
   int vec_store;                              // row-major float4 stores are legal
+  float* C_lo;                                // if set: C receives rn_tf32(x), C_lo rn_tf32(x - hi)
+  const float* resid;                         // optional addend [resid_rows, resid_ld]; row % resid_rows
+  long long resid_ld;
+  int resid_rows, resid_cols;                 // resid_rows == 0: one row per output row; cols < resid_cols get it
+  float alpha;                                // x = (acc + bias + resid) * alpha, then ReLU
 };
 
 template <int BN>
@@ -203,8 +209,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       tc_fence_after();
       const int row = m_t * kBM + ew * 32 + lane;
       const bool row_ok = row < g.M;
-      float* cb = g.C + static_cast<long long>(b) * g.c_batch_stride;
+      const long long boff = static_cast<long long>(b) * g.c_batch_stride;
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * BN);
+      const float* rrow = nullptr;
+      if (g.resid != nullptr && row_ok)
+        rrow = g.resid + static_cast<long long>(g.resid_rows > 0 ? row % g.resid_rows : row) * g.resid_ld;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         const int n0 = n_t * BN + c * 32;
@@ -217,26 +226,44 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int j = 0; j < 32; ++j) {
           float x = __uint_as_float(v[j]);
           if (g.bias != nullptr && n0 + j < g.N) x += __ldg(g.bias + n0 + j);
+          if (rrow != nullptr && n0 + j < g.resid_cols) x += __ldg(rrow + n0 + j);
+          x *= g.alpha;
           if (g.relu) x = fmaxf(x, 0.f);
           f[j] = x;
         }
-        if (g.transpose_c) {
-          if (row_ok) {
+        auto store = [&](float* base, const float (&val)[32]) {
+          float* cb = base + boff;
+          if (g.transpose_c) {
+            if (row_ok) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < g.N) cb[static_cast<long long>(n0 + j) * g.ldc + row] = f[j];
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < g.N) cb[static_cast<long long>(n0 + j) * g.ldc + row] = val[j];
+            }
+          } else if (row_ok) {
+            float* dst = cb + static_cast<long long>(row) * g.ldc + n0;
+            if (g.vec_store && n0 + 32 <= g.N) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(dst + j) = make_float4(val[j], val[j + 1], val[j + 2], val[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < g.N) dst[j] = val[j];
+            }
           }
-        } else if (row_ok) {
-          float* dst = cb + static_cast<long long>(row) * g.ldc + n0;
-          if (g.vec_store && n0 + 32 <= g.N) {
+        };
+        if (g.C_lo == nullptr) {
+          store(g.C, f);
+        } else {                       // emit the result pre-split for a following 3xTF32 consumer
+          float lo[32];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < g.N) dst[j] = f[j];
+          for (int j = 0; j < 32; ++j) {
+            const float h = rn_tf32(f[j]);
+            lo[j] = rn_tf32(f[j] - h);
+            f[j] = h;
           }
+          store(g.C, f);
+          store(g.C_lo, lo);
         }
       }
       tc_fence_before();
@@ -268,48 +295,45 @@ split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeFn get_encode() {
-  static EncodeFn fn = nullptr;
+int make_tmap_f32_3d(CUtensorMap* m, const float* base, long long d0, long long d1, long long d2,
+                     long long ld1, long long ld2, int box0, int box1) {
+  using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn enc = nullptr;
   static std::once_flag once;
   std::call_once(once, [] {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
         q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeFn>(p);
+      enc = reinterpret_cast<EncodeFn>(p);
   });
-  return fn;
-}
-
-// 3-D fp32 tensor [batch, rows, K] (K contiguous), box [1, box_rows, 32], 128-byte swizzle.
-static int make_tmap(CUtensorMap* m, const float* base, int K, long long rows, int batch, long long ld,
-                     long long batch_stride, int box_rows) {
-  EncodeFn enc = get_encode();
   if (enc == nullptr) {
     set_error("cuTensorMapEncodeTiled not available from the driver");
     return MPF_ERR_UNSUPPORTED;
   }
-  cuuint64_t dims[3] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(batch)};
-  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 4, static_cast<cuuint64_t>(batch_stride) * 4};
-  if (batch == 1) strides[1] = static_cast<cuuint64_t>(rows) * static_cast<cuuint64_t>(ld) * 4;
-  cuuint32_t box[3] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(box_rows), 1};
+  if (box0 * 4 != 128 || ld1 % 4 != 0 || ld2 % 4 != 0 || !aligned16(base)) {
+    set_error("make_tmap: need a 128-byte box row, 16-byte aligned base and strides (ld1=%lld ld2=%lld)", ld1, ld2);
+    return MPF_ERR_BAD_ARG;
+  }
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(d0), static_cast<cuuint64_t>(d1), static_cast<cuuint64_t>(d2)};
+  if (d2 == 1 && ld2 < d1 * ld1) ld2 = d1 * ld1;
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld1) * 4, static_cast<cuuint64_t>(ld2) * 4};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box0), static_cast<cuuint32_t>(box1), 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (CUresult %d) for base=%p K=%d rows=%lld batch=%d ld=%lld", (int)r,
-              (const void*)base, K, rows, batch, ld);
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d): base=%p dims=(%lld,%lld,%lld) ld=(%lld,%lld) box=(%d,%d)",
+              static_cast<int>(r), static_cast<const void*>(base), d0, d1, d2, ld1, ld2, box0, box1);
     return MPF_ERR_BAD_ARG;
   }
   return MPF_OK;
 }
 
-static int sm_count() {
+int sm_count() {
   static int n = 0;
   if (n == 0) {
     int dev = 0;
@@ -353,10 +377,11 @@ int mpf_split_tf32(const float* x, float* hi, float* lo, long long n, void* stre
   return mpf::finish_launch("split_tf32");
 }
 
-int mpf_gemm_tf32x3(const float* A, long long lda, long long a_batch_stride, const float* B_hi,
-                    const float* B_lo, long long ldb, long long b_batch_stride, const float* bias, float* C,
-                    long long ldc, long long c_batch_stride, int batch, int M, int N, int K, int relu,
-                    int transpose_c, void* stream) {
+int mpf_gemm_tf32x3_ex(const float* A, long long lda, long long a_batch_stride, const float* B_hi,
+                       const float* B_lo, long long ldb, long long b_batch_stride, const float* bias, float* C,
+                       float* C_lo, long long ldc, long long c_batch_stride, const float* resid,
+                       long long resid_ld, int resid_rows, int resid_cols, float alpha, int batch, int M, int N,
+                       int K, int relu, int transpose_c, void* stream) {
   using namespace mpf;
   clear_error();
   MPF_REQUIRE(A && B_hi && B_lo && C, "gemm_tf32x3: null pointer argument");
@@ -366,27 +391,41 @@ int mpf_gemm_tf32x3(const float* A, long long lda, long long a_batch_stride, con
                   aligned16(A) && aligned16(B_hi) && aligned16(B_lo),
               "gemm_tf32x3: A / B must be 16-byte aligned with row strides that are multiples of 4 elements");
   MPF_REQUIRE(lda >= K && ldb >= K, "gemm_tf32x3: row strides must be >= K");
+  MPF_REQUIRE(static_cast<long long>(batch) * ((M + kBM - 1) / kBM) * ((N + 63) / 64) < (1ll << 31),
+              "gemm_tf32x3: too many tiles");
   int bn = 64;
   if (N > 64) {
     const int waste128 = (N + 127) / 128 * 128 - N, waste256 = (N + 255) / 256 * 256 - N;
     bn = (N <= 128 || waste128 < waste256) ? 128 : 256;
   }
   CUtensorMap ta, tbh, tbl;
-  int rc = make_tmap(&ta, A, K, M, batch, lda, a_batch_stride, kBM);
+  int rc = make_tmap_f32_3d(&ta, A, K, M, batch, lda, a_batch_stride, kBK, kBM);
   if (rc) return rc;
-  rc = make_tmap(&tbh, B_hi, K, N, batch, ldb, b_batch_stride, bn);
+  rc = make_tmap_f32_3d(&tbh, B_hi, K, N, batch, ldb, b_batch_stride, kBK, bn);
   if (rc) return rc;
-  rc = make_tmap(&tbl, B_lo, K, N, batch, ldb, b_batch_stride, bn);
+  rc = make_tmap_f32_3d(&tbl, B_lo, K, N, batch, ldb, b_batch_stride, kBK, bn);
   if (rc) return rc;
   GemmArgs g;
-  g.C = C; g.bias = bias; g.c_batch_stride = c_batch_stride; g.ldc = ldc;
+  g.C = C; g.C_lo = C_lo; g.bias = bias; g.c_batch_stride = c_batch_stride; g.ldc = ldc;
   g.batch = batch; g.M = M; g.N = N; g.K = K; g.tiles_m = g.tiles_n = 0;
   g.relu = relu; g.transpose_c = transpose_c;
-  g.vec_store = (!transpose_c && ldc % 4 == 0 && c_batch_stride % 4 == 0 && aligned16(C)) ? 1 : 0;
+  g.resid = resid; g.resid_ld = resid_ld; g.resid_rows = resid_rows;
+  g.resid_cols = resid ? (resid_cols > 0 ? resid_cols : N) : 0;
+  g.alpha = alpha;
+  g.vec_store = (!transpose_c && ldc % 4 == 0 && c_batch_stride % 4 == 0 && aligned16(C) &&
+                 (C_lo == nullptr || aligned16(C_lo))) ? 1 : 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (bn == 64) return launch_gemm<64>(ta, tbh, tbl, g, st);
   if (bn == 128) return launch_gemm<128>(ta, tbh, tbl, g, st);
   return launch_gemm<256>(ta, tbh, tbl, g, st);
+}
+
+int mpf_gemm_tf32x3(const float* A, long long lda, long long a_batch_stride, const float* B_hi,
+                    const float* B_lo, long long ldb, long long b_batch_stride, const float* bias, float* C,
+                    long long ldc, long long c_batch_stride, int batch, int M, int N, int K, int relu,
+                    int transpose_c, void* stream) {
+  return mpf_gemm_tf32x3_ex(A, lda, a_batch_stride, B_hi, B_lo, ldb, b_batch_stride, bias, C, nullptr, ldc,
+                            c_batch_stride, nullptr, 0, 0, 0, 1.0f, batch, M, N, K, relu, transpose_c, stream);
 }
 
 }  // extern "C"

@@ -73,8 +73,9 @@ class CrossAttentionLayer(_AttnParams):
 
     def forward(self, tgt, memory, memory_mask=None, memory_key_padding_mask=None, pos=None,
                 query_pos=None):
-        """tgt [B,Q,C]; memory / pos [B,HW,C] (pos may be [1,HW,C]); memory_mask: bool [B,Q,HW]
-        shared by all heads, True = not allowed; rows that are entirely True attend everywhere."""
+        """tgt [B,Q,C]; memory / pos [B,HW,C] (pos may be [1,HW,C]); memory_mask: ops.PackedMask or
+        bool [B,Q,HW] shared by all heads, True = not allowed; rows that are entirely True attend
+        everywhere."""
         assert memory_key_padding_mask is None
         q_in = tgt if query_pos is None else tgt + query_pos
         a = self.multihead_attn
@@ -203,7 +204,8 @@ class _MaskedDecoderBase(nn.Module):
 
     def forward_prediction_heads(self, output, mask_features, attn_mask_target_size):
         """output [B,Q,C] -> (outputs_class [B,Q,K+1], outputs_mask [B,Q,H,W],
-        attn_mask bool [B,Q,h*w] shared by heads).  ref decoder :1859-1877."""
+        attn_mask: ops.PackedMask, one bit per (image, query, key), shared by heads).
+        ref decoder :1859-1877."""
         decoder_output = self.decoder_norm(output)
         outputs_class = self.class_embed(decoder_output)
         mask_embed = self.mask_embed(decoder_output)
@@ -343,7 +345,7 @@ class MultiScaleMaskedTransformerDecoderMaskDN(_MaskedDecoderBase):
         padding_mask[known] = masks
         output = torch.cat([padding, self.query_feat.weight.unsqueeze(0).repeat(bs, 1, 1)], 1)
         oc, om, attn_mask = self.forward_prediction_heads(output, mask_features, size_list[0])
-        attn_mask = torch.cat([padding_mask, attn_mask[:, pad_size:]], 1)
+        attn_mask = attn_mask.replace_rows(ops.PackedMask.from_bool(padding_mask), pad_size)
         tgt_size = pad_size + self.num_queries
         tgt_mask = torch.zeros(tgt_size, tgt_size, dtype=torch.bool, device=dev)
         tgt_mask[pad_size:, :pad_size] = True
@@ -384,7 +386,7 @@ class MultiScaleMaskedTransformerDecoderMaskDN(_MaskedDecoderBase):
                 if not (self.all_lys or i < 3):
                     return attn_mask
                 pm = self.gen_mask_dn(dn_args, size_list[level], known, pad_size, scalar)
-                return torch.cat([pm, attn_mask[:, pad_size:]], 1)
+                return attn_mask.replace_rows(ops.PackedMask.from_bool(pm), pad_size)
 
         pc, pm = self._decode(output, src, pos, size_list, mask_features, tgt_mask, heads0, dn_hook)
         if tgt_mask is not None:

@@ -17,6 +17,7 @@ from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
 from . import MultiScaleDeformableAttention as MSDA
+from . import ops
 
 
 class MSDeformAttnFunction(Function):
@@ -97,12 +98,16 @@ class MSDeformAttn(nn.Module):
             assert (input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum() == Len_in
         M, L, P = self.n_heads, self.n_levels, self.n_points
 
-        value = self.value_proj(input_flatten)
+        value = ops.linear(input_flatten, self.value_proj.weight, self.value_proj.bias)
         if input_padding_mask is not None:
             value = value.masked_fill(input_padding_mask[..., None], float(0))
         value = value.view(N, Len_in, M, self.d_model // M)
-        offsets = self.sampling_offsets(query).view(N, Len_q, M, L, P, 2)
-        weights = F.softmax(self.attention_weights(query).view(N, Len_q, M, L * P), -1)
+        # sampling offsets and attention logits share the input: one GEMM with N = M*L*P*3
+        n_off = M * L * P * 2
+        ow = ops.linear(query, torch.cat([self.sampling_offsets.weight, self.attention_weights.weight], 0),
+                        torch.cat([self.sampling_offsets.bias, self.attention_weights.bias], 0))
+        offsets = ow[..., :n_off].reshape(N, Len_q, M, L, P, 2)
+        weights = F.softmax(ow[..., n_off:].reshape(N, Len_q, M, L * P), -1)
         weights = weights.view(N, Len_q, M, L, P)
         if reference_points.shape[-1] == 2:
             normalizer = torch.stack([input_spatial_shapes[..., 1], input_spatial_shapes[..., 0]], -1)
@@ -117,4 +122,4 @@ class MSDeformAttn(nn.Module):
         output = MSDeformAttnFunction.apply(value.contiguous(), input_spatial_shapes,
                                             input_level_start_index, locations.contiguous(),
                                             weights.contiguous(), self.im2col_step)
-        return self.output_proj(output)
+        return ops.linear(output, self.output_proj.weight, self.output_proj.bias)

@@ -53,3 +53,111 @@ def gemm_tf32x3(a, b_hi, b_lo, bias=None, relu=False, transpose_c=False):
             M if transpose_c else N, out.stride(0), batch, M, N, K, int(relu), int(transpose_c), _stream())
     _lib.check(rc, "gemm_tf32x3")
     return out[0] if squeeze else out
+
+
+def gemm(a, b_hi, b_lo, bias=None, relu=False, transpose_c=False, split_out=False, resid=None,
+         resid_rows=0, resid_cols=0, alpha=1.0):
+    """Extended 3xTF32 GEMM (mpf_gemm_tf32x3_ex): x = (A @ B^T + bias + resid) * alpha (+ReLU).
+    ``resid`` [R, >=resid_cols] is added to output row r from resid row r % resid_rows (0: row r), to
+    columns < resid_cols (0: all).  ``split_out`` returns (hi, lo) TF32-exact halves."""
+    a = _f32c(a, "a")
+    squeeze = a.dim() == 2
+    if squeeze:
+        a, b_hi, b_lo = a[None], b_hi[None], b_lo[None]
+    if a.stride(2) != 1 or a.stride(1) % 4 or (a.shape[0] > 1 and a.stride(0) % 4):
+        a = a.contiguous()
+    if not (b_hi.is_contiguous() and b_lo.is_contiguous()):
+        b_hi, b_lo = b_hi.contiguous(), b_lo.contiguous()
+    batch, M, K = a.shape
+    N = b_hi.shape[1]
+    if b_hi.shape != (batch, N, K) or b_lo.shape != b_hi.shape:
+        raise RuntimeError(f"gemm: shape mismatch a={tuple(a.shape)} b={tuple(b_hi.shape)}")
+    if bias is not None:
+        bias = _f32c(bias, "bias").contiguous()
+    if resid is not None:
+        resid = _f32c(resid, "resid")
+        if resid.dim() != 2 or resid.stride(1) != 1:
+            resid = resid.reshape(-1, resid.shape[-1]).contiguous()
+    shape = (batch, N, M) if transpose_c else (batch, M, N)
+    out = torch.empty(shape, dtype=torch.float32, device=a.device)
+    out_lo = torch.empty_like(out) if split_out else None
+    with torch.cuda.device(a.device):
+        rc = _lib.load().mpf_gemm_tf32x3_ex(
+            a.data_ptr(), a.stride(1), a.stride(0) if batch > 1 else M * a.stride(1),
+            b_hi.data_ptr(), b_lo.data_ptr(), K, N * K,
+            None if bias is None else bias.data_ptr(), out.data_ptr(),
+            None if out_lo is None else out_lo.data_ptr(), M if transpose_c else N, out.stride(0),
+            None if resid is None else resid.data_ptr(), 0 if resid is None else resid.stride(0),
+            int(resid_rows), int(resid_cols), float(alpha), batch, M, N, K, int(relu), int(transpose_c),
+            _stream())
+    _lib.check(rc, "gemm_tf32x3_ex")
+    if squeeze:
+        out = out[0]
+        out_lo = None if out_lo is None else out_lo[0]
+    return (out, out_lo) if split_out else out
+
+
+def mask_words(n_keys):
+    """uint32 words per mask row: whole 64-key tiles (the attention kernel reads two words per tile)."""
+    return 2 * ((n_keys + 63) // 64)
+
+
+def attn_mask_bits(logits, target_size):
+    """logits [B, Q, H, W] fp32 -> packed bits int32 [B, Q, mask_words(h*w)], 1 = masked."""
+    logits = _f32c(logits, "logits")
+    if not logits.is_contiguous():
+        logits = logits.contiguous()
+    B, Q, H, W = logits.shape
+    h, w = int(target_size[0]), int(target_size[1])
+    words = mask_words(h * w)
+    bits = torch.empty((B, Q, words), dtype=torch.int32, device=logits.device)
+    with torch.cuda.device(logits.device):
+        rc = _lib.load().mpf_attn_mask_bits_f32(logits.data_ptr(), H * W, B * Q, H, W, h, w, bits.data_ptr(),
+                                                words, _stream())
+    _lib.check(rc, "attn_mask_bits")
+    return bits
+
+
+def pack_bool_bits(mask):
+    """bool [..., n] -> int32 [..., mask_words(n)], 1 = True; padding bits are 1."""
+    _lib.require_cuda(mask, "mask")
+    m8 = mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.uint8).contiguous()
+    n = mask.shape[-1]
+    rows = mask.numel() // n
+    words = mask_words(n)
+    bits = torch.empty(tuple(mask.shape[:-1]) + (words,), dtype=torch.int32, device=mask.device)
+    with torch.cuda.device(mask.device):
+        rc = _lib.load().mpf_pack_bool_bits(m8.data_ptr(), rows, n, bits.data_ptr(), words, _stream())
+    _lib.check(rc, "pack_bool_bits")
+    return bits
+
+
+def unpack_bits(bits, n):
+    """int32 [..., W] -> bool [..., n] (host-side helper for tests / the library backward)."""
+    shifts = torch.arange(32, device=bits.device, dtype=torch.int32)
+    b = ((bits.unsqueeze(-1) >> shifts) & 1).to(torch.bool)
+    return b.flatten(-2)[..., :n]
+
+
+def masked_xattn_fwd(q_hi, q_lo, k_hi, k_lo, vt_hi, vt_lo, bits, row_open, heads):
+    """Fused masked cross-attention forward.  Returns (out [B,Qt,E], lse2 [B,heads,Qt])."""
+    B, Qt, E = q_hi.shape
+    HW = k_hi.shape[1]
+    for t, n in ((q_hi, "q_hi"), (q_lo, "q_lo"), (k_hi, "k_hi"), (k_lo, "k_lo"), (vt_hi, "vt_hi"), (vt_lo, "vt_lo")):
+        _f32c(t, n)
+        if not t.is_contiguous():
+            raise RuntimeError(f"masked_xattn_fwd: {n} must be contiguous")
+    if vt_hi.shape != (B, E, HW) or bits.shape[:2] != (B, Qt) or bits.dtype != torch.int32:
+        raise RuntimeError("masked_xattn_fwd: inconsistent shapes")
+    out = torch.empty((B, Qt, E), dtype=torch.float32, device=q_hi.device)
+    lse2 = torch.empty((B, heads, Qt), dtype=torch.float32, device=q_hi.device)
+    bits = bits.contiguous()
+    if row_open is not None:
+        row_open = row_open.to(torch.uint8).contiguous()
+    with torch.cuda.device(q_hi.device):
+        rc = _lib.load().mpf_masked_xattn_fwd_f32(
+            q_hi.data_ptr(), q_lo.data_ptr(), k_hi.data_ptr(), k_lo.data_ptr(), vt_hi.data_ptr(),
+            vt_lo.data_ptr(), bits.data_ptr(), None if row_open is None else row_open.data_ptr(),
+            out.data_ptr(), lse2.data_ptr(), B, Qt, HW, heads, E // heads, bits.shape[2], _stream())
+    _lib.check(rc, "masked_xattn_fwd")
+    return out, lse2

@@ -1,68 +1,261 @@
-"""Device ops of the transformer decoder's hot path.
+"""Device ops of the hot path, each with exactly one implementation.
 
-Each function is the single entry the modules call; there is exactly one implementation per op
-(no backend dispatch).  Inputs must be CUDA tensors.
+Forward passes of ``linear``, ``mask_logits``, ``attn_mask_from_logits`` and ``masked_cross_attention``
+run on this package's hand-written sm_100a kernels (tcgen05 3xTF32 GEMM, bit-packed mask kernel, fused
+masked-attention kernel) through the C ABI.  Their backward passes are expressed with PyTorch CUDA
+library ops in round 1 (recomputing the probabilities from the saved log-sum-exp), except the
+input-gradient GEMM of ``linear`` which also runs on the tensor-core kernel.  ``self_attention`` and
+the tiny query-side layers stay on library ops (launch-latency bound).
 
-Status (round 1): ``mask_logits`` / ``attn_mask_from_logits`` / ``masked_cross_attention`` are being
-moved onto hand-written sm_100a kernels behind the C ABI; an op that is listed in
-``NATIVE_OPS`` runs on our kernels, the others still call PyTorch CUDA library ops (cuBLAS /
-SDPA) and are counted as library calls in bench.py.
+Inputs must be CUDA fp32 tensors; there is no CPU path.
 """
 import math
 
 import torch
 import torch.nn.functional as F
 
-from . import _lib
+from . import _lib, native
 
-NATIVE_OPS = {"ms_deform_attn_forward", "ms_deform_attn_backward"}
+NATIVE_OPS = {"ms_deform_attn_forward", "ms_deform_attn_backward", "linear(3xTF32 tcgen05 GEMM)",
+              "mask_logits(3xTF32 tcgen05 GEMM)", "attn_mask_bits", "masked_cross_attention_fwd(tcgen05)"}
+
+# fp32 ``sigmoid(x) < 0.5`` as evaluated by the reference (1/(1+exp(-x)) with a correctly rounded exp)
+# is EXACTLY ``x <= -0x1.7ffffep-23``: for -1.788e-7 < x < 0 the sigmoid rounds to 0.5 and the key stays
+# unmasked.  Verified exhaustively over every float32 in [-2.4e-7, -1.2e-7] against torch CPU
+# (tests/test_host_logic_cpu.py::test_mask_threshold_equals_sigmoid_rule).
+MASK_LOGIT_THRESHOLD = float.fromhex("-0x1.7ffffep-23")
+
+LOG2E = 1.4426950408889634
 
 
 def _cuda_only(t, name):
     _lib.require_cuda(t, name)
 
 
+# ------------------------------------------------------------------------------------------------
+# linear
+# ------------------------------------------------------------------------------------------------
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        x2 = x.reshape(-1, x.shape[-1])
+        w_hi, w_lo = native.split_tf32(weight)
+        y = native.gemm(x2, w_hi, w_lo, bias, relu=relu)
+        ctx.relu = relu
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x2, weight, y if relu else None)
+        return y.view(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, weight, y = ctx.saved_tensors
+        g2 = gy.reshape(-1, gy.shape[-1])
+        if ctx.relu:
+            g2 = g2 * (y > 0)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            if weight.shape[0] % 32 == 0:            # reduction dim of the input-gradient GEMM
+                wt_hi, wt_lo = native.split_tf32(weight.t().contiguous())
+                gx = native.gemm(g2.contiguous(), wt_hi, wt_lo)
+            else:
+                gx = g2 @ weight
+            gx = gx.view(*gy.shape[:-1], weight.shape[1])
+        if ctx.needs_input_grad[1]:
+            gw = g2.t() @ x2
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = g2.sum(0)
+        return gx, gw, gb, None
+
+
+def linear(x, weight, bias=None, relu=False):
+    """y = x W^T + b (optionally ReLU) in fp32-accurate 3xTF32 on the tensor cores.
+    Replaces nn.Linear at ref ops/modules/ms_deform_attn.py:98,102-103,124 and
+    pixel_decoder/msdeformattn.py:116-120."""
+    _cuda_only(x, "x")
+    if x.shape[-1] % 32 != 0:
+        y = F.linear(x, weight, bias)
+        return F.relu(y) if relu else y
+    return _Linear.apply(x, weight, bias, relu)
+
+
+# ------------------------------------------------------------------------------------------------
+# prediction heads: mask logits + boolean stage
+# ------------------------------------------------------------------------------------------------
+def _channels_last_tokens(mask_features):
+    """[B, C, H, W] (any memory format) -> [B, H*W, C] contiguous view/copy."""
+    t = mask_features.permute(0, 2, 3, 1)
+    if not t.is_contiguous():
+        t = t.contiguous()
+    return t.view(t.shape[0], -1, t.shape[-1])
+
+
+class _MaskLogits(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mask_embed, mask_features):
+        B, C, H, W = mask_features.shape
+        tokens = _channels_last_tokens(mask_features)                       # [B, HW, C]
+        e_hi, e_lo = native.split_tf32(mask_embed)
+        out = native.gemm(tokens, e_hi, e_lo, transpose_c=True)             # [B, Q, HW]
+        ctx.save_for_backward(mask_embed, tokens)
+        ctx.fshape = (B, C, H, W)
+        return out.view(B, mask_embed.shape[1], H, W)
+
+    @staticmethod
+    def backward(ctx, g):
+        mask_embed, tokens = ctx.saved_tensors
+        B, C, H, W = ctx.fshape
+        g2 = g.reshape(B, g.shape[1], H * W)
+        ge = gf = None
+        if ctx.needs_input_grad[0]:
+            ge = torch.bmm(g2, tokens)                                       # [B,Q,C]
+        if ctx.needs_input_grad[1]:
+            gf = torch.bmm(g2.transpose(1, 2), mask_embed)                  # [B,HW,C]
+            gf = gf.view(B, H, W, C).permute(0, 3, 1, 2)
+        return ge, gf
+
+
 def mask_logits(mask_embed, mask_features):
-    """einsum('bqc,bchw->bqhw') (ref decoder :1865).  mask_embed [B,Q,C], mask_features [B,C,H,W]."""
+    """einsum('bqc,bchw->bqhw') (ref decoder :1865) as a TMA-fed tcgen05 GEMM over channels-last
+    pixel features: M = H*W, N = Q, K = C, transposed store."""
     _cuda_only(mask_embed, "mask_embed")
-    return torch.einsum("bqc,bchw->bqhw", mask_embed, mask_features)
+    return _MaskLogits.apply(mask_embed.contiguous(), mask_features)
+
+
+class PackedMask:
+    """Attention mask of one decoder layer: ``bits`` int32 [B, Q, W] (bit i of word j = key 32j+i,
+    1 = not allowed), shared by all heads; ``n_keys`` = h*w."""
+
+    def __init__(self, bits, n_keys):
+        self.bits, self.n_keys = bits, n_keys
+
+    def to_bool(self):
+        return native.unpack_bits(self.bits, self.n_keys)
+
+    def replace_rows(self, other, n_rows):
+        """Rows [0, n_rows) come from ``other`` (the mask-piloted GT masks, ref decoder :1046-1048)."""
+        return PackedMask(torch.cat([other.bits[:, :n_rows], self.bits[:, n_rows:]], 1), self.n_keys)
+
+    @staticmethod
+    def from_bool(mask):
+        return PackedMask(native.pack_bool_bits(mask), mask.shape[-1])
 
 
 def attn_mask_from_logits(outputs_mask, target_size):
-    """bool [B,Q,h*w], True = key not allowed: bilinear resize (align_corners=False) -> sigmoid ->
-    ``< 0.5`` (ref decoder :1869-1875, without the 8x head repeat).  Detached."""
+    """Boolean stage of the heads (ref decoder :1869-1875): bilinear resize -> ``sigmoid < 0.5``, as ONE
+    bit per (image, query, key).  Returns a PackedMask (detached by construction)."""
     _cuda_only(outputs_mask, "outputs_mask")
-    a = F.interpolate(outputs_mask.detach(), size=target_size, mode="bilinear", align_corners=False)
-    return a.sigmoid().flatten(2) < 0.5
+    h, w = int(target_size[0]), int(target_size[1])
+    return PackedMask(native.attn_mask_bits(outputs_mask.detach(), (h, w)), h * w)
 
 
+# ------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------
 def _split_heads(x, nhead):
     B, L, E = x.shape
     return x.view(B, L, nhead, E // nhead).transpose(1, 2)       # [B,h,L,hd]
 
 
+class _MaskedCrossAttention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q_in, memory, pos, w_in, b_in, w_out, b_out, nhead, bits, n_keys):
+        B, Qt, E = q_in.shape
+        HW = memory.shape[1]
+        hd = E // nhead
+        scale2 = LOG2E / math.sqrt(hd)
+        wq_hi, wq_lo = native.split_tf32(w_in[:E])
+        wk_hi, wk_lo = native.split_tf32(w_in[E:2 * E])
+        wv_hi, wv_lo = native.split_tf32(w_in[2 * E:])
+        # Q (scaled into the log2 domain), pre-split for the attention kernel
+        q_hi, q_lo = native.gemm(q_in.reshape(B * Qt, E), wq_hi, wq_lo, b_in[:E], alpha=scale2, split_out=True)
+        # K = (memory + pos) Wk^T + bk = memory Wk^T + (pos Wk^T + bk): the second term is batch independent
+        pos_k = native.gemm(pos.reshape(-1, E), wk_hi, wk_lo, b_in[E:2 * E])                  # [HW, E]
+        k_hi, k_lo = native.gemm(memory.reshape(B * HW, E), wk_hi, wk_lo, None, resid=pos_k, resid_rows=HW,
+                                 split_out=True)
+        # V^T [B, E, HW] (keys contiguous) so that P V is a K-major tensor-core product
+        vt_hi, vt_lo = native.gemm(memory, wv_hi[None].expand(B, -1, -1), wv_lo[None].expand(B, -1, -1),
+                                   b_in[2 * E:], transpose_c=True, split_out=True)
+        row_open = (bits == -1).all(-1)                                                      # ref decoder :1780
+        o, lse2 = native.masked_xattn_fwd(q_hi.view(B, Qt, E), q_lo.view(B, Qt, E), k_hi.view(B, HW, E),
+                                          k_lo.view(B, HW, E), vt_hi, vt_lo, bits, row_open, nhead)
+        wo_hi, wo_lo = native.split_tf32(w_out)
+        y = native.gemm(o.view(B * Qt, E), wo_hi, wo_lo, b_out).view(B, Qt, E)
+        ctx.save_for_backward(q_in, memory, pos, w_in, b_in, w_out, bits, row_open, o, lse2)
+        ctx.nhead, ctx.n_keys = nhead, n_keys
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        q_in, memory, pos, w_in, b_in, w_out, bits, row_open, o, lse2 = ctx.saved_tensors
+        nhead = ctx.nhead
+        B, Qt, E = q_in.shape
+        HW = memory.shape[1]
+        hd = E // nhead
+        inv = 1.0 / math.sqrt(hd)
+        gy2 = gy.reshape(B * Qt, E)
+        g_wout = gy2.t() @ o.reshape(B * Qt, E)
+        g_bout = gy2.sum(0)
+        go = (gy2 @ w_out).view(B, Qt, E)
+        # recompute projections and probabilities (library ops, fp32)
+        wq, wk, wv = w_in[:E], w_in[E:2 * E], w_in[2 * E:]
+        kin = memory + pos
+        q = F.linear(q_in, wq, b_in[:E])
+        k = F.linear(kin, wk, b_in[E:2 * E])
+        v = F.linear(memory, wv, b_in[2 * E:])
+        qh, kh, vh = _split_heads(q, nhead), _split_heads(k, nhead), _split_heads(v, nhead)
+        s2 = torch.matmul(qh, kh.transpose(-1, -2)) * (inv * LOG2E)                 # [B,h,Q,HW] log2 domain
+        p = torch.exp2(s2 - lse2.unsqueeze(-1))
+        masked = native.unpack_bits(bits, ctx.n_keys) & ~row_open.unsqueeze(-1)     # [B,Q,HW]
+        p = p.masked_fill(masked.unsqueeze(1), 0.0)
+        goh, oh = _split_heads(go, nhead), _split_heads(o, nhead)
+        gv = torch.matmul(p.transpose(-1, -2), goh)                                  # [B,h,HW,hd]
+        gp = torch.matmul(goh, vh.transpose(-1, -2))                                 # [B,h,Q,HW]
+        delta = (goh * oh).sum(-1, keepdim=True)
+        gs = p * (gp - delta) * inv
+        gq = torch.matmul(gs, kh)                                                    # [B,h,Q,hd]
+        gk = torch.matmul(gs.transpose(-1, -2), qh)                                  # [B,h,HW,hd]
+        gq = gq.transpose(1, 2).reshape(B * Qt, E)
+        gk = gk.transpose(1, 2).reshape(B * HW, E)
+        gv = gv.transpose(1, 2).reshape(B * HW, E)
+        g_win = torch.cat([gq.t() @ q_in.reshape(B * Qt, E), gk.t() @ kin.reshape(B * HW, E),
+                           gv.t() @ memory.reshape(B * HW, E)], 0)
+        g_bin = torch.cat([gq.sum(0), gk.sum(0), gv.sum(0)], 0)
+        g_qin = (gq @ wq).view(B, Qt, E) if ctx.needs_input_grad[0] else None
+        g_mem = None
+        g_pos = None
+        if ctx.needs_input_grad[1]:
+            g_mem = (gk @ wk + gv @ wv).view(B, HW, E)
+        if ctx.needs_input_grad[2]:
+            g_pos = (gk @ wk).view(B, HW, E).sum(0, keepdim=True)
+        return g_qin, g_mem, g_pos, g_win, g_bin, g_wout, g_bout, None, None, None
+
+
 def masked_cross_attention(q_in, memory, pos, w_in, b_in, w_out, b_out, nhead, mask):
     """softmax((q Wq)(k Wk)^T / sqrt(hd) + mask) (v Wv) Wo with k = memory + pos, v = memory
-    (ref decoder :100-112 through nn.MultiheadAttention), mask bool [B,Q,HW] shared by heads;
-    a row that is entirely masked attends to every key (ref decoder :1780)."""
+    (ref decoder :100-112 through nn.MultiheadAttention); a row that is entirely masked attends to
+    every key (ref decoder :1780).  ``mask``: PackedMask, bool [B,Q,HW] (True = not allowed) or None."""
     _cuda_only(q_in, "tgt")
-    E = q_in.shape[-1]
-    q = F.linear(q_in, w_in[:E], b_in[:E])
-    k = F.linear(memory + pos, w_in[E:2 * E], b_in[E:2 * E])
-    v = F.linear(memory, w_in[2 * E:], b_in[2 * E:])
-    allowed = None
-    if mask is not None:
-        full = mask.all(-1, keepdim=True)
-        allowed = (~mask | full)[:, None]                          # [B,1,Q,HW] True = attend
-    o = F.scaled_dot_product_attention(_split_heads(q, nhead), _split_heads(k, nhead),
-                                       _split_heads(v, nhead), attn_mask=allowed)
-    o = o.transpose(1, 2).reshape(q_in.shape)
-    return F.linear(o, w_out, b_out)
+    B, Qt, E = q_in.shape
+    HW = memory.shape[1]
+    if mask is None:
+        bits = torch.zeros((B, Qt, native.mask_words(HW)), dtype=torch.int32, device=q_in.device)
+        n_keys = HW
+    elif isinstance(mask, PackedMask):
+        bits, n_keys = mask.bits, mask.n_keys
+    else:
+        bits, n_keys = native.pack_bool_bits(mask), mask.shape[-1]
+    if n_keys != HW or E // nhead != 32 or HW % 4 != 0:
+        raise RuntimeError(f"masked_cross_attention: unsupported geometry (keys {n_keys} vs memory {HW}, "
+                           f"head_dim {E // nhead}; the kernel needs head_dim 32 and HW % 4 == 0)")
+    if pos.dim() == 3 and pos.shape[0] != 1:
+        pos = pos[:1]
+    return _MaskedCrossAttention.apply(q_in.contiguous(), memory.contiguous(), pos.contiguous(), w_in, b_in,
+                                       w_out, b_out, nhead, bits, n_keys)
 
 
 def self_attention(qk_in, v_in, w_in, b_in, w_out, b_out, nhead, tgt_mask=None):
-    """nn.MultiheadAttention self-attention over the queries (ref decoder :42-52); tgt_mask bool
-    [Q,Q], True = not allowed (DN groups, ref decoder :1051-1059)."""
+    """nn.MultiheadAttention self-attention over the (few hundred) queries (ref decoder :42-52); tgt_mask
+    bool [Q,Q], True = not allowed (DN groups, ref decoder :1051-1059).  Library ops."""
     _cuda_only(qk_in, "tgt")
     E = qk_in.shape[-1]
     q = F.linear(qk_in, w_in[:E], b_in[:E])

@@ -24,6 +24,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from . import ops
 from .msdeform_attn import MSDeformAttn
 from .position_encoding import PositionEmbeddingSine
 from .registry import configurable, register_pixel_decoder
@@ -106,7 +107,8 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
         return tensor if pos is None else tensor + pos
 
     def forward_ffn(self, src):
-        src2 = self.linear2(self.dropout2(F.relu(self.linear1(src))))
+        hidden = ops.linear(src, self.linear1.weight, self.linear1.bias, relu=True)
+        src2 = ops.linear(self.dropout2(hidden), self.linear2.weight, self.linear2.bias)
         return self.norm2(src + self.dropout3(src2))
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None):

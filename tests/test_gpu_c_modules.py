@@ -91,7 +91,7 @@ def test_attn_mask_bits_bit_exact_on_shared_logits(golden_dir):
     logits = cases.threshold_logits().to(DEV)
     for key, ref in G["masks"].items():
         h, w = (int(v) for v in key.split("x"))
-        got = ops.attn_mask_from_logits(logits, (h, w)).cpu()            # [B,Q,hw], heads share it
+        got = ops.attn_mask_from_logits(logits, (h, w)).to_bool().cpu()  # [B,Q,hw], heads share it
         ref1 = ref.view(1, 8, 4, h * w)
         assert torch.equal(ref1[:, 0], ref1[:, 7])
         assert torch.equal(got, ref1[:, 0]), key

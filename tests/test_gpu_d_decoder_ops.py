@@ -1,0 +1,131 @@
+"""-m gpu: the decoder-side kernels (bit-packed mask stage, fused masked cross-attention, 3xTF32
+linear / mask-logit GEMMs) against the oracle's torch restatement evaluated in fp64.
+Tolerance 1e-4*max(1,|ref|) for fp32 results (contract: 1e-3); mask bits exact."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import cases
+from mp_former_b200 import native, ops
+from oracle import torch_oracle as O
+from test_oracle_vs_golden import load
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).abs() / b.double().abs().clamp(min=1.0)).max().item()
+
+
+def test_attn_mask_bits_bit_exact_vs_reference_golden(golden_dir):
+    G = load(golden_dir, "attn_mask_bits.pt")
+    logits = cases.threshold_logits().to(DEV)
+    for key, ref in G["masks"].items():
+        h, w = (int(v) for v in key.split("x"))
+        pm = ops.attn_mask_from_logits(logits, (h, w))
+        assert pm.bits.shape[-1] == native.mask_words(h * w)
+        got = pm.to_bool().cpu()
+        assert torch.equal(got, ref.view(1, 8, 4, h * w)[:, 0]), key
+        # padding bits (keys >= h*w) are set
+        full = native.unpack_bits(pm.bits, pm.bits.shape[-1] * 32).cpu()
+        assert full[..., h * w:].all()
+
+
+@pytest.mark.parametrize("H,W,h,w", [(256, 256, 32, 32), (256, 256, 64, 64), (256, 256, 128, 128),
+                                     (64, 128, 8, 16), (20, 20, 7, 9), (16, 16, 16, 16)])
+def test_attn_mask_bits_vs_torch_resize(H, W, h, w):
+    g = torch.Generator(device=DEV).manual_seed(H + h)
+    logits = torch.randn(2, 5, H, W, device=DEV, generator=g) * torch.logspace(-8, 1, 5, device=DEV).view(1, 5, 1, 1)
+    ref = F.interpolate(logits.cpu(), size=(h, w), mode="bilinear", align_corners=False).flatten(2) <= ops.MASK_LOGIT_THRESHOLD
+    got = ops.attn_mask_from_logits(logits, (h, w)).to_bool().cpu()
+    mism = (got != ref).float().mean().item()
+    if H % h == 0 and W % w == 0 and (H // h) in (1, 2, 4, 8):
+        assert mism == 0.0                  # power-of-two factors: every product is exact -> bit exact
+    else:
+        assert mism < 1e-5                  # general factors: fma / rounding-order differences only
+
+
+def test_pack_unpack_roundtrip():
+    g = torch.Generator(device=DEV).manual_seed(0)
+    for n in (4, 33, 64, 100, 1024):
+        m = torch.rand(3, 7, n, device=DEV, generator=g) < 0.3
+        bits = native.pack_bool_bits(m)
+        assert bits.shape == (3, 7, native.mask_words(n))
+        assert torch.equal(native.unpack_bits(bits, n), m)
+
+
+def torch_xattn(q_in, memory, pos, w_in, b_in, w_out, b_out, nhead, mask, dtype=torch.float64):
+    sd = {"in_proj_weight": w_in.to(dtype), "in_proj_bias": b_in.to(dtype), "out_proj.weight": w_out.to(dtype),
+          "out_proj.bias": b_out.to(dtype)}
+    m = mask & ~mask.all(-1, keepdim=True)
+    am = m[:, None].expand(-1, nhead, -1, -1).flatten(0, 1)
+    y = O.mha(sd, "", q_in.to(dtype).transpose(0, 1), (memory + pos).to(dtype).transpose(0, 1),
+              memory.to(dtype).transpose(0, 1), nhead, am)
+    return y.transpose(0, 1)
+
+
+@pytest.mark.parametrize("B,Qt,HW", [(2, 100, 1024), (1, 130, 256), (3, 10, 4), (2, 37, 100), (1, 128, 64),
+                                     (2, 120, 4096)])
+def test_masked_cross_attention_forward_backward(B, Qt, HW):
+    E, nhead = 256, 8
+    g = torch.Generator(device=DEV).manual_seed(B * 1000 + Qt + HW)
+    rn = lambda *s, sc=1.0: torch.randn(*s, device=DEV, generator=g) * sc
+    q_in, memory, pos = rn(B, Qt, E), rn(B, HW, E), rn(1, HW, E)
+    w_in, b_in = rn(3 * E, E, sc=1 / 16), rn(3 * E, sc=0.1)
+    w_out, b_out = rn(E, E, sc=1 / 16), rn(E, sc=0.1)
+    mask = torch.rand(B, Qt, HW, device=DEV, generator=g) < 0.7
+    mask[0, 0] = True                      # fully masked row -> attends everywhere (ref decoder :1780)
+    mask[0, 1] = True
+    mask[0, 1, HW - 1] = False             # exactly one open key (the last one)
+    mask[-1, Qt - 1] = False               # nothing masked
+    leaves = [t.clone().requires_grad_(True) for t in (q_in, memory, w_in, b_in, w_out, b_out)]
+    y = ops.masked_cross_attention(leaves[0], leaves[1], pos, leaves[2], leaves[3], leaves[4], leaves[5], nhead,
+                                   ops.PackedMask.from_bool(mask))
+    gy = rn(B, Qt, E)
+    y.backward(gy)
+    ref_leaves = [t.double().clone().requires_grad_(True) for t in (q_in, memory, w_in, b_in, w_out, b_out)]
+    yr = torch_xattn(ref_leaves[0], ref_leaves[1], pos.double(), ref_leaves[2], ref_leaves[3], ref_leaves[4],
+                     ref_leaves[5], nhead, mask)
+    yr.backward(gy.double())
+    assert torch.isfinite(y).all()
+    assert rel(y, yr) < 1e-4, rel(y, yr)
+    for name, a, b_ in zip(("q_in", "memory", "w_in", "b_in", "w_out", "b_out"), leaves, ref_leaves):
+        scale = b_.grad.abs().max().item()
+        err = (a.grad.double() - b_.grad).abs().max().item() / max(scale, 1e-6)
+        assert err < 2e-4, (name, err)
+    # a bool mask is accepted as well and gives the same result
+    y2 = ops.masked_cross_attention(q_in, memory, pos, w_in, b_in, w_out, b_out, nhead, mask)
+    assert torch.equal(y2, y.detach())
+
+
+def test_linear_and_mask_logits_autograd():
+    g = torch.Generator(device=DEV).manual_seed(3)
+    x = torch.randn(2, 300, 256, device=DEV, generator=g, requires_grad=True)
+    w = (torch.randn(288, 256, device=DEV, generator=g) / 16).requires_grad_(True)
+    b = torch.randn(288, device=DEV, generator=g).requires_grad_(True)
+    for relu in (False, True):
+        for t in (x, w, b):
+            t.grad = None
+        y = ops.linear(x, w, b, relu=relu)
+        gy = torch.randn(y.shape, device=DEV, generator=g)
+        y.backward(gy)
+        xr, wr, br = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+        yr = F.linear(xr, wr, br)
+        yr = yr.relu() if relu else yr
+        yr.backward(gy.double())
+        assert rel(y, yr) < 1e-4
+        assert rel(x.grad, xr.grad) < 1e-4 and rel(w.grad, wr.grad) < 1e-3 and rel(b.grad, br.grad) < 1e-4
+    e = torch.randn(2, 100, 256, device=DEV, generator=g, requires_grad=True)
+    f = torch.randn(2, 256, 32, 48, device=DEV, generator=g).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    out = ops.mask_logits(e, f)
+    go = torch.randn(out.shape, device=DEV, generator=g)
+    out.backward(go)
+    er, fr = e.detach().double().requires_grad_(True), f.detach().double().requires_grad_(True)
+    outr = torch.einsum("bqc,bchw->bqhw", er, fr)
+    outr.backward(go.double())
+    assert rel(out, outr) < 1e-4 and rel(e.grad, er.grad) < 1e-3 and rel(f.grad, fr.grad) < 1e-3
+    # NCHW-contiguous features are accepted too (one layout copy)
+    assert rel(ops.mask_logits(e.detach(), f.detach().contiguous()), outr) < 1e-4

@@ -16,12 +16,52 @@ from oracle import torch_oracle as O
 from test_oracle_vs_golden import (_cmp_out, close, decoder_template, load, pixel_decoder_template)
 
 
+def cpu_pack_bits(mask):
+    """bool [..., n] -> int32 [..., mask_words(n)] (bit i of word j = key 32j+i; padding = 1)."""
+    from mp_former_b200 import native
+    n = mask.shape[-1]
+    w = native.mask_words(n)
+    m = torch.ones(mask.shape[:-1] + (w * 32,), dtype=torch.bool)
+    m[..., :n] = mask
+    v = (m.view(*mask.shape[:-1], w, 32).to(torch.int64) << torch.arange(32)).sum(-1)
+    return torch.where(v >= 2 ** 31, v - 2 ** 32, v).to(torch.int32)
+
+
 @pytest.fixture()
 def cpu_ops(monkeypatch):
+    """Replaces every native kernel launcher by a CPU torch equivalent (test-only)."""
+    import torch.nn.functional as F
+    from mp_former_b200 import native, ops
+
     def fwd(value, shapes, lsi, loc, aw, step, host_shapes=None):
         return O.msda_core(value, shapes, loc, aw)
+
+    def linear(x, w, b=None, relu=False):
+        y = F.linear(x, w, b)
+        return F.relu(y) if relu else y
+
+    def attn_mask_bits(logits, size):
+        a = F.interpolate(logits, size=size, mode="bilinear", align_corners=False).flatten(2)
+        return cpu_pack_bits(a <= ops.MASK_LOGIT_THRESHOLD)
+
+    def xattn(q_in, memory, pos, w_in, b_in, w_out, b_out, nhead, mask):
+        sd = {"in_proj_weight": w_in, "in_proj_bias": b_in, "out_proj.weight": w_out, "out_proj.bias": b_out}
+        m = mask.to_bool() if isinstance(mask, ops.PackedMask) else mask
+        am = None
+        if m is not None:
+            m = m & ~m.all(-1, keepdim=True)
+            am = m[:, None].expand(-1, nhead, -1, -1).flatten(0, 1)
+        y = O.mha(sd, "", q_in.transpose(0, 1), (memory + pos).transpose(0, 1), memory.transpose(0, 1),
+                  nhead, am)
+        return y.transpose(0, 1)
+
     monkeypatch.setattr(MSDA, "ms_deform_attn_forward", fwd)
     monkeypatch.setattr(_lib, "require_cuda", lambda t, n: None)
+    monkeypatch.setattr(ops, "linear", linear)
+    monkeypatch.setattr(ops, "mask_logits", lambda e, f: torch.einsum("bqc,bchw->bqhw", e, f))
+    monkeypatch.setattr(native, "attn_mask_bits", attn_mask_bits)
+    monkeypatch.setattr(native, "pack_bool_bits", cpu_pack_bits)
+    monkeypatch.setattr(ops, "masked_cross_attention", xattn)
 
 
 def build_pixel_decoder():
@@ -122,3 +162,17 @@ def test_registries_hold_reference_names():
     assert "MSDeformAttnPixelDecoder" in M.SEM_SEG_HEADS_REGISTRY
     assert "MultiScaleMaskedTransformerDecoder" in M.TRANSFORMER_DECODER_REGISTRY
     assert "MultiScaleMaskedTransformerDecoderMaskDN" in M.TRANSFORMER_DECODER_REGISTRY
+
+
+def test_mask_threshold_equals_sigmoid_rule():
+    """``sigmoid(x) < 0.5`` (fp32, the reference's boolean rule, decoder :1873) == ``x <= -0x1.7ffffep-23``
+    for EVERY float32 in the only band where they could differ, plus ordinary values."""
+    import numpy as np
+    from mp_former_b200 import ops
+    lo = int(np.float32(-1.1920929e-7).view(np.uint32))
+    hi = int(np.float32(-2.3841858e-7).view(np.uint32))
+    x = torch.from_numpy(np.arange(lo, hi + 1, dtype=np.uint32).view(np.float32).copy())
+    assert torch.equal(x.sigmoid() < 0.5, x <= ops.MASK_LOGIT_THRESHOLD)
+    g = torch.randn(1 << 20, generator=torch.Generator().manual_seed(0)) * torch.logspace(-9, 2, 1 << 20)
+    g = torch.cat([g, torch.tensor([0.0, -0.0, float("inf"), -float("inf"), float("nan"), 1e-45, -1e-45])])
+    assert torch.equal(g.sigmoid() < 0.5, g <= ops.MASK_LOGIT_THRESHOLD)
