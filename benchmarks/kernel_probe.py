@@ -1,0 +1,108 @@
+"""Runs each native kernel at the bench geometry (B images of 1024x1024, R50 head) a few times and prints
+CUDA-event timings with the derived roofline numbers, one JSON object per kernel.  Also the target of the
+`ncu --set full -k regex:...` captures committed under profiles/."""
+import json
+import os
+import statistics
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from mp_former_b200 import MultiScaleDeformableAttention as MSDA  # noqa: E402
+from mp_former_b200 import native  # noqa: E402
+
+DEV = "cuda:0"
+B = int(os.environ.get("MPF_B", "16"))
+REPS = int(os.environ.get("MPF_REPS", "10"))
+PEAKS = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+    os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+TF32_PEAK = PEAKS["bf16_tflops"] / 2.0       # dense TF32 = half the measured bf16 cuBLAS rate
+
+
+def timeit(fn, reps=REPS, warm=2):
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return statistics.median(ts)
+
+
+def emit(name, ms, bytes_=None, mma_flops=None, **kw):
+    r = {"kernel": name, "ms": ms, "B": B}
+    if bytes_ is not None:
+        r.update(algorithmic_GB=bytes_ / 1e9, GBs=bytes_ / ms / 1e6, frac_of_measured_hbm=bytes_ / ms / 1e6 / PEAKS["hbm_gbs"])
+    if mma_flops is not None:
+        r.update(tensor_TFLOPs_issued=mma_flops / ms / 1e9,
+                 frac_of_tf32_peak=mma_flops / ms / 1e9 / TF32_PEAK, tf32_peak_TFLOPs=TF32_PEAK)
+    r.update(kw)
+    print(json.dumps(r), flush=True)
+
+
+def main():
+    g = torch.Generator(device=DEV).manual_seed(0)
+    rn = lambda *s: torch.randn(*s, device=DEV, generator=g)
+    which = os.environ.get("MPF_PROBE", "msda,gemm,masklogits,maskbits,xattn").split(",")
+    S, M, D, L, P = 21504, 8, 32, 3, 4
+    shapes = [(32, 32), (64, 64), (128, 128)]
+    if "msda" in which:
+        value = rn(B, S, M, D)
+        st = torch.as_tensor(shapes, dtype=torch.long, device=DEV)
+        st._mpf_host_shapes = tuple(shapes)
+        lsi = torch.cat((st.new_zeros((1,)), st.prod(1).cumsum(0)[:-1]))
+        ref = torch.cat([torch.stack(torch.meshgrid((torch.arange(w, device=DEV) + 0.5) / w,
+                                                    (torch.arange(h, device=DEV) + 0.5) / h, indexing="xy"), -1).reshape(-1, 2)
+                         for h, w in shapes])
+        norm = torch.tensor([[w, h] for h, w in shapes], device=DEV, dtype=torch.float32)
+        loc = (ref[None, :, None, None, None, :] + rn(B, S, M, L, P, 2) * 2.0 / norm[None, None, None, :, None, :]).contiguous()
+        aw = torch.softmax(rn(B, S, M, L * P), -1).view(B, S, M, L, P)
+        gout = rn(B, S, M * D)
+        alg_f = 4 * (S * M * D + 2 * S * M * L * P + S * M * L * P + S * M * D) * B
+        alg_b = alg_f + 4 * (S * M * D + 3 * S * M * L * P) * B
+        emit("msda_fwd_vec_kernel<8>", timeit(lambda: MSDA.ms_deform_attn_forward(value, st, lsi, loc, aw, 128)), alg_f)
+        emit("msda_bwd_vec_kernel<8>", timeit(lambda: MSDA.ms_deform_attn_backward(value, st, lsi, loc, aw, gout, 128)), alg_b)
+        del value, loc, aw, gout
+    if "gemm" in which:
+        for (m, n, k, tag) in ((B * S, 1024, 256, "ffn.linear1"), (B * S, 256, 1024, "ffn.linear2"),
+                               (B * S, 256, 256, "value_proj"), (B * S, 288, 256, "offsets+weights")):
+            a, w, bias = rn(m, k), rn(n, k) / 16, rn(n)
+            wh, wl = native.split_tf32(w)
+            ms = timeit(lambda: native.gemm(a, wh, wl, bias))
+            emit(f"gemm_tf32x3 {tag} M={m} N={n} K={k}", ms, 4 * (m * k + m * n + 2 * n * k), 3 * 2.0 * m * n * k,
+                 fp32_equiv_TFLOPs=2.0 * m * n * k / ms / 1e9)
+            del a
+    if "masklogits" in which:
+        Q, C, HW = 120, 256, 65536
+        e, f = rn(B, Q, C), rn(B, HW, C)
+        eh, el = native.split_tf32(e)
+        ms = timeit(lambda: native.gemm(f, eh, el, transpose_c=True))
+        emit(f"gemm_tf32x3 mask_logits B={B} Q={Q} HW={HW}", ms, 4 * B * (HW * C + Q * HW + 2 * Q * C), 3 * 2.0 * B * Q * C * HW,
+             fp32_equiv_TFLOPs=2.0 * B * Q * C * HW / ms / 1e9)
+        del f
+    if "maskbits" in which:
+        logits = rn(B, 120, 256, 256)
+        for hw in (32, 64, 128):
+            ms = timeit(lambda: native.attn_mask_bits(logits, (hw, hw)))
+            emit(f"attn_mask_bits 256->{hw}", ms, None, None, outputs_per_us=B * 120 * hw * hw / ms / 1e3)
+        del logits
+    if "xattn" in which:
+        E, heads, Qt = 256, 8, 120
+        for HW in (1024, 4096, 16384):
+            q, k, vt = rn(B, Qt, E), rn(B, HW, E), rn(B, E, HW)
+            qh, ql = native.split_tf32(q); kh, kl = native.split_tf32(k); vh, vl = native.split_tf32(vt)
+            bits = native.pack_bool_bits(torch.rand(B, Qt, HW, device=DEV, generator=g) < 0.7)
+            ms = timeit(lambda: native.masked_xattn_fwd(qh, ql, kh, kl, vh, vl, bits, None, heads))
+            mma = 3 * 2.0 * B * heads * 128 * HW * 32 * 2          # 128-row tiles, S and PV, 3 passes
+            emit(f"masked_xattn_fwd B={B} Qt={Qt} HW={HW}", ms, 4 * B * (4 * HW * E + 2 * Qt * E) + B * Qt * HW // 8, mma,
+                 useful_fp32_TFLOPs=4.0 * B * Qt * HW * E / ms / 1e9)
+
+
+if __name__ == "__main__":
+    main()

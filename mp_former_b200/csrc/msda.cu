@@ -10,8 +10,9 @@
 //     holding a float4, so every corner gather is one coalesced 16-byte-per-lane request
 //     (LPI lanes = one 128-byte line for D = 32).  A 256-thread CTA therefore works on 256/LPI
 //     items at a time.
-//   * Sampling locations / attention weights of an item are loaded once as float4 by the item's
-//     own lanes and handed round with warp shuffles (no shared memory, no __syncthreads).
+//   * Per level, the coordinate arithmetic of every (item, point) sample is done ONCE by one thread
+//     and staged in shared memory as a descriptor (corner offsets + weights); the item's lanes then
+//     only gather and FMA (see the comment above the vectorised kernels).
 //   * A CTA owns one (batch, head, chunk-of-128-queries) unit.  When the queries are known to be
 //     the pixel grid itself (encoder self-attention: num_query == spatial_size and host shapes are
 //     provided) chunks are 16x8 spatial tiles of one level, so the gather footprint of a CTA is a
@@ -73,99 +74,114 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Forward, vectorised: D = 4*LPI channels, P = 4 points, L <= LPI/2 levels.
+// Vectorised kernels: D = 4*LPI channels, P = 4 points, L <= 8 levels.
+//
+// Per level, phase A lets every thread turn two (item, point) samples of the CTA's 128-query chunk into
+// a descriptor in shared memory -- four corner offsets (-1 = corner outside the map / sample outside
+// the gate) plus the weights -- so the coordinate arithmetic is done once per sample instead of once
+// per lane; phase B is then pure gather + FMA: two broadcast LDS.128 and four 16-byte gathers per
+// sample and lane.  (ncu on the first version showed the kernel issue-bound, 68% of issue slots,
+// with only 52% of the L1 data pipe in use: see profiles/r1a_*.)
 // ------------------------------------------------------------------------------------------------
+constexpr int kDescStride = 5;   // 16-byte slots per item: 4 points + 1 pad so that the 4 items a warp
+                                 // reads in one LDS.128 fall into distinct bank groups
+
+template <bool kBackward>
+__device__ __forceinline__ void build_descriptors(int4* so, float4* sw, const float* __restrict__ loc,
+                                                  const float* __restrict__ aw, const MsdaTiling& tiling,
+                                                  int chunk, int b, int m, int M, int Lq, int LP, int l, int H,
+                                                  int W, int MD) {
+  for (int idx = threadIdx.x; idx < kChunkQ * 4; idx += kThreads) {
+    const int j = idx >> 2, p = idx & 3;
+    const int q = query_of(tiling, chunk, j, Lq);
+    int4 offs = make_int4(-1, -1, -1, -1);
+    float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q >= 0) {
+      const size_t s = ((static_cast<size_t>(b) * Lq + q) * M + m) * LP + l * 4 + p;
+      const float2 xy = __ldg(reinterpret_cast<const float2*>(loc + 2 * s));
+      const float a = __ldg(aw + s);
+      const float h_im = xy.y * H - 0.5f;
+      const float w_im = xy.x * W - 0.5f;
+      if ((h_im > -1.f) && (w_im > -1.f) && (h_im < H) && (w_im < W)) {
+        const float hf = floorf(h_im), wf = floorf(w_im);
+        const int h_low = static_cast<int>(hf), w_low = static_cast<int>(wf);
+        const float lh = h_im - hf, lw = w_im - wf;
+        const bool top = h_low >= 0, bot = h_low + 1 <= H - 1, lft = w_low >= 0, rgt = w_low + 1 <= W - 1;
+        const int rs = W * MD;
+        const int o1 = h_low * rs + w_low * MD;
+        offs.x = (top && lft) ? o1 : -1;
+        offs.y = (top && rgt) ? o1 + MD : -1;
+        offs.z = (bot && lft) ? o1 + rs : -1;
+        offs.w = (bot && rgt) ? o1 + rs + MD : -1;
+        if (kBackward) {
+          wv = make_float4(lh, lw, a, 0.f);
+        } else {
+          const float hh = 1.f - lh, hw = 1.f - lw;
+          wv = make_float4(hh * hw * a, hh * lw * a, lh * hw * a, lh * lw * a);
+        }
+      } else if (kBackward) {
+        wv.z = a;
+      }
+    }
+    so[j * kDescStride + p] = offs;
+    sw[j * kDescStride + p] = wv;
+  }
+}
+
 template <int LPI>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, 4)
 msda_fwd_vec_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lstart, const float* __restrict__ loc,
                     const float* __restrict__ aw, int S, int M, int L, int Lq,
                     float* __restrict__ out, const MsdaTiling tiling) {
   constexpr int D = LPI * 4;
-  constexpr int P = 4;
   constexpr int SLOTS = kThreads / LPI;
-  constexpr int MAXL = (LPI / 2) < 8 ? (LPI / 2) : 8;
-  const unsigned FULL = 0xffffffffu;
+  constexpr int ITERS = kChunkQ / SLOTS;
+  __shared__ int4 so[kChunkQ * kDescStride];
+  __shared__ float4 sw[kChunkQ * kDescStride];
 
   const int chunk = blockIdx.x, m = blockIdx.y, b = blockIdx.z;
-  const int tid = threadIdx.x;
-  const int slot = tid / LPI;
-  const int li = tid % LPI;                       // which float4 of the D channels
-  const int lane = tid & 31;
-  const int slot_lane0 = lane - li;               // first lane of this item's lane group
-  const int LP = L * P;
-  const int n_loc4 = LP / 2;                      // float4s of (x, y) pairs per item
-  const int n_aw4 = LP / 4;
-  const int MD = M * D;
-
-  int Hs[MAXL], Ws[MAXL], St[MAXL];
-#pragma unroll
-  for (int l = 0; l < MAXL; ++l) {
-    if (l < L) {
-      Hs[l] = static_cast<int>(shapes[2 * l]);
-      Ws[l] = static_cast<int>(shapes[2 * l + 1]);
-      St[l] = static_cast<int>(lstart[l]);
-    } else {
-      Hs[l] = Ws[l] = St[l] = 0;
-    }
-  }
+  const int slot = threadIdx.x / LPI, li = threadIdx.x % LPI;
+  const int MD = M * D, LP = L * 4;
   const float* vimg = value + static_cast<size_t>(b) * S * MD + m * D + li * 4;
 
-  for (int it = 0; it < kChunkQ / SLOTS; ++it) {
-    const int j = it * SLOTS + slot;
-    int q = query_of(tiling, chunk, j, Lq);
-    const bool active = q >= 0;
-    if (__all_sync(FULL, !active)) continue;       // warp-uniform skip keeps shuffles convergent
-    q = active ? q : 0;
-    const size_t item = (static_cast<size_t>(b) * Lq + q) * M + m;
-    float4 locv = make_float4(0.f, 0.f, 0.f, 0.f), awv = locv;
-    if (li < n_loc4) locv = ldg4(loc + item * LP * 2 + li * 4);
-    if (li < n_aw4) awv = ldg4(aw + item * LP + li * 4);
+  float4 acc[ITERS];
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) acc[it] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int l = 0; l < L; ++l) {
+    const int H = static_cast<int>(shapes[2 * l]), W = static_cast<int>(shapes[2 * l + 1]);
+    const float* vl = vimg + static_cast<size_t>(lstart[l]) * MD;
+    if (l > 0) __syncthreads();          // phase B of the previous level has finished reading
+    build_descriptors<false>(so, sw, loc, aw, tiling, chunk, b, m, M, Lq, LP, l, H, W, MD);
+    __syncthreads();
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int l = 0; l < MAXL; ++l) {
-      if (l < L) {
-        const int H = Hs[l], W = Ws[l];
-        const float* vl = vimg + static_cast<size_t>(St[l]) * MD;
-        const int row_stride = W * MD;
+    for (int it = 0; it < ITERS; ++it) {
+      const int j = it * SLOTS + slot;
 #pragma unroll
-        for (int p = 0; p < P; ++p) {
-          const int src = slot_lane0 + 2 * l + (p >> 1);
-          const float lx = __shfl_sync(FULL, (p & 1) ? locv.z : locv.x, src);
-          const float ly = __shfl_sync(FULL, (p & 1) ? locv.w : locv.y, src);
-          const float wgt = __shfl_sync(
-              FULL, p == 0 ? awv.x : (p == 1 ? awv.y : (p == 2 ? awv.z : awv.w)), slot_lane0 + l);
-          const float h_im = ly * H - 0.5f;
-          const float w_im = lx * W - 0.5f;
-          const bool inside = (h_im > -1.f) && (w_im > -1.f) && (h_im < H) && (w_im < W);
-          const float hf = inside ? floorf(h_im) : 0.f, wf = inside ? floorf(w_im) : 0.f;
-          const int h_low = static_cast<int>(hf), w_low = static_cast<int>(wf);
-          const float lh = h_im - hf, lw = w_im - wf;
-          const float hh = 1.f - lh, hw = 1.f - lw;
-          const bool top = inside && h_low >= 0, bot = inside && (h_low + 1 <= H - 1);
-          const bool lft = w_low >= 0, rgt = (w_low + 1 <= W - 1);
-          const int o1 = h_low * row_stride + w_low * MD;
-          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4 v1 = (top && lft) ? ldg4(vl + o1) : z;
-          const float4 v2 = (top && rgt) ? ldg4(vl + o1 + MD) : z;
-          const float4 v3 = (bot && lft) ? ldg4(vl + o1 + row_stride) : z;
-          const float4 v4 = (bot && rgt) ? ldg4(vl + o1 + row_stride + MD) : z;
-          const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
-          acc.x += wgt * (w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x);
-          acc.y += wgt * (w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y);
-          acc.z += wgt * (w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z);
-          acc.w += wgt * (w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w);
-        }
+      for (int p = 0; p < 4; ++p) {
+        const int4 o = so[j * kDescStride + p];
+        const float4 w = sw[j * kDescStride + p];
+        const float4 v1 = o.x >= 0 ? ldg4(vl + o.x) : z;
+        const float4 v2 = o.y >= 0 ? ldg4(vl + o.y) : z;
+        const float4 v3 = o.z >= 0 ? ldg4(vl + o.z) : z;
+        const float4 v4 = o.w >= 0 ? ldg4(vl + o.w) : z;
+        acc[it].x += w.x * v1.x + w.y * v2.x + w.z * v3.x + w.w * v4.x;
+        acc[it].y += w.x * v1.y + w.y * v2.y + w.z * v3.y + w.w * v4.y;
+        acc[it].z += w.x * v1.z + w.y * v2.z + w.z * v3.z + w.w * v4.z;
+        acc[it].w += w.x * v1.w + w.y * v2.w + w.z * v3.w + w.w * v4.w;
       }
     }
-    if (active) *reinterpret_cast<float4*>(out + item * D + li * 4) = acc;
+  }
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int q = query_of(tiling, chunk, it * SLOTS + slot, Lq);
+    if (q >= 0)
+      *reinterpret_cast<float4*>(out + ((static_cast<size_t>(b) * Lq + q) * M + m) * D + li * 4) = acc[it];
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Backward, vectorised (same mapping as the forward).
-// ------------------------------------------------------------------------------------------------
 template <int LPI>
 __global__ void __launch_bounds__(kThreads, 3)
 msda_bwd_vec_kernel(const float* __restrict__ grad_out, const float* __restrict__ value,
@@ -174,95 +190,60 @@ msda_bwd_vec_kernel(const float* __restrict__ grad_out, const float* __restrict_
                     int Lq, float* __restrict__ grad_value, float* __restrict__ grad_loc,
                     float* __restrict__ grad_aw, const MsdaTiling tiling) {
   constexpr int D = LPI * 4;
-  constexpr int P = 4;
   constexpr int SLOTS = kThreads / LPI;
-  constexpr int MAXL = (LPI / 2) < 8 ? (LPI / 2) : 8;
+  constexpr int ITERS = kChunkQ / SLOTS;
   const unsigned FULL = 0xffffffffu;
+  __shared__ int4 so[kChunkQ * kDescStride];
+  __shared__ float4 sw[kChunkQ * kDescStride];
 
   const int chunk = blockIdx.x, m = blockIdx.y, b = blockIdx.z;
-  const int tid = threadIdx.x;
-  const int slot = tid / LPI;
-  const int li = tid % LPI;
-  const int lane = tid & 31;
-  const int slot_lane0 = lane - li;
-  const int LP = L * P;
-  const int n_loc4 = LP / 2;
-  const int n_aw4 = LP / 4;
-  const int MD = M * D;
-
-  int Hs[MAXL], Ws[MAXL], St[MAXL];
-#pragma unroll
-  for (int l = 0; l < MAXL; ++l) {
-    if (l < L) {
-      Hs[l] = static_cast<int>(shapes[2 * l]);
-      Ws[l] = static_cast<int>(shapes[2 * l + 1]);
-      St[l] = static_cast<int>(lstart[l]);
-    } else {
-      Hs[l] = Ws[l] = St[l] = 0;
-    }
-  }
+  const int slot = threadIdx.x / LPI, li = threadIdx.x % LPI;
+  const int MD = M * D, LP = L * 4;
   const size_t img_off = static_cast<size_t>(b) * S * MD + m * D + li * 4;
   const float* vimg = value + img_off;
   float* gvimg = grad_value + img_off;
 
-  for (int it = 0; it < kChunkQ / SLOTS; ++it) {
-    const int j = it * SLOTS + slot;
-    int q = query_of(tiling, chunk, j, Lq);
-    const bool active = q >= 0;
-    if (__all_sync(FULL, !active)) continue;
-    q = active ? q : 0;
-    const size_t item = (static_cast<size_t>(b) * Lq + q) * M + m;
-    float4 locv = make_float4(0.f, 0.f, 0.f, 0.f), awv = locv;
-    if (li < n_loc4) locv = ldg4(loc + item * LP * 2 + li * 4);
-    if (li < n_aw4) awv = ldg4(aw + item * LP + li * 4);
-    float4 g = ldg4(grad_out + item * D + li * 4);
-    if (!active) g = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 g[ITERS];
+  size_t item[ITERS];
+  bool active[ITERS];
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int q = query_of(tiling, chunk, it * SLOTS + slot, Lq);
+    active[it] = q >= 0;
+    item[it] = (static_cast<size_t>(b) * Lq + (active[it] ? q : 0)) * M + m;
+    g[it] = active[it] ? ldg4(grad_out + item[it] * D + li * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
 
-    float4 gloc_out = make_float4(0.f, 0.f, 0.f, 0.f);  // this lane's float4 of grad_loc
-    float4 gaw_out = make_float4(0.f, 0.f, 0.f, 0.f);   // this lane's float4 of grad_aw
+  for (int l = 0; l < L; ++l) {
+    const int H = static_cast<int>(shapes[2 * l]), W = static_cast<int>(shapes[2 * l + 1]);
+    const size_t loff = static_cast<size_t>(lstart[l]) * MD;
+    const float* vl = vimg + loff;
+    float* gvl = gvimg + loff;
+    if (l > 0) __syncthreads();
+    build_descriptors<true>(so, sw, loc, aw, tiling, chunk, b, m, M, Lq, LP, l, H, W, MD);
+    __syncthreads();
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int l = 0; l < MAXL; ++l) {
-      if (l < L) {
-        const int H = Hs[l], W = Ws[l];
-        const size_t loff = static_cast<size_t>(St[l]) * MD;
-        const float* vl = vimg + loff;
-        float* gvl = gvimg + loff;
-        const int row_stride = W * MD;
+    for (int it = 0; it < ITERS; ++it) {
+      const int j = it * SLOTS + slot;
+      float mine_x = 0.f, mine_y = 0.f, mine_a = 0.f;      // results of point p == li (lanes 0..3)
 #pragma unroll
-        for (int p = 0; p < P; ++p) {
-          const int src = slot_lane0 + 2 * l + (p >> 1);
-          const float lx = __shfl_sync(FULL, (p & 1) ? locv.z : locv.x, src);
-          const float ly = __shfl_sync(FULL, (p & 1) ? locv.w : locv.y, src);
-          const float wgt = __shfl_sync(
-              FULL, p == 0 ? awv.x : (p == 1 ? awv.y : (p == 2 ? awv.z : awv.w)), slot_lane0 + l);
-          const float h_im = ly * H - 0.5f;
-          const float w_im = lx * W - 0.5f;
-          const bool inside = (h_im > -1.f) && (w_im > -1.f) && (h_im < H) && (w_im < W);
-          const float hf = inside ? floorf(h_im) : 0.f, wf = inside ? floorf(w_im) : 0.f;
-          const int h_low = static_cast<int>(hf), w_low = static_cast<int>(wf);
-          const float lh = h_im - hf, lw = w_im - wf;
-          const float hh = 1.f - lh, hw = 1.f - lw;
-          const bool top = inside && h_low >= 0, bot = inside && (h_low + 1 <= H - 1);
-          const bool lft = w_low >= 0, rgt = (w_low + 1 <= W - 1);
-          const int o1 = h_low * row_stride + w_low * MD;
-          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-          const bool c1 = top && lft, c2 = top && rgt, c3 = bot && lft, c4 = bot && rgt;
-          const float4 v1 = c1 ? ldg4(vl + o1) : z;
-          const float4 v2 = c2 ? ldg4(vl + o1 + MD) : z;
-          const float4 v3 = c3 ? ldg4(vl + o1 + row_stride) : z;
-          const float4 v4 = c4 ? ldg4(vl + o1 + row_stride + MD) : z;
-          const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
-          // top_grad_value = grad_out * attn_weight  (ref cuh:116)
-          const float4 tg = make_float4(g.x * wgt, g.y * wgt, g.z * wgt, g.w * wgt);
-          if (active) {
-            if (c1) red_add_v4(gvl + o1, w1 * tg.x, w1 * tg.y, w1 * tg.z, w1 * tg.w);
-            if (c2) red_add_v4(gvl + o1 + MD, w2 * tg.x, w2 * tg.y, w2 * tg.z, w2 * tg.w);
-            if (c3) red_add_v4(gvl + o1 + row_stride, w3 * tg.x, w3 * tg.y, w3 * tg.z, w3 * tg.w);
-            if (c4)
-              red_add_v4(gvl + o1 + row_stride + MD, w4 * tg.x, w4 * tg.y, w4 * tg.z, w4 * tg.w);
-          }
-          // d/d(h_im), d/d(w_im) of the bilinear value, per channel (ref cuh:119-157)
-          float gh = 0.f, gw = 0.f, ga = 0.f;
+      for (int p = 0; p < 4; ++p) {
+        const int4 o = so[j * kDescStride + p];
+        const float4 d = sw[j * kDescStride + p];         // (lh, lw, attention weight, -)
+        const float lh = d.x, lw = d.y, wgt = d.z;
+        const float hh = 1.f - lh, hw = 1.f - lw;
+        const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+        const float4 v1 = o.x >= 0 ? ldg4(vl + o.x) : z;
+        const float4 v2 = o.y >= 0 ? ldg4(vl + o.y) : z;
+        const float4 v3 = o.z >= 0 ? ldg4(vl + o.z) : z;
+        const float4 v4 = o.w >= 0 ? ldg4(vl + o.w) : z;
+        const float4 tg = make_float4(g[it].x * wgt, g[it].y * wgt, g[it].z * wgt, g[it].w * wgt);  // ref cuh:116
+        if (o.x >= 0) red_add_v4(gvl + o.x, w1 * tg.x, w1 * tg.y, w1 * tg.z, w1 * tg.w);
+        if (o.y >= 0) red_add_v4(gvl + o.y, w2 * tg.x, w2 * tg.y, w2 * tg.z, w2 * tg.w);
+        if (o.z >= 0) red_add_v4(gvl + o.z, w3 * tg.x, w3 * tg.y, w3 * tg.z, w3 * tg.w);
+        if (o.w >= 0) red_add_v4(gvl + o.w, w4 * tg.x, w4 * tg.y, w4 * tg.z, w4 * tg.w);
+        float gh = 0.f, gw = 0.f, ga = 0.f;                // ref cuh:119-161, per channel then summed
 #define MPF_ACC(comp)                                                                         \
   {                                                                                           \
     const float ghw = -hw * v1.comp - lw * v2.comp + hw * v3.comp + lw * v4.comp;             \
@@ -270,33 +251,23 @@ msda_bwd_vec_kernel(const float* __restrict__ grad_out, const float* __restrict_
     const float val = w1 * v1.comp + w2 * v2.comp + w3 * v3.comp + w4 * v4.comp;              \
     gh += ghw * tg.comp;                                                                      \
     gw += gww * tg.comp;                                                                      \
-    ga += val * g.comp;                                                                       \
+    ga += val * g[it].comp;                                                                   \
   }
-          MPF_ACC(x) MPF_ACC(y) MPF_ACC(z) MPF_ACC(w)
+        MPF_ACC(x) MPF_ACC(y) MPF_ACC(z) MPF_ACC(w)
 #undef MPF_ACC
 #pragma unroll
-          for (int o = LPI / 2; o >= 1; o >>= 1) {
-            gh += __shfl_xor_sync(FULL, gh, o);
-            gw += __shfl_xor_sync(FULL, gw, o);
-            ga += __shfl_xor_sync(FULL, ga, o);
-          }
-          const float glx = W * gw, gly = H * gh;  // ref cuh:162-163
-          if (li == 2 * l + (p >> 1)) {
-            if (p & 1) { gloc_out.z = glx; gloc_out.w = gly; }
-            else       { gloc_out.x = glx; gloc_out.y = gly; }
-          }
-          if (li == l) {
-            if (p == 0) gaw_out.x = ga;
-            else if (p == 1) gaw_out.y = ga;
-            else if (p == 2) gaw_out.z = ga;
-            else gaw_out.w = ga;
-          }
+        for (int off = LPI / 2; off >= 1; off >>= 1) {
+          gh += __shfl_xor_sync(FULL, gh, off);
+          gw += __shfl_xor_sync(FULL, gw, off);
+          ga += __shfl_xor_sync(FULL, ga, off);
         }
+        if (li == p) { mine_x = W * gw; mine_y = H * gh; mine_a = ga; }   // ref cuh:162-163
       }
-    }
-    if (active) {
-      if (li < n_loc4) *reinterpret_cast<float4*>(grad_loc + item * LP * 2 + li * 4) = gloc_out;
-      if (li < n_aw4) *reinterpret_cast<float4*>(grad_aw + item * LP + li * 4) = gaw_out;
+      if (active[it] && li < 4) {
+        const size_t s = item[it] * LP + l * 4 + li;
+        *reinterpret_cast<float2*>(grad_loc + 2 * s) = make_float2(mine_x, mine_y);
+        grad_aw[s] = mine_a;
+      }
     }
   }
 }
@@ -428,7 +399,7 @@ static bool vec_path_ok(int D, int L, int P, int M, int B, int* lpi) {
   if (P != 4 || D % 4 != 0) return false;
   const int l = D / 4;
   if (l != 4 && l != 8 && l != 16) return false;
-  if (2 * L > l || L > kMaxTiledLevels) return false;
+  if (L > kMaxTiledLevels) return false;
   if (M > 65535 || B > 65535) return false;
   *lpi = l;
   return true;

@@ -27,9 +27,9 @@ def cpu_pack_bits(mask):
     return torch.where(v >= 2 ** 31, v - 2 ** 32, v).to(torch.int32)
 
 
-@pytest.fixture()
-def cpu_ops(monkeypatch):
-    """Replaces every native kernel launcher by a CPU torch equivalent (test-only)."""
+def install_cpu_ops(setattr_fn):
+    """Replaces every native kernel launcher by a CPU torch equivalent (test-only).
+    ``setattr_fn(obj, name, value)`` performs the patch (pytest's monkeypatch.setattr or plain setattr)."""
     import torch.nn.functional as F
     from mp_former_b200 import native, ops
 
@@ -55,13 +55,18 @@ def cpu_ops(monkeypatch):
                   nhead, am)
         return y.transpose(0, 1)
 
-    monkeypatch.setattr(MSDA, "ms_deform_attn_forward", fwd)
-    monkeypatch.setattr(_lib, "require_cuda", lambda t, n: None)
-    monkeypatch.setattr(ops, "linear", linear)
-    monkeypatch.setattr(ops, "mask_logits", lambda e, f: torch.einsum("bqc,bchw->bqhw", e, f))
-    monkeypatch.setattr(native, "attn_mask_bits", attn_mask_bits)
-    monkeypatch.setattr(native, "pack_bool_bits", cpu_pack_bits)
-    monkeypatch.setattr(ops, "masked_cross_attention", xattn)
+    setattr_fn(MSDA, "ms_deform_attn_forward", fwd)
+    setattr_fn(_lib, "require_cuda", lambda t, n: None)
+    setattr_fn(ops, "linear", linear)
+    setattr_fn(ops, "mask_logits", lambda e, f: torch.einsum("bqc,bchw->bqhw", e, f))
+    setattr_fn(native, "attn_mask_bits", attn_mask_bits)
+    setattr_fn(native, "pack_bool_bits", cpu_pack_bits)
+    setattr_fn(ops, "masked_cross_attention", xattn)
+
+
+@pytest.fixture()
+def cpu_ops(monkeypatch):
+    install_cpu_ops(monkeypatch.setattr)
 
 
 def build_pixel_decoder():
