@@ -1,0 +1,107 @@
+"""Forward of the hot path at bs=16, 1024x1024 on one GPU: this package vs the STOCK path.
+
+"Stock" = what the reference executes on a GPU: its eager-PyTorch module code (here: the oracle's
+restatement oracle/torch_oracle.py run on CUDA tensors -- same library calls: conv/GroupNorm/Linear
+(fp32 SIMT cuBLAS, TF32 off), baddbmm/softmax/bmm attention with a materialised [B*8,Q,HW] mask, einsum,
+interpolate/sigmoid) with the UNMODIFIED reference MSDeformAttn CUDA kernel (oracle/_ref/libmsda_stock.so,
+built from /root/reference's .cuh at build time) plugged into msda_core.  The reference tree itself does not
+exist on the GPU box, hence the restatement; it is pinned to the reference by tests/golden.
+Prints one JSON line (north_star target: >= 5x)."""
+import ctypes
+import json
+import os
+import statistics
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import mp_former_b200 as M  # noqa: E402
+from mp_former_b200 import workload  # noqa: E402
+from oracle import torch_oracle as O  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def stock_msda():
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libmsda_stock.so"))
+    vp, i = ctypes.c_void_p, ctypes.c_int
+    lib.ref_msda_forward_f32.argtypes = [vp] * 5 + [i] * 7 + [vp, vp]
+
+    def msda_core(value, shapes, loc, aw):
+        N, S, Mh, D = value.shape
+        Lq, L, P = loc.shape[1], loc.shape[3], loc.shape[4]
+        st = torch.as_tensor(shapes, dtype=torch.long, device=value.device)
+        lsi = torch.cat((st.new_zeros((1,)), st.prod(1).cumsum(0)[:-1]))
+        out = torch.zeros(N, Lq, Mh * D, device=value.device)         # reference zero-fills (cuda.cu:59)
+        value, loc, aw = value.contiguous(), loc.contiguous(), aw.contiguous()
+        rc = lib.ref_msda_forward_f32(value.data_ptr(), st.data_ptr(), lsi.data_ptr(), loc.data_ptr(),
+                                      aw.data_ptr(), N, S, Mh, D, L, Lq, P, out.data_ptr(),
+                                      torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+        return out
+    return msda_core
+
+
+def timeit(fn, reps, warm=2):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return statistics.median(ts)
+
+
+def main():
+    B = int(os.environ.get("MPF_B", "16"))
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    pd, dec = workload.build_head(device=DEV, seed=0)
+    pd.eval(); dec.eval()
+    feats = workload.synthetic_features(B, device=DEV)
+    psd = {k: v.detach() for k, v in pd.state_dict().items()}
+    dsd = {k: v.detach() for k, v in dec.state_dict().items()}
+    O.msda_core = stock_msda()
+
+    @torch.no_grad()
+    def ours():
+        mf, _, ms = pd.forward_features(feats)
+        return dec(ms, mf)
+
+    @torch.no_grad()
+    def stock():
+        mf, _, ms = O.pixel_decoder_forward(psd, feats)
+        return O.decoder_forward(dsd, ms, mf, num_queries=100)
+
+    a, b = ours(), stock()
+    err = ((a["pred_masks"] - b["pred_masks"]).abs() / b["pred_masks"].abs().clamp(min=1.0)).max().item()
+    err_l = ((a["pred_logits"] - b["pred_logits"]).abs() / b["pred_logits"].abs().clamp(min=1.0)).max().item()
+    t_ours = timeit(ours, 5)
+    t_stock = timeit(stock, 3)
+
+    @torch.no_grad()
+    def ours_pd():
+        return pd.forward_features(feats)
+
+    @torch.no_grad()
+    def stock_pd():
+        return O.pixel_decoder_forward(psd, feats)
+    t_ours_pd, t_stock_pd = timeit(ours_pd, 5), timeit(stock_pd, 3)
+    print(json.dumps({
+        "what": "forward only, pixel decoder + 9-layer masked decoder, eval (no DN), fp32, TF32 off",
+        "B": B, "ours_ms": t_ours, "stock_ms": t_stock, "speedup": t_stock / t_ours,
+        "ours_img_s": B / t_ours * 1e3, "stock_img_s": B / t_stock * 1e3,
+        "pixel_decoder_only": {"ours_ms": t_ours_pd, "stock_ms": t_stock_pd, "speedup": t_stock_pd / t_ours_pd},
+        "decoder_only": {"ours_ms": t_ours - t_ours_pd, "stock_ms": t_stock - t_stock_pd,
+                         "speedup": (t_stock - t_stock_pd) / max(1e-9, t_ours - t_ours_pd)},
+        "max_rel_diff_pred_masks": err, "max_rel_diff_pred_logits": err_l,
+    }), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,42 @@
+"""torch.profiler breakdown of one bench step (which aten ops / custom Functions own the device time)."""
+import os
+import sys
+
+import torch
+from torch.profiler import ProfilerActivity, profile, record_function
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from bench import pseudo_loss  # noqa: E402
+from mp_former_b200 import workload  # noqa: E402
+
+DEV = "cuda:0"
+B = int(os.environ.get("MPF_B", "16"))
+torch.backends.cuda.matmul.allow_tf32 = False
+torch.backends.cudnn.allow_tf32 = False
+pd, dec = workload.build_head(device=DEV)
+feats = workload.synthetic_features(B, device=DEV)
+dn = {"tgt": workload.synthetic_targets(B, device=DEV), "scalar": 1, "noise_scale": 0.0}
+params = list(pd.parameters()) + list(dec.parameters())
+
+
+def step():
+    for p in params:
+        p.grad = None
+    with record_function("FWD_pixel_decoder"):
+        mf, _, ms = pd.forward_features(feats)
+    with record_function("FWD_decoder"):
+        out = dec(ms, mf, None, dn)
+    with record_function("LOSS"):
+        loss = pseudo_loss(out)
+    with record_function("BWD"):
+        loss.backward()
+
+
+for _ in range(2):
+    step()
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+    step()
+    torch.cuda.synchronize()
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=60))

@@ -202,17 +202,17 @@ class _MaskedCrossAttention(torch.autograd.Function):
         q = F.linear(q_in, wq, b_in[:E])
         k = F.linear(kin, wk, b_in[E:2 * E])
         v = F.linear(memory, wv, b_in[2 * E:])
-        qh, kh, vh = _split_heads(q, nhead), _split_heads(k, nhead), _split_heads(v, nhead)
-        s2 = torch.matmul(qh, kh.transpose(-1, -2)) * (inv * LOG2E)                 # [B,h,Q,HW] log2 domain
-        p = torch.exp2(s2 - lse2.unsqueeze(-1))
+        qh, kh, vh = _split_heads(q * inv, nhead), _split_heads(k, nhead), _split_heads(v, nhead)
         masked = native.unpack_bits(bits, ctx.n_keys) & ~row_open.unsqueeze(-1)     # [B,Q,HW]
-        p = p.masked_fill(masked.unsqueeze(1), 0.0)
-        goh, oh = _split_heads(go, nhead), _split_heads(o, nhead)
+        s = torch.matmul(qh, kh.transpose(-1, -2))                                   # [B,h,Q,HW]
+        p = torch.softmax(s.masked_fill_(masked.unsqueeze(1), float("-inf")), -1)
+        del s
+        goh = _split_heads(go, nhead)
         gv = torch.matmul(p.transpose(-1, -2), goh)                                  # [B,h,HW,hd]
         gp = torch.matmul(goh, vh.transpose(-1, -2))                                 # [B,h,Q,HW]
-        delta = (goh * oh).sum(-1, keepdim=True)
-        gs = p * (gp - delta) * inv
-        gq = torch.matmul(gs, kh)                                                    # [B,h,Q,hd]
+        gs = torch._softmax_backward_data(gp, p, -1, torch.float32)                  # p * (gp - sum(gp*p))
+        del gp, p
+        gq = torch.matmul(gs, kh) * inv                                              # [B,h,Q,hd] wrt unscaled q
         gk = torch.matmul(gs.transpose(-1, -2), qh)                                  # [B,h,HW,hd]
         gq = gq.transpose(1, 2).reshape(B * Qt, E)
         gk = gk.transpose(1, 2).reshape(B * HW, E)

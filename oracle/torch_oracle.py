@@ -38,8 +38,8 @@ def msda_core(value, spatial_shapes, sampling_locations, attention_weights):
     _, Lq, _, L, P, _ = sampling_locations.shape
     out = value.new_zeros(N, Lq, M, D)
     start = 0
-    b_idx = torch.arange(N).view(N, 1, 1, 1).expand(N, Lq, M, P)
-    m_idx = torch.arange(M).view(1, 1, M, 1).expand(N, Lq, M, P)
+    b_idx = torch.arange(N, device=value.device).view(N, 1, 1, 1).expand(N, Lq, M, P)
+    m_idx = torch.arange(M, device=value.device).view(1, 1, M, 1).expand(N, Lq, M, P)
     for l, (H, W) in enumerate(shapes):
         v = value[:, start:start + H * W].reshape(N, H, W, M, D)
         start += H * W
@@ -65,15 +65,15 @@ def msda_core(value, spatial_shapes, sampling_locations, attention_weights):
 # --------------------------------------------------------------------------------------------
 # a8: sine position embedding
 # --------------------------------------------------------------------------------------------
-def position_embedding_sine(B, H, W, num_pos_feats=128, temperature=10000, scale=2 * math.pi,
+def position_embedding_sine(B, H, W, num_pos_feats=128, temperature=10000, scale=2 * math.pi, device=None,
                             dtype=torch.float32):
     """ref: transformer_decoder/position_encoding.py:29-52 with mask=None, normalize=True."""
-    y_embed = torch.arange(1, H + 1, dtype=torch.float32).view(1, H, 1).expand(B, H, W)
-    x_embed = torch.arange(1, W + 1, dtype=torch.float32).view(1, 1, W).expand(B, H, W)
+    y_embed = torch.arange(1, H + 1, dtype=torch.float32, device=device).view(1, H, 1).expand(B, H, W)
+    x_embed = torch.arange(1, W + 1, dtype=torch.float32, device=device).view(1, 1, W).expand(B, H, W)
     eps = 1e-6
     y_embed = y_embed / (y_embed[:, -1:, :] + eps) * scale
     x_embed = x_embed / (x_embed[:, :, -1:] + eps) * scale
-    dim_t = torch.arange(num_pos_feats, dtype=torch.float32)
+    dim_t = torch.arange(num_pos_feats, dtype=torch.float32, device=device)
     dim_t = temperature ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / num_pos_feats)
     pos_x = x_embed[:, :, :, None] / dim_t
     pos_y = y_embed[:, :, :, None] / dim_t
@@ -102,7 +102,7 @@ def msdeform_attn_module(sd, prefix, query, reference_points, input_flatten, sha
     off = _lin(sd, prefix + "sampling_offsets", query).view(N, Lq, n_heads, L, n_points, 2)
     aw = _lin(sd, prefix + "attention_weights", query).view(N, Lq, n_heads, L * n_points)
     aw = F.softmax(aw, -1).view(N, Lq, n_heads, L, n_points)
-    normalizer = torch.tensor([[w, h] for h, w in shapes], dtype=query.dtype)
+    normalizer = torch.tensor([[w, h] for h, w in shapes], dtype=query.dtype, device=query.device)
     loc = reference_points[:, :, None, :, None, :] + off / normalizer[None, None, None, :, None, :]
     out = msda_core(value, shapes, loc, aw)
     return _lin(sd, prefix + "output_proj", out)
@@ -111,12 +111,12 @@ def msdeform_attn_module(sd, prefix, query, reference_points, input_flatten, sha
 # --------------------------------------------------------------------------------------------
 # a6/a7: pixel decoder
 # --------------------------------------------------------------------------------------------
-def encoder_reference_points(shapes, B, dtype=torch.float32):
+def encoder_reference_points(shapes, B, dtype=torch.float32, device=None):
     """ref: pixel_decoder/msdeformattn.py:141-153 with valid_ratios == 1."""
     pts = []
     for H, W in shapes:
-        ry = torch.linspace(0.5, H - 0.5, H, dtype=torch.float32) / H
-        rx = torch.linspace(0.5, W - 0.5, W, dtype=torch.float32) / W
+        ry = torch.linspace(0.5, H - 0.5, H, dtype=torch.float32, device=device) / H
+        rx = torch.linspace(0.5, W - 0.5, W, dtype=torch.float32, device=device) / W
         gy, gx = torch.meshgrid(ry, rx, indexing="ij")
         pts.append(torch.stack((gx.reshape(-1), gy.reshape(-1)), -1))
     ref = torch.cat(pts, 0)[None].expand(B, -1, -1)                    # [B,S,2]
@@ -135,17 +135,17 @@ def pixel_decoder_forward(sd, features, *, transformer_in_features=("res3", "res
         y = F.conv2d(x, sd[f"{p}input_proj.{idx}.0.weight"], sd[f"{p}input_proj.{idx}.0.bias"])
         y = F.group_norm(y, 32, sd[f"{p}input_proj.{idx}.1.weight"], sd[f"{p}input_proj.{idx}.1.bias"])
         srcs.append(y)
-        poss.append(position_embedding_sine(x.shape[0], x.shape[2], x.shape[3], y.shape[1] // 2))
+        poss.append(position_embedding_sine(x.shape[0], x.shape[2], x.shape[3], y.shape[1] // 2, device=x.device))
     B, C = srcs[0].shape[:2]
     shapes = [(s.shape[2], s.shape[3]) for s in srcs]
     src = torch.cat([s.flatten(2).transpose(1, 2) for s in srcs], 1)
     lvl = sd[p + "transformer.level_embed"]
     pos = torch.cat([q.flatten(2).transpose(1, 2) + lvl[i].view(1, 1, -1) for i, q in enumerate(poss)], 1)
-    ref = encoder_reference_points(shapes, B)
+    ref = encoder_reference_points(shapes, B, device=src.device)
     for i in range(enc_layers):
         lp = f"{p}transformer.encoder.layers.{i}."
         src2 = msdeform_attn_module(sd, lp + "self_attn.", src + pos, ref, src, shapes, n_heads, n_points,
-                                    padding_mask=torch.zeros(B, src.shape[1], dtype=torch.bool))
+                                    padding_mask=torch.zeros(B, src.shape[1], dtype=torch.bool, device=src.device))
         src = F.layer_norm(src + src2, (C,), sd[lp + "norm1.weight"], sd[lp + "norm1.bias"])
         ff = _lin(sd, lp + "linear2", F.relu(_lin(sd, lp + "linear1", src)))
         src = F.layer_norm(src + ff, (C,), sd[lp + "norm2.weight"], sd[lp + "norm2.bias"])
@@ -245,7 +245,7 @@ def decoder_forward(sd, x, mask_features, *, num_queries, n_heads=8, dec_layers=
     for i in range(3):
         H, W = x[i].shape[-2:]
         size_list.append((H, W))
-        pos.append(position_embedding_sine(B, H, W, C // 2).flatten(2).permute(2, 0, 1))
+        pos.append(position_embedding_sine(B, H, W, C // 2, device=x[i].device).flatten(2).permute(2, 0, 1))
         src.append((x[i].flatten(2) + lvl[i][None, :, None]).permute(2, 0, 1))
     qf = sd[p + "query_feat.weight"]
     tgt_mask, dn_meta, known = None, None, None
@@ -266,8 +266,8 @@ def decoder_forward(sd, x, mask_features, *, num_queries, n_heads=8, dec_layers=
         pad_size = scalar * max_num
         dn_meta = {"max_num": max_num, "pad_size": pad_size}
         hw0 = size_list[0][0] * size_list[0][1]
-        padding = torch.zeros(B, pad_size, C)
-        padding_mask = torch.ones(B, pad_size, hw0).bool()
+        padding = torch.zeros(B, pad_size, C, device=x[0].device)
+        padding_mask = torch.ones(B, pad_size, hw0, dtype=torch.bool, device=x[0].device)
         masks = _dn_noise(_dn_gt_masks(targets, size_list[0], scalar), noise_scale, hw0)
         labels = torch.cat([t["labels"] for t in targets])
         known_labels = labels.repeat(scalar, 1).view(-1).clone()
@@ -278,7 +278,7 @@ def decoder_forward(sd, x, mask_features, *, num_queries, n_heads=8, dec_layers=
         feats = sd[p + "label_enc.weight"][known_labels]
         batch_idx = torch.cat([torch.full_like(t["labels"].long(), i) for i, t in enumerate(targets)])
         known_bid = batch_idx.repeat(scalar, 1).view(-1)
-        idx = torch.cat([torch.arange(n) for n in num_boxes])
+        idx = torch.cat([torch.arange(n, device=x[0].device) for n in num_boxes])
         map_idx = torch.cat([idx + single_pad * i for i in range(scalar)]).long()
         known = (known_bid, map_idx)
         padding[known] = feats
@@ -290,7 +290,7 @@ def decoder_forward(sd, x, mask_features, *, num_queries, n_heads=8, dec_layers=
         attn_mask[:, :, :-num_queries] = padding_mask
         attn_mask = attn_mask.flatten(0, 1)
         tgt_size = pad_size + num_queries
-        tgt_mask = torch.zeros(tgt_size, tgt_size, dtype=torch.bool)
+        tgt_mask = torch.zeros(tgt_size, tgt_size, dtype=torch.bool, device=x[0].device)
         tgt_mask[pad_size:, :pad_size] = True
         for i in range(scalar):
             tgt_mask[single_pad * i:single_pad * (i + 1), single_pad * (i + 1):pad_size] = True
@@ -315,7 +315,7 @@ def decoder_forward(sd, x, mask_features, *, num_queries, n_heads=8, dec_layers=
         outputs_class, outputs_mask, attn_mask = prediction_heads(sd, p, output, mask_features, size_list[level], n_heads)
         if dn_args is not None and (all_lys or i < 3):
             hw = size_list[level][0] * size_list[level][1]
-            pm = torch.ones(B, dn_meta["pad_size"], hw).bool()
+            pm = torch.ones(B, dn_meta["pad_size"], hw, dtype=torch.bool, device=x[0].device)
             pm[known] = _dn_noise(_dn_gt_masks(dn_args["tgt"], size_list[level], scalar), dn_args["noise_scale"], hw)
             pm = pm.unsqueeze(1).repeat(1, n_heads, 1, 1)
             attn_mask = attn_mask.view(B, n_heads, -1, attn_mask.shape[-1])
