@@ -137,6 +137,20 @@ int mpf_gemm_tf32x3_ex(const float* A, long long lda, long long a_batch_stride, 
                        long long resid_ld, int resid_rows, int resid_cols, float alpha, int batch, int M,
                        int N, int K, int relu, int transpose_c, void* stream);
 
+/* General form: either operand may be "MN-major" (a_mn_major / b_mn_major != 0), i.e. stored
+ * [batch, K rows, M-or-N contiguous] -- the transpose of the default [batch, M-or-N rows, K contiguous] --
+ * and B may be plain fp32 (B_lo == NULL: it is split into TF32 halves in shared memory like A).
+ * With both operands MN-major this computes dW = dY^T X (weight gradient of an nn.Linear, reduction over
+ * the token dimension; the batch dimension then enumerates K-splits whose partial products the caller
+ * sums) and dF = dOut^T E of the mask-logit einsum without any transposed copy.  K need not be a
+ * multiple of 32 (the tail is zero-filled by TMA).  lda / ldb are the row strides of the stored layout. */
+int mpf_gemm_tf32x3_general(const float* A, int a_mn_major, long long lda, long long a_batch_stride,
+                            const float* B, const float* B_lo, int b_mn_major, long long ldb,
+                            long long b_batch_stride, const float* bias, float* C, float* C_lo,
+                            long long ldc, long long c_batch_stride, const float* resid, long long resid_ld,
+                            int resid_rows, int resid_cols, float alpha, int batch, int M, int N, int K,
+                            int relu, int transpose_c, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Boolean stage of the prediction heads, bit-packed:
  *   bits[row][j] bit i = ( sigmoid( bilinear_resize(logits[row], (h,w), align_corners=False) )[32j+i] < 0.5 )

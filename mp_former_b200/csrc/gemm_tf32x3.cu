@@ -68,7 +68,11 @@ __device__ __forceinline__ float rn_tf32(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
-template <int BN>
+// A_MN / B_MN: the operand is "MN-major" -- stored [K rows][M (or N) contiguous] in global memory, i.e.
+// the transpose of the K-major case -- and is fed to the tensor core through MN-major shared-memory
+// descriptors, so weight gradients (dW = dY^T X) and the like need no transposed copies.
+// SPLIT_B: B arrives as plain fp32 and is split into hi/lo in shared memory like A (tmBlo unused).
+template <int BN, bool A_MN, bool B_MN, bool SPLIT_B>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                    const __grid_constant__ CUtensorMap tmBlo, const GemmArgs g) {
@@ -124,10 +128,26 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * Cfg::kStageBytes;
-          mbar_arrive_expect_tx(&full[stage], kABytes + 2 * Cfg::kBBytes);
-          tma_load_3d(st, &tmA, &full[stage], kb * kBK, m_t * kBM, b);
-          tma_load_3d(st + 2 * kABytes, &tmBhi, &full[stage], kb * kBK, n_t * BN, b);
-          tma_load_3d(st + 2 * kABytes + Cfg::kBBytes, &tmBlo, &full[stage], kb * kBK, n_t * BN, b);
+          mbar_arrive_expect_tx(&full[stage], kABytes + (SPLIT_B ? 1 : 2) * Cfg::kBBytes);
+          if (A_MN) {          // [32 k-rows x 32 m] boxes of 4 KiB, one per 32-wide slice of M
+#pragma unroll
+            for (int i = 0; i < kBM / 32; ++i)
+              tma_load_3d(st + i * 4096, &tmA, &full[stage], m_t * kBM + i * 32, kb * kBK, b);
+          } else {
+            tma_load_3d(st, &tmA, &full[stage], kb * kBK, m_t * kBM, b);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int i = 0; i < BN / 32; ++i) {
+              tma_load_3d(st + 2 * kABytes + i * 4096, &tmBhi, &full[stage], n_t * BN + i * 32, kb * kBK, b);
+              if (!SPLIT_B)
+                tma_load_3d(st + 2 * kABytes + Cfg::kBBytes + i * 4096, &tmBlo, &full[stage], n_t * BN + i * 32,
+                            kb * kBK, b);
+            }
+          } else {
+            tma_load_3d(st + 2 * kABytes, &tmBhi, &full[stage], kb * kBK, n_t * BN, b);
+            if (!SPLIT_B) tma_load_3d(st + 2 * kABytes + Cfg::kBBytes, &tmBlo, &full[stage], kb * kBK, n_t * BN, b);
+          }
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
       }
@@ -135,7 +155,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      constexpr uint32_t idesc = idesc_tf32(kBM, BN);
+      constexpr uint32_t idesc = idesc_tf32(kBM, BN) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -154,9 +174,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const uint32_t b_lo = b_hi + Cfg::kBBytes;
 #pragma unroll
           for (int k = 0; k < kBK / kUmmaK; ++k) {
-            const uint32_t ko = k * kUmmaK * 4;      // bytes along K inside the 128-B swizzle row
-            const uint64_t dah = smem_desc_sw128_kmajor(a_hi + ko), dal = smem_desc_sw128_kmajor(a_lo + ko);
-            const uint64_t dbh = smem_desc_sw128_kmajor(b_hi + ko), dbl = smem_desc_sw128_kmajor(b_lo + ko);
+            // K-major: advance 32 bytes inside the 128-B swizzle row; MN-major: one 8-row (1 KiB) atom
+            const uint32_t koa = A_MN ? k * 1024 : k * kUmmaK * 4;
+            const uint32_t kob = B_MN ? k * 1024 : k * kUmmaK * 4;
+            const uint64_t dah = A_MN ? smem_desc_sw128_mnmajor(a_hi + koa) : smem_desc_sw128_kmajor(a_hi + koa);
+            const uint64_t dal = A_MN ? smem_desc_sw128_mnmajor(a_lo + koa) : smem_desc_sw128_kmajor(a_lo + koa);
+            const uint64_t dbh = B_MN ? smem_desc_sw128_mnmajor(b_hi + kob) : smem_desc_sw128_kmajor(b_hi + kob);
+            const uint64_t dbl = B_MN ? smem_desc_sw128_mnmajor(b_lo + kob) : smem_desc_sw128_kmajor(b_lo + kob);
             mma_tf32_ss(d_tmem, dal, dbh, idesc, (kb | k) ? 1u : 0u);
             mma_tf32_ss(d_tmem, dah, dbl, idesc, 1u);
             mma_tf32_ss(d_tmem, dah, dbh, idesc, 1u);
@@ -188,6 +212,20 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           lo.z = rn_tf32(x.z - hi.z); lo.w = rn_tf32(x.w - hi.w);
           *reinterpret_cast<float4*>(a + off) = hi;
           *reinterpret_cast<float4*>(a + kABytes + off) = lo;
+        }
+        if (SPLIT_B) {
+          uint8_t* bt = a + 2 * kABytes;
+#pragma unroll
+          for (int i = 0; i < Cfg::kBBytes / 16 / 128; ++i) {
+            const int off = (st_id + i * 128) * 16;
+            const float4 x = *reinterpret_cast<const float4*>(bt + off);
+            float4 hi, lo;
+            hi.x = rn_tf32(x.x); hi.y = rn_tf32(x.y); hi.z = rn_tf32(x.z); hi.w = rn_tf32(x.w);
+            lo.x = rn_tf32(x.x - hi.x); lo.y = rn_tf32(x.y - hi.y);
+            lo.z = rn_tf32(x.z - hi.z); lo.w = rn_tf32(x.w - hi.w);
+            *reinterpret_cast<float4*>(bt + off) = hi;
+            *reinterpret_cast<float4*>(bt + Cfg::kBBytes + off) = lo;
+          }
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -344,21 +382,21 @@ int sm_count() {
   return n;
 }
 
-template <int BN>
+template <int BN, bool A_MN, bool B_MN, bool SPLIT_B>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tbh, const CUtensorMap& tbl, GemmArgs g,
                        cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
   if (!configured) {
-    MPF_CUDA_OK(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     Cfg::kSmemBytes));
+    MPF_CUDA_OK(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, A_MN, B_MN, SPLIT_B>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
   g.tiles_m = (g.M + kBM - 1) / kBM;
   g.tiles_n = (g.N + BN - 1) / BN;
   const long long tiles = static_cast<long long>(g.batch) * g.tiles_m * g.tiles_n;
   const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
-  gemm_tf32x3_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tbh, tbl, g);
+  gemm_tf32x3_kernel<BN, A_MN, B_MN, SPLIT_B><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tbh, tbl, g);
   count_launch();
   return finish_launch("gemm_tf32x3");
 }
@@ -377,37 +415,46 @@ int mpf_split_tf32(const float* x, float* hi, float* lo, long long n, void* stre
   return mpf::finish_launch("split_tf32");
 }
 
-int mpf_gemm_tf32x3_ex(const float* A, long long lda, long long a_batch_stride, const float* B_hi,
-                       const float* B_lo, long long ldb, long long b_batch_stride, const float* bias, float* C,
-                       float* C_lo, long long ldc, long long c_batch_stride, const float* resid,
-                       long long resid_ld, int resid_rows, int resid_cols, float alpha, int batch, int M, int N,
-                       int K, int relu, int transpose_c, void* stream) {
+int mpf_gemm_tf32x3_general(const float* A, int a_mn_major, long long lda, long long a_batch_stride,
+                            const float* B, const float* B_lo, int b_mn_major, long long ldb,
+                            long long b_batch_stride, const float* bias, float* C, float* C_lo, long long ldc,
+                            long long c_batch_stride, const float* resid, long long resid_ld, int resid_rows,
+                            int resid_cols, float alpha, int batch, int M, int N, int K, int relu,
+                            int transpose_c, void* stream) {
   using namespace mpf;
   clear_error();
-  MPF_REQUIRE(A && B_hi && B_lo && C, "gemm_tf32x3: null pointer argument");
+  MPF_REQUIRE(A && B && C, "gemm_tf32x3: null pointer argument");
   MPF_REQUIRE(batch > 0 && M > 0 && N > 0 && K > 0, "gemm_tf32x3: dimensions must be positive");
-  MPF_REQUIRE(K % kBK == 0, "gemm_tf32x3: K (%d) must be a multiple of %d", K, kBK);
   MPF_REQUIRE(lda % 4 == 0 && ldb % 4 == 0 && a_batch_stride % 4 == 0 && b_batch_stride % 4 == 0 &&
-                  aligned16(A) && aligned16(B_hi) && aligned16(B_lo),
-              "gemm_tf32x3: A / B must be 16-byte aligned with row strides that are multiples of 4 elements");
-  MPF_REQUIRE(lda >= K && ldb >= K, "gemm_tf32x3: row strides must be >= K");
+                  aligned16(A) && aligned16(B) && (B_lo == nullptr || aligned16(B_lo)),
+              "gemm_tf32x3: A / B must be 16-byte aligned with strides that are multiples of 4 elements");
+  MPF_REQUIRE(lda >= (a_mn_major ? M : K) && ldb >= (b_mn_major ? N : K), "gemm_tf32x3: row stride too small");
   MPF_REQUIRE(static_cast<long long>(batch) * ((M + kBM - 1) / kBM) * ((N + 63) / 64) < (1ll << 31),
               "gemm_tf32x3: too many tiles");
+  const int Kp = (K + kBK - 1) / kBK * kBK;     // the tail k-block is zero-filled by TMA
   int bn = 64;
   if (N > 64) {
     const int waste128 = (N + 127) / 128 * 128 - N, waste256 = (N + 255) / 256 * 256 - N;
     bn = (N <= 128 || waste128 < waste256) ? 128 : 256;
   }
+  const bool split_b = B_lo == nullptr;
   CUtensorMap ta, tbh, tbl;
-  int rc = make_tmap_f32_3d(&ta, A, K, M, batch, lda, a_batch_stride, kBK, kBM);
+  int rc;
+  if (a_mn_major) rc = make_tmap_f32_3d(&ta, A, M, K, batch, lda, a_batch_stride, 32, kBK);
+  else rc = make_tmap_f32_3d(&ta, A, K, M, batch, lda, a_batch_stride, kBK, kBM);
   if (rc) return rc;
-  rc = make_tmap_f32_3d(&tbh, B_hi, K, N, batch, ldb, b_batch_stride, kBK, bn);
+  if (b_mn_major) rc = make_tmap_f32_3d(&tbh, B, N, K, batch, ldb, b_batch_stride, 32, kBK);
+  else rc = make_tmap_f32_3d(&tbh, B, K, N, batch, ldb, b_batch_stride, kBK, bn);
   if (rc) return rc;
-  rc = make_tmap_f32_3d(&tbl, B_lo, K, N, batch, ldb, b_batch_stride, kBK, bn);
-  if (rc) return rc;
+  tbl = tbh;
+  if (!split_b) {
+    if (b_mn_major) rc = make_tmap_f32_3d(&tbl, B_lo, N, K, batch, ldb, b_batch_stride, 32, kBK);
+    else rc = make_tmap_f32_3d(&tbl, B_lo, K, N, batch, ldb, b_batch_stride, kBK, bn);
+    if (rc) return rc;
+  }
   GemmArgs g;
   g.C = C; g.C_lo = C_lo; g.bias = bias; g.c_batch_stride = c_batch_stride; g.ldc = ldc;
-  g.batch = batch; g.M = M; g.N = N; g.K = K; g.tiles_m = g.tiles_n = 0;
+  g.batch = batch; g.M = M; g.N = N; g.K = Kp; g.tiles_m = g.tiles_n = 0;
   g.relu = relu; g.transpose_c = transpose_c;
   g.resid = resid; g.resid_ld = resid_ld; g.resid_rows = resid_rows;
   g.resid_cols = resid ? (resid_cols > 0 ? resid_cols : N) : 0;
@@ -415,9 +462,35 @@ int mpf_gemm_tf32x3_ex(const float* A, long long lda, long long a_batch_stride, 
   g.vec_store = (!transpose_c && ldc % 4 == 0 && c_batch_stride % 4 == 0 && aligned16(C) &&
                  (C_lo == nullptr || aligned16(C_lo))) ? 1 : 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (bn == 64) return launch_gemm<64>(ta, tbh, tbl, g, st);
-  if (bn == 128) return launch_gemm<128>(ta, tbh, tbl, g, st);
-  return launch_gemm<256>(ta, tbh, tbl, g, st);
+#define MPF_DISPATCH_BN(AM, BM_, SB)                                              \
+  do {                                                                            \
+    if (bn == 64) return launch_gemm<64, AM, BM_, SB>(ta, tbh, tbl, g, st);       \
+    if (bn == 128) return launch_gemm<128, AM, BM_, SB>(ta, tbh, tbl, g, st);     \
+    return launch_gemm<256, AM, BM_, SB>(ta, tbh, tbl, g, st);                    \
+  } while (0)
+  if (!a_mn_major && !b_mn_major && !split_b) MPF_DISPATCH_BN(false, false, false);
+  if (!a_mn_major && !b_mn_major && split_b) MPF_DISPATCH_BN(false, false, true);
+  if (!a_mn_major && b_mn_major && split_b) MPF_DISPATCH_BN(false, true, true);
+  if (a_mn_major && b_mn_major && split_b) MPF_DISPATCH_BN(true, true, true);
+  if (a_mn_major && !b_mn_major && split_b) MPF_DISPATCH_BN(true, false, true);
+#undef MPF_DISPATCH_BN
+  set_error("gemm_tf32x3: unsupported operand combination (a_mn=%d b_mn=%d presplit_b=%d)", a_mn_major,
+            b_mn_major, !split_b);
+  return MPF_ERR_UNSUPPORTED;
+}
+
+int mpf_gemm_tf32x3_ex(const float* A, long long lda, long long a_batch_stride, const float* B_hi,
+                       const float* B_lo, long long ldb, long long b_batch_stride, const float* bias, float* C,
+                       float* C_lo, long long ldc, long long c_batch_stride, const float* resid,
+                       long long resid_ld, int resid_rows, int resid_cols, float alpha, int batch, int M, int N,
+                       int K, int relu, int transpose_c, void* stream) {
+  if (B_lo == nullptr) {
+    mpf::set_error("gemm_tf32x3_ex: B_lo is required (use mpf_gemm_tf32x3_general for in-kernel splitting)");
+    return MPF_ERR_BAD_ARG;
+  }
+  return mpf_gemm_tf32x3_general(A, 0, lda, a_batch_stride, B_hi, B_lo, 0, ldb, b_batch_stride, bias, C, C_lo, ldc,
+                                 c_batch_stride, resid, resid_ld, resid_rows, resid_cols, alpha, batch, M, N, K,
+                                 relu, transpose_c, stream);
 }
 
 int mpf_gemm_tf32x3(const float* A, long long lda, long long a_batch_stride, const float* B_hi,

@@ -86,20 +86,49 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 constexpr int kDescStride = 5;   // 16-byte slots per item: 4 points + 1 pad so that the 4 items a warp
                                  // reads in one LDS.128 fall into distinct bank groups
 
+// The two (item, point) samples a thread prepares per level: thread t owns chunk samples t and t + 256.
+// Their locations / weights for level l+1 are fetched while phase B of level l runs.
+struct MySamples {
+  long long sbase[2];      // ((b*Lq + q)*M + m)*LP + p, or -1 if the item is padding
+  float2 xy[2];
+  float a[2];
+};
+
+__device__ __forceinline__ void my_samples_init(MySamples& ms, const MsdaTiling& tiling, int chunk, int b, int m,
+                                                int M, int Lq, int LP) {
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int idx = threadIdx.x + k * kThreads;
+    const int q = query_of(tiling, chunk, idx >> 2, Lq);
+    ms.sbase[k] = q >= 0 ? ((static_cast<long long>(b) * Lq + q) * M + m) * LP + (idx & 3) : -1;
+    ms.xy[k] = make_float2(0.f, 0.f);
+    ms.a[k] = 0.f;
+  }
+}
+
+__device__ __forceinline__ void my_samples_fetch(MySamples& ms, const float* __restrict__ loc,
+                                                 const float* __restrict__ aw, int l) {
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    if (ms.sbase[k] >= 0) {
+      const long long s = ms.sbase[k] + l * 4;
+      ms.xy[k] = __ldg(reinterpret_cast<const float2*>(loc + 2 * s));
+      ms.a[k] = __ldg(aw + s);
+    }
+  }
+}
+
 template <bool kBackward>
-__device__ __forceinline__ void build_descriptors(int4* so, float4* sw, const float* __restrict__ loc,
-                                                  const float* __restrict__ aw, const MsdaTiling& tiling,
-                                                  int chunk, int b, int m, int M, int Lq, int LP, int l, int H,
-                                                  int W, int MD) {
-  for (int idx = threadIdx.x; idx < kChunkQ * 4; idx += kThreads) {
+__device__ __forceinline__ void build_descriptors(int4* so, float4* sw, const MySamples& ms, int H, int W, int MD) {
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int idx = threadIdx.x + k * kThreads;
     const int j = idx >> 2, p = idx & 3;
-    const int q = query_of(tiling, chunk, j, Lq);
     int4 offs = make_int4(-1, -1, -1, -1);
     float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (q >= 0) {
-      const size_t s = ((static_cast<size_t>(b) * Lq + q) * M + m) * LP + l * 4 + p;
-      const float2 xy = __ldg(reinterpret_cast<const float2*>(loc + 2 * s));
-      const float a = __ldg(aw + s);
+    if (ms.sbase[k] >= 0) {
+      const float2 xy = ms.xy[k];
+      const float a = ms.a[k];
       const float h_im = xy.y * H - 0.5f;
       const float w_im = xy.x * W - 0.5f;
       if ((h_im > -1.f) && (w_im > -1.f) && (h_im < H) && (w_im < W)) {
@@ -149,11 +178,15 @@ msda_fwd_vec_kernel(const float* __restrict__ value, const int64_t* __restrict__
 #pragma unroll
   for (int it = 0; it < ITERS; ++it) acc[it] = make_float4(0.f, 0.f, 0.f, 0.f);
 
+  MySamples ms;
+  my_samples_init(ms, tiling, chunk, b, m, M, Lq, LP);
+  my_samples_fetch(ms, loc, aw, 0);
   for (int l = 0; l < L; ++l) {
     const int H = static_cast<int>(shapes[2 * l]), W = static_cast<int>(shapes[2 * l + 1]);
     const float* vl = vimg + static_cast<size_t>(lstart[l]) * MD;
     if (l > 0) __syncthreads();          // phase B of the previous level has finished reading
-    build_descriptors<false>(so, sw, loc, aw, tiling, chunk, b, m, M, Lq, LP, l, H, W, MD);
+    build_descriptors<false>(so, sw, ms, H, W, MD);
+    if (l + 1 < L) my_samples_fetch(ms, loc, aw, l + 1);   // in flight during phase B
     __syncthreads();
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -214,13 +247,17 @@ msda_bwd_vec_kernel(const float* __restrict__ grad_out, const float* __restrict_
     g[it] = active[it] ? ldg4(grad_out + item[it] * D + li * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 
+  MySamples ms;
+  my_samples_init(ms, tiling, chunk, b, m, M, Lq, LP);
+  my_samples_fetch(ms, loc, aw, 0);
   for (int l = 0; l < L; ++l) {
     const int H = static_cast<int>(shapes[2 * l]), W = static_cast<int>(shapes[2 * l + 1]);
     const size_t loff = static_cast<size_t>(lstart[l]) * MD;
     const float* vl = vimg + loff;
     float* gvl = gvimg + loff;
     if (l > 0) __syncthreads();
-    build_descriptors<true>(so, sw, loc, aw, tiling, chunk, b, m, M, Lq, LP, l, H, W, MD);
+    build_descriptors<true>(so, sw, ms, H, W, MD);
+    if (l + 1 < L) my_samples_fetch(ms, loc, aw, l + 1);
     __syncthreads();
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll

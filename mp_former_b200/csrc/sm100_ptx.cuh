@@ -134,6 +134,20 @@ __device__ __forceinline__ uint64_t smem_desc_sw128_kmajor(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major operand tile (the operand's M/N index is contiguous in memory): TMA boxes of [32 K-rows x 32
+// MN elements] (4 KiB, SWIZZLE_128B) laid side by side along MN.  An 8-row (1 KiB) swizzle atom holds 8
+// consecutive k for 32 consecutive m; LBO = byte stride between 32-element MN groups (4096), SBO = byte
+// stride between 8-row K groups (1024).  One tf32 MMA (K = 8) consumes exactly one atom row-group.
+__device__ __forceinline__ uint64_t smem_desc_sw128_mnmajor(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(4096 >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
 // Instruction descriptor, kind::tf32 (PTX ISA, tcgen05 instruction descriptor):
 //   [4,6) D format = 1 (F32)  [7,10) A format = 2 (TF32)  [10,13) B format = 2 (TF32)
 //   [15] A major = 0 (K)  [16] B major = 0 (K)  [17,23) N >> 3  [24,29) M >> 4

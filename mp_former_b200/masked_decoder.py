@@ -302,17 +302,26 @@ class MultiScaleMaskedTransformerDecoderMaskDN(_MaskedDecoderBase):
 
     # ---- mask-piloted (DN) preparation, on device --------------------------------------------
     @staticmethod
-    def _gt_masked(targets, size, scalar, noise_scale):
+    def _gt_masked(targets, size, scalar, noise_scale, cache=None):
         """Area-downsampled GT masks -> True where the cell holds (almost) no GT pixel
-        (ref decoder :986-987), optional point-flip noise (:994-998)."""
-        masks = torch.cat([F.interpolate(t["masks"].float().unsqueeze(1), size=size, mode="area").flatten(1) <= 1e-8
-                           for t in targets if len(t["masks"]) > 0]).repeat(scalar, 1)
+        (ref decoder :986-987), optional point-flip noise (:994-998).  The reference recomputes the
+        (deterministic) down-sampling for every layer; ``cache`` (dict, one forward) keeps it per size."""
+        key = (int(size[0]), int(size[1]))
+        if cache is not None and key in cache:
+            masks = cache[key]
+        else:
+            masks = torch.cat([F.interpolate(t["masks"].float().unsqueeze(1), size=size, mode="area").flatten(1) <= 1e-8
+                               for t in targets if len(t["masks"]) > 0]).repeat(scalar, 1)
+            if cache is not None:
+                cache[key] = masks
+        if noise_scale == 0:
+            return masks                      # the xor below would be with an all-False delta
         areas = (~masks).sum(1)
         ratio = areas * noise_scale / (size[0] * size[1])
         delta = torch.rand_like(masks, dtype=torch.float) < ratio[:, None]
         return torch.logical_xor(masks, delta)
 
-    def prepare_for_dn_v5(self, mask_features, dn_args, size_list):
+    def prepare_for_dn_v5(self, mask_features, dn_args, size_list, cache=None):
         """ref decoder :968-1060.  Returns None when there is nothing to denoise."""
         targets, scalar, noise_scale = dn_args["tgt"], dn_args["scalar"], dn_args["noise_scale"]
         num_boxes = [len(t["boxes"]) for t in targets]
@@ -326,7 +335,7 @@ class MultiScaleMaskedTransformerDecoderMaskDN(_MaskedDecoderBase):
         dn_meta = {"max_num": max_num, "pad_size": pad_size}
         bs = len(num_boxes)
         hw0 = size_list[0][0] * size_list[0][1]
-        masks = self._gt_masked(targets, size_list[0], scalar, noise_scale)
+        masks = self._gt_masked(targets, size_list[0], scalar, noise_scale, cache)
         labels = torch.cat([t["labels"] for t in targets]).to(dev)
         known_labels = labels.repeat(scalar, 1).view(-1).clone()
         if self.dn_label_noise_ratio > 0:
@@ -354,10 +363,10 @@ class MultiScaleMaskedTransformerDecoderMaskDN(_MaskedDecoderBase):
             tgt_mask[single_pad * i:single_pad * (i + 1), :single_pad * i] = True
         return known, output, tgt_mask, dn_meta, scalar, (oc, om, attn_mask)
 
-    def gen_mask_dn(self, dn_args, size, known, pad_size, scalar):
+    def gen_mask_dn(self, dn_args, size, known, pad_size, scalar, cache=None):
         """ref decoder :1584-1622 -> bool [B, pad_size, h*w]."""
         bs = len(dn_args["tgt"])
-        masks = self._gt_masked(dn_args["tgt"], size, scalar, dn_args["noise_scale"])
+        masks = self._gt_masked(dn_args["tgt"], size, scalar, dn_args["noise_scale"], cache)
         pm = torch.ones(bs, pad_size, size[0] * size[1], dtype=torch.bool, device=masks.device)
         pm[known] = masks
         return pm
@@ -373,7 +382,8 @@ class MultiScaleMaskedTransformerDecoderMaskDN(_MaskedDecoderBase):
             if self.dn_mode != "points":
                 raise NotImplementedError(
                     f"dn_mode={self.dn_mode!r}: only 'points' (the published MP-Former recipe) is implemented")
-            res = self.prepare_for_dn_v5(mask_features, dn_args, size_list)
+            gt_cache, bits_cache = {}, {}
+            res = self.prepare_for_dn_v5(mask_features, dn_args, size_list, gt_cache)
         dn_hook, tgt_mask, dn_meta = None, None, None
         if res is None:
             output = self.query_feat.weight.unsqueeze(0).repeat(bs, 1, 1)
@@ -385,8 +395,12 @@ class MultiScaleMaskedTransformerDecoderMaskDN(_MaskedDecoderBase):
             def dn_hook(i, level, attn_mask):
                 if not (self.all_lys or i < 3):
                     return attn_mask
-                pm = self.gen_mask_dn(dn_args, size_list[level], known, pad_size, scalar)
-                return attn_mask.replace_rows(ops.PackedMask.from_bool(pm), pad_size)
+                if dn_args["noise_scale"] == 0 and level in bits_cache:
+                    return attn_mask.replace_rows(bits_cache[level], pad_size)
+                pm = self.gen_mask_dn(dn_args, size_list[level], known, pad_size, scalar, gt_cache)
+                packed = ops.PackedMask.from_bool(pm)
+                bits_cache[level] = packed
+                return attn_mask.replace_rows(packed, pad_size)
 
         pc, pm = self._decode(output, src, pos, size_list, mask_features, tgt_mask, heads0, dn_hook)
         if tgt_mask is not None:

@@ -161,3 +161,62 @@ def masked_xattn_fwd(q_hi, q_lo, k_hi, k_lo, vt_hi, vt_lo, bits, row_open, heads
             out.data_ptr(), lse2.data_ptr(), B, Qt, HW, heads, E // heads, bits.shape[2], _stream())
     _lib.check(rc, "masked_xattn_fwd")
     return out, lse2
+
+
+def gemm_general(a, b, a_mn=False, b_mn=False, b_lo=None, bias=None, relu=False, transpose_c=False, alpha=1.0):
+    """C[i] = op(A[i]) @ op(B[i])^T with either operand optionally "MN-major" (stored [batch, K, M-or-N],
+    i.e. already transposed) and B split into TF32 halves in-kernel when ``b_lo`` is None.
+    Shapes (3-D, batch first; 2-D inputs are treated as batch 1):
+      a: [batch, M, K] (a_mn False) or [batch, K, M] (a_mn True);  b: [batch, N, K] or [batch, K, N].
+    The innermost dimension must be contiguous; row / batch strides must be multiples of 4 elements."""
+    a = _f32c(a, "a")
+    b = _f32c(b, "b")
+    squeeze = a.dim() == 2
+    if squeeze:
+        a, b = a[None], b[None]
+        b_lo = None if b_lo is None else b_lo[None]
+
+    def fix(t):
+        if t.stride(2) != 1 or t.stride(1) % 4 or (t.shape[0] > 1 and t.stride(0) % 4):
+            return t.contiguous()
+        return t
+    a, b = fix(a), fix(b)
+    if b_lo is not None:
+        b_lo = b_lo.contiguous()
+        b = b.contiguous()
+    batch = a.shape[0]
+    M, K = (a.shape[2], a.shape[1]) if a_mn else (a.shape[1], a.shape[2])
+    N, Kb = (b.shape[2], b.shape[1]) if b_mn else (b.shape[1], b.shape[2])
+    if Kb != K or b.shape[0] != batch:
+        raise RuntimeError(f"gemm_general: inner dimensions differ ({tuple(a.shape)} vs {tuple(b.shape)})")
+    if bias is not None:
+        bias = _f32c(bias, "bias").contiguous()
+    out = torch.empty((batch, N, M) if transpose_c else (batch, M, N), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        rc = _lib.load().mpf_gemm_tf32x3_general(
+            a.data_ptr(), int(a_mn), a.stride(1), a.stride(0) if batch > 1 else a.shape[1] * a.stride(1),
+            b.data_ptr(), None if b_lo is None else b_lo.data_ptr(), int(b_mn), b.stride(1),
+            b.stride(0) if batch > 1 else b.shape[1] * b.stride(1),
+            None if bias is None else bias.data_ptr(), out.data_ptr(), None, M if transpose_c else N,
+            out.stride(0), None, 0, 0, 0, float(alpha), batch, M, N, K, int(relu), int(transpose_c), _stream())
+    _lib.check(rc, "gemm_tf32x3_general")
+    return out[0] if squeeze else out
+
+
+def matmul_tn(x, y, target_tiles=296):
+    """x^T @ y for x [T, M], y [T, N] (reduction over the long token dimension T), e.g. the weight gradient
+    dW = dY^T X of an nn.Linear: both operands are consumed MN-major straight from their row-major
+    storage; T is cut into K-splits (the GEMM's batch dimension) whose partial products are summed."""
+    T, M = x.shape
+    N = y.shape[1]
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    want = max(1, min(64, target_tiles // max(1, tiles)))
+    splits = 1
+    for s in range(want, 0, -1):                 # largest split count <= want with 32 | T / s
+        if T % s == 0 and (T // s) % 32 == 0:
+            splits = s
+            break
+    xs = x.view(splits, T // splits, M)
+    ys = y.view(splits, T // splits, N)
+    part = gemm_general(xs, ys, a_mn=True, b_mn=True)          # [splits, M, N]
+    return part.sum(0) if splits > 1 else part[0]

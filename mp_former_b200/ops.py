@@ -61,7 +61,10 @@ class _Linear(torch.autograd.Function):
                 gx = g2 @ weight
             gx = gx.view(*gy.shape[:-1], weight.shape[1])
         if ctx.needs_input_grad[1]:
-            gw = g2.t() @ x2
+            if g2.shape[1] % 4 == 0 and x2.shape[1] % 4 == 0:
+                gw = native.matmul_tn(g2.contiguous(), x2)      # dW = dY^T X on the tensor cores, no transposes
+            else:
+                gw = g2.t() @ x2
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = g2.sum(0)
         return gx, gw, gb, None
@@ -106,10 +109,15 @@ class _MaskLogits(torch.autograd.Function):
         B, C, H, W = ctx.fshape
         g2 = g.reshape(B, g.shape[1], H * W)
         ge = gf = None
+        g2 = g2.contiguous()
+        ok = (H * W) % 4 == 0 and C % 4 == 0
         if ctx.needs_input_grad[0]:
-            ge = torch.bmm(g2, tokens)                                       # [B,Q,C]
+            # dE[b] = dOut[b] (Q x HW) @ F[b] (HW x C): F is consumed MN-major (no transpose)
+            ge = native.gemm_general(g2, tokens, a_mn=False, b_mn=True) if ok else torch.bmm(g2, tokens)
         if ctx.needs_input_grad[1]:
-            gf = torch.bmm(g2.transpose(1, 2), mask_embed)                  # [B,HW,C]
+            # dF[b] = dOut[b]^T (HW x Q) @ E[b] (Q x C): both operands MN-major
+            gf = native.gemm_general(g2, mask_embed, a_mn=True, b_mn=True) if ok \
+                else torch.bmm(g2.transpose(1, 2), mask_embed)
             gf = gf.view(B, H, W, C).permute(0, 3, 1, 2)
         return ge, gf
 

@@ -70,3 +70,35 @@ def test_strided_a_and_bad_args():
     assert rel_err(y, ref64(a, b)) < 1e-4
     with pytest.raises(RuntimeError, match="multiple of 32"):
         native.gemm_tf32x3(torch.randn(8, 48, device=DEV), *native.split_tf32(torch.randn(8, 48, device=DEV)))
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K,batch", [(128, 128, 32, 1), (300, 200, 104, 1), (1000, 256, 2048, 1),
+                                         (256, 100, 120, 3), (4096, 256, 120, 2)])
+def test_general_gemm_operand_majors_and_inkernel_split(a_mn, b_mn, M, N, K, batch):
+    """MN-major operands (stored transposed) and in-kernel splitting of B; K tails are zero-filled."""
+    if (K % 4 or M % 4 or N % 4):
+        pytest.skip("strides must be multiples of 4 elements")
+    g = torch.Generator(device=DEV).manual_seed(M * 7 + N * 3 + K + batch)
+    a = torch.randn(batch, M, K, device=DEV, generator=g)
+    b = torch.randn(batch, N, K, device=DEV, generator=g) / K ** 0.5
+    a_in = a.transpose(1, 2).contiguous() if a_mn else a
+    b_in = b.transpose(1, 2).contiguous() if b_mn else b
+    y = native.gemm_general(a_in, b_in, a_mn=a_mn, b_mn=b_mn)
+    r = ref64(a, b)
+    assert y.shape == (batch, M, N)
+    assert rel_err(y, r) < 1e-4, (a_mn, b_mn, M, N, K, batch, rel_err(y, r))
+
+
+def test_matmul_tn_weight_gradient_shape():
+    g = torch.Generator(device=DEV).manual_seed(11)
+    T = 21504 * 2
+    gy = torch.randn(T, 288, device=DEV, generator=g)
+    x = torch.randn(T, 256, device=DEV, generator=g)
+    gw = native.matmul_tn(gy, x)
+    ref = gy.double().t() @ x.double()
+    assert gw.shape == (288, 256)
+    assert rel_err(gw, ref) < 2e-4
+    # a token count with no 32-divisible split still works (single split, zero-filled K tail)
+    gw2 = native.matmul_tn(gy[:1004].contiguous(), x[:1004].contiguous())
+    assert rel_err(gw2, gy[:1004].double().t() @ x[:1004].double()) < 2e-4
