@@ -334,7 +334,7 @@ split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __
 // host side
 // ------------------------------------------------------------------------------------------------
 int make_tmap_f32_3d(CUtensorMap* m, const float* base, long long d0, long long d1, long long d2,
-                     long long ld1, long long ld2, int box0, int box1) {
+                     long long ld1, long long ld2, int box0, int box1, bool atom32) {
   using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -361,7 +361,9 @@ int make_tmap_f32_3d(CUtensorMap* m, const float* base, long long d0, long long 
   cuuint32_t box[3] = {static_cast<cuuint32_t>(box0), static_cast<cuuint32_t>(box1), 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (CUresult %d): base=%p dims=(%lld,%lld,%lld) ld=(%lld,%lld) box=(%d,%d)",
@@ -440,15 +442,15 @@ int mpf_gemm_tf32x3_general(const float* A, int a_mn_major, long long lda, long 
   const bool split_b = B_lo == nullptr;
   CUtensorMap ta, tbh, tbl;
   int rc;
-  if (a_mn_major) rc = make_tmap_f32_3d(&ta, A, M, K, batch, lda, a_batch_stride, 32, kBK);
+  if (a_mn_major) rc = make_tmap_f32_3d(&ta, A, M, K, batch, lda, a_batch_stride, 32, kBK, true);
   else rc = make_tmap_f32_3d(&ta, A, K, M, batch, lda, a_batch_stride, kBK, kBM);
   if (rc) return rc;
-  if (b_mn_major) rc = make_tmap_f32_3d(&tbh, B, N, K, batch, ldb, b_batch_stride, 32, kBK);
+  if (b_mn_major) rc = make_tmap_f32_3d(&tbh, B, N, K, batch, ldb, b_batch_stride, 32, kBK, true);
   else rc = make_tmap_f32_3d(&tbh, B, K, N, batch, ldb, b_batch_stride, kBK, bn);
   if (rc) return rc;
   tbl = tbh;
   if (!split_b) {
-    if (b_mn_major) rc = make_tmap_f32_3d(&tbl, B_lo, N, K, batch, ldb, b_batch_stride, 32, kBK);
+    if (b_mn_major) rc = make_tmap_f32_3d(&tbl, B_lo, N, K, batch, ldb, b_batch_stride, 32, kBK, true);
     else rc = make_tmap_f32_3d(&tbl, B_lo, K, N, batch, ldb, b_batch_stride, kBK, bn);
     if (rc) return rc;
   }

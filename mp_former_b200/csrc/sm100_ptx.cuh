@@ -134,17 +134,20 @@ __device__ __forceinline__ uint64_t smem_desc_sw128_kmajor(uint32_t smem_addr) {
   return d;
 }
 
-// MN-major operand tile (the operand's M/N index is contiguous in memory): TMA boxes of [32 K-rows x 32
-// MN elements] (4 KiB, SWIZZLE_128B) laid side by side along MN.  An 8-row (1 KiB) swizzle atom holds 8
-// consecutive k for 32 consecutive m; LBO = byte stride between 32-element MN groups (4096), SBO = byte
-// stride between 8-row K groups (1024).  One tf32 MMA (K = 8) consumes exactly one atom row-group.
+// MN-major operand tile (the operand's M/N index is contiguous in memory), 32-bit elements: the only
+// shared-memory layout the tensor core accepts is "128B swizzle with 32-byte atoms" (descriptor layout
+// type 1, SWIZZLE_128B_BASE32B; TMA mode CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of 128 bytes = 32
+// consecutive M (or N) elements for one k, consecutive k in consecutive rows, the four 32-byte chunks of a
+// row XOR-ed with (row % 4).  We load [32 k-rows x 32 elements] boxes (4 KiB) side by side along MN:
+//   LBO = byte stride between 32-element MN groups (4096), SBO = byte stride between 4-row K groups (512).
+// One tf32 MMA (K = 8) consumes two consecutive 4-row groups; the next K step starts 1024 bytes further.
 __device__ __forceinline__ uint64_t smem_desc_sw128_mnmajor(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
   d |= static_cast<uint64_t>(4096 >> 4) << 16;
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
+  d |= static_cast<uint64_t>(1) << 61;
   return d;
 }
 

@@ -21,7 +21,7 @@ def _loss(out):
     return out["pred_masks"].square().mean() + out["pred_logits"].square().mean()
 
 
-def _build():
+def _build(setattr_fn=setattr):
     import sys
     here = os.path.dirname(os.path.abspath(__file__))
     for p in (os.path.dirname(here), here, os.path.join(here, "golden")):
@@ -31,7 +31,7 @@ def _build():
     from oracle import torch_oracle as O
     from test_host_logic_cpu import build_decoder, install_cpu_ops
     from test_oracle_vs_golden import decoder_template
-    install_cpu_ops(setattr)
+    install_cpu_ops(setattr_fn)
     dec = build_decoder()
     dec.load_state_dict(O.seeded_state_dict(decoder_template(), seed=51))
     x, mf = cases.decoder_inputs(B=4, seed=77)
@@ -58,13 +58,13 @@ def _worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
-def test_two_rank_gloo_matches_single_process():
+def test_two_rank_gloo_matches_single_process(monkeypatch):
     world, port = 2, _free_port()
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert ret["max"] == float(world)
-    dec, x, mf = _build()
+    dec, x, mf = _build(monkeypatch.setattr)      # patches are undone after the test
     # DDP averages gradients over ranks; each rank's loss is the mean over its shard
     per = x[0].shape[0] // world
     total = 0

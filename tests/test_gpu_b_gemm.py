@@ -68,8 +68,11 @@ def test_strided_a_and_bad_args():
     bh, bl = native.split_tf32(b)
     y = native.gemm_tf32x3(a, bh, bl)
     assert rel_err(y, ref64(a, b)) < 1e-4
-    with pytest.raises(RuntimeError, match="multiple of 32"):
-        native.gemm_tf32x3(torch.randn(8, 48, device=DEV), *native.split_tf32(torch.randn(8, 48, device=DEV)))
+    # K that is not a multiple of 32: the tail k-block is zero-filled by TMA
+    a48, b48 = torch.randn(8, 48, device=DEV, generator=g), torch.randn(8, 48, device=DEV, generator=g)
+    assert rel_err(native.gemm_tf32x3(a48, *native.split_tf32(b48)), ref64(a48, b48)) < 1e-4
+    with pytest.raises(RuntimeError, match="multiples of 4"):
+        native.gemm_tf32x3(torch.randn(8, 30, device=DEV), *native.split_tf32(torch.randn(8, 30, device=DEV)))
 
 
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
@@ -98,7 +101,9 @@ def test_matmul_tn_weight_gradient_shape():
     gw = native.matmul_tn(gy, x)
     ref = gy.double().t() @ x.double()
     assert gw.shape == (288, 256)
-    assert rel_err(gw, ref) < 2e-4
+    # entries are sums of 43008 O(1) products (|ref| ~ 200): compare against the scale of the reduction
+    assert (gw.double() - ref).abs().max().item() / ref.abs().max().item() < 1e-4
     # a token count with no 32-divisible split still works (single split, zero-filled K tail)
     gw2 = native.matmul_tn(gy[:1004].contiguous(), x[:1004].contiguous())
-    assert rel_err(gw2, gy[:1004].double().t() @ x[:1004].double()) < 2e-4
+    ref2 = gy[:1004].double().t() @ x[:1004].double()
+    assert (gw2.double() - ref2).abs().max().item() / ref2.abs().max().item() < 1e-4
