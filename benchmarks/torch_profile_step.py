@@ -36,7 +36,11 @@ def step():
 for _ in range(2):
     step()
 torch.cuda.synchronize()
-with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=bool(os.environ.get("MPF_SHAPES"))) as prof:
     step()
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=60))
+if os.environ.get("MPF_SHAPES"):
+    print(prof.key_averages(group_by_input_shape=True).table(sort_by="self_cuda_time_total", row_limit=60,
+                                                             max_name_column_width=40, max_shapes_column_width=90))
+else:
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=60))

@@ -70,6 +70,19 @@ class ConvNormAct(nn.Conv2d):
         return x
 
 
+def conv1x1_tokens(x, conv):
+    """1x1 convolution of a (logically NCHW, channels-last in memory) map as a token GEMM on the
+    tensor-core kernel: [B*H*W, Cin] x W[Cout, Cin]^T (+ bias).  Returns the map in the same form."""
+    B, Cin, H, W = x.shape
+    if Cin % 32 != 0 or conv.kernel_size != (1, 1) or conv.stride != (1, 1):
+        return F.conv2d(x, conv.weight, conv.bias)
+    tokens = x.permute(0, 2, 3, 1)
+    if not tokens.is_contiguous():
+        tokens = tokens.contiguous()
+    y = ops.linear(tokens.view(B * H * W, Cin), conv.weight.view(conv.out_channels, Cin), conv.bias)
+    return y.view(B, H, W, conv.out_channels).permute(0, 3, 1, 2)
+
+
 def _get_norm(norm, channels):
     if norm is None or (isinstance(norm, str) and norm == ""):
         return None
@@ -282,7 +295,8 @@ class MSDeformAttnPixelDecoder(nn.Module):
         srcs, pos = [], []
         for idx, f in enumerate(self.transformer_in_features[::-1]):
             x = features[f].float().contiguous(memory_format=torch.channels_last)
-            srcs.append(self.input_proj[idx](x))
+            proj = self.input_proj[idx]
+            srcs.append(proj[1](conv1x1_tokens(x, proj[0])))
             pos.append(self.pe_layer(x))
         y, spatial_shapes, _ = self.transformer(srcs, pos)
         bs = y.shape[0]
@@ -294,8 +308,13 @@ class MSDeformAttnPixelDecoder(nn.Module):
             out.append(z.transpose(1, 2).reshape(bs, -1, h, w))   # logical NCHW, channels-last memory
         for idx, f in enumerate(self.in_features[:self.num_fpn_levels][::-1]):
             x = features[f].float().contiguous(memory_format=torch.channels_last)
-            cur_fpn = self.lateral_convs[idx](x)
+            lateral = self.lateral_convs[idx]
+            cur_fpn = conv1x1_tokens(x, lateral)
+            if lateral.norm is not None:
+                cur_fpn = lateral.norm(cur_fpn)
+            if lateral.activation is not None:
+                cur_fpn = lateral.activation(cur_fpn)
             up = F.interpolate(out[-1], size=cur_fpn.shape[-2:], mode="bilinear", align_corners=False)
             out.append(self.output_convs[idx](cur_fpn + up))
         multi_scale_features = out[:self.maskformer_num_feature_levels]
-        return self.mask_features(out[-1]), out[0], multi_scale_features
+        return conv1x1_tokens(out[-1], self.mask_features), out[0], multi_scale_features
