@@ -184,6 +184,22 @@ int mpf_masked_xattn_fwd_f32(const float* q_hi, const float* q_lo, const float* 
                              const uint8_t* row_open, float* out, float* lse2, int B, int Qt, int HW,
                              int heads, int head_dim, int mask_words, void* stream);
 
+/* Backward of mpf_masked_xattn_fwd_f32 (two tcgen05 kernels, probabilities recomputed from lse2):
+ *   dq[b,q,:]  = (1/sqrt(d)) * sum_k dS[q,k] K[k,:]      (gradient wrt the UNSCALED query projection)
+ *   dk[b,k,:]  = ln2 * sum_q dS[q,k] Qs[q,:]             (Qs = the pre-scaled query the forward consumed)
+ *   dv[b,k,:]  = sum_q P[q,k] dO[q,:]
+ * with P = exp2(Qs K^T - lse2) (0 where masked), dS = P * (dO V^T - delta), delta = rowsum(dO * O).
+ * Operands are TF32-split halves: q/qt (Qs and its transpose [B,E,qt_ld]), k/kt (K and K^T [B,E,HW]),
+ * v (V, row-major [B,HW,E]), do/dot (dO and dO^T [B,E,qt_ld]); lse2, delta [B,heads,Qt].
+ * ref: autograd backward of nn.MultiheadAttention in CrossAttentionLayer (decoder :100-112). */
+int mpf_masked_xattn_bwd_f32(const float* q_hi, const float* q_lo, const float* qt_hi, const float* qt_lo,
+                             const float* k_hi, const float* k_lo, const float* kt_hi, const float* kt_lo,
+                             const float* v_hi, const float* v_lo, const float* do_hi, const float* do_lo,
+                             const float* dot_hi, const float* dot_lo, const uint32_t* mask_bits,
+                             const uint8_t* row_open, const float* lse2, const float* delta, float* dq,
+                             float* dk, float* dv, int B, int Qt, int qt_ld, int HW, int heads, int head_dim,
+                             int mask_words, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,552 @@
+// Fused masked multi-head cross-attention, backward (two kernels; probabilities are recomputed from the
+// saved log-sum-exp, nothing of size [B*heads, Q, HW] ever exists in HBM).
+//
+//   forward (xattn.cu):  S2 = Qs K^T (log2 domain, Qs = q * log2e/sqrt(d)),  P = exp2(S2 - lse2) (0 where
+//                        masked),  O = P V
+//   given dO:   dP = dO V^T,   D = rowsum(dO * O),   dS = P * (dP - D)        (gradient wrt the natural logits)
+//               dq = dS K / sqrt(d)          dk = dS^T Qs * ln2          dv = P^T dO
+//
+//   kernel A  masked_xattn_bwd_dq_kernel : CTA = (128-query tile, head, image), walks the keys in tiles of 64;
+//             S and dP land in TMEM (double buffered), the softmax warps turn them into dS (hi/lo, shared
+//             memory, UMMA K-major layout), dQ += dS K accumulates in TMEM over all key tiles.
+//   kernel B  masked_xattn_bwd_dkv_kernel: CTA = (128-key tile, head, image), walks the queries in chunks of 64;
+//             computes the TRANSPOSED tiles S^T = K Qs^T and dP^T = V dO^T directly (TMEM lanes = keys), so P^T
+//             and dS^T are written row-wise by their owner threads and feed dV += P^T dO, dK += dS^T Qs
+//             as ordinary K-major operands -- no transposition through shared memory is ever needed.
+// All products are 3xTF32 (hi/lo split operands, fp32 accumulation in TMEM) like the forward.
+// ref: the backward of nn.MultiheadAttention in CrossAttentionLayer (decoder :100-112) under autograd.
+#include "mpf_common.cuh"
+#include "sm100_ptx.cuh"
+#include "tmap.cuh"
+
+namespace mpf {
+
+using namespace ptx;
+
+namespace xb {
+constexpr int kD = 32;            // head dim
+constexpr int kThreads = 256;
+constexpr float kLn2 = 0.6931471805599453f;
+
+__device__ __forceinline__ float rn(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+
+// Writes 32 fp32 values of one row as hi/lo TF32 halves into a [rows x 32] K-major SWIZZLE_128B atom.
+__device__ __forceinline__ void store_row_atom(uint8_t* atom_hi, uint8_t* atom_lo, int r, const float (&x)[32]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int sw = r * 128 + ((c ^ (r & 7)) << 4);
+    float4 h, l;
+    h.x = rn(x[4 * c]); h.y = rn(x[4 * c + 1]); h.z = rn(x[4 * c + 2]); h.w = rn(x[4 * c + 3]);
+    l.x = rn(x[4 * c] - h.x); l.y = rn(x[4 * c + 1] - h.y); l.z = rn(x[4 * c + 2] - h.z); l.w = rn(x[4 * c + 3] - h.w);
+    *reinterpret_cast<float4*>(atom_hi + sw) = h;
+    *reinterpret_cast<float4*>(atom_lo + sw) = l;
+  }
+}
+
+// three-pass 3xTF32 product step: D (+)= A B^T with split operands
+__device__ __forceinline__ void mma3(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                     uint32_t idesc, bool accumulate) {
+  mma_tf32_ss(d, smem_desc_sw128_kmajor(a_lo), smem_desc_sw128_kmajor(b_hi), idesc, accumulate ? 1u : 0u);
+  mma_tf32_ss(d, smem_desc_sw128_kmajor(a_hi), smem_desc_sw128_kmajor(b_lo), idesc, 1u);
+  mma_tf32_ss(d, smem_desc_sw128_kmajor(a_hi), smem_desc_sw128_kmajor(b_hi), idesc, 1u);
+}
+}  // namespace xb
+
+struct XbwdArgs {
+  const uint32_t* bits;     // [B, Qt, words]
+  const uint8_t* row_open;  // [B, Qt] or null
+  const float* lse2;        // [B, heads, Qt]
+  const float* delta;       // [B, heads, Qt]   D = rowsum(dO * O)
+  float* dq;                // kernel A: [B, Qt, E]
+  float* dk;                // kernel B: [B, HW, E]
+  float* dv;                // kernel B: [B, HW, E]
+  int B, Qt, HW, E, heads, words;
+  float inv_sqrt_d;
+};
+
+// ================================================================================================
+// kernel A: dQ
+// ================================================================================================
+namespace xa {
+constexpr int kQ = 128, kK = 64;
+constexpr int kQBytes = kQ * 32 * 4;            // 16 KiB (one of Q_hi, Q_lo, dO_hi, dO_lo)
+constexpr int kKBytes = kK * 32 * 4;            // 8 KiB  (K_hi / K_lo / V_hi / V_lo tile)
+constexpr int kKtBytes = 32 * kK * 4;           // 8 KiB  (K^T hi or lo: two [32 x 32] atoms)
+constexpr int kStage = 4 * kKBytes + 2 * kKtBytes;   // 48 KiB
+constexpr int kAtom = kQ * 32 * 4;              // 16 KiB: [128 rows x 32 keys]
+constexpr int kDsBytes = 2 * kAtom;             // 32 KiB (one of dS_hi / dS_lo)
+constexpr int kSmem = 4 * kQBytes + 2 * kStage + 2 * kDsBytes + 256 + 1024;
+constexpr uint32_t kTmemCols = 512;
+constexpr int kTS = 0, kTP = 128, kTQ = 256;    // S: 2x64, dP: 2x64, dQ: 32
+}  // namespace xa
+
+__global__ void __launch_bounds__(xb::kThreads, 1)
+masked_xattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
+                           const __grid_constant__ CUtensorMap tmDh, const __grid_constant__ CUtensorMap tmDl,
+                           const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
+                           const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl,
+                           const __grid_constant__ CUtensorMap tmKth, const __grid_constant__ CUtensorMap tmKtl,
+                           const XbwdArgs g) {
+  using namespace xa;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                         // Q_hi | Q_lo | dO_hi | dO_lo
+  uint8_t* sKV = smem + 4 * kQBytes;          // stage: K_hi | K_lo | V_hi | V_lo | Kt_hi | Kt_lo
+  uint8_t* sDS = sKV + 2 * kStage;            // dS_hi | dS_lo
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + 2 * kDsBytes);
+  uint64_t* qdo_full = bars;
+  uint64_t* kv_full = bars + 1;    // [2]
+  uint64_t* kv_empty = bars + 3;   // [2]
+  uint64_t* sdp_full = bars + 5;   // [2]
+  uint64_t* sdp_empty = bars + 7;  // [2]
+  uint64_t* ds_full = bars + 9;
+  uint64_t* ds_empty = bars + 10;
+  uint64_t* dq_full = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kQ, head = blockIdx.y, b = blockIdx.z;
+  const int T = (g.HW + kK - 1) / kK;
+
+  if (warp == 0 && lane == 0) {
+    mbar_init(qdo_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&sdp_full[i], 1);
+      mbar_init(&sdp_empty[i], 4);
+    }
+    mbar_init(ds_full, 4);
+    mbar_init(ds_empty, 1);
+    mbar_init(dq_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(qdo_full, 4 * kQBytes);
+      tma_load_3d(sQ, &tmQh, qdo_full, head * 32, q0, b);
+      tma_load_3d(sQ + kQBytes, &tmQl, qdo_full, head * 32, q0, b);
+      tma_load_3d(sQ + 2 * kQBytes, &tmDh, qdo_full, head * 32, q0, b);
+      tma_load_3d(sQ + 3 * kQBytes, &tmDl, qdo_full, head * 32, q0, b);
+      for (int j = 0; j < T; ++j) {
+        const int st = j & 1;
+        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        uint8_t* s = sKV + st * kStage;
+        mbar_arrive_expect_tx(&kv_full[st], kStage);
+        const int key0 = j * kK;
+        tma_load_3d(s, &tmKh, &kv_full[st], head * 32, key0, b);
+        tma_load_3d(s + kKBytes, &tmKl, &kv_full[st], head * 32, key0, b);
+        tma_load_3d(s + 2 * kKBytes, &tmVh, &kv_full[st], head * 32, key0, b);
+        tma_load_3d(s + 3 * kKBytes, &tmVl, &kv_full[st], head * 32, key0, b);
+        tma_load_3d(s + 4 * kKBytes, &tmKth, &kv_full[st], key0, head * 32, b);
+        tma_load_3d(s + 4 * kKBytes + kKtBytes / 2, &tmKth, &kv_full[st], key0 + 32, head * 32, b);
+        tma_load_3d(s + 4 * kKBytes + kKtBytes, &tmKtl, &kv_full[st], key0, head * 32, b);
+        tma_load_3d(s + 4 * kKBytes + kKtBytes + kKtBytes / 2, &tmKtl, &kv_full[st], key0 + 32, head * 32, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = idesc_tf32(kQ, kK);     // 128 x 64
+      constexpr uint32_t idesc_q = idesc_tf32(kQ, 32);     // 128 x 32
+      const uint32_t q_hi = smem_u32(sQ), q_lo = q_hi + kQBytes, do_hi = q_hi + 2 * kQBytes, do_lo = q_hi + 3 * kQBytes;
+      const uint32_t ds_hi = smem_u32(sDS), ds_lo = ds_hi + kDsBytes;
+      auto issue_sdp = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(&kv_full[st], (j >> 1) & 1);
+        mbar_wait(&sdp_empty[st], ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t k_hi = smem_u32(sKV + st * kStage), k_lo = k_hi + kKBytes;
+        const uint32_t v_hi = k_hi + 2 * kKBytes, v_lo = k_hi + 3 * kKBytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          xb::mma3(tmem_base + kTS + st * kK, q_hi + k * 32, q_lo + k * 32, k_hi + k * 32, k_lo + k * 32, idesc_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          xb::mma3(tmem_base + kTP + st * kK, do_hi + k * 32, do_lo + k * 32, v_hi + k * 32, v_lo + k * 32, idesc_s, k > 0);
+        mma_commit(&sdp_full[st]);
+      };
+      mbar_wait(qdo_full, 0);
+      issue_sdp(0);
+      for (int j = 0; j < T; ++j) {
+        if (j + 1 < T) issue_sdp(j + 1);
+        const int st = j & 1;
+        mbar_wait(ds_full, j & 1);
+        tc_fence_after();
+        const uint32_t kt_hi = smem_u32(sKV + st * kStage + 4 * kKBytes), kt_lo = kt_hi + kKtBytes;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t ao = (k >> 2) * kAtom + (k & 3) * 32;
+          const uint32_t bo = (k >> 2) * (kKtBytes / 2) + (k & 3) * 32;
+          xb::mma3(tmem_base + kTQ, ds_hi + ao, ds_lo + ao, kt_hi + bo, kt_lo + bo, idesc_q, (j | k) != 0);
+        }
+        mma_commit(ds_empty);
+        mma_commit(&kv_empty[st]);
+      }
+      mma_commit(dq_full);
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    const int r = ew * 32 + lane;
+    const int q = q0 + r;
+    const bool q_ok = q < g.Qt;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
+    const uint32_t* brow = g.bits + (static_cast<long long>(b) * g.Qt + (q_ok ? q : 0)) * g.words;
+    const bool open = !q_ok || (g.row_open != nullptr && g.row_open[static_cast<long long>(b) * g.Qt + q] != 0);
+    const long long rowi = (static_cast<long long>(b) * g.heads + head) * g.Qt + (q_ok ? q : 0);
+    const float lse = q_ok ? g.lse2[rowi] : 0.f;
+    const float dlt = q_ok ? g.delta[rowi] : 0.f;
+
+    for (int j = 0; j < T; ++j) {
+      const int st = j & 1;
+      const int key0 = j * kK;
+      uint32_t w[2] = {0u, 0u};
+      if (!open) { w[0] = brow[2 * j]; w[1] = brow[2 * j + 1]; }
+      if (key0 + 32 > g.HW) w[0] |= (key0 >= g.HW) ? 0xFFFFFFFFu : (0xFFFFFFFFu << (g.HW - key0));
+      if (key0 + 64 > g.HW) w[1] |= (key0 + 32 >= g.HW) ? 0xFFFFFFFFu : (0xFFFFFFFFu << (g.HW - key0 - 32));
+      if (!q_ok) { w[0] = 0xFFFFFFFFu; w[1] = 0xFFFFFFFFu; }      // padding rows contribute nothing
+      mbar_wait(&sdp_full[st], (j >> 1) & 1);
+      tc_fence_after();
+      float ds[2][32];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t sv[32], pv[32];
+        tmem_ld_32x32(lane_addr + kTS + st * kK + h * 32, sv);
+        tmem_ld_32x32(lane_addr + kTP + st * kK + h * 32, pv);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float p = ((w[h] >> i) & 1u) ? 0.f : exp2f(__uint_as_float(sv[i]) - lse);
+          ds[h][i] = p * (__uint_as_float(pv[i]) - dlt);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sdp_empty[st]);
+      mbar_wait(ds_empty, (j & 1) ^ 1);
+      xb::store_row_atom(sDS, sDS + kDsBytes, r, ds[0]);
+      xb::store_row_atom(sDS + kAtom, sDS + kDsBytes + kAtom, r, ds[1]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_full);
+    }
+    mbar_wait(dq_full, 0);
+    tc_fence_after();
+    uint32_t v[32];
+    tmem_ld_32x32(lane_addr + kTQ, v);
+    tmem_ld_wait();
+    if (q_ok) {
+      float* dst = g.dq + (static_cast<long long>(b) * g.Qt + q) * g.E + head * 32;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4)
+        *reinterpret_cast<float4*>(dst + i) =
+            make_float4(__uint_as_float(v[i]) * g.inv_sqrt_d, __uint_as_float(v[i + 1]) * g.inv_sqrt_d,
+                        __uint_as_float(v[i + 2]) * g.inv_sqrt_d, __uint_as_float(v[i + 3]) * g.inv_sqrt_d);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ================================================================================================
+// kernel B: dK, dV
+// ================================================================================================
+namespace xk {
+constexpr int kKeys = 128, kQc = 64;
+constexpr int kKVBytes = kKeys * 32 * 4;        // 16 KiB (one of K_hi, K_lo, V_hi, V_lo)
+constexpr int kQcBytes = kQc * 32 * 4;          // 8 KiB  (Q / dO chunk, hi or lo)
+constexpr int kQtBytes = 32 * kQc * 4;          // 8 KiB  (Q^T / dO^T chunk, hi or lo: two atoms)
+constexpr int kChunk = 4 * kQcBytes + 4 * kQtBytes;     // 64 KiB: Q_hi Q_lo dO_hi dO_lo | Qt_hi Qt_lo dOt_hi dOt_lo
+constexpr int kAtom = kKeys * 32 * 4;           // 16 KiB: [128 keys x 32 q]
+constexpr int kPBytes = 2 * kAtom;              // 32 KiB (hi or lo of P^T / dS^T)
+constexpr int kSmem = 4 * kKVBytes + kChunk + 2 * kPBytes + 256 + 1024;
+constexpr uint32_t kTmemCols = 256;
+constexpr int kTS = 0, kTP = 64, kTV = 128, kTK = 160;   // S^T 64, dP^T 64, dV 32, dK 32
+}  // namespace xk
+
+__global__ void __launch_bounds__(xb::kThreads, 1)
+masked_xattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
+                            const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl,
+                            const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
+                            const __grid_constant__ CUtensorMap tmDh, const __grid_constant__ CUtensorMap tmDl,
+                            const __grid_constant__ CUtensorMap tmQth, const __grid_constant__ CUtensorMap tmQtl,
+                            const __grid_constant__ CUtensorMap tmDth, const __grid_constant__ CUtensorMap tmDtl,
+                            const XbwdArgs g) {
+  using namespace xk;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sKV = smem;                        // K_hi | K_lo | V_hi | V_lo
+  uint8_t* sC = smem + 4 * kKVBytes;          // q-chunk stage
+  uint8_t* sP = sC + kChunk;                  // P^T / dS^T: hi | lo
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPBytes);
+  uint64_t* kv_full = bars;
+  uint64_t* qc_full = bars + 1;
+  uint64_t* qc_empty = bars + 2;   // commit after the chunk's dK MMAs: stage and P buffer are free
+  uint64_t* st_full = bars + 3;
+  uint64_t* st_empty = bars + 4;   // count 4
+  uint64_t* pt_full = bars + 5;    // count 4
+  uint64_t* pt_empty = bars + 6;   // commit after dV MMAs
+  uint64_t* dst_full = bars + 7;   // count 4
+  uint64_t* acc_full = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int key0 = blockIdx.x * kKeys, head = blockIdx.y, b = blockIdx.z;
+  const int NC = (g.Qt + kQc - 1) / kQc;
+
+  if (warp == 0 && lane == 0) {
+    mbar_init(kv_full, 1);
+    mbar_init(qc_full, 1);
+    mbar_init(qc_empty, 1);
+    mbar_init(st_full, 1);
+    mbar_init(st_empty, 4);
+    mbar_init(pt_full, 4);
+    mbar_init(pt_empty, 1);
+    mbar_init(dst_full, 4);
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(kv_full, 4 * kKVBytes);
+      tma_load_3d(sKV, &tmKh, kv_full, head * 32, key0, b);
+      tma_load_3d(sKV + kKVBytes, &tmKl, kv_full, head * 32, key0, b);
+      tma_load_3d(sKV + 2 * kKVBytes, &tmVh, kv_full, head * 32, key0, b);
+      tma_load_3d(sKV + 3 * kKVBytes, &tmVl, kv_full, head * 32, key0, b);
+      for (int c = 0; c < NC; ++c) {
+        mbar_wait(qc_empty, (c & 1) ^ 1);
+        mbar_arrive_expect_tx(qc_full, kChunk);
+        const int qc0 = c * kQc;
+        tma_load_3d(sC, &tmQh, qc_full, head * 32, qc0, b);
+        tma_load_3d(sC + kQcBytes, &tmQl, qc_full, head * 32, qc0, b);
+        tma_load_3d(sC + 2 * kQcBytes, &tmDh, qc_full, head * 32, qc0, b);
+        tma_load_3d(sC + 3 * kQcBytes, &tmDl, qc_full, head * 32, qc0, b);
+        uint8_t* t = sC + 4 * kQcBytes;
+        tma_load_3d(t, &tmQth, qc_full, qc0, head * 32, b);
+        tma_load_3d(t + kQtBytes / 2, &tmQth, qc_full, qc0 + 32, head * 32, b);
+        tma_load_3d(t + kQtBytes, &tmQtl, qc_full, qc0, head * 32, b);
+        tma_load_3d(t + kQtBytes + kQtBytes / 2, &tmQtl, qc_full, qc0 + 32, head * 32, b);
+        tma_load_3d(t + 2 * kQtBytes, &tmDth, qc_full, qc0, head * 32, b);
+        tma_load_3d(t + 2 * kQtBytes + kQtBytes / 2, &tmDth, qc_full, qc0 + 32, head * 32, b);
+        tma_load_3d(t + 3 * kQtBytes, &tmDtl, qc_full, qc0, head * 32, b);
+        tma_load_3d(t + 3 * kQtBytes + kQtBytes / 2, &tmDtl, qc_full, qc0 + 32, head * 32, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = idesc_tf32(kKeys, kQc);   // 128 x 64
+      constexpr uint32_t idesc_o = idesc_tf32(kKeys, 32);    // 128 x 32
+      const uint32_t k_hi = smem_u32(sKV), k_lo = k_hi + kKVBytes, v_hi = k_hi + 2 * kKVBytes, v_lo = k_hi + 3 * kKVBytes;
+      const uint32_t q_hi = smem_u32(sC), q_lo = q_hi + kQcBytes, do_hi = q_hi + 2 * kQcBytes, do_lo = q_hi + 3 * kQcBytes;
+      const uint32_t qt_hi = q_hi + 4 * kQcBytes, qt_lo = qt_hi + kQtBytes, dt_hi = qt_hi + 2 * kQtBytes, dt_lo = qt_hi + 3 * kQtBytes;
+      const uint32_t p_hi = smem_u32(sP), p_lo = p_hi + kPBytes;
+      mbar_wait(kv_full, 0);
+      for (int c = 0; c < NC; ++c) {
+        mbar_wait(qc_full, c & 1);
+        mbar_wait(st_empty, (c & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          xb::mma3(tmem_base + kTS, k_hi + k * 32, k_lo + k * 32, q_hi + k * 32, q_lo + k * 32, idesc_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          xb::mma3(tmem_base + kTP, v_hi + k * 32, v_lo + k * 32, do_hi + k * 32, do_lo + k * 32, idesc_s, k > 0);
+        mma_commit(st_full);
+        mbar_wait(pt_full, c & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t ao = (k >> 2) * kAtom + (k & 3) * 32, bo = (k >> 2) * (kQtBytes / 2) + (k & 3) * 32;
+          xb::mma3(tmem_base + kTV, p_hi + ao, p_lo + ao, dt_hi + bo, dt_lo + bo, idesc_o, (c | k) != 0);
+        }
+        mma_commit(pt_empty);
+        mbar_wait(dst_full, c & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t ao = (k >> 2) * kAtom + (k & 3) * 32, bo = (k >> 2) * (kQtBytes / 2) + (k & 3) * 32;
+          xb::mma3(tmem_base + kTK, p_hi + ao, p_lo + ao, qt_hi + bo, qt_lo + bo, idesc_o, (c | k) != 0);
+        }
+        mma_commit(qc_empty);
+      }
+      mma_commit(acc_full);
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    const int r = ew * 32 + lane;                 // key row inside the tile == TMEM lane
+    const int key = key0 + r;
+    const bool key_ok = key < g.HW;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
+    const int word = key >> 5;                    // mask word holding this key (warp-uniform)
+    const uint32_t bit = 1u << (key & 31);
+    const float* lse_b = g.lse2 + (static_cast<long long>(b) * g.heads + head) * g.Qt;
+    const float* dlt_b = g.delta + (static_cast<long long>(b) * g.heads + head) * g.Qt;
+
+    for (int c = 0; c < NC; ++c) {
+      const int qc0 = c * kQc;
+      mbar_wait(st_full, c & 1);
+      tc_fence_after();
+      float pt[2][32], ds[2][32];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t sv[32], pv[32];
+        tmem_ld_32x32(lane_addr + kTS + h * 32, sv);
+        tmem_ld_32x32(lane_addr + kTP + h * 32, pv);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int q = qc0 + h * 32 + i;
+          float p = 0.f, d = 0.f;
+          if (q < g.Qt && key_ok) {                // warp-uniform in q; key_ok differs only in the last tile
+            const long long qi = static_cast<long long>(b) * g.Qt + q;
+            const bool open = g.row_open != nullptr && g.row_open[qi] != 0;
+            const bool masked = !open && (g.bits[qi * g.words + word] & bit) != 0u;
+            if (!masked) {
+              p = exp2f(__uint_as_float(sv[i]) - __ldg(lse_b + q));
+              d = p * (__uint_as_float(pv[i]) - __ldg(dlt_b + q));
+            }
+          }
+          pt[h][i] = p;
+          ds[h][i] = d;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(st_empty);
+      // P^T(c): the buffer is free once the previous chunk's dK MMAs retired (qc_empty of chunk c-1)
+      if (c > 0) mbar_wait(qc_empty, (c - 1) & 1);
+      xb::store_row_atom(sP, sP + kPBytes, r, pt[0]);
+      xb::store_row_atom(sP + kAtom, sP + kPBytes + kAtom, r, pt[1]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pt_full);
+      mbar_wait(pt_empty, c & 1);                  // dV MMAs of this chunk have consumed P^T
+      xb::store_row_atom(sP, sP + kPBytes, r, ds[0]);
+      xb::store_row_atom(sP + kAtom, sP + kPBytes + kAtom, r, ds[1]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dst_full);
+    }
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    uint32_t vv[32], vk[32];
+    tmem_ld_32x32(lane_addr + kTV, vv);
+    tmem_ld_32x32(lane_addr + kTK, vk);
+    tmem_ld_wait();
+    if (key_ok) {
+      float* dv = g.dv + (static_cast<long long>(b) * g.HW + key) * g.E + head * 32;
+      float* dk = g.dk + (static_cast<long long>(b) * g.HW + key) * g.E + head * 32;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        *reinterpret_cast<float4*>(dv + i) = make_float4(__uint_as_float(vv[i]), __uint_as_float(vv[i + 1]),
+                                                         __uint_as_float(vv[i + 2]), __uint_as_float(vv[i + 3]));
+        *reinterpret_cast<float4*>(dk + i) =
+            make_float4(__uint_as_float(vk[i]) * xb::kLn2, __uint_as_float(vk[i + 1]) * xb::kLn2,
+                        __uint_as_float(vk[i + 2]) * xb::kLn2, __uint_as_float(vk[i + 3]) * xb::kLn2);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace mpf
+
+extern "C" {
+
+int mpf_masked_xattn_bwd_f32(const float* q_hi, const float* q_lo, const float* qt_hi, const float* qt_lo,
+                             const float* k_hi, const float* k_lo, const float* kt_hi, const float* kt_lo,
+                             const float* v_hi, const float* v_lo, const float* do_hi, const float* do_lo,
+                             const float* dot_hi, const float* dot_lo, const uint32_t* mask_bits,
+                             const uint8_t* row_open, const float* lse2, const float* delta, float* dq, float* dk,
+                             float* dv, int B, int Qt, int qt_ld, int HW, int heads, int head_dim, int mask_words,
+                             void* stream) {
+  using namespace mpf;
+  clear_error();
+  MPF_REQUIRE(q_hi && q_lo && qt_hi && qt_lo && k_hi && k_lo && kt_hi && kt_lo && v_hi && v_lo && do_hi && do_lo &&
+                  dot_hi && dot_lo && mask_bits && lse2 && delta && dq && dk && dv,
+              "masked_xattn_bwd: null pointer");
+  MPF_REQUIRE(B > 0 && Qt > 0 && HW > 0 && heads > 0, "masked_xattn_bwd: sizes must be positive");
+  MPF_REQUIRE(head_dim == xb::kD, "masked_xattn_bwd: head_dim must be 32 (got %d)", head_dim);
+  MPF_REQUIRE(HW % 4 == 0 && qt_ld % 4 == 0 && qt_ld >= Qt,
+              "masked_xattn_bwd: HW (%d) and the row stride of Q^T / dO^T (%d, >= Qt = %d) must be multiples of 4",
+              HW, qt_ld, Qt);
+  MPF_REQUIRE(mask_words >= 2 * ((HW + 63) / 64), "masked_xattn_bwd: mask_words too small");
+  MPF_REQUIRE(heads <= 65535 && B <= 65535, "masked_xattn_bwd: grid too large");
+  const int E = heads * head_dim;
+  const long long qs = static_cast<long long>(Qt) * E, ks = static_cast<long long>(HW) * E;
+  CUtensorMap tq_h, tq_l, td_h, td_l, tk_h, tk_l, tv_h, tv_l, tkt_h, tkt_l;
+  int rc;
+  // ---- kernel A maps: Q/dO [128 x 32], K/V [64 x 32], K^T atoms [32 d x 32 keys]
+  if ((rc = make_tmap_f32_3d(&tq_h, q_hi, E, Qt, B, E, qs, 32, xa::kQ))) return rc;
+  if ((rc = make_tmap_f32_3d(&tq_l, q_lo, E, Qt, B, E, qs, 32, xa::kQ))) return rc;
+  if ((rc = make_tmap_f32_3d(&td_h, do_hi, E, Qt, B, E, qs, 32, xa::kQ))) return rc;
+  if ((rc = make_tmap_f32_3d(&td_l, do_lo, E, Qt, B, E, qs, 32, xa::kQ))) return rc;
+  if ((rc = make_tmap_f32_3d(&tk_h, k_hi, E, HW, B, E, ks, 32, xa::kK))) return rc;
+  if ((rc = make_tmap_f32_3d(&tk_l, k_lo, E, HW, B, E, ks, 32, xa::kK))) return rc;
+  if ((rc = make_tmap_f32_3d(&tv_h, v_hi, E, HW, B, E, ks, 32, xa::kK))) return rc;
+  if ((rc = make_tmap_f32_3d(&tv_l, v_lo, E, HW, B, E, ks, 32, xa::kK))) return rc;
+  if ((rc = make_tmap_f32_3d(&tkt_h, kt_hi, HW, E, B, HW, ks, 32, 32))) return rc;
+  if ((rc = make_tmap_f32_3d(&tkt_l, kt_lo, HW, E, B, HW, ks, 32, 32))) return rc;
+  static bool configured = false;
+  if (!configured) {
+    MPF_CUDA_OK(cudaFuncSetAttribute(masked_xattn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, xa::kSmem));
+    MPF_CUDA_OK(cudaFuncSetAttribute(masked_xattn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, xk::kSmem));
+    configured = true;
+  }
+  XbwdArgs g;
+  g.bits = mask_bits; g.row_open = row_open; g.lse2 = lse2; g.delta = delta; g.dq = dq; g.dk = dk; g.dv = dv;
+  g.B = B; g.Qt = Qt; g.HW = HW; g.E = E; g.heads = heads; g.words = mask_words;
+  g.inv_sqrt_d = 1.0f / sqrtf(static_cast<float>(head_dim));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid_a((Qt + xa::kQ - 1) / xa::kQ, heads, B);
+  masked_xattn_bwd_dq_kernel<<<grid_a, xb::kThreads, xa::kSmem, st>>>(tq_h, tq_l, td_h, td_l, tk_h, tk_l, tv_h, tv_l,
+                                                                      tkt_h, tkt_l, g);
+  count_launch();
+  if ((rc = finish_launch("masked_xattn_bwd_dq"))) return rc;
+  // ---- kernel B maps: K/V [128 x 32], Q/dO chunks [64 x 32], Q^T/dO^T atoms [32 d x 32 q]
+  CUtensorMap bk_h, bk_l, bv_h, bv_l, bq_h, bq_l, bd_h, bd_l, bqt_h, bqt_l, bdt_h, bdt_l;
+  if ((rc = make_tmap_f32_3d(&bk_h, k_hi, E, HW, B, E, ks, 32, xk::kKeys))) return rc;
+  if ((rc = make_tmap_f32_3d(&bk_l, k_lo, E, HW, B, E, ks, 32, xk::kKeys))) return rc;
+  if ((rc = make_tmap_f32_3d(&bv_h, v_hi, E, HW, B, E, ks, 32, xk::kKeys))) return rc;
+  if ((rc = make_tmap_f32_3d(&bv_l, v_lo, E, HW, B, E, ks, 32, xk::kKeys))) return rc;
+  if ((rc = make_tmap_f32_3d(&bq_h, q_hi, E, Qt, B, E, qs, 32, xk::kQc))) return rc;
+  if ((rc = make_tmap_f32_3d(&bq_l, q_lo, E, Qt, B, E, qs, 32, xk::kQc))) return rc;
+  if ((rc = make_tmap_f32_3d(&bd_h, do_hi, E, Qt, B, E, qs, 32, xk::kQc))) return rc;
+  if ((rc = make_tmap_f32_3d(&bd_l, do_lo, E, Qt, B, E, qs, 32, xk::kQc))) return rc;
+  const long long qts = static_cast<long long>(qt_ld) * E;
+  if ((rc = make_tmap_f32_3d(&bqt_h, qt_hi, Qt, E, B, qt_ld, qts, 32, 32))) return rc;
+  if ((rc = make_tmap_f32_3d(&bqt_l, qt_lo, Qt, E, B, qt_ld, qts, 32, 32))) return rc;
+  if ((rc = make_tmap_f32_3d(&bdt_h, dot_hi, Qt, E, B, qt_ld, qts, 32, 32))) return rc;
+  if ((rc = make_tmap_f32_3d(&bdt_l, dot_lo, Qt, E, B, qt_ld, qts, 32, 32))) return rc;
+  dim3 grid_b((HW + xk::kKeys - 1) / xk::kKeys, heads, B);
+  masked_xattn_bwd_dkv_kernel<<<grid_b, xb::kThreads, xk::kSmem, st>>>(bk_h, bk_l, bv_h, bv_l, bq_h, bq_l, bd_h, bd_l,
+                                                                       bqt_h, bqt_l, bdt_h, bdt_l, g);
+  count_launch();
+  return finish_launch("masked_xattn_bwd_dkv");
+}
+
+}  // extern "C"

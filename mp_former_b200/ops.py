@@ -1,11 +1,10 @@
 """Device ops of the hot path, each with exactly one implementation.
 
-Forward passes of ``linear``, ``mask_logits``, ``attn_mask_from_logits`` and ``masked_cross_attention``
-run on this package's hand-written sm_100a kernels (tcgen05 3xTF32 GEMM, bit-packed mask kernel, fused
-masked-attention kernel) through the C ABI.  Their backward passes are expressed with PyTorch CUDA
-library ops in round 1 (recomputing the probabilities from the saved log-sum-exp), except the
-input-gradient GEMM of ``linear`` which also runs on the tensor-core kernel.  ``self_attention`` and
-the tiny query-side layers stay on library ops (launch-latency bound).
+``linear``, ``mask_logits``, ``attn_mask_from_logits`` and ``masked_cross_attention`` run forward AND
+backward on this package's hand-written sm_100a kernels (tcgen05 3xTF32 GEMM incl. MN-major operands for the
+weight gradients, bit-packed mask kernel, fused masked-attention forward and the two backward kernels that
+recompute the probabilities from the saved log-sum-exp) through the C ABI.  ``self_attention`` and the tiny
+query-side layers (a few hundred rows) stay on library ops (launch-latency bound).
 
 Inputs must be CUDA fp32 tensors; there is no CPU path.
 """
@@ -16,8 +15,9 @@ import torch.nn.functional as F
 
 from . import _lib, native
 
-NATIVE_OPS = {"ms_deform_attn_forward", "ms_deform_attn_backward", "linear(3xTF32 tcgen05 GEMM)",
-              "mask_logits(3xTF32 tcgen05 GEMM)", "attn_mask_bits", "masked_cross_attention_fwd(tcgen05)"}
+NATIVE_OPS = {"ms_deform_attn_forward", "ms_deform_attn_backward", "linear fwd+bwd (3xTF32 tcgen05 GEMM)",
+              "mask_logits fwd+bwd (3xTF32 tcgen05 GEMM)", "attn_mask_bits",
+              "masked_cross_attention fwd+bwd (tcgen05)"}
 
 # fp32 ``sigmoid(x) < 0.5`` as evaluated by the reference (1/(1+exp(-x)) with a correctly rounded exp)
 # is EXACTLY ``x <= -0x1.7ffffep-23``: for -1.788e-7 < x < 0 the sigmoid rounds to 0.5 and the key stays
@@ -188,53 +188,50 @@ class _MaskedCrossAttention(torch.autograd.Function):
                                           k_lo.view(B, HW, E), vt_hi, vt_lo, bits, row_open, nhead)
         wo_hi, wo_lo = native.split_tf32(w_out)
         y = native.gemm(o.view(B * Qt, E), wo_hi, wo_lo, b_out).view(B, Qt, E)
-        ctx.save_for_backward(q_in, memory, pos, w_in, b_in, w_out, bits, row_open, o, lse2)
+        ctx.save_for_backward(q_in, memory, pos, w_in, b_in, w_out, bits, row_open, o, lse2,
+                              q_hi.view(B, Qt, E), q_lo.view(B, Qt, E), k_hi.view(B, HW, E), k_lo.view(B, HW, E))
         ctx.nhead, ctx.n_keys = nhead, n_keys
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        q_in, memory, pos, w_in, b_in, w_out, bits, row_open, o, lse2 = ctx.saved_tensors
+        (q_in, memory, pos, w_in, b_in, w_out, bits, row_open, o, lse2, q_hi, q_lo, k_hi, k_lo) = ctx.saved_tensors
         nhead = ctx.nhead
         B, Qt, E = q_in.shape
         HW = memory.shape[1]
         hd = E // nhead
-        inv = 1.0 / math.sqrt(hd)
-        gy2 = gy.reshape(B * Qt, E)
-        g_wout = gy2.t() @ o.reshape(B * Qt, E)
+        gy2 = gy.reshape(B * Qt, E).contiguous()
+        o2 = o.reshape(B * Qt, E)
+        g_wout = native.matmul_tn(gy2, o2)
         g_bout = gy2.sum(0)
-        go = (gy2 @ w_out).view(B, Qt, E)
-        # recompute projections and probabilities (library ops, fp32)
+        go = (gy2 @ w_out).view(B, Qt, E)                                           # d(attention output)
+        delta = (go.view(B, Qt, nhead, hd) * o.view(B, Qt, nhead, hd)).sum(-1).permute(0, 2, 1).contiguous()
+        # operands the forward did not keep: V row-major and K^T (both pre-split by the GEMM epilogue)
         wq, wk, wv = w_in[:E], w_in[E:2 * E], w_in[2 * E:]
-        kin = memory + pos
-        q = F.linear(q_in, wq, b_in[:E])
-        k = F.linear(kin, wk, b_in[E:2 * E])
-        v = F.linear(memory, wv, b_in[2 * E:])
-        qh, kh, vh = _split_heads(q * inv, nhead), _split_heads(k, nhead), _split_heads(v, nhead)
-        masked = native.unpack_bits(bits, ctx.n_keys) & ~row_open.unsqueeze(-1)     # [B,Q,HW]
-        s = torch.matmul(qh, kh.transpose(-1, -2))                                   # [B,h,Q,HW]
-        p = torch.softmax(s.masked_fill_(masked.unsqueeze(1), float("-inf")), -1)
-        del s
-        goh = _split_heads(go, nhead)
-        gv = torch.matmul(p.transpose(-1, -2), goh)                                  # [B,h,HW,hd]
-        gp = torch.matmul(goh, vh.transpose(-1, -2))                                 # [B,h,Q,HW]
-        gs = torch._softmax_backward_data(gp, p, -1, torch.float32)                  # p * (gp - sum(gp*p))
-        del gp, p
-        gq = torch.matmul(gs, kh) * inv                                              # [B,h,Q,hd] wrt unscaled q
-        gk = torch.matmul(gs.transpose(-1, -2), qh)                                  # [B,h,HW,hd]
-        gq = gq.transpose(1, 2).reshape(B * Qt, E)
-        gk = gk.transpose(1, 2).reshape(B * HW, E)
-        gv = gv.transpose(1, 2).reshape(B * HW, E)
-        g_win = torch.cat([gq.t() @ q_in.reshape(B * Qt, E), gk.t() @ kin.reshape(B * HW, E),
-                           gv.t() @ memory.reshape(B * HW, E)], 0)
-        g_bin = torch.cat([gq.sum(0), gk.sum(0), gv.sum(0)], 0)
-        g_qin = (gq @ wq).view(B, Qt, E) if ctx.needs_input_grad[0] else None
-        g_mem = None
-        g_pos = None
+        wk_hi, wk_lo = native.split_tf32(wk)
+        wv_hi, wv_lo = native.split_tf32(wv)
+        pos2 = pos.reshape(-1, E)
+        pos_k = native.gemm(pos2, wk_hi, wk_lo, b_in[E:2 * E])                      # [HW, E]
+        v_hi, v_lo = native.gemm(memory.reshape(B * HW, E), wv_hi, wv_lo, b_in[2 * E:], split_out=True)
+        kt_hi, kt_lo = native.gemm(memory, wk_hi[None].expand(B, -1, -1), wk_lo[None].expand(B, -1, -1), None,
+                                   resid=pos_k, resid_rows=HW, transpose_c=True, split_out=True)   # [B, E, HW]
+        dq, dk, dv = native.masked_xattn_bwd(q_hi, q_lo, k_hi, k_lo, kt_hi, kt_lo, v_hi.view(B, HW, E),
+                                             v_lo.view(B, HW, E), go.contiguous(), bits, row_open, lse2, delta,
+                                             nhead)
+        dq2, dk2, dv2 = dq.view(B * Qt, E), dk.view(B * HW, E), dv.view(B * HW, E)
+        mem2 = memory.reshape(B * HW, E)
+        # in-projection weight gradients: dW = dY^T X on the tensor cores (keys see memory + pos)
+        g_wk = native.matmul_tn(dk2, mem2) + native.matmul_tn(dk.sum(0), pos2)
+        g_win = torch.cat([native.matmul_tn(dq2, q_in.reshape(B * Qt, E)), g_wk, native.matmul_tn(dv2, mem2)], 0)
+        g_bin = torch.cat([dq2.sum(0), dk2.sum(0), dv2.sum(0)], 0)
+        g_qin = (dq2 @ wq).view(B, Qt, E) if ctx.needs_input_grad[0] else None
+        g_mem = g_pos = None
         if ctx.needs_input_grad[1]:
-            g_mem = (gk @ wk + gv @ wv).view(B, HW, E)
+            wkt_hi, wkt_lo = native.split_tf32(wk.t().contiguous())
+            wvt_hi, wvt_lo = native.split_tf32(wv.t().contiguous())
+            g_mem = (native.gemm(dk2, wkt_hi, wkt_lo) + native.gemm(dv2, wvt_hi, wvt_lo)).view(B, HW, E)
         if ctx.needs_input_grad[2]:
-            g_pos = (gk @ wk).view(B, HW, E).sum(0, keepdim=True)
+            g_pos = (dk.sum(0) @ wk).view(1, HW, E)
         return g_qin, g_mem, g_pos, g_win, g_bin, g_wout, g_bout, None, None, None
 
 
