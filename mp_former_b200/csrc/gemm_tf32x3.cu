@@ -351,6 +351,13 @@ int make_tmap_f32_3d(CUtensorMap* m, const float* base, long long d0, long long 
     set_error("cuTensorMapEncodeTiled not available from the driver");
     return MPF_ERR_UNSUPPORTED;
   }
+  // The encoder needs a current CUDA context; a fresh thread (e.g. PyTorch's autograd worker) may not have
+  // one bound yet.  cudaFree(0) binds the device's primary context to this thread (no-op afterwards).
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(nullptr);
+    ctx_bound = true;
+  }
   if (box0 * 4 != 128 || ld1 % 4 != 0 || ld2 % 4 != 0 || !aligned16(base)) {
     set_error("make_tmap: need a 128-byte box row, 16-byte aligned base and strides (ld1=%lld ld2=%lld)", ld1, ld2);
     return MPF_ERR_BAD_ARG;

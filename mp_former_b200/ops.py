@@ -112,8 +112,10 @@ class _MaskLogits(torch.autograd.Function):
         g2 = g2.contiguous()
         ok = (H * W) % 4 == 0 and C % 4 == 0
         if ctx.needs_input_grad[0]:
-            # dE[b] = dOut[b] (Q x HW) @ F[b] (HW x C): F is consumed MN-major (no transpose)
-            ge = native.gemm_general(g2, tokens, a_mn=False, b_mn=True) if ok else torch.bmm(g2, tokens)
+            # dE[b] = dOut[b] (Q x HW) @ F[b] (HW x C): a [Q x C] result reduced over H*W = 65536 -- only
+            # B*ceil(Q/128) output tiles, so the tensor-core kernel (no split-K across CTAs yet) is slower
+            # here than cuBLAS' split-K SGEMM (3.4 ms vs ~1 ms measured); library call until split-K lands.
+            ge = torch.bmm(g2, tokens)
         if ctx.needs_input_grad[1]:
             # dF[b] = dOut[b]^T (HW x Q) @ E[b] (Q x C): both operands MN-major
             gf = native.gemm_general(g2, mask_embed, a_mn=True, b_mn=True) if ok \
