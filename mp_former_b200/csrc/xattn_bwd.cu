@@ -395,13 +395,37 @@ masked_xattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKh, const __gr
     const int key = key0 + r;
     const bool key_ok = key < g.HW;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
-    const int word = key >> 5;                    // mask word holding this key (warp-uniform)
     const uint32_t bit = 1u << (key & 31);
     const float* lse_b = g.lse2 + (static_cast<long long>(b) * g.heads + head) * g.Qt;
     const float* dlt_b = g.delta + (static_cast<long long>(b) * g.heads + head) * g.Qt;
+    // per-chunk column data (log-sum-exp, delta, the mask word of each of the tile's four 32-key groups),
+    // staged once by the 128 softmax threads; double buffered by chunk parity, one named barrier per chunk
+    __shared__ float s_lse[2][kQc], s_dlt[2][kQc];
+    __shared__ uint32_t s_mw[2][kQc][4];
+    const int st_id = threadIdx.x - 128;          // 0..127
 
     for (int c = 0; c < NC; ++c) {
       const int qc0 = c * kQc;
+      const int pb = c & 1;
+      if (st_id < kQc) {
+        const int q = qc0 + st_id;
+        s_lse[pb][st_id] = q < g.Qt ? __ldg(lse_b + q) : 0.f;
+        s_dlt[pb][st_id] = q < g.Qt ? __ldg(dlt_b + q) : 0.f;
+      }
+#pragma unroll
+      for (int i = st_id; i < kQc * 4; i += 128) {
+        const int ql = i >> 2, wg = i & 3;
+        const int q = qc0 + ql;
+        uint32_t w = 0xFFFFFFFFu;                  // queries beyond Qt contribute nothing
+        if (q < g.Qt) {
+          const long long qi = static_cast<long long>(b) * g.Qt + q;
+          const bool open = g.row_open != nullptr && g.row_open[qi] != 0;
+          const int wi = (key0 >> 5) + wg;
+          w = open ? 0u : (wi < g.words ? g.bits[qi * g.words + wi] : 0xFFFFFFFFu);
+        }
+        s_mw[pb][ql][wg] = w;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(st_full, c & 1);
       tc_fence_after();
       float pt[2][32], ds[2][32];
@@ -413,19 +437,11 @@ masked_xattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKh, const __gr
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const int q = qc0 + h * 32 + i;
-          float p = 0.f, d = 0.f;
-          if (q < g.Qt && key_ok) {                // warp-uniform in q; key_ok differs only in the last tile
-            const long long qi = static_cast<long long>(b) * g.Qt + q;
-            const bool open = g.row_open != nullptr && g.row_open[qi] != 0;
-            const bool masked = !open && (g.bits[qi * g.words + word] & bit) != 0u;
-            if (!masked) {
-              p = exp2f(__uint_as_float(sv[i]) - __ldg(lse_b + q));
-              d = p * (__uint_as_float(pv[i]) - __ldg(dlt_b + q));
-            }
-          }
+          const int ql = h * 32 + i;
+          const bool masked = !key_ok || (s_mw[pb][ql][ew] & bit) != 0u;
+          const float p = masked ? 0.f : exp2f(__uint_as_float(sv[i]) - s_lse[pb][ql]);
           pt[h][i] = p;
-          ds[h][i] = d;
+          ds[h][i] = p * (__uint_as_float(pv[i]) - s_dlt[pb][ql]);
         }
       }
       tc_fence_before();
