@@ -143,13 +143,16 @@ int mpf_gemm_tf32x3_ex(const float* A, long long lda, long long a_batch_stride, 
  * With both operands MN-major this computes dW = dY^T X (weight gradient of an nn.Linear, reduction over
  * the token dimension; the batch dimension then enumerates K-splits whose partial products the caller
  * sums) and dF = dOut^T E of the mask-logit einsum without any transposed copy.  K need not be a
- * multiple of 32 (the tail is zero-filled by TMA).  lda / ldb are the row strides of the stored layout. */
+ * multiple of 32 (the tail is zero-filled by TMA).  lda / ldb are the row strides of the stored layout.
+ * k_splits > 1 cuts the reduction into k_splits ranges handled by different CTAs; C must then hold
+ * batch*k_splits slabs ([batch, k_splits, M, N]) of partial sums which the caller adds (no bias / ReLU /
+ * residual / scaling in that mode). */
 int mpf_gemm_tf32x3_general(const float* A, int a_mn_major, long long lda, long long a_batch_stride,
                             const float* B, const float* B_lo, int b_mn_major, long long ldb,
                             long long b_batch_stride, const float* bias, float* C, float* C_lo,
                             long long ldc, long long c_batch_stride, const float* resid, long long resid_ld,
                             int resid_rows, int resid_cols, float alpha, int batch, int M, int N, int K,
-                            int relu, int transpose_c, void* stream);
+                            int k_splits, int relu, int transpose_c, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Boolean stage of the prediction heads, bit-packed:

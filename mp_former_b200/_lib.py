@@ -39,7 +39,7 @@ SIGNATURES = {
                                     _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp]),
     "mpf_gemm_tf32x3_general": (_c_int, [_c_vp, _c_int, _c_ll, _c_ll, _c_vp, _c_vp, _c_int, _c_ll, _c_ll, _c_vp,
                                          _c_vp, _c_vp, _c_ll, _c_ll, _c_vp, _c_ll, _c_int, _c_int, ctypes.c_float,
-                                         _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp]),
+                                         _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp]),
     "mpf_attn_mask_bits_f32": (_c_int, [_c_vp, _c_ll] + [_c_int] * 5 + [_c_vp, _c_int, _c_vp]),
     "mpf_pack_bool_bits": (_c_int, [_c_vp, _c_int, _c_int, _c_vp, _c_int, _c_vp]),
     "mpf_masked_xattn_fwd_f32": (_c_int, [_c_vp] * 10 + [_c_int] * 6 + [_c_vp]),

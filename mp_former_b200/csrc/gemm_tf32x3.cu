@@ -24,6 +24,7 @@
 #include "sm100_ptx.cuh"
 #include "tmap.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace mpf {
@@ -51,6 +52,8 @@ struct GemmArgs {
   long long resid_ld;
   int resid_rows, resid_cols;                 // resid_rows == 0: one row per output row; cols < resid_cols get it
   float alpha;                                // x = (acc + bias + resid) * alpha, then ReLU
+  int k_splits;                               // K is cut into k_splits ranges of k_per_split (multiple of 32);
+  int k_per_split;                            // split s of batch b writes partial sums to C[(b*k_splits+s)]
 };
 
 template <int BN>
@@ -112,8 +115,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_tiles = g.batch * g.tiles_m * g.tiles_n;
-  const int kblocks = g.K / kBK;
+  const int num_tiles = g.batch * g.k_splits * g.tiles_m * g.tiles_n;
+  const int kblocks = g.k_per_split / kBK;
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -122,10 +125,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n_t = tile % g.tiles_n;
-        const int rest = tile / g.tiles_n;
+        int rest = tile / g.tiles_n;
         const int m_t = rest % g.tiles_m;
-        const int b = rest / g.tiles_m;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        rest /= g.tiles_m;
+        const int ks = rest % g.k_splits;
+        const int b = rest / g.k_splits;
+        const int kb0 = ks * kblocks;
+        for (int kbi = 0; kbi < kblocks; ++kbi) {
+          const int kb = kb0 + kbi;
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * Cfg::kStageBytes;
           mbar_arrive_expect_tx(&full[stage], kABytes + (SPLIT_B ? 1 : 2) * Cfg::kBBytes);
@@ -240,9 +247,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n_t = tile % g.tiles_n;
-      const int rest = tile / g.tiles_n;
+      int rest = tile / g.tiles_n;
       const int m_t = rest % g.tiles_m;
-      const int b = rest / g.tiles_m;
+      const int b = rest / g.tiles_m;             // = batch * k_splits + split: index of the output slab
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const int row = m_t * kBM + ew * 32 + lane;
@@ -403,7 +410,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tbh, const CUte
   }
   g.tiles_m = (g.M + kBM - 1) / kBM;
   g.tiles_n = (g.N + BN - 1) / BN;
-  const long long tiles = static_cast<long long>(g.batch) * g.tiles_m * g.tiles_n;
+  const long long tiles = static_cast<long long>(g.batch) * g.k_splits * g.tiles_m * g.tiles_n;
   const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
   gemm_tf32x3_kernel<BN, A_MN, B_MN, SPLIT_B><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tbh, tbl, g);
   count_launch();
@@ -428,23 +435,31 @@ int mpf_gemm_tf32x3_general(const float* A, int a_mn_major, long long lda, long 
                             const float* B, const float* B_lo, int b_mn_major, long long ldb,
                             long long b_batch_stride, const float* bias, float* C, float* C_lo, long long ldc,
                             long long c_batch_stride, const float* resid, long long resid_ld, int resid_rows,
-                            int resid_cols, float alpha, int batch, int M, int N, int K, int relu,
+                            int resid_cols, float alpha, int batch, int M, int N, int K, int k_splits, int relu,
                             int transpose_c, void* stream) {
   using namespace mpf;
   clear_error();
   MPF_REQUIRE(A && B && C, "gemm_tf32x3: null pointer argument");
+  MPF_REQUIRE(k_splits >= 1, "gemm_tf32x3: k_splits must be >= 1");
+  MPF_REQUIRE(k_splits == 1 || (!bias && !resid && !relu && !C_lo && alpha == 1.0f),
+              "gemm_tf32x3: split-K produces partial sums; bias / residual / ReLU / scale / split output are not allowed");
   MPF_REQUIRE(batch > 0 && M > 0 && N > 0 && K > 0, "gemm_tf32x3: dimensions must be positive");
   MPF_REQUIRE(lda % 4 == 0 && ldb % 4 == 0 && a_batch_stride % 4 == 0 && b_batch_stride % 4 == 0 &&
                   aligned16(A) && aligned16(B) && (B_lo == nullptr || aligned16(B_lo)),
               "gemm_tf32x3: A / B must be 16-byte aligned with strides that are multiples of 4 elements");
   MPF_REQUIRE(lda >= (a_mn_major ? M : K) && ldb >= (b_mn_major ? N : K), "gemm_tf32x3: row stride too small");
-  MPF_REQUIRE(static_cast<long long>(batch) * ((M + kBM - 1) / kBM) * ((N + 63) / 64) < (1ll << 31),
+  MPF_REQUIRE(static_cast<long long>(batch) * k_splits * ((M + kBM - 1) / kBM) * ((N + 63) / 64) < (1ll << 31),
               "gemm_tf32x3: too many tiles");
-  const int Kp = (K + kBK - 1) / kBK * kBK;     // the tail k-block is zero-filled by TMA
+  const int kblocks_total = (K + kBK - 1) / kBK;  // the tail k-block is zero-filled by TMA
+  const int k_per_split = (kblocks_total + k_splits - 1) / k_splits * kBK;
   int bn = 64;
   if (N > 64) {
     const int waste128 = (N + 127) / 128 * 128 - N, waste256 = (N + 255) / 256 * 256 - N;
     bn = (N <= 128 || waste128 < waste256) ? 128 : 256;
+  }
+  if (const char* force = getenv("MPF_GEMM_BN")) {        // tuning aid (benchmarks/kernel_probe.py)
+    const int f = atoi(force);
+    if (f == 64 || f == 128 || f == 256) bn = f;
   }
   const bool split_b = B_lo == nullptr;
   CUtensorMap ta, tbh, tbl;
@@ -463,7 +478,8 @@ int mpf_gemm_tf32x3_general(const float* A, int a_mn_major, long long lda, long 
   }
   GemmArgs g;
   g.C = C; g.C_lo = C_lo; g.bias = bias; g.c_batch_stride = c_batch_stride; g.ldc = ldc;
-  g.batch = batch; g.M = M; g.N = N; g.K = Kp; g.tiles_m = g.tiles_n = 0;
+  g.batch = batch; g.M = M; g.N = N; g.K = K; g.tiles_m = g.tiles_n = 0;
+  g.k_splits = k_splits; g.k_per_split = k_per_split;
   g.relu = relu; g.transpose_c = transpose_c;
   g.resid = resid; g.resid_ld = resid_ld; g.resid_rows = resid_rows;
   g.resid_cols = resid ? (resid_cols > 0 ? resid_cols : N) : 0;
@@ -498,7 +514,7 @@ int mpf_gemm_tf32x3_ex(const float* A, long long lda, long long a_batch_stride, 
     return MPF_ERR_BAD_ARG;
   }
   return mpf_gemm_tf32x3_general(A, 0, lda, a_batch_stride, B_hi, B_lo, 0, ldb, b_batch_stride, bias, C, C_lo, ldc,
-                                 c_batch_stride, resid, resid_ld, resid_rows, resid_cols, alpha, batch, M, N, K,
+                                 c_batch_stride, resid, resid_ld, resid_rows, resid_cols, alpha, batch, M, N, K, 1,
                                  relu, transpose_c, stream);
 }
 

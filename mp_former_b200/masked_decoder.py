@@ -101,7 +101,8 @@ class FFNLayer(nn.Module):
                 nn.init.xavier_uniform_(p)
 
     def forward(self, tgt):
-        tgt2 = self.linear2(self.dropout(F.relu(self.linear1(tgt))))
+        hidden = ops.linear(tgt, self.linear1.weight, self.linear1.bias, relu=True)
+        tgt2 = ops.linear(self.dropout(hidden), self.linear2.weight, self.linear2.bias)
         return self.norm(tgt + self.dropout(tgt2))
 
 
@@ -116,7 +117,7 @@ class MLP(nn.Module):
 
     def forward(self, x):
         for i, layer in enumerate(self.layers):
-            x = F.relu(layer(x)) if i < self.num_layers - 1 else layer(x)
+            x = ops.linear(x, layer.weight, layer.bias, relu=i < self.num_layers - 1)
         return x
 
 
@@ -207,7 +208,7 @@ class _MaskedDecoderBase(nn.Module):
         attn_mask: ops.PackedMask, one bit per (image, query, key), shared by heads).
         ref decoder :1859-1877."""
         decoder_output = self.decoder_norm(output)
-        outputs_class = self.class_embed(decoder_output)
+        outputs_class = ops.linear(decoder_output, self.class_embed.weight, self.class_embed.bias)
         mask_embed = self.mask_embed(decoder_output)
         outputs_mask = ops.mask_logits(mask_embed, mask_features)
         attn_mask = ops.attn_mask_from_logits(outputs_mask, attn_mask_target_size)

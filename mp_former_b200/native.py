@@ -163,7 +163,8 @@ def masked_xattn_fwd(q_hi, q_lo, k_hi, k_lo, vt_hi, vt_lo, bits, row_open, heads
     return out, lse2
 
 
-def gemm_general(a, b, a_mn=False, b_mn=False, b_lo=None, bias=None, relu=False, transpose_c=False, alpha=1.0):
+def gemm_general(a, b, a_mn=False, b_mn=False, b_lo=None, bias=None, relu=False, transpose_c=False, alpha=1.0,
+                 k_splits=1):
     """C[i] = op(A[i]) @ op(B[i])^T with either operand optionally "MN-major" (stored [batch, K, M-or-N],
     i.e. already transposed) and B split into TF32 halves in-kernel when ``b_lo`` is None.
     Shapes (3-D, batch first; 2-D inputs are treated as batch 1):
@@ -191,65 +192,29 @@ def gemm_general(a, b, a_mn=False, b_mn=False, b_lo=None, bias=None, relu=False,
         raise RuntimeError(f"gemm_general: inner dimensions differ ({tuple(a.shape)} vs {tuple(b.shape)})")
     if bias is not None:
         bias = _f32c(bias, "bias").contiguous()
-    out = torch.empty((batch, N, M) if transpose_c else (batch, M, N), dtype=torch.float32, device=a.device)
+    k_splits = max(1, min(int(k_splits), (K + 31) // 32))
+    shape = (batch * k_splits, N, M) if transpose_c else (batch * k_splits, M, N)
+    out = torch.empty(shape, dtype=torch.float32, device=a.device)
     with torch.cuda.device(a.device):
         rc = _lib.load().mpf_gemm_tf32x3_general(
             a.data_ptr(), int(a_mn), a.stride(1), a.stride(0) if batch > 1 else a.shape[1] * a.stride(1),
             b.data_ptr(), None if b_lo is None else b_lo.data_ptr(), int(b_mn), b.stride(1),
             b.stride(0) if batch > 1 else b.shape[1] * b.stride(1),
             None if bias is None else bias.data_ptr(), out.data_ptr(), None, M if transpose_c else N,
-            out.stride(0), None, 0, 0, 0, float(alpha), batch, M, N, K, int(relu), int(transpose_c), _stream())
+            out.stride(0), None, 0, 0, 0, float(alpha), batch, M, N, K, k_splits, int(relu), int(transpose_c),
+            _stream())
     _lib.check(rc, "gemm_tf32x3_general")
+    if k_splits > 1:
+        out = out.view(batch, k_splits, *out.shape[1:]).sum(1)
     return out[0] if squeeze else out
 
 
 def matmul_tn(x, y, target_tiles=296):
     """x^T @ y for x [T, M], y [T, N] (reduction over the long token dimension T), e.g. the weight gradient
     dW = dY^T X of an nn.Linear: both operands are consumed MN-major straight from their row-major
-    storage; T is cut into K-splits (the GEMM's batch dimension) whose partial products are summed."""
+    storage; T is cut into K-splits handled by different CTAs whose partial products are summed."""
     T, M = x.shape
     N = y.shape[1]
     tiles = ((M + 127) // 128) * ((N + 127) // 128)
-    want = max(1, min(64, target_tiles // max(1, tiles)))
-    splits = 1
-    for s in range(want, 0, -1):                 # largest split count <= want with 32 | T / s
-        if T % s == 0 and (T // s) % 32 == 0:
-            splits = s
-            break
-    xs = x.view(splits, T // splits, M)
-    ys = y.view(splits, T // splits, N)
-    part = gemm_general(xs, ys, a_mn=True, b_mn=True)          # [splits, M, N]
-    return part.sum(0) if splits > 1 else part[0]
-
-
-def masked_xattn_bwd(q_hi, q_lo, k_hi, k_lo, kt_hi, kt_lo, v_hi, v_lo, d_o, bits, row_open, lse2, delta, heads):
-    """Backward of the fused masked cross-attention.  q_*: pre-scaled query halves [B,Qt,E]; k_*, v_*:
-    [B,HW,E]; kt_*: K^T [B,E,HW]; d_o: gradient of the attention output [B,Qt,E]; lse2, delta: [B,heads,Qt].
-    Returns (dq wrt the unscaled query projection, dk, dv)."""
-    B, Qt, E = q_hi.shape
-    HW = k_hi.shape[1]
-    qt_ld = (Qt + 3) // 4 * 4
-    do_hi, do_lo = split_tf32(d_o)
-
-    def transposed(t):                     # [B,Qt,E] -> [B,E,qt_ld] (zero padded); exact, so halves stay halves
-        out = torch.zeros((B, E, qt_ld), dtype=torch.float32, device=t.device)
-        out[:, :, :Qt] = t.transpose(1, 2)
-        return out
-    qt_hi, qt_lo, dot_hi, dot_lo = transposed(q_hi), transposed(q_lo), transposed(do_hi), transposed(do_lo)
-    dq = torch.empty((B, Qt, E), dtype=torch.float32, device=q_hi.device)
-    dk = torch.empty((B, HW, E), dtype=torch.float32, device=q_hi.device)
-    dv = torch.empty_like(dk)
-    ro = None if row_open is None else row_open.to(torch.uint8).contiguous()
-    ts = [q_hi, q_lo, qt_hi, qt_lo, k_hi, k_lo, kt_hi, kt_lo, v_hi, v_lo, do_hi, do_lo, dot_hi, dot_lo]
-    for t in ts:
-        if not t.is_contiguous():
-            raise RuntimeError("masked_xattn_bwd: operands must be contiguous")
-    bits = bits.contiguous()
-    lse2, delta = lse2.contiguous(), delta.contiguous()
-    with torch.cuda.device(q_hi.device):
-        rc = _lib.load().mpf_masked_xattn_bwd_f32(
-            *[t.data_ptr() for t in ts], bits.data_ptr(), None if ro is None else ro.data_ptr(),
-            lse2.data_ptr(), delta.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
-            B, Qt, qt_ld, HW, heads, E // heads, bits.shape[2], _stream())
-    _lib.check(rc, "masked_xattn_bwd")
-    return dq, dk, dv
+    splits = max(1, min(64, target_tiles // max(1, tiles), (T + 1023) // 1024))
+    return gemm_general(x, y, a_mn=True, b_mn=True, k_splits=splits)

@@ -112,10 +112,10 @@ class _MaskLogits(torch.autograd.Function):
         g2 = g2.contiguous()
         ok = (H * W) % 4 == 0 and C % 4 == 0
         if ctx.needs_input_grad[0]:
-            # dE[b] = dOut[b] (Q x HW) @ F[b] (HW x C): a [Q x C] result reduced over H*W = 65536 -- only
-            # B*ceil(Q/128) output tiles, so the tensor-core kernel (no split-K across CTAs yet) is slower
-            # here than cuBLAS' split-K SGEMM (3.4 ms vs ~1 ms measured); library call until split-K lands.
-            ge = torch.bmm(g2, tokens)
+            # dE[b] = dOut[b] (Q x HW) @ F[b] (HW x C): a small [Q x C] result reduced over H*W = 65536, so the
+            # reduction is cut into K-splits across CTAs; F is consumed MN-major (no transpose)
+            ge = native.gemm_general(g2, tokens, a_mn=False, b_mn=True, k_splits=16) if ok \
+                else torch.bmm(g2, tokens)
         if ctx.needs_input_grad[1]:
             # dF[b] = dOut[b]^T (HW x Q) @ E[b] (Q x C): both operands MN-major
             gf = native.gemm_general(g2, mask_embed, a_mn=True, b_mn=True) if ok \
@@ -163,7 +163,7 @@ def attn_mask_from_logits(outputs_mask, target_size):
 # ------------------------------------------------------------------------------------------------
 def _split_heads(x, nhead):
     B, L, E = x.shape
-    return x.view(B, L, nhead, E // nhead).transpose(1, 2)       # [B,h,L,hd]
+    return x.reshape(B, L, nhead, E // nhead).transpose(1, 2)    # [B,h,L,hd]
 
 
 class _MaskedCrossAttention(torch.autograd.Function):
@@ -262,14 +262,19 @@ def masked_cross_attention(q_in, memory, pos, w_in, b_in, w_out, b_out, nhead, m
 
 def self_attention(qk_in, v_in, w_in, b_in, w_out, b_out, nhead, tgt_mask=None):
     """nn.MultiheadAttention self-attention over the (few hundred) queries (ref decoder :42-52); tgt_mask
-    bool [Q,Q], True = not allowed (DN groups, ref decoder :1051-1059).  Library ops."""
+    bool [Q,Q], True = not allowed (DN groups, ref decoder :1051-1059).  Projections on the tensor-core
+    GEMM; the [Q x Q] attention itself is a library SDPA call (launch-latency bound)."""
     _cuda_only(qk_in, "tgt")
     E = qk_in.shape[-1]
-    q = F.linear(qk_in, w_in[:E], b_in[:E])
-    k = F.linear(qk_in, w_in[E:2 * E], b_in[E:2 * E])
-    v = F.linear(v_in, w_in[2 * E:], b_in[2 * E:])
+    if qk_in is v_in:                                              # no query_pos: one GEMM for q, k and v
+        qkv = linear(qk_in, w_in, b_in)
+        q, k, v = qkv[..., :E], qkv[..., E:2 * E], qkv[..., 2 * E:]
+    else:
+        qk = linear(qk_in, w_in[:2 * E], b_in[:2 * E])             # q and k share the input
+        q, k = qk[..., :E], qk[..., E:]
+        v = linear(v_in, w_in[2 * E:], b_in[2 * E:])
     allowed = None if tgt_mask is None else ~tgt_mask
     o = F.scaled_dot_product_attention(_split_heads(q, nhead), _split_heads(k, nhead),
                                        _split_heads(v, nhead), attn_mask=allowed)
     o = o.transpose(1, 2).reshape(qk_in.shape)
-    return F.linear(o, w_out, b_out)
+    return linear(o, w_out, b_out)

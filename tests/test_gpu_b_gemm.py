@@ -107,3 +107,19 @@ def test_matmul_tn_weight_gradient_shape():
     gw2 = native.matmul_tn(gy[:1004].contiguous(), x[:1004].contiguous())
     ref2 = gy[:1004].double().t() @ x[:1004].double()
     assert (gw2.double() - ref2).abs().max().item() / ref2.abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
+@pytest.mark.parametrize("M,N,K,batch,splits", [(120, 256, 4096, 2, 8), (256, 256, 1000, 1, 5), (288, 256, 43008, 1, 42)])
+def test_split_k(a_mn, b_mn, M, N, K, batch, splits):
+    """In-kernel split-K: partial products of K ranges from different CTAs, summed by the wrapper; the last
+    range may be ragged (zero-filled)."""
+    g = torch.Generator(device=DEV).manual_seed(M + N + K + splits)
+    a = torch.randn(batch, M, K, device=DEV, generator=g)
+    b = torch.randn(batch, N, K, device=DEV, generator=g)
+    a_in = a.transpose(1, 2).contiguous() if a_mn else a
+    b_in = b.transpose(1, 2).contiguous() if b_mn else b
+    y = native.gemm_general(a_in, b_in, a_mn=a_mn, b_mn=b_mn, k_splits=splits)
+    r = ref64(a, b)
+    assert y.shape == (batch, M, N)
+    assert (y.double() - r).abs().max().item() / r.abs().max().item() < 1e-4
