@@ -218,3 +218,36 @@ def matmul_tn(x, y, target_tiles=296):
     tiles = ((M + 127) // 128) * ((N + 127) // 128)
     splits = max(1, min(64, target_tiles // max(1, tiles), (T + 1023) // 1024))
     return gemm_general(x, y, a_mn=True, b_mn=True, k_splits=splits)
+
+
+def masked_xattn_bwd(q_hi, q_lo, k_hi, k_lo, kt_hi, kt_lo, v_hi, v_lo, d_o, bits, row_open, lse2, delta, heads):
+    """Backward of the fused masked cross-attention.  q_*: pre-scaled query halves [B,Qt,E]; k_*, v_*:
+    [B,HW,E]; kt_*: K^T [B,E,HW]; d_o: gradient of the attention output [B,Qt,E]; lse2, delta: [B,heads,Qt].
+    Returns (dq wrt the unscaled query projection, dk, dv)."""
+    B, Qt, E = q_hi.shape
+    HW = k_hi.shape[1]
+    qt_ld = (Qt + 3) // 4 * 4
+    do_hi, do_lo = split_tf32(d_o)
+
+    def transposed(t):                     # [B,Qt,E] -> [B,E,qt_ld] (zero padded); exact, so halves stay halves
+        out = torch.zeros((B, E, qt_ld), dtype=torch.float32, device=t.device)
+        out[:, :, :Qt] = t.transpose(1, 2)
+        return out
+    qt_hi, qt_lo, dot_hi, dot_lo = transposed(q_hi), transposed(q_lo), transposed(do_hi), transposed(do_lo)
+    dq = torch.empty((B, Qt, E), dtype=torch.float32, device=q_hi.device)
+    dk = torch.empty((B, HW, E), dtype=torch.float32, device=q_hi.device)
+    dv = torch.empty_like(dk)
+    ro = None if row_open is None else row_open.to(torch.uint8).contiguous()
+    ts = [q_hi, q_lo, qt_hi, qt_lo, k_hi, k_lo, kt_hi, kt_lo, v_hi, v_lo, do_hi, do_lo, dot_hi, dot_lo]
+    for t in ts:
+        if not t.is_contiguous():
+            raise RuntimeError("masked_xattn_bwd: operands must be contiguous")
+    bits = bits.contiguous()
+    lse2, delta = lse2.contiguous(), delta.contiguous()
+    with torch.cuda.device(q_hi.device):
+        rc = _lib.load().mpf_masked_xattn_bwd_f32(
+            *[t.data_ptr() for t in ts], bits.data_ptr(), None if ro is None else ro.data_ptr(),
+            lse2.data_ptr(), delta.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+            B, Qt, qt_ld, HW, heads, E // heads, bits.shape[2], _stream())
+    _lib.check(rc, "masked_xattn_bwd")
+    return dq, dk, dv
