@@ -74,6 +74,26 @@ int mpf_msda_forward_f64(const double* value, const int64_t* spatial_shapes,
                          int channels, int num_levels, int num_query, int num_point, double* out,
                          void* stream);
 
+/* Encoder-fused form: consumes the raw output of the offsets+logits projection and the reference points;
+ * the softmax over the L*P logits and  loc = ref + off / (W_l, H_l)  (ref ops/modules/ms_deform_attn.py:
+ * 102-109) are evaluated inside the kernel.
+ *   offsets_logits [batch, num_query, M*L*P*3]: first M*L*P*2 offsets laid out (m, l, p, xy), then M*L*P
+ *                  attention logits laid out (m, l, p)  (= cat(sampling_offsets(q), attention_weights(q)))
+ *   reference_points [*, num_query, L, 2] with batch stride ref_batch_stride elements (0 = shared)
+ * Supported: P == 4, channels in {16, 32, 64}, L <= 4; otherwise MPF_ERR_UNSUPPORTED (use the plain form).
+ * The backward returns grad_value (zero-filled, then accumulated) and grad_offsets_logits (overwritten). */
+int mpf_msda_enc_forward_f32(const float* value, const int64_t* spatial_shapes,
+                             const int64_t* level_start_index, const float* offsets_logits,
+                             const float* reference_points, long long ref_batch_stride, int batch,
+                             int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                             int num_point, float* out, const int64_t* spatial_shapes_host, void* stream);
+int mpf_msda_enc_backward_f32(const float* grad_out, const float* value, const int64_t* spatial_shapes,
+                              const int64_t* level_start_index, const float* offsets_logits,
+                              const float* reference_points, long long ref_batch_stride, int batch,
+                              int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                              int num_point, float* grad_value, float* grad_offsets_logits,
+                              const int64_t* spatial_shapes_host, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Multi-scale deformable attention, backward.
  * ref: .../src/ms_deform_attn.h:47-66 (ms_deform_attn_backward), .../cuda/ms_deform_attn_cuda.cu:88-158,
@@ -146,13 +166,15 @@ int mpf_gemm_tf32x3_ex(const float* A, long long lda, long long a_batch_stride, 
  * multiple of 32 (the tail is zero-filled by TMA).  lda / ldb are the row strides of the stored layout.
  * k_splits > 1 cuts the reduction into k_splits ranges handled by different CTAs; C must then hold
  * batch*k_splits slabs ([batch, k_splits, M, N]) of partial sums which the caller adds (no bias / ReLU /
- * residual / scaling in that mode). */
+ * residual / scaling in that mode).  gate (optional, [M, gate_ld], batch 1): the result is zeroed where
+ * gate[m][n] <= 0 -- the ReLU backward of the layer below fused into this layer's input-gradient GEMM. */
 int mpf_gemm_tf32x3_general(const float* A, int a_mn_major, long long lda, long long a_batch_stride,
                             const float* B, const float* B_lo, int b_mn_major, long long ldb,
                             long long b_batch_stride, const float* bias, float* C, float* C_lo,
                             long long ldc, long long c_batch_stride, const float* resid, long long resid_ld,
-                            int resid_rows, int resid_cols, float alpha, int batch, int M, int N, int K,
-                            int k_splits, int relu, int transpose_c, void* stream);
+                            int resid_rows, int resid_cols, const float* gate, long long gate_ld, float alpha,
+                            int batch, int M, int N, int K, int k_splits, int relu, int transpose_c,
+                            void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Boolean stage of the prediction heads, bit-packed:

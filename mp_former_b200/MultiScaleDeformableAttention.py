@@ -154,3 +154,62 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
                 grad_aw.data_ptr(), stream)
     _lib.check(rc, "ms_deform_attn_backward")
     return [grad_value, grad_loc, grad_aw]
+
+
+# ------------------------------------------------------------------------------------------------
+# Encoder-fused form (extension to the reference's extension API): consumes the raw projection output
+# cat(sampling_offsets(q), attention_weights(q)) and the reference points; softmax and location arithmetic
+# run inside the kernel (see include/mpformer_b200.h, mpf_msda_enc_*).
+# ------------------------------------------------------------------------------------------------
+def enc_supported(value, num_levels, num_points):
+    D = value.shape[-1]
+    return value.dtype == torch.float32 and num_points == 4 and D in (16, 32, 64) and num_levels <= 4
+
+
+def _ref_stride(reference_points, batch):
+    if reference_points.shape[0] == 1 or reference_points.stride(0) == 0:
+        return 0
+    if reference_points.shape[0] != batch:
+        raise RuntimeError("reference_points batch mismatch")
+    return reference_points.stride(0)
+
+
+def ms_deform_attn_enc_forward(value, spatial_shapes, level_start_index, offsets_logits, reference_points,
+                               num_points, host_shapes=None):
+    """value [N,S,M,D]; offsets_logits [N,Lq,M*L*P*3]; reference_points [N or 1, Lq, L, 2] -> [N,Lq,M*D]."""
+    _check_inputs([("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+                   ("offsets_logits", offsets_logits)])
+    B, S, M, D = value.shape
+    L = spatial_shapes.shape[0]
+    Lq = offsets_logits.shape[1]
+    if offsets_logits.shape != (B, Lq, M * L * num_points * 3) or reference_points.shape[1:] != (Lq, L, 2):
+        raise RuntimeError("ms_deform_attn_enc: inconsistent shapes")
+    ref = reference_points if reference_points[0].is_contiguous() else reference_points.contiguous()
+    out = torch.empty((B, Lq, M * D), dtype=value.dtype, device=value.device)
+    with torch.cuda.device(value.device), _Timed("fwd"):
+        rc = _lib.load().mpf_msda_enc_forward_f32(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), offsets_logits.data_ptr(),
+            ref.data_ptr(), _ref_stride(ref, B), B, S, M, D, L, Lq, num_points, out.data_ptr(),
+            _host_shapes_array(spatial_shapes, host_shapes), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "ms_deform_attn_enc_forward")
+    return out
+
+
+def ms_deform_attn_enc_backward(value, spatial_shapes, level_start_index, offsets_logits, reference_points,
+                                grad_output, num_points, host_shapes=None):
+    """Returns [grad_value, grad_offsets_logits]."""
+    _check_inputs([("value", value), ("offsets_logits", offsets_logits), ("grad_output", grad_output)])
+    B, S, M, D = value.shape
+    L = spatial_shapes.shape[0]
+    Lq = offsets_logits.shape[1]
+    ref = reference_points if reference_points[0].is_contiguous() else reference_points.contiguous()
+    grad_value = torch.empty_like(value)
+    grad_ow = torch.empty_like(offsets_logits)
+    with torch.cuda.device(value.device), _Timed("bwd"):
+        rc = _lib.load().mpf_msda_enc_backward_f32(
+            grad_output.data_ptr(), value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+            offsets_logits.data_ptr(), ref.data_ptr(), _ref_stride(ref, B), B, S, M, D, L, Lq, num_points,
+            grad_value.data_ptr(), grad_ow.data_ptr(), _host_shapes_array(spatial_shapes, host_shapes),
+            torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "ms_deform_attn_enc_backward")
+    return [grad_value, grad_ow]

@@ -10,6 +10,7 @@ from . import _lib
 _lib.load()
 
 from . import MultiScaleDeformableAttention  # noqa: E402,F401
+from . import msdeform_attn  # noqa: E402,F401
 from .msdeform_attn import MSDeformAttn, MSDeformAttnFunction  # noqa: E402,F401
 from .position_encoding import PositionEmbeddingSine  # noqa: E402,F401
 from .pixel_decoder import (MSDeformAttnPixelDecoder, MSDeformAttnTransformerEncoderOnly,  # noqa: E402,F401

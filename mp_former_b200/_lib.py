@@ -30,6 +30,8 @@ SIGNATURES = {
     "mpf_msda_backward_f32": (_c_int, _MSDA_BWD),
     "mpf_msda_backward_f32_ex": (_c_int, _MSDA_BWD_EX),
     "mpf_msda_backward_f64": (_c_int, _MSDA_BWD),
+    "mpf_msda_enc_forward_f32": (_c_int, [_c_vp] * 5 + [_c_ll] + [_c_int] * 7 + [_c_vp, _c_vp, _c_vp]),
+    "mpf_msda_enc_backward_f32": (_c_int, [_c_vp] * 6 + [_c_ll] + [_c_int] * 7 + [_c_vp, _c_vp, _c_vp, _c_vp]),
     "mpf_split_tf32": (_c_int, [_c_vp, _c_vp, _c_vp, ctypes.c_longlong, _c_vp]),
     "mpf_gemm_tf32x3": (_c_int, [_c_vp, ctypes.c_longlong, ctypes.c_longlong, _c_vp, _c_vp,
                                  ctypes.c_longlong, ctypes.c_longlong, _c_vp, _c_vp, ctypes.c_longlong,
@@ -38,7 +40,8 @@ SIGNATURES = {
                                     _c_ll, _c_ll, _c_vp, _c_ll, _c_int, _c_int, ctypes.c_float,
                                     _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp]),
     "mpf_gemm_tf32x3_general": (_c_int, [_c_vp, _c_int, _c_ll, _c_ll, _c_vp, _c_vp, _c_int, _c_ll, _c_ll, _c_vp,
-                                         _c_vp, _c_vp, _c_ll, _c_ll, _c_vp, _c_ll, _c_int, _c_int, ctypes.c_float,
+                                         _c_vp, _c_vp, _c_ll, _c_ll, _c_vp, _c_ll, _c_int, _c_int, _c_vp, _c_ll,
+                                         ctypes.c_float,
                                          _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp]),
     "mpf_attn_mask_bits_f32": (_c_int, [_c_vp, _c_ll] + [_c_int] * 5 + [_c_vp, _c_int, _c_vp]),
     "mpf_pack_bool_bits": (_c_int, [_c_vp, _c_int, _c_int, _c_vp, _c_int, _c_vp]),

@@ -52,6 +52,8 @@ struct GemmArgs {
   long long resid_ld;
   int resid_rows, resid_cols;                 // resid_rows == 0: one row per output row; cols < resid_cols get it
   float alpha;                                // x = (acc + bias + resid) * alpha, then ReLU
+  const float* gate;                          // optional [M, gate_ld]: x = gate[row][n] > 0 ? x : 0 (ReLU backward)
+  long long gate_ld;
   int k_splits;                               // K is cut into k_splits ranges of k_per_split (multiple of 32);
   int k_per_split;                            // split s of batch b writes partial sums to C[(b*k_splits+s)]
 };
@@ -256,6 +258,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const bool row_ok = row < g.M;
       const long long boff = static_cast<long long>(b) * g.c_batch_stride;
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * BN);
+      const float* grow = (g.gate != nullptr && row_ok) ? g.gate + static_cast<long long>(row) * g.gate_ld : nullptr;
       const float* rrow = nullptr;
       if (g.resid != nullptr && row_ok)
         rrow = g.resid + static_cast<long long>(g.resid_rows > 0 ? row % g.resid_rows : row) * g.resid_ld;
@@ -274,6 +277,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           if (rrow != nullptr && n0 + j < g.resid_cols) x += __ldg(rrow + n0 + j);
           x *= g.alpha;
           if (g.relu) x = fmaxf(x, 0.f);
+          if (grow != nullptr && n0 + j < g.N && !(__ldg(grow + n0 + j) > 0.f)) x = 0.f;
           f[j] = x;
         }
         auto store = [&](float* base, const float (&val)[32]) {
@@ -435,13 +439,14 @@ int mpf_gemm_tf32x3_general(const float* A, int a_mn_major, long long lda, long 
                             const float* B, const float* B_lo, int b_mn_major, long long ldb,
                             long long b_batch_stride, const float* bias, float* C, float* C_lo, long long ldc,
                             long long c_batch_stride, const float* resid, long long resid_ld, int resid_rows,
-                            int resid_cols, float alpha, int batch, int M, int N, int K, int k_splits, int relu,
-                            int transpose_c, void* stream) {
+                            int resid_cols, const float* gate, long long gate_ld, float alpha, int batch, int M,
+                            int N, int K, int k_splits, int relu, int transpose_c, void* stream) {
   using namespace mpf;
   clear_error();
   MPF_REQUIRE(A && B && C, "gemm_tf32x3: null pointer argument");
   MPF_REQUIRE(k_splits >= 1, "gemm_tf32x3: k_splits must be >= 1");
-  MPF_REQUIRE(k_splits == 1 || (!bias && !resid && !relu && !C_lo && alpha == 1.0f),
+  MPF_REQUIRE(gate == nullptr || (batch == 1 && !transpose_c), "gemm_tf32x3: gate needs batch 1, row-major C");
+  MPF_REQUIRE(k_splits == 1 || (!bias && !resid && !relu && !C_lo && !gate && alpha == 1.0f),
               "gemm_tf32x3: split-K produces partial sums; bias / residual / ReLU / scale / split output are not allowed");
   MPF_REQUIRE(batch > 0 && M > 0 && N > 0 && K > 0, "gemm_tf32x3: dimensions must be positive");
   MPF_REQUIRE(lda % 4 == 0 && ldb % 4 == 0 && a_batch_stride % 4 == 0 && b_batch_stride % 4 == 0 &&
@@ -480,6 +485,7 @@ int mpf_gemm_tf32x3_general(const float* A, int a_mn_major, long long lda, long 
   g.C = C; g.C_lo = C_lo; g.bias = bias; g.c_batch_stride = c_batch_stride; g.ldc = ldc;
   g.batch = batch; g.M = M; g.N = N; g.K = K; g.tiles_m = g.tiles_n = 0;
   g.k_splits = k_splits; g.k_per_split = k_per_split;
+  g.gate = gate; g.gate_ld = gate_ld;
   g.relu = relu; g.transpose_c = transpose_c;
   g.resid = resid; g.resid_ld = resid_ld; g.resid_rows = resid_rows;
   g.resid_cols = resid ? (resid_cols > 0 ? resid_cols : N) : 0;
@@ -514,8 +520,8 @@ int mpf_gemm_tf32x3_ex(const float* A, long long lda, long long a_batch_stride, 
     return MPF_ERR_BAD_ARG;
   }
   return mpf_gemm_tf32x3_general(A, 0, lda, a_batch_stride, B_hi, B_lo, 0, ldb, b_batch_stride, bias, C, C_lo, ldc,
-                                 c_batch_stride, resid, resid_ld, resid_rows, resid_cols, alpha, batch, M, N, K, 1,
-                                 relu, transpose_c, stream);
+                                 c_batch_stride, resid, resid_ld, resid_rows, resid_cols, nullptr, 0, alpha, batch, M,
+                                 N, K, 1, relu, transpose_c, stream);
 }
 
 int mpf_gemm_tf32x3(const float* A, long long lda, long long a_batch_stride, const float* B_hi,

@@ -310,6 +310,278 @@ msda_bwd_vec_kernel(const float* __restrict__ grad_out, const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
+// Encoder-fused variants: the kernels consume the raw output ``ow`` of the offsets+logits projection
+// ([B, Lq, M*L*P*3]: offsets first, then attention logits) and the reference points, i.e. the softmax over
+// the L*P logits and the location arithmetic  loc = ref + off / (W_l, H_l)  (ref ops/modules/
+// ms_deform_attn.py:102-109) happen in the descriptor builder instead of five elementwise passes, two
+// slicing copies and their backward counterparts.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxLP = 16;     // L*P of the fused path (L <= 4, P = 4)
+
+struct EncSamples {
+  long long obase[2];          // offset of (b, q, 0) in ow, or -1 if padding
+  long long rbase[2];          // offset of (b or 0, q, 0, 0) in ref
+  float2 off[2], ref[2];
+};
+
+__device__ __forceinline__ void enc_samples_init(EncSamples& es, const MsdaTiling& tiling, int chunk, int b, int Lq,
+                                                 int owc, int L, long long ref_bstride) {
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int idx = threadIdx.x + k * kThreads;
+    const int q = query_of(tiling, chunk, idx >> 2, Lq);
+    es.obase[k] = q >= 0 ? (static_cast<long long>(b) * Lq + q) * owc : -1;
+    es.rbase[k] = q >= 0 ? b * ref_bstride + static_cast<long long>(q) * L * 2 : 0;
+    es.off[k] = es.ref[k] = make_float2(0.f, 0.f);
+  }
+}
+
+__device__ __forceinline__ void enc_samples_fetch(EncSamples& es, const float* __restrict__ ow,
+                                                  const float* __restrict__ ref, int m, int LP, int l) {
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    if (es.obase[k] >= 0) {
+      const int p = (threadIdx.x + k * kThreads) & 3;
+      es.off[k] = __ldg(reinterpret_cast<const float2*>(ow + es.obase[k] + (m * LP + l * 4 + p) * 2));
+      es.ref[k] = __ldg(reinterpret_cast<const float2*>(ref + es.rbase[k] + l * 2));
+    }
+  }
+}
+
+// softmax over the item's L*P logits -> s_aw[item][LP]   (threads 0..127, one item each)
+__device__ __forceinline__ void enc_softmax(float* s_aw, const float* __restrict__ ow, const MsdaTiling& tiling,
+                                            int chunk, int b, int m, int M, int Lq, int owc, int LP) {
+  if (threadIdx.x < kChunkQ) {
+    const int j = threadIdx.x;
+    const int q = query_of(tiling, chunk, j, Lq);
+    if (q >= 0) {
+      const float* lg = ow + (static_cast<long long>(b) * Lq + q) * owc + M * LP * 2 + m * LP;
+      float v[kMaxLP];
+      float mx = -INFINITY;
+#pragma unroll 4
+      for (int i = 0; i < LP; ++i) { v[i] = __ldg(lg + i); mx = fmaxf(mx, v[i]); }
+      float sum = 0.f;
+#pragma unroll 4
+      for (int i = 0; i < LP; ++i) { v[i] = expf(v[i] - mx); sum += v[i]; }
+#pragma unroll 4
+      for (int i = 0; i < LP; ++i) s_aw[j * kMaxLP + i] = v[i] / sum;
+    }
+  }
+}
+
+template <bool kBackward>
+__device__ __forceinline__ void enc_build_descriptors(int4* so, float4* sw, const EncSamples& es, const float* s_aw,
+                                                      int l, int H, int W, int MD) {
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int idx = threadIdx.x + k * kThreads;
+    const int j = idx >> 2, p = idx & 3;
+    int4 offs = make_int4(-1, -1, -1, -1);
+    float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (es.obase[k] >= 0) {
+      const float a = s_aw[j * kMaxLP + l * 4 + p];
+      // loc = ref + off / (W, H), then pixel = loc * size - 0.5: the reference's operation order
+      const float lx = es.ref[k].x + __fdiv_rn(es.off[k].x, static_cast<float>(W));
+      const float ly = es.ref[k].y + __fdiv_rn(es.off[k].y, static_cast<float>(H));
+      const float h_im = ly * H - 0.5f;
+      const float w_im = lx * W - 0.5f;
+      if ((h_im > -1.f) && (w_im > -1.f) && (h_im < H) && (w_im < W)) {
+        const float hf = floorf(h_im), wf = floorf(w_im);
+        const int h_low = static_cast<int>(hf), w_low = static_cast<int>(wf);
+        const float lh = h_im - hf, lw = w_im - wf;
+        const bool top = h_low >= 0, bot = h_low + 1 <= H - 1, lft = w_low >= 0, rgt = w_low + 1 <= W - 1;
+        const int rs = W * MD;
+        const int o1 = h_low * rs + w_low * MD;
+        offs.x = (top && lft) ? o1 : -1;
+        offs.y = (top && rgt) ? o1 + MD : -1;
+        offs.z = (bot && lft) ? o1 + rs : -1;
+        offs.w = (bot && rgt) ? o1 + rs + MD : -1;
+        if (kBackward) {
+          wv = make_float4(lh, lw, a, 0.f);
+        } else {
+          const float hh = 1.f - lh, hw = 1.f - lw;
+          wv = make_float4(hh * hw * a, hh * lw * a, lh * hw * a, lh * lw * a);
+        }
+      } else if (kBackward) {
+        wv.z = a;
+      }
+    }
+    so[j * kDescStride + p] = offs;
+    sw[j * kDescStride + p] = wv;
+  }
+}
+
+template <int LPI>
+__global__ void __launch_bounds__(kThreads, 3)
+msda_enc_fwd_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
+                    const int64_t* __restrict__ lstart, const float* __restrict__ ow, const float* __restrict__ ref,
+                    long long ref_bstride, int S, int M, int L, int Lq, float* __restrict__ out,
+                    const MsdaTiling tiling) {
+  constexpr int D = LPI * 4;
+  constexpr int SLOTS = kThreads / LPI;
+  constexpr int ITERS = kChunkQ / SLOTS;
+  __shared__ int4 so[kChunkQ * kDescStride];
+  __shared__ float4 sw[kChunkQ * kDescStride];
+  __shared__ float s_aw[kChunkQ * kMaxLP];
+
+  const int chunk = blockIdx.x, m = blockIdx.y, b = blockIdx.z;
+  const int slot = threadIdx.x / LPI, li = threadIdx.x % LPI;
+  const int MD = M * D, LP = L * 4, owc = M * LP * 3;
+  const float* vimg = value + static_cast<size_t>(b) * S * MD + m * D + li * 4;
+
+  float4 acc[ITERS];
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) acc[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  EncSamples es;
+  enc_samples_init(es, tiling, chunk, b, Lq, owc, L, ref_bstride);
+  enc_samples_fetch(es, ow, ref, m, LP, 0);
+  enc_softmax(s_aw, ow, tiling, chunk, b, m, M, Lq, owc, LP);
+  __syncthreads();
+  for (int l = 0; l < L; ++l) {
+    const int H = static_cast<int>(shapes[2 * l]), W = static_cast<int>(shapes[2 * l + 1]);
+    const float* vl = vimg + static_cast<size_t>(lstart[l]) * MD;
+    if (l > 0) __syncthreads();
+    enc_build_descriptors<false>(so, sw, es, s_aw, l, H, W, MD);
+    if (l + 1 < L) enc_samples_fetch(es, ow, ref, m, LP, l + 1);
+    __syncthreads();
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int j = it * SLOTS + slot;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int4 o = so[j * kDescStride + p];
+        const float4 w = sw[j * kDescStride + p];
+        const float4 v1 = o.x >= 0 ? ldg4(vl + o.x) : z;
+        const float4 v2 = o.y >= 0 ? ldg4(vl + o.y) : z;
+        const float4 v3 = o.z >= 0 ? ldg4(vl + o.z) : z;
+        const float4 v4 = o.w >= 0 ? ldg4(vl + o.w) : z;
+        acc[it].x += w.x * v1.x + w.y * v2.x + w.z * v3.x + w.w * v4.x;
+        acc[it].y += w.x * v1.y + w.y * v2.y + w.z * v3.y + w.w * v4.y;
+        acc[it].z += w.x * v1.z + w.y * v2.z + w.z * v3.z + w.w * v4.z;
+        acc[it].w += w.x * v1.w + w.y * v2.w + w.z * v3.w + w.w * v4.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int q = query_of(tiling, chunk, it * SLOTS + slot, Lq);
+    if (q >= 0)
+      *reinterpret_cast<float4*>(out + ((static_cast<size_t>(b) * Lq + q) * M + m) * D + li * 4) = acc[it];
+  }
+}
+
+template <int LPI>
+__global__ void __launch_bounds__(kThreads, 2)
+msda_enc_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict__ value,
+                    const int64_t* __restrict__ shapes, const int64_t* __restrict__ lstart,
+                    const float* __restrict__ ow, const float* __restrict__ ref, long long ref_bstride, int S, int M,
+                    int L, int Lq, float* __restrict__ grad_value, float* __restrict__ grad_ow,
+                    const MsdaTiling tiling) {
+  constexpr int D = LPI * 4;
+  constexpr int SLOTS = kThreads / LPI;
+  constexpr int ITERS = kChunkQ / SLOTS;
+  const unsigned FULL = 0xffffffffu;
+  __shared__ int4 so[kChunkQ * kDescStride];
+  __shared__ float4 sw[kChunkQ * kDescStride];
+  __shared__ float s_aw[kChunkQ * kMaxLP];
+  __shared__ float s_ga[kChunkQ * kMaxLP];      // d(loss)/d(attention weight) per item and sample
+
+  const int chunk = blockIdx.x, m = blockIdx.y, b = blockIdx.z;
+  const int slot = threadIdx.x / LPI, li = threadIdx.x % LPI;
+  const int MD = M * D, LP = L * 4, owc = M * LP * 3;
+  const size_t img_off = static_cast<size_t>(b) * S * MD + m * D + li * 4;
+  const float* vimg = value + img_off;
+  float* gvimg = grad_value + img_off;
+
+  float4 g[ITERS];
+  long long obase[ITERS];
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int q = query_of(tiling, chunk, it * SLOTS + slot, Lq);
+    obase[it] = q >= 0 ? (static_cast<long long>(b) * Lq + q) * owc : -1;
+    g[it] = q >= 0 ? ldg4(grad_out + ((static_cast<size_t>(b) * Lq + q) * M + m) * D + li * 4)
+                   : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+
+  EncSamples es;
+  enc_samples_init(es, tiling, chunk, b, Lq, owc, L, ref_bstride);
+  enc_samples_fetch(es, ow, ref, m, LP, 0);
+  enc_softmax(s_aw, ow, tiling, chunk, b, m, M, Lq, owc, LP);
+  __syncthreads();
+  for (int l = 0; l < L; ++l) {
+    const int H = static_cast<int>(shapes[2 * l]), W = static_cast<int>(shapes[2 * l + 1]);
+    const size_t loff = static_cast<size_t>(lstart[l]) * MD;
+    const float* vl = vimg + loff;
+    float* gvl = gvimg + loff;
+    if (l > 0) __syncthreads();
+    enc_build_descriptors<true>(so, sw, es, s_aw, l, H, W, MD);
+    if (l + 1 < L) enc_samples_fetch(es, ow, ref, m, LP, l + 1);
+    __syncthreads();
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int j = it * SLOTS + slot;
+      float mine_x = 0.f, mine_y = 0.f, mine_a = 0.f;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int4 o = so[j * kDescStride + p];
+        const float4 d = sw[j * kDescStride + p];
+        const float lh = d.x, lw = d.y, wgt = d.z;
+        const float hh = 1.f - lh, hw = 1.f - lw;
+        const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+        const float4 v1 = o.x >= 0 ? ldg4(vl + o.x) : z;
+        const float4 v2 = o.y >= 0 ? ldg4(vl + o.y) : z;
+        const float4 v3 = o.z >= 0 ? ldg4(vl + o.z) : z;
+        const float4 v4 = o.w >= 0 ? ldg4(vl + o.w) : z;
+        const float4 tg = make_float4(g[it].x * wgt, g[it].y * wgt, g[it].z * wgt, g[it].w * wgt);
+        if (o.x >= 0) red_add_v4(gvl + o.x, w1 * tg.x, w1 * tg.y, w1 * tg.z, w1 * tg.w);
+        if (o.y >= 0) red_add_v4(gvl + o.y, w2 * tg.x, w2 * tg.y, w2 * tg.z, w2 * tg.w);
+        if (o.z >= 0) red_add_v4(gvl + o.z, w3 * tg.x, w3 * tg.y, w3 * tg.z, w3 * tg.w);
+        if (o.w >= 0) red_add_v4(gvl + o.w, w4 * tg.x, w4 * tg.y, w4 * tg.z, w4 * tg.w);
+        float gh = 0.f, gw = 0.f, ga = 0.f;
+#define MPF_ACC(comp)                                                                         \
+  {                                                                                           \
+    const float ghw = -hw * v1.comp - lw * v2.comp + hw * v3.comp + lw * v4.comp;             \
+    const float gww = -hh * v1.comp + hh * v2.comp - lh * v3.comp + lh * v4.comp;             \
+    const float val = w1 * v1.comp + w2 * v2.comp + w3 * v3.comp + w4 * v4.comp;              \
+    gh += ghw * tg.comp;                                                                      \
+    gw += gww * tg.comp;                                                                      \
+    ga += val * g[it].comp;                                                                   \
+  }
+        MPF_ACC(x) MPF_ACC(y) MPF_ACC(z) MPF_ACC(w)
+#undef MPF_ACC
+#pragma unroll
+        for (int off = LPI / 2; off >= 1; off >>= 1) {
+          gh += __shfl_xor_sync(FULL, gh, off);
+          gw += __shfl_xor_sync(FULL, gw, off);
+          ga += __shfl_xor_sync(FULL, ga, off);
+        }
+        // d/d(off) = d/d(loc) / (W, H) = (W*gw)/W ... : the W, H factors of ref cuh:162-163 cancel
+        if (li == p) { mine_x = gw; mine_y = gh; mine_a = ga; }
+      }
+      if (obase[it] >= 0 && li < 4) {
+        *reinterpret_cast<float2*>(grad_ow + obase[it] + (m * LP + l * 4 + li) * 2) = make_float2(mine_x, mine_y);
+        s_ga[j * kMaxLP + l * 4 + li] = mine_a;
+      }
+    }
+  }
+  __syncthreads();
+  // softmax backward per item: d(logit_i) = aw_i * (ga_i - sum_j aw_j ga_j)
+  if (threadIdx.x < kChunkQ) {
+    const int j = threadIdx.x;
+    const int q = query_of(tiling, chunk, j, Lq);
+    if (q >= 0) {
+      float dot = 0.f;
+      for (int i = 0; i < LP; ++i) dot += s_aw[j * kMaxLP + i] * s_ga[j * kMaxLP + i];
+      float* gl = grad_ow + (static_cast<long long>(b) * Lq + q) * owc + M * LP * 2 + m * LP;
+      for (int i = 0; i < LP; ++i) gl[i] = s_aw[j * kMaxLP + i] * (s_ga[j * kMaxLP + i] - dot);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Generic kernels: one thread per (b, q, m, c); any D / L / P; float or double.
 // ------------------------------------------------------------------------------------------------
 template <typename T>
@@ -543,6 +815,50 @@ int msda_backward_f32(const float* grad_out, const float* value, const int64_t* 
   return finish_launch("msda_bwd_vec");
 }
 
+static bool enc_path_ok(int D, int L, int P, int M, int B, int* lpi) {
+  return vec_path_ok(D, L, P, M, B, lpi) && L * P <= kMaxLP;
+}
+
+int msda_enc_forward_f32(const float* value, const int64_t* shapes, const int64_t* lstart, const float* ow,
+                         const float* ref, long long ref_bstride, int B, int S, int M, int D, int L, int Lq, int P,
+                         float* out, const int64_t* shapes_host, cudaStream_t st) {
+  int lpi = 0;
+  if (!(enc_path_ok(D, L, P, M, B, &lpi) && aligned16(value) && aligned16(out) && aligned16(ow) && aligned16(ref))) {
+    set_error("msda_enc_forward: unsupported geometry for the fused path (D=%d L=%d P=%d)", D, L, P);
+    return MPF_ERR_UNSUPPORTED;
+  }
+  const MsdaTiling t = make_tiling(shapes_host, L, S, Lq);
+  dim3 grid(t.num_chunks, M, B);
+  switch (lpi) {
+    case 4: msda_enc_fwd_kernel<4><<<grid, kThreads, 0, st>>>(value, shapes, lstart, ow, ref, ref_bstride, S, M, L, Lq, out, t); break;
+    case 8: msda_enc_fwd_kernel<8><<<grid, kThreads, 0, st>>>(value, shapes, lstart, ow, ref, ref_bstride, S, M, L, Lq, out, t); break;
+    default: msda_enc_fwd_kernel<16><<<grid, kThreads, 0, st>>>(value, shapes, lstart, ow, ref, ref_bstride, S, M, L, Lq, out, t); break;
+  }
+  count_launch();
+  return finish_launch("msda_enc_fwd");
+}
+
+int msda_enc_backward_f32(const float* grad_out, const float* value, const int64_t* shapes, const int64_t* lstart,
+                          const float* ow, const float* ref, long long ref_bstride, int B, int S, int M, int D, int L,
+                          int Lq, int P, float* gv, float* gow, const int64_t* shapes_host, cudaStream_t st) {
+  int lpi = 0;
+  if (!(enc_path_ok(D, L, P, M, B, &lpi) && aligned16(value) && aligned16(grad_out) && aligned16(ow) &&
+        aligned16(ref) && aligned16(gv) && aligned16(gow))) {
+    set_error("msda_enc_backward: unsupported geometry for the fused path (D=%d L=%d P=%d)", D, L, P);
+    return MPF_ERR_UNSUPPORTED;
+  }
+  MPF_CUDA_OK(cudaMemsetAsync(gv, 0, static_cast<size_t>(B) * S * M * D * sizeof(float), st));
+  const MsdaTiling t = make_tiling(shapes_host, L, S, Lq);
+  dim3 grid(t.num_chunks, M, B);
+  switch (lpi) {
+    case 4: msda_enc_bwd_kernel<4><<<grid, kThreads, 0, st>>>(grad_out, value, shapes, lstart, ow, ref, ref_bstride, S, M, L, Lq, gv, gow, t); break;
+    case 8: msda_enc_bwd_kernel<8><<<grid, kThreads, 0, st>>>(grad_out, value, shapes, lstart, ow, ref, ref_bstride, S, M, L, Lq, gv, gow, t); break;
+    default: msda_enc_bwd_kernel<16><<<grid, kThreads, 0, st>>>(grad_out, value, shapes, lstart, ow, ref, ref_bstride, S, M, L, Lq, gv, gow, t); break;
+  }
+  count_launch();
+  return finish_launch("msda_enc_bwd");
+}
+
 }  // namespace mpf
 
 // ------------------------------------------------------------------------------------------------
@@ -643,6 +959,38 @@ int mpf_msda_backward_f64(const double* grad_out, const double* value,
                                          sampling_loc, attn_weight, batch, spatial_size, num_heads,
                                          channels, num_levels, num_query, num_point, grad_value,
                                          grad_sampling_loc, grad_attn_weight, st);
+}
+
+int mpf_msda_enc_forward_f32(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                             const float* offsets_logits, const float* reference_points, long long ref_batch_stride,
+                             int batch, int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                             int num_point, float* out, const int64_t* spatial_shapes_host, void* stream) {
+  mpf::clear_error();
+  int rc = mpf::check_dims(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point);
+  if (rc) return rc;
+  MPF_REQUIRE(value && spatial_shapes && level_start_index && offsets_logits && reference_points && out,
+              "msda_enc_forward: null pointer argument");
+  return mpf::msda_enc_forward_f32(value, spatial_shapes, level_start_index, offsets_logits, reference_points,
+                                   ref_batch_stride, batch, spatial_size, num_heads, channels, num_levels, num_query,
+                                   num_point, out, spatial_shapes_host, static_cast<cudaStream_t>(stream));
+}
+
+int mpf_msda_enc_backward_f32(const float* grad_out, const float* value, const int64_t* spatial_shapes,
+                              const int64_t* level_start_index, const float* offsets_logits,
+                              const float* reference_points, long long ref_batch_stride, int batch, int spatial_size,
+                              int num_heads, int channels, int num_levels, int num_query, int num_point,
+                              float* grad_value, float* grad_offsets_logits, const int64_t* spatial_shapes_host,
+                              void* stream) {
+  mpf::clear_error();
+  int rc = mpf::check_dims(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point);
+  if (rc) return rc;
+  MPF_REQUIRE(grad_out && value && spatial_shapes && level_start_index && offsets_logits && reference_points &&
+                  grad_value && grad_offsets_logits,
+              "msda_enc_backward: null pointer argument");
+  return mpf::msda_enc_backward_f32(grad_out, value, spatial_shapes, level_start_index, offsets_logits,
+                                    reference_points, ref_batch_stride, batch, spatial_size, num_heads, channels,
+                                    num_levels, num_query, num_point, grad_value, grad_offsets_logits,
+                                    spatial_shapes_host, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -101,8 +101,11 @@ class FFNLayer(nn.Module):
                 nn.init.xavier_uniform_(p)
 
     def forward(self, tgt):
-        hidden = ops.linear(tgt, self.linear1.weight, self.linear1.bias, relu=True)
-        tgt2 = ops.linear(self.dropout(hidden), self.linear2.weight, self.linear2.bias)
+        if self.dropout.p == 0.0 or not self.training:
+            tgt2 = ops.ffn(tgt, self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias)
+        else:
+            hidden = ops.linear(tgt, self.linear1.weight, self.linear1.bias, relu=True)
+            tgt2 = ops.linear(self.dropout(hidden), self.linear2.weight, self.linear2.bias)
         return self.norm(tgt + self.dropout(tgt2))
 
 

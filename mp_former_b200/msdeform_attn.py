@@ -43,6 +43,29 @@ class MSDeformAttnFunction(Function):
         return grad_value, None, None, grad_loc, grad_aw, None
 
 
+class MSDeformAttnEncFunction(Function):
+    """MSDeformAttn with the softmax over the L*P logits and loc = ref + off / (W_l, H_l) evaluated inside
+    the kernels (forward and backward): inputs are the raw projection output and the reference points."""
+
+    @staticmethod
+    def forward(ctx, value, spatial_shapes, level_start_index, offsets_logits, reference_points, num_points):
+        ctx.num_points = num_points
+        ctx.host_shapes = getattr(spatial_shapes, "_mpf_host_shapes", None)
+        out = MSDA.ms_deform_attn_enc_forward(value, spatial_shapes, level_start_index, offsets_logits,
+                                              reference_points, num_points, host_shapes=ctx.host_shapes)
+        ctx.save_for_backward(value, spatial_shapes, level_start_index, offsets_logits, reference_points)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, shapes, level_start, ow, ref = ctx.saved_tensors
+        grad_value, grad_ow = MSDA.ms_deform_attn_enc_backward(
+            value, shapes, level_start, ow, ref, grad_output.contiguous(), ctx.num_points,
+            host_shapes=ctx.host_shapes)
+        return grad_value, None, None, grad_ow, None, None
+
+
 def _is_power_of_2(n):
     if (not isinstance(n, int)) or (n < 0):
         raise ValueError("invalid input for _is_power_of_2: {} (type: {})".format(n, type(n)))
@@ -106,6 +129,11 @@ class MSDeformAttn(nn.Module):
         n_off = M * L * P * 2
         ow = ops.linear(query, torch.cat([self.sampling_offsets.weight, self.attention_weights.weight], 0),
                         torch.cat([self.sampling_offsets.bias, self.attention_weights.bias], 0))
+        if reference_points.shape[-1] == 2 and MSDA.enc_supported(value, L, P) and not reference_points.requires_grad:
+            # fused path: softmax + location arithmetic inside the MSDeformAttn kernels
+            output = MSDeformAttnEncFunction.apply(value.contiguous(), input_spatial_shapes,
+                                                   input_level_start_index, ow.contiguous(), reference_points, P)
+            return ops.linear(output, self.output_proj.weight, self.output_proj.bias)
         offsets = ow[..., :n_off].reshape(N, Len_q, M, L, P, 2)
         weights = F.softmax(ow[..., n_off:].reshape(N, Len_q, M, L * P), -1)
         weights = weights.view(N, Len_q, M, L, P)

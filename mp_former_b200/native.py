@@ -164,7 +164,7 @@ def masked_xattn_fwd(q_hi, q_lo, k_hi, k_lo, vt_hi, vt_lo, bits, row_open, heads
 
 
 def gemm_general(a, b, a_mn=False, b_mn=False, b_lo=None, bias=None, relu=False, transpose_c=False, alpha=1.0,
-                 k_splits=1):
+                 k_splits=1, gate=None):
     """C[i] = op(A[i]) @ op(B[i])^T with either operand optionally "MN-major" (stored [batch, K, M-or-N],
     i.e. already transposed) and B split into TF32 halves in-kernel when ``b_lo`` is None.
     Shapes (3-D, batch first; 2-D inputs are treated as batch 1):
@@ -201,8 +201,9 @@ def gemm_general(a, b, a_mn=False, b_mn=False, b_lo=None, bias=None, relu=False,
             b.data_ptr(), None if b_lo is None else b_lo.data_ptr(), int(b_mn), b.stride(1),
             b.stride(0) if batch > 1 else b.shape[1] * b.stride(1),
             None if bias is None else bias.data_ptr(), out.data_ptr(), None, M if transpose_c else N,
-            out.stride(0), None, 0, 0, 0, float(alpha), batch, M, N, K, k_splits, int(relu), int(transpose_c),
-            _stream())
+            out.stride(0), None, 0, 0, 0, None if gate is None else gate.data_ptr(),
+            0 if gate is None else gate.stride(0), float(alpha), batch, M, N, K, k_splits, int(relu),
+            int(transpose_c), _stream())
     _lib.check(rc, "gemm_tf32x3_general")
     if k_splits > 1:
         out = out.view(batch, k_splits, *out.shape[1:]).sum(1)

@@ -81,6 +81,44 @@ def linear(x, weight, bias=None, relu=False):
     return _Linear.apply(x, weight, bias, relu)
 
 
+class _FFN(torch.autograd.Function):
+    """y = relu(x W1^T + b1) W2^T + b2 as one autograd node, so the ReLU backward is fused into the epilogue
+    of the input-gradient GEMM of the second layer (``gate``) instead of a separate pass over [tokens, d_ffn]."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        x2 = x.reshape(-1, x.shape[-1])
+        w1_hi, w1_lo = native.split_tf32(w1)
+        hidden = native.gemm(x2, w1_hi, w1_lo, b1, relu=True)
+        w2_hi, w2_lo = native.split_tf32(w2)
+        y = native.gemm(hidden, w2_hi, w2_lo, b2)
+        ctx.save_for_backward(x2, w1, w2, hidden)
+        return y.view(*x.shape[:-1], w2.shape[0])
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, w1, w2, hidden = ctx.saved_tensors
+        g2 = gy.reshape(-1, gy.shape[-1]).contiguous()
+        w2t_hi, w2t_lo = native.split_tf32(w2.t().contiguous())
+        gh = native.gemm_general(g2, w2t_hi, b_lo=w2t_lo, gate=hidden)       # d(hidden) with the ReLU mask applied
+        gw2 = native.matmul_tn(g2, hidden)
+        gb2 = g2.sum(0)
+        w1t_hi, w1t_lo = native.split_tf32(w1.t().contiguous())
+        gx = native.gemm(gh, w1t_hi, w1t_lo).view(*gy.shape[:-1], w1.shape[1]) if ctx.needs_input_grad[0] else None
+        gw1 = native.matmul_tn(gh, x2)
+        gb1 = gh.sum(0)
+        return gx, gw1, gb1, gw2, gb2
+
+
+def ffn(x, w1, b1, w2, b2):
+    """Linear -> ReLU -> Linear (ref pixel_decoder/msdeformattn.py:116-120, decoder :165-169 with
+    dropout 0)."""
+    _cuda_only(x, "x")
+    if x.shape[-1] % 32 or w1.shape[0] % 32 or w2.shape[0] % 4:
+        return linear(linear(x, w1, b1, relu=True), w2, b2)
+    return _FFN.apply(x, w1, b1, w2, b2)
+
+
 # ------------------------------------------------------------------------------------------------
 # prediction heads: mask logits + boolean stage
 # ------------------------------------------------------------------------------------------------

@@ -120,8 +120,11 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
         return tensor if pos is None else tensor + pos
 
     def forward_ffn(self, src):
-        hidden = ops.linear(src, self.linear1.weight, self.linear1.bias, relu=True)
-        src2 = ops.linear(self.dropout2(hidden), self.linear2.weight, self.linear2.bias)
+        if self.dropout2.p == 0.0 or not self.training:
+            src2 = ops.ffn(src, self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias)
+        else:
+            hidden = ops.linear(src, self.linear1.weight, self.linear1.bias, relu=True)
+            src2 = ops.linear(self.dropout2(hidden), self.linear2.weight, self.linear2.bias)
         return self.norm2(src + self.dropout3(src2))
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None):
@@ -314,7 +317,10 @@ class MSDeformAttnPixelDecoder(nn.Module):
                 cur_fpn = lateral.norm(cur_fpn)
             if lateral.activation is not None:
                 cur_fpn = lateral.activation(cur_fpn)
-            up = F.interpolate(out[-1], size=cur_fpn.shape[-2:], mode="bilinear", align_corners=False)
+            # keep the whole FPN stage channels-last (the upsampled map would otherwise come back NCHW and
+            # force layout copies of the 256x256 maps around the 3x3 convolution)
+            up = F.interpolate(out[-1].contiguous(memory_format=torch.channels_last), size=cur_fpn.shape[-2:],
+                               mode="bilinear", align_corners=False)
             out.append(self.output_convs[idx](cur_fpn + up))
         multi_scale_features = out[:self.maskformer_num_feature_levels]
         return conv1x1_tokens(out[-1], self.mask_features), out[0], multi_scale_features

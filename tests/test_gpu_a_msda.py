@@ -150,3 +150,45 @@ def test_error_behaviour_matches_reference():
                                     torch.cat([a, a, a]), 2)
     with pytest.raises(RuntimeError):
         MSDA.ms_deform_attn_forward(v.half(), st, lsi, l.half(), a.half(), 128)
+
+
+@pytest.mark.parametrize("geom", [
+    dict(N=2, L=3, shapes=[(8, 8), (16, 16), (32, 32)], Lq=None, shared_ref=True),
+    dict(N=2, L=4, shapes=[(16, 16), (8, 8), (4, 4), (2, 2)], Lq=77, shared_ref=False),
+    dict(N=1, L=1, shapes=[(5, 36)], Lq=None, shared_ref=True),
+])
+def test_encoder_fused_softmax_and_locations(geom):
+    """MSDeformAttnEncFunction (softmax + loc = ref + off/(W,H) inside the kernels) vs the unfused arithmetic
+    of ref ops/modules/ms_deform_attn.py:102-118 evaluated with the oracle in fp64."""
+    g = torch.Generator().manual_seed(17)
+    M_, D, P, L = 8, 32, 4, geom["L"]
+    shapes = geom["shapes"]
+    S = sum(h * w for h, w in shapes)
+    Lq = geom["Lq"] or S
+    N = geom["N"]
+    value = torch.randn(N, S, M_, D, generator=g)
+    ow = torch.cat([torch.randn(N, Lq, M_ * L * P * 2, generator=g) * 2.0,
+                    torch.randn(N, Lq, M_ * L * P, generator=g)], -1)
+    ref = torch.rand(1 if geom["shared_ref"] else N, Lq, L, 2, generator=g) * 1.2 - 0.1
+    gy = torch.randn(N, Lq, M_ * D, generator=g)
+
+    def reference(value, ow, ref):
+        n_off = M_ * L * P * 2
+        off = ow[..., :n_off].reshape(N, Lq, M_, L, P, 2)
+        aw = torch.softmax(ow[..., n_off:].reshape(N, Lq, M_, L * P), -1).view(N, Lq, M_, L, P)
+        norm = torch.tensor([[w, h] for h, w in shapes], dtype=ow.dtype)
+        loc = ref.expand(N, -1, -1, -1)[:, :, None, :, None, :] + off / norm[None, None, None, :, None, :]
+        return O.msda_core(value, shapes, loc, aw)
+
+    v64, o64 = value.double().requires_grad_(True), ow.double().requires_grad_(True)
+    yr = reference(v64, o64, ref.double())
+    yr.backward(gy.double())
+    st, lsi = dev_shapes(shapes, True)
+    vd, od = value.to(DEV).requires_grad_(True), ow.to(DEV).requires_grad_(True)
+    refd = ref.to(DEV).expand(N, -1, -1, -1) if geom["shared_ref"] else ref.to(DEV)
+    y = M.msdeform_attn.MSDeformAttnEncFunction.apply(vd, st, lsi, od, refd, P)
+    y.backward(gy.to(DEV))
+    close(y.detach().cpu(), yr.detach().float(), 2e-5)
+    close(vd.grad.cpu(), v64.grad.float(), 1e-4)
+    scale = o64.grad.abs().max().item()
+    assert (od.grad.cpu().double() - o64.grad).abs().max().item() / scale < 2e-4

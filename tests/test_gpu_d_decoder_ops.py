@@ -129,3 +129,22 @@ def test_linear_and_mask_logits_autograd():
     assert rel(out, outr) < 1e-4 and rel(e.grad, er.grad) < 1e-3 and rel(f.grad, fr.grad) < 1e-3
     # NCHW-contiguous features are accepted too (one layout copy)
     assert rel(ops.mask_logits(e.detach(), f.detach().contiguous()), outr) < 1e-4
+
+
+def test_ffn_fused_relu_backward():
+    g = torch.Generator(device=DEV).manual_seed(9)
+    x = torch.randn(3, 500, 256, device=DEV, generator=g, requires_grad=True)
+    w1 = (torch.randn(1024, 256, device=DEV, generator=g) / 16).requires_grad_(True)
+    b1 = torch.randn(1024, device=DEV, generator=g).requires_grad_(True)
+    w2 = (torch.randn(256, 1024, device=DEV, generator=g) / 32).requires_grad_(True)
+    b2 = torch.randn(256, device=DEV, generator=g).requires_grad_(True)
+    y = ops.ffn(x, w1, b1, w2, b2)
+    gy = torch.randn(y.shape, device=DEV, generator=g)
+    y.backward(gy)
+    refs = [t.detach().double().requires_grad_(True) for t in (x, w1, b1, w2, b2)]
+    yr = F.linear(F.relu(F.linear(refs[0], refs[1], refs[2])), refs[3], refs[4])
+    yr.backward(gy.double())
+    assert rel(y, yr) < 1e-4
+    for name, a, r in zip(("x", "w1", "b1", "w2", "b2"), (x, w1, b1, w2, b2), refs):
+        scale = r.grad.abs().max().item()
+        assert (a.grad.double() - r.grad).abs().max().item() / scale < 2e-4, name

@@ -56,8 +56,10 @@ def install_cpu_ops(setattr_fn):
         return y.transpose(0, 1)
 
     setattr_fn(MSDA, "ms_deform_attn_forward", fwd)
+    setattr_fn(MSDA, "enc_supported", lambda value, L, P: False)       # CPU: exercise the unfused module path
     setattr_fn(_lib, "require_cuda", lambda t, n: None)
     setattr_fn(ops, "linear", linear)
+    setattr_fn(ops, "ffn", lambda x, w1, b1, w2, b2: F.linear(F.relu(F.linear(x, w1, b1)), w2, b2))
     setattr_fn(ops, "mask_logits", lambda e, f: torch.einsum("bqc,bchw->bqhw", e, f))
     setattr_fn(native, "attn_mask_bits", attn_mask_bits)
     setattr_fn(native, "pack_bool_bits", cpu_pack_bits)
