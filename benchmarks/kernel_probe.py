@@ -68,7 +68,15 @@ def main():
         alg_b = alg_f + 4 * (S * M * D + 3 * S * M * L * P) * B
         emit("msda_fwd_vec_kernel<8>", timeit(lambda: MSDA.ms_deform_attn_forward(value, st, lsi, loc, aw, 128)), alg_f)
         emit("msda_bwd_vec_kernel<8>", timeit(lambda: MSDA.ms_deform_attn_backward(value, st, lsi, loc, aw, gout, 128)), alg_b)
-        del value, loc, aw, gout
+        ow = torch.cat([rn(B, S, M * L * P * 2) * 2.0, rn(B, S, M * L * P)], -1).contiguous()
+        refp = ref[None, :, None, :].expand(1, S, L, 2).contiguous()
+        alg_ef = 4 * (S * M * D + S * M * L * P * 3 + S * M * D) * B
+        emit("msda_enc_fwd_kernel<8> (softmax+loc fused)",
+             timeit(lambda: MSDA.ms_deform_attn_enc_forward(value, st, lsi, ow, refp, P)), alg_ef)
+        emit("msda_enc_bwd_kernel<8> (softmax+loc fused)",
+             timeit(lambda: MSDA.ms_deform_attn_enc_backward(value, st, lsi, ow, refp, gout, P)),
+             alg_ef + 4 * (S * M * D + S * M * L * P * 3) * B)
+        del value, loc, aw, gout, ow
     if "gemm" in which:
         for (m, n, k, tag) in ((B * S, 1024, 256, "ffn.linear1"), (B * S, 256, 1024, "ffn.linear2"),
                                (B * S, 256, 256, "value_proj"), (B * S, 288, 256, "offsets+weights")):

@@ -47,6 +47,7 @@ struct GemmArgs {
   int relu;
   int transpose_c;
   int vec_store;                              // row-major float4 stores are legal
+  int vec_aux;                                // bias / resid / gate may be read as float4
   float* C_lo;                                // if set: C receives rn_tf32(x), C_lo rn_tf32(x - hi)
   const float* resid;                         // optional addend [resid_rows, resid_ld]; row % resid_rows
   long long resid_ld;
@@ -271,14 +272,58 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         tmem_ld_wait();
         float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(v[j]);
-          if (g.bias != nullptr && n0 + j < g.N) x += __ldg(g.bias + n0 + j);
-          if (rrow != nullptr && n0 + j < g.resid_cols) x += __ldg(rrow + n0 + j);
-          x *= g.alpha;
-          if (g.relu) x = fmaxf(x, 0.f);
-          if (grow != nullptr && n0 + j < g.N && !(__ldg(grow + n0 + j) > 0.f)) x = 0.f;
-          f[j] = x;
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        const bool full = n0 + 32 <= g.N;
+        // addends / gate are read 16 bytes at a time when the chunk is full and the pointers allow it
+        if (g.bias != nullptr) {
+          if (full && g.vec_aux) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + j));
+              f[j] += t.x; f[j + 1] += t.y; f[j + 2] += t.z; f[j + 3] += t.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < g.N) f[j] += __ldg(g.bias + n0 + j);
+          }
+        }
+        if (rrow != nullptr) {
+          if (n0 + 32 <= g.resid_cols && g.vec_aux) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(rrow + n0 + j));
+              f[j] += t.x; f[j + 1] += t.y; f[j + 2] += t.z; f[j + 3] += t.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < g.resid_cols) f[j] += __ldg(rrow + n0 + j);
+          }
+        }
+        if (g.alpha != 1.0f) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] *= g.alpha;
+        }
+        if (g.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (grow != nullptr) {
+          if (full && g.vec_aux) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(grow + n0 + j));
+              if (!(t.x > 0.f)) f[j] = 0.f;
+              if (!(t.y > 0.f)) f[j + 1] = 0.f;
+              if (!(t.z > 0.f)) f[j + 2] = 0.f;
+              if (!(t.w > 0.f)) f[j + 3] = 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < g.N && !(__ldg(grow + n0 + j) > 0.f)) f[j] = 0.f;
+          }
         }
         auto store = [&](float* base, const float (&val)[32]) {
           float* cb = base + boff;
@@ -492,6 +537,8 @@ int mpf_gemm_tf32x3_general(const float* A, int a_mn_major, long long lda, long 
   g.alpha = alpha;
   g.vec_store = (!transpose_c && ldc % 4 == 0 && c_batch_stride % 4 == 0 && aligned16(C) &&
                  (C_lo == nullptr || aligned16(C_lo))) ? 1 : 0;
+  g.vec_aux = ((bias == nullptr || aligned16(bias)) && (resid == nullptr || (aligned16(resid) && resid_ld % 4 == 0)) &&
+               (gate == nullptr || (aligned16(gate) && gate_ld % 4 == 0))) ? 1 : 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define MPF_DISPATCH_BN(AM, BM_, SB)                                              \
   do {                                                                            \

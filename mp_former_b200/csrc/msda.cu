@@ -473,7 +473,7 @@ msda_enc_fwd_kernel(const float* __restrict__ value, const int64_t* __restrict__
 }
 
 template <int LPI>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 3)
 msda_enc_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict__ value,
                     const int64_t* __restrict__ shapes, const int64_t* __restrict__ lstart,
                     const float* __restrict__ ow, const float* __restrict__ ref, long long ref_bstride, int S, int M,
