@@ -258,16 +258,36 @@ def run_ours(a):
         host = workload.synthetic_features(B, a.height, a.width, seed=rank, device="cpu", pin=True)
         h2d = sum(t_.numel() * t_.element_size() for t_ in host.values())
 
-        def e2e_step():
-            f = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-            return float(step(f).item())
-        e2e_step()
+        # Every step's inputs come from pinned host memory; the copy of step i+1 runs on a side stream while
+        # step i computes (double buffering, as a data loader would), and each step's loss is read back.
+        copy_stream = torch.cuda.Stream(device=dev)
+
+        def upload():
+            with torch.cuda.stream(copy_stream):
+                f = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return f, ev
+
+        def e2e_run(n):
+            nxt = upload()
+            last = 0.0
+            for i in range(n):
+                f, ev = nxt
+                torch.cuda.current_stream().wait_event(ev)
+                if i + 1 < n:
+                    nxt = upload()
+                loss = step(f)
+                for t_ in f.values():
+                    t_.record_stream(torch.cuda.current_stream())
+                last = float(loss.item())            # D2H read of the step's result
+            return last
+        e2e_run(2)
         sync()
         n_e2e = max(3, min(a.steps, 10))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(n_e2e):
-            e2e_step()
+        e2e_run(n_e2e)
         e1.record()
         sync()
         te = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -292,7 +312,8 @@ def run_ours(a):
         roof = None
         if fwd_ms:
             ach = alg / (fwd_ms / 1e3) / 1e9
-            roof = {"kernel": "msda_fwd_vec_kernel<8>", "bound": "hbm", "achieved": ach, "peak": hbm,
+            roof = {"kernel": "msda_enc_fwd_kernel<8> (MSDeformAttn forward, softmax+locations fused)",
+                    "bound": "hbm", "achieved": ach, "peak": hbm,
                     "unit": "GB/s", "frac": ach / hbm, "traffic": None,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                     "algorithmic_bytes_per_launch": alg, "avg_launch_ms": fwd_ms,
@@ -300,7 +321,7 @@ def run_ours(a):
                     "share_of_step": fwd_ms * len(prof["fwd_ms"]) / ms_total}
             if bwd_ms:
                 alg_b = (4 * (S * Mh * D * 2 + 3 * S * Mh * L * P) + 4 * (S * Mh * D + 3 * S * Mh * L * P)) * B
-                roof["backward"] = {"kernel": "msda_bwd_vec_kernel<8>", "avg_launch_ms": bwd_ms,
+                roof["backward"] = {"kernel": "msda_enc_bwd_kernel<8> (+ grad_value memset)", "avg_launch_ms": bwd_ms,
                                     "achieved": alg_b / (bwd_ms / 1e3) / 1e9,
                                     "frac": alg_b / (bwd_ms / 1e3) / 1e9 / hbm,
                                     "algorithmic_bytes_per_launch": alg_b,

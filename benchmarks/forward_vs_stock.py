@@ -79,8 +79,20 @@ def main():
         return O.decoder_forward(dsd, ms, mf, num_queries=100)
 
     a, b = ours(), stock()
-    err = ((a["pred_masks"] - b["pred_masks"]).abs() / b["pred_masks"].abs().clamp(min=1.0)).max().item()
-    err_l = ((a["pred_logits"] - b["pred_logits"]).abs() / b["pred_logits"].abs().clamp(min=1.0)).max().item()
+
+    def rel(x, y):
+        return (x - y).abs() / y.abs().clamp(min=1.0)
+    err = rel(a["pred_masks"], b["pred_masks"]).max().item()
+    err_l = rel(a["pred_logits"], b["pred_logits"]).max().item()
+    # Layer-0 predictions depend only on the pixel decoder and the heads (no thresholded attention mask has
+    # influenced them yet): they isolate arithmetic error.  Later layers additionally see mask-bit flips:
+    # ~2.4e9 threshold decisions per forward, a logit within ~1e-6 of the threshold flips its key in or out.
+    r0 = rel(a["aux_outputs"][0]["pred_masks"], b["aux_outputs"][0]["pred_masks"])
+    rl = rel(a["pred_masks"], b["pred_masks"])
+    parity = {"layer0_pred_masks_max_rel": r0.max().item(),
+              "final_pred_masks_median_rel": rl.flatten()[::97].median().item(),
+              "final_pred_masks_frac_above_1e-3": (rl > 1e-3).float().mean().item(),
+              "final_pred_masks_max_rel": err, "final_pred_logits_max_rel": err_l}
     t_ours = timeit(ours, 5)
     t_stock = timeit(stock, 3)
 
@@ -99,7 +111,7 @@ def main():
         "pixel_decoder_only": {"ours_ms": t_ours_pd, "stock_ms": t_stock_pd, "speedup": t_stock_pd / t_ours_pd},
         "decoder_only": {"ours_ms": t_ours - t_ours_pd, "stock_ms": t_stock - t_stock_pd,
                          "speedup": (t_stock - t_stock_pd) / max(1e-9, t_ours - t_ours_pd)},
-        "max_rel_diff_pred_masks": err, "max_rel_diff_pred_logits": err_l,
+        "parity_vs_stock": parity,
     }), flush=True)
 
 
