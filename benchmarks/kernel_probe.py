@@ -86,6 +86,21 @@ def main():
             emit(f"gemm_tf32x3 {tag} M={m} N={n} K={k}", ms, 4 * (m * k + m * n + 2 * n * k), 3 * 2.0 * m * n * k,
                  fp32_equiv_TFLOPs=2.0 * m * n * k / ms / 1e9)
             del a
+        # epilogue variants at the FFN-backward / residual shapes
+        m = B * S
+        a, w, hid = rn(m, 256), rn(1024, 256) / 16, rn(m, 1024)
+        wh, wl = native.split_tf32(w)
+        ms = timeit(lambda: native.gemm_general(a, wh, b_lo=wl, gate=hid))
+        emit(f"gemm_tf32x3 ffn.d_hidden (gated) M={m} N=1024 K=256", ms, 4 * (m * 256 + 2 * m * 1024 + 2 * 1024 * 256),
+             3 * 2.0 * m * 1024 * 256)
+        w2 = rn(256, 1024) / 32
+        w2h, w2l = native.split_tf32(w2)
+        ms = timeit(lambda: native.gemm(hid, w2h, w2l))
+        emit(f"gemm_tf32x3 ffn.d_x M={m} N=256 K=1024", ms, 4 * (m * 1024 + m * 256 + 2 * 1024 * 256), 3 * 2.0 * m * 1024 * 256)
+        ms = timeit(lambda: native.matmul_tn(hid, a))
+        emit(f"gemm_tf32x3 ffn.d_w1 (MN-major, split-K) [1024 x 256] over M={m}", ms, 4 * (m * 1024 + m * 256),
+             3 * 2.0 * m * 1024 * 256)
+        del a, hid
     if "masklogits" in which:
         Q, C, HW = 120, 256, 65536
         e, f = rn(B, Q, C), rn(B, HW, C)

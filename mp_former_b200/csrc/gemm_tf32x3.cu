@@ -59,18 +59,13 @@ struct GemmArgs {
   int k_per_split;                            // split s of batch b writes partial sums to C[(b*k_splits+s)]
 };
 
-constexpr int kStgLd = 36;
-
 template <int BN>
 struct GemmCfg {
   static constexpr int kBBytes = BN * kBK * 4;
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
   static constexpr int kStages = (BN == 256) ? 2 : (BN == 128 ? 3 : 4);
   static constexpr int kBarrierBytes = 256;
-  // epilogue staging: per epilogue warp a [32 rows x 32 cols] fp32 tile, rows padded to 36 floats so both the
-  // row-owner float4 writes and the 8-lanes-per-row float4 reads are bank-conflict free
-  static constexpr int kStagingBytes = 4 * 32 * kStgLd * 4;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarrierBytes + kStagingBytes + 1024;  // + align slack
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarrierBytes + 1024;  // + alignment slack
   static constexpr int kTmemCols = 2 * BN;     // power of two >= 32 for BN in {64,128,256}
 };
 
@@ -98,7 +93,6 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint64_t* tfull = bars + 3 * S;      // [2] accumulator complete
   uint64_t* tempty = bars + 3 * S + 2; // [2] accumulator drained by the epilogue
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 4);
-  float* staging = reinterpret_cast<float*>(smem + S * Cfg::kStageBytes + Cfg::kBarrierBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -266,7 +260,6 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const long long boff = static_cast<long long>(b) * g.c_batch_stride;
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * BN);
       const float* grow = (g.gate != nullptr && row_ok) ? g.gate + static_cast<long long>(row) * g.gate_ld : nullptr;
-      const bool coalesced = !g.transpose_c && g.vec_store && g.vec_aux;
       const float* rrow = nullptr;
       if (g.resid != nullptr && row_ok)
         rrow = g.resid + static_cast<long long>(g.resid_rows > 0 ? row % g.resid_rows : row) * g.resid_ld;
@@ -277,66 +270,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         uint32_t v[32];
         tmem_ld_32x32(t_addr + c * 32, v);
         tmem_ld_wait();
-        const bool full = n0 + 32 <= g.N;
-        if (full && coalesced) {
-          // Row-major C: the accumulator chunk is transposed through shared memory so that 8 consecutive lanes
-          // cover one 128-byte row segment -- every global access of the epilogue (C, C_lo, resid, gate) moves
-          // whole lines instead of 32 scattered 16-byte pieces per instruction.
-          float* stg = staging + ew * (32 * kStgLd);
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<uint4*>(stg + lane * kStgLd + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          __syncwarp();
-          const int cq = (lane & 7) * 4;
-          const int n = n0 + cq;
-          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (g.bias != nullptr) bv = __ldg(reinterpret_cast<const float4*>(g.bias + n));
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = i * 4 + (lane >> 3);
-            const int grow_i = m_t * kBM + ew * 32 + r;
-            float4 x = *reinterpret_cast<const float4*>(stg + r * kStgLd + cq);
-            if (grow_i < g.M) {
-              x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
-              if (g.resid != nullptr) {
-                const float* rp = g.resid +
-                    static_cast<long long>(g.resid_rows > 0 ? grow_i % g.resid_rows : grow_i) * g.resid_ld + n;
-                if (n + 4 <= g.resid_cols) {
-                  const float4 t = __ldg(reinterpret_cast<const float4*>(rp));
-                  x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
-                } else {
-                  if (n + 0 < g.resid_cols) x.x += __ldg(rp + 0);
-                  if (n + 1 < g.resid_cols) x.y += __ldg(rp + 1);
-                  if (n + 2 < g.resid_cols) x.z += __ldg(rp + 2);
-                }
-              }
-              if (g.alpha != 1.0f) { x.x *= g.alpha; x.y *= g.alpha; x.z *= g.alpha; x.w *= g.alpha; }
-              if (g.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-              if (g.gate != nullptr) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(g.gate + static_cast<long long>(grow_i) * g.gate_ld + n));
-                if (!(t.x > 0.f)) x.x = 0.f;
-                if (!(t.y > 0.f)) x.y = 0.f;
-                if (!(t.z > 0.f)) x.z = 0.f;
-                if (!(t.w > 0.f)) x.w = 0.f;
-              }
-              const long long off = boff + static_cast<long long>(grow_i) * g.ldc + n;
-              if (g.C_lo == nullptr) {
-                *reinterpret_cast<float4*>(g.C + off) = x;
-              } else {
-                float4 h;
-                h.x = rn_tf32(x.x); h.y = rn_tf32(x.y); h.z = rn_tf32(x.z); h.w = rn_tf32(x.w);
-                *reinterpret_cast<float4*>(g.C + off) = h;
-                *reinterpret_cast<float4*>(g.C_lo + off) =
-                    make_float4(rn_tf32(x.x - h.x), rn_tf32(x.y - h.y), rn_tf32(x.z - h.z), rn_tf32(x.w - h.w));
-              }
-            }
-          }
-          __syncwarp();
-          continue;
-        }
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        const bool full = n0 + 32 <= g.N;
         // addends / gate are read 16 bytes at a time when the chunk is full and the pointers allow it
         if (g.bias != nullptr) {
           if (full && g.vec_aux) {
