@@ -57,6 +57,9 @@ struct GemmArgs {
   long long gate_ld;
   int k_splits;                               // K is cut into k_splits ranges of k_per_split (multiple of 32);
   int k_per_split;                            // split s of batch b writes partial sums to C[(b*k_splits+s)]
+  int debug;                                  // MPF_GEMM_DEBUG bit mask (timing experiments only; results invalid):
+                                              //  1 no global stores  2 no epilogue work  4 no A/B splitting
+                                              //  8 one MMA of three  16 no B loads  32 no A loads  64 epilogue = tcgen05.ld only
 };
 
 template <int BN>
@@ -138,15 +141,18 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const int kb = kb0 + kbi;
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * Cfg::kStageBytes;
-          mbar_arrive_expect_tx(&full[stage], kABytes + (SPLIT_B ? 1 : 2) * Cfg::kBBytes);
-          if (A_MN) {          // [32 k-rows x 32 m] boxes of 4 KiB, one per 32-wide slice of M
+          const bool ldA = !(g.debug & 32), ldB = !(g.debug & 16);
+          mbar_arrive_expect_tx(&full[stage], (ldA ? kABytes : 0) + (ldB ? (SPLIT_B ? 1 : 2) * Cfg::kBBytes : 0));
+          if (!ldA) {
+          } else if (A_MN) {          // [32 k-rows x 32 m] boxes of 4 KiB, one per 32-wide slice of M
 #pragma unroll
             for (int i = 0; i < kBM / 32; ++i)
               tma_load_3d(st + i * 4096, &tmA, &full[stage], m_t * kBM + i * 32, kb * kBK, b);
           } else {
             tma_load_3d(st, &tmA, &full[stage], kb * kBK, m_t * kBM, b);
           }
-          if (B_MN) {
+          if (!ldB) {
+          } else if (B_MN) {
 #pragma unroll
             for (int i = 0; i < BN / 32; ++i) {
               tma_load_3d(st + 2 * kABytes + i * 4096, &tmBhi, &full[stage], n_t * BN + i * 32, kb * kBK, b);
@@ -191,6 +197,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const uint64_t dal = A_MN ? smem_desc_sw128_mnmajor(a_lo + koa) : smem_desc_sw128_kmajor(a_lo + koa);
             const uint64_t dbh = B_MN ? smem_desc_sw128_mnmajor(b_hi + kob) : smem_desc_sw128_kmajor(b_hi + kob);
             const uint64_t dbl = B_MN ? smem_desc_sw128_mnmajor(b_lo + kob) : smem_desc_sw128_kmajor(b_lo + kob);
+            if (g.debug & 8) {
+              mma_tf32_ss(d_tmem, dah, dbh, idesc, (kb | k) ? 1u : 0u);
+              continue;
+            }
             mma_tf32_ss(d_tmem, dal, dbh, idesc, (kb | k) ? 1u : 0u);
             mma_tf32_ss(d_tmem, dah, dbl, idesc, 1u);
             mma_tf32_ss(d_tmem, dah, dbh, idesc, 1u);
@@ -212,6 +222,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(&full[stage], phase);
         uint8_t* a = smem + stage * Cfg::kStageBytes;
+        if (g.debug & 4) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&split[stage]);
+          if (++stage == S) { stage = 0; phase ^= 1; }
+          continue;
+        }
 #pragma unroll
         for (int i = 0; i < kABytes / 16 / 128; ++i) {
           const int off = (st_id + i * 128) * 16;
@@ -266,10 +282,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         const int n0 = n_t * BN + c * 32;
-        if (n0 >= g.N) break;
+        if (n0 >= g.N || (g.debug & 2)) break;
         uint32_t v[32];
         tmem_ld_32x32(t_addr + c * 32, v);
         tmem_ld_wait();
+        if (g.debug & 64) continue;
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -346,7 +363,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
           }
         };
-        if (g.C_lo == nullptr) {
+        if (g.debug & 1) {
+        } else if (g.C_lo == nullptr) {
           store(g.C, f);
         } else {                       // emit the result pre-split for a following 3xTF32 consumer
           float lo[32];
@@ -535,6 +553,8 @@ int mpf_gemm_tf32x3_general(const float* A, int a_mn_major, long long lda, long 
   g.resid = resid; g.resid_ld = resid_ld; g.resid_rows = resid_rows;
   g.resid_cols = resid ? (resid_cols > 0 ? resid_cols : N) : 0;
   g.alpha = alpha;
+  g.debug = 0;
+  if (const char* dbg = getenv("MPF_GEMM_DEBUG")) g.debug = atoi(dbg);
   g.vec_store = (!transpose_c && ldc % 4 == 0 && c_batch_stride % 4 == 0 && aligned16(C) &&
                  (C_lo == nullptr || aligned16(C_lo))) ? 1 : 0;
   g.vec_aux = ((bias == nullptr || aligned16(bias)) && (resid == nullptr || (aligned16(resid) && resid_ld % 4 == 0)) &&
