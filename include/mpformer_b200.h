@@ -177,6 +177,24 @@ int mpf_gemm_tf32x3_general(const float* A, int a_mn_major, long long lda, long 
                             void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * "bf16x3" tensor-core GEMM (tcgen05.mma.kind::f16 + TMA loads AND TMA stores), the default for the same call
+ * sites as mpf_gemm_tf32x3* when both operands are K-major:
+ *   x = (A*B^T + bias + resid) * alpha, optional ReLU / gate;  C (and C_lo) as in mpf_gemm_tf32x3_general.
+ * A [batch,M,K] is fp32 and is split into bf16 halves (hi = bf16_rn(x), lo = bf16_rn(x - hi)) inside the kernel;
+ * B [batch,N,K] is passed pre-split by mpf_split_bf16 (b_batch_stride == 0: one B shared by the whole batch).
+ * D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi keeps ~2^-16 relative error per product (contract: 1e-3) at twice the
+ * tensor rate and half the operand bytes of 3xTF32.  C_lo (optional) still receives TF32 halves of the result
+ * (consumed by the attention kernels).
+ * Requirements: A/B/C 16-byte aligned; lda, ldc, batch strides multiples of 4 elements; ldb multiple of 8.
+ * ------------------------------------------------------------------------------------------- */
+int mpf_split_bf16(const float* x, uint16_t* hi, uint16_t* lo, long long n, void* stream);
+int mpf_gemm_bf16x3(const float* A, long long lda, long long a_batch_stride, const uint16_t* B_hi,
+                    const uint16_t* B_lo, long long ldb, long long b_batch_stride, const float* bias, float* C,
+                    float* C_lo, long long ldc, long long c_batch_stride, const float* resid, long long resid_ld,
+                    int resid_rows, int resid_cols, const float* gate, long long gate_ld, float alpha, int batch,
+                    int M, int N, int K, int k_splits, int relu, int transpose_c, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Boolean stage of the prediction heads, bit-packed:
  *   bits[row][j] bit i = ( sigmoid( bilinear_resize(logits[row], (h,w), align_corners=False) )[32j+i] < 0.5 )
  * ref: transformer_decoder/mask2former_transformer_decoder.py:1869-1875 (F.interpolate, sigmoid, < 0.5;

@@ -43,6 +43,10 @@ SIGNATURES = {
                                          _c_vp, _c_vp, _c_ll, _c_ll, _c_vp, _c_ll, _c_int, _c_int, _c_vp, _c_ll,
                                          ctypes.c_float,
                                          _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp]),
+    "mpf_split_bf16": (_c_int, [_c_vp, _c_vp, _c_vp, _c_ll, _c_vp]),
+    "mpf_gemm_bf16x3": (_c_int, [_c_vp, _c_ll, _c_ll, _c_vp, _c_vp, _c_ll, _c_ll, _c_vp, _c_vp, _c_vp, _c_ll, _c_ll,
+                                 _c_vp, _c_ll, _c_int, _c_int, _c_vp, _c_ll, ctypes.c_float,
+                                 _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp]),
     "mpf_attn_mask_bits_f32": (_c_int, [_c_vp, _c_ll] + [_c_int] * 5 + [_c_vp, _c_int, _c_vp]),
     "mpf_pack_bool_bits": (_c_int, [_c_vp, _c_int, _c_int, _c_vp, _c_int, _c_vp]),
     "mpf_masked_xattn_fwd_f32": (_c_int, [_c_vp] * 10 + [_c_int] * 6 + [_c_vp]),

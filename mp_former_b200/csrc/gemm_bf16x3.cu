@@ -1,0 +1,621 @@
+// C[b] = A[b] * B[b]^T (+ bias, + residual, * alpha, ReLU, gate) with "bf16x3" split arithmetic on the 5th-gen
+// tensor cores: every fp32 operand value is written x = hi + lo with hi = bf16_rn(x), lo = bf16_rn(x - hi) (16
+// significand bits together) and
+//     D += A_lo * B_hi + A_hi * B_lo + A_hi * B_hi                        (fp32 accumulate in TMEM)
+// which keeps a relative error of ~2^-16 per product (the path's contract is 1e-3 against the reference's fp32
+// results) at TWICE the tensor rate and HALF the shared-memory operand bytes of the 3xTF32 kernel
+// (gemm_tf32x3.cu, kept for the MN-major / in-kernel-split variants and as the higher-precision option).
+//
+//   A : [batch, M, K] fp32, K contiguous -- loaded raw by TMA, split into bf16 hi/lo by converter warps
+//   B : [batch or 1, N, K] PRE-SPLIT bf16 hi/lo (mpf_split_bf16): weights / per-query mask embedding
+//   C : row-major [slab, M, ldc] or transposed [slab, N, ldc]; written by TMA STORES from a shared-memory staging
+//       tile, so the LSU never sees the 128-rows-x-16-bytes scatter the 3xTF32 epilogue issues (the timing
+//       decomposition in profiles/r1i_gemm_debug_probe.jsonl shows those stores cost 30% of a K=256 GEMM).
+//
+// One persistent CTA per SM, 12 warps:
+//   warp 0      TMA producer   raw A (fp32, SWIZZLE_128B) + B_hi + B_lo (bf16, SWIZZLE_64B) per 32-wide k-block
+//   warps 8-11  converters     thread = tile row: 8 x LDS.128 raw -> 4 + 4 x STS.128 bf16 hi / lo (SWIZZLE_64B K-major)
+//   warp 1      MMA issuer     2 k-steps x 3 tcgen05.mma.kind::f16 (M=128, N=BN, K=16) per k-block
+//   warps 4-7   epilogue       tcgen05.ld -> bias/residual/scale/ReLU/gate -> staging tile -> cp.async.bulk.tensor store
+//   warp 2      TMEM allocation (2 accumulators x 256 columns, double-buffered across tiles)
+#include "mpf_common.cuh"
+#include "sm100_ptx.cuh"
+#include "tmap.cuh"
+
+#include <cuda_bf16.h>
+
+#include <cstdlib>
+#include <mutex>
+
+namespace mpf {
+
+using namespace ptx;
+
+namespace bf3 {
+
+constexpr int kBM = 128;
+constexpr int kBK = 32;                        // k-block: 32 fp32 = 128 B raw rows, 32 bf16 = 64 B operand rows
+constexpr int kRawABytes = kBM * kBK * 4;      // 16 KiB
+constexpr int kOpABytes = kBM * kBK * 2;       // 8 KiB each for A_hi, A_lo
+constexpr int kStagingBytes = kBM * 32 * 4;    // 16 KiB: 128 rows x 32 fp32 (or 32 x 128 transposed)
+constexpr int kThreads = 384;
+constexpr int kMaxStages = 6;
+constexpr int kSmemBudget = 232448;            // 227 KiB opt-in maximum per CTA
+constexpr int kTmemCols = 512;
+
+struct Args {
+  const float* bias;
+  const float* resid;
+  long long resid_ld;
+  int resid_rows, resid_cols;
+  const float* gate;
+  long long gate_ld;
+  float alpha;
+  int batch, M, N, K;
+  int bn;                                     // N tile (multiple of 32, <= 256)
+  int tiles_m, tiles_n;
+  int k_splits, k_per_split;
+  int stages, stage_bytes;
+  int relu, transpose_c, split_out, vec_aux;
+  int b_broadcast;                            // B has no batch dimension (shared weight)
+  int debug;
+};
+
+__device__ __forceinline__ void tma_load_3d_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                 int c2) {
+  tma_load_3d(smem_dst, m, bar, c0, c1, c2);
+}
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate.  One thread issues.
+__device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// K-major operand tile, SWIZZLE_64B: rows of 64 bytes (32 bf16), 8-row groups of 512 B stacked along M/N.
+//   [0,14) start >> 4   [16,30) LBO (unused for swizzled K-major; 1)   [32,46) SBO = 512 >> 4
+//   [46,48) version 1   [61,64) layout 4 (SWIZZLE_64B)
+__device__ __forceinline__ uint64_t smem_desc_sw64_kmajor(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;
+  return d;
+}
+
+// Instruction descriptor, kind::f16: [4,6) D = F32 (1)  [7,10) A = BF16 (1)  [10,13) B = BF16 (1)
+//   [15] A major K  [16] B major K  [17,23) N >> 3  [24,29) M >> 4
+__device__ __forceinline__ uint32_t idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {      // a -> low half (lower address)
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_lo_f32(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi_f32(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+__device__ __forceinline__ float rn_tf32(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+                   const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmC,
+                   const __grid_constant__ CUtensorMap tmClo, const Args g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int S = g.stages;
+  uint8_t* staging = smem + S * g.stage_bytes;                 // 2 x 16 KiB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * kStagingBytes);
+  uint64_t* full = bars;                         // [S] TMA bytes landed
+  uint64_t* conv = bars + kMaxStages;            // [S] A_hi / A_lo written
+  uint64_t* empty = bars + 2 * kMaxStages;       // [S] MMAs reading the stage retired
+  uint64_t* tfull = bars + 3 * kMaxStages;       // [2] accumulator complete
+  uint64_t* tempty = bars + 3 * kMaxStages + 2;  // [2] accumulator drained by the epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kMaxStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int BN = g.bn;
+  const int b_bytes = BN * kBK * 2;              // one of B_hi / B_lo per stage
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmBhi);
+    prefetch_tmap(&tmBlo);
+    prefetch_tmap(&tmC);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&conv[s], 4);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = g.batch * g.k_splits * g.tiles_m * g.tiles_n;
+  const int kblocks = g.k_per_split / kBK;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const bool ldA = !(g.debug & 32), ldB = !(g.debug & 16);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_t = tile % g.tiles_n;
+        int rest = tile / g.tiles_n;
+        const int m_t = rest % g.tiles_m;
+        rest /= g.tiles_m;
+        const int ks = rest % g.k_splits;
+        const int b = rest / g.k_splits;
+        const int kb0 = ks * kblocks;
+        const int bb = g.b_broadcast ? 0 : b;
+        for (int kbi = 0; kbi < kblocks; ++kbi) {
+          const int kb = kb0 + kbi;
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* st = smem + stage * g.stage_bytes;
+          mbar_arrive_expect_tx(&full[stage], (ldA ? kRawABytes : 0) + (ldB ? 2 * b_bytes : 0));
+          if (ldA) tma_load_3d(st, &tmA, &full[stage], kb * kBK, m_t * kBM, b);
+          if (ldB) {
+            uint8_t* bs = st + kRawABytes + 2 * kOpABytes;
+            tma_load_3d(bs, &tmBhi, &full[stage], kb * kBK, n_t * BN, bb);
+            tma_load_3d(bs + b_bytes, &tmBlo, &full[stage], kb * kBK, n_t * BN, bb);
+          }
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16(kBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          mbar_wait(&conv[stage], phase);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + stage * g.stage_bytes);
+          const uint32_t a_hi = st + kRawABytes;
+          const uint32_t a_lo = a_hi + kOpABytes;
+          const uint32_t b_hi = a_lo + kOpABytes;
+          const uint32_t b_lo = b_hi + b_bytes;
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {              // 16 bf16 = 32 bytes per MMA K step inside the 64-B swizzle row
+            const uint64_t dah = smem_desc_sw64_kmajor(a_hi + k * 32);
+            const uint64_t dal = smem_desc_sw64_kmajor(a_lo + k * 32);
+            const uint64_t dbh = smem_desc_sw64_kmajor(b_hi + k * 32);
+            const uint64_t dbl = smem_desc_sw64_kmajor(b_lo + k * 32);
+            if (g.debug & 8) {
+              mma_bf16_ss(d_tmem, dah, dbh, idesc, (kb | k) ? 1u : 0u);
+              continue;
+            }
+            mma_bf16_ss(d_tmem, dal, dbh, idesc, (kb | k) ? 1u : 0u);
+            mma_bf16_ss(d_tmem, dah, dbl, idesc, 1u);
+            mma_bf16_ss(d_tmem, dah, dbh, idesc, 1u);
+          }
+          mma_commit(&empty[stage]);
+          if (kb == kblocks - 1) mma_commit(&tfull[acc]);
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 8) {
+    // ================= converters (128 threads, thread = tile row) =================
+    const int r = threadIdx.x - 256;
+    const int rsw = r & 7;                 // SWIZZLE_128B: 16-byte chunk index ^ (row % 8)
+    const int osw = (r >> 1) & 3;          // SWIZZLE_64B:  16-byte chunk index ^ ((row / 2) % 4)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(&full[stage], phase);
+        uint8_t* st = smem + stage * g.stage_bytes;
+        if (!(g.debug & 4)) {
+          const uint8_t* raw = st + r * 128;
+          uint8_t* ohi = st + kRawABytes + r * 64;
+          uint8_t* olo = ohi + kOpABytes;
+          float4 x[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) x[c] = *reinterpret_cast<const float4*>(raw + ((c ^ rsw) << 4));
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const float4 u = x[2 * p], v = x[2 * p + 1];
+            uint4 h, l;
+            h.x = pack_bf16x2(u.x, u.y); h.y = pack_bf16x2(u.z, u.w);
+            h.z = pack_bf16x2(v.x, v.y); h.w = pack_bf16x2(v.z, v.w);
+            l.x = pack_bf16x2(u.x - bf16_lo_f32(h.x), u.y - bf16_hi_f32(h.x));
+            l.y = pack_bf16x2(u.z - bf16_lo_f32(h.y), u.w - bf16_hi_f32(h.y));
+            l.z = pack_bf16x2(v.x - bf16_lo_f32(h.z), v.y - bf16_hi_f32(h.z));
+            l.w = pack_bf16x2(v.z - bf16_lo_f32(h.w), v.w - bf16_hi_f32(h.w));
+            const int off = (p ^ osw) << 4;
+            *reinterpret_cast<uint4*>(ohi + off) = h;
+            *reinterpret_cast<uint4*>(olo + off) = l;
+          }
+          fence_proxy_async_smem();
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&conv[stage]);
+        if (++stage == S) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue (warps 4..7 -> TMEM lane groups 0..3) =================
+    const int ew = warp - 4;
+    const int trow = ew * 32 + lane;               // row of the tile this thread drains
+    const bool issuer = (threadIdx.x == 128);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t chunk_ctr = 0;
+    const int nchunks = BN / 32;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_t = tile % g.tiles_n;
+      int rest = tile / g.tiles_n;
+      const int m_t = rest % g.tiles_m;
+      const int slab = rest / g.tiles_m;            // = batch * k_splits + split: index of the output slab
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_t * kBM + trow;
+      const bool row_ok = row < g.M;
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * 256);
+      const float* grow = (g.gate != nullptr && row_ok) ? g.gate + static_cast<long long>(row) * g.gate_ld : nullptr;
+      const float* rrow = nullptr;
+      if (g.resid != nullptr && row_ok)
+        rrow = g.resid + static_cast<long long>(g.resid_rows > 0 ? row % g.resid_rows : row) * g.resid_ld;
+      int live = 0;                                 // chunks of this tile that hold output columns
+      for (int c = 0; c < nchunks; ++c)
+        if (n_t * BN + c * 32 < g.N) live = c + 1;
+      if (g.debug & 2) live = 0;
+#pragma unroll 1
+      for (int c = 0; c < live; ++c) {
+        const int n0 = n_t * BN + c * 32;
+        uint32_t v[32];
+        tmem_ld_32x32(t_addr + c * 32, v);
+        tmem_ld_wait();
+        if (c == live - 1) {                        // accumulator fully read: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+        if (g.debug & 64) continue;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        const bool fullc = n0 + 32 <= g.N;
+        if (g.bias != nullptr) {
+          if (fullc && g.vec_aux) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + j));
+              f[j] += t.x; f[j + 1] += t.y; f[j + 2] += t.z; f[j + 3] += t.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < g.N) f[j] += __ldg(g.bias + n0 + j);
+          }
+        }
+        if (rrow != nullptr) {
+          if (n0 + 32 <= g.resid_cols && g.vec_aux) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(rrow + n0 + j));
+              f[j] += t.x; f[j + 1] += t.y; f[j + 2] += t.z; f[j + 3] += t.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < g.resid_cols) f[j] += __ldg(rrow + n0 + j);
+          }
+        }
+        if (g.alpha != 1.0f) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] *= g.alpha;
+        }
+        if (g.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (grow != nullptr) {
+          if (fullc && g.vec_aux) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(grow + n0 + j));
+              if (!(t.x > 0.f)) f[j] = 0.f;
+              if (!(t.y > 0.f)) f[j + 1] = 0.f;
+              if (!(t.z > 0.f)) f[j + 2] = 0.f;
+              if (!(t.w > 0.f)) f[j + 3] = 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < g.N && !(__ldg(grow + n0 + j) > 0.f)) f[j] = 0.f;
+          }
+        }
+        if (g.debug & 1) continue;
+
+        // ---- registers -> staging tile -> TMA store (clipped at M / N by the tensor map) ----
+        // row-major C: staging is [128 rows][32 fp32] with the 128-byte swizzle (16-byte chunk ^ row % 8);
+        // transposed C: staging is [32 n-rows][128 m] plain (a warp writes 128 contiguous bytes).
+        uint8_t* buf0 = staging + (g.split_out ? 0 : (chunk_ctr & 1) * kStagingBytes);
+        uint8_t* buf1 = staging + kStagingBytes;
+        if (issuer) {
+          if (g.split_out) bulk_wait_read<0>(); else bulk_wait_read<1>();
+        }
+        epi_bar();
+        auto put = [&](uint8_t* buf, const float (&val)[32]) {
+          if (g.transpose_c) {
+            float* bt = reinterpret_cast<float*>(buf) + trow;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) bt[j * kBM] = val[j];
+          } else {
+            uint8_t* br = buf + trow * 128;
+            const int sw = trow & 7;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(br + ((q ^ sw) << 4)) =
+                  make_float4(val[4 * q], val[4 * q + 1], val[4 * q + 2], val[4 * q + 3]);
+          }
+        };
+        if (!g.split_out) {
+          put(buf0, f);
+        } else {                       // emit the result pre-split (TF32 halves) for the attention kernels
+          float lo[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float h = rn_tf32(f[j]);
+            lo[j] = rn_tf32(f[j] - h);
+            f[j] = h;
+          }
+          put(buf0, f);
+          put(buf1, lo);
+        }
+        fence_proxy_async_smem();
+        epi_bar();
+        if (issuer) {
+          if (g.transpose_c) {
+            tma_store_3d(&tmC, buf0, m_t * kBM, n0, slab);
+            if (g.split_out) tma_store_3d(&tmClo, buf1, m_t * kBM, n0, slab);
+          } else {
+            tma_store_3d(&tmC, buf0, n0, m_t * kBM, slab);
+            if (g.split_out) tma_store_3d(&tmClo, buf1, n0, m_t * kBM, slab);
+          }
+          bulk_commit();
+        }
+        ++chunk_ctr;
+      }
+      if (live == 0) {                               // (debug only) nothing read: still release the accumulator
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (issuer) bulk_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                  long long n) {
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * 256) {
+    const float v = x[i];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeFn encoder() {
+  static EncodeFn enc = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      enc = reinterpret_cast<EncodeFn>(p);
+  });
+  static thread_local bool ctx_bound = false;   // see make_tmap_f32_3d
+  if (!ctx_bound) {
+    cudaFree(nullptr);
+    ctx_bound = true;
+  }
+  return enc;
+}
+
+// 3-D tensor [d2, d1, d0] (d0 contiguous) of `esize`-byte elements; strides in elements.
+static int make_tmap_3d(CUtensorMap* m, CUtensorMapDataType dt, int esize, const void* base, long long d0,
+                        long long d1, long long d2, long long ld1, long long ld2, int box0, int box1,
+                        CUtensorMapSwizzle sw, const char* what) {
+  EncodeFn enc = encoder();
+  if (enc == nullptr) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return MPF_ERR_UNSUPPORTED;
+  }
+  if ((ld1 * esize) % 16 != 0 || (ld2 * esize) % 16 != 0 || !aligned16(base)) {
+    set_error("gemm_bf16x3: %s needs a 16-byte aligned base and byte strides that are multiples of 16", what);
+    return MPF_ERR_BAD_ARG;
+  }
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(d0), static_cast<cuuint64_t>(d1), static_cast<cuuint64_t>(d2)};
+  if (ld2 < d1 * ld1) ld2 = d1 * ld1;
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld1) * esize, static_cast<cuuint64_t>(ld2) * esize};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box0), static_cast<cuuint32_t>(box1), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(%s) failed (CUresult %d): dims=(%lld,%lld,%lld) ld=(%lld,%lld) box=(%d,%d)", what,
+              static_cast<int>(r), d0, d1, d2, ld1, ld2, box0, box1);
+    return MPF_ERR_BAD_ARG;
+  }
+  return MPF_OK;
+}
+
+static int pick_bn(int N) {
+  if (N <= 64) return 64;
+  for (int bn = 256; bn >= 64; bn -= 32) {
+    const int padded = (N + bn - 1) / bn * bn;
+    if ((padded - N) * 8 <= N) return bn;          // <= 12.5 % of the tile columns wasted
+  }
+  return 64;
+}
+
+}  // namespace bf3
+}  // namespace mpf
+
+extern "C" {
+
+int mpf_split_bf16(const float* x, uint16_t* hi, uint16_t* lo, long long n, void* stream) {
+  mpf::clear_error();
+  MPF_REQUIRE(x && hi && lo && n > 0, "split_bf16: bad arguments");
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  mpf::bf3::split_bf16_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), n);
+  mpf::count_launch();
+  return mpf::finish_launch("split_bf16");
+}
+
+int mpf_gemm_bf16x3(const float* A, long long lda, long long a_batch_stride, const uint16_t* B_hi,
+                    const uint16_t* B_lo, long long ldb, long long b_batch_stride, const float* bias, float* C,
+                    float* C_lo, long long ldc, long long c_batch_stride, const float* resid, long long resid_ld,
+                    int resid_rows, int resid_cols, const float* gate, long long gate_ld, float alpha, int batch,
+                    int M, int N, int K, int k_splits, int relu, int transpose_c, void* stream) {
+  using namespace mpf;
+  using namespace mpf::bf3;
+  clear_error();
+  MPF_REQUIRE(A && B_hi && B_lo && C, "gemm_bf16x3: null pointer argument");
+  MPF_REQUIRE(batch > 0 && M > 0 && N > 0 && K > 0 && k_splits >= 1, "gemm_bf16x3: dimensions must be positive");
+  MPF_REQUIRE(gate == nullptr || (batch == 1 && !transpose_c), "gemm_bf16x3: gate needs batch 1, row-major C");
+  MPF_REQUIRE(k_splits == 1 || (!bias && !resid && !relu && !C_lo && !gate && alpha == 1.0f),
+              "gemm_bf16x3: split-K produces partial sums; no epilogue operations are allowed");
+  MPF_REQUIRE(lda >= K && ldb >= K, "gemm_bf16x3: row stride too small");
+  Args g;
+  g.bn = pick_bn(N);
+  if (const char* force = getenv("MPF_GEMM_BN")) {
+    const int f = atoi(force);
+    if (f >= 32 && f <= 256 && f % 32 == 0) g.bn = f;
+  }
+  g.tiles_m = (M + kBM - 1) / kBM;
+  g.tiles_n = (N + g.bn - 1) / g.bn;
+  MPF_REQUIRE(static_cast<long long>(batch) * k_splits * g.tiles_m * g.tiles_n < (1ll << 31), "gemm_bf16x3: too many tiles");
+  const int kblocks_total = (K + kBK - 1) / kBK;
+  g.k_splits = k_splits;
+  g.k_per_split = (kblocks_total + k_splits - 1) / k_splits * kBK;
+  g.stage_bytes = kRawABytes + 2 * kOpABytes + 2 * g.bn * kBK * 2;
+  const int avail = kSmemBudget - 1024 - 2 * kStagingBytes - 512;
+  g.stages = avail / g.stage_bytes;
+  if (g.stages > kMaxStages) g.stages = kMaxStages;
+  MPF_REQUIRE(g.stages >= 2, "gemm_bf16x3: not enough shared memory for two stages");
+  const int smem_bytes = g.stages * g.stage_bytes + 2 * kStagingBytes + 512 + 1024;
+  g.b_broadcast = (b_batch_stride == 0) ? 1 : 0;
+  const int slabs = batch * k_splits;
+
+  CUtensorMap ta, tbh, tbl, tc, tcl;
+  int rc = make_tmap_3d(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, A, K, M, batch, lda, a_batch_stride, kBK, kBM,
+                        CU_TENSOR_MAP_SWIZZLE_128B, "A");
+  if (rc) return rc;
+  const long long nb = g.b_broadcast ? 1 : batch;
+  rc = make_tmap_3d(&tbh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B_hi, K, N, nb, ldb, b_batch_stride, kBK, g.bn,
+                    CU_TENSOR_MAP_SWIZZLE_64B, "B_hi");
+  if (rc) return rc;
+  rc = make_tmap_3d(&tbl, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B_lo, K, N, nb, ldb, b_batch_stride, kBK, g.bn,
+                    CU_TENSOR_MAP_SWIZZLE_64B, "B_lo");
+  if (rc) return rc;
+  if (transpose_c) {
+    rc = make_tmap_3d(&tc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, C, M, N, slabs, ldc, c_batch_stride, kBM, 32,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, "C^T");
+    if (rc) return rc;
+    tcl = tc;
+    if (C_lo) rc = make_tmap_3d(&tcl, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, C_lo, M, N, slabs, ldc, c_batch_stride, kBM,
+                                32, CU_TENSOR_MAP_SWIZZLE_NONE, "C_lo^T");
+  } else {
+    rc = make_tmap_3d(&tc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, C, N, M, slabs, ldc, c_batch_stride, 32, kBM,
+                      CU_TENSOR_MAP_SWIZZLE_128B, "C");
+    if (rc) return rc;
+    tcl = tc;
+    if (C_lo) rc = make_tmap_3d(&tcl, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, C_lo, N, M, slabs, ldc, c_batch_stride, 32,
+                                kBM, CU_TENSOR_MAP_SWIZZLE_128B, "C_lo");
+  }
+  if (rc) return rc;
+
+  g.bias = bias;
+  g.resid = resid; g.resid_ld = resid_ld; g.resid_rows = resid_rows;
+  g.resid_cols = resid ? (resid_cols > 0 ? resid_cols : N) : 0;
+  g.gate = gate; g.gate_ld = gate_ld;
+  g.alpha = alpha;
+  g.batch = batch; g.M = M; g.N = N; g.K = K;
+  g.relu = relu; g.transpose_c = transpose_c; g.split_out = C_lo ? 1 : 0;
+  g.vec_aux = ((bias == nullptr || aligned16(bias)) && (resid == nullptr || (aligned16(resid) && resid_ld % 4 == 0)) &&
+               (gate == nullptr || (aligned16(gate) && gate_ld % 4 == 0))) ? 1 : 0;
+  g.debug = 0;
+  if (const char* dbg = getenv("MPF_GEMM_DEBUG")) g.debug = atoi(dbg);
+
+  static bool configured = false;
+  if (!configured) {
+    MPF_CUDA_OK(cudaFuncSetAttribute(gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    configured = true;
+  }
+  const long long tiles = static_cast<long long>(slabs) * g.tiles_m * g.tiles_n;
+  const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
+  gemm_bf16x3_kernel<<<grid, kThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(ta, tbh, tbl, tc, tcl, g);
+  count_launch();
+  return finish_launch("gemm_bf16x3");
+}
+
+}  // extern "C"

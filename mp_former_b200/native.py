@@ -1,5 +1,7 @@
 """Python launchers for the C-ABI kernels other than MSDeformAttn (tensor in, tensor out; the caller
 owns autograd).  Every function requires CUDA fp32 tensors and raises RuntimeError otherwise."""
+import os
+
 import torch
 
 from . import _lib
@@ -24,6 +26,54 @@ def split_tf32(x):
         rc = _lib.load().mpf_split_tf32(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), _stream())
     _lib.check(rc, "split_tf32")
     return hi, lo
+
+
+GEMM_MODE = os.environ.get("MPF_GEMM", "bf16x3")       # "bf16x3" (default) | "tf32x3"
+
+
+def split_bf16(x):
+    """x = hi + lo with hi = bf16_rn(x), lo = bf16_rn(x - hi); returns (hi, lo) as bfloat16 tensors."""
+    x = _f32c(x, "x").contiguous()
+    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty_like(hi)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().mpf_split_bf16(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), _stream())
+    _lib.check(rc, "split_bf16")
+    return hi, lo
+
+
+def split_b(w):
+    """Pre-split the B operand ([..., N, K], K contiguous) of ``gemm`` / ``gemm_general``: bf16 halves for the
+    bf16x3 kernel when its TMA constraints hold (K % 8 == 0, N % 4 == 0), TF32 halves for the 3xTF32 kernel
+    otherwise (or when MPF_GEMM=tf32x3)."""
+    if GEMM_MODE == "bf16x3" and w.shape[-1] % 8 == 0 and w.shape[-2] % 4 == 0:
+        return split_bf16(w)
+    return split_tf32(w)
+
+
+def _gemm_bf16x3(a, b_hi, b_lo, bias, relu, transpose_c, split_out, resid, resid_rows, resid_cols, alpha, gate=None):
+    """a [batch, M, K] fp32 (K contiguous); b_hi / b_lo bf16 [batch or 1, N, K] contiguous."""
+    batch, M, K = a.shape
+    nb, N = b_hi.shape[0], b_hi.shape[1]
+    if b_hi.shape[2] != K or nb not in (1, batch) or b_lo.shape != b_hi.shape:
+        raise RuntimeError(f"gemm: shape mismatch a={tuple(a.shape)} b={tuple(b_hi.shape)}")
+    if (M if transpose_c else N) % 4 != 0:
+        raise RuntimeError("gemm (bf16x3): the contiguous output dimension must be a multiple of 4")
+    shape = (batch, N, M) if transpose_c else (batch, M, N)
+    out = torch.empty(shape, dtype=torch.float32, device=a.device)
+    out_lo = torch.empty_like(out) if split_out else None
+    with torch.cuda.device(a.device):
+        rc = _lib.load().mpf_gemm_bf16x3(
+            a.data_ptr(), a.stride(1), a.stride(0) if batch > 1 else M * a.stride(1),
+            b_hi.data_ptr(), b_lo.data_ptr(), K, N * K if (nb > 1) else 0,
+            None if bias is None else bias.data_ptr(), out.data_ptr(),
+            None if out_lo is None else out_lo.data_ptr(), M if transpose_c else N, out.stride(0),
+            None if resid is None else resid.data_ptr(), 0 if resid is None else resid.stride(0),
+            int(resid_rows), int(resid_cols), None if gate is None else gate.data_ptr(),
+            0 if gate is None else gate.stride(0), float(alpha), batch, M, N, K, 1, int(relu), int(transpose_c),
+            _stream())
+    _lib.check(rc, "gemm_bf16x3")
+    return out, out_lo
 
 
 def gemm_tf32x3(a, b_hi, b_lo, bias=None, relu=False, transpose_c=False):
@@ -66,18 +116,27 @@ def gemm(a, b_hi, b_lo, bias=None, relu=False, transpose_c=False, split_out=Fals
         a, b_hi, b_lo = a[None], b_hi[None], b_lo[None]
     if a.stride(2) != 1 or a.stride(1) % 4 or (a.shape[0] > 1 and a.stride(0) % 4):
         a = a.contiguous()
-    if not (b_hi.is_contiguous() and b_lo.is_contiguous()):
-        b_hi, b_lo = b_hi.contiguous(), b_lo.contiguous()
-    batch, M, K = a.shape
-    N = b_hi.shape[1]
-    if b_hi.shape != (batch, N, K) or b_lo.shape != b_hi.shape:
-        raise RuntimeError(f"gemm: shape mismatch a={tuple(a.shape)} b={tuple(b_hi.shape)}")
     if bias is not None:
         bias = _f32c(bias, "bias").contiguous()
     if resid is not None:
         resid = _f32c(resid, "resid")
         if resid.dim() != 2 or resid.stride(1) != 1:
             resid = resid.reshape(-1, resid.shape[-1]).contiguous()
+    if b_hi.dtype == torch.bfloat16:
+        if b_hi.dim() == 3 and b_hi.shape[0] > 1 and b_hi.stride(0) == 0:     # expanded shared weight
+            b_hi, b_lo = b_hi[:1], b_lo[:1]
+        out, out_lo = _gemm_bf16x3(a, b_hi.contiguous(), b_lo.contiguous(), bias, relu, transpose_c, split_out,
+                                   resid, resid_rows, resid_cols, alpha)
+        if squeeze:
+            out = out[0]
+            out_lo = None if out_lo is None else out_lo[0]
+        return (out, out_lo) if split_out else out
+    if not (b_hi.is_contiguous() and b_lo.is_contiguous()):
+        b_hi, b_lo = b_hi.contiguous(), b_lo.contiguous()
+    batch, M, K = a.shape
+    N = b_hi.shape[1]
+    if b_hi.shape != (batch, N, K) or b_lo.shape != b_hi.shape:
+        raise RuntimeError(f"gemm: shape mismatch a={tuple(a.shape)} b={tuple(b_hi.shape)}")
     shape = (batch, N, M) if transpose_c else (batch, M, N)
     out = torch.empty(shape, dtype=torch.float32, device=a.device)
     out_lo = torch.empty_like(out) if split_out else None
@@ -171,6 +230,19 @@ def gemm_general(a, b, a_mn=False, b_mn=False, b_lo=None, bias=None, relu=False,
       a: [batch, M, K] (a_mn False) or [batch, K, M] (a_mn True);  b: [batch, N, K] or [batch, K, N].
     The innermost dimension must be contiguous; row / batch strides must be multiples of 4 elements."""
     a = _f32c(a, "a")
+    if b.dtype == torch.bfloat16:
+        if a_mn or b_mn or b_lo is None or k_splits != 1:
+            raise RuntimeError("gemm_general: bf16 halves are only accepted for K-major operands without split-K")
+        squeeze = a.dim() == 2
+        if squeeze:
+            a, b, b_lo = a[None], b[None], b_lo[None]
+        if a.stride(2) != 1 or a.stride(1) % 4 or (a.shape[0] > 1 and a.stride(0) % 4):
+            a = a.contiguous()
+        if bias is not None:
+            bias = _f32c(bias, "bias").contiguous()
+        out, _ = _gemm_bf16x3(a, b.contiguous(), b_lo.contiguous(), bias, relu, transpose_c, False, None, 0, 0,
+                              alpha, gate=gate)
+        return out[0] if squeeze else out
     b = _f32c(b, "b")
     squeeze = a.dim() == 2
     if squeeze:

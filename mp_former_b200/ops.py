@@ -39,7 +39,7 @@ class _Linear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, relu):
         x2 = x.reshape(-1, x.shape[-1])
-        w_hi, w_lo = native.split_tf32(weight)
+        w_hi, w_lo = native.split_b(weight)
         y = native.gemm(x2, w_hi, w_lo, bias, relu=relu)
         ctx.relu = relu
         ctx.has_bias = bias is not None
@@ -55,7 +55,7 @@ class _Linear(torch.autograd.Function):
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             if weight.shape[0] % 32 == 0:            # reduction dim of the input-gradient GEMM
-                wt_hi, wt_lo = native.split_tf32(weight.t().contiguous())
+                wt_hi, wt_lo = native.split_b(weight.t().contiguous())
                 gx = native.gemm(g2.contiguous(), wt_hi, wt_lo)
             else:
                 gx = g2 @ weight
@@ -88,9 +88,9 @@ class _FFN(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2):
         x2 = x.reshape(-1, x.shape[-1])
-        w1_hi, w1_lo = native.split_tf32(w1)
+        w1_hi, w1_lo = native.split_b(w1)
         hidden = native.gemm(x2, w1_hi, w1_lo, b1, relu=True)
-        w2_hi, w2_lo = native.split_tf32(w2)
+        w2_hi, w2_lo = native.split_b(w2)
         y = native.gemm(hidden, w2_hi, w2_lo, b2)
         ctx.save_for_backward(x2, w1, w2, hidden)
         return y.view(*x.shape[:-1], w2.shape[0])
@@ -99,11 +99,11 @@ class _FFN(torch.autograd.Function):
     def backward(ctx, gy):
         x2, w1, w2, hidden = ctx.saved_tensors
         g2 = gy.reshape(-1, gy.shape[-1]).contiguous()
-        w2t_hi, w2t_lo = native.split_tf32(w2.t().contiguous())
+        w2t_hi, w2t_lo = native.split_b(w2.t().contiguous())
         gh = native.gemm_general(g2, w2t_hi, b_lo=w2t_lo, gate=hidden)       # d(hidden) with the ReLU mask applied
         gw2 = native.matmul_tn(g2, hidden)
         gb2 = g2.sum(0)
-        w1t_hi, w1t_lo = native.split_tf32(w1.t().contiguous())
+        w1t_hi, w1t_lo = native.split_b(w1.t().contiguous())
         gx = native.gemm(gh, w1t_hi, w1t_lo).view(*gy.shape[:-1], w1.shape[1]) if ctx.needs_input_grad[0] else None
         gw1 = native.matmul_tn(gh, x2)
         gb1 = gh.sum(0)
@@ -135,7 +135,7 @@ class _MaskLogits(torch.autograd.Function):
     def forward(ctx, mask_embed, mask_features):
         B, C, H, W = mask_features.shape
         tokens = _channels_last_tokens(mask_features)                       # [B, HW, C]
-        e_hi, e_lo = native.split_tf32(mask_embed)
+        e_hi, e_lo = native.split_b(mask_embed)
         out = native.gemm(tokens, e_hi, e_lo, transpose_c=True)             # [B, Q, HW]
         ctx.save_for_backward(mask_embed, tokens)
         ctx.fshape = (B, C, H, W)
@@ -211,9 +211,9 @@ class _MaskedCrossAttention(torch.autograd.Function):
         HW = memory.shape[1]
         hd = E // nhead
         scale2 = LOG2E / math.sqrt(hd)
-        wq_hi, wq_lo = native.split_tf32(w_in[:E])
-        wk_hi, wk_lo = native.split_tf32(w_in[E:2 * E])
-        wv_hi, wv_lo = native.split_tf32(w_in[2 * E:])
+        wq_hi, wq_lo = native.split_b(w_in[:E])
+        wk_hi, wk_lo = native.split_b(w_in[E:2 * E])
+        wv_hi, wv_lo = native.split_b(w_in[2 * E:])
         # Q (scaled into the log2 domain), pre-split for the attention kernel
         q_hi, q_lo = native.gemm(q_in.reshape(B * Qt, E), wq_hi, wq_lo, b_in[:E], alpha=scale2, split_out=True)
         # K = (memory + pos) Wk^T + bk = memory Wk^T + (pos Wk^T + bk): the second term is batch independent
@@ -226,7 +226,7 @@ class _MaskedCrossAttention(torch.autograd.Function):
         row_open = (bits == -1).all(-1)                                                      # ref decoder :1780
         o, lse2 = native.masked_xattn_fwd(q_hi.view(B, Qt, E), q_lo.view(B, Qt, E), k_hi.view(B, HW, E),
                                           k_lo.view(B, HW, E), vt_hi, vt_lo, bits, row_open, nhead)
-        wo_hi, wo_lo = native.split_tf32(w_out)
+        wo_hi, wo_lo = native.split_b(w_out)
         y = native.gemm(o.view(B * Qt, E), wo_hi, wo_lo, b_out).view(B, Qt, E)
         ctx.save_for_backward(q_in, memory, pos, w_in, b_in, w_out, bits, row_open, o, lse2,
                               q_hi.view(B, Qt, E), q_lo.view(B, Qt, E), k_hi.view(B, HW, E), k_lo.view(B, HW, E))
@@ -248,8 +248,8 @@ class _MaskedCrossAttention(torch.autograd.Function):
         delta = (go.view(B, Qt, nhead, hd) * o.view(B, Qt, nhead, hd)).sum(-1).permute(0, 2, 1).contiguous()
         # operands the forward did not keep: V row-major and K^T (both pre-split by the GEMM epilogue)
         wq, wk, wv = w_in[:E], w_in[E:2 * E], w_in[2 * E:]
-        wk_hi, wk_lo = native.split_tf32(wk)
-        wv_hi, wv_lo = native.split_tf32(wv)
+        wk_hi, wk_lo = native.split_b(wk)
+        wv_hi, wv_lo = native.split_b(wv)
         pos2 = pos.reshape(-1, E)
         pos_k = native.gemm(pos2, wk_hi, wk_lo, b_in[E:2 * E])                      # [HW, E]
         v_hi, v_lo = native.gemm(memory.reshape(B * HW, E), wv_hi, wv_lo, b_in[2 * E:], split_out=True)
@@ -267,8 +267,8 @@ class _MaskedCrossAttention(torch.autograd.Function):
         g_qin = (dq2 @ wq).view(B, Qt, E) if ctx.needs_input_grad[0] else None
         g_mem = g_pos = None
         if ctx.needs_input_grad[1]:
-            wkt_hi, wkt_lo = native.split_tf32(wk.t().contiguous())
-            wvt_hi, wvt_lo = native.split_tf32(wv.t().contiguous())
+            wkt_hi, wkt_lo = native.split_b(wk.t().contiguous())
+            wvt_hi, wvt_lo = native.split_b(wv.t().contiguous())
             g_mem = (native.gemm(dk2, wkt_hi, wkt_lo) + native.gemm(dv2, wvt_hi, wvt_lo)).view(B, HW, E)
         if ctx.needs_input_grad[2]:
             g_pos = (dk.sum(0) @ wk).view(1, HW, E)

@@ -1,0 +1,110 @@
+"""-m gpu: the tcgen05 bf16x3 GEMM (A split in-kernel, TMA-store epilogue) vs an fp64 reference.
+Tolerance: |err| <= 2e-4 * max(1, |ref|) -- operands carry 16 significand bits (hi + lo bf16), i.e. a relative
+error of ~2^-16 per product, 5x inside the path's 1e-3 fp32 contract (the 3xTF32 kernel is held to 1e-4)."""
+import pytest
+import torch
+
+from mp_former_b200 import native
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 2e-4
+
+
+def rel_err(y, r):
+    return ((y.double() - r).abs() / r.abs().clamp(min=1.0)).max().item()
+
+
+def ref64(a, b, bias=None, relu=False):
+    y = a.double() @ b.double().transpose(-1, -2)
+    if bias is not None:
+        y = y + bias.double()
+    return y.relu() if relu else y
+
+
+def test_split_bf16_halves():
+    x = torch.randn(1000, 64, device=DEV) * 3
+    hi, lo = native.split_bf16(x)
+    assert hi.dtype == torch.bfloat16 and lo.dtype == torch.bfloat16
+    assert torch.equal(hi, x.to(torch.bfloat16))
+    assert ((hi.float() + lo.float() - x).abs() <= x.abs() * 2.0 ** -16).all()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 64, 256), (256, 128, 256), (1000, 100, 256),
+                                   (4096, 288, 256), (300, 1024, 256), (777, 256, 1024), (128, 2048, 256),
+                                   (65536, 100, 256), (21504, 768, 256), (40, 256, 48)])
+def test_gemm_matches_fp64(M, N, K):
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    a = torch.randn(M, K, device=DEV, generator=g)
+    b = torch.randn(N, K, device=DEV, generator=g) / K ** 0.5
+    bias = torch.randn(N, device=DEV, generator=g)
+    bh, bl = native.split_bf16(b)
+    for relu in (False, True):
+        y = native.gemm(a, bh, bl, bias, relu=relu)
+        assert y.shape == (M, N)
+        err = rel_err(y, ref64(a, b, bias, relu))
+        assert err < TOL, (M, N, K, relu, err)
+    if M % 4 == 0:
+        yt = native.gemm(a, bh, bl, None, transpose_c=True)
+        assert yt.shape == (N, M)
+        assert rel_err(yt.t(), ref64(a, b)) < TOL
+
+
+def test_batched_transposed_mask_logit_shape():
+    B, Q, C, H, W = 3, 120, 256, 64, 64
+    g = torch.Generator(device=DEV).manual_seed(1)
+    E = torch.randn(B, Q, C, device=DEV, generator=g)
+    F_ = torch.randn(B, C, H, W, device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    eh, el = native.split_bf16(E)
+    a = F_.permute(0, 2, 3, 1).reshape(B, H * W, C)
+    out = native.gemm(a, eh, el, None, transpose_c=True).view(B, Q, H, W)
+    ref = torch.einsum("bqc,bchw->bqhw", E.double(), F_.double())
+    assert rel_err(out, ref) < TOL
+
+
+def test_epilogue_variants():
+    g = torch.Generator(device=DEV).manual_seed(5)
+    B, HW, E = 3, 1000, 256
+    mem = torch.randn(B, HW, E, device=DEV, generator=g)
+    w = torch.randn(E, E, device=DEV, generator=g) / 16
+    bias = torch.randn(E, device=DEV, generator=g)
+    pos_k = torch.randn(HW, E, device=DEV, generator=g)
+    wh, wl = native.split_bf16(w)
+    # row-periodic residual (K projection: memory Wk^T + (pos Wk^T + bk)), pre-split output
+    hi, lo = native.gemm(mem.reshape(B * HW, E), wh, wl, None, resid=pos_k, resid_rows=HW, split_out=True)
+    ref = (mem.double() @ w.double().t() + pos_k.double()).reshape(B * HW, E)
+    assert rel_err(hi + lo, ref) < TOL
+    assert torch.equal(hi.view(torch.int32) & 0x1FFF, torch.zeros_like(hi, dtype=torch.int32))   # TF32-exact halves
+    # scale + bias (query projection), broadcast weight over a batch, transposed + split output (V^T)
+    y = native.gemm(mem.reshape(B * HW, E), wh, wl, bias, alpha=0.25)
+    assert rel_err(y, (mem.double().reshape(-1, E) @ w.double().t() + bias.double()) * 0.25) < TOL
+    vt_hi, vt_lo = native.gemm(mem, wh[None].expand(B, -1, -1), wl[None].expand(B, -1, -1), bias, transpose_c=True,
+                               split_out=True)
+    refv = (mem.double() @ w.double().t() + bias.double()).transpose(1, 2)
+    assert vt_hi.shape == (B, E, HW) and rel_err(vt_hi + vt_lo, refv) < TOL
+    # gate (ReLU backward fused into the input-gradient GEMM of an FFN)
+    T = 3000
+    gy = torch.randn(T, 256, device=DEV, generator=g)
+    w2 = torch.randn(256, 1024, device=DEV, generator=g) / 32
+    hidden = torch.randn(T, 1024, device=DEV, generator=g).relu()
+    w2t_hi, w2t_lo = native.split_bf16(w2.t().contiguous())
+    gh = native.gemm_general(gy, w2t_hi, b_lo=w2t_lo, gate=hidden)
+    refg = (gy.double() @ w2.double()) * (hidden > 0)
+    assert rel_err(gh, refg) < TOL
+
+
+def test_strided_a_and_k_tail():
+    g = torch.Generator(device=DEV).manual_seed(2)
+    big = torch.randn(512, 512, device=DEV, generator=g)
+    a = big[:, :256]                                   # row stride 512, K = 256
+    b = torch.randn(96, 256, device=DEV, generator=g)
+    y = native.gemm(a, *native.split_bf16(b))
+    assert rel_err(y, ref64(a, b)) < TOL * 16          # |b| ~ 1 here: outputs ~ N(0, 256)
+    a48, b48 = torch.randn(8, 48, device=DEV, generator=g), torch.randn(8, 48, device=DEV, generator=g)
+    assert rel_err(native.gemm(a48, *native.split_bf16(b48)), ref64(a48, b48)) < TOL * 4
+
+
+def test_split_b_picks_kernel_by_shape():
+    w = torch.randn(256, 256, device=DEV)
+    assert native.split_b(w)[0].dtype == (torch.bfloat16 if native.GEMM_MODE == "bf16x3" else torch.float32)
+    assert native.split_b(torch.randn(81, 256, device=DEV))[0].dtype == torch.float32      # N % 4 != 0 -> 3xTF32
