@@ -34,7 +34,7 @@ def timeit(fn, reps=5, warm=2):
 def main():
     g = torch.Generator(device=DEV).manual_seed(0)
     rn = lambda *s: torch.randn(*s, device=DEV, generator=g)
-    flags = [0, 1, 64, 2, 4, 8, 16, 32, 48, 2 | 4, 2 | 4 | 8, 2 | 4 | 48, 2 | 4 | 8 | 48]
+    flags = [0, 128, 1, 64, 2, 4, 8, 16, 32, 48, 2 | 4, 2 | 4 | 8, 2 | 4 | 48, 2 | 4 | 8 | 48]
     shapes = ((B * S, 256, 256, "value_proj"), (B * S, 288, 256, "offsets+logits"), (B * S, 1024, 256, "ffn.linear1"),
               (B * S, 256, 1024, "ffn.linear2"))
     for (m, n, k, tag) in shapes:

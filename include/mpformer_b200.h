@@ -208,6 +208,12 @@ int mpf_attn_mask_bits_f32(const float* logits, long long row_stride, int rows, 
                            uint32_t* bits, int words_per_row, void* stream);
 int mpf_pack_bool_bits(const uint8_t* src, int rows, int n, uint32_t* bits, int words_per_row,
                        void* stream);
+/* Mask-piloted (DN) attention masks straight from the ground-truth instance masks:
+ *   bits[row] bit of cell (i,j) = ( F.interpolate(masks[row].float(), (h,w), mode="area")[i,j] <= 1e-8 )
+ * ref: decoder :986-987 (prepare_for_dn_v5), :1593-1594 (gen_mask_dn).  masks [rows, H, W] uint8/bool (0/1);
+ * the area mean of a 0/1 window is <= 1e-8 exactly when the window holds no set pixel (window area < 1e8). */
+int mpf_gt_mask_area_bits(const uint8_t* masks, int rows, int H, int W, int h, int w, uint32_t* bits,
+                          int words_per_row, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused masked multi-head cross-attention, forward (tcgen05 + TMA, 3xTF32):

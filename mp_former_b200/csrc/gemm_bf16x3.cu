@@ -415,7 +415,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         fence_proxy_async_smem();
         epi_bar();
         if (issuer) {
-          if (g.transpose_c) {
+          if (g.debug & 128) {
+          } else if (g.transpose_c) {
             tma_store_3d(&tmC, buf0, m_t * kBM, n0, slab);
             if (g.split_out) tma_store_3d(&tmClo, buf1, m_t * kBM, n0, slab);
           } else {

@@ -79,9 +79,68 @@ pack_bool_bits_kernel(const uint8_t* __restrict__ src, int rows, int n, uint32_t
   if (lane == 0) bits[static_cast<long long>(row) * words_per_row + word] = m;
 }
 
+// Mask-piloted (DN) attention masks: a key (cell of the h x w grid) is masked for a ground-truth instance
+// when the cell holds no pixel of the instance,
+//   F.interpolate(gt.float(), (h, w), mode="area") <= 1e-8            (ref decoder :986-987, :1593-1594)
+// "area" is adaptive average pooling over the window [floor(i*H/h), ceil((i+1)*H/h)) (same for columns); the
+// mean of a 0/1 window is <= 1e-8 exactly when no pixel is set (any set pixel gives >= 1/area >> 1e-8), so the
+// kernel ORs the window's bytes instead of averaging floats.  One warp per 32 consecutive cells of one mask;
+// the lanes' windows are adjacent in memory, 16-byte loads when the window allows.
+__global__ void __launch_bounds__(256)
+gt_mask_area_bits_kernel(const uint8_t* __restrict__ masks, int rows, int H, int W, int h, int w,
+                         uint32_t* __restrict__ bits, int words_per_row) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long total = static_cast<long long>(rows) * words_per_row;
+  if (warp_global >= total) return;
+  const int row = static_cast<int>(warp_global / words_per_row);
+  const int word = static_cast<int>(warp_global - static_cast<long long>(row) * words_per_row);
+  const int key = word * 32 + lane;
+  bool masked = true;                      // padding keys (>= h*w) count as masked
+  if (key < h * w) {
+    const int oy = key / w, ox = key - oy * w;
+    const int y0 = static_cast<int>((static_cast<long long>(oy) * H) / h);
+    const int y1 = static_cast<int>((static_cast<long long>(oy + 1) * H + h - 1) / h);
+    const int x0 = static_cast<int>((static_cast<long long>(ox) * W) / w);
+    const int x1 = static_cast<int>((static_cast<long long>(ox + 1) * W + w - 1) / w);
+    const uint8_t* base = masks + static_cast<long long>(row) * H * W;
+    uint32_t any = 0;
+    for (int y = y0; y < y1 && any == 0; ++y) {
+      const uint8_t* p = base + static_cast<long long>(y) * W + x0;
+      const uint8_t* e = p + (x1 - x0);
+      while (p < e && (reinterpret_cast<uintptr_t>(p) & 15u)) any |= *p++;
+      for (; p + 16 <= e; p += 16) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+        any |= v.x | v.y | v.z | v.w;
+      }
+      while (p < e) any |= *p++;
+    }
+    masked = any == 0;
+  }
+  const uint32_t m = __ballot_sync(0xffffffffu, masked);
+  if (lane == 0) bits[static_cast<long long>(row) * words_per_row + word] = m;
+}
+
 }  // namespace mpf
 
 extern "C" {
+
+int mpf_gt_mask_area_bits(const uint8_t* masks, int rows, int H, int W, int h, int w, uint32_t* bits,
+                          int words_per_row, void* stream) {
+  using namespace mpf;
+  clear_error();
+  MPF_REQUIRE(masks && bits, "gt_mask_area_bits: null pointer argument");
+  MPF_REQUIRE(rows > 0 && H > 0 && W > 0 && h > 0 && w > 0, "gt_mask_area_bits: sizes must be positive");
+  MPF_REQUIRE(words_per_row * 32 >= h * w, "gt_mask_area_bits: words_per_row (%d) too small for %dx%d keys",
+              words_per_row, h, w);
+  const long long warps = static_cast<long long>(rows) * words_per_row;
+  const long long blocks = (warps * 32 + 255) / 256;
+  MPF_REQUIRE(blocks < (1ll << 31), "gt_mask_area_bits: problem too large");
+  gt_mask_area_bits_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      masks, rows, H, W, h, w, bits, words_per_row);
+  count_launch();
+  return finish_launch("gt_mask_area_bits");
+}
 
 int mpf_attn_mask_bits_f32(const float* logits, long long row_stride, int rows, int H, int W, int h, int w,
                            uint32_t* bits, int words_per_row, void* stream) {

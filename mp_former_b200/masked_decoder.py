@@ -28,7 +28,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from . import ops
+from . import native, ops
 from .position_encoding import PositionEmbeddingSine
 from .registry import configurable, register_transformer_decoder
 
@@ -325,6 +325,20 @@ class MultiScaleMaskedTransformerDecoderMaskDN(_MaskedDecoderBase):
         delta = torch.rand_like(masks, dtype=torch.float) < ratio[:, None]
         return torch.logical_xor(masks, delta)
 
+    @staticmethod
+    def _gt_packed(targets, size, scalar, known, bs, pad_size, cache):
+        """Noise-free mask-piloted rows as packed bits [bs, pad_size, words], straight from the GT instance masks
+        (one kernel per image instead of float conversion + area pooling + compare + scatter + pack); rows
+        without a GT instance are fully masked, as in ref decoder :1036-1039."""
+        key = ("bits", int(size[0]), int(size[1]))
+        if key not in cache:
+            rows = [native.gt_mask_area_bits(t["masks"], size) for t in targets if len(t["masks"]) > 0]
+            gt = torch.cat(rows).repeat(scalar, 1)
+            full = torch.full((bs, pad_size, gt.shape[-1]), -1, dtype=torch.int32, device=gt.device)
+            full[known] = gt
+            cache[key] = ops.PackedMask(full, int(size[0]) * int(size[1]))
+        return cache[key]
+
     def prepare_for_dn_v5(self, mask_features, dn_args, size_list, cache=None):
         """ref decoder :968-1060.  Returns None when there is nothing to denoise."""
         targets, scalar, noise_scale = dn_args["tgt"], dn_args["scalar"], dn_args["noise_scale"]
@@ -339,7 +353,7 @@ class MultiScaleMaskedTransformerDecoderMaskDN(_MaskedDecoderBase):
         dn_meta = {"max_num": max_num, "pad_size": pad_size}
         bs = len(num_boxes)
         hw0 = size_list[0][0] * size_list[0][1]
-        masks = self._gt_masked(targets, size_list[0], scalar, noise_scale, cache)
+        cache = {} if cache is None else cache
         labels = torch.cat([t["labels"] for t in targets]).to(dev)
         known_labels = labels.repeat(scalar, 1).view(-1).clone()
         if self.dn_label_noise_ratio > 0:
@@ -354,11 +368,16 @@ class MultiScaleMaskedTransformerDecoderMaskDN(_MaskedDecoderBase):
         known = (known_bid, map_idx)
         padding = torch.zeros(bs, pad_size, feats.shape[-1], device=dev, dtype=feats.dtype)
         padding = padding.index_put(known, feats)
-        padding_mask = torch.ones(bs, pad_size, hw0, dtype=torch.bool, device=dev)
-        padding_mask[known] = masks
+        if noise_scale == 0:
+            gt_rows = self._gt_packed(targets, size_list[0], scalar, known, bs, pad_size, cache)
+        else:
+            masks = self._gt_masked(targets, size_list[0], scalar, noise_scale, cache)
+            padding_mask = torch.ones(bs, pad_size, hw0, dtype=torch.bool, device=dev)
+            padding_mask[known] = masks
+            gt_rows = ops.PackedMask.from_bool(padding_mask)
         output = torch.cat([padding, self.query_feat.weight.unsqueeze(0).repeat(bs, 1, 1)], 1)
         oc, om, attn_mask = self.forward_prediction_heads(output, mask_features, size_list[0])
-        attn_mask = attn_mask.replace_rows(ops.PackedMask.from_bool(padding_mask), pad_size)
+        attn_mask = attn_mask.replace_rows(gt_rows, pad_size)
         tgt_size = pad_size + self.num_queries
         tgt_mask = torch.zeros(tgt_size, tgt_size, dtype=torch.bool, device=dev)
         tgt_mask[pad_size:, :pad_size] = True
@@ -386,7 +405,7 @@ class MultiScaleMaskedTransformerDecoderMaskDN(_MaskedDecoderBase):
             if self.dn_mode != "points":
                 raise NotImplementedError(
                     f"dn_mode={self.dn_mode!r}: only 'points' (the published MP-Former recipe) is implemented")
-            gt_cache, bits_cache = {}, {}
+            gt_cache = {}
             res = self.prepare_for_dn_v5(mask_features, dn_args, size_list, gt_cache)
         dn_hook, tgt_mask, dn_meta = None, None, None
         if res is None:
@@ -399,18 +418,19 @@ class MultiScaleMaskedTransformerDecoderMaskDN(_MaskedDecoderBase):
             def dn_hook(i, level, attn_mask):
                 if not (self.all_lys or i < 3):
                     return attn_mask
-                if dn_args["noise_scale"] == 0 and level in bits_cache:
-                    return attn_mask.replace_rows(bits_cache[level], pad_size)
+                if dn_args["noise_scale"] == 0:
+                    packed = self._gt_packed(dn_args["tgt"], size_list[level], scalar, known, bs, pad_size, gt_cache)
+                    return attn_mask.replace_rows(packed, pad_size)
                 pm = self.gen_mask_dn(dn_args, size_list[level], known, pad_size, scalar, gt_cache)
-                packed = ops.PackedMask.from_bool(pm)
-                bits_cache[level] = packed
-                return attn_mask.replace_rows(packed, pad_size)
+                return attn_mask.replace_rows(ops.PackedMask.from_bool(pm), pad_size)
 
         pc, pm = self._decode(output, src, pos, size_list, mask_features, tgt_mask, heads0, dn_hook)
         if tgt_mask is not None:
-            nq = self.num_queries
-            dn_c, dn_m = [c[:, :-nq] for c in pc], [m[:, :-nq] for m in pm]
-            pc, pm = [c[:, -nq:] for c in pc], [m[:, -nq:] for m in pm]
+            n_dn = pc[0].shape[1] - self.num_queries
+            pc_split = [ops.split_queries(c, n_dn) for c in pc]
+            pm_split = [ops.split_queries(m, n_dn) for m in pm]
+            dn_c, dn_m = [c[0] for c in pc_split], [m[0] for m in pm_split]
+            pc, pm = [c[1] for c in pc_split], [m[1] for m in pm_split]
             dn_out = {"pred_logits": dn_c[-1], "pred_masks": dn_m[-1],
                       "aux_outputs": self._set_aux_loss(dn_c if self.mask_classification else None, dn_m),
                       "dn_args": dn_meta}

@@ -191,6 +191,25 @@ def pack_bool_bits(mask):
     return bits
 
 
+def gt_mask_area_bits(masks, target_size):
+    """masks [n, H, W] bool / uint8 -> packed bits int32 [n, mask_words(h*w)]; bit = 1 (masked) where the
+    area-downsampled mask is <= 1e-8, i.e. the cell holds no instance pixel (ref decoder :986-987)."""
+    _lib.require_cuda(masks, "masks")
+    if masks.dtype not in (torch.bool, torch.uint8) or masks.dim() != 3:
+        raise RuntimeError("gt_mask_area_bits: expected bool/uint8 masks [n, H, W]")
+    m8 = masks.contiguous().view(torch.uint8)
+    n, H, W = m8.shape
+    h, w = int(target_size[0]), int(target_size[1])
+    words = mask_words(h * w)
+    bits = torch.empty((n, words), dtype=torch.int32, device=masks.device)
+    if n == 0:
+        return bits
+    with torch.cuda.device(masks.device):
+        rc = _lib.load().mpf_gt_mask_area_bits(m8.data_ptr(), n, H, W, h, w, bits.data_ptr(), words, _stream())
+    _lib.check(rc, "gt_mask_area_bits")
+    return bits
+
+
 def unpack_bits(bits, n):
     """int32 [..., W] -> bool [..., n] (host-side helper for tests / the library backward)."""
     shifts = torch.arange(32, device=bits.device, dtype=torch.int32)

@@ -196,6 +196,39 @@ def attn_mask_from_logits(outputs_mask, target_size):
     return PackedMask(native.attn_mask_bits(outputs_mask.detach(), (h, w)), h * w)
 
 
+class _SplitQueries(torch.autograd.Function):
+    """x [B, Qt, ...] -> (x[:, :n_first], x[:, n_first:]) as views.  Unlike two independent slices, whose
+    backward each materialise a zero-filled full-size gradient that autograd then adds (five passes over the
+    503 MB mask-logit gradient per prediction head at the bench geometry), the backward here writes both
+    incoming gradients into ONE buffer."""
+
+    @staticmethod
+    def forward(ctx, x, n_first):
+        ctx.set_materialize_grads(False)
+        ctx.n_first = n_first
+        ctx.meta = (x.shape, x.dtype, x.device)
+        return x[:, :n_first], x[:, n_first:]
+
+    @staticmethod
+    def backward(ctx, g0, g1):
+        if g0 is None and g1 is None:
+            return None, None
+        shape, dtype, device = ctx.meta
+        if g0 is not None and g1 is not None:
+            return torch.cat([g0, g1], 1), None
+        g = torch.zeros(shape, dtype=dtype, device=device)
+        if g0 is not None:
+            g[:, :ctx.n_first] = g0
+        else:
+            g[:, ctx.n_first:] = g1
+        return g, None
+
+
+def split_queries(x, n_first):
+    """Splits predictions into the mask-piloted (DN) queries and the matching queries (ref decoder :1697-1703)."""
+    return _SplitQueries.apply(x, n_first)
+
+
 # ------------------------------------------------------------------------------------------------
 # attention
 # ------------------------------------------------------------------------------------------------

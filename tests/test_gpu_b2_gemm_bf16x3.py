@@ -53,7 +53,7 @@ def test_gemm_matches_fp64(M, N, K):
 def test_batched_transposed_mask_logit_shape():
     B, Q, C, H, W = 3, 120, 256, 64, 64
     g = torch.Generator(device=DEV).manual_seed(1)
-    E = torch.randn(B, Q, C, device=DEV, generator=g)
+    E = torch.randn(B, Q, C, device=DEV, generator=g) / C ** 0.5          # logits ~ N(0, 1)
     F_ = torch.randn(B, C, H, W, device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
     eh, el = native.split_bf16(E)
     a = F_.permute(0, 2, 3, 1).reshape(B, H * W, C)

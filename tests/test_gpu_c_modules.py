@@ -5,7 +5,7 @@ import torch
 
 import cases
 import mp_former_b200 as M
-from mp_former_b200 import ops
+from mp_former_b200 import native, ops
 from oracle import torch_oracle as O
 from test_host_logic_cpu import build_decoder, build_pixel_decoder
 from test_oracle_vs_golden import _cmp_out, close, decoder_template, load, pixel_decoder_template
@@ -48,7 +48,7 @@ def test_msdeform_attn_module_vs_reference_golden(golden_dir):
     lsi = torch.cat((st.new_zeros((1,)), st.prod(1).cumsum(0)[:-1]))
     with torch.no_grad():
         y = m.to(DEV)(query.to(DEV), ref_pts.to(DEV), src.to(DEV), st, lsi, None)
-    close(y.cpu(), G["out"], 1e-4)
+    close(y.cpu(), G["out"], 1e-4 if native.GEMM_MODE == "tf32x3" else 5e-4)
 
 
 def test_pixel_decoder_vs_reference_golden(golden_dir):

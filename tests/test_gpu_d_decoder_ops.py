@@ -1,6 +1,8 @@
-"""-m gpu: the decoder-side kernels (bit-packed mask stage, fused masked cross-attention, 3xTF32
+"""-m gpu: the decoder-side kernels (bit-packed mask stage, fused masked cross-attention, split-precision
 linear / mask-logit GEMMs) against the oracle's torch restatement evaluated in fp64.
-Tolerance 1e-4*max(1,|ref|) for fp32 results (contract: 1e-3); mask bits exact."""
+Tolerance TOL*max(1,|ref|) for fp32 results -- 1e-4 with the 3xTF32 GEMM, 5e-4 with the default bf16x3 GEMM
+(16 significand bits per operand; the inputs here are unscaled N(0,1) so |ref| ~ 16 at K = 256) -- against
+the contract's 1e-3; mask bits exact."""
 import math
 
 import pytest
@@ -14,6 +16,7 @@ from test_oracle_vs_golden import load
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
+TOL = 1e-4 if native.GEMM_MODE == "tf32x3" else 5e-4
 
 
 def rel(a, b):
@@ -91,11 +94,11 @@ def test_masked_cross_attention_forward_backward(B, Qt, HW):
                      ref_leaves[5], nhead, mask)
     yr.backward(gy.double())
     assert torch.isfinite(y).all()
-    assert rel(y, yr) < 1e-4, rel(y, yr)
+    assert rel(y, yr) < TOL, rel(y, yr)
     for name, a, b_ in zip(("q_in", "memory", "w_in", "b_in", "w_out", "b_out"), leaves, ref_leaves):
         scale = b_.grad.abs().max().item()
         err = (a.grad.double() - b_.grad).abs().max().item() / max(scale, 1e-6)
-        assert err < 2e-4, (name, err)
+        assert err < 2 * TOL, (name, err)
     # a bool mask is accepted as well and gives the same result
     y2 = ops.masked_cross_attention(q_in, memory, pos, w_in, b_in, w_out, b_out, nhead, mask)
     assert torch.equal(y2, y.detach())
@@ -116,8 +119,8 @@ def test_linear_and_mask_logits_autograd():
         yr = F.linear(xr, wr, br)
         yr = yr.relu() if relu else yr
         yr.backward(gy.double())
-        assert rel(y, yr) < 1e-4
-        assert rel(x.grad, xr.grad) < 1e-4 and rel(w.grad, wr.grad) < 1e-3 and rel(b.grad, br.grad) < 1e-4
+        assert rel(y, yr) < TOL
+        assert rel(x.grad, xr.grad) < TOL and rel(w.grad, wr.grad) < 1e-3 and rel(b.grad, br.grad) < 1e-4
     e = torch.randn(2, 100, 256, device=DEV, generator=g, requires_grad=True)
     f = torch.randn(2, 256, 32, 48, device=DEV, generator=g).contiguous(memory_format=torch.channels_last).requires_grad_(True)
     out = ops.mask_logits(e, f)
@@ -126,9 +129,9 @@ def test_linear_and_mask_logits_autograd():
     er, fr = e.detach().double().requires_grad_(True), f.detach().double().requires_grad_(True)
     outr = torch.einsum("bqc,bchw->bqhw", er, fr)
     outr.backward(go.double())
-    assert rel(out, outr) < 1e-4 and rel(e.grad, er.grad) < 1e-3 and rel(f.grad, fr.grad) < 1e-3
+    assert rel(out, outr) < TOL and rel(e.grad, er.grad) < 1e-3 and rel(f.grad, fr.grad) < 1e-3
     # NCHW-contiguous features are accepted too (one layout copy)
-    assert rel(ops.mask_logits(e.detach(), f.detach().contiguous()), outr) < 1e-4
+    assert rel(ops.mask_logits(e.detach(), f.detach().contiguous()), outr) < TOL
 
 
 def test_ffn_fused_relu_backward():
@@ -144,7 +147,27 @@ def test_ffn_fused_relu_backward():
     refs = [t.detach().double().requires_grad_(True) for t in (x, w1, b1, w2, b2)]
     yr = F.linear(F.relu(F.linear(refs[0], refs[1], refs[2])), refs[3], refs[4])
     yr.backward(gy.double())
-    assert rel(y, yr) < 1e-4
+    assert rel(y, yr) < TOL
     for name, a, r in zip(("x", "w1", "b1", "w2", "b2"), (x, w1, b1, w2, b2), refs):
         scale = r.grad.abs().max().item()
-        assert (a.grad.double() - r.grad).abs().max().item() / scale < 2e-4, name
+        assert (a.grad.double() - r.grad).abs().max().item() / scale < 2 * TOL, name
+
+
+@pytest.mark.parametrize("H,W,h,w,n", [(1024, 1024, 32, 32, 5), (1024, 1024, 128, 128, 3), (512, 768, 64, 96, 4),
+                                       (250, 333, 32, 32, 6), (100, 100, 7, 13, 2), (64, 64, 64, 64, 2)])
+def test_gt_mask_area_bits_equal_area_interpolate_rule(H, W, h, w, n):
+    """Mask-piloted rows from GT masks: bit = (F.interpolate(mask.float(), (h, w), mode='area') <= 1e-8)
+    (ref decoder :986-987), including windows that do not divide the mask size and unaligned rows."""
+    g = torch.Generator(device=DEV).manual_seed(H + W + h + w)
+    masks = torch.zeros(n, H, W, dtype=torch.bool, device=DEV)
+    for i in range(n):                                           # sparse blobs + isolated pixels + one empty mask
+        if i == n - 1:
+            break
+        y0, x0 = int(torch.randint(0, H // 2, (1,), generator=g, device=DEV)), int(torch.randint(0, W // 2, (1,), generator=g, device=DEV))
+        masks[i, y0:y0 + H // 3, x0:x0 + W // 4] = True
+        pts = torch.randint(0, H * W, (5,), generator=g, device=DEV)
+        masks[i].view(-1)[pts] = True
+    bits = native.gt_mask_area_bits(masks, (h, w))
+    ref = F.interpolate(masks.float().unsqueeze(1), size=(h, w), mode="area").flatten(1) <= 1e-8
+    assert torch.equal(native.unpack_bits(bits, h * w), ref)
+    assert torch.equal(bits, native.pack_bool_bits(ref))         # padding bits agree with the packer

@@ -63,6 +63,8 @@ def install_cpu_ops(setattr_fn):
     setattr_fn(ops, "mask_logits", lambda e, f: torch.einsum("bqc,bchw->bqhw", e, f))
     setattr_fn(native, "attn_mask_bits", attn_mask_bits)
     setattr_fn(native, "pack_bool_bits", cpu_pack_bits)
+    setattr_fn(native, "gt_mask_area_bits", lambda masks, size: cpu_pack_bits(
+        F.interpolate(masks.float().unsqueeze(1), size=size, mode="area").flatten(1) <= 1e-8))   # ref decoder :986
     setattr_fn(ops, "masked_cross_attention", xattn)
 
 
@@ -143,6 +145,18 @@ def test_dn_label_noise_and_empty_targets(cpu_ops):
               "boxes": torch.zeros(0, 4)} for _ in range(2)]
     o = dec(x, mf, None, {"tgt": empty, "scalar": 1, "noise_scale": 0.0})
     assert o["dn_out"] is None
+
+
+def test_split_queries_backward_equals_slicing():
+    x = torch.randn(2, 7, 3, 5, requires_grad=True)
+    a, b = M.ops.split_queries(x, 3)
+    (a.sum() * 2 + (b ** 2).sum()).backward()
+    y = x.detach().clone().requires_grad_(True)
+    (y[:, :3].sum() * 2 + (y[:, 3:] ** 2).sum()).backward()
+    assert torch.equal(x.grad, y.grad)
+    x.grad = None
+    M.ops.split_queries(x, 3)[1].sum().backward()            # only one half used: the other half's gradient is zero
+    assert x.grad[:, :3].abs().sum() == 0 and x.grad[:, 3:].eq(1).all()
 
 
 def test_static_query_checkpoint_migration():
