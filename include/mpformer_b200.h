@@ -194,6 +194,15 @@ int mpf_gemm_bf16x3(const float* A, long long lda, long long a_batch_stride, con
                     int resid_rows, int resid_cols, const float* gate, long long gate_ld, float alpha, int batch,
                     int M, int N, int K, int k_splits, int relu, int transpose_c, void* stream);
 
+/* "TN" form in bf16x3: C[b] = A[b]^T * B[b] with A [batch, T, M] and B [batch, T, N] fp32 row-major (reduction over
+ * the leading token dimension T) -- the weight gradient dW = dY^T X of an nn.Linear and dF = dOut^T E of the
+ * mask-logit einsum (ref decoder :1865), without transposed copies: both operands are split into bf16 halves
+ * inside the kernel.  k_splits > 1 cuts T into ranges handled by different CTAs; C then holds batch*k_splits
+ * partial slabs [batch, k_splits, M, N] that the caller sums.  lda/ldb/ldc and batch strides: multiples of 4. */
+int mpf_gemm_bf16x3_tn(const float* A, long long lda, long long a_batch_stride, const float* B, long long ldb,
+                       long long b_batch_stride, float* C, long long ldc, long long c_batch_stride, int batch, int M,
+                       int N, int T, int k_splits, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Boolean stage of the prediction heads, bit-packed:
  *   bits[row][j] bit i = ( sigmoid( bilinear_resize(logits[row], (h,w), align_corners=False) )[32j+i] < 0.5 )

@@ -301,12 +301,48 @@ def gemm_general(a, b, a_mn=False, b_mn=False, b_lo=None, bias=None, relu=False,
     return out[0] if squeeze else out
 
 
+def gemm_tn(a, b, k_splits=1):
+    """C[i] = a[i]^T @ b[i] for a [batch, T, M], b [batch, T, N] (fp32, row-major; 2-D inputs = batch 1) on the
+    bf16x3 TN kernel: both operands are split in-kernel, reduction over T, optional split-K (partials summed here)."""
+    a, b = _f32c(a, "a"), _f32c(b, "b")
+    squeeze = a.dim() == 2
+    if squeeze:
+        a, b = a[None], b[None]
+
+    def fix(t):
+        if t.stride(2) != 1 or t.stride(1) % 4 or (t.shape[0] > 1 and t.stride(0) % 4):
+            return t.contiguous()
+        return t
+    a, b = fix(a), fix(b)
+    batch, T, M = a.shape
+    N = b.shape[2]
+    if b.shape[0] != batch or b.shape[1] != T:
+        raise RuntimeError(f"gemm_tn: shape mismatch a={tuple(a.shape)} b={tuple(b.shape)}")
+    if N % 4:
+        raise RuntimeError("gemm_tn: N must be a multiple of 4")
+    k_splits = max(1, min(int(k_splits), (T + 31) // 32))
+    out = torch.empty((batch * k_splits, M, N), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        rc = _lib.load().mpf_gemm_bf16x3_tn(
+            a.data_ptr(), a.stride(1), a.stride(0) if batch > 1 else T * a.stride(1),
+            b.data_ptr(), b.stride(1), b.stride(0) if batch > 1 else T * b.stride(1),
+            out.data_ptr(), N, M * N, batch, M, N, T, k_splits, _stream())
+    _lib.check(rc, "gemm_bf16x3_tn")
+    if k_splits > 1:
+        out = out.view(batch, k_splits, M, N).sum(1)
+    return out[0] if squeeze else out
+
+
 def matmul_tn(x, y, target_tiles=296):
     """x^T @ y for x [T, M], y [T, N] (reduction over the long token dimension T), e.g. the weight gradient
     dW = dY^T X of an nn.Linear: both operands are consumed MN-major straight from their row-major
     storage; T is cut into K-splits handled by different CTAs whose partial products are summed."""
     T, M = x.shape
     N = y.shape[1]
+    if GEMM_MODE == "bf16x3" and N % 4 == 0 and M % 4 == 0:
+        tiles = ((M + 127) // 128) * ((N + 255) // 256)
+        splits = max(1, min(148, target_tiles // max(1, tiles), (T + 1023) // 1024))
+        return gemm_tn(x, y, k_splits=splits)
     tiles = ((M + 127) // 128) * ((N + 127) // 128)
     splits = max(1, min(64, target_tiles // max(1, tiles), (T + 1023) // 1024))
     return gemm_general(x, y, a_mn=True, b_mn=True, k_splits=splits)

@@ -108,3 +108,22 @@ def test_split_b_picks_kernel_by_shape():
     w = torch.randn(256, 256, device=DEV)
     assert native.split_b(w)[0].dtype == (torch.bfloat16 if native.GEMM_MODE == "bf16x3" else torch.float32)
     assert native.split_b(torch.randn(81, 256, device=DEV))[0].dtype == torch.float32      # N % 4 != 0 -> 3xTF32
+
+
+@pytest.mark.parametrize("T,M,N,batch,splits", [(1024, 128, 256, 1, 1), (64, 128, 64, 1, 1), (43008, 288, 256, 1, 42),
+                                                (1004, 256, 1024, 1, 3), (120, 4096, 256, 2, 1), (344, 100, 64, 3, 2),
+                                                (5000, 1024, 256, 1, 5), (2048, 256, 192, 1, 4), (1920, 768, 256, 1, 2)])
+def test_gemm_tn_matches_fp64(T, M, N, batch, splits):
+    """C = A^T B over the token dimension (weight gradients, dF of the mask logits): both operands split in-kernel,
+    MN-major SWIZZLE_128B operand tiles, ragged T / M / N tails, split-K."""
+    g = torch.Generator(device=DEV).manual_seed(T + M + N + batch)
+    a = torch.randn(batch, T, M, device=DEV, generator=g)
+    b = torch.randn(batch, T, N, device=DEV, generator=g)
+    y = native.gemm_tn(a, b, k_splits=splits)
+    r = a.double().transpose(1, 2) @ b.double()
+    assert y.shape == (batch, M, N)
+    # entries are sums of T O(1) products: compare against the scale of the reduction (sqrt(T))
+    assert (y.double() - r).abs().max().item() / T ** 0.5 < TOL, (y.double() - r).abs().max().item() / T ** 0.5
+    if batch == 1:
+        y2 = native.matmul_tn(a[0], b[0])
+        assert (y2.double() - r[0]).abs().max().item() / T ** 0.5 < TOL
