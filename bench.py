@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--no-dn", action="store_true", help="drop the mask-piloted (DN) query group")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue every launch eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -174,7 +175,7 @@ def run_ours(a):
     import torch.distributed as dist
     import mp_former_b200 as M
     from mp_former_b200 import MultiScaleDeformableAttention as MSDA
-    from mp_former_b200 import _lib, workload
+    from mp_former_b200 import _lib, graphs, native, workload
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -200,9 +201,6 @@ def run_ours(a):
             return self.predictor(ms, mf, None, dn_args)
 
     head = Head()
-    model = head
-    if world > 1:
-        model = torch.nn.parallel.DistributedDataParallel(head, device_ids=[local], gradient_as_bucket_view=True)
     params = [p for p in head.parameters()]
     feats = workload.synthetic_features(B, a.height, a.width, seed=rank, device=dev)
     dn_args = None
@@ -210,12 +208,42 @@ def run_ours(a):
         dn_args = {"tgt": workload.synthetic_targets(B, a.height, a.width, seed=rank, device=dev),
                    "scalar": 1, "noise_scale": 0.0}
 
-    def step(f):
+    # Gradient all-reduce (the path's only collective): one flat NCCL all-reduce of the head's
+    # gradients (~20 M parameters) after the backward, averaged over ranks like DistributedDataParallel.
+    def allreduce_grads():
+        graphs.allreduce_gradients(params, world)
+
+    def eager_step(f):
         for p in params:
             p.grad = None
-        out = model(f, dn_args)
-        loss = pseudo_loss(out)
+        loss = pseudo_loss(head(f, dn_args))
         loss.backward()
+        allreduce_grads()
+        return loss
+
+    for _ in range(max(a.warmup, 3)):
+        eager_step(feats)
+    torch.cuda.synchronize()
+
+    # One CUDA graph for forward + loss + backward (mp_former_b200/graphs.py): ~2,600 launches per step would
+    # otherwise be issued from Python.  Falls back to eager stepping (and says so) if capture is refused.
+    gs, graph_note = None, "disabled (--no-graph)"
+    if not a.no_graph:
+        try:
+            gs = graphs.GraphedStep(lambda inp: pseudo_loss(head(inp, dn_args)), feats, params, warmup=1)
+            graph_note = "forward+loss+backward captured once, replayed per step"
+        except Exception as e:  # noqa: BLE001
+            gs, graph_note = None, f"capture failed, eager stepping: {type(e).__name__}: {str(e)[:160]}"
+            torch.cuda.synchronize()
+
+    def step(f=None):
+        """One step on device-resident inputs (f None: the graph's static input buffers)."""
+        if gs is None:
+            return eager_step(feats if f is None else f)
+        if f is not None:
+            gs.load_inputs(f)
+        loss = gs.replay()
+        allreduce_grads()
         return loss
 
     def sync():
@@ -225,7 +253,7 @@ def run_ours(a):
             torch.cuda.synchronize()
 
     for _ in range(max(a.warmup, 3)):
-        step(feats)
+        step()
     sync()
 
     # ---- timed region: device-resident inputs ------------------------------------------------
@@ -233,18 +261,16 @@ def run_ours(a):
     if sampler:
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         sampler.start()
-    MSDA.profile_begin()
     l0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync()
     ev0.record()
     for _ in range(a.steps):
-        step(feats)
+        step()
     ev1.record()
     sync()
     ms_total = ev0.elapsed_time(ev1)
-    launches = _lib.launch_count() - l0
-    prof = MSDA.profile_end()
+    launches = (_lib.launch_count() - l0) if gs is None else gs.launches_per_replay * a.steps
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if world > 1:
@@ -296,36 +322,70 @@ def run_ours(a):
         e2e = {"value": B * world * n_e2e / (float(te.item()) / 1e3), "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": n_e2e}
 
+    # ---- per-kernel device times (CUDA events around each launch) over two eager steps --------------------------
+    # taken outside the timed region: events cannot be read inside a captured graph, and they serialise nothing
+    n_prof = 2
+    MSDA.profile_begin()
+    native.profile_begin()
+    for _ in range(n_prof):
+        eager_step(feats)
+    prof = MSDA.profile_end()
+    gprof = native.profile_end()
+
     if rank == 0:
         peaks = {}
         pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(pk):
             peaks = json.load(open(pk))
         hbm = peaks.get("hbm_gbs", 6650.0)
-        # MSDeformAttn forward: algorithmic bytes per launch:
+        tens = peaks.get("bf16_tflops_sustained", 1400.0)          # kernels timed inside a long step
+        src = "MEASURED_PEAKS.json" if peaks else "fallback (6650 GB/s, 1400 TFLOP/s sustained)"
+        step_ms = ms_total / a.steps
+
+        def gemm_roof(kind, what):
+            r = gprof.get(kind)
+            if not r or r["ms"] <= 0:
+                return None
+            n = r["launches"]
+            tf = r["flops"] / (r["ms"] / 1e3) / 1e12
+            gb = r["bytes"] / (r["ms"] / 1e3) / 1e9
+            return {"kernel": f"{kind} ({what})", "bound": "tensor", "achieved": tf, "peak": tens, "unit": "TFLOP/s",
+                    "frac": tf / tens, "traffic": None, "peak_source": src + " bf16_tflops_sustained",
+                    "note": "algorithmic flops 2*M*N*K; the bf16x3 split issues 3 MMAs per product, so frac <= 1/3",
+                    "tensor_issue_frac": 3 * tf / tens, "achieved_hbm_GBs": gb, "hbm_frac": gb / hbm,
+                    "algorithmic_flops_per_launch": r["flops"] / n, "algorithmic_bytes_per_launch": r["bytes"] / n,
+                    "avg_launch_ms": r["ms"] / n, "launches_timed": n,
+                    "share_of_step": r["ms"] / n_prof / step_ms}
+
+        # MSDeformAttn: algorithmic bytes per launch:
         #   4 * (S*M*D + 2*Lq*M*L*P + Lq*M*L*P + Lq*M*D) per image
         S = sum((a.height // s) * (a.width // s) for s in (32, 16, 8))
         Mh, D, L, P = 8, 32, 3, 4
         alg = 4 * (S * Mh * D + 2 * S * Mh * L * P + S * Mh * L * P + S * Mh * D) * B
         fwd_ms = statistics.mean(prof["fwd_ms"]) if prof["fwd_ms"] else None
         bwd_ms = statistics.mean(prof["bwd_ms"]) if prof["bwd_ms"] else None
-        roof = None
+        msda = None
         if fwd_ms:
             ach = alg / (fwd_ms / 1e3) / 1e9
-            roof = {"kernel": "msda_enc_fwd_kernel<8> (MSDeformAttn forward, softmax+locations fused)",
+            msda = {"kernel": "msda_enc_fwd_kernel<8> (MSDeformAttn forward, softmax+locations fused)",
                     "bound": "hbm", "achieved": ach, "peak": hbm,
                     "unit": "GB/s", "frac": ach / hbm, "traffic": None,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                    "peak_source": src + " hbm_gbs",
                     "algorithmic_bytes_per_launch": alg, "avg_launch_ms": fwd_ms,
                     "launches_timed": len(prof["fwd_ms"]),
-                    "share_of_step": fwd_ms * len(prof["fwd_ms"]) / ms_total}
+                    "share_of_step": fwd_ms * len(prof["fwd_ms"]) / n_prof / step_ms}
             if bwd_ms:
                 alg_b = (4 * (S * Mh * D * 2 + 3 * S * Mh * L * P) + 4 * (S * Mh * D + 3 * S * Mh * L * P)) * B
-                roof["backward"] = {"kernel": "msda_enc_bwd_kernel<8> (+ grad_value memset)", "avg_launch_ms": bwd_ms,
+                msda["backward"] = {"kernel": "msda_enc_bwd_kernel<8> (+ grad_value memset)", "avg_launch_ms": bwd_ms,
                                     "achieved": alg_b / (bwd_ms / 1e3) / 1e9,
                                     "frac": alg_b / (bwd_ms / 1e3) / 1e9 / hbm,
                                     "algorithmic_bytes_per_launch": alg_b,
-                                    "share_of_step": bwd_ms * len(prof["bwd_ms"]) / ms_total}
+                                    "share_of_step": bwd_ms * len(prof["bwd_ms"]) / n_prof / step_ms}
+        # `roofline` = the dominant kernel of the step (largest share); the others ride along under their names
+        gk = gemm_roof("gemm_bf16x3_kernel", "linears / 1x1 convs / mask logits / projections, fwd + input grads")
+        gt = gemm_roof("gemm_bf16x3_tn_kernel", "weight gradients, dF of the mask logits")
+        cands = [r for r in (gk, gt, msda) if r]
+        roof = max(cands, key=lambda r: r["share_of_step"]) if cands else None
         cpu = None
         if not a.no_cpu_baseline and world == 1:
             fn, sample = cpu_port_step_fn(a)
@@ -339,13 +399,17 @@ def run_ours(a):
                    "sample": sample + f" ({n} steps, {dt:.1f}s)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
-            "warmup": max(a.warmup, 3), "ms_per_step": ms_total / a.steps, "higher_is_better": True,
+            "warmup": max(a.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "images_per_gpu": B, "global_batch": B * world,
                        "parallelism": f"dp{world}" if world > 1 else "single",
                        "l2": "inputs+activations per step (>2 GB) exceed the 126 MB L2; no explicit flush",
-                       "native_ops": sorted(M.ops.NATIVE_OPS), "tf32": False},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+                       "native_ops": sorted(M.ops.NATIVE_OPS), "tf32": False,
+                       "arithmetic": "fp32 storage; GEMMs in bf16x3 split arithmetic (fp32 accumulate), attention "
+                                     "core in 3xTF32; no single-pass reduced precision",
+                       "cuda_graph": graph_note},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof,
+            "roofline_msda": msda, "roofline_gemm": gk, "roofline_gemm_tn": gt, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

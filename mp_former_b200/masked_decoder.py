@@ -339,6 +339,21 @@ class MultiScaleMaskedTransformerDecoderMaskDN(_MaskedDecoderBase):
             cache[key] = ops.PackedMask(full, int(size[0]) * int(size[1]))
         return cache[key]
 
+    @staticmethod
+    def _dn_indices(dn_args, num_boxes, scalar, single_pad, dev):
+        """(batch index, slot index) of every mask-piloted query (ref decoder :1020-1029).  They depend only on the
+        host-known instance counts; built once per ``dn_args`` and kept in it, so a second call with the same
+        targets (e.g. under CUDA-graph capture) performs no host-to-device copy."""
+        cache = dn_args.setdefault("_mpf_index_cache", {})
+        key = (str(dev), int(scalar), int(single_pad), tuple(num_boxes))
+        if key not in cache:
+            bs = len(num_boxes)
+            batch_idx = torch.repeat_interleave(torch.arange(bs), torch.as_tensor(num_boxes))
+            idx = torch.cat([torch.arange(n) for n in num_boxes])
+            map_idx = torch.cat([idx + single_pad * i for i in range(scalar)]).long()
+            cache[key] = (batch_idx.repeat(scalar).to(dev), map_idx.to(dev))
+        return cache[key]
+
     def prepare_for_dn_v5(self, mask_features, dn_args, size_list, cache=None):
         """ref decoder :968-1060.  Returns None when there is nothing to denoise."""
         targets, scalar, noise_scale = dn_args["tgt"], dn_args["scalar"], dn_args["noise_scale"]
@@ -357,15 +372,13 @@ class MultiScaleMaskedTransformerDecoderMaskDN(_MaskedDecoderBase):
         labels = torch.cat([t["labels"] for t in targets]).to(dev)
         known_labels = labels.repeat(scalar, 1).view(-1).clone()
         if self.dn_label_noise_ratio > 0:
+            # same law as ref :1007-1015 (each label is replaced w.p. LB_NOISE_RATIO by a uniform class), written
+            # without boolean-mask indexing so that it neither synchronises nor breaks CUDA-graph capture
             prob = torch.rand_like(known_labels.float())
             chosen = prob < self.dn_label_noise_ratio
-            known_labels[chosen] = torch.randint_like(known_labels[chosen], 0, self.num_classes)
+            known_labels = torch.where(chosen, torch.randint_like(known_labels, 0, self.num_classes), known_labels)
         feats = self.label_enc(known_labels)
-        batch_idx = torch.repeat_interleave(torch.arange(bs), torch.as_tensor(num_boxes))
-        known_bid = batch_idx.repeat(scalar).to(dev)
-        idx = torch.cat([torch.arange(n) for n in num_boxes])
-        map_idx = torch.cat([idx + single_pad * i for i in range(scalar)]).long().to(dev)
-        known = (known_bid, map_idx)
+        known = self._dn_indices(dn_args, num_boxes, scalar, single_pad, dev)
         padding = torch.zeros(bs, pad_size, feats.shape[-1], device=dev, dtype=feats.dtype)
         padding = padding.index_put(known, feats)
         if noise_scale == 0:

@@ -30,6 +30,47 @@ def split_tf32(x):
 
 GEMM_MODE = os.environ.get("MPF_GEMM", "bf16x3")       # "bf16x3" (default) | "tf32x3"
 
+# Optional per-launch device timing of the GEMM kernels (bench.py's roofline leg): CUDA events on the launching
+# stream right around the C-ABI call, with the launch's algorithmic flops / bytes.  Off by default.
+_PROFILE = None
+
+
+def profile_begin():
+    global _PROFILE
+    _PROFILE = []
+
+
+def profile_end():
+    """-> {kernel: {"ms", "launches", "flops", "bytes"}} summed over the launches since profile_begin()."""
+    global _PROFILE
+    p, _PROFILE = _PROFILE, None
+    torch.cuda.synchronize()
+    out = {}
+    for kind, flops, nbytes, a, b in p or []:
+        r = out.setdefault(kind, {"ms": 0.0, "launches": 0, "flops": 0.0, "bytes": 0.0})
+        r["ms"] += a.elapsed_time(b)
+        r["launches"] += 1
+        r["flops"] += flops
+        r["bytes"] += nbytes
+    return out
+
+
+class _Timed:
+    def __init__(self, kind, flops, nbytes):
+        self.rec = (kind, flops, nbytes)
+
+    def __enter__(self):
+        if _PROFILE is not None:
+            self.a, self.b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _PROFILE is not None:
+            self.b.record()
+            _PROFILE.append(self.rec + (self.a, self.b))
+        return False
+
 
 def split_bf16(x):
     """x = hi + lo with hi = bf16_rn(x), lo = bf16_rn(x - hi); returns (hi, lo) as bfloat16 tensors."""
@@ -62,7 +103,8 @@ def _gemm_bf16x3(a, b_hi, b_lo, bias, relu, transpose_c, split_out, resid, resid
     shape = (batch, N, M) if transpose_c else (batch, M, N)
     out = torch.empty(shape, dtype=torch.float32, device=a.device)
     out_lo = torch.empty_like(out) if split_out else None
-    with torch.cuda.device(a.device):
+    nbytes = 4.0 * batch * (M * K + M * N * (2 if split_out else 1) + (M * N if gate is not None else 0)) + 4.0 * nb * N * K
+    with torch.cuda.device(a.device), _Timed("gemm_bf16x3_kernel", 2.0 * batch * M * N * K, nbytes):
         rc = _lib.load().mpf_gemm_bf16x3(
             a.data_ptr(), a.stride(1), a.stride(0) if batch > 1 else M * a.stride(1),
             b_hi.data_ptr(), b_lo.data_ptr(), K, N * K if (nb > 1) else 0,
@@ -322,7 +364,8 @@ def gemm_tn(a, b, k_splits=1):
         raise RuntimeError("gemm_tn: N must be a multiple of 4")
     k_splits = max(1, min(int(k_splits), (T + 31) // 32))
     out = torch.empty((batch * k_splits, M, N), dtype=torch.float32, device=a.device)
-    with torch.cuda.device(a.device):
+    with torch.cuda.device(a.device), _Timed("gemm_bf16x3_tn_kernel", 2.0 * batch * M * N * T,
+                                             4.0 * batch * (T * M + T * N + k_splits * M * N)):
         rc = _lib.load().mpf_gemm_bf16x3_tn(
             a.data_ptr(), a.stride(1), a.stride(0) if batch > 1 else T * a.stride(1),
             b.data_ptr(), b.stride(1), b.stride(0) if batch > 1 else T * b.stride(1),

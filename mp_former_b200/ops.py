@@ -1,9 +1,10 @@
 """Device ops of the hot path, each with exactly one implementation.
 
 ``linear``, ``mask_logits``, ``attn_mask_from_logits`` and ``masked_cross_attention`` run forward AND
-backward on this package's hand-written sm_100a kernels (tcgen05 3xTF32 GEMM incl. MN-major operands for the
-weight gradients, bit-packed mask kernel, fused masked-attention forward and the two backward kernels that
-recompute the probabilities from the saved log-sum-exp) through the C ABI.  ``self_attention`` and the tiny
+backward on this package's hand-written sm_100a kernels (tcgen05 split-precision GEMMs: bf16x3 with in-kernel
+operand splitting and TMA-store epilogue for K-major products and for the token-reduction "TN" products of the
+weight gradients, 3xTF32 for the remaining mixed-major case; bit-packed mask kernels; fused masked-attention
+forward and the two backward kernels that recompute the probabilities from the saved log-sum-exp) through the C ABI.  ``self_attention`` and the tiny
 query-side layers (a few hundred rows) stay on library ops (launch-latency bound).
 
 Inputs must be CUDA fp32 tensors; there is no CPU path.
@@ -15,8 +16,8 @@ import torch.nn.functional as F
 
 from . import _lib, native
 
-NATIVE_OPS = {"ms_deform_attn_forward", "ms_deform_attn_backward", "linear fwd+bwd (3xTF32 tcgen05 GEMM)",
-              "mask_logits fwd+bwd (3xTF32 tcgen05 GEMM)", "attn_mask_bits",
+NATIVE_OPS = {"ms_deform_attn_forward", "ms_deform_attn_backward", "linear fwd+bwd (bf16x3 tcgen05 GEMM, TMA in/out)",
+              "mask_logits fwd+bwd (bf16x3 / 3xTF32 tcgen05 GEMM)", "attn_mask_bits", "gt_mask_area_bits",
               "masked_cross_attention fwd+bwd (tcgen05)"}
 
 # fp32 ``sigmoid(x) < 0.5`` as evaluated by the reference (1/(1+exp(-x)) with a correctly rounded exp)

@@ -51,9 +51,18 @@ def _worker(rank, world, port, ret):
     t = torch.tensor([float(rank + 1)])
     dist.all_reduce(t, op=dist.ReduceOp.MAX)           # the bench's max-over-ranks reduction
     grads = {n: p.grad.clone() for n, p in dec.named_parameters() if p.grad is not None}
+    # the flat gradient all-reduce bench.py uses after a CUDA-graph replay must equal DDP's bucketed one
+    from mp_former_b200 import graphs
+    for p in dec.parameters():
+        p.grad = None
+    _loss(dec([t_[sl] for t_ in x], mf[sl])).backward()
+    graphs.allreduce_gradients(list(dec.parameters()), world)
+    flat_ok = all((p.grad - grads[n]).abs().max().item() <= 1e-5 * max(1e-6, grads[n].abs().max().item())
+                  for n, p in dec.named_parameters() if p.grad is not None)
     if rank == 0:
         ret["grads"] = grads
         ret["max"] = t.item()
+        ret["flat_ok"] = flat_ok
     dist.barrier()
     dist.destroy_process_group()
 
@@ -64,6 +73,7 @@ def test_two_rank_gloo_matches_single_process(monkeypatch):
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert ret["max"] == float(world)
+    assert ret["flat_ok"]
     dec, x, mf = _build(monkeypatch.setattr)      # patches are undone after the test
     # DDP averages gradients over ranks; each rank's loss is the mean over its shard
     per = x[0].shape[0] // world
