@@ -204,6 +204,23 @@ int mpf_gemm_bf16x3_tn(const float* A, long long lda, long long a_batch_stride, 
                        int N, int T, int k_splits, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Row-wise kernels of the encoder / decoder layers.
+ *   mpf_add_layernorm_fwd_f32:  y = LayerNorm(x + r) * gamma + beta over the last dimension (C = 128, 256 or 512;
+ *     r may be NULL), also writing the per-row mean and 1/sqrt(var + eps) for the backward.
+ *     ref: pixel_decoder/msdeformattn.py:125-126,129 (norm1 / norm2 of the encoder layer), decoder :52,:112,:169.
+ *   mpf_add_layernorm_bwd_f32:  dx (= gradient of both x and r) and per-CTA partial sums
+ *     partial[p][0][c] = sum dy*xhat, partial[p][1][c] = sum dy  for p < mpf_add_layernorm_partials(rows)
+ *     (the caller adds the partials: dgamma, dbeta).
+ *   mpf_colsum_f32:  out[c] = sum_rows x[row*ld + c]  (bias gradients of the Linear layers; out is zeroed here).
+ * ------------------------------------------------------------------------------------------- */
+int mpf_add_layernorm_partials(long long rows);
+int mpf_add_layernorm_fwd_f32(const float* x, const float* r, const float* gamma, const float* beta, float eps,
+                              long long rows, int C, float* y, float* mean, float* rstd, void* stream);
+int mpf_add_layernorm_bwd_f32(const float* dy, const float* x, const float* r, const float* gamma, const float* mean,
+                              const float* rstd, long long rows, int C, float* dx, float* partial, void* stream);
+int mpf_colsum_f32(const float* x, long long rows, int C, long long ld, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Boolean stage of the prediction heads, bit-packed:
  *   bits[row][j] bit i = ( sigmoid( bilinear_resize(logits[row], (h,w), align_corners=False) )[32j+i] < 0.5 )
  * ref: transformer_decoder/mask2former_transformer_decoder.py:1869-1875 (F.interpolate, sigmoid, < 0.5;

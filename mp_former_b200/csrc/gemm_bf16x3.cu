@@ -12,11 +12,12 @@
 //       tile, so the LSU never sees the 128-rows-x-16-bytes scatter the 3xTF32 epilogue issues (the timing
 //       decomposition in profiles/r1i_gemm_debug_probe.jsonl shows those stores cost 30% of a K=256 GEMM).
 //
-// One persistent CTA per SM, 12 warps:
+// One persistent CTA per SM, 16 warps:
 //   warp 0      TMA producer   raw A (fp32, SWIZZLE_128B) + B_hi + B_lo (bf16, SWIZZLE_64B) per 32-wide k-block
 //   warps 8-11  converters     thread = tile row: 8 x LDS.128 raw -> 4 + 4 x STS.128 bf16 hi / lo (SWIZZLE_64B K-major)
 //   warp 1      MMA issuer     2 k-steps x 3 tcgen05.mma.kind::f16 (M=128, N=BN, K=16) per k-block
-//   warps 4-7   epilogue       tcgen05.ld -> bias/residual/scale/ReLU/gate -> staging tile -> cp.async.bulk.tensor store
+//   warps 4-7, 12-15  epilogue (two groups, alternate 32-column chunks)
+//                              tcgen05.ld -> bias/residual/scale/ReLU/gate -> staging tile -> cp.async.bulk.tensor store
 //   warp 2      TMEM allocation (2 accumulators x 256 columns, double-buffered across tiles)
 #include "mpf_common.cuh"
 #include "sm100_ptx.cuh"
@@ -38,7 +39,7 @@ constexpr int kBK = 32;                        // k-block: 32 fp32 = 128 B raw r
 constexpr int kRawABytes = kBM * kBK * 4;      // 16 KiB
 constexpr int kOpABytes = kBM * kBK * 2;       // 8 KiB each for A_hi, A_lo
 constexpr int kStagingBytes = kBM * 32 * 4;    // 16 KiB: 128 rows x 32 fp32 (or 32 x 128 transposed)
-constexpr int kThreads = 384;
+constexpr int kThreads = 512;
 constexpr int kMaxStages = 6;
 constexpr int kSmemBudget = 232448;            // 227 KiB opt-in maximum per CTA
 constexpr int kTmemCols = 512;
@@ -78,7 +79,7 @@ __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
 // D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate.  One thread issues.
 __device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -156,7 +157,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4);
+      mbar_init(&tempty[a], 8);
     }
     fence_mbar_init();
   }
@@ -242,7 +243,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (acc == 0) acc_phase ^= 1;
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 8 && warp < 12) {
     // ================= converters (128 threads, thread = tile row) =================
     const int r = threadIdx.x - 256;
     const int rsw = r & 7;                 // SWIZZLE_128B: 16-byte chunk index ^ (row % 8)
@@ -282,13 +283,17 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
     }
   } else if (warp >= 4) {
-    // ================= epilogue (warps 4..7 -> TMEM lane groups 0..3) =================
-    const int ew = warp - 4;
+    // ================= epilogue: two groups of 4 warps (4..7 and 12..15), warp % 4 -> TMEM lane group =========
+    // Group eg drains the 32-column chunks c = eg, eg + 2, ... of every tile through its own staging buffer and
+    // named barrier, so two chunks are in flight (tcgen05.ld / math / staging / TMA store) at any time.
+    const int eg = warp >= 12 ? 1 : 0;
+    const int ew = warp & 3;
     const int trow = ew * 32 + lane;               // row of the tile this thread drains
-    const bool issuer = (threadIdx.x == 128);
+    const bool issuer = (ew == 0 && lane == 0);
+    const int bar_id = 1 + eg;
+    uint8_t* const sbuf = staging + eg * kStagingBytes;
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint32_t chunk_ctr = 0;
     const int nchunks = BN / 32;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n_t = tile % g.tiles_n;
@@ -308,13 +313,19 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       for (int c = 0; c < nchunks; ++c)
         if (n_t * BN + c * 32 < g.N) live = c + 1;
       if (g.debug & 2) live = 0;
+      const int my_last = live - 1 - ((live - 1 - eg) & 1);     // last chunk of this group (< eg: none)
+      if (live <= eg) {                             // nothing to drain for this group: release the accumulator
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+      }
 #pragma unroll 1
-      for (int c = 0; c < live; ++c) {
+      for (int c = eg; c < live; c += 2) {
         const int n0 = n_t * BN + c * 32;
         uint32_t v[32];
         tmem_ld_32x32(t_addr + c * 32, v);
         tmem_ld_wait();
-        if (c == live - 1) {                        // accumulator fully read: hand it back to the MMA warp
+        if (c == my_last) {                         // this group's part of the accumulator is read
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -379,19 +390,13 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // ---- registers -> staging tile -> TMA store (clipped at M / N by the tensor map) ----
         // row-major C: staging is [128 rows][32 fp32] with the 128-byte swizzle (16-byte chunk ^ row % 8);
         // transposed C: staging is [32 n-rows][128 m] plain (a warp writes 128 contiguous bytes).
-        uint8_t* buf0 = staging + (g.split_out ? 0 : (chunk_ctr & 1) * kStagingBytes);
-        uint8_t* buf1 = staging + kStagingBytes;
-        if (issuer) {
-          if (g.split_out) bulk_wait_read<0>(); else bulk_wait_read<1>();
-        }
-        epi_bar();
-        auto put = [&](uint8_t* buf, const float (&val)[32]) {
+        auto put = [&](const float (&val)[32]) {
           if (g.transpose_c) {
-            float* bt = reinterpret_cast<float*>(buf) + trow;
+            float* bt = reinterpret_cast<float*>(sbuf) + trow;
 #pragma unroll
             for (int j = 0; j < 32; ++j) bt[j * kBM] = val[j];
           } else {
-            uint8_t* br = buf + trow * 128;
+            uint8_t* br = sbuf + trow * 128;
             const int sw = trow & 7;
 #pragma unroll
             for (int q = 0; q < 8; ++q)
@@ -399,8 +404,24 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                   make_float4(val[4 * q], val[4 * q + 1], val[4 * q + 2], val[4 * q + 3]);
           }
         };
+        auto flush = [&](const CUtensorMap* tm) {   // staging tile of this group -> global
+          fence_proxy_async_smem();
+          epi_bar(bar_id);
+          if (issuer) {
+            if (g.debug & 128) {
+            } else if (g.transpose_c) {
+              tma_store_3d(tm, sbuf, m_t * kBM, n0, slab);
+            } else {
+              tma_store_3d(tm, sbuf, n0, m_t * kBM, slab);
+            }
+            bulk_commit();
+          }
+        };
+        if (issuer) bulk_wait_read<0>();            // the previous store of this group has left the staging tile
+        epi_bar(bar_id);
         if (!g.split_out) {
-          put(buf0, f);
+          put(f);
+          flush(&tmC);
         } else {                       // emit the result pre-split (TF32 halves) for the attention kernels
           float lo[32];
 #pragma unroll
@@ -409,28 +430,13 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             lo[j] = rn_tf32(f[j] - h);
             f[j] = h;
           }
-          put(buf0, f);
-          put(buf1, lo);
+          put(f);
+          flush(&tmC);
+          if (issuer) bulk_wait_read<0>();
+          epi_bar(bar_id);
+          put(lo);
+          flush(&tmClo);
         }
-        fence_proxy_async_smem();
-        epi_bar();
-        if (issuer) {
-          if (g.debug & 128) {
-          } else if (g.transpose_c) {
-            tma_store_3d(&tmC, buf0, m_t * kBM, n0, slab);
-            if (g.split_out) tma_store_3d(&tmClo, buf1, m_t * kBM, n0, slab);
-          } else {
-            tma_store_3d(&tmC, buf0, n0, m_t * kBM, slab);
-            if (g.split_out) tma_store_3d(&tmClo, buf1, n0, m_t * kBM, slab);
-          }
-          bulk_commit();
-        }
-        ++chunk_ctr;
-      }
-      if (live == 0) {                               // (debug only) nothing read: still release the accumulator
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[acc]);
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;

@@ -1,0 +1,258 @@
+// Row-wise HBM-bound kernels of the encoder / decoder layers (C = 256 channels per token):
+//
+//   y = LayerNorm(x + r) * gamma + beta            (ref: pixel_decoder/msdeformattn.py:125-126,129 norm1/norm2 of the
+//                                                    encoder layer; decoder :52,:112,:169 post-norm blocks)
+//   its backward (dx = ds for both addends, dgamma, dbeta)
+//   column sums of a [rows, C] matrix               (bias gradients of the nn.Linear layers)
+//
+// The reference runs `src + src2` and `LayerNorm` as separate PyTorch kernels (5 passes over the token matrix
+// forward, 5 backward); here the sum is never written: forward = read x, r / write y (3 passes), backward = read
+// x, r, dy / write dx (4 passes) with the per-channel dgamma / dbeta partial sums kept in registers across the rows a
+// warp owns.  One warp per token row: 32 lanes x VPT float4 = C channels, 16-byte coalesced accesses, mean / variance
+// by warp shuffles (two-pass: mean, then sum of squared deviations, both in fp32).
+#include "mpf_common.cuh"
+
+namespace mpf {
+
+constexpr int kRowThreads = 256;           // 8 warps = 8 rows in flight per CTA
+constexpr int kRowWarps = kRowThreads / 32;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int VPT>   // float4 per lane: C = 128 * VPT
+__global__ void __launch_bounds__(kRowThreads)
+add_layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ r, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, float eps, long long rows, float* __restrict__ y,
+                         float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  constexpr int C = 128 * VPT;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = static_cast<long long>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5);
+  const long long nwarps = static_cast<long long>(gridDim.x) * kRowWarps;
+  float4 gm[VPT], bt[VPT];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    gm[i] = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
+    bt[i] = __ldg(reinterpret_cast<const float4*>(beta) + i * 32 + lane);
+  }
+  for (long long row = warp0; row < rows; row += nwarps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + row * C);
+    float4 s[VPT];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      s[i] = __ldg(xr + i * 32 + lane);
+      if (r != nullptr) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(r + row * C) + i * 32 + lane);
+        s[i].x += t.x; s[i].y += t.y; s[i].z += t.z; s[i].w += t.w;
+      }
+      sum += (s[i].x + s[i].y) + (s[i].z + s[i].w);
+    }
+    const float mean = warp_sum(sum) * (1.f / C);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const float a = s[i].x - mean, b = s[i].y - mean, c = s[i].z - mean, d = s[i].w - mean;
+      sq += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(sq) * (1.f / C) + eps);
+    float4* yr = reinterpret_cast<float4*>(y + row * C);
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      float4 o;
+      o.x = (s[i].x - mean) * rstd * gm[i].x + bt[i].x;
+      o.y = (s[i].y - mean) * rstd * gm[i].y + bt[i].y;
+      o.z = (s[i].z - mean) * rstd * gm[i].z + bt[i].z;
+      o.w = (s[i].w - mean) * rstd * gm[i].w + bt[i].w;
+      yr[i * 32 + lane] = o;
+    }
+    if (lane == 0) {
+      mean_out[row] = mean;
+      rstd_out[row] = rstd;
+    }
+  }
+}
+
+// dx = rstd * (g - mean_c(g) - xhat * mean_c(g * xhat)),  g = dy * gamma,  xhat = (x + r - mean) * rstd
+// partial[blockIdx.x][0][c] = sum over this CTA's rows of dy * xhat, partial[blockIdx.x][1][c] = sum of dy.
+template <int VPT>
+__global__ void __launch_bounds__(kRowThreads)
+add_layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ r,
+                         const float* __restrict__ gamma, const float* __restrict__ mean_in,
+                         const float* __restrict__ rstd_in, long long rows, float* __restrict__ dx,
+                         float* __restrict__ partial) {
+  constexpr int C = 128 * VPT;
+  __shared__ float4 red[kRowWarps][2 * VPT][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long warp0 = static_cast<long long>(blockIdx.x) * kRowWarps + w;
+  const long long nwarps = static_cast<long long>(gridDim.x) * kRowWarps;
+  float4 gm[VPT], dg[VPT], db[VPT];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    gm[i] = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
+    dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (long long row = warp0; row < rows; row += nwarps) {
+    const float mean = __ldg(mean_in + row), rstd = __ldg(rstd_in + row);
+    float4 xh[VPT], g[VPT];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      float4 s = __ldg(reinterpret_cast<const float4*>(x + row * C) + i * 32 + lane);
+      if (r != nullptr) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(r + row * C) + i * 32 + lane);
+        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+      }
+      const float4 d = __ldg(reinterpret_cast<const float4*>(dy + row * C) + i * 32 + lane);
+      xh[i] = make_float4((s.x - mean) * rstd, (s.y - mean) * rstd, (s.z - mean) * rstd, (s.w - mean) * rstd);
+      g[i] = make_float4(d.x * gm[i].x, d.y * gm[i].y, d.z * gm[i].z, d.w * gm[i].w);
+      s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+      s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
+      dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y; dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
+      db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
+    }
+    const float m1 = warp_sum(s1) * (1.f / C), m2 = warp_sum(s2) * (1.f / C);
+    float4* dr = reinterpret_cast<float4*>(dx + row * C);
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      float4 o;
+      o.x = rstd * (g[i].x - m1 - xh[i].x * m2);
+      o.y = rstd * (g[i].y - m1 - xh[i].y * m2);
+      o.z = rstd * (g[i].z - m1 - xh[i].z * m2);
+      o.w = rstd * (g[i].w - m1 - xh[i].w * m2);
+      dr[i * 32 + lane] = o;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    red[w][i][lane] = dg[i];
+    red[w][VPT + i][lane] = db[i];
+  }
+  __syncthreads();
+  // 2 * VPT * 32 float4 slots per CTA, summed over the 8 warps
+  for (int slot = threadIdx.x; slot < 2 * VPT * 32; slot += kRowThreads) {
+    const int i = slot >> 5, l = slot & 31;
+    float4 a = red[0][i][l];
+#pragma unroll
+    for (int ww = 1; ww < kRowWarps; ++ww) {
+      const float4 b = red[ww][i][l];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    // layout [block][2][C]: i < VPT -> dgamma chunk i, else dbeta chunk i - VPT
+    const int which = i / VPT, chunk = i % VPT;
+    reinterpret_cast<float4*>(partial + (static_cast<long long>(blockIdx.x) * 2 + which) * C)[chunk * 32 + l] = a;
+  }
+}
+
+// out[c] += sum over rows of x[row][c]   (out zeroed by the launcher); C % 4 == 0, C <= 4096.
+// blockDim = (C/4 rounded up to a multiple of 32 lanes... ) -- simple layout: thread t owns float4 column chunk
+// t % chunks and row phase t / chunks; partial sums meet in shared memory, one atomicAdd per column per CTA.
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ x, long long rows, int C, long long ld, float* __restrict__ out) {
+  extern __shared__ float4 sh[];
+  const int chunks = C >> 2;
+  const int rpb = 256 / chunks > 0 ? 256 / chunks : 1;          // row phases per CTA (chunks <= 256)
+  const int t = threadIdx.x;
+  const int cchunk = t % chunks, phase = t / chunks;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (phase < rpb) {
+    for (long long row = static_cast<long long>(blockIdx.x) * rpb + phase; row < rows;
+         row += static_cast<long long>(gridDim.x) * rpb) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + row * ld) + cchunk);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  sh[t] = acc;
+  __syncthreads();
+  if (t < chunks) {
+    float4 a = sh[t];
+    for (int p = 1; p < rpb; ++p) {
+      const float4 b = sh[p * chunks + t];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    atomicAdd(out + 4 * t + 0, a.x);
+    atomicAdd(out + 4 * t + 1, a.y);
+    atomicAdd(out + 4 * t + 2, a.z);
+    atomicAdd(out + 4 * t + 3, a.w);
+  }
+}
+
+static int row_grid(long long rows) {
+  long long blocks = (rows + kRowWarps - 1) / kRowWarps;
+  const long long cap = 148 * 8;                 // persistent: 8 CTAs of 256 threads per SM
+  return static_cast<int>(blocks < cap ? blocks : cap);
+}
+
+}  // namespace mpf
+
+extern "C" {
+
+int mpf_add_layernorm_partials(long long rows) { return mpf::row_grid(rows); }
+
+int mpf_add_layernorm_fwd_f32(const float* x, const float* r, const float* gamma, const float* beta, float eps,
+                              long long rows, int C, float* y, float* mean, float* rstd, void* stream) {
+  using namespace mpf;
+  clear_error();
+  MPF_REQUIRE(x && gamma && beta && y && mean && rstd, "add_layernorm_fwd: null pointer argument");
+  MPF_REQUIRE(rows > 0, "add_layernorm_fwd: rows must be positive");
+  MPF_REQUIRE(aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta) && (r == nullptr || aligned16(r)),
+              "add_layernorm_fwd: pointers must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = row_grid(rows);
+  switch (C) {
+    case 128: add_layernorm_fwd_kernel<1><<<grid, kRowThreads, 0, st>>>(x, r, gamma, beta, eps, rows, y, mean, rstd); break;
+    case 256: add_layernorm_fwd_kernel<2><<<grid, kRowThreads, 0, st>>>(x, r, gamma, beta, eps, rows, y, mean, rstd); break;
+    case 512: add_layernorm_fwd_kernel<4><<<grid, kRowThreads, 0, st>>>(x, r, gamma, beta, eps, rows, y, mean, rstd); break;
+    default:
+      set_error("add_layernorm_fwd: C = %d is not supported (128, 256, 512)", C);
+      return MPF_ERR_UNSUPPORTED;
+  }
+  count_launch();
+  return finish_launch("add_layernorm_fwd");
+}
+
+int mpf_add_layernorm_bwd_f32(const float* dy, const float* x, const float* r, const float* gamma, const float* mean,
+                              const float* rstd, long long rows, int C, float* dx, float* partial, void* stream) {
+  using namespace mpf;
+  clear_error();
+  MPF_REQUIRE(dy && x && gamma && mean && rstd && dx && partial, "add_layernorm_bwd: null pointer argument");
+  MPF_REQUIRE(rows > 0, "add_layernorm_bwd: rows must be positive");
+  MPF_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(dx) && aligned16(gamma) && aligned16(partial) &&
+                  (r == nullptr || aligned16(r)),
+              "add_layernorm_bwd: pointers must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = row_grid(rows);
+  switch (C) {
+    case 128: add_layernorm_bwd_kernel<1><<<grid, kRowThreads, 0, st>>>(dy, x, r, gamma, mean, rstd, rows, dx, partial); break;
+    case 256: add_layernorm_bwd_kernel<2><<<grid, kRowThreads, 0, st>>>(dy, x, r, gamma, mean, rstd, rows, dx, partial); break;
+    case 512: add_layernorm_bwd_kernel<4><<<grid, kRowThreads, 0, st>>>(dy, x, r, gamma, mean, rstd, rows, dx, partial); break;
+    default:
+      set_error("add_layernorm_bwd: C = %d is not supported (128, 256, 512)", C);
+      return MPF_ERR_UNSUPPORTED;
+  }
+  count_launch();
+  return finish_launch("add_layernorm_bwd");
+}
+
+int mpf_colsum_f32(const float* x, long long rows, int C, long long ld, float* out, void* stream) {
+  using namespace mpf;
+  clear_error();
+  MPF_REQUIRE(x && out && rows > 0 && C > 0, "colsum: bad arguments");
+  MPF_REQUIRE(C % 4 == 0 && C <= 1024 && ld % 4 == 0 && ld >= C && aligned16(x),
+              "colsum: C must be a multiple of 4 (<= 1024), ld a multiple of 4, x 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MPF_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * C, st));
+  const int chunks = C / 4;
+  const int rpb = 256 / chunks > 0 ? 256 / chunks : 1;
+  long long blocks = (rows + rpb - 1) / rpb;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  colsum_kernel<<<static_cast<int>(blocks), 256, 256 * sizeof(float4), st>>>(x, rows, C, ld, out);
+  count_launch();
+  return finish_launch("colsum");
+}
+
+}  // extern "C"

@@ -62,7 +62,7 @@ class SelfAttentionLayer(_AttnParams):
         a = self.self_attn
         out = ops.self_attention(qk, tgt, a.in_proj_weight, a.in_proj_bias, a.out_proj.weight,
                                  a.out_proj.bias, self.nhead, tgt_mask)
-        return self.norm(tgt + out)
+        return ops.add_layer_norm(tgt, out, self.norm)
 
 
 class CrossAttentionLayer(_AttnParams):
@@ -81,7 +81,7 @@ class CrossAttentionLayer(_AttnParams):
         a = self.multihead_attn
         out = ops.masked_cross_attention(q_in, memory, pos, a.in_proj_weight, a.in_proj_bias,
                                          a.out_proj.weight, a.out_proj.bias, self.nhead, memory_mask)
-        return self.norm(tgt + out)
+        return ops.add_layer_norm(tgt, out, self.norm)
 
 
 class FFNLayer(nn.Module):
@@ -106,7 +106,7 @@ class FFNLayer(nn.Module):
         else:
             hidden = ops.linear(tgt, self.linear1.weight, self.linear1.bias, relu=True)
             tgt2 = ops.linear(self.dropout(hidden), self.linear2.weight, self.linear2.bias)
-        return self.norm(tgt + self.dropout(tgt2))
+        return ops.add_layer_norm(tgt, self.dropout(tgt2), self.norm)
 
 
 class MLP(nn.Module):
@@ -210,7 +210,7 @@ class _MaskedDecoderBase(nn.Module):
         """output [B,Q,C] -> (outputs_class [B,Q,K+1], outputs_mask [B,Q,H,W],
         attn_mask: ops.PackedMask, one bit per (image, query, key), shared by heads).
         ref decoder :1859-1877."""
-        decoder_output = self.decoder_norm(output)
+        decoder_output = ops.add_layer_norm(output, None, self.decoder_norm)
         outputs_class = ops.linear(decoder_output, self.class_embed.weight, self.class_embed.bias)
         mask_embed = self.mask_embed(decoder_output)
         outputs_mask = ops.mask_logits(mask_embed, mask_features)

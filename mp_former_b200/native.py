@@ -198,6 +198,69 @@ def gemm(a, b_hi, b_lo, bias=None, relu=False, transpose_c=False, split_out=Fals
     return (out, out_lo) if split_out else out
 
 
+def add_layernorm_fwd(x, r, gamma, beta, eps):
+    """y = LayerNorm(x + r) (r may be None) over the last dimension; returns (y, mean, rstd)."""
+    x = _f32c(x, "x")
+    C = x.shape[-1]
+    x2 = x.reshape(-1, C)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    r2 = None
+    if r is not None:
+        r2 = _f32c(r, "r").reshape(-1, C)
+        if not r2.is_contiguous():
+            r2 = r2.contiguous()
+    rows = x2.shape[0]
+    y = torch.empty_like(x2)
+    mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().mpf_add_layernorm_fwd_f32(x2.data_ptr(), None if r2 is None else r2.data_ptr(),
+                                                   gamma.contiguous().data_ptr(), beta.contiguous().data_ptr(),
+                                                   float(eps), rows, C, y.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                                   _stream())
+    _lib.check(rc, "add_layernorm_fwd")
+    return y.view(x.shape), mean, rstd
+
+
+def add_layernorm_bwd(dy, x, r, gamma, mean, rstd):
+    """-> (dx, dgamma, dbeta); dx is the gradient of both x and r."""
+    C = x.shape[-1]
+    dy2 = _f32c(dy, "dy").reshape(-1, C)
+    if not dy2.is_contiguous():
+        dy2 = dy2.contiguous()
+    x2 = x.reshape(-1, C)
+    r2 = None if r is None else r.reshape(-1, C)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    if r2 is not None and not r2.is_contiguous():
+        r2 = r2.contiguous()
+    rows = x2.shape[0]
+    lib = _lib.load()
+    dx = torch.empty_like(x2)
+    partial = torch.empty((lib.mpf_add_layernorm_partials(rows), 2, C), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.mpf_add_layernorm_bwd_f32(dy2.data_ptr(), x2.data_ptr(), None if r2 is None else r2.data_ptr(),
+                                           gamma.contiguous().data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, C,
+                                           dx.data_ptr(), partial.data_ptr(), _stream())
+    _lib.check(rc, "add_layernorm_bwd")
+    dgb = partial.sum(0)
+    return dx.view(x.shape), dgb[0], dgb[1]
+
+
+def colsum(x2):
+    """Column sums of a [rows, C] fp32 matrix (row stride a multiple of 4): the bias gradient of a Linear layer."""
+    x2 = _f32c(x2, "x")
+    rows, C = x2.shape
+    if x2.stride(1) != 1 or x2.stride(0) % 4 or C % 4 or C > 1024 or rows < 2048:
+        return x2.sum(0)
+    out = torch.empty(C, dtype=torch.float32, device=x2.device)
+    with torch.cuda.device(x2.device):
+        rc = _lib.load().mpf_colsum_f32(x2.data_ptr(), rows, C, x2.stride(0), out.data_ptr(), _stream())
+    _lib.check(rc, "colsum")
+    return out
+
+
 def mask_words(n_keys):
     """uint32 words per mask row: whole 64-key tiles (the attention kernel reads two words per tile)."""
     return 2 * ((n_keys + 63) // 64)

@@ -67,7 +67,7 @@ class _Linear(torch.autograd.Function):
             else:
                 gw = g2.t() @ x2
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = g2.sum(0)
+            gb = native.colsum(g2)
         return gx, gw, gb, None
 
 
@@ -80,6 +80,31 @@ def linear(x, weight, bias=None, relu=False):
         y = F.linear(x, weight, bias)
         return F.relu(y) if relu else y
     return _Linear.apply(x, weight, bias, relu)
+
+
+class _AddLayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, r, weight, bias, eps):
+        y, mean, rstd = native.add_layernorm_fwd(x, r, weight, bias, eps)
+        ctx.save_for_backward(x, r, weight, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, r, weight, mean, rstd = ctx.saved_tensors
+        dx, dgamma, dbeta = native.add_layernorm_bwd(gy, x, r, weight, mean, rstd)
+        return dx, (dx if r is not None else None), dgamma, dbeta, None
+
+
+def add_layer_norm(x, r, norm):
+    """``norm(x + r)`` for an nn.LayerNorm over the last dimension (``r`` may be None) as ONE kernel forward and one
+    backward: the sum is never materialised (ref pixel_decoder/msdeformattn.py:125-126,129; decoder :52,:112,:169)."""
+    _cuda_only(x, "x")
+    C = x.shape[-1]
+    if C not in (128, 256, 512) or x.dtype != torch.float32 or tuple(norm.normalized_shape) != (C,) \
+            or norm.weight is None or norm.bias is None:
+        return norm(x if r is None else x + r)
+    return _AddLayerNorm.apply(x, r, norm.weight, norm.bias, norm.eps)
 
 
 class _FFN(torch.autograd.Function):
@@ -103,11 +128,11 @@ class _FFN(torch.autograd.Function):
         w2t_hi, w2t_lo = native.split_b(w2.t().contiguous())
         gh = native.gemm_general(g2, w2t_hi, b_lo=w2t_lo, gate=hidden)       # d(hidden) with the ReLU mask applied
         gw2 = native.matmul_tn(g2, hidden)
-        gb2 = g2.sum(0)
+        gb2 = native.colsum(g2)
         w1t_hi, w1t_lo = native.split_b(w1.t().contiguous())
         gx = native.gemm(gh, w1t_hi, w1t_lo).view(*gy.shape[:-1], w1.shape[1]) if ctx.needs_input_grad[0] else None
         gw1 = native.matmul_tn(gh, x2)
-        gb1 = gh.sum(0)
+        gb1 = native.colsum(gh)
         return gx, gw1, gb1, gw2, gb2
 
 
@@ -157,8 +182,12 @@ class _MaskLogits(torch.autograd.Function):
                 else torch.bmm(g2, tokens)
         if ctx.needs_input_grad[1]:
             # dF[b] = dOut[b]^T (HW x Q) @ E[b] (Q x C): both operands MN-major
-            gf = native.gemm_general(g2, mask_embed, a_mn=True, b_mn=True) if ok \
-                else torch.bmm(g2.transpose(1, 2), mask_embed)
+            if ok and native.GEMM_MODE == "bf16x3":
+                gf = native.gemm_tn(g2, mask_embed)              # reduction over the Q queries, both operands as stored
+            elif ok:
+                gf = native.gemm_general(g2, mask_embed, a_mn=True, b_mn=True)
+            else:
+                gf = torch.bmm(g2.transpose(1, 2), mask_embed)
             gf = gf.view(B, H, W, C).permute(0, 3, 1, 2)
         return ge, gf
 
@@ -297,7 +326,7 @@ class _MaskedCrossAttention(torch.autograd.Function):
         # in-projection weight gradients: dW = dY^T X on the tensor cores (keys see memory + pos)
         g_wk = native.matmul_tn(dk2, mem2) + native.matmul_tn(dk.sum(0), pos2)
         g_win = torch.cat([native.matmul_tn(dq2, q_in.reshape(B * Qt, E)), g_wk, native.matmul_tn(dv2, mem2)], 0)
-        g_bin = torch.cat([dq2.sum(0), dk2.sum(0), dv2.sum(0)], 0)
+        g_bin = torch.cat([dq2.sum(0), native.colsum(dk2), native.colsum(dv2)], 0)
         g_qin = (dq2 @ wq).view(B, Qt, E) if ctx.needs_input_grad[0] else None
         g_mem = g_pos = None
         if ctx.needs_input_grad[1]:

@@ -125,12 +125,12 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
         else:
             hidden = ops.linear(src, self.linear1.weight, self.linear1.bias, relu=True)
             src2 = ops.linear(self.dropout2(hidden), self.linear2.weight, self.linear2.bias)
-        return self.norm2(src + self.dropout3(src2))
+        return ops.add_layer_norm(src, self.dropout3(src2), self.norm2)
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None):
         src2 = self.self_attn(self.with_pos_embed(src, pos), reference_points, src, spatial_shapes,
                               level_start_index, padding_mask)
-        src = self.norm1(src + self.dropout1(src2))
+        src = ops.add_layer_norm(src, self.dropout1(src2), self.norm1)
         return self.forward_ffn(src)
 
 

@@ -178,3 +178,42 @@ def test_gt_mask_area_bits_equal_area_interpolate_rule(H, W, h, w, n):
     ref = F.interpolate(masks.float().unsqueeze(1), size=(h, w), mode="area").flatten(1) <= 1e-8
     assert torch.equal(native.unpack_bits(bits, h * w), ref)
     assert torch.equal(bits, native.pack_bool_bits(ref))         # padding bits agree with the packer
+
+
+@pytest.mark.parametrize("shape,with_r", [((16, 2150, 256), True), ((3, 120, 256), True), ((5, 7, 256), False),
+                                          ((1000, 128), True), ((33, 512), True)])
+def test_add_layer_norm_forward_backward(shape, with_r):
+    """Fused residual + LayerNorm (ref msdeformattn.py:125-126, decoder :52,:112,:169) vs torch in fp64."""
+    C = shape[-1]
+    g = torch.Generator(device=DEV).manual_seed(sum(shape))
+    x = (torch.randn(*shape, device=DEV, generator=g) * 2 + 0.3).requires_grad_(True)
+    r = torch.randn(*shape, device=DEV, generator=g).requires_grad_(True) if with_r else None
+    norm = torch.nn.LayerNorm(C).to(DEV)
+    with torch.no_grad():
+        norm.weight.copy_(torch.randn(C, device=DEV, generator=g))
+        norm.bias.copy_(torch.randn(C, device=DEV, generator=g))
+    y = ops.add_layer_norm(x, r, norm)
+    gy = torch.randn(*shape, device=DEV, generator=g)
+    y.backward(gy)
+    xr = x.detach().double().requires_grad_(True)
+    rr = r.detach().double().requires_grad_(True) if with_r else None
+    wr, br = norm.weight.detach().double().requires_grad_(True), norm.bias.detach().double().requires_grad_(True)
+    yr = F.layer_norm(xr + rr if with_r else xr, (C,), wr, br, norm.eps)
+    yr.backward(gy.double())
+    assert rel(y, yr) < 1e-5
+    assert rel(x.grad, xr.grad) < 1e-5
+    if with_r:
+        assert torch.equal(r.grad, x.grad)
+    for a, b in ((norm.weight.grad, wr.grad), (norm.bias.grad, br.grad)):
+        assert (a.double() - b).abs().max().item() / max(1.0, b.abs().max().item()) < 1e-5
+
+
+@pytest.mark.parametrize("rows,C,ld", [(344064, 256, 256), (5000, 1024, 1024), (4096, 288, 288), (3000, 100, 256),
+                                       (100, 64, 64)])
+def test_colsum(rows, C, ld):
+    g = torch.Generator(device=DEV).manual_seed(rows + C)
+    big = torch.randn(rows, ld, device=DEV, generator=g)
+    x = big[:, :C]
+    out = native.colsum(x)
+    ref = x.double().sum(0)
+    assert (out.double() - ref).abs().max().item() < 1e-4 * max(1.0, rows ** 0.5)

@@ -49,4 +49,4 @@ def test_graphed_step_matches_eager_step():
             if r is None:
                 continue
             scale = max(1e-6, r.abs().max().item())
-            assert (p.grad - r).abs().max().item() / scale < 1e-4
+            assert (p.grad - r).abs().max().item() / scale < 5e-4      # fp32 atomics: summation order differs run to run
