@@ -49,7 +49,7 @@ def emit(name, ms, bytes_=None, mma_flops=None, **kw):
 def main():
     g = torch.Generator(device=DEV).manual_seed(0)
     rn = lambda *s: torch.randn(*s, device=DEV, generator=g)
-    which = os.environ.get("MPF_PROBE", "msda,gemm,masklogits,maskbits,xattn").split(",")
+    which = os.environ.get("MPF_PROBE", "msda,gemm,masklogits,layernorm,maskbits,xattn").split(",")
     S, M, D, L, P = 21504, 8, 32, 3, 4
     shapes = [(32, 32), (64, 64), (128, 128)]
     if "msda" in which:
@@ -81,34 +81,45 @@ def main():
         for (m, n, k, tag) in ((B * S, 1024, 256, "ffn.linear1"), (B * S, 256, 1024, "ffn.linear2"),
                                (B * S, 256, 256, "value_proj"), (B * S, 288, 256, "offsets+weights")):
             a, w, bias = rn(m, k), rn(n, k) / 16, rn(n)
-            wh, wl = native.split_tf32(w)
+            wh, wl = native.split_b(w)
             ms = timeit(lambda: native.gemm(a, wh, wl, bias))
-            emit(f"gemm_tf32x3 {tag} M={m} N={n} K={k}", ms, 4 * (m * k + m * n + 2 * n * k), 3 * 2.0 * m * n * k,
+            emit(f"gemm_{native.GEMM_MODE} {tag} M={m} N={n} K={k}", ms, 4 * (m * k + m * n) + 4 * n * k, 3 * 2.0 * m * n * k,
                  fp32_equiv_TFLOPs=2.0 * m * n * k / ms / 1e9)
             del a
         # epilogue variants at the FFN-backward / residual shapes
         m = B * S
         a, w, hid = rn(m, 256), rn(1024, 256) / 16, rn(m, 1024)
-        wh, wl = native.split_tf32(w)
+        wh, wl = native.split_b(w)
         ms = timeit(lambda: native.gemm_general(a, wh, b_lo=wl, gate=hid))
-        emit(f"gemm_tf32x3 ffn.d_hidden (gated) M={m} N=1024 K=256", ms, 4 * (m * 256 + 2 * m * 1024 + 2 * 1024 * 256),
+        emit(f"gemm_{native.GEMM_MODE} ffn.d_hidden (gated) M={m} N=1024 K=256", ms, 4 * (m * 256 + 2 * m * 1024 + 2 * 1024 * 256),
              3 * 2.0 * m * 1024 * 256)
         w2 = rn(256, 1024) / 32
-        w2h, w2l = native.split_tf32(w2)
+        w2h, w2l = native.split_b(w2)
         ms = timeit(lambda: native.gemm(hid, w2h, w2l))
-        emit(f"gemm_tf32x3 ffn.d_x M={m} N=256 K=1024", ms, 4 * (m * 1024 + m * 256 + 2 * 1024 * 256), 3 * 2.0 * m * 1024 * 256)
+        emit(f"gemm_{native.GEMM_MODE} ffn.d_x M={m} N=256 K=1024", ms, 4 * (m * 1024 + m * 256 + 2 * 1024 * 256), 3 * 2.0 * m * 1024 * 256)
         ms = timeit(lambda: native.matmul_tn(hid, a))
-        emit(f"gemm_tf32x3 ffn.d_w1 (MN-major, split-K) [1024 x 256] over M={m}", ms, 4 * (m * 1024 + m * 256),
+        emit(f"gemm_{native.GEMM_MODE}_tn ffn.d_w1 (token reduction, split-K) [1024 x 256] over M={m}", ms, 4 * (m * 1024 + m * 256),
              3 * 2.0 * m * 1024 * 256)
         del a, hid
     if "masklogits" in which:
         Q, C, HW = 120, 256, 65536
         e, f = rn(B, Q, C), rn(B, HW, C)
-        eh, el = native.split_tf32(e)
+        eh, el = native.split_b(e)
         ms = timeit(lambda: native.gemm(f, eh, el, transpose_c=True))
-        emit(f"gemm_tf32x3 mask_logits B={B} Q={Q} HW={HW}", ms, 4 * B * (HW * C + Q * HW + 2 * Q * C), 3 * 2.0 * B * Q * C * HW,
+        emit(f"gemm_{native.GEMM_MODE} mask_logits B={B} Q={Q} HW={HW}", ms, 4 * B * (HW * C + Q * HW + 2 * Q * C), 3 * 2.0 * B * Q * C * HW,
              fp32_equiv_TFLOPs=2.0 * B * Q * C * HW / ms / 1e9)
         del f
+    if "layernorm" in which:
+        x, r, gy = rn(B * S, 256), rn(B * S, 256), rn(B * S, 256)
+        gm, bt = rn(256), rn(256)
+        ms = timeit(lambda: native.add_layernorm_fwd(x, r, gm, bt, 1e-5))
+        emit("add_layernorm_fwd [344064 x 256]", ms, 4 * 3 * B * S * 256)
+        _, mean, rstd = native.add_layernorm_fwd(x, r, gm, bt, 1e-5)
+        ms = timeit(lambda: native.add_layernorm_bwd(gy, x, r, gm, mean, rstd))
+        emit("add_layernorm_bwd [344064 x 256]", ms, 4 * 4 * B * S * 256)
+        ms = timeit(lambda: native.colsum(gy))
+        emit("colsum [344064 x 256]", ms, 4 * B * S * 256)
+        del x, r, gy
     if "maskbits" in which:
         logits = rn(B, 120, 256, 256)
         for hw in (32, 64, 128):

@@ -219,6 +219,17 @@ int mpf_add_layernorm_fwd_f32(const float* x, const float* r, const float* gamma
 int mpf_add_layernorm_bwd_f32(const float* dy, const float* x, const float* r, const float* gamma, const float* mean,
                               const float* rstd, long long rows, int C, float* dx, float* partial, void* stream);
 int mpf_colsum_f32(const float* x, long long rows, int C, long long ld, float* out, void* stream);
+/* GroupNorm over channels-last maps x [batch, HW, C] (groups of C/groups consecutive channels, 4..32 channels per
+ * group), optionally fused with the ReLU that follows it.  ref: pixel_decoder/msdeformattn.py:216-219 (input
+ * projections), :262-275 (lateral / output convs, norm "GN").  stats_ws: 2*batch*groups doubles of scratch (zeroed
+ * here).  Forward also writes mean / rstd [batch, groups] for the backward; the backward returns dx and
+ * dgamma_dbeta [2, C] (zeroed here, accumulated with fp32 atomics); with relu != 0 the gate is recomputed from x. */
+int mpf_groupnorm_cl_fwd_f32(const float* x, const float* gamma, const float* beta, float eps, int batch,
+                             long long HW, int C, int groups, int relu, float* y, float* mean, float* rstd,
+                             double* stats_ws, void* stream);
+int mpf_groupnorm_cl_bwd_f32(const float* dy, const float* x, const float* gamma, const float* beta,
+                             const float* mean, const float* rstd, int batch, long long HW, int C, int groups,
+                             int relu, float* dx, float* dgamma_dbeta, double* stats_ws, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Boolean stage of the prediction heads, bit-packed:

@@ -52,6 +52,8 @@ SIGNATURES = {
     "mpf_add_layernorm_fwd_f32": (_c_int, [_c_vp] * 4 + [ctypes.c_float, _c_ll, _c_int] + [_c_vp] * 4),
     "mpf_add_layernorm_bwd_f32": (_c_int, [_c_vp] * 6 + [_c_ll, _c_int] + [_c_vp] * 3),
     "mpf_colsum_f32": (_c_int, [_c_vp, _c_ll, _c_int, _c_ll, _c_vp, _c_vp]),
+    "mpf_groupnorm_cl_fwd_f32": (_c_int, [_c_vp] * 3 + [ctypes.c_float, _c_int, _c_ll, _c_int, _c_int, _c_int] + [_c_vp] * 5),
+    "mpf_groupnorm_cl_bwd_f32": (_c_int, [_c_vp] * 6 + [_c_int, _c_ll, _c_int, _c_int, _c_int] + [_c_vp] * 4),
     "mpf_attn_mask_bits_f32": (_c_int, [_c_vp, _c_ll] + [_c_int] * 5 + [_c_vp, _c_int, _c_vp]),
     "mpf_pack_bool_bits": (_c_int, [_c_vp, _c_int, _c_int, _c_vp, _c_int, _c_vp]),
     "mpf_gt_mask_area_bits": (_c_int, [_c_vp] + [_c_int] * 5 + [_c_vp, _c_int, _c_vp]),

@@ -256,3 +256,257 @@ int mpf_colsum_f32(const float* x, long long rows, int C, long long ld, float* o
 }
 
 }  // extern "C"
+
+namespace mpf {
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm over channels-last maps (x [B, HW, C], groups of C/G consecutive channels; the pixel decoder uses
+// G = 32, C = 256), optionally fused with the ReLU that follows it (ref pixel_decoder/msdeformattn.py:216-219 input
+// projections, :262-275 lateral / output convs with norm "GN").  PyTorch's kernel runs 1.7 ms per [16,256,256,256]
+// map; here: one statistics pass (fp32 partial sums per thread, combined in
+// fp64 atomics so E[x^2] - E[x]^2 does not cancel) and one normalise pass, 16-byte coalesced accesses.
+//   stats[b][g] = (sum, sum of squares) as doubles, zeroed by the launcher.
+// ------------------------------------------------------------------------------------------------
+constexpr int kGnThreads = 256;
+
+// thread t: channel quad q = t % (C/4), row phase t / (C/4); rows [row0, row1) of image b = blockIdx.y
+__global__ void __launch_bounds__(kGnThreads)
+groupnorm_stats_kernel(const float* __restrict__ x, long long HW, int C, int cpg, int rows_per_cta,
+                       double* __restrict__ stats) {
+  const int quads = C >> 2;
+  const int rpb = kGnThreads / quads;
+  const int q = threadIdx.x % quads, phase = threadIdx.x / quads;
+  const int b = blockIdx.y;
+  const long long row0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
+  long long row1 = row0 + rows_per_cta;
+  if (row1 > HW) row1 = HW;
+  float s1 = 0.f, s2 = 0.f;
+  if (phase < rpb) {
+    const float* xb = x + (static_cast<long long>(b) * HW) * C + 4 * q;
+    for (long long r = row0 + phase; r < row1; r += rpb) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(xb + r * C));
+      s1 += (v.x + v.y) + (v.z + v.w);
+      s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    }
+  }
+  // combine the quads of one group inside the warp when a group spans several lanes (cpg = 8 -> 2 lanes)
+  const int lanes_per_group = cpg >> 2;          // cpg is a multiple of 4
+  for (int o = 1; o < lanes_per_group; o <<= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if (phase < rpb && (q % lanes_per_group) == 0) {
+    const int g = (4 * q) / cpg;
+    double* st = stats + (static_cast<long long>(b) * (C / cpg) + g) * 2;
+    atomicAdd(st, static_cast<double>(s1));
+    atomicAdd(st + 1, static_cast<double>(s2));
+  }
+}
+
+__global__ void __launch_bounds__(kGnThreads)
+groupnorm_apply_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                       const double* __restrict__ stats, long long HW, int C, int cpg, float eps, int relu,
+                       float* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int quads = C >> 2;
+  const int b = blockIdx.y;
+  const long long total = HW * quads;
+  const int G = C / cpg;
+  const double inv_n = 1.0 / (static_cast<double>(HW) * cpg);
+  for (long long i = static_cast<long long>(blockIdx.x) * kGnThreads + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * kGnThreads) {
+    const int q = static_cast<int>(i % quads);
+    const int g = (4 * q) / cpg;
+    const double* st = stats + (static_cast<long long>(b) * G + g) * 2;
+    const double m = st[0] * inv_n;
+    double var = st[1] * inv_n - m * m;
+    if (var < 0.0) var = 0.0;
+    const float mean = static_cast<float>(m);
+    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    if (i < quads && (q % (cpg >> 2)) == 0) {        // first row of the image: publish the statistics once
+      mean_out[b * G + g] = mean;
+      rstd_out[b * G + g] = rstd;
+    }
+    const long long off = (static_cast<long long>(b) * HW) * C + i * 4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + off));
+    const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + q);
+    const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + q);
+    float4 o;
+    o.x = (v.x - mean) * rstd * gm.x + bt.x;
+    o.y = (v.y - mean) * rstd * gm.y + bt.y;
+    o.z = (v.z - mean) * rstd * gm.z + bt.z;
+    o.w = (v.w - mean) * rstd * gm.w + bt.w;
+    if (relu) {
+      o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+    }
+    *reinterpret_cast<float4*>(y + off) = o;
+  }
+}
+
+// backward pass 1: per (b, g) sums of g = gamma*dy' and g*xhat (doubles), per channel sums of dy'*xhat and dy'
+// (floats, [2][C]); dy' = dy masked by the fused ReLU (y > 0 recomputed from x).
+__global__ void __launch_bounds__(kGnThreads)
+groupnorm_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+                           const float* __restrict__ beta, const float* __restrict__ mean_in,
+                           const float* __restrict__ rstd_in, long long HW, int C, int cpg, int relu,
+                           int rows_per_cta, double* __restrict__ gstats, float* __restrict__ dgb) {
+  const int quads = C >> 2;
+  const int rpb = kGnThreads / quads;
+  const int q = threadIdx.x % quads, phase = threadIdx.x / quads;
+  const int b = blockIdx.y;
+  const int G = C / cpg;
+  const long long row0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
+  long long row1 = row0 + rows_per_cta;
+  if (row1 > HW) row1 = HW;
+  float s1 = 0.f, s2 = 0.f;
+  float4 dg = make_float4(0.f, 0.f, 0.f, 0.f), db = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (phase < rpb) {
+    const int g = (4 * q) / cpg;
+    const float mean = __ldg(mean_in + b * G + g), rstd = __ldg(rstd_in + b * G + g);
+    const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + q);
+    const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + q);
+    const long long base = (static_cast<long long>(b) * HW) * C + 4 * q;
+    for (long long r = row0 + phase; r < row1; r += rpb) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + base + r * C));
+      float4 d = __ldg(reinterpret_cast<const float4*>(dy + base + r * C));
+      const float4 xh = make_float4((v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd);
+      if (relu) {
+        if (!(xh.x * gm.x + bt.x > 0.f)) d.x = 0.f;
+        if (!(xh.y * gm.y + bt.y > 0.f)) d.y = 0.f;
+        if (!(xh.z * gm.z + bt.z > 0.f)) d.z = 0.f;
+        if (!(xh.w * gm.w + bt.w > 0.f)) d.w = 0.f;
+      }
+      const float4 gg = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+      s1 += (gg.x + gg.y) + (gg.z + gg.w);
+      s2 += (gg.x * xh.x + gg.y * xh.y) + (gg.z * xh.z + gg.w * xh.w);
+      dg.x += d.x * xh.x; dg.y += d.y * xh.y; dg.z += d.z * xh.z; dg.w += d.w * xh.w;
+      db.x += d.x; db.y += d.y; db.z += d.z; db.w += d.w;
+    }
+  }
+  const int lanes_per_group = cpg >> 2;
+  for (int o = 1; o < lanes_per_group; o <<= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if (phase < rpb) {
+    if ((q % lanes_per_group) == 0) {
+      const int g = (4 * q) / cpg;
+      double* st = gstats + (static_cast<long long>(b) * G + g) * 2;
+      atomicAdd(st, static_cast<double>(s1));
+      atomicAdd(st + 1, static_cast<double>(s2));
+    }
+    float* pg = dgb + 4 * q;
+    atomicAdd(pg + 0, dg.x); atomicAdd(pg + 1, dg.y); atomicAdd(pg + 2, dg.z); atomicAdd(pg + 3, dg.w);
+    float* pb = dgb + C + 4 * q;
+    atomicAdd(pb + 0, db.x); atomicAdd(pb + 1, db.y); atomicAdd(pb + 2, db.z); atomicAdd(pb + 3, db.w);
+  }
+}
+
+// backward pass 2: dx = rstd * (g - mean_grp(g) - xhat * mean_grp(g * xhat))
+__global__ void __launch_bounds__(kGnThreads)
+groupnorm_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+                           const float* __restrict__ beta, const float* __restrict__ mean_in,
+                           const float* __restrict__ rstd_in, const double* __restrict__ gstats, long long HW, int C,
+                           int cpg, int relu, float* __restrict__ dx) {
+  const int quads = C >> 2;
+  const int b = blockIdx.y;
+  const int G = C / cpg;
+  const long long total = HW * quads;
+  const double inv_n = 1.0 / (static_cast<double>(HW) * cpg);
+  for (long long i = static_cast<long long>(blockIdx.x) * kGnThreads + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * kGnThreads) {
+    const int q = static_cast<int>(i % quads);
+    const int g = (4 * q) / cpg;
+    const float mean = __ldg(mean_in + b * G + g), rstd = __ldg(rstd_in + b * G + g);
+    const double* st = gstats + (static_cast<long long>(b) * G + g) * 2;
+    const float m1 = static_cast<float>(st[0] * inv_n), m2 = static_cast<float>(st[1] * inv_n);
+    const long long off = (static_cast<long long>(b) * HW) * C + i * 4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + off));
+    float4 d = __ldg(reinterpret_cast<const float4*>(dy + off));
+    const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + q);
+    const float4 xh = make_float4((v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd);
+    if (relu) {
+      const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + q);
+      if (!(xh.x * gm.x + bt.x > 0.f)) d.x = 0.f;
+      if (!(xh.y * gm.y + bt.y > 0.f)) d.y = 0.f;
+      if (!(xh.z * gm.z + bt.z > 0.f)) d.z = 0.f;
+      if (!(xh.w * gm.w + bt.w > 0.f)) d.w = 0.f;
+    }
+    float4 o;
+    o.x = rstd * (d.x * gm.x - m1 - xh.x * m2);
+    o.y = rstd * (d.y * gm.y - m1 - xh.y * m2);
+    o.z = rstd * (d.z * gm.z - m1 - xh.z * m2);
+    o.w = rstd * (d.w * gm.w - m1 - xh.w * m2);
+    *reinterpret_cast<float4*>(dx + off) = o;
+  }
+}
+
+static bool gn_shape_ok(int C, int G) {
+  if (G <= 0 || C % G) return false;
+  const int cpg = C / G;
+  // a group is 4, 8, 16 or 32 channels (1..8 lanes of one warp), C/4 threads per row divide the CTA
+  return C % 4 == 0 && (cpg == 4 || cpg == 8 || cpg == 16 || cpg == 32) && (C >> 2) <= kGnThreads &&
+         32 % (cpg >> 2) == 0 && (C >> 2) % (cpg >> 2) == 0;
+}
+
+}  // namespace mpf
+
+extern "C" {
+
+int mpf_groupnorm_cl_fwd_f32(const float* x, const float* gamma, const float* beta, float eps, int batch,
+                             long long HW, int C, int groups, int relu, float* y, float* mean, float* rstd,
+                             double* stats_ws, void* stream) {
+  using namespace mpf;
+  clear_error();
+  MPF_REQUIRE(x && gamma && beta && y && mean && rstd && stats_ws, "groupnorm_fwd: null pointer argument");
+  MPF_REQUIRE(batch > 0 && HW > 0 && gn_shape_ok(C, groups), "groupnorm_fwd: unsupported shape (C=%d, groups=%d)", C, groups);
+  MPF_REQUIRE(aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta), "groupnorm_fwd: 16-byte alignment");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int cpg = C / groups;
+  MPF_CUDA_OK(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * batch * groups, st));
+  int ctas_x = static_cast<int>((148ll * 8 + batch - 1) / batch);
+  long long rows_per_cta = (HW + ctas_x - 1) / ctas_x;
+  if (rows_per_cta < 64) rows_per_cta = 64;
+  ctas_x = static_cast<int>((HW + rows_per_cta - 1) / rows_per_cta);
+  groupnorm_stats_kernel<<<dim3(ctas_x, batch), kGnThreads, 0, st>>>(x, HW, C, cpg, static_cast<int>(rows_per_cta),
+                                                                     stats_ws);
+  long long total = HW * (C / 4);
+  int ax = static_cast<int>((total + kGnThreads - 1) / kGnThreads);
+  const int cap = (148 * 8 + batch - 1) / batch;
+  if (ax > cap) ax = cap;
+  groupnorm_apply_kernel<<<dim3(ax, batch), kGnThreads, 0, st>>>(x, gamma, beta, stats_ws, HW, C, cpg, eps, relu, y,
+                                                                 mean, rstd);
+  count_launch(2);
+  return finish_launch("groupnorm_fwd");
+}
+
+int mpf_groupnorm_cl_bwd_f32(const float* dy, const float* x, const float* gamma, const float* beta,
+                             const float* mean, const float* rstd, int batch, long long HW, int C, int groups,
+                             int relu, float* dx, float* dgamma_dbeta, double* stats_ws, void* stream) {
+  using namespace mpf;
+  clear_error();
+  MPF_REQUIRE(dy && x && gamma && beta && mean && rstd && dx && dgamma_dbeta && stats_ws,
+              "groupnorm_bwd: null pointer argument");
+  MPF_REQUIRE(batch > 0 && HW > 0 && gn_shape_ok(C, groups), "groupnorm_bwd: unsupported shape (C=%d, groups=%d)", C, groups);
+  MPF_REQUIRE(aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(gamma) && aligned16(beta),
+              "groupnorm_bwd: 16-byte alignment");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int cpg = C / groups;
+  MPF_CUDA_OK(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * batch * groups, st));
+  MPF_CUDA_OK(cudaMemsetAsync(dgamma_dbeta, 0, sizeof(float) * 2 * C, st));
+  int ctas_x = static_cast<int>((148ll * 8 + batch - 1) / batch);
+  long long rows_per_cta = (HW + ctas_x - 1) / ctas_x;
+  if (rows_per_cta < 64) rows_per_cta = 64;
+  ctas_x = static_cast<int>((HW + rows_per_cta - 1) / rows_per_cta);
+  groupnorm_bwd_stats_kernel<<<dim3(ctas_x, batch), kGnThreads, 0, st>>>(
+      dy, x, gamma, beta, mean, rstd, HW, C, cpg, relu, static_cast<int>(rows_per_cta), stats_ws, dgamma_dbeta);
+  long long total = HW * (C / 4);
+  int ax = static_cast<int>((total + kGnThreads - 1) / kGnThreads);
+  const int cap = (148 * 8 + batch - 1) / batch;
+  if (ax > cap) ax = cap;
+  groupnorm_bwd_apply_kernel<<<dim3(ax, batch), kGnThreads, 0, st>>>(dy, x, gamma, beta, mean, rstd, stats_ws, HW, C,
+                                                                     cpg, relu, dx);
+  count_launch(2);
+  return finish_launch("groupnorm_bwd");
+}
+
+}  // extern "C"

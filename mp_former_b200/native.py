@@ -248,6 +248,42 @@ def add_layernorm_bwd(dy, x, r, gamma, mean, rstd):
     return dx.view(x.shape), dgb[0], dgb[1]
 
 
+def groupnorm_cl_ok(C, groups):
+    cpg = C // groups if groups > 0 and C % groups == 0 else 0
+    return cpg in (4, 8, 16, 32) and C % 4 == 0 and C // 4 <= 256
+
+
+def groupnorm_cl_fwd(x, gamma, beta, eps, groups, relu):
+    """x [B, HW, C] contiguous (channels-last tokens) -> (y, mean [B,G], rstd [B,G])."""
+    x = _f32c(x, "x")
+    B, HW, C = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty((B, groups), dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    ws = torch.empty((B, groups, 2), dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().mpf_groupnorm_cl_fwd_f32(x.data_ptr(), gamma.contiguous().data_ptr(),
+                                                  beta.contiguous().data_ptr(), float(eps), B, HW, C, groups, int(relu),
+                                                  y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), ws.data_ptr(), _stream())
+    _lib.check(rc, "groupnorm_cl_fwd")
+    return y, mean, rstd
+
+
+def groupnorm_cl_bwd(dy, x, gamma, beta, mean, rstd, groups, relu):
+    """-> (dx [B,HW,C], dgamma [C], dbeta [C])."""
+    dy = _f32c(dy, "dy")
+    B, HW, C = x.shape
+    dx = torch.empty_like(x)
+    dgb = torch.empty((2, C), dtype=torch.float32, device=x.device)
+    ws = torch.empty((B, groups, 2), dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().mpf_groupnorm_cl_bwd_f32(dy.data_ptr(), x.data_ptr(), gamma.contiguous().data_ptr(),
+                                                  beta.contiguous().data_ptr(), mean.data_ptr(), rstd.data_ptr(), B, HW, C,
+                                                  groups, int(relu), dx.data_ptr(), dgb.data_ptr(), ws.data_ptr(), _stream())
+    _lib.check(rc, "groupnorm_cl_bwd")
+    return dx, dgb[0], dgb[1]
+
+
 def colsum(x2):
     """Column sums of a [rows, C] fp32 matrix (row stride a multiple of 4): the bias gradient of a Linear layer."""
     x2 = _f32c(x2, "x")

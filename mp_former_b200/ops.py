@@ -107,6 +107,42 @@ def add_layer_norm(x, r, norm):
     return _AddLayerNorm.apply(x, r, norm.weight, norm.bias, norm.eps)
 
 
+class _GroupNormCL(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, groups, relu):
+        # x: logical [B, C, H, W] in channels-last memory == tokens [B, H*W, C]
+        B, C, H, W = x.shape
+        tokens = x.permute(0, 2, 3, 1).reshape(B, H * W, C)
+        y, mean, rstd = native.groupnorm_cl_fwd(tokens, weight, bias, eps, groups, relu)
+        ctx.save_for_backward(tokens, weight, bias, mean, rstd)
+        ctx.groups, ctx.relu, ctx.hw = groups, relu, (H, W)
+        return y.view(B, H, W, C).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, gy):
+        tokens, weight, bias, mean, rstd = ctx.saved_tensors
+        B, HW, C = tokens.shape
+        g = gy.permute(0, 2, 3, 1)
+        if not g.is_contiguous():
+            g = g.contiguous()
+        dx, dgamma, dbeta = native.groupnorm_cl_bwd(g.view(B, HW, C), tokens, weight, bias, mean, rstd, ctx.groups,
+                                                    ctx.relu)
+        H, W = ctx.hw
+        return dx.view(B, H, W, C).permute(0, 3, 1, 2), dgamma, dbeta, None, None, None
+
+
+def group_norm_cl(x, gn, relu=False):
+    """nn.GroupNorm (optionally followed by ReLU) on a logically-NCHW map held in channels-last memory, as two
+    HBM passes forward / two backward (ref pixel_decoder/msdeformattn.py:216-219, :262-275).  Other layouts /
+    group sizes go through the library GroupNorm."""
+    if (x.is_cuda and x.dim() == 4 and x.dtype == torch.float32 and gn.affine
+            and native.groupnorm_cl_ok(x.shape[1], gn.num_groups)
+            and x.permute(0, 2, 3, 1).is_contiguous()):
+        return _GroupNormCL.apply(x, gn.weight, gn.bias, gn.eps, gn.num_groups, relu)
+    y = gn(x)
+    return F.relu(y) if relu else y
+
+
 class _FFN(torch.autograd.Function):
     """y = relu(x W1^T + b1) W2^T + b2 as one autograd node, so the ReLU backward is fused into the epilogue
     of the input-gradient GEMM of the second layer (``gate``) instead of a separate pass over [tokens, d_ffn]."""

@@ -63,6 +63,12 @@ class ConvNormAct(nn.Conv2d):
 
     def forward(self, x):
         x = super().forward(x)
+        return self.norm_act(x)
+
+    def norm_act(self, x):
+        """norm (+ ReLU) of the convolution output; GroupNorm on channels-last maps runs on the fused kernels."""
+        if isinstance(self.norm, nn.GroupNorm) and self.activation in (None, F.relu):
+            return ops.group_norm_cl(x, self.norm, relu=self.activation is F.relu)
         if self.norm is not None:
             x = self.norm(x)
         if self.activation is not None:
@@ -299,7 +305,7 @@ class MSDeformAttnPixelDecoder(nn.Module):
         for idx, f in enumerate(self.transformer_in_features[::-1]):
             x = features[f].float().contiguous(memory_format=torch.channels_last)
             proj = self.input_proj[idx]
-            srcs.append(proj[1](conv1x1_tokens(x, proj[0])))
+            srcs.append(ops.group_norm_cl(conv1x1_tokens(x, proj[0]), proj[1]))
             pos.append(self.pe_layer(x))
         y, spatial_shapes, _ = self.transformer(srcs, pos)
         bs = y.shape[0]
@@ -312,11 +318,7 @@ class MSDeformAttnPixelDecoder(nn.Module):
         for idx, f in enumerate(self.in_features[:self.num_fpn_levels][::-1]):
             x = features[f].float().contiguous(memory_format=torch.channels_last)
             lateral = self.lateral_convs[idx]
-            cur_fpn = conv1x1_tokens(x, lateral)
-            if lateral.norm is not None:
-                cur_fpn = lateral.norm(cur_fpn)
-            if lateral.activation is not None:
-                cur_fpn = lateral.activation(cur_fpn)
+            cur_fpn = lateral.norm_act(conv1x1_tokens(x, lateral))
             # keep the whole FPN stage channels-last (the upsampled map would otherwise come back NCHW and
             # force layout copies of the 256x256 maps around the 3x3 convolution)
             up = F.interpolate(out[-1].contiguous(memory_format=torch.channels_last), size=cur_fpn.shape[-2:],

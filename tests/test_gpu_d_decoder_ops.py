@@ -217,3 +217,31 @@ def test_colsum(rows, C, ld):
     out = native.colsum(x)
     ref = x.double().sum(0)
     assert (out.double() - ref).abs().max().item() < 1e-4 * max(1.0, rows ** 0.5)
+
+
+@pytest.mark.parametrize("B,C,H,W,G,relu", [(2, 256, 64, 64, 32, False), (2, 256, 48, 80, 32, True), (3, 128, 17, 9, 32, True),
+                                            (1, 256, 256, 256, 32, True)])
+def test_group_norm_channels_last(B, C, H, W, G, relu):
+    """GroupNorm (+ReLU) on channels-last maps vs torch in fp64 (ref pixel_decoder/msdeformattn.py:216-219, :262-275)."""
+    g = torch.Generator(device=DEV).manual_seed(B + C + H + W)
+    x = (torch.randn(B, C, H, W, device=DEV, generator=g) * 1.5 + 0.7).contiguous(memory_format=torch.channels_last)
+    x.requires_grad_(True)
+    gn = torch.nn.GroupNorm(G, C).to(DEV)
+    with torch.no_grad():
+        gn.weight.copy_(torch.randn(C, device=DEV, generator=g))
+        gn.bias.copy_(torch.randn(C, device=DEV, generator=g) * 0.3)
+    y = ops.group_norm_cl(x, gn, relu=relu)
+    assert y.shape == x.shape and y.permute(0, 2, 3, 1).is_contiguous()
+    gy = torch.randn(B, C, H, W, device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    y.backward(gy)
+    xr = x.detach().double().requires_grad_(True)
+    wr, br = gn.weight.detach().double().requires_grad_(True), gn.bias.detach().double().requires_grad_(True)
+    yr = F.group_norm(xr, G, wr, br, gn.eps)
+    if relu:
+        assert ((yr > 0) != (y > 0)).float().mean().item() < 1e-4
+        yr = yr * (y.detach() > 0)
+    yr.backward(gy.double())
+    assert rel(y, yr) < 1e-5
+    assert rel(x.grad, xr.grad) < 2e-5
+    for a, b in ((gn.weight.grad, wr.grad), (gn.bias.grad, br.grad)):
+        assert (a.double() - b).abs().max().item() / max(1.0, b.abs().max().item()) < 2e-5
