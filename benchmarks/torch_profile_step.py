@@ -39,7 +39,15 @@ torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=bool(os.environ.get("MPF_SHAPES"))) as prof:
     step()
     torch.cuda.synchronize()
-if os.environ.get("MPF_SHAPES"):
+if os.environ.get("MPF_KERNELS"):
+    # every device kernel of the step, one line each: total us, calls, name (complete, unlike the top-N tables)
+    rows = [(e.self_device_time_total, e.count, e.key) for e in prof.key_averages() if e.self_device_time_total > 0]
+    rows.sort(reverse=True)
+    tot = sum(r[0] for r in rows if not r[2].startswith(("FWD_", "BWD", "LOSS")))
+    print(f"# total self device time (kernels + memcpy/memset): {tot / 1e3:.3f} ms")
+    for us, n, k in rows:
+        print(f"{us:10.1f}\t{n:5d}\t{k[:150]}")
+elif os.environ.get("MPF_SHAPES"):
     print(prof.key_averages(group_by_input_shape=True).table(sort_by="self_cuda_time_total", row_limit=60,
                                                              max_name_column_width=40, max_shapes_column_width=90))
 else:

@@ -10,6 +10,7 @@ query-side layers (a few hundred rows) stay on library ops (launch-latency bound
 Inputs must be CUDA fp32 tensors; there is no CPU path.
 """
 import math
+import os
 
 import torch
 import torch.nn.functional as F
@@ -107,6 +108,9 @@ def add_layer_norm(x, r, norm):
     return _AddLayerNorm.apply(x, r, norm.weight, norm.bias, norm.eps)
 
 
+_NO_GN_KERNEL = bool(os.environ.get("MPF_NO_GN_KERNEL"))     # A/B switch for benchmarks only
+
+
 class _GroupNormCL(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, eps, groups, relu):
@@ -135,7 +139,7 @@ def group_norm_cl(x, gn, relu=False):
     """nn.GroupNorm (optionally followed by ReLU) on a logically-NCHW map held in channels-last memory, as two
     HBM passes forward / two backward (ref pixel_decoder/msdeformattn.py:216-219, :262-275).  Other layouts /
     group sizes go through the library GroupNorm."""
-    if (x.is_cuda and x.dim() == 4 and x.dtype == torch.float32 and gn.affine
+    if (x.is_cuda and x.dim() == 4 and x.dtype == torch.float32 and gn.affine and not _NO_GN_KERNEL
             and native.groupnorm_cl_ok(x.shape[1], gn.num_groups)
             and x.permute(0, 2, 3, 1).is_contiguous()):
         return _GroupNormCL.apply(x, gn.weight, gn.bias, gn.eps, gn.num_groups, relu)

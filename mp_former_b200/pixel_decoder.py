@@ -323,6 +323,8 @@ class MSDeformAttnPixelDecoder(nn.Module):
             # force layout copies of the 256x256 maps around the 3x3 convolution)
             up = F.interpolate(out[-1].contiguous(memory_format=torch.channels_last), size=cur_fpn.shape[-2:],
                                mode="bilinear", align_corners=False)
-            out.append(self.output_convs[idx](cur_fpn + up))
+            # cuDNN's fp32 3x3 convolution is ~7x slower on NHWC maps (46 ms vs 6.5 ms forward at [16,256,256,256],
+            # profiles/README.md r1p): hand the sum over in NCHW; the GroupNorm+ReLU behind it returns to tokens.
+            out.append(self.output_convs[idx]((cur_fpn + up).contiguous()))
         multi_scale_features = out[:self.maskformer_num_feature_levels]
         return conv1x1_tokens(out[-1], self.mask_features), out[0], multi_scale_features
