@@ -202,6 +202,11 @@ int mpf_gemm_bf16x3(const float* A, long long lda, long long a_batch_stride, con
 int mpf_gemm_bf16x3_tn(const float* A, long long lda, long long a_batch_stride, const float* B, long long ldb,
                        long long b_batch_stride, float* C, long long ldc, long long c_batch_stride, int batch, int M,
                        int N, int T, int k_splits, void* stream);
+/* Same product; accumulate != 0 adds it into C (TMA reduce-add, C must hold valid data) instead of overwriting: the
+ * mask-feature gradient is the sum over the 10 prediction heads (ref decoder :1865 called at :1767,:1797). */
+int mpf_gemm_bf16x3_tn_ex(const float* A, long long lda, long long a_batch_stride, const float* B, long long ldb,
+                          long long b_batch_stride, float* C, long long ldc, long long c_batch_stride, int batch, int M,
+                          int N, int T, int k_splits, int accumulate, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Row-wise kernels of the encoder / decoder layers.
@@ -285,6 +290,27 @@ int mpf_masked_xattn_bwd_f32(const float* q_hi, const float* q_lo, const float* 
                              const uint8_t* row_open, const float* lse2, const float* delta, float* dq,
                              float* dk, float* dv, int B, int Qt, int qt_ld, int HW, int heads, int head_dim,
                              int mask_words, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * FPN stage of the pixel decoder (ref pixel_decoder/msdeformattn.py:343-351): the map changes layout twice around
+ * the 3x3 convolution (library, NCHW); both crossings are fused into the elementwise work next to them.
+ *   mpf_upsample2x_add_nchw_fwd_f32:  out[b,c,h,w] = cur[b,h,w,c] + bilinear_x2(prev)[b,h,w,c]
+ *     (ref :347-349: cur_fpn + F.interpolate(out[-1], size=cur_fpn.shape[-2:], mode="bilinear", align_corners=False)
+ *     for the exact-x2 case); cur [B,H,W,C], prev [B,H/2,W/2,C] channels-last; H even, W % 4 == 0, C % 64 == 0.
+ *   mpf_upsample2x_add_nchw_bwd_f32:  g [B,C,H,W] -> g_cur [B,H,W,C] and g_prev [B,H/2,W/2,C] (adjoint of the x2 resize).
+ *   mpf_groupnorm_nchw2cl_fwd_f32 / _bwd_f32:  GroupNorm (+ReLU) reading the convolution output in NCHW and writing
+ *     channels-last tokens (ref :275 output conv norm + activation); arguments as mpf_groupnorm_cl_*, x / dx NCHW
+ *     [B,C,HW], y / dy channels-last [B,HW,C]; C % 64 == 0, channels per group a multiple of 4 dividing 64, HW % 4 == 0. */
+int mpf_upsample2x_add_nchw_fwd_f32(const float* cur, const float* prev, int batch, int H, int W, int C, float* out,
+                                    void* stream);
+int mpf_upsample2x_add_nchw_bwd_f32(const float* g, int batch, int H, int W, int C, float* g_cur, float* g_prev,
+                                    void* stream);
+int mpf_groupnorm_nchw2cl_fwd_f32(const float* x, const float* gamma, const float* beta, float eps, int batch,
+                                  long long HW, int C, int groups, int relu, float* y, float* mean, float* rstd,
+                                  double* stats_ws, void* stream);
+int mpf_groupnorm_nchw2cl_bwd_f32(const float* dy, const float* x, const float* gamma, const float* beta,
+                                  const float* mean, const float* rstd, int batch, long long HW, int C, int groups,
+                                  int relu, float* dx, float* dgamma_dbeta, double* stats_ws, void* stream);
 
 #ifdef __cplusplus
 }

@@ -48,12 +48,17 @@ SIGNATURES = {
                                  _c_vp, _c_ll, _c_int, _c_int, _c_vp, _c_ll, ctypes.c_float,
                                  _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp]),
     "mpf_gemm_bf16x3_tn": (_c_int, [_c_vp, _c_ll, _c_ll, _c_vp, _c_ll, _c_ll, _c_vp, _c_ll, _c_ll] + [_c_int] * 5 + [_c_vp]),
+    "mpf_gemm_bf16x3_tn_ex": (_c_int, [_c_vp, _c_ll, _c_ll, _c_vp, _c_ll, _c_ll, _c_vp, _c_ll, _c_ll] + [_c_int] * 6 + [_c_vp]),
     "mpf_add_layernorm_partials": (_c_int, [_c_ll]),
     "mpf_add_layernorm_fwd_f32": (_c_int, [_c_vp] * 4 + [ctypes.c_float, _c_ll, _c_int] + [_c_vp] * 4),
     "mpf_add_layernorm_bwd_f32": (_c_int, [_c_vp] * 6 + [_c_ll, _c_int] + [_c_vp] * 3),
     "mpf_colsum_f32": (_c_int, [_c_vp, _c_ll, _c_int, _c_ll, _c_vp, _c_vp]),
     "mpf_groupnorm_cl_fwd_f32": (_c_int, [_c_vp] * 3 + [ctypes.c_float, _c_int, _c_ll, _c_int, _c_int, _c_int] + [_c_vp] * 5),
     "mpf_groupnorm_cl_bwd_f32": (_c_int, [_c_vp] * 6 + [_c_int, _c_ll, _c_int, _c_int, _c_int] + [_c_vp] * 4),
+    "mpf_groupnorm_nchw2cl_fwd_f32": (_c_int, [_c_vp] * 3 + [ctypes.c_float, _c_int, _c_ll, _c_int, _c_int, _c_int] + [_c_vp] * 5),
+    "mpf_groupnorm_nchw2cl_bwd_f32": (_c_int, [_c_vp] * 6 + [_c_int, _c_ll, _c_int, _c_int, _c_int] + [_c_vp] * 4),
+    "mpf_upsample2x_add_nchw_fwd_f32": (_c_int, [_c_vp] * 2 + [_c_int] * 4 + [_c_vp] * 2),
+    "mpf_upsample2x_add_nchw_bwd_f32": (_c_int, [_c_vp] + [_c_int] * 4 + [_c_vp] * 3),
     "mpf_attn_mask_bits_f32": (_c_int, [_c_vp, _c_ll] + [_c_int] * 5 + [_c_vp, _c_int, _c_vp]),
     "mpf_pack_bool_bits": (_c_int, [_c_vp, _c_int, _c_int, _c_vp, _c_int, _c_vp]),
     "mpf_gt_mask_area_bits": (_c_int, [_c_vp] + [_c_int] * 5 + [_c_vp, _c_int, _c_vp]),

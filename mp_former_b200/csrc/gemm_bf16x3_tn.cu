@@ -46,10 +46,18 @@ struct Args {
   int k_splits, k_per_split;                   // tokens per split (multiple of 32)
   int raw_bytes, op_bytes;                     // per ring slot
   int debug;
+  int accumulate;                              // 1: C += product (TMA reduce-add store) instead of C = product
 };
 
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+// same box, but added into global memory by the TMA unit (f32 add taken from the tensor map's data type)
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(m)),
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
@@ -312,7 +320,8 @@ gemm_bf16x3_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         fence_proxy_async_smem();
         epi_bar();
         if (issuer) {
-          tma_store_3d(&tmC, buf, n0, m_t * kBM, slab);
+          if (g.accumulate) tma_reduce_add_3d(&tmC, buf, n0, m_t * kBM, slab);
+          else tma_store_3d(&tmC, buf, n0, m_t * kBM, slab);
           bulk_commit();
         }
         ++chunk_ctr;
@@ -386,9 +395,9 @@ static int make_tmap(CUtensorMap* m, const float* base, long long d0, long long 
 
 extern "C" {
 
-int mpf_gemm_bf16x3_tn(const float* A, long long lda, long long a_batch_stride, const float* B, long long ldb,
-                       long long b_batch_stride, float* C, long long ldc, long long c_batch_stride, int batch, int M,
-                       int N, int T, int k_splits, void* stream) {
+int mpf_gemm_bf16x3_tn_ex(const float* A, long long lda, long long a_batch_stride, const float* B, long long ldb,
+                          long long b_batch_stride, float* C, long long ldc, long long c_batch_stride, int batch, int M,
+                          int N, int T, int k_splits, int accumulate, void* stream) {
   using namespace mpf;
   using namespace mpf::bf3tn;
   clear_error();
@@ -421,6 +430,7 @@ int mpf_gemm_bf16x3_tn(const float* A, long long lda, long long a_batch_stride, 
   MPF_REQUIRE(static_cast<long long>(batch) * k_splits * g.tiles_m * g.tiles_n < (1ll << 31), "gemm_bf16x3_tn: too many tiles");
   g.debug = 0;
   if (const char* dbg = getenv("MPF_GEMM_DEBUG")) g.debug = atoi(dbg);
+  g.accumulate = accumulate ? 1 : 0;
 
   CUtensorMap ta, tb, tc;
   int rc = make_tmap(&ta, A, M, T, batch, lda, a_batch_stride, kBK, "A");
@@ -440,6 +450,13 @@ int mpf_gemm_bf16x3_tn(const float* A, long long lda, long long a_batch_stride, 
   gemm_bf16x3_tn_kernel<<<grid, kThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(ta, tb, tc, g);
   count_launch();
   return finish_launch("gemm_bf16x3_tn");
+}
+
+int mpf_gemm_bf16x3_tn(const float* A, long long lda, long long a_batch_stride, const float* B, long long ldb,
+                       long long b_batch_stride, float* C, long long ldc, long long c_batch_stride, int batch, int M,
+                       int N, int T, int k_splits, void* stream) {
+  return mpf_gemm_bf16x3_tn_ex(A, lda, a_batch_stride, B, ldb, b_batch_stride, C, ldc, c_batch_stride, batch, M, N, T,
+                               k_splits, 0, stream);
 }
 
 }  // extern "C"

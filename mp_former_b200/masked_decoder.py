@@ -124,6 +124,28 @@ class MLP(nn.Module):
         return x
 
 
+class _HeadFeatures:
+    """The per-head aliases of ``mask_features`` handed out in call order (ops.grad_fanout)."""
+
+    def __init__(self, aliases, shared):
+        self.aliases, self.shared, self.used = aliases, shared, 0
+
+    def next(self):
+        if self.used >= len(self.aliases):
+            raise RuntimeError("more prediction heads than aliases of mask_features")
+        a = self.aliases[self.used]
+        self.used += 1
+        return a, self.shared
+
+    @property
+    def shape(self):
+        return self.aliases[0].shape
+
+    @property
+    def device(self):
+        return self.aliases[0].device
+
+
 class _MaskedDecoderBase(nn.Module):
     _version = 2
 
@@ -206,14 +228,25 @@ class _MaskedDecoderBase(nn.Module):
             src.append(s + self.level_embed.weight[i].view(1, 1, -1))
         return src, pos, size_list
 
+    def _fanout_mask_features(self, mask_features):
+        """One alias of ``mask_features`` per prediction head (num_layers + 1 of them), channels-last, with the
+        heads' gradients accumulated in the GEMM epilogue (ops.grad_fanout)."""
+        mask_features = mask_features.contiguous(memory_format=torch.channels_last)
+        aliases, shared = ops.grad_fanout(mask_features, self.num_layers + 1)
+        return _HeadFeatures(aliases, shared)
+
     def forward_prediction_heads(self, output, mask_features, attn_mask_target_size):
         """output [B,Q,C] -> (outputs_class [B,Q,K+1], outputs_mask [B,Q,H,W],
         attn_mask: ops.PackedMask, one bit per (image, query, key), shared by heads).
-        ref decoder :1859-1877."""
+        ref decoder :1859-1877.  ``mask_features``: the map, or the ``_HeadFeatures`` of ``_fanout_mask_features``."""
         decoder_output = ops.add_layer_norm(output, None, self.decoder_norm)
         outputs_class = ops.linear(decoder_output, self.class_embed.weight, self.class_embed.bias)
         mask_embed = self.mask_embed(decoder_output)
-        outputs_mask = ops.mask_logits(mask_embed, mask_features)
+        if isinstance(mask_features, _HeadFeatures):
+            mf, shared = mask_features.next()
+            outputs_mask = ops.mask_logits(mask_embed, mf, shared)
+        else:
+            outputs_mask = ops.mask_logits(mask_embed, mask_features)
         attn_mask = ops.attn_mask_from_logits(outputs_mask, attn_mask_target_size)
         return outputs_class, outputs_mask, attn_mask
 
@@ -268,6 +301,7 @@ class MultiScaleMaskedTransformerDecoder(_MaskedDecoderBase):
                                       "part of the MP-Former recipe; use ...DecoderMaskDN")
         src, pos, size_list = self._memory(x)
         bs = src[0].shape[0]
+        mask_features = self._fanout_mask_features(mask_features)
         output = self.query_feat.weight.unsqueeze(0).repeat(bs, 1, 1)
         heads0 = self.forward_prediction_heads(output, mask_features, size_list[0])
         pc, pm = self._decode(output, src, pos, size_list, mask_features, None, heads0)
@@ -413,6 +447,7 @@ class MultiScaleMaskedTransformerDecoderMaskDN(_MaskedDecoderBase):
         del mask
         src, pos, size_list = self._memory(x)
         bs = src[0].shape[0]
+        mask_features = self._fanout_mask_features(mask_features)
         res = None
         if dn_args is not None:
             if self.dn_mode != "points":

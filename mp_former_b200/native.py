@@ -284,6 +284,78 @@ def groupnorm_cl_bwd(dy, x, gamma, beta, mean, rstd, groups, relu):
     return dx, dgb[0], dgb[1]
 
 
+def groupnorm_nchw2cl_ok(C, groups, HW):
+    cpg = C // groups if groups > 0 and C % groups == 0 else 0
+    return C % 64 == 0 and cpg > 0 and cpg % 4 == 0 and 64 % cpg == 0 and HW % 4 == 0
+
+
+def groupnorm_nchw2cl_fwd(x, gamma, beta, eps, groups, relu):
+    """x [B, C, HW] contiguous (NCHW) -> (y [B, HW, C] channels-last tokens, mean [B,G], rstd [B,G])."""
+    x = _f32c(x, "x")
+    B, C, HW = x.shape
+    y = torch.empty((B, HW, C), dtype=torch.float32, device=x.device)
+    mean = torch.empty((B, groups), dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    ws = torch.empty((B, groups, 2), dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().mpf_groupnorm_nchw2cl_fwd_f32(x.data_ptr(), gamma.contiguous().data_ptr(),
+                                                       beta.contiguous().data_ptr(), float(eps), B, HW, C, groups,
+                                                       int(relu), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                                       ws.data_ptr(), _stream())
+    _lib.check(rc, "groupnorm_nchw2cl_fwd")
+    return y, mean, rstd
+
+
+def groupnorm_nchw2cl_bwd(dy, x, gamma, beta, mean, rstd, groups, relu):
+    """dy [B, HW, C] (channels-last), x [B, C, HW] (NCHW) -> (dx [B, C, HW], dgamma [C], dbeta [C])."""
+    dy = _f32c(dy, "dy")
+    B, C, HW = x.shape
+    dx = torch.empty_like(x)
+    dgb = torch.empty((2, C), dtype=torch.float32, device=x.device)
+    ws = torch.empty((B, groups, 2), dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().mpf_groupnorm_nchw2cl_bwd_f32(dy.data_ptr(), x.data_ptr(), gamma.contiguous().data_ptr(),
+                                                       beta.contiguous().data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                                       B, HW, C, groups, int(relu), dx.data_ptr(), dgb.data_ptr(),
+                                                       ws.data_ptr(), _stream())
+    _lib.check(rc, "groupnorm_nchw2cl_bwd")
+    return dx, dgb[0], dgb[1]
+
+
+def upsample2x_add_ok(H, W, C):
+    return H % 2 == 0 and W % 4 == 0 and C % 64 == 0 and H >= 2 and W >= 4
+
+
+def upsample2x_add_nchw_fwd(cur, prev):
+    """cur [B, H, W, C], prev [B, H/2, W/2, C] (both channels-last, contiguous) -> cur + bilinear_x2(prev) as
+    NCHW-contiguous [B, C, H, W]."""
+    cur, prev = _f32c(cur, "cur"), _f32c(prev, "prev")
+    B, H, W, C = cur.shape
+    if prev.shape != (B, H // 2, W // 2, C) or not cur.is_contiguous() or not prev.is_contiguous():
+        raise RuntimeError(f"upsample2x_add: shapes {tuple(cur.shape)} / {tuple(prev.shape)} (contiguous channels-last)")
+    out = torch.empty((B, C, H, W), dtype=torch.float32, device=cur.device)
+    with torch.cuda.device(cur.device):
+        rc = _lib.load().mpf_upsample2x_add_nchw_fwd_f32(cur.data_ptr(), prev.data_ptr(), B, H, W, C, out.data_ptr(),
+                                                         _stream())
+    _lib.check(rc, "upsample2x_add_nchw_fwd")
+    return out
+
+
+def upsample2x_add_nchw_bwd(g):
+    """g [B, C, H, W] NCHW-contiguous -> (g_cur [B, H, W, C], g_prev [B, H/2, W/2, C])."""
+    g = _f32c(g, "g")
+    if not g.is_contiguous():
+        g = g.contiguous()
+    B, C, H, W = g.shape
+    g_cur = torch.empty((B, H, W, C), dtype=torch.float32, device=g.device)
+    g_prev = torch.empty((B, H // 2, W // 2, C), dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device):
+        rc = _lib.load().mpf_upsample2x_add_nchw_bwd_f32(g.data_ptr(), B, H, W, C, g_cur.data_ptr(), g_prev.data_ptr(),
+                                                         _stream())
+    _lib.check(rc, "upsample2x_add_nchw_bwd")
+    return g_cur, g_prev
+
+
 def colsum(x2):
     """Column sums of a [rows, C] fp32 matrix (row stride a multiple of 4): the bias gradient of a Linear layer."""
     x2 = _f32c(x2, "x")
@@ -442,9 +514,11 @@ def gemm_general(a, b, a_mn=False, b_mn=False, b_lo=None, bias=None, relu=False,
     return out[0] if squeeze else out
 
 
-def gemm_tn(a, b, k_splits=1):
+def gemm_tn(a, b, k_splits=1, accumulate_into=None):
     """C[i] = a[i]^T @ b[i] for a [batch, T, M], b [batch, T, N] (fp32, row-major; 2-D inputs = batch 1) on the
-    bf16x3 TN kernel: both operands are split in-kernel, reduction over T, optional split-K (partials summed here)."""
+    bf16x3 TN kernel: both operands are split in-kernel, reduction over T, optional split-K (partials summed here).
+    ``accumulate_into`` [batch, M, N] (contiguous fp32): the product is ADDED to it by the kernel's TMA reduce-add
+    epilogue and the same tensor is returned (no split-K in that mode)."""
     a, b = _f32c(a, "a"), _f32c(b, "b")
     squeeze = a.dim() == 2
     if squeeze:
@@ -462,6 +536,19 @@ def gemm_tn(a, b, k_splits=1):
     if N % 4:
         raise RuntimeError("gemm_tn: N must be a multiple of 4")
     k_splits = max(1, min(int(k_splits), (T + 31) // 32))
+    if accumulate_into is not None:
+        acc = accumulate_into
+        if (acc.dtype != torch.float32 or not acc.is_contiguous() or acc.numel() != batch * M * N
+                or acc.device != a.device):
+            raise RuntimeError("gemm_tn: accumulate_into must be a contiguous fp32 [batch, M, N] tensor on the same device")
+        with torch.cuda.device(a.device), _Timed("gemm_bf16x3_tn_kernel", 2.0 * batch * M * N * T,
+                                                 4.0 * batch * (T * M + T * N + 2 * M * N)):
+            rc = _lib.load().mpf_gemm_bf16x3_tn_ex(
+                a.data_ptr(), a.stride(1), a.stride(0) if batch > 1 else T * a.stride(1),
+                b.data_ptr(), b.stride(1), b.stride(0) if batch > 1 else T * b.stride(1),
+                acc.data_ptr(), N, M * N, batch, M, N, T, 1, 1, _stream())
+        _lib.check(rc, "gemm_bf16x3_tn_ex")
+        return acc
     out = torch.empty((batch * k_splits, M, N), dtype=torch.float32, device=a.device)
     with torch.cuda.device(a.device), _Timed("gemm_bf16x3_tn_kernel", 2.0 * batch * M * N * T,
                                              4.0 * batch * (T * M + T * N + k_splits * M * N)):

@@ -83,6 +83,59 @@ def linear(x, weight, bias=None, relu=False):
     return _Linear.apply(x, weight, bias, relu)
 
 
+class _Conv1x1NCHW(torch.autograd.Function):
+    """1x1 convolution of an NCHW-contiguous map (backbone output) straight into channels-last tokens: the map is
+    the MN-major operand [B, Cin, HW] of the token-reduction ("TN") GEMM, so no layout copy of the input is made."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        B, Cin, H, W = x.shape
+        Cout = weight.shape[0]
+        x3 = x.view(B, Cin, H * W)
+        wt = weight.view(Cout, Cin).t()[None].expand(B, -1, -1).contiguous()          # [B, Cin, Cout], a few MB
+        y = native.gemm_tn(x3, wt)                                                   # [B, HW, Cout]
+        if bias is not None:
+            y += bias
+        ctx.save_for_backward(x3, weight)
+        ctx.has_bias, ctx.hw = bias is not None, (H, W)
+        return y.view(B, H, W, Cout).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x3, weight = ctx.saved_tensors
+        B, Cin, HW = x3.shape
+        Cout = weight.shape[0]
+        g = gy.permute(0, 2, 3, 1)
+        if not g.is_contiguous():
+            g = g.contiguous()
+        g3 = g.view(B, HW, Cout)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            # dX[b] (Cin x HW) = W^T dY[b]^T: token GEMM with a transposed store -> NCHW directly
+            wt_hi, wt_lo = native.split_b(weight.view(Cout, Cin).t().contiguous())
+            gx = native.gemm(g3, wt_hi[None].expand(B, -1, -1), wt_lo[None].expand(B, -1, -1), transpose_c=True)
+            gx = gx.view(B, Cin, *ctx.hw)
+        if ctx.needs_input_grad[1]:
+            # dW = sum_b dY[b]^T (Cout x HW) X[b]^T (HW x Cin): dY is MN-major, X K-major; K = HW cut into splits
+            tiles = ((Cout + 127) // 128) * ((Cin + 127) // 128) * B
+            splits = max(1, min(64, 296 // max(1, tiles), (HW + 1023) // 1024))
+            gw = native.gemm_general(g3, x3, a_mn=True, b_mn=False, k_splits=splits).sum(0).view(weight.shape)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = native.colsum(g3.view(B * HW, Cout))
+        return gx, gw, gb
+
+
+def conv1x1_nchw_to_cl(x, weight, bias=None):
+    """1x1 convolution (ref pixel_decoder/msdeformattn.py:216-219 input projections, :262 lateral convs) of an
+    NCHW-contiguous map; result: the same logical [B, Cout, H, W] in channels-last memory.  None when the geometry is
+    not covered."""
+    if (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.is_contiguous() and native.GEMM_MODE == "bf16x3"
+            and (x.shape[2] * x.shape[3]) % 4 == 0 and x.shape[2] * x.shape[3] >= 128 and weight.shape[0] % 4 == 0
+            and x.shape[1] % 4 == 0):
+        return _Conv1x1NCHW.apply(x, weight, bias)
+    return None
+
+
 class _AddLayerNorm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, r, weight, bias, eps):
@@ -108,7 +161,8 @@ def add_layer_norm(x, r, norm):
     return _AddLayerNorm.apply(x, r, norm.weight, norm.bias, norm.eps)
 
 
-_NO_GN_KERNEL = bool(os.environ.get("MPF_NO_GN_KERNEL"))     # A/B switch for benchmarks only
+_NO_GN_KERNEL = bool(os.environ.get("MPF_NO_GN_KERNEL"))     # A/B switches for benchmarks only
+NO_FUSED_ENCODER_LAYER = bool(os.environ.get("MPF_NO_FUSED_ENCODER_LAYER"))
 
 
 class _GroupNormCL(torch.autograd.Function):
@@ -145,6 +199,67 @@ def group_norm_cl(x, gn, relu=False):
         return _GroupNormCL.apply(x, gn.weight, gn.bias, gn.eps, gn.num_groups, relu)
     y = gn(x)
     return F.relu(y) if relu else y
+
+
+class _GroupNormNCHW2CL(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, groups, relu):
+        # x: NCHW-contiguous [B, C, H, W] (a cuDNN convolution output) -> logical NCHW in channels-last memory
+        B, C, H, W = x.shape
+        x3 = x.view(B, C, H * W)
+        y, mean, rstd = native.groupnorm_nchw2cl_fwd(x3, weight, bias, eps, groups, relu)
+        ctx.save_for_backward(x3, weight, bias, mean, rstd)
+        ctx.groups, ctx.relu, ctx.hw = groups, relu, (H, W)
+        return y.view(B, H, W, C).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x3, weight, bias, mean, rstd = ctx.saved_tensors
+        B, C, HW = x3.shape
+        g = gy.permute(0, 2, 3, 1)
+        if not g.is_contiguous():
+            g = g.contiguous()
+        dx, dgamma, dbeta = native.groupnorm_nchw2cl_bwd(g.view(B, HW, C), x3, weight, bias, mean, rstd, ctx.groups,
+                                                         ctx.relu)
+        H, W = ctx.hw
+        return dx.view(B, C, H, W), dgamma, dbeta, None, None, None
+
+
+def group_norm_nchw_to_cl(x, gn, relu=False):
+    """nn.GroupNorm (optionally + ReLU) of an NCHW-contiguous map, returned as the same logical [B,C,H,W] tensor in
+    channels-last memory (ready to be viewed as tokens): ref pixel_decoder/msdeformattn.py:262-275 output conv norm +
+    activation.  Returns None when the geometry is not covered (caller uses the library GroupNorm)."""
+    if (x.is_cuda and x.dim() == 4 and x.dtype == torch.float32 and gn.affine and not _NO_GN_KERNEL
+            and x.is_contiguous()
+            and native.groupnorm_nchw2cl_ok(x.shape[1], gn.num_groups, x.shape[2] * x.shape[3])):
+        return _GroupNormNCHW2CL.apply(x, gn.weight, gn.bias, gn.eps, gn.num_groups, relu)
+    return None
+
+
+class _Upsample2xAddNCHW(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cur, prev):
+        # cur, prev: logical NCHW in channels-last memory; result NCHW-contiguous
+        out = native.upsample2x_add_nchw_fwd(cur.permute(0, 2, 3, 1), prev.permute(0, 2, 3, 1))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g_cur, g_prev = native.upsample2x_add_nchw_bwd(g)
+        return g_cur.permute(0, 3, 1, 2), g_prev.permute(0, 3, 1, 2)
+
+
+def upsample2x_add_to_nchw(cur, prev):
+    """``cur + F.interpolate(prev, size=cur.shape[-2:], mode="bilinear", align_corners=False)`` for the exact x2 case of
+    the FPN stage (ref pixel_decoder/msdeformattn.py:347-349), both inputs channels-last, result NCHW-contiguous for
+    the 3x3 convolution.  Returns None when the geometry is not covered."""
+    if (cur.is_cuda and cur.dtype == torch.float32 and prev.dtype == torch.float32 and cur.dim() == 4
+            and not _NO_GN_KERNEL
+            and cur.shape[2] == 2 * prev.shape[2] and cur.shape[3] == 2 * prev.shape[3]
+            and native.upsample2x_add_ok(cur.shape[2], cur.shape[3], cur.shape[1])
+            and cur.permute(0, 2, 3, 1).is_contiguous() and prev.permute(0, 2, 3, 1).is_contiguous()):
+        return _Upsample2xAddNCHW.apply(cur, prev)
+    return None
 
 
 class _FFN(torch.autograd.Function):
@@ -186,6 +301,118 @@ def ffn(x, w1, b1, w2, b2):
 
 
 # ------------------------------------------------------------------------------------------------
+# MSDeformAttn encoder layer as one autograd node
+# ------------------------------------------------------------------------------------------------
+class _EncoderLayer(torch.autograd.Function):
+    """One MSDeformAttnTransformerEncoderLayer (ref pixel_decoder/msdeformattn.py:92-131 with dropout inactive):
+
+        value = src Wv^T + bv;  ow = (src + pos) [Woff; Watt]^T + [boff; batt];  a = MSDeformAttn(value, ow, ref)
+        src1 = LN1(src + a Wo^T + bo);  out = LN2(src1 + relu(src1 W1^T + b1) W2^T + b2)
+
+    as ONE node, so that the elementwise traffic autograd would add around the kernels disappears:
+    ``src + pos`` is never formed (pos [1,S,C] is batch independent: its projection enters the GEMM epilogue as a
+    row-periodic residual); in the backward the three gradient contributions to ``src`` and the two to ``src1``
+    are chained through the ``resid`` input of the input-gradient GEMMs instead of separate full-size additions,
+    and the gradient of ``pos`` is one small GEMM on the batch-summed logit gradients."""
+
+    @staticmethod
+    def forward(ctx, src, pos, ref, shapes, lsi, n_heads, n_points,
+                wv, bv, woff, boff, watt, batt, wo, bo, g1, be1, eps1, w1, b1, w2, b2, g2, be2, eps2):
+        from . import MultiScaleDeformableAttention as MSDA
+        B, S, C = src.shape
+        M, P = n_heads, n_points
+        host_shapes = getattr(shapes, "_mpf_host_shapes", None)
+        x2 = src.reshape(B * S, C)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        pos2 = pos.reshape(S, C)
+        wv_hi, wv_lo = native.split_b(wv)
+        value = native.gemm(x2, wv_hi, wv_lo, bv)
+        wow = torch.cat([woff, watt], 0)
+        bow = torch.cat([boff, batt], 0)
+        wow_hi, wow_lo = native.split_b(wow)
+        pos_ow = native.gemm(pos2, wow_hi, wow_lo, bow)                             # [S, M*L*P*3]
+        ow = native.gemm(x2, wow_hi, wow_lo, None, resid=pos_ow, resid_rows=S)
+        attn = MSDA.ms_deform_attn_enc_forward(value.view(B, S, M, C // M), shapes, lsi, ow.view(B, S, -1), ref, P,
+                                               host_shapes=host_shapes)
+        wo_hi, wo_lo = native.split_b(wo)
+        proj = native.gemm(attn.view(B * S, C), wo_hi, wo_lo, bo)
+        src1, mean1, rstd1 = native.add_layernorm_fwd(x2, proj, g1, be1, eps1)
+        w1_hi, w1_lo = native.split_b(w1)
+        hidden = native.gemm(src1, w1_hi, w1_lo, b1, relu=True)
+        w2_hi, w2_lo = native.split_b(w2)
+        y = native.gemm(hidden, w2_hi, w2_lo, b2)
+        out, mean2, rstd2 = native.add_layernorm_fwd(src1, y, g2, be2, eps2)
+        ctx.save_for_backward(x2, pos2, ref, shapes, lsi, value, ow, attn, proj, mean1, rstd1, src1, hidden, y, mean2,
+                              rstd2, wv, wow, wo, g1, w1, w2, g2)
+        ctx.geom = (B, S, C, M, P, host_shapes, woff.shape[0])
+        return out.view(B, S, C)
+
+    @staticmethod
+    def backward(ctx, g_out):
+        from . import MultiScaleDeformableAttention as MSDA
+        (x2, pos2, ref, shapes, lsi, value, ow, attn, proj, mean1, rstd1, src1, hidden, y, mean2, rstd2,
+         wv, wow, wo, g1, w1, w2, g2) = ctx.saved_tensors
+        B, S, C, M, P, host_shapes, n_off = ctx.geom
+
+        def t_halves(w):
+            return native.split_b(w.t().contiguous())
+
+        # FFN block
+        dsum2, dg2, db2 = native.add_layernorm_bwd(g_out.reshape(B * S, C), src1, y, g2, mean2, rstd2)
+        gb2 = native.colsum(dsum2)
+        w2t_hi, w2t_lo = t_halves(w2)
+        gh = native.gemm_general(dsum2, w2t_hi, b_lo=w2t_lo, gate=hidden)            # ReLU mask in the epilogue
+        gw2 = native.matmul_tn(dsum2, hidden)
+        w1t_hi, w1t_lo = t_halves(w1)
+        g_src1 = native.gemm(gh, w1t_hi, w1t_lo, resid=dsum2)                        # + the residual branch
+        gw1 = native.matmul_tn(gh, src1)
+        gb1 = native.colsum(gh)
+        del gh
+        # attention block
+        dsum1, dg1, db1 = native.add_layernorm_bwd(g_src1, x2, proj, g1, mean1, rstd1)
+        gbo = native.colsum(dsum1)
+        wot_hi, wot_lo = t_halves(wo)
+        g_attn = native.gemm(dsum1, wot_hi, wot_lo)
+        gwo = native.matmul_tn(dsum1, attn.view(B * S, C))
+        g_value, g_ow = MSDA.ms_deform_attn_enc_backward(value.view(B, S, M, C // M), shapes, lsi, ow.view(B, S, -1), ref,
+                                                         g_attn.view(B, S, C), P, host_shapes=host_shapes)
+        gv2, gow2 = g_value.view(B * S, C), g_ow.view(B * S, -1)
+        wvt_hi, wvt_lo = t_halves(wv)
+        wowt_hi, wowt_lo = t_halves(wow)
+        g_src = native.gemm(gv2, wvt_hi, wvt_lo, resid=dsum1)                        # residual + value branch
+        g_src = native.gemm(gow2, wowt_hi, wowt_lo, resid=g_src)                     # + query branch
+        gwv = native.matmul_tn(gv2, x2)
+        gbv = native.colsum(gv2)
+        gow_b = g_ow.view(B, S, -1).sum(0)                                           # [S, M*L*P*3]
+        gwow = native.matmul_tn(gow2, x2) + native.matmul_tn(gow_b, pos2)
+        gbow = native.colsum(gow2)
+        g_pos = native.gemm(gow_b, wowt_hi, wowt_lo).view(1, S, C) if ctx.needs_input_grad[1] else None
+        return (g_src.view(B, S, C), g_pos, None, None, None, None, None,
+                gwv, gbv, gwow[:n_off], gbow[:n_off], gwow[n_off:], gbow[n_off:], gwo, gbo, dg1, db1, None,
+                gw1, gb1, gw2, gb2, dg2, db2, None)
+
+
+def encoder_layer_supported(src, pos, reference_points, d_ffn, n_heads, n_levels, n_points):
+    C = src.shape[-1]
+    return (src.is_cuda and src.dtype == torch.float32 and src.dim() == 3 and pos is not None and pos.dim() == 3
+            and pos.shape[0] == 1 and pos.shape[1:] == src.shape[1:] and C in (128, 256, 512) and C % n_heads == 0
+            and (C // n_heads) in (16, 32, 64) and n_points == 4 and n_levels <= 4 and d_ffn % 32 == 0
+            and (n_heads * n_levels * n_points * 3) % 32 == 0
+            and reference_points.shape[-1] == 2 and not reference_points.requires_grad)
+
+
+def encoder_layer(src, pos, reference_points, spatial_shapes, level_start_index, attn, norm1, linear1, linear2, norm2):
+    """Fused forward/backward of one encoder layer; ``attn``: the layer's MSDeformAttn module (parameters only)."""
+    return _EncoderLayer.apply(
+        src, pos, reference_points, spatial_shapes, level_start_index, attn.n_heads, attn.n_points,
+        attn.value_proj.weight, attn.value_proj.bias, attn.sampling_offsets.weight, attn.sampling_offsets.bias,
+        attn.attention_weights.weight, attn.attention_weights.bias, attn.output_proj.weight, attn.output_proj.bias,
+        norm1.weight, norm1.bias, norm1.eps, linear1.weight, linear1.bias, linear2.weight, linear2.bias,
+        norm2.weight, norm2.bias, norm2.eps)
+
+
+# ------------------------------------------------------------------------------------------------
 # prediction heads: mask logits + boolean stage
 # ------------------------------------------------------------------------------------------------
 def _channels_last_tokens(mask_features):
@@ -196,15 +423,59 @@ def _channels_last_tokens(mask_features):
     return t.view(t.shape[0], -1, t.shape[-1])
 
 
+class _SharedGrad:
+    """Accumulator of the gradients that several consumers send to ONE tensor (see ``grad_fanout``)."""
+    __slots__ = ("buf",)
+
+    def __init__(self):
+        self.buf = None
+
+
+class _GradFanout(torch.autograd.Function):
+    """x -> n aliases of x, one per consumer.  Consumers that know the protocol (``_MaskLogits``) add their gradient
+    into ``state.buf`` inside their own kernel epilogue instead of returning n full-size tensors for autograd to
+    sum; autograd runs this node's backward only after every consumer's, so the buffer is complete here."""
+
+    @staticmethod
+    def forward(ctx, x, n, state):
+        ctx.state = state
+        ctx.xshape = x.shape
+        ctx.set_materialize_grads(False)
+        return tuple(x.view_as(x) for _ in range(n))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        buf, ctx.state.buf = ctx.state.buf, None
+        rest = [g for g in grads if g is not None and (buf is None or g.data_ptr() != buf.data_ptr())]
+        total = None
+        if buf is not None:                             # tokens [B, H*W, C] -> logical [B, C, H, W]
+            B, C, H, W = ctx.xshape
+            total = buf.view(B, H, W, C).permute(0, 3, 1, 2)
+        for g in rest:                                  # consumers outside the protocol: plain sum
+            total = g if total is None else total + g
+        return total, None, None
+
+
+def grad_fanout(x, n):
+    """n aliases of ``x`` for n consumers whose gradients are accumulated in place (the 10 prediction heads all read
+    ``mask_features``: nine 1 GB gradient additions per step at the bench geometry otherwise).
+    Returns (aliases, state); pass ``state`` to ``mask_logits``."""
+    state = _SharedGrad()
+    if not (torch.is_grad_enabled() and x.requires_grad):
+        return [x] * n, None
+    return list(_GradFanout.apply(x, n, state)), state
+
+
 class _MaskLogits(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, mask_embed, mask_features):
+    def forward(ctx, mask_embed, mask_features, shared):
         B, C, H, W = mask_features.shape
         tokens = _channels_last_tokens(mask_features)                       # [B, HW, C]
         e_hi, e_lo = native.split_b(mask_embed)
         out = native.gemm(tokens, e_hi, e_lo, transpose_c=True)             # [B, Q, HW]
         ctx.save_for_backward(mask_embed, tokens)
         ctx.fshape = (B, C, H, W)
+        ctx.shared = shared
         return out.view(B, mask_embed.shape[1], H, W)
 
     @staticmethod
@@ -223,20 +494,27 @@ class _MaskLogits(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             # dF[b] = dOut[b]^T (HW x Q) @ E[b] (Q x C): both operands MN-major
             if ok and native.GEMM_MODE == "bf16x3":
-                gf = native.gemm_tn(g2, mask_embed)              # reduction over the Q queries, both operands as stored
+                # reduction over the Q queries, both operands as stored; with a shared accumulator the heads after
+                # the first add into it in the kernel epilogue (TMA reduce-add)
+                sh = ctx.shared
+                if sh is None:
+                    gf = native.gemm_tn(g2, mask_embed)
+                else:
+                    sh.buf = gf = native.gemm_tn(g2, mask_embed, accumulate_into=sh.buf)
             elif ok:
                 gf = native.gemm_general(g2, mask_embed, a_mn=True, b_mn=True)
             else:
                 gf = torch.bmm(g2.transpose(1, 2), mask_embed)
             gf = gf.view(B, H, W, C).permute(0, 3, 1, 2)
-        return ge, gf
+        return ge, gf, None
 
 
-def mask_logits(mask_embed, mask_features):
+def mask_logits(mask_embed, mask_features, shared=None):
     """einsum('bqc,bchw->bqhw') (ref decoder :1865) as a TMA-fed tcgen05 GEMM over channels-last
-    pixel features: M = H*W, N = Q, K = C, transposed store."""
+    pixel features: M = H*W, N = Q, K = C, transposed store.  ``shared``: state of ``grad_fanout`` when
+    ``mask_features`` is one of its aliases."""
     _cuda_only(mask_embed, "mask_embed")
-    return _MaskLogits.apply(mask_embed.contiguous(), mask_features)
+    return _MaskLogits.apply(mask_embed.contiguous(), mask_features, shared)
 
 
 class PackedMask:

@@ -68,7 +68,9 @@ class ConvNormAct(nn.Conv2d):
     def norm_act(self, x):
         """norm (+ ReLU) of the convolution output; GroupNorm on channels-last maps runs on the fused kernels."""
         if isinstance(self.norm, nn.GroupNorm) and self.activation in (None, F.relu):
-            return ops.group_norm_cl(x, self.norm, relu=self.activation is F.relu)
+            relu = self.activation is F.relu
+            y = ops.group_norm_nchw_to_cl(x, self.norm, relu=relu)      # NCHW convolution output -> tokens
+            return y if y is not None else ops.group_norm_cl(x, self.norm, relu=relu)
         if self.norm is not None:
             x = self.norm(x)
         if self.activation is not None:
@@ -82,6 +84,11 @@ def conv1x1_tokens(x, conv):
     B, Cin, H, W = x.shape
     if Cin % 32 != 0 or conv.kernel_size != (1, 1) or conv.stride != (1, 1):
         return F.conv2d(x, conv.weight, conv.bias)
+    if x.is_contiguous() and not x.permute(0, 2, 3, 1).is_contiguous():
+        # NCHW backbone output: consumed as the MN-major operand of the token-reduction GEMM, no layout copy
+        y = ops.conv1x1_nchw_to_cl(x, conv.weight, conv.bias)
+        if y is not None:
+            return y
     tokens = x.permute(0, 2, 3, 1)
     if not tokens.is_contiguous():
         tokens = tokens.contiguous()
@@ -134,6 +141,13 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
         return ops.add_layer_norm(src, self.dropout3(src2), self.norm2)
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None):
+        dropout_off = not self.training or (self.dropout1.p == 0.0 and self.dropout2.p == 0.0 and self.dropout3.p == 0.0)
+        if (padding_mask is None and dropout_off and not ops.NO_FUSED_ENCODER_LAYER and ops.encoder_layer_supported(
+                src, pos, reference_points, self.linear1.out_features, self.self_attn.n_heads,
+                self.self_attn.n_levels, self.self_attn.n_points)):
+            # the whole layer as one autograd node (no ``src + pos``, no full-size gradient additions)
+            return ops.encoder_layer(src, pos, reference_points, spatial_shapes, level_start_index, self.self_attn,
+                                     self.norm1, self.linear1, self.linear2, self.norm2)
         src2 = self.self_attn(self.with_pos_embed(src, pos), reference_points, src, spatial_shapes,
                               level_start_index, padding_mask)
         src = ops.add_layer_norm(src, self.dropout1(src2), self.norm1)
@@ -213,6 +227,8 @@ class MSDeformAttnTransformerEncoderOnly(nn.Module):
         B = srcs[0].shape[0]
         spatial_shapes, level_start_index, ref = self._geometry(shapes, srcs[0].device)
         src_flatten = torch.cat([s.permute(0, 2, 3, 1).flatten(1, 2) for s in srcs], 1)
+        # the sine embedding of an unpadded map is batch independent (an expanded [1,...] tensor): keep it [1,S,C]
+        pos_embeds = [p[:1] if p.shape[0] > 1 and p.stride(0) == 0 else p for p in pos_embeds]
         lvl_pos = torch.cat([p.permute(0, 2, 3, 1).flatten(1, 2) + self.level_embed[i].view(1, 1, -1)
                              for i, p in enumerate(pos_embeds)], 1)
         memory = self.encoder(src_flatten, spatial_shapes, level_start_index, None, lvl_pos, None,
@@ -303,7 +319,7 @@ class MSDeformAttnPixelDecoder(nn.Module):
     def _forward_features(self, features):
         srcs, pos = [], []
         for idx, f in enumerate(self.transformer_in_features[::-1]):
-            x = features[f].float().contiguous(memory_format=torch.channels_last)
+            x = features[f].float()
             proj = self.input_proj[idx]
             srcs.append(ops.group_norm_cl(conv1x1_tokens(x, proj[0]), proj[1]))
             pos.append(self.pe_layer(x))
@@ -316,15 +332,17 @@ class MSDeformAttnPixelDecoder(nn.Module):
             start += h * w
             out.append(z.transpose(1, 2).reshape(bs, -1, h, w))   # logical NCHW, channels-last memory
         for idx, f in enumerate(self.in_features[:self.num_fpn_levels][::-1]):
-            x = features[f].float().contiguous(memory_format=torch.channels_last)
+            x = features[f].float()
             lateral = self.lateral_convs[idx]
             cur_fpn = lateral.norm_act(conv1x1_tokens(x, lateral))
-            # keep the whole FPN stage channels-last (the upsampled map would otherwise come back NCHW and
-            # force layout copies of the 256x256 maps around the 3x3 convolution)
-            up = F.interpolate(out[-1].contiguous(memory_format=torch.channels_last), size=cur_fpn.shape[-2:],
-                               mode="bilinear", align_corners=False)
             # cuDNN's fp32 3x3 convolution is ~7x slower on NHWC maps (46 ms vs 6.5 ms forward at [16,256,256,256],
-            # profiles/README.md r1p): hand the sum over in NCHW; the GroupNorm+ReLU behind it returns to tokens.
-            out.append(self.output_convs[idx]((cur_fpn + up).contiguous()))
+            # profiles/README.md r1p): the sum is handed over in NCHW -- written that way by the fused
+            # upsample+add kernel -- and the GroupNorm+ReLU behind the convolution returns to channels-last tokens.
+            prev = out[-1].contiguous(memory_format=torch.channels_last)
+            y = ops.upsample2x_add_to_nchw(cur_fpn, prev)
+            if y is None:
+                up = F.interpolate(prev, size=cur_fpn.shape[-2:], mode="bilinear", align_corners=False)
+                y = (cur_fpn + up).contiguous()
+            out.append(self.output_convs[idx](y))
         multi_scale_features = out[:self.maskformer_num_feature_levels]
         return conv1x1_tokens(out[-1], self.mask_features), out[0], multi_scale_features

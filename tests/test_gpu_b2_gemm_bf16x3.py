@@ -127,3 +127,21 @@ def test_gemm_tn_matches_fp64(T, M, N, batch, splits):
     if batch == 1:
         y2 = native.matmul_tn(a[0], b[0])
         assert (y2.double() - r[0]).abs().max().item() / T ** 0.5 < TOL
+
+
+@pytest.mark.parametrize("T,M,N,batch", [(120, 4096, 256, 2), (100, 1000, 64, 3), (37, 300, 128, 1)])
+def test_gemm_tn_accumulate_into(T, M, N, batch):
+    """TMA reduce-add epilogue: C += A^T B (sum over the prediction heads of the mask-feature gradient, ragged M tail
+    included -- out-of-range rows of the last tile must not be added anywhere)."""
+    g = torch.Generator(device=DEV).manual_seed(T + M + N)
+    acc = torch.randn(batch, M, N, device=DEV, generator=g)
+    ref = acc.double().clone()
+    for i in range(3):
+        a = torch.randn(batch, T, M, device=DEV, generator=g)
+        b = torch.randn(batch, T, N, device=DEV, generator=g)
+        out = native.gemm_tn(a, b, accumulate_into=acc)
+        assert out.data_ptr() == acc.data_ptr()
+        ref += a.double().transpose(1, 2) @ b.double()
+    assert (acc.double() - ref).abs().max().item() / (3 * T) ** 0.5 < TOL
+    with pytest.raises(RuntimeError):
+        native.gemm_tn(a, b, accumulate_into=acc[:, :, : N // 2])

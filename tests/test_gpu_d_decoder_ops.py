@@ -245,3 +245,107 @@ def test_group_norm_channels_last(B, C, H, W, G, relu):
     assert rel(x.grad, xr.grad) < 2e-5
     for a, b in ((gn.weight.grad, wr.grad), (gn.bias.grad, br.grad)):
         assert (a.double() - b).abs().max().item() / max(1.0, b.abs().max().item()) < 2e-5
+
+
+@pytest.mark.parametrize("B,C,H,W,G,relu", [(2, 256, 64, 64, 32, True), (2, 128, 48, 80, 32, False), (3, 64, 18, 12, 16, True),
+                                            (1, 256, 256, 256, 32, True)])
+def test_group_norm_nchw_to_channels_last(B, C, H, W, G, relu):
+    """GroupNorm (+ReLU) reading the NCHW convolution output and writing channels-last tokens, vs torch in fp64
+    (ref pixel_decoder/msdeformattn.py:262-275)."""
+    g = torch.Generator(device=DEV).manual_seed(B + C + H + W)
+    x = (torch.randn(B, C, H, W, device=DEV, generator=g) * 1.5 + 0.7).requires_grad_(True)
+    gn = torch.nn.GroupNorm(G, C).to(DEV)
+    with torch.no_grad():
+        gn.weight.copy_(torch.randn(C, device=DEV, generator=g))
+        gn.bias.copy_(torch.randn(C, device=DEV, generator=g) * 0.3)
+    y = ops.group_norm_nchw_to_cl(x, gn, relu=relu)
+    assert y is not None and y.shape == x.shape and y.permute(0, 2, 3, 1).is_contiguous()
+    gy = torch.randn(B, C, H, W, device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    y.backward(gy)
+    assert x.grad.is_contiguous()
+    xr = x.detach().double().requires_grad_(True)
+    wr, br = gn.weight.detach().double().requires_grad_(True), gn.bias.detach().double().requires_grad_(True)
+    yr = F.group_norm(xr, G, wr, br, gn.eps)
+    if relu:
+        assert ((yr > 0) != (y > 0)).float().mean().item() < 1e-4
+        yr = yr * (y.detach() > 0)
+    yr.backward(gy.double())
+    assert rel(y, yr) < 1e-5
+    assert rel(x.grad, xr.grad) < 2e-5
+    for a, b in ((gn.weight.grad, wr.grad), (gn.bias.grad, br.grad)):
+        assert (a.double() - b).abs().max().item() / max(1.0, b.abs().max().item()) < 2e-5
+    # geometry outside the kernel's cover -> None (the caller falls back to the library op)
+    assert ops.group_norm_nchw_to_cl(torch.randn(1, 96, 5, 5, device=DEV), torch.nn.GroupNorm(32, 96).to(DEV)) is None
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 64, 8, 8), (1, 128, 34, 52), (2, 256, 64, 160), (1, 64, 2, 4), (1, 256, 256, 256)])
+def test_upsample2x_add_to_nchw(B, C, H, W):
+    """cur + bilinear x2 upsample(prev) (ref pixel_decoder/msdeformattn.py:349) as one CL,CL -> NCHW kernel, and its
+    backward (transposition for cur, adjoint of the resize for prev) vs torch in fp64."""
+    g = torch.Generator(device=DEV).manual_seed(B + C + H + W)
+    cur = torch.randn(B, C, H, W, device=DEV, generator=g).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    prev = torch.randn(B, C, H // 2, W // 2, device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    prev.requires_grad_(True)
+    y = ops.upsample2x_add_to_nchw(cur, prev)
+    assert y is not None and y.is_contiguous() and y.shape == cur.shape
+    ref32 = cur.detach() + F.interpolate(prev.detach(), size=(H, W), mode="bilinear", align_corners=False)
+    assert (y.detach() - ref32).abs().max().item() < 2e-6          # same association as ATen: last-ulp agreement
+    gy = torch.randn(B, C, H, W, device=DEV, generator=g)
+    y.backward(gy)
+    cr, pr = cur.detach().double().requires_grad_(True), prev.detach().double().requires_grad_(True)
+    yr = cr + F.interpolate(pr, size=(H, W), mode="bilinear", align_corners=False)
+    yr.backward(gy.double())
+    assert rel(y, yr) < 1e-6
+    assert rel(cur.grad, cr.grad) < 1e-6
+    assert rel(prev.grad, pr.grad) < 1e-5
+    assert ops.upsample2x_add_to_nchw(cur, torch.randn(B, C, H // 2 + 1, W // 2, device=DEV)) is None
+
+
+def test_mask_feature_gradient_fanout_accumulates_in_the_epilogue():
+    """ops.grad_fanout: the gradients the prediction heads send to mask_features are added inside the GEMM epilogue;
+    result equals the plain autograd sum."""
+    g = torch.Generator(device=DEV).manual_seed(5)
+    B, Q, C, H, W = 2, 24, 64, 16, 24
+    mf = torch.randn(B, C, H, W, device=DEV, generator=g).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    embeds = [torch.randn(B, Q, C, device=DEV, generator=g).requires_grad_(True) for _ in range(4)]
+    gouts = [torch.randn(B, Q, H, W, device=DEV, generator=g) for _ in range(4)]
+    aliases, shared = ops.grad_fanout(mf, 4)
+    loss = sum((ops.mask_logits(e, a, shared) * go).sum() for e, a, go in zip(embeds[:3], aliases, gouts))
+    loss = loss + (aliases[3] * 0.5).sum()                         # a consumer outside the protocol
+    loss.backward()
+    got, got_e = mf.grad.clone(), [e.grad.clone() for e in embeds[:3]]
+    mf.grad = None
+    for e in embeds:
+        e.grad = None
+    loss = sum((ops.mask_logits(e, mf) * go).sum() for e, go in zip(embeds[:3], gouts)) + (mf * 0.5).sum()
+    loss.backward()
+    assert rel(got, mf.grad) < TOL
+    for a, e in zip(got_e, embeds[:3]):
+        assert rel(a, e.grad) < TOL
+    assert shared.buf is None
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W,bias", [(2, 256, 256, 32, 32, False), (2, 96, 256, 18, 20, True),
+                                                 (1, 2048, 256, 16, 8, True), (3, 512, 128, 12, 12, False)])
+def test_conv1x1_nchw_to_channels_last(B, Cin, Cout, H, W, bias):
+    """1x1 convolution of an NCHW backbone map into channels-last tokens without a layout copy (the map is the
+    MN-major operand of the TN GEMM; ref pixel_decoder/msdeformattn.py:216-219, :262), forward and all gradients."""
+    g = torch.Generator(device=DEV).manual_seed(B + Cin + H)
+    x = torch.randn(B, Cin, H, W, device=DEV, generator=g).requires_grad_(True)
+    w = (torch.randn(Cout, Cin, 1, 1, device=DEV, generator=g) / Cin ** 0.5).requires_grad_(True)
+    b = torch.randn(Cout, device=DEV, generator=g).requires_grad_(True) if bias else None
+    y = ops.conv1x1_nchw_to_cl(x, w, b)
+    assert y is not None and y.shape == (B, Cout, H, W) and y.permute(0, 2, 3, 1).is_contiguous()
+    gy = torch.randn(B, Cout, H, W, device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    y.backward(gy)
+    xr, wr = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True)
+    br = b.detach().double().requires_grad_(True) if bias else None
+    yr = F.conv2d(xr, wr, br)
+    yr.backward(gy.double())
+    assert rel(y, yr) < TOL
+    assert rel(x.grad, xr.grad) < TOL and x.grad.is_contiguous()
+    assert (w.grad.double() - wr.grad).abs().max().item() / (B * H * W) ** 0.5 < TOL
+    if bias:
+        assert (b.grad.double() - br.grad).abs().max().item() / (B * H * W) ** 0.5 < TOL
+    # channels-last or tiny inputs are not this op's business
+    assert ops.conv1x1_nchw_to_cl(torch.randn(1, 64, 4, 4, device=DEV), w[:, :64]) is None

@@ -62,7 +62,7 @@ def install_cpu_ops(setattr_fn):
     setattr_fn(ops, "ffn", lambda x, w1, b1, w2, b2: F.linear(F.relu(F.linear(x, w1, b1)), w2, b2))
     setattr_fn(ops, "add_layer_norm", lambda x, r, norm: norm(x if r is None else x + r))
     setattr_fn(ops, "group_norm_cl", lambda x, gn, relu=False: F.relu(gn(x)) if relu else gn(x))
-    setattr_fn(ops, "mask_logits", lambda e, f: torch.einsum("bqc,bchw->bqhw", e, f))
+    setattr_fn(ops, "mask_logits", lambda e, f, shared=None: torch.einsum("bqc,bchw->bqhw", e, f))
     setattr_fn(native, "attn_mask_bits", attn_mask_bits)
     setattr_fn(native, "pack_bool_bits", cpu_pack_bits)
     setattr_fn(native, "gt_mask_area_bits", lambda masks, size: cpu_pack_bits(
