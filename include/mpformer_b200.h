@@ -214,8 +214,9 @@ int mpf_gemm_bf16x3_tn_ex(const float* A, long long lda, long long a_batch_strid
  *     r may be NULL), also writing the per-row mean and 1/sqrt(var + eps) for the backward.
  *     ref: pixel_decoder/msdeformattn.py:125-126,129 (norm1 / norm2 of the encoder layer), decoder :52,:112,:169.
  *   mpf_add_layernorm_bwd_f32:  dx (= gradient of both x and r) and per-CTA partial sums
- *     partial[p][0][c] = sum dy*xhat, partial[p][1][c] = sum dy  for p < mpf_add_layernorm_partials(rows)
- *     (the caller adds the partials: dgamma, dbeta).
+ *     partial[p][0][c] = sum dy*xhat, partial[p][1][c] = sum dy, partial[p][2][c] = sum dx
+ *     for p < mpf_add_layernorm_partials(rows)  (the caller adds the partials: dgamma, dbeta, and the bias
+ *     gradient of the Linear layer that produced r).
  *   mpf_colsum_f32:  out[c] = sum_rows x[row*ld + c]  (bias gradients of the Linear layers; out is zeroed here).
  * ------------------------------------------------------------------------------------------- */
 int mpf_add_layernorm_partials(long long rows);

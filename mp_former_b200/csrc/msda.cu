@@ -316,55 +316,69 @@ msda_bwd_vec_kernel(const float* __restrict__ grad_out, const float* __restrict_
 // ms_deform_attn.py:102-109) happen in the descriptor builder instead of five elementwise passes, two
 // slicing copies and their backward counterparts.
 // ------------------------------------------------------------------------------------------------
-constexpr int kMaxLP = 16;     // L*P of the fused path (L <= 4, P = 4)
+constexpr int kMaxEncLevels = 4;
+constexpr int kMaxLP = 4 * kMaxEncLevels;     // L*P of the fused path (L <= 4, P = 4)
 
 struct EncSamples {
-  long long obase[2];          // offset of (b, q, 0) in ow, or -1 if padding
-  long long rbase[2];          // offset of (b or 0, q, 0, 0) in ref
+  int q[2];                    // query of slot (threadIdx.x + k * kThreads) >> 2, or -1 if padding
   float2 off[2], ref[2];
 };
 
-__device__ __forceinline__ void enc_samples_init(EncSamples& es, const MsdaTiling& tiling, int chunk, int b, int Lq,
-                                                 int owc, int L, long long ref_bstride) {
+__device__ __forceinline__ void enc_samples_init(EncSamples& es, const MsdaTiling& tiling, int chunk, int Lq) {
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
     const int idx = threadIdx.x + k * kThreads;
-    const int q = query_of(tiling, chunk, idx >> 2, Lq);
-    es.obase[k] = q >= 0 ? (static_cast<long long>(b) * Lq + q) * owc : -1;
-    es.rbase[k] = q >= 0 ? b * ref_bstride + static_cast<long long>(q) * L * 2 : 0;
+    es.q[k] = query_of(tiling, chunk, idx >> 2, Lq);
     es.off[k] = es.ref[k] = make_float2(0.f, 0.f);
   }
 }
 
-__device__ __forceinline__ void enc_samples_fetch(EncSamples& es, const float* __restrict__ ow,
-                                                  const float* __restrict__ ref, int m, int LP, int l) {
+// ow_b / ref_b: this image's slices of ow [Lq, owc] and ref [Lq, L, 2]
+__device__ __forceinline__ void enc_samples_fetch(EncSamples& es, const float* __restrict__ ow_b,
+                                                  const float* __restrict__ ref_b, int m, int L, int owc, int l) {
+  const int LP = L * 4;
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
-    if (es.obase[k] >= 0) {
+    if (es.q[k] >= 0) {
       const int p = (threadIdx.x + k * kThreads) & 3;
-      es.off[k] = __ldg(reinterpret_cast<const float2*>(ow + es.obase[k] + (m * LP + l * 4 + p) * 2));
-      es.ref[k] = __ldg(reinterpret_cast<const float2*>(ref + es.rbase[k] + l * 2));
+      es.off[k] = __ldg(reinterpret_cast<const float2*>(ow_b + static_cast<size_t>(es.q[k]) * owc +
+                                                        (m * LP + l * 4 + p) * 2));
+      es.ref[k] = __ldg(reinterpret_cast<const float2*>(ref_b + (static_cast<size_t>(es.q[k]) * L + l) * 2));
     }
   }
 }
 
-// softmax over the item's L*P logits -> s_aw[item][LP]   (threads 0..127, one item each)
-__device__ __forceinline__ void enc_softmax(float* s_aw, const float* __restrict__ ow, const MsdaTiling& tiling,
-                                            int chunk, int b, int m, int M, int Lq, int owc, int LP) {
-  if (threadIdx.x < kChunkQ) {
-    const int j = threadIdx.x;
-    const int q = query_of(tiling, chunk, j, Lq);
-    if (q >= 0) {
-      const float* lg = ow + (static_cast<long long>(b) * Lq + q) * owc + M * LP * 2 + m * LP;
-      float v[kMaxLP];
-      float mx = -INFINITY;
-#pragma unroll 4
-      for (int i = 0; i < LP; ++i) { v[i] = __ldg(lg + i); mx = fmaxf(mx, v[i]); }
-      float sum = 0.f;
-#pragma unroll 4
-      for (int i = 0; i < LP; ++i) { v[i] = expf(v[i] - mx); sum += v[i]; }
-#pragma unroll 4
-      for (int i = 0; i < LP; ++i) s_aw[j * kMaxLP + i] = v[i] / sum;
+// softmax over each item's L*P logits -> s_aw[item][LP].  The four lanes that own an item's four points hold the
+// logits of one point each (one per level, L <= 4) and combine maximum and sum with two shuffles.
+__device__ __forceinline__ void enc_softmax(float* s_aw, const EncSamples& es, const float* __restrict__ ow_b, int m,
+                                            int M, int L, int owc) {
+  const int LP = L * 4;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int idx = threadIdx.x + k * kThreads;
+    const int j = idx >> 2, p = idx & 3;
+    float v[kMaxEncLevels];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int l = 0; l < kMaxEncLevels; ++l) {
+      v[l] = -INFINITY;
+      if (l < L && es.q[k] >= 0) v[l] = __ldg(ow_b + static_cast<size_t>(es.q[k]) * owc + M * LP * 2 + m * LP + l * 4 + p);
+      mx = fmaxf(mx, v[l]);
+    }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    float sum = 0.f;
+#pragma unroll
+    for (int l = 0; l < kMaxEncLevels; ++l) {
+      v[l] = (l < L && es.q[k] >= 0) ? expf(v[l] - mx) : 0.f;
+      sum += v[l];
+    }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    if (es.q[k] >= 0) {
+#pragma unroll
+      for (int l = 0; l < kMaxEncLevels; ++l)
+        if (l < L) s_aw[j * kMaxLP + l * 4 + p] = v[l] / sum;
     }
   }
 }
@@ -378,7 +392,7 @@ __device__ __forceinline__ void enc_build_descriptors(int4* so, float4* sw, cons
     const int j = idx >> 2, p = idx & 3;
     int4 offs = make_int4(-1, -1, -1, -1);
     float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (es.obase[k] >= 0) {
+    if (es.q[k] >= 0) {
       const float a = s_aw[j * kMaxLP + l * 4 + p];
       // loc = ref + off / (W, H), then pixel = loc * size - 0.5: the reference's operation order
       const float lx = es.ref[k].x + __fdiv_rn(es.off[k].x, static_cast<float>(W));
@@ -412,7 +426,7 @@ __device__ __forceinline__ void enc_build_descriptors(int4* so, float4* sw, cons
 }
 
 template <int LPI>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, LPI <= 8 ? 4 : 3)      // D <= 32: 64 registers without spilling
 msda_enc_fwd_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lstart, const float* __restrict__ ow, const float* __restrict__ ref,
                     long long ref_bstride, int S, int M, int L, int Lq, float* __restrict__ out,
@@ -428,22 +442,24 @@ msda_enc_fwd_kernel(const float* __restrict__ value, const int64_t* __restrict__
   const int slot = threadIdx.x / LPI, li = threadIdx.x % LPI;
   const int MD = M * D, LP = L * 4, owc = M * LP * 3;
   const float* vimg = value + static_cast<size_t>(b) * S * MD + m * D + li * 4;
+  const float* ow_b = ow + static_cast<size_t>(b) * Lq * owc;
+  const float* ref_b = ref + b * ref_bstride;
 
   float4 acc[ITERS];
 #pragma unroll
   for (int it = 0; it < ITERS; ++it) acc[it] = make_float4(0.f, 0.f, 0.f, 0.f);
 
   EncSamples es;
-  enc_samples_init(es, tiling, chunk, b, Lq, owc, L, ref_bstride);
-  enc_samples_fetch(es, ow, ref, m, LP, 0);
-  enc_softmax(s_aw, ow, tiling, chunk, b, m, M, Lq, owc, LP);
+  enc_samples_init(es, tiling, chunk, Lq);
+  enc_samples_fetch(es, ow_b, ref_b, m, L, owc, 0);
+  enc_softmax(s_aw, es, ow_b, m, M, L, owc);
   __syncthreads();
   for (int l = 0; l < L; ++l) {
     const int H = static_cast<int>(shapes[2 * l]), W = static_cast<int>(shapes[2 * l + 1]);
     const float* vl = vimg + static_cast<size_t>(lstart[l]) * MD;
     if (l > 0) __syncthreads();
     enc_build_descriptors<false>(so, sw, es, s_aw, l, H, W, MD);
-    if (l + 1 < L) enc_samples_fetch(es, ow, ref, m, LP, l + 1);
+    if (l + 1 < L) enc_samples_fetch(es, ow_b, ref_b, m, L, owc, l + 1);
     __syncthreads();
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -505,10 +521,12 @@ msda_enc_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict_
                    : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 
+  const float* ow_b = ow + static_cast<size_t>(b) * Lq * owc;
+  const float* ref_b = ref + b * ref_bstride;
   EncSamples es;
-  enc_samples_init(es, tiling, chunk, b, Lq, owc, L, ref_bstride);
-  enc_samples_fetch(es, ow, ref, m, LP, 0);
-  enc_softmax(s_aw, ow, tiling, chunk, b, m, M, Lq, owc, LP);
+  enc_samples_init(es, tiling, chunk, Lq);
+  enc_samples_fetch(es, ow_b, ref_b, m, L, owc, 0);
+  enc_softmax(s_aw, es, ow_b, m, M, L, owc);
   __syncthreads();
   for (int l = 0; l < L; ++l) {
     const int H = static_cast<int>(shapes[2 * l]), W = static_cast<int>(shapes[2 * l + 1]);
@@ -517,7 +535,7 @@ msda_enc_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict_
     float* gvl = gvimg + loff;
     if (l > 0) __syncthreads();
     enc_build_descriptors<true>(so, sw, es, s_aw, l, H, W, MD);
-    if (l + 1 < L) enc_samples_fetch(es, ow, ref, m, LP, l + 1);
+    if (l + 1 < L) enc_samples_fetch(es, ow_b, ref_b, m, L, owc, l + 1);
     __syncthreads();
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll

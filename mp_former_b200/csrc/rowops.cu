@@ -77,7 +77,8 @@ add_layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ 
 }
 
 // dx = rstd * (g - mean_c(g) - xhat * mean_c(g * xhat)),  g = dy * gamma,  xhat = (x + r - mean) * rstd
-// partial[blockIdx.x][0][c] = sum over this CTA's rows of dy * xhat, partial[blockIdx.x][1][c] = sum of dy.
+// partial[blockIdx.x][0][c] = sum over this CTA's rows of dy * xhat, [1][c] = sum of dy, [2][c] = sum of dx (the bias
+// gradient of the Linear layer that produced the normalised sum's second addend).
 template <int VPT>
 __global__ void __launch_bounds__(kRowThreads)
 add_layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ r,
@@ -85,16 +86,17 @@ add_layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__
                          const float* __restrict__ rstd_in, long long rows, float* __restrict__ dx,
                          float* __restrict__ partial) {
   constexpr int C = 128 * VPT;
-  __shared__ float4 red[kRowWarps][2 * VPT][32];
+  __shared__ float4 red[kRowWarps][VPT][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const long long warp0 = static_cast<long long>(blockIdx.x) * kRowWarps + w;
   const long long nwarps = static_cast<long long>(gridDim.x) * kRowWarps;
-  float4 gm[VPT], dg[VPT], db[VPT];
+  float4 gm[VPT], dg[VPT], db[VPT], ds[VPT];
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
     gm[i] = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
     dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ds[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (long long row = warp0; row < rows; row += nwarps) {
     const float mean = __ldg(mean_in + row), rstd = __ldg(rstd_in + row);
@@ -125,26 +127,26 @@ add_layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__
       o.z = rstd * (g[i].z - m1 - xh[i].z * m2);
       o.w = rstd * (g[i].w - m1 - xh[i].w * m2);
       dr[i * 32 + lane] = o;
+      ds[i].x += o.x; ds[i].y += o.y; ds[i].z += o.z; ds[i].w += o.w;
     }
   }
+  // three rounds through one [warps][VPT][32] staging array: dgamma, dbeta, column sums of dx
 #pragma unroll
-  for (int i = 0; i < VPT; ++i) {
-    red[w][i][lane] = dg[i];
-    red[w][VPT + i][lane] = db[i];
-  }
-  __syncthreads();
-  // 2 * VPT * 32 float4 slots per CTA, summed over the 8 warps
-  for (int slot = threadIdx.x; slot < 2 * VPT * 32; slot += kRowThreads) {
-    const int i = slot >> 5, l = slot & 31;
-    float4 a = red[0][i][l];
+  for (int which = 0; which < 3; ++which) {
+    if (which) __syncthreads();
 #pragma unroll
-    for (int ww = 1; ww < kRowWarps; ++ww) {
-      const float4 b = red[ww][i][l];
-      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    for (int i = 0; i < VPT; ++i) red[w][i][lane] = which == 0 ? dg[i] : (which == 1 ? db[i] : ds[i]);
+    __syncthreads();
+    for (int slot = threadIdx.x; slot < VPT * 32; slot += kRowThreads) {
+      const int i = slot >> 5, l = slot & 31;
+      float4 a = red[0][i][l];
+#pragma unroll
+      for (int ww = 1; ww < kRowWarps; ++ww) {
+        const float4 b = red[ww][i][l];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      reinterpret_cast<float4*>(partial + (static_cast<long long>(blockIdx.x) * 3 + which) * C)[i * 32 + l] = a;
     }
-    // layout [block][2][C]: i < VPT -> dgamma chunk i, else dbeta chunk i - VPT
-    const int which = i / VPT, chunk = i % VPT;
-    reinterpret_cast<float4*>(partial + (static_cast<long long>(blockIdx.x) * 2 + which) * C)[chunk * 32 + l] = a;
   }
 }
 
@@ -160,11 +162,27 @@ colsum_kernel(const float* __restrict__ x, long long rows, int C, long long ld, 
   const int cchunk = t % chunks, phase = t / chunks;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (phase < rpb) {
-    for (long long row = static_cast<long long>(blockIdx.x) * rpb + phase; row < rows;
-         row += static_cast<long long>(gridDim.x) * rpb) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(x + row * ld) + cchunk);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    const long long step = static_cast<long long>(gridDim.x) * rpb;
+    long long row = static_cast<long long>(blockIdx.x) * rpb + phase;
+    // four independent 16-byte loads in flight per thread (a single dependent load chain reaches ~half of HBM)
+    float4 a4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (; row + 3 * step < rows; row += 4 * step) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(x + (row + u * step) * ld) + cchunk);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { a4[u].x += v[u].x; a4[u].y += v[u].y; a4[u].z += v[u].z; a4[u].w += v[u].w; }
     }
+    for (; row < rows; row += step) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + row * ld) + cchunk);
+      a4[0].x += v.x; a4[0].y += v.y; a4[0].z += v.z; a4[0].w += v.w;
+    }
+    acc.x = (a4[0].x + a4[1].x) + (a4[2].x + a4[3].x);
+    acc.y = (a4[0].y + a4[1].y) + (a4[2].y + a4[3].y);
+    acc.z = (a4[0].z + a4[1].z) + (a4[2].z + a4[3].z);
+    acc.w = (a4[0].w + a4[1].w) + (a4[2].w + a4[3].w);
   }
   sh[t] = acc;
   __syncthreads();

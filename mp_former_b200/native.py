@@ -223,8 +223,8 @@ def add_layernorm_fwd(x, r, gamma, beta, eps):
     return y.view(x.shape), mean, rstd
 
 
-def add_layernorm_bwd(dy, x, r, gamma, mean, rstd):
-    """-> (dx, dgamma, dbeta); dx is the gradient of both x and r."""
+def add_layernorm_bwd(dy, x, r, gamma, mean, rstd, with_colsum=False):
+    """-> (dx, dgamma, dbeta[, colsum(dx)]); dx is the gradient of both x and r."""
     C = x.shape[-1]
     dy2 = _f32c(dy, "dy").reshape(-1, C)
     if not dy2.is_contiguous():
@@ -238,13 +238,15 @@ def add_layernorm_bwd(dy, x, r, gamma, mean, rstd):
     rows = x2.shape[0]
     lib = _lib.load()
     dx = torch.empty_like(x2)
-    partial = torch.empty((lib.mpf_add_layernorm_partials(rows), 2, C), dtype=torch.float32, device=x.device)
+    partial = torch.empty((lib.mpf_add_layernorm_partials(rows), 3, C), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         rc = lib.mpf_add_layernorm_bwd_f32(dy2.data_ptr(), x2.data_ptr(), None if r2 is None else r2.data_ptr(),
                                            gamma.contiguous().data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, C,
                                            dx.data_ptr(), partial.data_ptr(), _stream())
     _lib.check(rc, "add_layernorm_bwd")
     dgb = partial.sum(0)
+    if with_colsum:
+        return dx.view(x.shape), dgb[0], dgb[1], dgb[2]
     return dx.view(x.shape), dgb[0], dgb[1]
 
 

@@ -359,8 +359,8 @@ class _EncoderLayer(torch.autograd.Function):
             return native.split_b(w.t().contiguous())
 
         # FFN block
-        dsum2, dg2, db2 = native.add_layernorm_bwd(g_out.reshape(B * S, C), src1, y, g2, mean2, rstd2)
-        gb2 = native.colsum(dsum2)
+        dsum2, dg2, db2, gb2 = native.add_layernorm_bwd(g_out.reshape(B * S, C), src1, y, g2, mean2, rstd2,
+                                                        with_colsum=True)          # colsum(dx) = bias gradient of W2
         w2t_hi, w2t_lo = t_halves(w2)
         gh = native.gemm_general(dsum2, w2t_hi, b_lo=w2t_lo, gate=hidden)            # ReLU mask in the epilogue
         gw2 = native.matmul_tn(dsum2, hidden)
@@ -370,8 +370,7 @@ class _EncoderLayer(torch.autograd.Function):
         gb1 = native.colsum(gh)
         del gh
         # attention block
-        dsum1, dg1, db1 = native.add_layernorm_bwd(g_src1, x2, proj, g1, mean1, rstd1)
-        gbo = native.colsum(dsum1)
+        dsum1, dg1, db1, gbo = native.add_layernorm_bwd(g_src1, x2, proj, g1, mean1, rstd1, with_colsum=True)
         wot_hi, wot_lo = t_halves(wo)
         g_attn = native.gemm(dsum1, wot_hi, wot_lo)
         gwo = native.matmul_tn(dsum1, attn.view(B * S, C))
@@ -656,6 +655,18 @@ class _MaskedCrossAttention(torch.autograd.Function):
         return g_qin, g_mem, g_pos, g_win, g_bin, g_wout, g_bout, None, None, None
 
 
+_TAIL_BITS = {}
+
+
+def _tail_bits(n_keys, words, device):
+    """int32 [words]: bit k of the row set iff key k >= n_keys (the mask of a row that attends to all real keys)."""
+    key = (n_keys, words, str(device))
+    if key not in _TAIL_BITS:
+        k = torch.arange(words * 32, device=device)
+        _TAIL_BITS[key] = native.pack_bool_bits((k >= n_keys)[None, None])[0, 0, :words].contiguous()
+    return _TAIL_BITS[key]
+
+
 def masked_cross_attention(q_in, memory, pos, w_in, b_in, w_out, b_out, nhead, mask):
     """softmax((q Wq)(k Wk)^T / sqrt(hd) + mask) (v Wv) Wo with k = memory + pos, v = memory
     (ref decoder :100-112 through nn.MultiheadAttention); a row that is entirely masked attends to
@@ -670,11 +681,21 @@ def masked_cross_attention(q_in, memory, pos, w_in, b_in, w_out, b_out, nhead, m
         bits, n_keys = mask.bits, mask.n_keys
     else:
         bits, n_keys = native.pack_bool_bits(mask), mask.shape[-1]
-    if n_keys != HW or E // nhead != 32 or HW % 4 != 0:
+    if n_keys != HW or E // nhead != 32:
         raise RuntimeError(f"masked_cross_attention: unsupported geometry (keys {n_keys} vs memory {HW}, "
-                           f"head_dim {E // nhead}; the kernel needs head_dim 32 and HW % 4 == 0)")
+                           f"head_dim {E // nhead}; the kernel needs head_dim 32)")
     if pos.dim() == 3 and pos.shape[0] != 1:
         pos = pos[:1]
+    if HW % 4 != 0:
+        # The TMA row stride of V^T [B, E, HW] must be a multiple of 16 bytes: append up to three zero keys.  Every
+        # mask producer already sets the bits of keys >= HW, so ordinary rows never see them; a row whose real keys
+        # are ALL masked attends to every real key (ref decoder :1780) -- its mask becomes "padding keys only"
+        # here instead of the kernel's row_open flag, which would let the padding in.
+        pad = (-HW) % 4
+        memory = F.pad(memory, (0, 0, 0, pad))
+        pos = F.pad(pos, (0, 0, 0, pad))
+        all_masked = (bits == -1).all(-1, keepdim=True)
+        bits = torch.where(all_masked, _tail_bits(HW, bits.shape[-1], bits.device), bits)
     return _MaskedCrossAttention.apply(q_in.contiguous(), memory.contiguous(), pos.contiguous(), w_in, b_in,
                                        w_out, b_out, nhead, bits, n_keys)
 

@@ -71,8 +71,9 @@ def torch_xattn(q_in, memory, pos, w_in, b_in, w_out, b_out, nhead, mask, dtype=
 
 
 @pytest.mark.parametrize("B,Qt,HW", [(2, 100, 1024), (1, 130, 256), (3, 10, 4), (2, 37, 100), (1, 128, 64),
-                                     (2, 120, 4096)])
+                                     (2, 120, 4096), (2, 37, 475), (1, 220, 950), (1, 9, 63), (2, 300, 2048)])
 def test_masked_cross_attention_forward_backward(B, Qt, HW):
+    """HW % 4 != 0 (19x25, 25x38 maps of images padded to multiples of 32): keys are padded inside the op."""
     E, nhead = 256, 8
     g = torch.Generator(device=DEV).manual_seed(B * 1000 + Qt + HW)
     rn = lambda *s, sc=1.0: torch.randn(*s, device=DEV, generator=g) * sc
@@ -206,6 +207,14 @@ def test_add_layer_norm_forward_backward(shape, with_r):
         assert torch.equal(r.grad, x.grad)
     for a, b in ((norm.weight.grad, wr.grad), (norm.bias.grad, br.grad)):
         assert (a.double() - b).abs().max().item() / max(1.0, b.abs().max().item()) < 1e-5
+    # the backward kernel also returns the column sums of dx (bias gradient of the Linear that produced r)
+    with torch.no_grad():
+        _, mean, rstd = native.add_layernorm_fwd(x.detach(), None if r is None else r.detach(), norm.weight, norm.bias,
+                                                 norm.eps)
+        dx, _, _, cs = native.add_layernorm_bwd(gy, x.detach(), None if r is None else r.detach(), norm.weight, mean,
+                                                rstd, with_colsum=True)
+    ref_cs = xr.grad.reshape(-1, C).sum(0)
+    assert (cs.double() - ref_cs).abs().max().item() / max(1.0, ref_cs.abs().max().item()) < 1e-5
 
 
 @pytest.mark.parametrize("rows,C,ld", [(344064, 256, 256), (5000, 1024, 1024), (4096, 288, 288), (3000, 100, 256),

@@ -1,0 +1,84 @@
+"""-m gpu: the geometries of BASELINE.json configs[3] (Swin-L panoptic: backbone channels 192/384/768/1536,
+200 queries, 133 classes) and configs[4] (Cityscapes 1024x2048: non-square maps, S = 43008 encoder tokens, key
+lengths 2048 / 8192 / 32768, 8 classes) through the product modules vs the CPU oracle, one image each.
+
+The layer counts are cut (2 encoder / 3 decoder layers) so that the CPU oracle finishes in seconds and so that the
+discrete attention masks -- a logit within float noise of the threshold flips a key on or off, and nine layers
+compound such flips -- leave the final prediction comparable: the kernels' geometry handling is what is under test.
+Pixel decoder (no discrete stage) and the first prediction head: 1e-3 * max(1, |ref|) everywhere; later heads:
+median and 98th-percentile bounds."""
+import pytest
+import torch
+
+from mp_former_b200 import workload
+from mp_former_b200.masked_decoder import MultiScaleMaskedTransformerDecoderMaskDN
+from mp_former_b200.pixel_decoder import MSDeformAttnPixelDecoder, ShapeSpec
+from oracle import torch_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+CONFIGS = {
+    # name: (backbone, H, W, queries, classes, with DN group)
+    "swin_l_panoptic_q200": ("swin_l", 512, 512, 200, 133, True),
+    "cityscapes_1024x2048": ("r50", 1024, 2048, 100, 8, False),
+    "odd_sized_608x800": ("r50", 608, 800, 100, 80, True),          # maps 19x25 / 38x50 / 76x100 / 152x200
+}
+
+
+def relerr(a, b):
+    return (a.double() - b.double()).abs() / b.double().abs().clamp(min=1.0)
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_config_geometry_vs_oracle(name):
+    backbone, H, W, Q, K, dn = CONFIGS[name]
+    torch.manual_seed(7)
+    ch = workload.BACKBONE_CHANNELS[backbone]
+    shape = {k: ShapeSpec(channels=ch[k], stride=workload.STRIDES[k]) for k in ch}
+    pd = MSDeformAttnPixelDecoder(shape, transformer_dropout=0.0, transformer_nheads=8, transformer_dim_feedforward=1024,
+                                  transformer_enc_layers=2, conv_dim=256, mask_dim=256, norm="GN",
+                                  transformer_in_features=["res3", "res4", "res5"], common_stride=4)
+    dec = MultiScaleMaskedTransformerDecoderMaskDN(256, True, num_classes=K, hidden_dim=256, num_queries=Q, nheads=8,
+                                                   dim_feedforward=2048, dec_layers=3, pre_norm=False, mask_dim=256,
+                                                   enforce_input_project=False, dn_mode="points", all_lys=True,
+                                                   dn_label_noise_ratio=-1.0)
+    with torch.no_grad():
+        for m in pd.modules():
+            if m.__class__.__name__ == "MSDeformAttn":
+                m.attention_weights.weight.normal_(std=0.02)
+                m.sampling_offsets.weight.normal_(std=0.02)
+    psd = {k: v.detach().clone() for k, v in pd.state_dict().items()}
+    dsd = {k: v.detach().clone() for k, v in dec.state_dict().items()}
+    feats = workload.synthetic_features(1, H, W, backbone=backbone, seed=3)
+    tgt = workload.synthetic_targets(1, H, W, num_classes=K, seed=3, max_inst=6) if dn else None
+
+    pd, dec = pd.to(DEV).eval(), dec.to(DEV).eval()
+    with torch.no_grad():
+        mf, enc0, ms = pd.forward_features({k: v.to(DEV) for k, v in feats.items()})
+        dn_dev = None if tgt is None else {"tgt": [{k: v.to(DEV) for k, v in t.items()} for t in tgt], "scalar": 1,
+                                           "noise_scale": 0.0}
+        out = dec(ms, mf, None, dn_dev)
+        omf, oenc0, oms = O.pixel_decoder_forward(psd, feats, enc_layers=2)
+        dn_cpu = None if tgt is None else {"tgt": tgt, "scalar": 1, "noise_scale": 0.0}
+        oout = O.decoder_forward(dsd, oms, omf, num_queries=Q, dec_layers=3, num_classes=K, dn_args=dn_cpu)
+
+    # pixel decoder: no discrete stage -> the contract everywhere
+    assert relerr(mf.cpu(), omf).max().item() < 1e-3
+    assert relerr(enc0.cpu(), oenc0).max().item() < 1e-3
+    for a, b in zip(ms, oms):
+        assert a.shape == b.shape and relerr(a.cpu(), b).max().item() < 1e-3
+    # decoder on the ORACLE's pixel-decoder outputs?  No: on its own (the product path end to end); first head strict
+    a0, b0 = out["aux_outputs"][0], oout["aux_outputs"][0]
+    assert a0["pred_masks"].shape == (1, Q, H // 4, W // 4)
+    assert relerr(a0["pred_logits"].cpu(), b0["pred_logits"]).max().item() < 1e-3
+    assert relerr(a0["pred_masks"].cpu(), b0["pred_masks"]).max().item() < 1e-3
+    for got, ref in ((out, oout),) + (((out["dn_out"], oout["dn_out"]),) if dn else ()):
+        for key in ("pred_logits", "pred_masks"):
+            e = relerr(got[key].cpu(), ref[key]).flatten().float()
+            if e.numel() > 4_000_000:
+                e = e[:: e.numel() // 4_000_000]
+            assert e.median().item() < 1e-4, (key, e.median().item())
+            assert torch.quantile(e, 0.98).item() < 1e-3, (key, torch.quantile(e, 0.98).item())
+    if dn:
+        assert out["dn_out"]["dn_args"] == oout["dn_out"]["dn_args"]
