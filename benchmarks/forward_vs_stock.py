@@ -104,10 +104,30 @@ def main():
     def stock_pd():
         return O.pixel_decoder_forward(psd, feats)
     t_ours_pd, t_stock_pd = timeit(ours_pd, 5), timeit(stock_pd, 3)
+
+    # our forward has no host synchronisation, so it can be replayed as ONE CUDA graph (the reference's cannot:
+    # `.item()` / `torch.where` index counts at decoder :474/:1780, shape syncs at msdeformattn.py:330-339)
+    t_graph = None
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            ours()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            held = ours()
+        t_graph = timeit(graph.replay, 5)
+        assert torch.equal(held["pred_logits"], a["pred_logits"])
+    except Exception as e:  # noqa: BLE001
+        t_graph = f"capture failed: {type(e).__name__}: {str(e)[:120]}"
     print(json.dumps({
         "what": "forward only, pixel decoder + 9-layer masked decoder, eval (no DN), fp32, TF32 off",
         "B": B, "ours_ms": t_ours, "stock_ms": t_stock, "speedup": t_stock / t_ours,
         "ours_img_s": B / t_ours * 1e3, "stock_img_s": B / t_stock * 1e3,
+        "ours_cuda_graph_ms": t_graph,
+        "speedup_cuda_graph": (t_stock / t_graph) if isinstance(t_graph, float) else None,
         "pixel_decoder_only": {"ours_ms": t_ours_pd, "stock_ms": t_stock_pd, "speedup": t_stock_pd / t_ours_pd},
         "decoder_only": {"ours_ms": t_ours - t_ours_pd, "stock_ms": t_stock - t_stock_pd,
                          "speedup": (t_stock - t_stock_pd) / max(1e-9, t_ours - t_ours_pd)},

@@ -49,7 +49,7 @@ def emit(name, ms, bytes_=None, mma_flops=None, **kw):
 def main():
     g = torch.Generator(device=DEV).manual_seed(0)
     rn = lambda *s: torch.randn(*s, device=DEV, generator=g)
-    which = os.environ.get("MPF_PROBE", "msda,gemm,masklogits,layernorm,maskbits,xattn").split(",")
+    which = os.environ.get("MPF_PROBE", "msda,gemm,masklogits,layernorm,fpn,maskbits,xattn").split(",")
     S, M, D, L, P = 21504, 8, 32, 3, 4
     shapes = [(32, 32), (64, 64), (128, 128)]
     if "msda" in which:
@@ -120,6 +120,25 @@ def main():
         ms = timeit(lambda: native.colsum(gy))
         emit("colsum [344064 x 256]", ms, 4 * B * S * 256)
         del x, r, gy
+    if "fpn" in which:
+        # FPN-stage layout-crossing kernels at the bench geometry ([16, 256, 256, 256] maps)
+        C, H, W = 256, 256, 256
+        cur, prev = rn(B, H, W, C), rn(B, H // 2, W // 2, C)
+        ms = timeit(lambda: native.upsample2x_add_nchw_fwd(cur, prev))
+        emit("upsample2x_add_nchw_fwd [16,256,256,256]", ms, 4 * B * C * H * W * (2 + 0.25))
+        gout = rn(B, C, H, W)
+        ms = timeit(lambda: native.upsample2x_add_nchw_bwd(gout))
+        emit("upsample2x_add_nchw_bwd [16,256,256,256]", ms, 4 * B * C * H * W * (2 + 0.25))
+        del cur, prev
+        x3, gm, bt = gout.view(B, C, H * W), rn(C), rn(C)
+        ms = timeit(lambda: native.groupnorm_nchw2cl_fwd(x3, gm, bt, 1e-5, 32, True))
+        emit("groupnorm_nchw2cl_fwd (stats + apply) [16,256,65536]", ms, 4 * B * C * H * W * 3)
+        y, mean, rstd = native.groupnorm_nchw2cl_fwd(x3, gm, bt, 1e-5, 32, True)
+        ms = timeit(lambda: native.groupnorm_nchw2cl_bwd(y, x3, gm, bt, mean, rstd, 32, True))
+        emit("groupnorm_nchw2cl_bwd (stats + apply) [16,256,65536]", ms, 4 * B * C * H * W * 5)
+        ms = timeit(lambda: native.groupnorm_cl_fwd(y, gm, bt, 1e-5, 32, False))
+        emit("groupnorm_cl_fwd (stats + apply) [16,65536,256]", ms, 4 * B * C * H * W * 3)
+        del x3, y, gout
     if "maskbits" in which:
         logits = rn(B, 120, 256, 256)
         for hw in (32, 64, 128):

@@ -83,6 +83,56 @@ def linear(x, weight, bias=None, relu=False):
     return _Linear.apply(x, weight, bias, relu)
 
 
+class fp32_math:
+    """Context manager: cuDNN / cuBLAS library calls inside run in true fp32 (TF32 off)."""
+
+    def __enter__(self):
+        self._c = torch.backends.cudnn.allow_tf32
+        self._m = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+
+    def __exit__(self, *exc):
+        torch.backends.cudnn.allow_tf32 = self._c
+        torch.backends.cuda.matmul.allow_tf32 = self._m
+        return False
+
+
+class _ConvFp32(torch.autograd.Function):
+    """Library convolution (the pixel decoder's 3x3 output conv, ref pixel_decoder/msdeformattn.py:268-275) pinned to
+    true fp32 in BOTH directions.  The reference forces fp32 here (`autocast(enabled=False)`, :314); PyTorch's
+    default ``cudnn.allow_tf32 = True`` would still run the convolution -- and, outside any forward-time context
+    manager, its backward -- on TF32 tensor cores (1e-3 .. 1e-2 relative error, algorithm-dependent)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, padding, dilation, groups):
+        with fp32_math():
+            y = F.conv2d(x, weight, bias, stride, padding, dilation, groups)
+        ctx.save_for_backward(x, weight)
+        ctx.cfg = (stride, padding, dilation, groups, None if bias is None else tuple(bias.shape))
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        stride, padding, dilation, groups, bias_shape = ctx.cfg
+        mask = [ctx.needs_input_grad[0], ctx.needs_input_grad[1], bias_shape is not None and ctx.needs_input_grad[2]]
+        with fp32_math():
+            gx, gw, gb = torch.ops.aten.convolution_backward(
+                gy, x, weight, None if bias_shape is None else list(bias_shape), list(stride), list(padding),
+                list(dilation), False, [0, 0], groups, mask)
+        return gx, gw, gb, None, None, None, None
+
+
+def conv2d_fp32(x, conv):
+    """``conv`` (an nn.Conv2d) applied to ``x`` with fp32 arithmetic forward and backward."""
+    if conv.padding_mode != "zeros" or isinstance(conv.padding, str):
+        with fp32_math():
+            return conv._conv_forward(x, conv.weight, conv.bias)
+    return _ConvFp32.apply(x, conv.weight, conv.bias, tuple(conv.stride), tuple(conv.padding), tuple(conv.dilation),
+                           conv.groups)
+
+
 class _Conv1x1NCHW(torch.autograd.Function):
     """1x1 convolution of an NCHW-contiguous map (backbone output) straight into channels-last tokens: the map is
     the MN-major operand [B, Cin, HW] of the token-reduction ("TN") GEMM, so no layout copy of the input is made."""

@@ -30,19 +30,7 @@ from .position_encoding import PositionEmbeddingSine
 from .registry import configurable, register_pixel_decoder
 
 
-class fp32_math:
-    """Context manager: cuDNN / cuBLAS library calls inside run in true fp32 (TF32 off)."""
-
-    def __enter__(self):
-        self._c = torch.backends.cudnn.allow_tf32
-        self._m = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cudnn.allow_tf32 = False
-        torch.backends.cuda.matmul.allow_tf32 = False
-
-    def __exit__(self, *exc):
-        torch.backends.cudnn.allow_tf32 = self._c
-        torch.backends.cuda.matmul.allow_tf32 = self._m
-        return False
+fp32_math = ops.fp32_math
 
 
 class ShapeSpec:
@@ -62,7 +50,7 @@ class ConvNormAct(nn.Conv2d):
         self.activation = activation
 
     def forward(self, x):
-        x = super().forward(x)
+        x = ops.conv2d_fp32(x, self) if x.is_cuda else super().forward(x)
         return self.norm_act(x)
 
     def norm_act(self, x):
@@ -83,7 +71,7 @@ def conv1x1_tokens(x, conv):
     tensor-core kernel: [B*H*W, Cin] x W[Cout, Cin]^T (+ bias).  Returns the map in the same form."""
     B, Cin, H, W = x.shape
     if Cin % 32 != 0 or conv.kernel_size != (1, 1) or conv.stride != (1, 1):
-        return F.conv2d(x, conv.weight, conv.bias)
+        return ops.conv2d_fp32(x, conv) if x.is_cuda else F.conv2d(x, conv.weight, conv.bias)
     if x.is_contiguous() and not x.permute(0, 2, 3, 1).is_contiguous():
         # NCHW backbone output: consumed as the MN-major operand of the token-reduction GEMM, no layout copy
         y = ops.conv1x1_nchw_to_cl(x, conv.weight, conv.bias)
