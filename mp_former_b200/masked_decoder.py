@@ -305,6 +305,7 @@ class MultiScaleMaskedTransformerDecoder(_MaskedDecoderBase):
         output = self.query_feat.weight.unsqueeze(0).repeat(bs, 1, 1)
         heads0 = self.forward_prediction_heads(output, mask_features, size_list[0])
         pc, pm = self._decode(output, src, pos, size_list, mask_features, None, heads0)
+        _, pm = ops.collect_mask_heads(pm, 0, mask_features.shared)
         return {"pred_logits": pc[-1], "pred_masks": pm[-1],
                 "aux_outputs": self._set_aux_loss(pc if self.mask_classification else None, pm),
                 "dn_out": None}
@@ -476,14 +477,15 @@ class MultiScaleMaskedTransformerDecoderMaskDN(_MaskedDecoderBase):
         if tgt_mask is not None:
             n_dn = pc[0].shape[1] - self.num_queries
             pc_split = [ops.split_queries(c, n_dn) for c in pc]
-            pm_split = [ops.split_queries(m, n_dn) for m in pm]
-            dn_c, dn_m = [c[0] for c in pc_split], [m[0] for m in pm_split]
-            pc, pm = [c[1] for c in pc_split], [m[1] for m in pm_split]
+            dn_c, pc = [c[0] for c in pc_split], [c[1] for c in pc_split]
+            # mask logits of all heads: split AND collected, so that the heads' backward GEMMs run batched
+            dn_m, pm = ops.collect_mask_heads(pm, n_dn, mask_features.shared)
             dn_out = {"pred_logits": dn_c[-1], "pred_masks": dn_m[-1],
                       "aux_outputs": self._set_aux_loss(dn_c if self.mask_classification else None, dn_m),
                       "dn_args": dn_meta}
         else:
             dn_out = None
+            _, pm = ops.collect_mask_heads(pm, 0, mask_features.shared)
             pc[-1] = pc[-1] + self.label_enc.weight[0, 0] * 0.0      # keeps label_enc in the DDP graph (ref :1846)
         return {"pred_logits": pc[-1], "pred_masks": pm[-1],
                 "aux_outputs": self._set_aux_loss(pc if self.mask_classification else None, pm),

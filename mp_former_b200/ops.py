@@ -473,11 +473,16 @@ def _channels_last_tokens(mask_features):
 
 
 class _SharedGrad:
-    """Accumulator of the gradients that several consumers send to ONE tensor (see ``grad_fanout``)."""
-    __slots__ = ("buf",)
+    """State shared by the prediction heads of one decoder forward: the accumulator of the gradients they send to
+    ``mask_features`` (see ``grad_fanout``) and, when the heads' outputs pass through ``collect_mask_heads``, the
+    per-head operands / precomputed gradients of the batched backward."""
+    __slots__ = ("buf", "embeds", "tokens", "dE")
 
     def __init__(self):
-        self.buf = None
+        self.buf = None          # d(mask_features) as tokens [B, H*W, C]
+        self.embeds = []         # mask_embed of every head, in call order (detached)
+        self.tokens = None       # mask_features as tokens [B, H*W, C]
+        self.dE = None           # [B, heads, Qt, C] once the collector's backward has run
 
 
 class _GradFanout(torch.autograd.Function):
@@ -495,6 +500,7 @@ class _GradFanout(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grads):
         buf, ctx.state.buf = ctx.state.buf, None
+        ctx.state.dE, ctx.state.embeds, ctx.state.tokens = None, [], None
         rest = [g for g in grads if g is not None and (buf is None or g.data_ptr() != buf.data_ptr())]
         total = None
         if buf is not None:                             # tokens [B, H*W, C] -> logical [B, C, H, W]
@@ -525,12 +531,23 @@ class _MaskLogits(torch.autograd.Function):
         ctx.save_for_backward(mask_embed, tokens)
         ctx.fshape = (B, C, H, W)
         ctx.shared = shared
+        ctx.head = -1
+        if shared is not None:
+            ctx.head = len(shared.embeds)
+            shared.embeds.append(mask_embed.detach())
+            shared.tokens = tokens.detach()
         return out.view(B, mask_embed.shape[1], H, W)
 
     @staticmethod
     def backward(ctx, g):
         mask_embed, tokens = ctx.saved_tensors
         B, C, H, W = ctx.fshape
+        sh = ctx.shared
+        if sh is not None and sh.dE is not None:
+            # collect_mask_heads already computed both gradients for all heads in two batched GEMMs
+            ge = sh.dE[:, ctx.head] if ctx.needs_input_grad[0] else None
+            gf = sh.buf.view(B, H, W, C).permute(0, 3, 1, 2) if ctx.needs_input_grad[1] else None
+            return ge, gf, None
         g2 = g.reshape(B, g.shape[1], H * W)
         ge = gf = None
         g2 = g2.contiguous()
@@ -564,6 +581,71 @@ def mask_logits(mask_embed, mask_features, shared=None):
     ``mask_features`` is one of its aliases."""
     _cuda_only(mask_embed, "mask_embed")
     return _MaskLogits.apply(mask_embed.contiguous(), mask_features, shared)
+
+
+class _HeadCollector(torch.autograd.Function):
+    """Identity on the mask logits of ALL prediction heads (optionally split into the DN and the matching queries),
+    placed at the end of the decoder so that its backward sees every head's incoming gradient at once.  Those
+    gradients come from the loss alone (the attention masks derived from the logits are detached, ref decoder
+    :1875), so the heads' backward GEMMs can be batched:
+
+        dE_all[b] = G_all[b] (heads*Qt x HW) @ F[b] (HW x C)        -- mask_features read once, not once per head
+        dF[b]     = G_all[b]^T (HW x heads*Qt) @ E_all[b]           -- written once, not accumulated ten times
+
+    G_all [B, heads, Qt, HW] is assembled here from the (up to two per head) gradient pieces -- the pass that
+    ``split_queries`` would otherwise spend on concatenating them."""
+
+    @staticmethod
+    def forward(ctx, shared, n_dn, *masks):
+        ctx.shared, ctx.n_dn, ctx.n_heads = shared, n_dn, len(masks)
+        ctx.mshape = masks[0].shape
+        ctx.set_materialize_grads(False)
+        outs = []
+        for m in masks:
+            if n_dn > 0:
+                outs += [m[:, :n_dn], m[:, n_dn:]]
+            else:
+                outs.append(m.view_as(m))
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        sh, n_dn, nH = ctx.shared, ctx.n_dn, ctx.n_heads
+        B, Qt, H, W = ctx.mshape
+        dev = sh.tokens.device if sh.tokens is not None else next(g.device for g in grads if g is not None)
+        G = torch.empty((B, nH, Qt, H, W), dtype=torch.float32, device=dev)
+        for h in range(nH):
+            pieces = ((grads[2 * h], slice(0, n_dn)), (grads[2 * h + 1], slice(n_dn, Qt))) if n_dn > 0 \
+                else ((grads[h], slice(0, Qt)),)
+            for g, sl in pieces:
+                if g is None:
+                    G[:, h, sl].zero_()
+                else:
+                    G[:, h, sl].copy_(g)
+        C = sh.tokens.shape[-1] if sh.tokens is not None else 0
+        if (sh.tokens is not None and len(sh.embeds) == nH and native.GEMM_MODE == "bf16x3" and (H * W) % 4 == 0
+                and C % 4 == 0):
+            G2 = G.view(B, nH * Qt, H * W)
+            E_all = torch.stack(sh.embeds, 1).view(B, nH * Qt, C)
+            tiles = ((nH * Qt + 127) // 128) * ((C + 255) // 256) * B
+            splits = max(1, min(16, 592 // max(1, tiles), (H * W + 4095) // 4096))
+            sh.dE = native.gemm_general(G2, sh.tokens, a_mn=False, b_mn=True, k_splits=splits).view(B, nH, Qt, C)
+            sh.buf = native.gemm_tn(G2, E_all)                                 # [B, HW, C]
+        return (None, None) + tuple(G[:, h] for h in range(nH))
+
+
+def collect_mask_heads(masks, n_dn, shared):
+    """masks: the mask logits [B, Qt, H, W] of every prediction head, in call order.  Returns
+    ``(dn_parts, matching_parts)`` (``dn_parts`` is None when ``n_dn == 0``): views of the inputs, with the heads'
+    backward batched as described in ``_HeadCollector``.  ``shared``: the state ``grad_fanout`` returned."""
+    if shared is None or not torch.is_grad_enabled() or not any(m.requires_grad for m in masks):
+        if n_dn > 0:
+            return [m[:, :n_dn] for m in masks], [m[:, n_dn:] for m in masks]
+        return None, list(masks)
+    outs = _HeadCollector.apply(shared, n_dn, *masks)
+    if n_dn > 0:
+        return list(outs[0::2]), list(outs[1::2])
+    return None, list(outs)
 
 
 class PackedMask:

@@ -358,3 +358,44 @@ def test_conv1x1_nchw_to_channels_last(B, Cin, Cout, H, W, bias):
         assert (b.grad.double() - br.grad).abs().max().item() / (B * H * W) ** 0.5 < TOL
     # channels-last or tiny inputs are not this op's business
     assert ops.conv1x1_nchw_to_cl(torch.randn(1, 64, 4, 4, device=DEV), w[:, :64]) is None
+
+
+@pytest.mark.parametrize("n_dn", [0, 7])
+def test_collected_mask_heads_batched_backward(n_dn):
+    """ops.collect_mask_heads: the heads' dE / dF GEMMs batched into two launches (mask_features read once, its
+    gradient written once) give the gradients of the head-by-head path; one head receives no gradient for its DN
+    part, one none at all."""
+    g = torch.Generator(device=DEV).manual_seed(11 + n_dn)
+    B, Qt, C, H, W, nH = 2, 27, 64, 16, 24, 4
+    mf = torch.randn(B, C, H, W, device=DEV, generator=g).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    embeds = [torch.randn(B, Qt, C, device=DEV, generator=g).requires_grad_(True) for _ in range(nH)]
+    gouts = [torch.randn(B, Qt, H, W, device=DEV, generator=g) for _ in range(nH)]
+
+    def loss_of(parts_dn, parts_m):
+        total = 0.0
+        for h in range(nH):
+            if h == 2:
+                continue                                            # head 2: unused by the loss
+            total = total + (parts_m[h] * gouts[h][:, n_dn:]).sum()
+            if n_dn and h != 1:                                     # head 1: no gradient for its DN rows
+                total = total + (parts_dn[h] * gouts[h][:, :n_dn]).sum()
+        return total
+
+    aliases, shared = ops.grad_fanout(mf, nH)
+    masks = [ops.mask_logits(e, a, shared) for e, a in zip(embeds, aliases)]
+    dn_parts, m_parts = ops.collect_mask_heads(masks, n_dn, shared)
+    assert (dn_parts is None) == (n_dn == 0) and m_parts[0].shape == (B, Qt - n_dn, H, W)
+    loss_of(dn_parts, m_parts).backward()
+    got_mf, got_e = mf.grad.clone(), [None if e.grad is None else e.grad.clone() for e in embeds]
+    assert shared.buf is None and shared.dE is None
+    mf.grad = None
+    for e in embeds:
+        e.grad = None
+    masks = [ops.mask_logits(e, mf) for e in embeds]
+    loss_of([m[:, :n_dn] for m in masks], [m[:, n_dn:] for m in masks]).backward()
+    assert rel(got_mf, mf.grad) < TOL
+    for h, (a, e) in enumerate(zip(got_e, embeds)):
+        if e.grad is None:
+            assert a is None or a.abs().max().item() == 0.0
+        else:
+            assert rel(a, e.grad) < TOL, h
