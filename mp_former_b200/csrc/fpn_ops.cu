@@ -90,7 +90,7 @@ upsample2x_add_nchw_fwd_kernel(const float* __restrict__ cur, const float* __res
 // (clamping the index reproduces the border taps of the forward exactly)
 constexpr int kBC = 32;                         // channels per CTA
 constexpr int kBRows = 6;                       // fine rows staged: 2*i0-1 .. 2*i0+4
-constexpr int kBCols = 66;                      // fine columns staged: 2*j0-1 .. 2*j0+64
+// fine columns staged: 2*j0-1 .. 2*j0+64 (66 of them) in rows of kBRowLd floats
 constexpr int kBRowLd = 72;
 constexpr int kBChLd = kBRows * kBRowLd + 1;    // odd: channel-quad reads hit distinct banks
 constexpr int kBSmem = kBC * kBChLd * 4;
@@ -108,16 +108,36 @@ upsample2x_add_nchw_bwd_kernel(const float* __restrict__ g, int H, int W, int C,
   const int t = threadIdx.x;
   const float* gb = g + (static_cast<long long>(b) * C + c0) * H * W;
 
-  // stage: column index cc in [0, 66) <-> fine column 2*j0 - 1 + cc (clamped); row rr in [0, 6) <-> 2*i0 - 1 + rr
-  for (int i = t; i < kBC * kBRows * kBCols; i += kThreads) {
-    const int cc = i % kBCols;
-    const int rr = (i / kBCols) % kBRows;
-    const int ch = i / (kBCols * kBRows);
-    int col = 2 * j0 - 1 + cc;
-    col = col < 0 ? 0 : (col > W - 1 ? W - 1 : col);
+  // stage: column index cc in [0, 66) <-> fine column 2*j0 - 1 + cc (clamped); row rr in [0, 6) <-> 2*i0 - 1 + rr.
+  // interior columns cc = 1..64 (fine columns 2*j0 .. 2*j0+63, 16-byte aligned since W % 4 == 0) as float4 loads,
+  // 16 per (channel, row); the two halo columns as scalars.
+  for (int i = t; i < kBC * kBRows * 16; i += kThreads) {
+    const int v = i & 15;
+    const int rr = (i >> 4) % kBRows;
+    const int ch = (i >> 4) / kBRows;
     int row = 2 * i0 - 1 + rr;
     row = row < 0 ? 0 : (row > H - 1 ? H - 1 : row);
-    gs[ch * kBChLd + rr * kBRowLd + cc] = __ldg(gb + (static_cast<long long>(ch) * H + row) * W + col);
+    const int col = 2 * j0 + 4 * v;
+    float* d = gs + ch * kBChLd + rr * kBRowLd + 1 + 4 * v;
+    const float* src = gb + (static_cast<long long>(ch) * H + row) * W;
+    if (col + 3 < W) {
+      const float4 q = ld4(src + col);
+      d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
+    } else {                                   // right edge of the map: clamp (only the first is ever read back)
+      const float e = __ldg(src + W - 1);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) d[u] = col + u < W ? __ldg(src + col + u) : e;
+    }
+  }
+  for (int i = t; i < kBC * kBRows * 2; i += kThreads) {
+    const int side = i & 1;
+    const int rr = (i >> 1) % kBRows;
+    const int ch = (i >> 1) / kBRows;
+    int row = 2 * i0 - 1 + rr;
+    row = row < 0 ? 0 : (row > H - 1 ? H - 1 : row);
+    int col = side ? 2 * j0 + 64 : 2 * j0 - 1;
+    col = col < 0 ? 0 : (col > W - 1 ? W - 1 : col);
+    gs[ch * kBChLd + rr * kBRowLd + (side ? 65 : 0)] = __ldg(gb + (static_cast<long long>(ch) * H + row) * W + col);
   }
   __syncthreads();
   const int c4 = t & 7;

@@ -613,15 +613,12 @@ class _HeadCollector(torch.autograd.Function):
         sh, n_dn, nH = ctx.shared, ctx.n_dn, ctx.n_heads
         B, Qt, H, W = ctx.mshape
         dev = sh.tokens.device if sh.tokens is not None else next(g.device for g in grads if g is not None)
-        G = torch.empty((B, nH, Qt, H, W), dtype=torch.float32, device=dev)
-        for h in range(nH):
-            pieces = ((grads[2 * h], slice(0, n_dn)), (grads[2 * h + 1], slice(n_dn, Qt))) if n_dn > 0 \
-                else ((grads[h], slice(0, Qt)),)
-            for g, sl in pieces:
-                if g is None:
-                    G[:, h, sl].zero_()
-                else:
-                    G[:, h, sl].copy_(g)
+        # ONE concatenation along the (head, query) axis: contiguous output, vectorised batched copy
+        sizes = ([n_dn, Qt - n_dn] * nH) if n_dn > 0 else ([Qt] * nH)
+        pieces = [g.reshape(B, n, H * W) if g is not None else torch.zeros((B, n, H * W), dtype=torch.float32, device=dev)
+                  for g, n in zip(grads, sizes)]
+        G = torch.cat(pieces, 1).view(B, nH, Qt, H, W)
+        del pieces
         C = sh.tokens.shape[-1] if sh.tokens is not None else 0
         if (sh.tokens is not None and len(sh.embeds) == nH and native.GEMM_MODE == "bf16x3" and (H * W) % 4 == 0
                 and C % 4 == 0):
