@@ -188,6 +188,10 @@ int mpf_gemm_tf32x3_general(const float* A, int a_mn_major, long long lda, long 
  * Requirements: A/B/C 16-byte aligned; lda, ldc, batch strides multiples of 4 elements; ldb multiple of 8.
  * ------------------------------------------------------------------------------------------- */
 int mpf_split_bf16(const float* x, uint16_t* hi, uint16_t* lo, long long n, void* stream);
+/* x [batch, R, Cc] fp32 -> bf16 halves of its transpose, hi / lo [batch, Cc, R] (R, Cc multiples of 4): the B operand
+ * of a product that reduces over R when x is stored R-major (mask_features tokens in the batched dE of the
+ * prediction heads, ref decoder :1865 under autograd). */
+int mpf_transpose_split_bf16(const float* x, uint16_t* hi, uint16_t* lo, int batch, long long R, int Cc, void* stream);
 int mpf_gemm_bf16x3(const float* A, long long lda, long long a_batch_stride, const uint16_t* B_hi,
                     const uint16_t* B_lo, long long ldb, long long b_batch_stride, const float* bias, float* C,
                     float* C_lo, long long ldc, long long c_batch_stride, const float* resid, long long resid_ld,

@@ -463,6 +463,46 @@ split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, _
   }
 }
 
+// x [batch, R, Cc] fp32 -> hi, lo [batch, Cc, R] bf16: the split of mpf_split_bf16 fused with a transposition, for a
+// big activation that a later product needs as its K-major B operand (mask_features in the batched dE of the
+// prediction heads: reduction over the H*W pixels).  64 x 64 tile through shared memory; 16-byte loads along Cc,
+// 8-byte (4 x bf16) stores along R.  grid (ceil(R/64), ceil(Cc/64), batch); R % 4 == 0, Cc % 4 == 0.
+__global__ void __launch_bounds__(256)
+transpose_split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                            __nv_bfloat16* __restrict__ lo, long long R, int Cc) {
+  __shared__ float tile[64 * 65];
+  const long long r0 = static_cast<long long>(blockIdx.x) * 64;
+  const int c0 = blockIdx.y * 64, b = blockIdx.z, t = threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = t + 256 * k;
+    const int r = i >> 4, c4 = i & 15;
+    if (r0 + r < R && c0 + 4 * c4 < Cc) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + (static_cast<long long>(b) * R + r0 + r) * Cc + c0) + c4);
+      float* s = tile + (4 * c4) * 65 + r;
+      s[0] = v.x; s[65] = v.y; s[130] = v.z; s[195] = v.w;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = t + 256 * k;
+    const int c = i >> 4, r4 = i & 15;
+    if (c0 + c < Cc && r0 + 4 * r4 < R) {
+      const float* s = tile + c * 65 + 4 * r4;
+      __nv_bfloat16 h[4], l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        h[e] = __float2bfloat16_rn(s[e]);
+        l[e] = __float2bfloat16_rn(s[e] - __bfloat162float(h[e]));
+      }
+      const long long o = (static_cast<long long>(b) * Cc + c0 + c) * R + r0 + 4 * r4;
+      *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<const uint2*>(h);
+      *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<const uint2*>(l);
+    }
+  }
+}
+
 using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -536,6 +576,21 @@ int mpf_split_bf16(const float* x, uint16_t* hi, uint16_t* lo, long long n, void
       x, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), n);
   mpf::count_launch();
   return mpf::finish_launch("split_bf16");
+}
+
+int mpf_transpose_split_bf16(const float* x, uint16_t* hi, uint16_t* lo, int batch, long long R, int Cc, void* stream) {
+  using namespace mpf;
+  clear_error();
+  MPF_REQUIRE(x && hi && lo && batch > 0 && R > 0 && Cc > 0, "transpose_split_bf16: bad arguments");
+  MPF_REQUIRE(R % 4 == 0 && Cc % 4 == 0 && aligned16(x) && (reinterpret_cast<uintptr_t>(hi) & 7u) == 0 &&
+                  (reinterpret_cast<uintptr_t>(lo) & 7u) == 0,
+              "transpose_split_bf16: R and Cc must be multiples of 4, x 16-byte and hi / lo 8-byte aligned");
+  MPF_REQUIRE(batch <= 65535 && (Cc + 63) / 64 <= 65535, "transpose_split_bf16: grid too large");
+  dim3 grid(static_cast<unsigned>((R + 63) / 64), (Cc + 63) / 64, batch);
+  bf3::transpose_split_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), R, Cc);
+  count_launch();
+  return finish_launch("transpose_split_bf16");
 }
 
 int mpf_gemm_bf16x3(const float* A, long long lda, long long a_batch_stride, const uint16_t* B_hi,

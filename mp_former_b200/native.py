@@ -92,6 +92,39 @@ def split_b(w):
     return split_tf32(w)
 
 
+def transpose_split_bf16(x):
+    """x [batch, R, Cc] fp32 contiguous -> (hi, lo) bf16 [batch, Cc, R]: bf16x3 halves of the transpose."""
+    x = _f32c(x, "x")
+    if x.dim() != 3 or not x.is_contiguous():
+        raise RuntimeError("transpose_split_bf16: x must be a contiguous [batch, R, Cc] tensor")
+    batch, R, Cc = x.shape
+    hi = torch.empty((batch, Cc, R), dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty_like(hi)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().mpf_transpose_split_bf16(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), batch, R, Cc, _stream())
+    _lib.check(rc, "transpose_split_bf16")
+    return hi, lo
+
+
+def gemm_bf16x3_splitk(a, b_hi, b_lo, k_splits):
+    """C[i] = a[i] @ b[i]^T for a [batch, M, K] fp32 and pre-split bf16 b_hi / b_lo [batch, N, K], with the long
+    reduction K cut into ``k_splits`` ranges handled by different CTAs (partial slabs summed here)."""
+    a = _f32c(a, "a")
+    batch, M, K = a.shape
+    N = b_hi.shape[1]
+    k_splits = max(1, min(int(k_splits), (K + 31) // 32))
+    if b_hi.shape != (batch, N, K) or b_lo.shape != b_hi.shape or N % 4 or a.stride(2) != 1:
+        raise RuntimeError(f"gemm_bf16x3_splitk: shapes a={tuple(a.shape)} b={tuple(b_hi.shape)}")
+    out = torch.empty((batch * k_splits, M, N), dtype=torch.float32, device=a.device)
+    nbytes = 4.0 * batch * (M * K + k_splits * M * N) + 4.0 * batch * N * K
+    with torch.cuda.device(a.device), _Timed("gemm_bf16x3_kernel", 2.0 * batch * M * N * K, nbytes):
+        rc = _lib.load().mpf_gemm_bf16x3(
+            a.data_ptr(), a.stride(1), a.stride(0), b_hi.data_ptr(), b_lo.data_ptr(), K, N * K, None, out.data_ptr(),
+            None, N, M * N, None, 0, 0, 0, None, 0, 1.0, batch, M, N, K, k_splits, 0, 0, _stream())
+    _lib.check(rc, "gemm_bf16x3 (split-K)")
+    return out.view(batch, k_splits, M, N).sum(1) if k_splits > 1 else out
+
+
 def _gemm_bf16x3(a, b_hi, b_lo, bias, relu, transpose_c, split_out, resid, resid_rows, resid_cols, alpha, gate=None):
     """a [batch, M, K] fp32 (K contiguous); b_hi / b_lo bf16 [batch or 1, N, K] contiguous."""
     batch, M, K = a.shape

@@ -624,9 +624,18 @@ class _HeadCollector(torch.autograd.Function):
                 and C % 4 == 0):
             G2 = G.view(B, nH * Qt, H * W)
             E_all = torch.stack(sh.embeds, 1).view(B, nH * Qt, C)
+            # dE: reduction over the H*W pixels -> mask_features is needed K-major: one transposing split per step
+            # (instead of ten passes of the 3xTF32 mixed-major kernel), then the bf16x3 GEMM with split-K chosen so
+            # that the tile count fills whole waves of the 148 SMs
             tiles = ((nH * Qt + 127) // 128) * ((C + 255) // 256) * B
-            splits = max(1, min(16, 592 // max(1, tiles), (H * W + 4095) // 4096))
-            sh.dE = native.gemm_general(G2, sh.tokens, a_mn=False, b_mn=True, k_splits=splits).view(B, nH, Qt, C)
+            max_splits = max(1, min(16, (H * W) // 2048))
+            splits = min(range(1, max_splits + 1), key=lambda k: (-(-tiles * k // 148)) / (tiles * k / 148.0) + 0.01 * k)
+            if (H * W) % 8 == 0:
+                ft_hi, ft_lo = native.transpose_split_bf16(sh.tokens)              # [B, C, HW]
+                sh.dE = native.gemm_bf16x3_splitk(G2, ft_hi, ft_lo, splits).view(B, nH, Qt, C)
+                del ft_hi, ft_lo
+            else:
+                sh.dE = native.gemm_general(G2, sh.tokens, a_mn=False, b_mn=True, k_splits=splits).view(B, nH, Qt, C)
             sh.buf = native.gemm_tn(G2, E_all)                                 # [B, HW, C]
         return (None, None) + tuple(G[:, h] for h in range(nH))
 

@@ -145,3 +145,30 @@ def test_gemm_tn_accumulate_into(T, M, N, batch):
     assert (acc.double() - ref).abs().max().item() / (3 * T) ** 0.5 < TOL
     with pytest.raises(RuntimeError):
         native.gemm_tn(a, b, accumulate_into=acc[:, :, : N // 2])
+
+
+@pytest.mark.parametrize("batch,R,Cc", [(2, 256, 64), (1, 1000, 100), (3, 68, 256), (1, 4096, 256)])
+def test_transpose_split_bf16(batch, R, Cc):
+    """hi + lo of the transposed tensor: hi = bf16_rn(x^T) exactly, hi + lo reproduces x to 2^-16 relative."""
+    g = torch.Generator(device=DEV).manual_seed(R + Cc)
+    x = torch.randn(batch, R, Cc, device=DEV, generator=g) * 3
+    hi, lo = native.transpose_split_bf16(x)
+    assert hi.shape == (batch, Cc, R) and hi.dtype == torch.bfloat16
+    xt = x.transpose(1, 2)
+    assert torch.equal(hi, xt.to(torch.bfloat16))
+    assert torch.equal(lo, (xt - hi.float()).to(torch.bfloat16))
+    assert ((hi.float() + lo.float() - xt).abs() <= xt.abs() * 2.0 ** -16 + 1e-30).all()
+
+
+@pytest.mark.parametrize("batch,M,N,K,splits", [(2, 300, 256, 4096, 5), (1, 1200, 64, 2048, 3), (3, 100, 128, 1000, 1)])
+def test_gemm_bf16x3_split_k_with_transposed_operand(batch, M, N, K, splits):
+    """The batched dE of the prediction heads: A [M x K] (fp32, split in-kernel) times a K-major B produced by the
+    transposing split, reduction K cut across CTAs."""
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    a = torch.randn(batch, M, K, device=DEV, generator=g)
+    f = torch.randn(batch, K, N, device=DEV, generator=g)                  # stored reduction-major, like the tokens
+    hi, lo = native.transpose_split_bf16(f)
+    y = native.gemm_bf16x3_splitk(a, hi, lo, splits)
+    r = a.double() @ f.double()
+    assert y.shape == (batch, M, N)
+    assert (y.double() - r).abs().max().item() / K ** 0.5 < TOL
