@@ -317,6 +317,26 @@ int mpf_groupnorm_nchw2cl_bwd_f32(const float* dy, const float* x, const float* 
                                   const float* mean, const float* rstd, int batch, long long HW, int C, int groups,
                                   int relu, float* dx, float* dgamma_dbeta, double* stats_ws, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * 3x3 convolution (stride 1, zero padding 1) of a channels-last map on the bf16x3 tensor-core GEMMs
+ * (ref pixel_decoder/msdeformattn.py:268-275 output conv `layer_{i}`, 77 GFLOP per image at stride 4):
+ * K = 9 * Cin runs over (tap, channel); the tap only shifts the TMA box, out-of-map pixels are zero-filled.
+ *   mpf_conv3x3_cl_bf16x3:        y[b,h,w,co] = bias[co] + sum_{ky,kx,ci} x[b,h+ky-1,w+kx-1,ci] * Wm[co,(ky*3+kx)*Cin+ci]
+ *                                 (Wm pre-split by mpf_split_bf16; also the input gradient, with the flipped /
+ *                                 transposed weights);  W % 128 == 0, Cin % 32 == 0, Cout % 4 == 0.
+ *   mpf_conv3x3_cl_wgrad_bf16x3:  dw[s][co][(ky*3+kx)*Cin+ci] = partial sums over the pixels of split s of
+ *                                 dy[b,h,w,co] * x[b,h+ky-1,w+kx-1,ci]  (k_splits slabs, summed by the caller);
+ *                                 W % 32 == 0, Cin % 64 == 0.
+ *   mpf_upsample2x_add_cl_fwd_f32 / mpf_upsample2x_cl_bwd_f32: the FPN merge with both sides channels-last
+ *                                 (the gradient of `cur` is the incoming gradient itself). */
+int mpf_conv3x3_cl_bf16x3(const float* x, const uint16_t* w_hi, const uint16_t* w_lo, const float* bias, float* y,
+                          int batch, int H, int W, int Cin, int Cout, int relu, void* stream);
+int mpf_conv3x3_cl_wgrad_bf16x3(const float* dy, const float* x, float* dw, int batch, int H, int W, int Cin, int Cout,
+                                int k_splits, void* stream);
+int mpf_upsample2x_add_cl_fwd_f32(const float* cur, const float* prev, int batch, int H, int W, int C, float* out,
+                                  void* stream);
+int mpf_upsample2x_cl_bwd_f32(const float* g, int batch, int H, int W, int C, float* g_prev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,6 +58,10 @@ SIGNATURES = {
     "mpf_groupnorm_cl_bwd_f32": (_c_int, [_c_vp] * 6 + [_c_int, _c_ll, _c_int, _c_int, _c_int] + [_c_vp] * 4),
     "mpf_groupnorm_nchw2cl_fwd_f32": (_c_int, [_c_vp] * 3 + [ctypes.c_float, _c_int, _c_ll, _c_int, _c_int, _c_int] + [_c_vp] * 5),
     "mpf_groupnorm_nchw2cl_bwd_f32": (_c_int, [_c_vp] * 6 + [_c_int, _c_ll, _c_int, _c_int, _c_int] + [_c_vp] * 4),
+    "mpf_conv3x3_cl_bf16x3": (_c_int, [_c_vp] * 5 + [_c_int] * 6 + [_c_vp]),
+    "mpf_conv3x3_cl_wgrad_bf16x3": (_c_int, [_c_vp] * 3 + [_c_int] * 6 + [_c_vp]),
+    "mpf_upsample2x_add_cl_fwd_f32": (_c_int, [_c_vp] * 2 + [_c_int] * 4 + [_c_vp] * 2),
+    "mpf_upsample2x_cl_bwd_f32": (_c_int, [_c_vp] + [_c_int] * 4 + [_c_vp] * 2),
     "mpf_upsample2x_add_nchw_fwd_f32": (_c_int, [_c_vp] * 2 + [_c_int] * 4 + [_c_vp] * 2),
     "mpf_upsample2x_add_nchw_bwd_f32": (_c_int, [_c_vp] + [_c_int] * 4 + [_c_vp] * 3),
     "mpf_attn_mask_bits_f32": (_c_int, [_c_vp, _c_ll] + [_c_int] * 5 + [_c_vp, _c_int, _c_vp]),

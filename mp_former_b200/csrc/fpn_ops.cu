@@ -186,6 +186,76 @@ upsample2x_add_nchw_bwd_kernel(const float* __restrict__ g, int H, int W, int C,
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same merge with BOTH sides channels-last, for the path where the 3x3 convolution runs on this library's
+// tensor-core GEMM (mpf_conv3x3_cl_bf16x3) and no layout change is needed:
+//   fwd: out[b,h,w,:] = cur[b,h,w,:] + bilinear_x2(prev)[b,h,w,:]        one float4 of channels per thread
+//   bwd: g_cur = g (the same tensor);  g_prev[b,i,j,:] = 4x4 clamped stencil of g     one float4 per thread
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+upsample2x_add_cl_fwd_kernel(const float* __restrict__ cur, const float* __restrict__ prev, int H, int W, int C,
+                             long long total4, float* __restrict__ out) {
+  const int Hp = H >> 1, Wp = W >> 1, c4n = C >> 2;
+  for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < total4;
+       i += static_cast<long long>(gridDim.x) * kThreads) {
+    const int c4 = static_cast<int>(i % c4n);
+    long long p = i / c4n;
+    const int x = static_cast<int>(p % W);
+    p /= W;
+    const int h = static_cast<int>(p % H);
+    const int b = static_cast<int>(p / H);
+    const float ys = fmaxf(0.5f * (static_cast<float>(h) + 0.5f) - 0.5f, 0.f);
+    const int y0 = static_cast<int>(ys), y1 = y0 + (y0 < Hp - 1 ? 1 : 0);
+    const float ly1 = ys - static_cast<float>(y0), ly0 = 1.f - ly1;
+    const float xs = fmaxf(0.5f * (static_cast<float>(x) + 0.5f) - 0.5f, 0.f);
+    const int xa = static_cast<int>(xs), xb = xa + (xa < Wp - 1 ? 1 : 0);
+    const float lx1 = xs - static_cast<float>(xa), lx0 = 1.f - lx1;
+    const float* pb = prev + static_cast<long long>(b) * Hp * Wp * C + 4 * c4;
+    const float4 a = ld4(cur + i * 4);
+    const float4 v00 = ld4(pb + (static_cast<long long>(y0) * Wp + xa) * C), v01 = ld4(pb + (static_cast<long long>(y0) * Wp + xb) * C);
+    const float4 v10 = ld4(pb + (static_cast<long long>(y1) * Wp + xa) * C), v11 = ld4(pb + (static_cast<long long>(y1) * Wp + xb) * C);
+    float4 o;
+    o.x = a.x + (ly0 * (lx0 * v00.x + lx1 * v01.x) + ly1 * (lx0 * v10.x + lx1 * v11.x));
+    o.y = a.y + (ly0 * (lx0 * v00.y + lx1 * v01.y) + ly1 * (lx0 * v10.y + lx1 * v11.y));
+    o.z = a.z + (ly0 * (lx0 * v00.z + lx1 * v01.z) + ly1 * (lx0 * v10.z + lx1 * v11.z));
+    o.w = a.w + (ly0 * (lx0 * v00.w + lx1 * v01.w) + ly1 * (lx0 * v10.w + lx1 * v11.w));
+    st4(out + i * 4, o);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+upsample2x_cl_bwd_kernel(const float* __restrict__ g, int H, int W, int C, long long total4,
+                         float* __restrict__ g_prev) {
+  const int Hp = H >> 1, Wp = W >> 1, c4n = C >> 2;
+  for (long long idx = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; idx < total4;
+       idx += static_cast<long long>(gridDim.x) * kThreads) {
+    const int c4 = static_cast<int>(idx % c4n);
+    long long p = idx / c4n;
+    const int j = static_cast<int>(p % Wp);
+    p /= Wp;
+    const int i = static_cast<int>(p % Hp);
+    const int b = static_cast<int>(p / Hp);
+    const float* gb = g + static_cast<long long>(b) * H * W * C + 4 * c4;
+    const float w4[4] = {0.25f, 0.75f, 0.75f, 0.25f};
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int dy = 0; dy < 4; ++dy) {
+      int row = 2 * i - 1 + dy;
+      row = row < 0 ? 0 : (row > H - 1 ? H - 1 : row);
+      float4 ra = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int dx = 0; dx < 4; ++dx) {
+        int col = 2 * j - 1 + dx;
+        col = col < 0 ? 0 : (col > W - 1 ? W - 1 : col);
+        const float4 v = ld4(gb + (static_cast<long long>(row) * W + col) * C);
+        ra.x += w4[dx] * v.x; ra.y += w4[dx] * v.y; ra.z += w4[dx] * v.z; ra.w += w4[dx] * v.w;
+      }
+      acc.x += w4[dy] * ra.x; acc.y += w4[dy] * ra.y; acc.z += w4[dy] * ra.z; acc.w += w4[dy] * ra.w;
+    }
+    st4(g_prev + idx * 4, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // GroupNorm (+ReLU), NCHW in -> channels-last out
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum_d(double v) {
@@ -495,6 +565,41 @@ int mpf_upsample2x_add_nchw_bwd_f32(const float* g, int batch, int H, int W, int
   upsample2x_add_nchw_bwd_kernel<<<grid, kThreads, kBSmem, static_cast<cudaStream_t>(stream)>>>(g, H, W, C, g_cur, g_prev);
   count_launch();
   return finish_launch("upsample2x_add_bwd");
+}
+
+int mpf_upsample2x_add_cl_fwd_f32(const float* cur, const float* prev, int batch, int H, int W, int C, float* out,
+                                  void* stream) {
+  using namespace mpf;
+  using namespace mpf::fpn;
+  clear_error();
+  MPF_REQUIRE(cur && prev && out, "upsample2x_add_cl_fwd: null pointer argument");
+  MPF_REQUIRE(batch > 0 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0 && C > 0 && C % 4 == 0,
+              "upsample2x_add_cl_fwd: needs even H, W and C %% 4 == 0 (H=%d W=%d C=%d)", H, W, C);
+  MPF_REQUIRE(aligned16(cur) && aligned16(prev) && aligned16(out), "upsample2x_add_cl_fwd: 16-byte alignment");
+  const long long total4 = static_cast<long long>(batch) * H * W * (C / 4);
+  long long blocks = (total4 + kThreads - 1) / kThreads;
+  if (blocks > 148ll * 32) blocks = 148ll * 32;
+  upsample2x_add_cl_fwd_kernel<<<static_cast<int>(blocks), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      cur, prev, H, W, C, total4, out);
+  count_launch();
+  return finish_launch("upsample2x_add_cl_fwd");
+}
+
+int mpf_upsample2x_cl_bwd_f32(const float* g, int batch, int H, int W, int C, float* g_prev, void* stream) {
+  using namespace mpf;
+  using namespace mpf::fpn;
+  clear_error();
+  MPF_REQUIRE(g && g_prev, "upsample2x_cl_bwd: null pointer argument");
+  MPF_REQUIRE(batch > 0 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0 && C > 0 && C % 4 == 0,
+              "upsample2x_cl_bwd: needs even H, W and C %% 4 == 0 (H=%d W=%d C=%d)", H, W, C);
+  MPF_REQUIRE(aligned16(g) && aligned16(g_prev), "upsample2x_cl_bwd: 16-byte alignment");
+  const long long total4 = static_cast<long long>(batch) * (H / 2) * (W / 2) * (C / 4);
+  long long blocks = (total4 + kThreads - 1) / kThreads;
+  if (blocks > 148ll * 32) blocks = 148ll * 32;
+  upsample2x_cl_bwd_kernel<<<static_cast<int>(blocks), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(g, H, W, C,
+                                                                                                      total4, g_prev);
+  count_launch();
+  return finish_launch("upsample2x_cl_bwd");
 }
 
 int mpf_groupnorm_nchw2cl_fwd_f32(const float* x, const float* gamma, const float* beta, float eps, int batch,

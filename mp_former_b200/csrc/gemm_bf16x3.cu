@@ -60,6 +60,11 @@ struct Args {
   int relu, transpose_c, split_out, vec_aux;
   int b_broadcast;                            // B has no batch dimension (shared weight)
   int debug;
+  // 3x3 convolution mode (conv_wt > 0): A is a channels-last map [batch, H, W, Cin] behind a 4-D tensor map with
+  // box {32 channels, 128 pixels of one row}; an M tile is 128 consecutive pixels of a row, K = 9 * Cin runs over
+  // (tap, channel block) and the tap only shifts the box: pixels outside the map are zero-filled by TMA.
+  int conv_wt;                                // tiles per image row (W / 128)
+  int conv_cb;                                // channel blocks per tap (Cin / 32)
 };
 
 __device__ __forceinline__ void tma_load_3d_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
@@ -190,7 +195,16 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * g.stage_bytes;
           mbar_arrive_expect_tx(&full[stage], (ldA ? kRawABytes : 0) + (ldB ? 2 * b_bytes : 0));
-          if (ldA) tma_load_3d(st, &tmA, &full[stage], kb * kBK, m_t * kBM, b);
+          if (ldA) {
+            if (g.conv_wt) {
+              const int y = m_t / g.conv_wt, x0 = (m_t - y * g.conv_wt) * kBM;
+              const int tap = kb / g.conv_cb, c0 = (kb - tap * g.conv_cb) * kBK;
+              const int ty = tap / 3;
+              tma_load_4d(st, &tmA, &full[stage], c0, x0 + (tap - 3 * ty) - 1, y + ty - 1, b);
+            } else {
+              tma_load_3d(st, &tmA, &full[stage], kb * kBK, m_t * kBM, b);
+            }
+          }
           if (ldB) {
             uint8_t* bs = st + kRawABytes + 2 * kOpABytes;
             tma_load_3d(bs, &tmBhi, &full[stage], kb * kBK, n_t * BN, bb);
@@ -553,6 +567,36 @@ static int make_tmap_3d(CUtensorMap* m, CUtensorMapDataType dt, int esize, const
   return MPF_OK;
 }
 
+// channels-last fp32 map [d3, d2, d1, d0 = channels] (dense), box {box0 channels, box1 pixels of one row, 1, 1},
+// SWIZZLE_128B (box0 * 4 == 128); coordinates outside the map read as zero.
+static int make_tmap_f32_4d(CUtensorMap* m, const float* base, long long d0, long long d1, long long d2, long long d3,
+                            int box0, int box1, const char* what) {
+  EncodeFn enc = encoder();
+  if (enc == nullptr) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return MPF_ERR_UNSUPPORTED;
+  }
+  if (box0 * 4 != 128 || d0 % 4 != 0 || !aligned16(base)) {
+    set_error("gemm_bf16x3: %s needs a 16-byte aligned base, channels %% 4 == 0 and a 128-byte box row", what);
+    return MPF_ERR_BAD_ARG;
+  }
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(d0), static_cast<cuuint64_t>(d1), static_cast<cuuint64_t>(d2),
+                        static_cast<cuuint64_t>(d3)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(d0) * 4, static_cast<cuuint64_t>(d0) * d1 * 4,
+                           static_cast<cuuint64_t>(d0) * d1 * d2 * 4};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(box0), static_cast<cuuint32_t>(box1), 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(%s, 4-D) failed (CUresult %d): dims=(%lld,%lld,%lld,%lld)", what,
+              static_cast<int>(r), d0, d1, d2, d3);
+    return MPF_ERR_BAD_ARG;
+  }
+  return MPF_OK;
+}
+
 static int pick_bn(int N) {
   if (N <= 64) return 64;
   for (int bn = 256; bn >= 64; bn -= 32) {
@@ -593,11 +637,14 @@ int mpf_transpose_split_bf16(const float* x, uint16_t* hi, uint16_t* lo, int bat
   return finish_launch("transpose_split_bf16");
 }
 
-int mpf_gemm_bf16x3(const float* A, long long lda, long long a_batch_stride, const uint16_t* B_hi,
-                    const uint16_t* B_lo, long long ldb, long long b_batch_stride, const float* bias, float* C,
-                    float* C_lo, long long ldc, long long c_batch_stride, const float* resid, long long resid_ld,
-                    int resid_rows, int resid_cols, const float* gate, long long gate_ld, float alpha, int batch,
-                    int M, int N, int K, int k_splits, int relu, int transpose_c, void* stream) {
+// conv_H > 0: 3x3 convolution of the channels-last map A [batch, conv_H, conv_W, conv_C] (M = conv_H * conv_W,
+// K = 9 * conv_C; lda / a_batch_stride unused)
+static int gemm_bf16x3_impl(const float* A, long long lda, long long a_batch_stride, const uint16_t* B_hi,
+                            const uint16_t* B_lo, long long ldb, long long b_batch_stride, const float* bias, float* C,
+                            float* C_lo, long long ldc, long long c_batch_stride, const float* resid,
+                            long long resid_ld, int resid_rows, int resid_cols, const float* gate, long long gate_ld,
+                            float alpha, int batch, int M, int N, int K, int k_splits, int relu, int transpose_c,
+                            int conv_H, int conv_W, int conv_C, void* stream) {
   using namespace mpf;
   using namespace mpf::bf3;
   clear_error();
@@ -629,8 +676,16 @@ int mpf_gemm_bf16x3(const float* A, long long lda, long long a_batch_stride, con
   const int slabs = batch * k_splits;
 
   CUtensorMap ta, tbh, tbl, tc, tcl;
-  int rc = make_tmap_3d(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, A, K, M, batch, lda, a_batch_stride, kBK, kBM,
-                        CU_TENSOR_MAP_SWIZZLE_128B, "A");
+  int rc;
+  g.conv_wt = g.conv_cb = 0;
+  if (conv_H > 0) {
+    g.conv_wt = conv_W / kBM;
+    g.conv_cb = conv_C / kBK;
+    rc = make_tmap_f32_4d(&ta, A, conv_C, conv_W, conv_H, batch, kBK, kBM, "conv input");
+  } else {
+    rc = make_tmap_3d(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, A, K, M, batch, lda, a_batch_stride, kBK, kBM,
+                      CU_TENSOR_MAP_SWIZZLE_128B, "A");
+  }
   if (rc) return rc;
   const long long nb = g.b_broadcast ? 1 : batch;
   rc = make_tmap_3d(&tbh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B_hi, K, N, nb, ldb, b_batch_stride, kBK, g.bn,
@@ -678,6 +733,29 @@ int mpf_gemm_bf16x3(const float* A, long long lda, long long a_batch_stride, con
   gemm_bf16x3_kernel<<<grid, kThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(ta, tbh, tbl, tc, tcl, g);
   count_launch();
   return finish_launch("gemm_bf16x3");
+}
+
+int mpf_gemm_bf16x3(const float* A, long long lda, long long a_batch_stride, const uint16_t* B_hi,
+                    const uint16_t* B_lo, long long ldb, long long b_batch_stride, const float* bias, float* C,
+                    float* C_lo, long long ldc, long long c_batch_stride, const float* resid, long long resid_ld,
+                    int resid_rows, int resid_cols, const float* gate, long long gate_ld, float alpha, int batch,
+                    int M, int N, int K, int k_splits, int relu, int transpose_c, void* stream) {
+  return gemm_bf16x3_impl(A, lda, a_batch_stride, B_hi, B_lo, ldb, b_batch_stride, bias, C, C_lo, ldc, c_batch_stride,
+                          resid, resid_ld, resid_rows, resid_cols, gate, gate_ld, alpha, batch, M, N, K, k_splits, relu,
+                          transpose_c, 0, 0, 0, stream);
+}
+
+int mpf_conv3x3_cl_bf16x3(const float* x, const uint16_t* w_hi, const uint16_t* w_lo, const float* bias, float* y,
+                          int batch, int H, int W, int Cin, int Cout, int relu, void* stream) {
+  using namespace mpf;
+  clear_error();
+  MPF_REQUIRE(x && w_hi && w_lo && y, "conv3x3_cl: null pointer argument");
+  MPF_REQUIRE(batch > 0 && H > 0 && W > 0 && W % 128 == 0 && Cin > 0 && Cin % 32 == 0 && Cout > 0 && Cout % 4 == 0,
+              "conv3x3_cl: needs W %% 128 == 0, Cin %% 32 == 0, Cout %% 4 == 0 (H=%d W=%d Cin=%d Cout=%d)", H, W, Cin, Cout);
+  MPF_REQUIRE(static_cast<long long>(H) * W < (1ll << 31) / 2, "conv3x3_cl: map too large");
+  const int M = H * W, K = 9 * Cin;
+  return gemm_bf16x3_impl(x, K, 0, w_hi, w_lo, K, 0, bias, y, nullptr, Cout, static_cast<long long>(M) * Cout, nullptr, 0,
+                          0, 0, nullptr, 0, 1.0f, batch, M, Cout, K, 1, relu, 0, H, W, Cin, stream);
 }
 
 }  // extern "C"

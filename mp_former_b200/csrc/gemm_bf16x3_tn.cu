@@ -47,6 +47,11 @@ struct Args {
   int raw_bytes, op_bytes;                     // per ring slot
   int debug;
   int accumulate;                              // 1: C += product (TMA reduce-add store) instead of C = product
+  // weight gradient of a 3x3 convolution over channels-last maps (conv_W > 0): the reduction index is the pixel
+  // (b, y, x), A = dY tokens [T, Cout]; B is the INPUT map [batch, H, W, Cin] behind a 4-D tensor map and the N tile
+  // selects (tap, channel range): the tap only shifts the 32-pixel box, pixels outside the map read as zero.
+  int conv_W, conv_HW;                         // W and H * W
+  int conv_nt;                                 // N tiles per tap (Cin / bn)
 };
 
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
@@ -186,8 +191,18 @@ gemm_bf16x3_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           mbar_arrive_expect_tx(&raw_full[slot], (4 + b_boxes) * kBoxBytes);
 #pragma unroll
           for (int i = 0; i < 4; ++i) tma_load_3d(st + i * kBoxBytes, &tmA, &raw_full[slot], m_t * kBM + i * 32, t0, b);
-          for (int j = 0; j < b_boxes; ++j)
-            tma_load_3d(st + (4 + j) * kBoxBytes, &tmB, &raw_full[slot], n_t * BN + j * 32, t0, b);
+          if (g.conv_W) {
+            const int tap = n_t / g.conv_nt, c0 = (n_t - tap * g.conv_nt) * BN;
+            const int img = t0 / g.conv_HW, rem = t0 - img * g.conv_HW;
+            const int y = rem / g.conv_W, x0 = rem - y * g.conv_W;
+            const int ty = tap / 3;
+            for (int j = 0; j < b_boxes; ++j)
+              tma_load_4d(st + (4 + j) * kBoxBytes, &tmB, &raw_full[slot], c0 + j * 32, x0 + (tap - 3 * ty) - 1,
+                          y + ty - 1, img);
+          } else {
+            for (int j = 0; j < b_boxes; ++j)
+              tma_load_3d(st + (4 + j) * kBoxBytes, &tmB, &raw_full[slot], n_t * BN + j * 32, t0, b);
+          }
           if (++slot == kRing) { slot = 0; phase ^= 1; }
         }
       }
@@ -390,14 +405,46 @@ static int make_tmap(CUtensorMap* m, const float* base, long long d0, long long 
   return MPF_OK;
 }
 
+// channels-last fp32 map [d3, d2, d1, d0 = channels], box {32 channels, 32 pixels of one row, 1, 1}, SWIZZLE_128B
+static int make_tmap_4d(CUtensorMap* m, const float* base, long long d0, long long d1, long long d2, long long d3,
+                        const char* what) {
+  EncodeFn enc = encoder();
+  if (enc == nullptr) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return MPF_ERR_UNSUPPORTED;
+  }
+  if (d0 % 4 != 0 || !aligned16(base)) {
+    set_error("gemm_bf16x3_tn: %s needs a 16-byte aligned base and channels %% 4 == 0", what);
+    return MPF_ERR_BAD_ARG;
+  }
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(d0), static_cast<cuuint64_t>(d1), static_cast<cuuint64_t>(d2),
+                        static_cast<cuuint64_t>(d3)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(d0) * 4, static_cast<cuuint64_t>(d0) * d1 * 4,
+                           static_cast<cuuint64_t>(d0) * d1 * d2 * 4};
+  cuuint32_t box[4] = {32, static_cast<cuuint32_t>(kBK), 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(%s, 4-D) failed (CUresult %d): dims=(%lld,%lld,%lld,%lld)", what,
+              static_cast<int>(r), d0, d1, d2, d3);
+    return MPF_ERR_BAD_ARG;
+  }
+  return MPF_OK;
+}
+
 }  // namespace bf3tn
 }  // namespace mpf
 
 extern "C" {
 
-int mpf_gemm_bf16x3_tn_ex(const float* A, long long lda, long long a_batch_stride, const float* B, long long ldb,
-                          long long b_batch_stride, float* C, long long ldc, long long c_batch_stride, int batch, int M,
-                          int N, int T, int k_splits, int accumulate, void* stream) {
+// conv_H > 0: weight gradient of a 3x3 convolution; B = the channels-last input map [conv_B, conv_H, conv_W, conv_C],
+// N = 9 * conv_C, T = conv_B * conv_H * conv_W, batch = 1 (ldb / b_batch_stride unused)
+static int gemm_bf16x3_tn_impl(const float* A, long long lda, long long a_batch_stride, const float* B, long long ldb,
+                               long long b_batch_stride, float* C, long long ldc, long long c_batch_stride, int batch,
+                               int M, int N, int T, int k_splits, int accumulate, int conv_B, int conv_H, int conv_W,
+                               int conv_C, void* stream) {
   using namespace mpf;
   using namespace mpf::bf3tn;
   clear_error();
@@ -409,12 +456,13 @@ int mpf_gemm_bf16x3_tn_ex(const float* A, long long lda, long long a_batch_strid
   g.bn = 64;
   long long best_cost = -1;
   for (int bn = 64; bn <= 256; bn += 64) {
+    if (conv_H > 0 && conv_C % bn != 0) continue;          // an N tile must not straddle two taps
     const long long cost = static_cast<long long>((N + bn - 1) / bn) * (bn + 128);
     if (best_cost < 0 || cost <= best_cost) { best_cost = cost; g.bn = bn; }
   }
   if (const char* force = getenv("MPF_GEMM_BN")) {
     const int f = atoi(force);
-    if (f >= 64 && f <= 256 && f % 64 == 0) g.bn = f;
+    if (f >= 64 && f <= 256 && f % 64 == 0 && (conv_H == 0 || conv_C % f == 0)) g.bn = f;
   }
   g.batch = batch; g.M = M; g.N = N; g.T = T;
   g.tiles_m = (M + kBM - 1) / kBM;
@@ -435,7 +483,15 @@ int mpf_gemm_bf16x3_tn_ex(const float* A, long long lda, long long a_batch_strid
   CUtensorMap ta, tb, tc;
   int rc = make_tmap(&ta, A, M, T, batch, lda, a_batch_stride, kBK, "A");
   if (rc) return rc;
-  rc = make_tmap(&tb, B, N, T, batch, ldb, b_batch_stride, kBK, "B");
+  g.conv_W = g.conv_HW = g.conv_nt = 0;
+  if (conv_H > 0) {
+    g.conv_W = conv_W;
+    g.conv_HW = conv_H * conv_W;
+    g.conv_nt = conv_C / g.bn;
+    rc = make_tmap_4d(&tb, B, conv_C, conv_W, conv_H, conv_B, "conv input");
+  } else {
+    rc = make_tmap(&tb, B, N, T, batch, ldb, b_batch_stride, kBK, "B");
+  }
   if (rc) return rc;
   rc = make_tmap(&tc, C, N, M, static_cast<long long>(batch) * k_splits, ldc, c_batch_stride, kBM, "C");
   if (rc) return rc;
@@ -450,6 +506,28 @@ int mpf_gemm_bf16x3_tn_ex(const float* A, long long lda, long long a_batch_strid
   gemm_bf16x3_tn_kernel<<<grid, kThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(ta, tb, tc, g);
   count_launch();
   return finish_launch("gemm_bf16x3_tn");
+}
+
+int mpf_gemm_bf16x3_tn_ex(const float* A, long long lda, long long a_batch_stride, const float* B, long long ldb,
+                          long long b_batch_stride, float* C, long long ldc, long long c_batch_stride, int batch, int M,
+                          int N, int T, int k_splits, int accumulate, void* stream) {
+  return gemm_bf16x3_tn_impl(A, lda, a_batch_stride, B, ldb, b_batch_stride, C, ldc, c_batch_stride, batch, M, N, T,
+                             k_splits, accumulate, 0, 0, 0, 0, stream);
+}
+
+int mpf_conv3x3_cl_wgrad_bf16x3(const float* dy, const float* x, float* dw, int batch, int H, int W, int Cin, int Cout,
+                                int k_splits, void* stream) {
+  using namespace mpf;
+  clear_error();
+  MPF_REQUIRE(dy && x && dw, "conv3x3_cl_wgrad: null pointer argument");
+  MPF_REQUIRE(batch > 0 && H > 0 && W > 0 && W % 32 == 0 && Cin > 0 && Cin % 64 == 0 && Cout > 0 && Cout % 4 == 0,
+              "conv3x3_cl_wgrad: needs W %% 32 == 0, Cin %% 64 == 0, Cout %% 4 == 0 (H=%d W=%d Cin=%d Cout=%d)", H, W, Cin,
+              Cout);
+  const long long T = static_cast<long long>(batch) * H * W;
+  MPF_REQUIRE(T < (1ll << 31), "conv3x3_cl_wgrad: too many pixels");
+  const int N = 9 * Cin;
+  return gemm_bf16x3_tn_impl(dy, Cout, 0, x, N, 0, dw, N, static_cast<long long>(Cout) * N, 1, Cout, N,
+                             static_cast<int>(T), k_splits, 0, batch, H, W, Cin, stream);
 }
 
 int mpf_gemm_bf16x3_tn(const float* A, long long lda, long long a_batch_stride, const float* B, long long ldb,

@@ -391,6 +391,77 @@ def upsample2x_add_nchw_bwd(g):
     return g_cur, g_prev
 
 
+def conv3x3_cl_ok(H, W, Cin, Cout):
+    """Geometry covered by the tensor-core 3x3 convolution (forward / input gradient / weight gradient)."""
+    return GEMM_MODE == "bf16x3" and W % 128 == 0 and Cin % 64 == 0 and Cout % 64 == 0
+
+
+def conv3x3_cl(x, w_hi, w_lo, bias=None, relu=False):
+    """x [B, H, W, Cin] fp32 contiguous (channels-last); w_hi / w_lo bf16 [Cout, 9*Cin] with column (ky*3+kx)*Cin + ci
+    -> y [B, H, W, Cout]: 3x3 convolution, stride 1, zero padding 1, on the bf16x3 tensor-core GEMM."""
+    x = _f32c(x, "x")
+    if x.dim() != 4 or not x.is_contiguous():
+        raise RuntimeError("conv3x3_cl: x must be a contiguous [B, H, W, C] tensor")
+    B, H, W, Cin = x.shape
+    Cout = w_hi.shape[0]
+    if w_hi.shape != (Cout, 9 * Cin) or w_lo.shape != w_hi.shape or w_hi.dtype != torch.bfloat16:
+        raise RuntimeError(f"conv3x3_cl: weight halves must be bf16 [{Cout}, {9 * Cin}]")
+    y = torch.empty((B, H, W, Cout), dtype=torch.float32, device=x.device)
+    flops = 2.0 * B * H * W * Cout * 9 * Cin
+    with torch.cuda.device(x.device), _Timed("gemm_bf16x3_kernel", flops, 4.0 * B * H * W * (Cin + Cout) + 4.0 * Cout * 9 * Cin):
+        rc = _lib.load().mpf_conv3x3_cl_bf16x3(x.data_ptr(), w_hi.contiguous().data_ptr(), w_lo.contiguous().data_ptr(),
+                                               None if bias is None else _f32c(bias, "bias").contiguous().data_ptr(),
+                                               y.data_ptr(), B, H, W, Cin, Cout, int(relu), _stream())
+    _lib.check(rc, "conv3x3_cl")
+    return y
+
+
+def conv3x3_cl_wgrad(dy, x, target_tiles=296):
+    """dy [B, H, W, Cout], x [B, H, W, Cin] (channels-last, contiguous) -> dW as [Cout, 9*Cin] (column (ky*3+kx)*Cin+ci):
+    reduction over all pixels on the TN GEMM, the input map consumed tap by tap through shifted TMA boxes."""
+    dy, x = _f32c(dy, "dy"), _f32c(x, "x")
+    if not (dy.is_contiguous() and x.is_contiguous()) or dy.shape[:3] != x.shape[:3]:
+        raise RuntimeError("conv3x3_cl_wgrad: dy / x must be contiguous [B, H, W, C] tensors of the same map size")
+    B, H, W, Cin = x.shape
+    Cout = dy.shape[3]
+    N = 9 * Cin
+    tiles = ((Cout + 127) // 128) * ((N + 255) // 256)
+    T = B * H * W
+    splits = max(1, min(148, target_tiles // max(1, tiles), (T + 1023) // 1024))
+    out = torch.empty((splits, Cout, N), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device), _Timed("gemm_bf16x3_tn_kernel", 2.0 * T * Cout * N, 4.0 * T * (Cout * ((N + 255) // 256) + N)):
+        rc = _lib.load().mpf_conv3x3_cl_wgrad_bf16x3(dy.data_ptr(), x.data_ptr(), out.data_ptr(), B, H, W, Cin, Cout, splits,
+                                                     _stream())
+    _lib.check(rc, "conv3x3_cl_wgrad")
+    return out.sum(0) if splits > 1 else out[0]
+
+
+def upsample2x_add_cl_fwd(cur, prev):
+    """cur [B, H, W, C], prev [B, H/2, W/2, C] (channels-last, contiguous) -> cur + bilinear_x2(prev), channels-last."""
+    cur, prev = _f32c(cur, "cur"), _f32c(prev, "prev")
+    B, H, W, C = cur.shape
+    if prev.shape != (B, H // 2, W // 2, C) or not cur.is_contiguous() or not prev.is_contiguous():
+        raise RuntimeError(f"upsample2x_add_cl: shapes {tuple(cur.shape)} / {tuple(prev.shape)} (contiguous channels-last)")
+    out = torch.empty_like(cur)
+    with torch.cuda.device(cur.device):
+        rc = _lib.load().mpf_upsample2x_add_cl_fwd_f32(cur.data_ptr(), prev.data_ptr(), B, H, W, C, out.data_ptr(), _stream())
+    _lib.check(rc, "upsample2x_add_cl_fwd")
+    return out
+
+
+def upsample2x_cl_bwd(g):
+    """g [B, H, W, C] channels-last contiguous -> gradient of the x2-upsampled map [B, H/2, W/2, C]."""
+    g = _f32c(g, "g")
+    if not g.is_contiguous():
+        g = g.contiguous()
+    B, H, W, C = g.shape
+    g_prev = torch.empty((B, H // 2, W // 2, C), dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device):
+        rc = _lib.load().mpf_upsample2x_cl_bwd_f32(g.data_ptr(), B, H, W, C, g_prev.data_ptr(), _stream())
+    _lib.check(rc, "upsample2x_cl_bwd")
+    return g_prev
+
+
 def colsum(x2):
     """Column sums of a [rows, C] fp32 matrix (row stride a multiple of 4): the bias gradient of a Linear layer."""
     x2 = _f32c(x2, "x")

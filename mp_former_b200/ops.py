@@ -18,6 +18,7 @@ import torch.nn.functional as F
 from . import _lib, native
 
 NATIVE_OPS = {"ms_deform_attn_forward", "ms_deform_attn_backward", "linear fwd+bwd (bf16x3 tcgen05 GEMM, TMA in/out)",
+              "conv3x3 fwd+bwd (bf16x3 tcgen05 GEMM, taps as shifted TMA boxes)",
               "mask_logits fwd+bwd (bf16x3 / 3xTF32 tcgen05 GEMM)", "attn_mask_bits", "gt_mask_area_bits",
               "masked_cross_attention fwd+bwd (tcgen05)"}
 
@@ -213,6 +214,7 @@ def add_layer_norm(x, r, norm):
 
 _NO_GN_KERNEL = bool(os.environ.get("MPF_NO_GN_KERNEL"))     # A/B switches for benchmarks only
 NO_FUSED_ENCODER_LAYER = bool(os.environ.get("MPF_NO_FUSED_ENCODER_LAYER"))
+NO_CONV3X3_KERNEL = bool(os.environ.get("MPF_NO_CONV3X3_KERNEL"))
 
 
 class _GroupNormCL(torch.autograd.Function):
@@ -309,6 +311,82 @@ def upsample2x_add_to_nchw(cur, prev):
             and native.upsample2x_add_ok(cur.shape[2], cur.shape[3], cur.shape[1])
             and cur.permute(0, 2, 3, 1).is_contiguous() and prev.permute(0, 2, 3, 1).is_contiguous()):
         return _Upsample2xAddNCHW.apply(cur, prev)
+    return None
+
+
+class _Upsample2xAddCL(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cur, prev):
+        # cur, prev: logical NCHW in channels-last memory; result likewise
+        out = native.upsample2x_add_cl_fwd(cur.permute(0, 2, 3, 1), prev.permute(0, 2, 3, 1))
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, g):
+        gc = g.permute(0, 2, 3, 1)
+        if not gc.is_contiguous():
+            gc = gc.contiguous()
+        g_prev = native.upsample2x_cl_bwd(gc) if ctx.needs_input_grad[1] else None
+        return gc.permute(0, 3, 1, 2), (None if g_prev is None else g_prev.permute(0, 3, 1, 2))
+
+
+def upsample2x_add_cl(cur, prev):
+    """``cur + F.interpolate(prev, x2, bilinear, align_corners=False)`` with inputs and result channels-last (the FPN
+    merge in front of the tensor-core 3x3 convolution).  None when the geometry is not covered."""
+    if (cur.is_cuda and cur.dtype == torch.float32 and prev.dtype == torch.float32 and cur.dim() == 4
+            and cur.shape[2] == 2 * prev.shape[2] and cur.shape[3] == 2 * prev.shape[3] and cur.shape[1] % 4 == 0
+            and cur.permute(0, 2, 3, 1).is_contiguous() and prev.permute(0, 2, 3, 1).is_contiguous()):
+        return _Upsample2xAddCL.apply(cur, prev)
+    return None
+
+
+class _Conv3x3CL(torch.autograd.Function):
+    """3x3 convolution (stride 1, padding 1) of a channels-last map as ONE tensor-core GEMM per direction: the nine
+    taps are the outer part of the reduction dimension (K = 9 * Cin) and only shift the TMA box of the activation
+    operand, so no im2col buffer, no padded copy and no layout change exist (ref pixel_decoder/msdeformattn.py:268-275;
+    cuDNN's fp32 path for this layer: Winograd on CUDA cores, 6.5 ms forward / 12.7 ms backward at [16,256,256,256])."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        Cout, Cin = weight.shape[0], weight.shape[1]
+        xc = x.permute(0, 2, 3, 1)                                            # [B, H, W, Cin] contiguous
+        w_hi, w_lo = native.split_bf16(weight.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin))
+        y = native.conv3x3_cl(xc, w_hi, w_lo, bias)
+        ctx.save_for_backward(xc, weight)
+        ctx.has_bias = bias is not None
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xc, weight = ctx.saved_tensors
+        Cout, Cin = weight.shape[0], weight.shape[1]
+        g = gy.permute(0, 2, 3, 1)
+        if not g.is_contiguous():
+            g = g.contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            # dX = conv3x3(dY, W') with W'[ci, co, ky, kx] = W[co, ci, 2-ky, 2-kx]
+            wt_hi, wt_lo = native.split_bf16(weight.flip(2, 3).permute(1, 2, 3, 0).reshape(Cin, 9 * Cout))
+            gx = native.conv3x3_cl(g, wt_hi, wt_lo).permute(0, 3, 1, 2)
+        if ctx.needs_input_grad[1]:
+            gw = native.conv3x3_cl_wgrad(g, xc).view(Cout, 3, 3, Cin).permute(0, 3, 1, 2)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = native.colsum(g.reshape(-1, Cout))
+        return gx, gw, gb
+
+
+def conv3x3_cl_supported(x, conv):
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and conv.kernel_size == (3, 3)
+            and conv.stride == (1, 1) and conv.padding == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1
+            and conv.padding_mode == "zeros" and not NO_CONV3X3_KERNEL
+            and native.conv3x3_cl_ok(x.shape[2], x.shape[3], conv.in_channels, conv.out_channels))
+
+
+def conv3x3_cl(x, conv):
+    """``conv`` (nn.Conv2d, 3x3, stride 1, padding 1) on a logically-NCHW map in channels-last memory, result likewise.
+    None when the layer / geometry is not covered (caller uses the library convolution)."""
+    if conv3x3_cl_supported(x, conv) and x.permute(0, 2, 3, 1).is_contiguous():
+        return _Conv3x3CL.apply(x, conv.weight, conv.bias)
     return None
 
 

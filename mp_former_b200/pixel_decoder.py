@@ -327,10 +327,20 @@ class MSDeformAttnPixelDecoder(nn.Module):
             # profiles/README.md r1p): the sum is handed over in NCHW -- written that way by the fused
             # upsample+add kernel -- and the GroupNorm+ReLU behind the convolution returns to channels-last tokens.
             prev = out[-1].contiguous(memory_format=torch.channels_last)
+            oconv = self.output_convs[idx]
+            y = None
+            if ops.conv3x3_cl_supported(cur_fpn, oconv):
+                # everything channels-last: merge -> 3x3 conv on the tensor-core GEMM -> GroupNorm + ReLU
+                merged = ops.upsample2x_add_cl(cur_fpn, prev)
+                if merged is not None:
+                    y = ops.conv3x3_cl(merged, oconv)
+            if y is not None:
+                out.append(oconv.norm_act(y))
+                continue
             y = ops.upsample2x_add_to_nchw(cur_fpn, prev)
             if y is None:
                 up = F.interpolate(prev, size=cur_fpn.shape[-2:], mode="bilinear", align_corners=False)
                 y = (cur_fpn + up).contiguous()
-            out.append(self.output_convs[idx](y))
+            out.append(oconv(y))
         multi_scale_features = out[:self.maskformer_num_feature_levels]
         return conv1x1_tokens(out[-1], self.mask_features), out[0], multi_scale_features

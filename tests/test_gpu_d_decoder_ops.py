@@ -399,3 +399,59 @@ def test_collected_mask_heads_batched_backward(n_dn):
             assert a is None or a.abs().max().item() == 0.0
         else:
             assert rel(a, e.grad) < TOL, h
+
+
+class _Conv(torch.nn.Conv2d):
+    pass
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W,bias", [(2, 64, 64, 8, 128, True), (1, 256, 256, 16, 256, False),
+                                                 (2, 128, 64, 5, 128, False), (1, 64, 192, 33, 384, True)])
+def test_conv3x3_channels_last_tensor_core(B, Cin, Cout, H, W, bias):
+    """3x3 convolution as one GEMM with K = 9*Cin (taps = shifted TMA boxes, zero-filled outside the map), forward,
+    input gradient (same kernel, flipped/transposed weights) and weight gradient (TN GEMM over all pixels) vs
+    F.conv2d in fp64 (ref pixel_decoder/msdeformattn.py:268-275)."""
+    g = torch.Generator(device=DEV).manual_seed(B + Cin + H + W)
+    conv = _Conv(Cin, Cout, 3, padding=1, bias=bias).to(DEV)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(Cout, Cin, 3, 3, device=DEV, generator=g) / (9 * Cin) ** 0.5)
+        if bias:
+            conv.bias.copy_(torch.randn(Cout, device=DEV, generator=g))
+    x = torch.randn(B, Cin, H, W, device=DEV, generator=g).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    assert ops.conv3x3_cl_supported(x, conv)
+    y = ops.conv3x3_cl(x, conv)
+    assert y is not None and y.shape == (B, Cout, H, W) and y.permute(0, 2, 3, 1).is_contiguous()
+    gy = torch.randn(B, Cout, H, W, device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    y.backward(gy)
+    xr = x.detach().double().requires_grad_(True)
+    wr = conv.weight.detach().double().requires_grad_(True)
+    br = conv.bias.detach().double().requires_grad_(True) if bias else None
+    yr = F.conv2d(xr, wr, br, padding=1)
+    yr.backward(gy.double())
+    assert rel(y, yr) < TOL, rel(y, yr)
+    assert rel(x.grad, xr.grad) < TOL, rel(x.grad, xr.grad)
+    T = B * H * W
+    assert (conv.weight.grad.double() - wr.grad).abs().max().item() / T ** 0.5 < TOL
+    if bias:
+        assert (conv.bias.grad.double() - br.grad).abs().max().item() / T ** 0.5 < TOL
+    # geometry outside the kernel's cover
+    assert ops.conv3x3_cl(torch.randn(1, Cin, 8, 100, device=DEV).contiguous(memory_format=torch.channels_last), conv) is None
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 64, 8, 8), (1, 128, 34, 52), (2, 256, 64, 160), (1, 4, 2, 2)])
+def test_upsample2x_add_channels_last(B, C, H, W):
+    """The FPN merge with both sides channels-last (in front of the tensor-core 3x3 convolution) vs torch."""
+    g = torch.Generator(device=DEV).manual_seed(B + C + H + W)
+    cur = torch.randn(B, C, H, W, device=DEV, generator=g).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    prev = torch.randn(B, C, H // 2, W // 2, device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    prev.requires_grad_(True)
+    y = ops.upsample2x_add_cl(cur, prev)
+    assert y is not None and y.permute(0, 2, 3, 1).is_contiguous()
+    ref32 = cur.detach() + F.interpolate(prev.detach(), size=(H, W), mode="bilinear", align_corners=False)
+    assert (y.detach() - ref32).abs().max().item() < 2e-6
+    gy = torch.randn(B, C, H, W, device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    y.backward(gy)
+    cr, pr = cur.detach().double().requires_grad_(True), prev.detach().double().requires_grad_(True)
+    (cr + F.interpolate(pr, size=(H, W), mode="bilinear", align_corners=False)).backward(gy.double())
+    assert rel(cur.grad, cr.grad) < 1e-6
+    assert rel(prev.grad, pr.grad) < 1e-5
