@@ -49,7 +49,7 @@ def emit(name, ms, bytes_=None, mma_flops=None, **kw):
 def main():
     g = torch.Generator(device=DEV).manual_seed(0)
     rn = lambda *s: torch.randn(*s, device=DEV, generator=g)
-    which = os.environ.get("MPF_PROBE", "msda,gemm,masklogits,layernorm,fpn,maskbits,xattn").split(",")
+    which = os.environ.get("MPF_PROBE", "msda,gemm,masklogits,layernorm,conv,fpn,maskbits,xattn").split(",")
     S, M, D, L, P = 21504, 8, 32, 3, 4
     shapes = [(32, 32), (64, 64), (128, 128)]
     if "msda" in which:
@@ -120,6 +120,20 @@ def main():
         ms = timeit(lambda: native.colsum(gy))
         emit("colsum [344064 x 256]", ms, 4 * B * S * 256)
         del x, r, gy
+    if "conv" in which:
+        # 3x3 convolution of the FPN stage on the tensor-core GEMMs ([16, 256, 256, 256] channels-last, 256 -> 256)
+        C, H, W = 256, 256, 256
+        x, gy = rn(B, H, W, C), rn(B, H, W, C)
+        w = rn(C, C, 3, 3) / (9 * C) ** 0.5
+        w_hi, w_lo = native.split_bf16(w.permute(0, 2, 3, 1).reshape(C, 9 * C))
+        fl = 2.0 * B * H * W * C * 9 * C
+        ms = timeit(lambda: native.conv3x3_cl(x, w_hi, w_lo))
+        emit("conv3x3_cl fwd / dgrad (gemm_bf16x3_kernel, K = 2304)", ms, 4 * (2 * B * H * W * C + 9 * C * C), 3 * fl,
+             fp32_equiv_TFLOPs=fl / ms / 1e9)
+        ms = timeit(lambda: native.conv3x3_cl_wgrad(gy, x))
+        emit("conv3x3_cl wgrad (gemm_bf16x3_tn_kernel, N = 2304)", ms, 4 * (2 * B * H * W * C + 9 * C * C), 3 * fl,
+             fp32_equiv_TFLOPs=fl / ms / 1e9)
+        del x, gy
     if "fpn" in which:
         # FPN-stage layout-crossing kernels at the bench geometry ([16, 256, 256, 256] maps)
         C, H, W = 256, 256, 256
@@ -131,6 +145,12 @@ def main():
         emit("upsample2x_add_nchw_bwd [16,256,256,256]", ms, 4 * B * C * H * W * (2 + 0.25))
         del cur, prev
         x3, gm, bt = gout.view(B, C, H * W), rn(C), rn(C)
+        cur, prev = rn(B, H, W, C), rn(B, H // 2, W // 2, C)
+        ms = timeit(lambda: native.upsample2x_add_cl_fwd(cur, prev))
+        emit("upsample2x_add_cl_fwd [16,256,256,256]", ms, 4 * B * C * H * W * (2 + 0.25))
+        ms = timeit(lambda: native.upsample2x_cl_bwd(cur))
+        emit("upsample2x_cl_bwd [16,256,256,256]", ms, 4 * B * C * H * W * (1 + 0.25))
+        del cur, prev
         ms = timeit(lambda: native.groupnorm_nchw2cl_fwd(x3, gm, bt, 1e-5, 32, True))
         emit("groupnorm_nchw2cl_fwd (stats + apply) [16,256,65536]", ms, 4 * B * C * H * W * 3)
         y, mean, rstd = native.groupnorm_nchw2cl_fwd(x3, gm, bt, 1e-5, 32, True)

@@ -323,10 +323,10 @@ int mpf_groupnorm_nchw2cl_bwd_f32(const float* dy, const float* x, const float* 
  * K = 9 * Cin runs over (tap, channel); the tap only shifts the TMA box, out-of-map pixels are zero-filled.
  *   mpf_conv3x3_cl_bf16x3:        y[b,h,w,co] = bias[co] + sum_{ky,kx,ci} x[b,h+ky-1,w+kx-1,ci] * Wm[co,(ky*3+kx)*Cin+ci]
  *                                 (Wm pre-split by mpf_split_bf16; also the input gradient, with the flipped /
- *                                 transposed weights);  W % 128 == 0, Cin % 32 == 0, Cout % 4 == 0.
+ *                                 transposed weights);  any H, W; Cin % 32 == 0, Cout % 4 == 0.
  *   mpf_conv3x3_cl_wgrad_bf16x3:  dw[s][co][(ky*3+kx)*Cin+ci] = partial sums over the pixels of split s of
  *                                 dy[b,h,w,co] * x[b,h+ky-1,w+kx-1,ci]  (k_splits slabs, summed by the caller);
- *                                 W % 32 == 0, Cin % 64 == 0.
+ *                                 any H, W; Cin % 64 == 0.
  *   mpf_upsample2x_add_cl_fwd_f32 / mpf_upsample2x_cl_bwd_f32: the FPN merge with both sides channels-last
  *                                 (the gradient of `cur` is the incoming gradient itself). */
 int mpf_conv3x3_cl_bf16x3(const float* x, const uint16_t* w_hi, const uint16_t* w_lo, const float* bias, float* y,

@@ -63,7 +63,7 @@ struct Args {
   // 3x3 convolution mode (conv_wt > 0): A is a channels-last map [batch, H, W, Cin] behind a 4-D tensor map with
   // box {32 channels, 128 pixels of one row}; an M tile is 128 consecutive pixels of a row, K = 9 * Cin runs over
   // (tap, channel block) and the tap only shifts the box: pixels outside the map are zero-filled by TMA.
-  int conv_wt;                                // tiles per image row (W / 128)
+  int conv_wt;                                // tiles per image row (ceil(W / 128))
   int conv_cb;                                // channel blocks per tap (Cin / 32)
 };
 
@@ -76,6 +76,12 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(m)),
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -423,6 +429,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           epi_bar(bar_id);
           if (issuer) {
             if (g.debug & 128) {
+            } else if (g.conv_wt) {               // 4-D map [batch, H, W, N]: the row segment is clipped at W
+              const int y = m_t / g.conv_wt;
+              tma_store_4d(tm, sbuf, n0, (m_t - y * g.conv_wt) * kBM, y, slab);
             } else if (g.transpose_c) {
               tma_store_3d(tm, sbuf, m_t * kBM, n0, slab);
             } else {
@@ -660,7 +669,7 @@ static int gemm_bf16x3_impl(const float* A, long long lda, long long a_batch_str
     const int f = atoi(force);
     if (f >= 32 && f <= 256 && f % 32 == 0) g.bn = f;
   }
-  g.tiles_m = (M + kBM - 1) / kBM;
+  g.tiles_m = conv_H > 0 ? conv_H * ((conv_W + kBM - 1) / kBM) : (M + kBM - 1) / kBM;
   g.tiles_n = (N + g.bn - 1) / g.bn;
   MPF_REQUIRE(static_cast<long long>(batch) * k_splits * g.tiles_m * g.tiles_n < (1ll << 31), "gemm_bf16x3: too many tiles");
   const int kblocks_total = (K + kBK - 1) / kBK;
@@ -679,7 +688,7 @@ static int gemm_bf16x3_impl(const float* A, long long lda, long long a_batch_str
   int rc;
   g.conv_wt = g.conv_cb = 0;
   if (conv_H > 0) {
-    g.conv_wt = conv_W / kBM;
+    g.conv_wt = (conv_W + kBM - 1) / kBM;
     g.conv_cb = conv_C / kBK;
     rc = make_tmap_f32_4d(&ta, A, conv_C, conv_W, conv_H, batch, kBK, kBM, "conv input");
   } else {
@@ -694,7 +703,12 @@ static int gemm_bf16x3_impl(const float* A, long long lda, long long a_batch_str
   rc = make_tmap_3d(&tbl, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B_lo, K, N, nb, ldb, b_batch_stride, kBK, g.bn,
                     CU_TENSOR_MAP_SWIZZLE_64B, "B_lo");
   if (rc) return rc;
-  if (transpose_c) {
+  if (conv_H > 0) {
+    MPF_REQUIRE(!transpose_c && !C_lo && k_splits == 1 && !resid && !gate && ldc == N,
+                "conv3x3_cl: plain row-major output only");
+    rc = make_tmap_f32_4d(&tc, C, N, conv_W, conv_H, batch, 32, kBM, "conv output");
+    tcl = tc;
+  } else if (transpose_c) {
     rc = make_tmap_3d(&tc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, C, M, N, slabs, ldc, c_batch_stride, kBM, 32,
                       CU_TENSOR_MAP_SWIZZLE_NONE, "C^T");
     if (rc) return rc;
@@ -750,8 +764,8 @@ int mpf_conv3x3_cl_bf16x3(const float* x, const uint16_t* w_hi, const uint16_t* 
   using namespace mpf;
   clear_error();
   MPF_REQUIRE(x && w_hi && w_lo && y, "conv3x3_cl: null pointer argument");
-  MPF_REQUIRE(batch > 0 && H > 0 && W > 0 && W % 128 == 0 && Cin > 0 && Cin % 32 == 0 && Cout > 0 && Cout % 4 == 0,
-              "conv3x3_cl: needs W %% 128 == 0, Cin %% 32 == 0, Cout %% 4 == 0 (H=%d W=%d Cin=%d Cout=%d)", H, W, Cin, Cout);
+  MPF_REQUIRE(batch > 0 && H > 0 && W > 0 && Cin > 0 && Cin % 32 == 0 && Cout > 0 && Cout % 4 == 0,
+              "conv3x3_cl: needs Cin %% 32 == 0, Cout %% 4 == 0 (H=%d W=%d Cin=%d Cout=%d)", H, W, Cin, Cout);
   MPF_REQUIRE(static_cast<long long>(H) * W < (1ll << 31) / 2, "conv3x3_cl: map too large");
   const int M = H * W, K = 9 * Cin;
   return gemm_bf16x3_impl(x, K, 0, w_hi, w_lo, K, 0, bias, y, nullptr, Cout, static_cast<long long>(M) * Cout, nullptr, 0,

@@ -50,7 +50,8 @@ struct Args {
   // weight gradient of a 3x3 convolution over channels-last maps (conv_W > 0): the reduction index is the pixel
   // (b, y, x), A = dY tokens [T, Cout]; B is the INPUT map [batch, H, W, Cin] behind a 4-D tensor map and the N tile
   // selects (tap, channel range): the tap only shifts the 32-pixel box, pixels outside the map read as zero.
-  int conv_W, conv_HW;                         // W and H * W
+  int conv_H, conv_ws;                         // H and row segments of 32 pixels per image row (ceil(W / 32)):
+                                               // k-block index = (image * H + y) * conv_ws + segment
   int conv_nt;                                 // N tiles per tap (Cin / bn)
 };
 
@@ -189,17 +190,26 @@ gemm_bf16x3_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           mbar_wait(&raw_empty[slot], phase ^ 1);
           uint8_t* st = raw_ring + slot * g.raw_bytes;
           mbar_arrive_expect_tx(&raw_full[slot], (4 + b_boxes) * kBoxBytes);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) tma_load_3d(st + i * kBoxBytes, &tmA, &raw_full[slot], m_t * kBM + i * 32, t0, b);
-          if (g.conv_W) {
+          if (g.conv_ws) {
+            // both operands through 4-D maps over [image, y, x, channel]: dY at the segment, the input shifted by the tap
+            const int kbg = t0 / kBK;
+            const int seg = kbg % g.conv_ws, row = kbg / g.conv_ws;
+            const int y = row % g.conv_H, img = row / g.conv_H;
+            const int x0 = seg * kBK;
             const int tap = n_t / g.conv_nt, c0 = (n_t - tap * g.conv_nt) * BN;
-            const int img = t0 / g.conv_HW, rem = t0 - img * g.conv_HW;
-            const int y = rem / g.conv_W, x0 = rem - y * g.conv_W;
             const int ty = tap / 3;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              tma_load_4d(st + i * kBoxBytes, &tmA, &raw_full[slot], m_t * kBM + i * 32, x0, y, img);
             for (int j = 0; j < b_boxes; ++j)
               tma_load_4d(st + (4 + j) * kBoxBytes, &tmB, &raw_full[slot], c0 + j * 32, x0 + (tap - 3 * ty) - 1,
                           y + ty - 1, img);
-          } else {
+            if (++slot == kRing) { slot = 0; phase ^= 1; }
+            continue;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) tma_load_3d(st + i * kBoxBytes, &tmA, &raw_full[slot], m_t * kBM + i * 32, t0, b);
+          {
             for (int j = 0; j < b_boxes; ++j)
               tma_load_3d(st + (4 + j) * kBoxBytes, &tmB, &raw_full[slot], n_t * BN + j * 32, t0, b);
           }
@@ -483,11 +493,13 @@ static int gemm_bf16x3_tn_impl(const float* A, long long lda, long long a_batch_
   CUtensorMap ta, tb, tc;
   int rc = make_tmap(&ta, A, M, T, batch, lda, a_batch_stride, kBK, "A");
   if (rc) return rc;
-  g.conv_W = g.conv_HW = g.conv_nt = 0;
+  g.conv_H = g.conv_ws = g.conv_nt = 0;
   if (conv_H > 0) {
-    g.conv_W = conv_W;
-    g.conv_HW = conv_H * conv_W;
+    g.conv_H = conv_H;
+    g.conv_ws = (conv_W + kBK - 1) / kBK;
     g.conv_nt = conv_C / g.bn;
+    rc = make_tmap_4d(&ta, A, M, conv_W, conv_H, conv_B, "conv output gradient");
+    if (rc) return rc;
     rc = make_tmap_4d(&tb, B, conv_C, conv_W, conv_H, conv_B, "conv input");
   } else {
     rc = make_tmap(&tb, B, N, T, batch, ldb, b_batch_stride, kBK, "B");
@@ -520,10 +532,10 @@ int mpf_conv3x3_cl_wgrad_bf16x3(const float* dy, const float* x, float* dw, int 
   using namespace mpf;
   clear_error();
   MPF_REQUIRE(dy && x && dw, "conv3x3_cl_wgrad: null pointer argument");
-  MPF_REQUIRE(batch > 0 && H > 0 && W > 0 && W % 32 == 0 && Cin > 0 && Cin % 64 == 0 && Cout > 0 && Cout % 4 == 0,
-              "conv3x3_cl_wgrad: needs W %% 32 == 0, Cin %% 64 == 0, Cout %% 4 == 0 (H=%d W=%d Cin=%d Cout=%d)", H, W, Cin,
-              Cout);
-  const long long T = static_cast<long long>(batch) * H * W;
+  MPF_REQUIRE(batch > 0 && H > 0 && W > 0 && Cin > 0 && Cin % 64 == 0 && Cout > 0 && Cout % 4 == 0,
+              "conv3x3_cl_wgrad: needs Cin %% 64 == 0, Cout %% 4 == 0 (H=%d W=%d Cin=%d Cout=%d)", H, W, Cin, Cout);
+  // the reduction runs over row segments of 32 pixels (the last one of a row is zero-filled beyond W)
+  const long long T = static_cast<long long>(batch) * H * ((W + 31) / 32) * 32;
   MPF_REQUIRE(T < (1ll << 31), "conv3x3_cl_wgrad: too many pixels");
   const int N = 9 * Cin;
   return gemm_bf16x3_tn_impl(dy, Cout, 0, x, N, 0, dw, N, static_cast<long long>(Cout) * N, 1, Cout, N,

@@ -393,7 +393,7 @@ def upsample2x_add_nchw_bwd(g):
 
 def conv3x3_cl_ok(H, W, Cin, Cout):
     """Geometry covered by the tensor-core 3x3 convolution (forward / input gradient / weight gradient)."""
-    return GEMM_MODE == "bf16x3" and W % 128 == 0 and Cin % 64 == 0 and Cout % 64 == 0
+    return GEMM_MODE == "bf16x3" and H > 0 and W > 0 and Cin % 64 == 0 and Cout % 64 == 0
 
 
 def conv3x3_cl(x, w_hi, w_lo, bias=None, relu=False):

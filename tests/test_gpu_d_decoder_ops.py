@@ -406,9 +406,12 @@ class _Conv(torch.nn.Conv2d):
 
 
 @pytest.mark.parametrize("B,Cin,Cout,H,W,bias", [(2, 64, 64, 8, 128, True), (1, 256, 256, 16, 256, False),
-                                                 (2, 128, 64, 5, 128, False), (1, 64, 192, 33, 384, True)])
+                                                 (2, 128, 64, 5, 128, False), (1, 64, 192, 33, 384, True),
+                                                 (2, 64, 64, 7, 100, True), (1, 256, 256, 19, 200, False),
+                                                 (1, 64, 128, 3, 9, False), (2, 128, 128, 40, 304, False)])
 def test_conv3x3_channels_last_tensor_core(B, Cin, Cout, H, W, bias):
-    """3x3 convolution as one GEMM with K = 9*Cin (taps = shifted TMA boxes, zero-filled outside the map), forward,
+    """3x3 convolution as one GEMM with K = 9*Cin (taps = shifted TMA boxes, zero-filled outside the map; any map
+    width: the last 128-pixel segment of a row is clipped by the 4-D output map), forward,
     input gradient (same kernel, flipped/transposed weights) and weight gradient (TN GEMM over all pixels) vs
     F.conv2d in fp64 (ref pixel_decoder/msdeformattn.py:268-275)."""
     g = torch.Generator(device=DEV).manual_seed(B + Cin + H + W)
@@ -434,8 +437,9 @@ def test_conv3x3_channels_last_tensor_core(B, Cin, Cout, H, W, bias):
     assert (conv.weight.grad.double() - wr.grad).abs().max().item() / T ** 0.5 < TOL
     if bias:
         assert (conv.bias.grad.double() - br.grad).abs().max().item() / T ** 0.5 < TOL
-    # geometry outside the kernel's cover
-    assert ops.conv3x3_cl(torch.randn(1, Cin, 8, 100, device=DEV).contiguous(memory_format=torch.channels_last), conv) is None
+    # layers outside the kernel's cover (channel counts that are not multiples of 64) -> None, the caller falls back
+    assert ops.conv3x3_cl(torch.randn(1, 48, 8, 100, device=DEV).contiguous(memory_format=torch.channels_last),
+                          _Conv(48, 64, 3, padding=1).to(DEV)) is None
 
 
 @pytest.mark.parametrize("B,C,H,W", [(2, 64, 8, 8), (1, 128, 34, 52), (2, 256, 64, 160), (1, 4, 2, 2)])
