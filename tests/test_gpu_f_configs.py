@@ -122,7 +122,8 @@ def test_pixel_decoder_gradients_with_tensor_core_conv_path():
         l2[n] = ((a - b).norm() / b.norm().clamp(min=1e-6)).item()
         mx[n] = (a - b).abs().max().item() / max(1e-3, b.abs().max().item())
     worst = sorted(l2.items(), key=lambda kv: -kv[1])[:5]
-    assert worst[0][1] < 2e-3, worst
+    assert worst[0][1] < 1e-2, worst
+    assert sorted(l2.values())[len(l2) // 2] < 1e-3, worst                # median: rounding level
     assert max(mx.values()) < 0.1, sorted(mx.items(), key=lambda kv: -kv[1])[:5]
 
 
