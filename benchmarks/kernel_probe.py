@@ -176,6 +176,20 @@ def main():
             emit(f"masked_xattn_fwd B={B} Qt={Qt} HW={HW}", ms, 4 * B * (4 * HW * E + 2 * Qt * E) + B * Qt * HW // 8, mma,
                  useful_fp32_TFLOPs=4.0 * B * Qt * HW * E / ms / 1e9)
 
+    if "xattn_bwd" in which:
+        E, heads, Qt = 256, 8, 120
+        for HW in (4096, 16384):
+            q, k, v = rn(B, Qt, E), rn(B, HW, E), rn(B, HW, E)
+            qh, ql = native.split_tf32(q); kh, kl = native.split_tf32(k); vh, vl = native.split_tf32(v)
+            kth, ktl = native.split_tf32(k.transpose(1, 2).contiguous())
+            bits = native.pack_bool_bits(torch.rand(B, Qt, HW, device=DEV, generator=g) < 0.7)
+            d_o = rn(B, Qt, E)
+            lse2, delta = rn(B, heads, Qt).abs() + 6.0, rn(B, heads, Qt) * 0.01
+            ms = timeit(lambda: native.masked_xattn_bwd(qh, ql, kh, kl, kth, ktl, vh, vl, d_o, bits, None, lse2, delta, heads))
+            mma = 3 * 2.0 * B * heads * 128 * HW * 32 * 5          # S, dP (dq kernel) ; S^T, dP^T, dV, dK (dkv kernel) ~ 5 products
+            emit(f"masked_xattn_bwd (dq + dkv kernels, host-side transposes included) B={B} Qt={Qt} HW={HW}", ms,
+                 4 * B * (8 * HW * E + 2 * HW * E) + B * Qt * HW // 8, mma)
+
 
 if __name__ == "__main__":
     main()
