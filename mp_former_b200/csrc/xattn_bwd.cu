@@ -45,6 +45,20 @@ __device__ __forceinline__ void store_row_atom(uint8_t* atom_hi, uint8_t* atom_l
   }
 }
 
+// Same for 16 values: columns [16 * half, 16 * half + 16) of the row (two threads share a row).
+__device__ __forceinline__ void store_half_row_atom(uint8_t* atom_hi, uint8_t* atom_lo, int r, int half,
+                                                    const float (&x)[16]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int sw = r * 128 + (((4 * half + c) ^ (r & 7)) << 4);
+    float4 h, l;
+    h.x = rn(x[4 * c]); h.y = rn(x[4 * c + 1]); h.z = rn(x[4 * c + 2]); h.w = rn(x[4 * c + 3]);
+    l.x = rn(x[4 * c] - h.x); l.y = rn(x[4 * c + 1] - h.y); l.z = rn(x[4 * c + 2] - h.z); l.w = rn(x[4 * c + 3] - h.w);
+    *reinterpret_cast<float4*>(atom_hi + sw) = h;
+    *reinterpret_cast<float4*>(atom_lo + sw) = l;
+  }
+}
+
 // three-pass 3xTF32 product step: D (+)= A B^T with split operands
 __device__ __forceinline__ void mma3(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
                                      uint32_t idesc, bool accumulate) {
@@ -264,19 +278,33 @@ masked_xattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
 // kernel B: dK, dV
 // ================================================================================================
 namespace xk {
-constexpr int kKeys = 128, kQc = 64;
+// CTA = (128-key tile, head, image); the queries are walked in chunks of 32 through a software pipeline:
+//   T1(c)  MMA      S^T(c) = K Qs(c)^T,  dP^T(c) = V dO(c)^T                 -> TMEM buffer c & 1
+//   T2(c)  softmax  P^T(c), dS^T(c) from the TMEM buffer -> shared memory (hi/lo, UMMA K-major)
+//   T3(c)  MMA      dV += P^T(c) dO(c),  dK += dS^T(c) Qs(c)
+// The MMA warp issues T1(c+1) BEFORE T3(c), so the tensor pipe works on the next chunk's scores while the softmax
+// warps turn the current ones into operands; chunk loads (Q, dO and their transposes) run two stages ahead.
+// (The first version used 64-query chunks, one stage and one shared P/dS buffer: every step of the chain waited for
+// the previous one -- 7 % tensor-pipe, 8 % DRAM at one 192 KB CTA per SM, profiles/r1x_ncu_xattn_bwd_dkv.txt.)
+constexpr int kKeys = 128, kQc = 32;
 constexpr int kKVBytes = kKeys * 32 * 4;        // 16 KiB (one of K_hi, K_lo, V_hi, V_lo)
-constexpr int kQcBytes = kQc * 32 * 4;          // 8 KiB  (Q / dO chunk, hi or lo)
-constexpr int kQtBytes = 32 * kQc * 4;          // 8 KiB  (Q^T / dO^T chunk, hi or lo: two atoms)
-constexpr int kChunk = 4 * kQcBytes + 4 * kQtBytes;     // 64 KiB: Q_hi Q_lo dO_hi dO_lo | Qt_hi Qt_lo dOt_hi dOt_lo
+constexpr int kQcBytes = kQc * 32 * 4;          // 4 KiB  (Q / dO chunk, hi or lo: [32 q x 32 d])
+constexpr int kQtBytes = 32 * kQc * 4;          // 4 KiB  (Q^T / dO^T chunk, hi or lo: one [32 d x 32 q] atom)
+constexpr int kChunk = 4 * kQcBytes + 4 * kQtBytes;     // 32 KiB: Q_hi Q_lo dO_hi dO_lo | Qt_hi Qt_lo dOt_hi dOt_lo
+constexpr int kStages = 2;
 constexpr int kAtom = kKeys * 32 * 4;           // 16 KiB: [128 keys x 32 q]
-constexpr int kPBytes = 2 * kAtom;              // 32 KiB (hi or lo of P^T / dS^T)
-constexpr int kSmem = 4 * kKVBytes + kChunk + 2 * kPBytes + 256 + 1024;
+constexpr int kPBytes = 2 * kAtom;              // P^T hi | lo  (same for dS^T)
+constexpr int kSmem = 4 * kKVBytes + kStages * kChunk + 2 * kPBytes + 256 + 1024;
 constexpr uint32_t kTmemCols = 256;
-constexpr int kTS = 0, kTP = 64, kTV = 128, kTK = 160;   // S^T 64, dP^T 64, dV 32, dK 32
+constexpr int kTS = 0, kTP = 64, kTV = 128, kTK = 160;   // S^T 2 x 32, dP^T 2 x 32, dV 32, dK 32 columns
+// 12 warps: 0 TMA, 1 MMA, 2 TMEM allocation, 4-11 softmax.  A key row (TMEM lane) is shared by TWO threads -- warps
+// w and w + 4 address the same lane quarter -- each taking 16 of the chunk's 32 query columns: the exp2 / split /
+// store work of a chunk is the critical path of the tile, and with one softmax warp per scheduler it ran at the
+// issue latency of a single dependent instruction stream.
+constexpr int kThreads = 384;
 }  // namespace xk
 
-__global__ void __launch_bounds__(xb::kThreads, 1)
+__global__ void __launch_bounds__(xk::kThreads, 1)
 masked_xattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
                             const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl,
                             const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
@@ -288,19 +316,19 @@ masked_xattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKh, const __gr
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sKV = smem;                        // K_hi | K_lo | V_hi | V_lo
-  uint8_t* sC = smem + 4 * kKVBytes;          // q-chunk stage
-  uint8_t* sP = sC + kChunk;                  // P^T / dS^T: hi | lo
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPBytes);
+  uint8_t* sC = smem + 4 * kKVBytes;          // kStages query-chunk stages
+  uint8_t* sP = sC + kStages * kChunk;        // P^T: hi | lo
+  uint8_t* sD = sP + kPBytes;                 // dS^T: hi | lo
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sD + kPBytes);
   uint64_t* kv_full = bars;
-  uint64_t* qc_full = bars + 1;
-  uint64_t* qc_empty = bars + 2;   // commit after the chunk's dK MMAs: stage and P buffer are free
-  uint64_t* st_full = bars + 3;
-  uint64_t* st_empty = bars + 4;   // count 4
-  uint64_t* pt_full = bars + 5;    // count 4
-  uint64_t* pt_empty = bars + 6;   // commit after dV MMAs
-  uint64_t* dst_full = bars + 7;   // count 4
-  uint64_t* acc_full = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* qc_full = bars + 1;               // [2] chunk stage landed
+  uint64_t* qc_empty = bars + 3;              // [2] commit after the chunk's dV / dK MMAs: stage free
+  uint64_t* s_full = bars + 5;                // [2] commit after S^T / dP^T MMAs: TMEM buffer ready
+  uint64_t* s_empty = bars + 7;               // [2] count 8: softmax warps have read the TMEM buffer
+  uint64_t* p_full = bars + 9;                // count 8: P^T and dS^T written
+  uint64_t* p_empty = bars + 10;              // commit after the dV / dK MMAs: P^T / dS^T buffers free
+  uint64_t* acc_full = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int key0 = blockIdx.x * kKeys, head = blockIdx.y, b = blockIdx.z;
@@ -308,13 +336,14 @@ masked_xattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKh, const __gr
 
   if (warp == 0 && lane == 0) {
     mbar_init(kv_full, 1);
-    mbar_init(qc_full, 1);
-    mbar_init(qc_empty, 1);
-    mbar_init(st_full, 1);
-    mbar_init(st_empty, 4);
-    mbar_init(pt_full, 4);
-    mbar_init(pt_empty, 1);
-    mbar_init(dst_full, 4);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&qc_full[s], 1);
+      mbar_init(&qc_empty[s], 1);
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], 8);
+    }
+    mbar_init(p_full, 8);
+    mbar_init(p_empty, 1);
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
@@ -332,65 +361,66 @@ masked_xattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKh, const __gr
       tma_load_3d(sKV + 2 * kKVBytes, &tmVh, kv_full, head * 32, key0, b);
       tma_load_3d(sKV + 3 * kKVBytes, &tmVl, kv_full, head * 32, key0, b);
       for (int c = 0; c < NC; ++c) {
-        mbar_wait(qc_empty, (c & 1) ^ 1);
-        mbar_arrive_expect_tx(qc_full, kChunk);
+        const int s = c & 1;
+        mbar_wait(&qc_empty[s], ((c >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&qc_full[s], kChunk);
         const int qc0 = c * kQc;
-        tma_load_3d(sC, &tmQh, qc_full, head * 32, qc0, b);
-        tma_load_3d(sC + kQcBytes, &tmQl, qc_full, head * 32, qc0, b);
-        tma_load_3d(sC + 2 * kQcBytes, &tmDh, qc_full, head * 32, qc0, b);
-        tma_load_3d(sC + 3 * kQcBytes, &tmDl, qc_full, head * 32, qc0, b);
-        uint8_t* t = sC + 4 * kQcBytes;
-        tma_load_3d(t, &tmQth, qc_full, qc0, head * 32, b);
-        tma_load_3d(t + kQtBytes / 2, &tmQth, qc_full, qc0 + 32, head * 32, b);
-        tma_load_3d(t + kQtBytes, &tmQtl, qc_full, qc0, head * 32, b);
-        tma_load_3d(t + kQtBytes + kQtBytes / 2, &tmQtl, qc_full, qc0 + 32, head * 32, b);
-        tma_load_3d(t + 2 * kQtBytes, &tmDth, qc_full, qc0, head * 32, b);
-        tma_load_3d(t + 2 * kQtBytes + kQtBytes / 2, &tmDth, qc_full, qc0 + 32, head * 32, b);
-        tma_load_3d(t + 3 * kQtBytes, &tmDtl, qc_full, qc0, head * 32, b);
-        tma_load_3d(t + 3 * kQtBytes + kQtBytes / 2, &tmDtl, qc_full, qc0 + 32, head * 32, b);
+        uint8_t* st = sC + s * kChunk;
+        tma_load_3d(st, &tmQh, &qc_full[s], head * 32, qc0, b);
+        tma_load_3d(st + kQcBytes, &tmQl, &qc_full[s], head * 32, qc0, b);
+        tma_load_3d(st + 2 * kQcBytes, &tmDh, &qc_full[s], head * 32, qc0, b);
+        tma_load_3d(st + 3 * kQcBytes, &tmDl, &qc_full[s], head * 32, qc0, b);
+        uint8_t* t = st + 4 * kQcBytes;
+        tma_load_3d(t, &tmQth, &qc_full[s], qc0, head * 32, b);
+        tma_load_3d(t + kQtBytes, &tmQtl, &qc_full[s], qc0, head * 32, b);
+        tma_load_3d(t + 2 * kQtBytes, &tmDth, &qc_full[s], qc0, head * 32, b);
+        tma_load_3d(t + 3 * kQtBytes, &tmDtl, &qc_full[s], qc0, head * 32, b);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc_s = idesc_tf32(kKeys, kQc);   // 128 x 64
+      constexpr uint32_t idesc_s = idesc_tf32(kKeys, kQc);   // 128 x 32
       constexpr uint32_t idesc_o = idesc_tf32(kKeys, 32);    // 128 x 32
       const uint32_t k_hi = smem_u32(sKV), k_lo = k_hi + kKVBytes, v_hi = k_hi + 2 * kKVBytes, v_lo = k_hi + 3 * kKVBytes;
-      const uint32_t q_hi = smem_u32(sC), q_lo = q_hi + kQcBytes, do_hi = q_hi + 2 * kQcBytes, do_lo = q_hi + 3 * kQcBytes;
-      const uint32_t qt_hi = q_hi + 4 * kQcBytes, qt_lo = qt_hi + kQtBytes, dt_hi = qt_hi + 2 * kQtBytes, dt_lo = qt_hi + 3 * kQtBytes;
-      const uint32_t p_hi = smem_u32(sP), p_lo = p_hi + kPBytes;
+      const uint32_t p_hi = smem_u32(sP), p_lo = p_hi + kAtom, d_hi = smem_u32(sD), d_lo = d_hi + kAtom;
+      auto issue_scores = [&](int c) {          // T1(c)
+        const int s = c & 1;
+        mbar_wait(&qc_full[s], (c >> 1) & 1);
+        mbar_wait(&s_empty[s], ((c >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t q_hi = smem_u32(sC + s * kChunk), q_lo = q_hi + kQcBytes, do_hi = q_hi + 2 * kQcBytes,
+                       do_lo = q_hi + 3 * kQcBytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          xb::mma3(tmem_base + kTS + s * 32, k_hi + k * 32, k_lo + k * 32, q_hi + k * 32, q_lo + k * 32, idesc_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          xb::mma3(tmem_base + kTP + s * 32, v_hi + k * 32, v_lo + k * 32, do_hi + k * 32, do_lo + k * 32, idesc_s, k > 0);
+        mma_commit(&s_full[s]);
+      };
       mbar_wait(kv_full, 0);
+      issue_scores(0);
       for (int c = 0; c < NC; ++c) {
-        mbar_wait(qc_full, c & 1);
-        mbar_wait(st_empty, (c & 1) ^ 1);
+        if (c + 1 < NC) issue_scores(c + 1);
+        const int s = c & 1;
+        const uint32_t qt_hi = smem_u32(sC + s * kChunk) + 4 * kQcBytes, qt_lo = qt_hi + kQtBytes,
+                       dt_hi = qt_hi + 2 * kQtBytes, dt_lo = qt_hi + 3 * kQtBytes;
+        mbar_wait(p_full, c & 1);               // T3(c)
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          xb::mma3(tmem_base + kTS, k_hi + k * 32, k_lo + k * 32, q_hi + k * 32, q_lo + k * 32, idesc_s, k > 0);
+          xb::mma3(tmem_base + kTV, p_hi + k * 32, p_lo + k * 32, dt_hi + k * 32, dt_lo + k * 32, idesc_o, (c | k) != 0);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          xb::mma3(tmem_base + kTP, v_hi + k * 32, v_lo + k * 32, do_hi + k * 32, do_lo + k * 32, idesc_s, k > 0);
-        mma_commit(st_full);
-        mbar_wait(pt_full, c & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t ao = (k >> 2) * kAtom + (k & 3) * 32, bo = (k >> 2) * (kQtBytes / 2) + (k & 3) * 32;
-          xb::mma3(tmem_base + kTV, p_hi + ao, p_lo + ao, dt_hi + bo, dt_lo + bo, idesc_o, (c | k) != 0);
-        }
-        mma_commit(pt_empty);
-        mbar_wait(dst_full, c & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t ao = (k >> 2) * kAtom + (k & 3) * 32, bo = (k >> 2) * (kQtBytes / 2) + (k & 3) * 32;
-          xb::mma3(tmem_base + kTK, p_hi + ao, p_lo + ao, qt_hi + bo, qt_lo + bo, idesc_o, (c | k) != 0);
-        }
-        mma_commit(qc_empty);
+          xb::mma3(tmem_base + kTK, d_hi + k * 32, d_lo + k * 32, qt_hi + k * 32, qt_lo + k * 32, idesc_o, (c | k) != 0);
+        mma_commit(p_empty);
+        mma_commit(&qc_empty[s]);
       }
       mma_commit(acc_full);
     }
   } else if (warp >= 4) {
-    const int ew = warp - 4;
+    const int ew = (warp - 4) & 3;                // TMEM lane quarter
+    const int half = (warp - 4) >> 2;             // which 16 of the chunk's 32 query columns
     const int r = ew * 32 + lane;                 // key row inside the tile == TMEM lane
     const int key = key0 + r;
     const bool key_ok = key < g.HW;
@@ -398,11 +428,11 @@ masked_xattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKh, const __gr
     const uint32_t bit = 1u << (key & 31);
     const float* lse_b = g.lse2 + (static_cast<long long>(b) * g.heads + head) * g.Qt;
     const float* dlt_b = g.delta + (static_cast<long long>(b) * g.heads + head) * g.Qt;
-    // per-chunk column data (log-sum-exp, delta, the mask word of each of the tile's four 32-key groups),
-    // staged once by the 128 softmax threads; double buffered by chunk parity, one named barrier per chunk
+    // per-chunk column data (log-sum-exp, delta, the mask word of each of the tile's four 32-key groups), staged by
+    // the first 128 softmax threads; double buffered by chunk parity, one named barrier (256 threads) per chunk
     __shared__ float s_lse[2][kQc], s_dlt[2][kQc];
     __shared__ uint32_t s_mw[2][kQc][4];
-    const int st_id = threadIdx.x - 128;          // 0..127
+    const int st_id = threadIdx.x - 128;          // 0..255
 
     for (int c = 0; c < NC; ++c) {
       const int qc0 = c * kQc;
@@ -412,9 +442,8 @@ masked_xattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKh, const __gr
         s_lse[pb][st_id] = q < g.Qt ? __ldg(lse_b + q) : 0.f;
         s_dlt[pb][st_id] = q < g.Qt ? __ldg(dlt_b + q) : 0.f;
       }
-#pragma unroll
-      for (int i = st_id; i < kQc * 4; i += 128) {
-        const int ql = i >> 2, wg = i & 3;
+      if (st_id < 4 * kQc) {
+        const int ql = st_id >> 2, wg = st_id & 3;            // kQc * 4 == 128 threads: one word each
         const int q = qc0 + ql;
         uint32_t w = 0xFFFFFFFFu;                  // queries beyond Qt contribute nothing
         if (q < g.Qt) {
@@ -425,59 +454,48 @@ masked_xattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKh, const __gr
         }
         s_mw[pb][ql][wg] = w;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      mbar_wait(st_full, c & 1);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mbar_wait(&s_full[pb], (c >> 1) & 1);
       tc_fence_after();
-      float pt[2][32], ds[2][32];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t sv[32], pv[32];
-        tmem_ld_32x32(lane_addr + kTS + h * 32, sv);
-        tmem_ld_32x32(lane_addr + kTP + h * 32, pv);
+      float pt[16], ds[16];
+      {
+        uint32_t sv[16], pv[16];
+        tmem_ld_32x16(lane_addr + kTS + pb * 32 + half * 16, sv);
+        tmem_ld_32x16(lane_addr + kTP + pb * 32 + half * 16, pv);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int ql = h * 32 + i;
+        for (int i = 0; i < 16; ++i) {
+          const int ql = half * 16 + i;
           const bool masked = !key_ok || (s_mw[pb][ql][ew] & bit) != 0u;
           const float p = masked ? 0.f : exp2f(__uint_as_float(sv[i]) - s_lse[pb][ql]);
-          pt[h][i] = p;
-          ds[h][i] = p * (__uint_as_float(pv[i]) - s_dlt[pb][ql]);
+          pt[i] = p;
+          ds[i] = p * (__uint_as_float(pv[i]) - s_dlt[pb][ql]);
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(st_empty);
-      // P^T(c): the buffer is free once the previous chunk's dK MMAs retired (qc_empty of chunk c-1)
-      if (c > 0) mbar_wait(qc_empty, (c - 1) & 1);
-      xb::store_row_atom(sP, sP + kPBytes, r, pt[0]);
-      xb::store_row_atom(sP + kAtom, sP + kPBytes + kAtom, r, pt[1]);
+      if (lane == 0) mbar_arrive(&s_empty[pb]);
+      // the P^T / dS^T buffers are free once the previous chunk's dV / dK MMAs retired
+      if (c > 0) mbar_wait(p_empty, (c - 1) & 1);
+      xb::store_half_row_atom(sP, sP + kAtom, r, half, pt);
+      xb::store_half_row_atom(sD, sD + kAtom, r, half, ds);
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(pt_full);
-      mbar_wait(pt_empty, c & 1);                  // dV MMAs of this chunk have consumed P^T
-      xb::store_row_atom(sP, sP + kPBytes, r, ds[0]);
-      xb::store_row_atom(sP + kAtom, sP + kPBytes + kAtom, r, ds[1]);
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(dst_full);
+      if (lane == 0) mbar_arrive(p_full);
     }
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    uint32_t vv[32], vk[32];
-    tmem_ld_32x32(lane_addr + kTV, vv);
-    tmem_ld_32x32(lane_addr + kTK, vk);
+    // the two threads of a row share the final store: half 0 writes dV, half 1 writes dK
+    uint32_t vv[32];
+    tmem_ld_32x32(lane_addr + (half == 0 ? kTV : kTK), vv);
     tmem_ld_wait();
     if (key_ok) {
-      float* dv = g.dv + (static_cast<long long>(b) * g.HW + key) * g.E + head * 32;
-      float* dk = g.dk + (static_cast<long long>(b) * g.HW + key) * g.E + head * 32;
+      float* dst = (half == 0 ? g.dv : g.dk) + (static_cast<long long>(b) * g.HW + key) * g.E + head * 32;
+      const float sc = half == 0 ? 1.f : xb::kLn2;
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        *reinterpret_cast<float4*>(dv + i) = make_float4(__uint_as_float(vv[i]), __uint_as_float(vv[i + 1]),
-                                                         __uint_as_float(vv[i + 2]), __uint_as_float(vv[i + 3]));
-        *reinterpret_cast<float4*>(dk + i) =
-            make_float4(__uint_as_float(vk[i]) * xb::kLn2, __uint_as_float(vk[i + 1]) * xb::kLn2,
-                        __uint_as_float(vk[i + 2]) * xb::kLn2, __uint_as_float(vk[i + 3]) * xb::kLn2);
-      }
+      for (int i = 0; i < 32; i += 4)
+        *reinterpret_cast<float4*>(dst + i) = make_float4(__uint_as_float(vv[i]) * sc, __uint_as_float(vv[i + 1]) * sc,
+                                                          __uint_as_float(vv[i + 2]) * sc, __uint_as_float(vv[i + 3]) * sc);
     }
   }
 
@@ -559,7 +577,7 @@ int mpf_masked_xattn_bwd_f32(const float* q_hi, const float* q_lo, const float* 
   if ((rc = make_tmap_f32_3d(&bdt_h, dot_hi, Qt, E, B, qt_ld, qts, 32, 32))) return rc;
   if ((rc = make_tmap_f32_3d(&bdt_l, dot_lo, Qt, E, B, qt_ld, qts, 32, 32))) return rc;
   dim3 grid_b((HW + xk::kKeys - 1) / xk::kKeys, heads, B);
-  masked_xattn_bwd_dkv_kernel<<<grid_b, xb::kThreads, xk::kSmem, st>>>(bk_h, bk_l, bv_h, bv_l, bq_h, bq_l, bd_h, bd_l,
+  masked_xattn_bwd_dkv_kernel<<<grid_b, xk::kThreads, xk::kSmem, st>>>(bk_h, bk_l, bv_h, bv_l, bq_h, bq_l, bd_h, bd_l,
                                                                        bqt_h, bqt_l, bdt_h, bdt_l, g);
   count_launch();
   return finish_launch("masked_xattn_bwd_dkv");
