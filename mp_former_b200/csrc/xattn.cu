@@ -33,7 +33,7 @@ using namespace ptx;
 constexpr int kXQ = 128;                 // queries per CTA (UMMA M)
 constexpr int kXK = 64;                  // keys per tile
 constexpr int kXD = 32;                  // head dim (= one 128-byte swizzle row of fp32)
-constexpr int kXThreads = 256;
+constexpr int kXThreads = 384;            // warps 0 TMA, 1 MMA, 2 TMEM allocation, 4-11 softmax (two threads per row)
 constexpr int kQBytes = kXQ * kXD * 4;   // 16 KiB  (one of Q_hi / Q_lo)
 constexpr int kKBytes = kXK * kXD * 4;   // 8 KiB   (one of K_hi / K_lo)
 constexpr int kVBytes = kXD * kXK * 4;   // 8 KiB   (one of Vt_hi / Vt_lo): two 32x32 atoms of 4 KiB
@@ -90,11 +90,11 @@ masked_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_c
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 4);
+      mbar_init(&s_empty[i], 8);
       mbar_init(&o_full[i], 1);
-      mbar_init(&o_empty[i], 4);
+      mbar_init(&o_empty[i], 8);
     }
-    mbar_init(p_full, 4);
+    mbar_init(p_full, 8);
     mbar_init(p_empty, 1);
     fence_mbar_init();
   }
@@ -173,25 +173,32 @@ masked_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_c
     }
   } else if (warp >= 4) {
     // ================= softmax / output warps =================
-    const int ew = warp - 4;
+    // A query row (TMEM lane) belongs to TWO threads: warps w and w + 4 address the same lane quarter; thread h takes
+    // the 32-key half h of every 64-key tile (one atom of P) and 16 of the 32 output columns.  The row maximum of a
+    // tile is exchanged through shared memory (one named barrier per tile), so both threads derive identical
+    // rescale factors; the row sums stay per thread until the end.  With one softmax warp per scheduler the exp2 /
+    // split / store stream ran at single-warp issue latency and was the critical path of the tile.
+    const int ew = (warp - 4) & 3;
+    const int h = (warp - 4) >> 2;
     const int r = ew * 32 + lane;                 // query row inside the tile == TMEM lane
     const int q = q0 + r;
     const bool q_ok = q < g.Qt;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
     const uint32_t* brow = g.bits + (static_cast<long long>(b) * g.Qt + (q_ok ? q : 0)) * g.words;
     const bool open = !q_ok || (g.row_open != nullptr && g.row_open[static_cast<long long>(b) * g.Qt + q] != 0);
+    __shared__ float s_xch[2][2][kXQ];            // [tile parity][half][row]
 
     float m = -INFINITY, l = 0.f, m_o = -INFINITY, m_prev = -INFINITY;
-    float o[kXD];
+    float o[kXD / 2];
 #pragma unroll
-    for (int i = 0; i < kXD; ++i) o[i] = 0.f;
+    for (int i = 0; i < kXD / 2; ++i) o[i] = 0.f;
 
     auto accumulate_o = [&](int j, float m_j) {
       const int st = j & 1;
       mbar_wait(&o_full[st], (j >> 1) & 1);
       tc_fence_after();
-      uint32_t v[32];
-      tmem_ld_32x32(lane_addr + kTmemO + st * kXD, v);
+      uint32_t v[16];
+      tmem_ld_32x16(lane_addr + kTmemO + st * kXD + 16 * h, v);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
@@ -199,7 +206,7 @@ masked_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_c
       if (m_j != -INFINITY) {              // a fully masked tile contributes exactly zero
         const float sc = (m_o == -INFINITY) ? 0.f : exp2f(m_o - m_j);   // m_j >= m_o: never overflows
 #pragma unroll
-        for (int i = 0; i < kXD; ++i) o[i] = o[i] * sc + __uint_as_float(v[i]);
+        for (int i = 0; i < kXD / 2; ++i) o[i] = o[i] * sc + __uint_as_float(v[i]);
         m_o = m_j;
       }
     };
@@ -208,33 +215,29 @@ masked_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_c
       const int st = j & 1;
       mbar_wait(&s_full[st], (j >> 1) & 1);
       tc_fence_after();
-      uint32_t s0[32], s1[32];
-      tmem_ld_32x32(lane_addr + kTmemS + st * kXK, s0);
-      tmem_ld_32x32(lane_addr + kTmemS + st * kXK + 32, s1);
+      uint32_t s0[32];
+      tmem_ld_32x32(lane_addr + kTmemS + st * kXK + 32 * h, s0);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[st]);
 
-      // mask words for keys [64j, 64j+64): bit = 1 -> masked.  Keys >= HW are always masked.
-      const int key0 = j * kXK;
-      uint32_t w0 = 0u, w1 = 0u;
-      if (!open) {
-        w0 = brow[2 * j];
-        w1 = brow[2 * j + 1];
-      }
+      // mask word for keys [64j + 32h, 64j + 32h + 32): bit = 1 -> masked.  Keys >= HW are always masked.
+      const int key0 = j * kXK + 32 * h;
+      uint32_t w0 = 0u;
+      if (!open) w0 = brow[2 * j + h];
       if (key0 + 32 > g.HW) w0 |= (key0 >= g.HW) ? 0xFFFFFFFFu : (0xFFFFFFFFu << (g.HW - key0));
-      if (key0 + 64 > g.HW) w1 |= (key0 + 32 >= g.HW) ? 0xFFFFFFFFu : (0xFFFFFFFFu << (g.HW - key0 - 32));
 
       float tmax = -INFINITY;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const float a = ((w0 >> i) & 1u) ? -INFINITY : __uint_as_float(s0[i]);
-        const float c = ((w1 >> i) & 1u) ? -INFINITY : __uint_as_float(s1[i]);
         s0[i] = __float_as_uint(a);
-        s1[i] = __float_as_uint(c);
-        tmax = fmaxf(tmax, fmaxf(a, c));
+        tmax = fmaxf(tmax, a);
       }
+      s_xch[st][h][r] = tmax;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      tmax = fmaxf(tmax, s_xch[st][h ^ 1][r]);
       const float m_new = fmaxf(m, tmax);
       const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
       const float alpha = (m == -INFINITY) ? 0.f : exp2f(m - m_new);
@@ -242,33 +245,25 @@ masked_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_c
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const float a = exp2f(__uint_as_float(s0[i]) - m_safe);
-        const float c = exp2f(__uint_as_float(s1[i]) - m_safe);
-        psum += a + c;
+        psum += a;
         s0[i] = __float_as_uint(a);
-        s1[i] = __float_as_uint(c);
       }
-      l = l * alpha + psum;
+      l = l * alpha + psum;                 // this thread's half of the row sum
 
       // P(j) -> smem (UMMA A operand, K-major, 128B swizzle): row r, 16-byte chunk c of atom a lives at
-      // a*16K + r*128 + ((c ^ (r & 7)) << 4)
+      // a*16K + r*128 + ((c ^ (r & 7)) << 4); this thread writes atom h
       mbar_wait(p_empty, (j & 1) ^ 1);
-      uint8_t* prow = sP + r * 128;
+      uint8_t* prow = sP + h * kPAtom + r * 128;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const int sw = ((c ^ (r & 7)) << 4);
-        float4 h0, l0, h1, l1;
+        float4 h0, l0;
         const float a0 = __uint_as_float(s0[4 * c]), a1 = __uint_as_float(s0[4 * c + 1]);
         const float a2 = __uint_as_float(s0[4 * c + 2]), a3 = __uint_as_float(s0[4 * c + 3]);
         h0.x = rn_tf32x(a0); h0.y = rn_tf32x(a1); h0.z = rn_tf32x(a2); h0.w = rn_tf32x(a3);
         l0.x = rn_tf32x(a0 - h0.x); l0.y = rn_tf32x(a1 - h0.y); l0.z = rn_tf32x(a2 - h0.z); l0.w = rn_tf32x(a3 - h0.w);
-        const float c0 = __uint_as_float(s1[4 * c]), c1 = __uint_as_float(s1[4 * c + 1]);
-        const float c2 = __uint_as_float(s1[4 * c + 2]), c3 = __uint_as_float(s1[4 * c + 3]);
-        h1.x = rn_tf32x(c0); h1.y = rn_tf32x(c1); h1.z = rn_tf32x(c2); h1.w = rn_tf32x(c3);
-        l1.x = rn_tf32x(c0 - h1.x); l1.y = rn_tf32x(c1 - h1.y); l1.z = rn_tf32x(c2 - h1.z); l1.w = rn_tf32x(c3 - h1.w);
-        *reinterpret_cast<float4*>(prow + sw) = h0;                          // P_hi, atom 0 (keys 0..31)
-        *reinterpret_cast<float4*>(prow + kPAtom + sw) = h1;                 // P_hi, atom 1 (keys 32..63)
-        *reinterpret_cast<float4*>(prow + kPBytes + sw) = l0;                // P_lo, atom 0
-        *reinterpret_cast<float4*>(prow + kPBytes + kPAtom + sw) = l1;       // P_lo, atom 1
+        *reinterpret_cast<float4*>(prow + sw) = h0;                          // P_hi
+        *reinterpret_cast<float4*>(prow + kPBytes + sw) = l0;                // P_lo
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -280,13 +275,17 @@ masked_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_c
     }
     accumulate_o(T - 1, m_prev);
 
+    // total row sum = the two threads' halves (both were rescaled by identical factors)
+    s_xch[T & 1][h][r] = l;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    l += s_xch[T & 1][h ^ 1][r];
     if (q_ok) {
       const float inv = 1.f / l;
-      float* dst = g.out + (static_cast<long long>(b) * g.Qt + q) * g.E + head * kXD;
+      float* dst = g.out + (static_cast<long long>(b) * g.Qt + q) * g.E + head * kXD + 16 * h;
 #pragma unroll
-      for (int i = 0; i < kXD; i += 4)
+      for (int i = 0; i < kXD / 2; i += 4)
         *reinterpret_cast<float4*>(dst + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
-      if (g.lse2 != nullptr)
+      if (g.lse2 != nullptr && h == 0)
         g.lse2[(static_cast<long long>(b) * g.heads + head) * g.Qt + q] = m + log2f(l);
     }
   }

@@ -25,7 +25,6 @@ using namespace ptx;
 
 namespace xb {
 constexpr int kD = 32;            // head dim
-constexpr int kThreads = 256;
 constexpr float kLn2 = 0.6931471805599453f;
 
 __device__ __forceinline__ float rn(float x) {
@@ -94,9 +93,10 @@ constexpr int kDsBytes = 2 * kAtom;             // 32 KiB (one of dS_hi / dS_lo)
 constexpr int kSmem = 4 * kQBytes + 2 * kStage + 2 * kDsBytes + 256 + 1024;
 constexpr uint32_t kTmemCols = 512;
 constexpr int kTS = 0, kTP = 128, kTQ = 256;    // S: 2x64, dP: 2x64, dQ: 32
+constexpr int kThreads = 384;                   // warps 0 TMA, 1 MMA, 2 TMEM allocation, 4-11 softmax
 }  // namespace xa
 
-__global__ void __launch_bounds__(xb::kThreads, 1)
+__global__ void __launch_bounds__(xa::kThreads, 1)
 masked_xattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
                            const __grid_constant__ CUtensorMap tmDh, const __grid_constant__ CUtensorMap tmDl,
                            const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
@@ -130,9 +130,9 @@ masked_xattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
       mbar_init(&sdp_full[i], 1);
-      mbar_init(&sdp_empty[i], 4);
+      mbar_init(&sdp_empty[i], 8);
     }
-    mbar_init(ds_full, 4);
+    mbar_init(ds_full, 8);
     mbar_init(ds_empty, 1);
     mbar_init(dq_full, 1);
     fence_mbar_init();
@@ -207,7 +207,10 @@ masked_xattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
       mma_commit(dq_full);
     }
   } else if (warp >= 4) {
-    const int ew = warp - 4;
+    // 8 softmax warps: warps w and w + 4 share a TMEM lane quarter (a query row belongs to two threads); each takes
+    // one 32-key half of the 64-key tile = one [128 x 32] atom of dS
+    const int ew = (warp - 4) & 3;
+    const int h = (warp - 4) >> 2;
     const int r = ew * 32 + lane;
     const int q = q0 + r;
     const bool q_ok = q < g.Qt;
@@ -220,46 +223,44 @@ masked_xattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
 
     for (int j = 0; j < T; ++j) {
       const int st = j & 1;
-      const int key0 = j * kK;
-      uint32_t w[2] = {0u, 0u};
-      if (!open) { w[0] = brow[2 * j]; w[1] = brow[2 * j + 1]; }
-      if (key0 + 32 > g.HW) w[0] |= (key0 >= g.HW) ? 0xFFFFFFFFu : (0xFFFFFFFFu << (g.HW - key0));
-      if (key0 + 64 > g.HW) w[1] |= (key0 + 32 >= g.HW) ? 0xFFFFFFFFu : (0xFFFFFFFFu << (g.HW - key0 - 32));
-      if (!q_ok) { w[0] = 0xFFFFFFFFu; w[1] = 0xFFFFFFFFu; }      // padding rows contribute nothing
+      const int key0 = j * kK + 32 * h;
+      uint32_t w = 0u;
+      if (!open) w = brow[2 * j + h];
+      if (key0 + 32 > g.HW) w |= (key0 >= g.HW) ? 0xFFFFFFFFu : (0xFFFFFFFFu << (g.HW - key0));
+      if (!q_ok) w = 0xFFFFFFFFu;                                  // padding rows contribute nothing
       mbar_wait(&sdp_full[st], (j >> 1) & 1);
       tc_fence_after();
-      float ds[2][32];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      float ds[32];
+      {
         uint32_t sv[32], pv[32];
         tmem_ld_32x32(lane_addr + kTS + st * kK + h * 32, sv);
         tmem_ld_32x32(lane_addr + kTP + st * kK + h * 32, pv);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float p = ((w[h] >> i) & 1u) ? 0.f : exp2f(__uint_as_float(sv[i]) - lse);
-          ds[h][i] = p * (__uint_as_float(pv[i]) - dlt);
+          const float p = ((w >> i) & 1u) ? 0.f : exp2f(__uint_as_float(sv[i]) - lse);
+          ds[i] = p * (__uint_as_float(pv[i]) - dlt);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sdp_empty[st]);
       mbar_wait(ds_empty, (j & 1) ^ 1);
-      xb::store_row_atom(sDS, sDS + kDsBytes, r, ds[0]);
-      xb::store_row_atom(sDS + kAtom, sDS + kDsBytes + kAtom, r, ds[1]);
+      xb::store_row_atom(sDS + h * kAtom, sDS + kDsBytes + h * kAtom, r, ds);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(ds_full);
     }
     mbar_wait(dq_full, 0);
     tc_fence_after();
-    uint32_t v[32];
-    tmem_ld_32x32(lane_addr + kTQ, v);
+    // the row's two threads store 16 of the 32 head-dim values each
+    uint32_t v[16];
+    tmem_ld_32x16(lane_addr + kTQ + 16 * h, v);
     tmem_ld_wait();
     if (q_ok) {
-      float* dst = g.dq + (static_cast<long long>(b) * g.Qt + q) * g.E + head * 32;
+      float* dst = g.dq + (static_cast<long long>(b) * g.Qt + q) * g.E + head * 32 + 16 * h;
 #pragma unroll
-      for (int i = 0; i < 32; i += 4)
+      for (int i = 0; i < 16; i += 4)
         *reinterpret_cast<float4*>(dst + i) =
             make_float4(__uint_as_float(v[i]) * g.inv_sqrt_d, __uint_as_float(v[i + 1]) * g.inv_sqrt_d,
                         __uint_as_float(v[i + 2]) * g.inv_sqrt_d, __uint_as_float(v[i + 3]) * g.inv_sqrt_d);
@@ -557,7 +558,7 @@ int mpf_masked_xattn_bwd_f32(const float* q_hi, const float* q_lo, const float* 
   g.inv_sqrt_d = 1.0f / sqrtf(static_cast<float>(head_dim));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid_a((Qt + xa::kQ - 1) / xa::kQ, heads, B);
-  masked_xattn_bwd_dq_kernel<<<grid_a, xb::kThreads, xa::kSmem, st>>>(tq_h, tq_l, td_h, td_l, tk_h, tk_l, tv_h, tv_l,
+  masked_xattn_bwd_dq_kernel<<<grid_a, xa::kThreads, xa::kSmem, st>>>(tq_h, tq_l, td_h, td_l, tk_h, tk_l, tv_h, tv_l,
                                                                       tkt_h, tkt_l, g);
   count_launch();
   if ((rc = finish_launch("masked_xattn_bwd_dq"))) return rc;
