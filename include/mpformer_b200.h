@@ -188,6 +188,14 @@ int mpf_gemm_tf32x3_general(const float* A, int a_mn_major, long long lda, long 
  * Requirements: A/B/C 16-byte aligned; lda, ldc, batch strides multiples of 4 elements; ldb multiple of 8.
  * ------------------------------------------------------------------------------------------- */
 int mpf_split_bf16(const float* x, uint16_t* hi, uint16_t* lo, long long n, void* stream);
+/* C = A B^T (+ bias, + full residual, ReLU) for one [M, K] x [N, K] product with the ReLU pattern kept as ONE BIT per
+ * element: relu_bits_out (with relu != 0) receives word [n / 32][m] whose bit n % 32 says C[m][n] > 0; gate_bits zeroes
+ * the elements of C whose bit is clear (the backward of Linear -> ReLU -> Linear reads 1/32 of the bytes of the
+ * activation: ref pixel_decoder/msdeformattn.py:116-120 under autograd).  N % 32 == 0. */
+int mpf_gemm_bf16x3_relubits(const float* A, long long lda, const uint16_t* B_hi, const uint16_t* B_lo, long long ldb,
+                             const float* bias, float* C, long long ldc, const float* resid, long long resid_ld,
+                             int M, int N, int K, int relu, uint32_t* relu_bits_out, const uint32_t* gate_bits,
+                             void* stream);
 /* x [batch, R, Cc] fp32 -> bf16 halves of its transpose, hi / lo [batch, Cc, R] (R, Cc multiples of 4): the B operand
  * of a product that reduces over R when x is stored R-major (mask_features tokens in the batched dE of the
  * prediction heads, ref decoder :1865 under autograd). */

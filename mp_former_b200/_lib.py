@@ -47,6 +47,8 @@ SIGNATURES = {
     "mpf_gemm_bf16x3": (_c_int, [_c_vp, _c_ll, _c_ll, _c_vp, _c_vp, _c_ll, _c_ll, _c_vp, _c_vp, _c_vp, _c_ll, _c_ll,
                                  _c_vp, _c_ll, _c_int, _c_int, _c_vp, _c_ll, ctypes.c_float,
                                  _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp]),
+    "mpf_gemm_bf16x3_relubits": (_c_int, [_c_vp, _c_ll, _c_vp, _c_vp, _c_ll, _c_vp, _c_vp, _c_ll, _c_vp, _c_ll,
+                                          _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_vp]),
     "mpf_transpose_split_bf16": (_c_int, [_c_vp] * 3 + [_c_int, _c_ll, _c_int, _c_vp]),
     "mpf_gemm_bf16x3_tn": (_c_int, [_c_vp, _c_ll, _c_ll, _c_vp, _c_ll, _c_ll, _c_vp, _c_ll, _c_ll] + [_c_int] * 5 + [_c_vp]),
     "mpf_gemm_bf16x3_tn_ex": (_c_int, [_c_vp, _c_ll, _c_ll, _c_vp, _c_ll, _c_ll, _c_vp, _c_ll, _c_ll] + [_c_int] * 6 + [_c_vp]),

@@ -51,6 +51,11 @@ struct Args {
   int resid_rows, resid_cols;
   const float* gate;
   long long gate_ld;
+  // the same ReLU gate as ONE BIT per element (batch 1, row-major C, N % 32 == 0): word [n / 32][m], bit n % 32.
+  // relu_bits_out is written by a GEMM with relu (bit = output > 0); gate_bits replaces `gate` in the backward GEMM:
+  // 1/32 of the bytes of reading the activation back (1.4 GB -> 44 MB for the encoder FFN at the bench geometry).
+  uint32_t* relu_bits_out;
+  const uint32_t* gate_bits;
   float alpha;
   int batch, M, N, K;
   int bn;                                     // N tile (multiple of 32, <= 256)
@@ -388,6 +393,18 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (g.relu) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          if (g.relu_bits_out != nullptr && row_ok) {
+            uint32_t w = 0u;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) w |= (f[j] > 0.f ? 1u : 0u) << j;
+            g.relu_bits_out[static_cast<long long>(n0 >> 5) * g.M + row] = w;
+          }
+        }
+        if (g.gate_bits != nullptr && row_ok) {
+          const uint32_t w = __ldg(g.gate_bits + static_cast<long long>(n0 >> 5) * g.M + row);
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (!((w >> j) & 1u)) f[j] = 0.f;
         }
         if (grow != nullptr) {
           if (fullc && g.vec_aux) {
@@ -653,7 +670,8 @@ static int gemm_bf16x3_impl(const float* A, long long lda, long long a_batch_str
                             float* C_lo, long long ldc, long long c_batch_stride, const float* resid,
                             long long resid_ld, int resid_rows, int resid_cols, const float* gate, long long gate_ld,
                             float alpha, int batch, int M, int N, int K, int k_splits, int relu, int transpose_c,
-                            int conv_H, int conv_W, int conv_C, void* stream) {
+                            int conv_H, int conv_W, int conv_C, uint32_t* relu_bits_out, const uint32_t* gate_bits,
+                            void* stream) {
   using namespace mpf;
   using namespace mpf::bf3;
   clear_error();
@@ -729,6 +747,11 @@ static int gemm_bf16x3_impl(const float* A, long long lda, long long a_batch_str
   g.resid = resid; g.resid_ld = resid_ld; g.resid_rows = resid_rows;
   g.resid_cols = resid ? (resid_cols > 0 ? resid_cols : N) : 0;
   g.gate = gate; g.gate_ld = gate_ld;
+  MPF_REQUIRE((relu_bits_out == nullptr && gate_bits == nullptr) ||
+                  (batch == 1 && !transpose_c && k_splits == 1 && N % 32 == 0 && conv_H == 0),
+              "gemm_bf16x3: ReLU bit masks need batch 1, row-major C and N %% 32 == 0");
+  MPF_REQUIRE(relu_bits_out == nullptr || relu, "gemm_bf16x3: relu_bits_out without relu");
+  g.relu_bits_out = relu_bits_out; g.gate_bits = gate_bits;
   g.alpha = alpha;
   g.batch = batch; g.M = M; g.N = N; g.K = K;
   g.relu = relu; g.transpose_c = transpose_c; g.split_out = C_lo ? 1 : 0;
@@ -756,7 +779,16 @@ int mpf_gemm_bf16x3(const float* A, long long lda, long long a_batch_stride, con
                     int M, int N, int K, int k_splits, int relu, int transpose_c, void* stream) {
   return gemm_bf16x3_impl(A, lda, a_batch_stride, B_hi, B_lo, ldb, b_batch_stride, bias, C, C_lo, ldc, c_batch_stride,
                           resid, resid_ld, resid_rows, resid_cols, gate, gate_ld, alpha, batch, M, N, K, k_splits, relu,
-                          transpose_c, 0, 0, 0, stream);
+                          transpose_c, 0, 0, 0, nullptr, nullptr, stream);
+}
+
+int mpf_gemm_bf16x3_relubits(const float* A, long long lda, const uint16_t* B_hi, const uint16_t* B_lo, long long ldb,
+                             const float* bias, float* C, long long ldc, const float* resid, long long resid_ld,
+                             int M, int N, int K, int relu, uint32_t* relu_bits_out, const uint32_t* gate_bits,
+                             void* stream) {
+  return gemm_bf16x3_impl(A, lda, static_cast<long long>(M) * lda, B_hi, B_lo, ldb, 0, bias, C, nullptr, ldc,
+                          static_cast<long long>(M) * ldc, resid, resid_ld, 0, 0, nullptr, 0, 1.0f, 1, M, N, K, 1, relu, 0, 0,
+                          0, 0, relu_bits_out, gate_bits, stream);
 }
 
 int mpf_conv3x3_cl_bf16x3(const float* x, const uint16_t* w_hi, const uint16_t* w_lo, const float* bias, float* y,
@@ -769,7 +801,7 @@ int mpf_conv3x3_cl_bf16x3(const float* x, const uint16_t* w_hi, const uint16_t* 
   MPF_REQUIRE(static_cast<long long>(H) * W < (1ll << 31) / 2, "conv3x3_cl: map too large");
   const int M = H * W, K = 9 * Cin;
   return gemm_bf16x3_impl(x, K, 0, w_hi, w_lo, K, 0, bias, y, nullptr, Cout, static_cast<long long>(M) * Cout, nullptr, 0,
-                          0, 0, nullptr, 0, 1.0f, batch, M, Cout, K, 1, relu, 0, H, W, Cin, stream);
+                          0, 0, nullptr, 0, 1.0f, batch, M, Cout, K, 1, relu, 0, H, W, Cin, nullptr, nullptr, stream);
 }
 
 }  // extern "C"

@@ -125,6 +125,35 @@ def gemm_bf16x3_splitk(a, b_hi, b_lo, k_splits):
     return out.view(batch, k_splits, M, N).sum(1) if k_splits > 1 else out
 
 
+def gemm_relu_bits(a, b_hi, b_lo, bias=None, resid=None, relu_bits_out=False, gate_bits=None):
+    """y = a @ b^T (+ bias + resid) for a [M, K] fp32 and pre-split bf16 b [N, K] (N % 32 == 0), with the ReLU pattern
+    as one bit per element.  ``relu_bits_out=True``: y = relu(...), returns (y, bits) with bits int32 [N/32, M];
+    ``gate_bits``: the elements of y whose bit is clear are zeroed (backward through the ReLU), returns y."""
+    a = _f32c(a, "a")
+    M, K = a.shape
+    N = b_hi.shape[0]
+    if a.stride(1) != 1 or a.stride(0) % 4 or b_hi.shape != (N, K) or b_hi.dtype != torch.bfloat16 or N % 32 or K % 8:
+        raise RuntimeError(f"gemm_relu_bits: unsupported operands a={tuple(a.shape)} b={tuple(b_hi.shape)}")
+    y = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    bits = torch.empty((N // 32, M), dtype=torch.int32, device=a.device) if relu_bits_out else None
+    if gate_bits is not None and (gate_bits.shape != (N // 32, M) or not gate_bits.is_contiguous()):
+        raise RuntimeError("gemm_relu_bits: gate_bits must be a contiguous int32 [N/32, M] tensor")
+    if resid is not None:
+        resid = _f32c(resid, "resid")
+        if resid.shape != (M, N) or resid.stride(1) != 1:
+            raise RuntimeError("gemm_relu_bits: resid must be [M, N] with unit column stride")
+    nbytes = 4.0 * (M * K + M * N + (M * N if resid is not None else 0)) + 4.0 * N * K + M * N / 8.0
+    with torch.cuda.device(a.device), _Timed("gemm_bf16x3_kernel", 2.0 * M * N * K, nbytes):
+        rc = _lib.load().mpf_gemm_bf16x3_relubits(
+            a.data_ptr(), a.stride(0), b_hi.contiguous().data_ptr(), b_lo.contiguous().data_ptr(), K,
+            None if bias is None else _f32c(bias, "bias").contiguous().data_ptr(), y.data_ptr(), N,
+            None if resid is None else resid.data_ptr(), 0 if resid is None else resid.stride(0), M, N, K,
+            int(relu_bits_out), None if bits is None else bits.data_ptr(),
+            None if gate_bits is None else gate_bits.data_ptr(), _stream())
+    _lib.check(rc, "gemm_bf16x3_relubits")
+    return (y, bits) if relu_bits_out else y
+
+
 def _gemm_bf16x3(a, b_hi, b_lo, bias, relu, transpose_c, split_out, resid, resid_rows, resid_cols, alpha, gate=None):
     """a [batch, M, K] fp32 (K contiguous); b_hi / b_lo bf16 [batch or 1, N, K] contiguous."""
     batch, M, K = a.shape

@@ -467,10 +467,15 @@ class _EncoderLayer(torch.autograd.Function):
         proj = native.gemm(attn.view(B * S, C), wo_hi, wo_lo, bo)
         src1, mean1, rstd1 = native.add_layernorm_fwd(x2, proj, g1, be1, eps1)
         w1_hi, w1_lo = native.split_b(w1)
-        hidden = native.gemm(src1, w1_hi, w1_lo, b1, relu=True)
+        if w1_hi.dtype == torch.bfloat16 and w1.shape[0] % 32 == 0:
+            # the ReLU pattern is kept as one bit per element for the backward (1/32 of re-reading `hidden`)
+            hidden, hbits = native.gemm_relu_bits(src1, w1_hi, w1_lo, b1, relu_bits_out=True)
+        else:
+            hidden, hbits = native.gemm(src1, w1_hi, w1_lo, b1, relu=True), None
         w2_hi, w2_lo = native.split_b(w2)
         y = native.gemm(hidden, w2_hi, w2_lo, b2)
         out, mean2, rstd2 = native.add_layernorm_fwd(src1, y, g2, be2, eps2)
+        ctx.hbits = hbits
         ctx.save_for_backward(x2, pos2, ref, shapes, lsi, value, ow, attn, proj, mean1, rstd1, src1, hidden, y, mean2,
                               rstd2, wv, wow, wo, g1, w1, w2, g2)
         ctx.geom = (B, S, C, M, P, host_shapes, woff.shape[0])
@@ -490,7 +495,10 @@ class _EncoderLayer(torch.autograd.Function):
         dsum2, dg2, db2, gb2 = native.add_layernorm_bwd(g_out.reshape(B * S, C), src1, y, g2, mean2, rstd2,
                                                         with_colsum=True)          # colsum(dx) = bias gradient of W2
         w2t_hi, w2t_lo = t_halves(w2)
-        gh = native.gemm_general(dsum2, w2t_hi, b_lo=w2t_lo, gate=hidden)            # ReLU mask in the epilogue
+        if ctx.hbits is not None and w2t_hi.dtype == torch.bfloat16:
+            gh = native.gemm_relu_bits(dsum2, w2t_hi, w2t_lo, gate_bits=ctx.hbits)   # ReLU mask (bits) in the epilogue
+        else:
+            gh = native.gemm_general(dsum2, w2t_hi, b_lo=w2t_lo, gate=hidden)        # ReLU mask in the epilogue
         gw2 = native.matmul_tn(dsum2, hidden)
         w1t_hi, w1t_lo = t_halves(w1)
         g_src1 = native.gemm(gh, w1t_hi, w1t_lo, resid=dsum2)                        # + the residual branch

@@ -172,3 +172,27 @@ def test_gemm_bf16x3_split_k_with_transposed_operand(batch, M, N, K, splits):
     r = a.double() @ f.double()
     assert y.shape == (batch, M, N)
     assert (y.double() - r).abs().max().item() / K ** 0.5 < TOL
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 1024, 256), (128, 32, 64), (4099, 256, 1024)])
+def test_relu_bit_mask_epilogues(M, N, K):
+    """relu output + one bit per element; the backward GEMM gated by those bits equals gating by the activation."""
+    g = torch.Generator(device=DEV).manual_seed(M + N)
+    a = torch.randn(M, K, device=DEV, generator=g)
+    w = torch.randn(N, K, device=DEV, generator=g) / K ** 0.5
+    b = torch.randn(N, device=DEV, generator=g)
+    w_hi, w_lo = native.split_bf16(w)
+    y, bits = native.gemm_relu_bits(a, w_hi, w_lo, b, relu_bits_out=True)
+    ref = torch.relu(a.double() @ w.double().t() + b.double())
+    assert (y.double() - ref).abs().max().item() < TOL * max(1.0, ref.abs().max().item())
+    assert bits.shape == (N // 32, M)
+    unpacked = ((bits.view(N // 32, M, 1) >> torch.arange(32, device=DEV).view(1, 1, 32)) & 1).bool()   # [N/32, M, 32]
+    assert torch.equal(unpacked.permute(1, 0, 2).reshape(M, N), y > 0)
+    # backward: dH = (dY @ W2) gated
+    w2 = torch.randn(N, K, device=DEV, generator=g) / K ** 0.5          # acts as W2^T: [d_ffn, d_model]
+    dy = torch.randn(M, K, device=DEV, generator=g)
+    w2_hi, w2_lo = native.split_bf16(w2)
+    gh = native.gemm_relu_bits(dy, w2_hi, w2_lo, gate_bits=bits)
+    gh_ref = (dy.double() @ w2.double().t()) * (y > 0)
+    assert (gh.double() - gh_ref).abs().max().item() < TOL * max(1.0, gh_ref.abs().max().item())
+    assert torch.equal(gh == 0, ~(y > 0) | (gh == 0))
