@@ -58,6 +58,20 @@ __device__ __forceinline__ void store_half_row_atom(uint8_t* atom_hi, uint8_t* a
   }
 }
 
+// Same for 8 values: columns [8 * part, 8 * part + 8) of the row (four threads share a row).
+__device__ __forceinline__ void store_quarter_row_atom(uint8_t* atom_hi, uint8_t* atom_lo, int r, int part,
+                                                       const float (&x)[8]) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const int sw = r * 128 + (((2 * part + c) ^ (r & 7)) << 4);
+    float4 h, l;
+    h.x = rn(x[4 * c]); h.y = rn(x[4 * c + 1]); h.z = rn(x[4 * c + 2]); h.w = rn(x[4 * c + 3]);
+    l.x = rn(x[4 * c] - h.x); l.y = rn(x[4 * c + 1] - h.y); l.z = rn(x[4 * c + 2] - h.z); l.w = rn(x[4 * c + 3] - h.w);
+    *reinterpret_cast<float4*>(atom_hi + sw) = h;
+    *reinterpret_cast<float4*>(atom_lo + sw) = l;
+  }
+}
+
 // three-pass 3xTF32 product step: D (+)= A B^T with split operands
 __device__ __forceinline__ void mma3(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
                                      uint32_t idesc, bool accumulate) {
@@ -298,11 +312,11 @@ constexpr int kPBytes = 2 * kAtom;              // P^T hi | lo  (same for dS^T)
 constexpr int kSmem = 4 * kKVBytes + kStages * kChunk + 2 * kPBytes + 256 + 1024;
 constexpr uint32_t kTmemCols = 256;
 constexpr int kTS = 0, kTP = 64, kTV = 128, kTK = 160;   // S^T 2 x 32, dP^T 2 x 32, dV 32, dK 32 columns
-// 12 warps: 0 TMA, 1 MMA, 2 TMEM allocation, 4-11 softmax.  A key row (TMEM lane) is shared by TWO threads -- warps
-// w and w + 4 address the same lane quarter -- each taking 16 of the chunk's 32 query columns: the exp2 / split /
-// store work of a chunk is the critical path of the tile, and with one softmax warp per scheduler it ran at the
-// issue latency of a single dependent instruction stream.
-constexpr int kThreads = 384;
+// 20 warps: 0 TMA, 1 MMA, 2 TMEM allocation, 4-19 softmax.  A key row (TMEM lane) is shared by FOUR threads -- warps
+// w, w + 4, w + 8, w + 12 address the same lane quarter -- each taking 8 of the chunk's 32 query columns: the exp2 /
+// split / store work of a chunk is the critical path of the tile, and with one softmax warp per scheduler it ran at
+// the issue latency of a single dependent instruction stream (one warp per row: 9.8 ms per step, two: 6.6 ms).
+constexpr int kThreads = 640;
 }  // namespace xk
 
 __global__ void __launch_bounds__(xk::kThreads, 1)
@@ -325,8 +339,8 @@ masked_xattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKh, const __gr
   uint64_t* qc_full = bars + 1;               // [2] chunk stage landed
   uint64_t* qc_empty = bars + 3;              // [2] commit after the chunk's dV / dK MMAs: stage free
   uint64_t* s_full = bars + 5;                // [2] commit after S^T / dP^T MMAs: TMEM buffer ready
-  uint64_t* s_empty = bars + 7;               // [2] count 8: softmax warps have read the TMEM buffer
-  uint64_t* p_full = bars + 9;                // count 8: P^T and dS^T written
+  uint64_t* s_empty = bars + 7;               // [2] count 16: softmax warps have read the TMEM buffer
+  uint64_t* p_full = bars + 9;                // count 16: P^T and dS^T written
   uint64_t* p_empty = bars + 10;              // commit after the dV / dK MMAs: P^T / dS^T buffers free
   uint64_t* acc_full = bars + 11;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
@@ -341,9 +355,9 @@ masked_xattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKh, const __gr
       mbar_init(&qc_full[s], 1);
       mbar_init(&qc_empty[s], 1);
       mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], 8);
+      mbar_init(&s_empty[s], 16);
     }
-    mbar_init(p_full, 8);
+    mbar_init(p_full, 16);
     mbar_init(p_empty, 1);
     mbar_init(acc_full, 1);
     fence_mbar_init();
@@ -421,7 +435,7 @@ masked_xattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKh, const __gr
     }
   } else if (warp >= 4) {
     const int ew = (warp - 4) & 3;                // TMEM lane quarter
-    const int half = (warp - 4) >> 2;             // which 16 of the chunk's 32 query columns
+    const int part = (warp - 4) >> 2;             // which 8 of the chunk's 32 query columns (0..3)
     const int r = ew * 32 + lane;                 // key row inside the tile == TMEM lane
     const int key = key0 + r;
     const bool key_ok = key < g.HW;
@@ -430,10 +444,10 @@ masked_xattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKh, const __gr
     const float* lse_b = g.lse2 + (static_cast<long long>(b) * g.heads + head) * g.Qt;
     const float* dlt_b = g.delta + (static_cast<long long>(b) * g.heads + head) * g.Qt;
     // per-chunk column data (log-sum-exp, delta, the mask word of each of the tile's four 32-key groups), staged by
-    // the first 128 softmax threads; double buffered by chunk parity, one named barrier (256 threads) per chunk
+    // the first 128 softmax threads; double buffered by chunk parity, one named barrier (512 threads) per chunk
     __shared__ float s_lse[2][kQc], s_dlt[2][kQc];
     __shared__ uint32_t s_mw[2][kQc][4];
-    const int st_id = threadIdx.x - 128;          // 0..255
+    const int st_id = threadIdx.x - 128;          // 0..511
 
     for (int c = 0; c < NC; ++c) {
       const int qc0 = c * kQc;
@@ -455,18 +469,18 @@ masked_xattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKh, const __gr
         }
         s_mw[pb][ql][wg] = w;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, 512;" ::: "memory");
       mbar_wait(&s_full[pb], (c >> 1) & 1);
       tc_fence_after();
-      float pt[16], ds[16];
+      float pt[8], ds[8];
       {
-        uint32_t sv[16], pv[16];
-        tmem_ld_32x16(lane_addr + kTS + pb * 32 + half * 16, sv);
-        tmem_ld_32x16(lane_addr + kTP + pb * 32 + half * 16, pv);
+        uint32_t sv[8], pv[8];
+        tmem_ld_32x8(lane_addr + kTS + pb * 32 + part * 8, sv);
+        tmem_ld_32x8(lane_addr + kTP + pb * 32 + part * 8, pv);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int ql = half * 16 + i;
+        for (int i = 0; i < 8; ++i) {
+          const int ql = part * 8 + i;
           const bool masked = !key_ok || (s_mw[pb][ql][ew] & bit) != 0u;
           const float p = masked ? 0.f : exp2f(__uint_as_float(sv[i]) - s_lse[pb][ql]);
           pt[i] = p;
@@ -478,23 +492,24 @@ masked_xattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKh, const __gr
       if (lane == 0) mbar_arrive(&s_empty[pb]);
       // the P^T / dS^T buffers are free once the previous chunk's dV / dK MMAs retired
       if (c > 0) mbar_wait(p_empty, (c - 1) & 1);
-      xb::store_half_row_atom(sP, sP + kAtom, r, half, pt);
-      xb::store_half_row_atom(sD, sD + kAtom, r, half, ds);
+      xb::store_quarter_row_atom(sP, sP + kAtom, r, part, pt);
+      xb::store_quarter_row_atom(sD, sD + kAtom, r, part, ds);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
     }
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    // the two threads of a row share the final store: half 0 writes dV, half 1 writes dK
-    uint32_t vv[32];
-    tmem_ld_32x32(lane_addr + (half == 0 ? kTV : kTK), vv);
+    // the four threads of a row share the final store: parts 0, 1 write the halves of dV, parts 2, 3 those of dK
+    uint32_t vv[16];
+    const int which = part >> 1, hh = part & 1;
+    tmem_ld_32x16(lane_addr + (which == 0 ? kTV : kTK) + 16 * hh, vv);
     tmem_ld_wait();
     if (key_ok) {
-      float* dst = (half == 0 ? g.dv : g.dk) + (static_cast<long long>(b) * g.HW + key) * g.E + head * 32;
-      const float sc = half == 0 ? 1.f : xb::kLn2;
+      float* dst = (which == 0 ? g.dv : g.dk) + (static_cast<long long>(b) * g.HW + key) * g.E + head * 32 + 16 * hh;
+      const float sc = which == 0 ? 1.f : xb::kLn2;
 #pragma unroll
-      for (int i = 0; i < 32; i += 4)
+      for (int i = 0; i < 16; i += 4)
         *reinterpret_cast<float4*>(dst + i) = make_float4(__uint_as_float(vv[i]) * sc, __uint_as_float(vv[i + 1]) * sc,
                                                           __uint_as_float(vv[i + 2]) * sc, __uint_as_float(vv[i + 3]) * sc);
     }
