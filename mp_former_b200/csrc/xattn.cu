@@ -40,7 +40,8 @@ constexpr int kVBytes = kXD * kXK * 4;   // 8 KiB   (one of Vt_hi / Vt_lo): two 
 constexpr int kPAtom = kXQ * 32 * 4;     // 16 KiB  (128 rows x 32 keys)
 constexpr int kPBytes = 2 * kPAtom;      // 32 KiB  (one of P_hi / P_lo)
 constexpr int kKVStage = 2 * kKBytes + 2 * kVBytes;          // 32 KiB
-constexpr int kXSmem = 2 * kQBytes + 2 * kKVStage + 2 * kPBytes + 256 + 1024;
+constexpr int kKVStages = 3;             // K / Vt ring: loads run two tiles ahead of the MMAs
+constexpr int kXSmem = 2 * kQBytes + kKVStages * kKVStage + 2 * kPBytes + 256 + 1024;
 constexpr uint32_t kTmemColsX = 256;     // S: 2 x 64, O_tile: 2 x 32
 constexpr int kTmemS = 0, kTmemO = 128;
 
@@ -65,18 +66,18 @@ masked_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_c
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                   // Q_hi | Q_lo
   uint8_t* sKV = smem + 2 * kQBytes;                    // stage s: K_hi | K_lo | Vt_hi | Vt_lo
-  uint8_t* sP = sKV + 2 * kKVStage;                     // P_hi | P_lo
+  uint8_t* sP = sKV + kKVStages * kKVStage;             // P_hi | P_lo
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPBytes);
   uint64_t* q_full = bars;          // [1]
-  uint64_t* kv_full = bars + 1;     // [2]
-  uint64_t* kv_empty = bars + 3;    // [2]
-  uint64_t* s_full = bars + 5;      // [2]
-  uint64_t* s_empty = bars + 7;     // [2]
-  uint64_t* p_full = bars + 9;      // [1]
-  uint64_t* p_empty = bars + 10;    // [1]
-  uint64_t* o_full = bars + 11;     // [2]
-  uint64_t* o_empty = bars + 13;    // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* kv_full = bars + 1;     // [kKVStages]
+  uint64_t* kv_empty = bars + 4;    // [kKVStages]
+  uint64_t* s_full = bars + 7;      // [2]
+  uint64_t* s_empty = bars + 9;     // [2]
+  uint64_t* p_full = bars + 11;     // [1]
+  uint64_t* p_empty = bars + 12;    // [1]
+  uint64_t* o_full = bars + 13;     // [2]
+  uint64_t* o_empty = bars + 15;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kXQ, head = blockIdx.y, b = blockIdx.z;
@@ -86,9 +87,11 @@ masked_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_c
     prefetch_tmap(&tmQh); prefetch_tmap(&tmQl); prefetch_tmap(&tmKh);
     prefetch_tmap(&tmKl); prefetch_tmap(&tmVh); prefetch_tmap(&tmVl);
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kKVStages; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&s_empty[i], 8);
       mbar_init(&o_full[i], 1);
@@ -111,8 +114,8 @@ masked_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_c
       tma_load_3d(sQ, &tmQh, q_full, head * kXD, q0, b);
       tma_load_3d(sQ + kQBytes, &tmQl, q_full, head * kXD, q0, b);
       for (int j = 0; j < T; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
+        const int st = j % kKVStages;
+        const uint32_t ph = (j / kKVStages) & 1;
         mbar_wait(&kv_empty[st], ph ^ 1);
         uint8_t* s = sKV + st * kKVStage;
         mbar_arrive_expect_tx(&kv_full[st], kKVStage);
@@ -133,11 +136,11 @@ masked_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_c
       const uint32_t q_hi = smem_u32(sQ), q_lo = q_hi + kQBytes;
       const uint32_t p_hi = smem_u32(sP), p_lo = p_hi + kPBytes;
       auto issue_s = [&](int j) {
-        const int st = j & 1;
-        mbar_wait(&kv_full[st], (j >> 1) & 1);
+        const int st = j & 1, kvs = j % kKVStages;
+        mbar_wait(&kv_full[kvs], (j / kKVStages) & 1);
         mbar_wait(&s_empty[st], ((j >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t k_hi = smem_u32(sKV + st * kKVStage), k_lo = k_hi + kKBytes;
+        const uint32_t k_hi = smem_u32(sKV + kvs * kKVStage), k_lo = k_hi + kKBytes;
         const uint32_t d = tmem_base + kTmemS + st * kXK;
 #pragma unroll
         for (int k = 0; k < kXD / 8; ++k) {
@@ -156,7 +159,8 @@ masked_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_c
         mbar_wait(p_full, j & 1);
         mbar_wait(&o_empty[st], ((j >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t v_hi = smem_u32(sKV + st * kKVStage + 2 * kKBytes), v_lo = v_hi + kVBytes;
+        const int kvs = j % kKVStages;
+        const uint32_t v_hi = smem_u32(sKV + kvs * kKVStage + 2 * kKBytes), v_lo = v_hi + kVBytes;
         const uint32_t d = tmem_base + kTmemO + st * kXD;
 #pragma unroll
         for (int k = 0; k < kXK / 8; ++k) {
@@ -168,7 +172,7 @@ masked_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_c
         }
         mma_commit(&o_full[st]);
         mma_commit(p_empty);
-        mma_commit(&kv_empty[st]);
+        mma_commit(&kv_empty[kvs]);
       }
     }
   } else if (warp >= 4) {

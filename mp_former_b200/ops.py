@@ -873,7 +873,8 @@ class _MaskedCrossAttention(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             wkt_hi, wkt_lo = native.split_b(wk.t().contiguous())
             wvt_hi, wvt_lo = native.split_b(wv.t().contiguous())
-            g_mem = (native.gemm(dk2, wkt_hi, wkt_lo) + native.gemm(dv2, wvt_hi, wvt_lo)).view(B, HW, E)
+            # dK Wk + dV Wv: the second GEMM adds the first one's result in its epilogue (no separate full-size add)
+            g_mem = native.gemm(dv2, wvt_hi, wvt_lo, resid=native.gemm(dk2, wkt_hi, wkt_lo)).view(B, HW, E)
         if ctx.needs_input_grad[2]:
             g_pos = (dk.sum(0) @ wk).view(1, HW, E)
         return g_qin, g_mem, g_pos, g_win, g_bin, g_wout, g_bout, None, None, None
