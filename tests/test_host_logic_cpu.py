@@ -199,3 +199,43 @@ def test_mask_threshold_equals_sigmoid_rule():
     g = torch.randn(1 << 20, generator=torch.Generator().manual_seed(0)) * torch.logspace(-9, 2, 1 << 20)
     g = torch.cat([g, torch.tensor([0.0, -0.0, float("inf"), -float("inf"), float("nan"), 1e-45, -1e-45])])
     assert torch.equal(g.sigmoid() < 0.5, g <= ops.MASK_LOGIT_THRESHOLD)
+
+
+def test_grad_fanout_and_head_collector_fall_back_to_plain_autograd_sums():
+    """ops.grad_fanout / ops.collect_mask_heads with consumers that do not speak the in-kernel accumulation protocol
+    (here: einsum on CPU): gradients equal the plain autograd result, DN / matching split included, unused heads
+    and missing DN gradients tolerated."""
+    from mp_former_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    B, Qt, C, H, W, nH, n_dn = 2, 9, 8, 4, 6, 3, 4
+    mf = torch.randn(B, C, H, W, generator=g, requires_grad=True)
+    embeds = [torch.randn(B, Qt, C, generator=g, requires_grad=True) for _ in range(nH)]
+    gouts = [torch.randn(B, Qt, H, W, generator=g) for _ in range(nH)]
+
+    def loss_of(dn, mm):
+        t = (mm[0] * gouts[0][:, n_dn:]).sum() + (dn[0] * gouts[0][:, :n_dn]).sum()
+        return t + (mm[2] * gouts[2][:, n_dn:]).sum()                     # head 1 unused, head 2: no DN gradient
+
+    aliases, shared = ops.grad_fanout(mf, nH)
+    masks = [torch.einsum("bqc,bchw->bqhw", e, a) for e, a in zip(embeds, aliases)]
+    dn, mm = ops.collect_mask_heads(masks, n_dn, shared)
+    assert dn[0].shape == (B, n_dn, H, W) and mm[0].shape == (B, Qt - n_dn, H, W)
+    loss_of(dn, mm).backward()
+    got = [mf.grad.clone()] + [None if e.grad is None else e.grad.clone() for e in embeds]
+    mf.grad = None
+    for e in embeds:
+        e.grad = None
+    masks = [torch.einsum("bqc,bchw->bqhw", e, mf) for e in embeds]
+    loss_of([m[:, :n_dn] for m in masks], [m[:, n_dn:] for m in masks]).backward()
+    assert torch.allclose(got[0], mf.grad, atol=1e-5)
+    for a, e in zip(got[1:], embeds):
+        if e.grad is None:
+            assert a is None or float(a.abs().max()) == 0.0
+        else:
+            assert torch.allclose(a, e.grad, atol=1e-5)
+    # without autograd (inference) both helpers are pass-throughs
+    with torch.no_grad():
+        al, sh = ops.grad_fanout(mf, 2)
+        assert sh is None and al[0] is mf
+        d2, m2 = ops.collect_mask_heads([masks[0].detach()], 0, None)
+        assert d2 is None and m2[0].shape == (B, Qt, H, W)
