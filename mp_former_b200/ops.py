@@ -1,11 +1,15 @@
-"""Device ops of the hot path (SURVEY.md §8 a5, a9-a12), each with exactly one implementation.
+"""Device ops of the hot path (SURVEY.md §8 a5-a12), each with exactly one implementation.
 
-``linear``, ``mask_logits``, ``attn_mask_from_logits`` and ``masked_cross_attention`` run forward AND
-backward on this package's hand-written sm_100a kernels (tcgen05 split-precision GEMMs: bf16x3 with in-kernel
-operand splitting and TMA-store epilogue for K-major products and for the token-reduction "TN" products of the
-weight gradients, 3xTF32 for the remaining mixed-major case; bit-packed mask kernels; fused masked-attention
-forward and the two backward kernels that recompute the probabilities from the saved log-sum-exp) through the C ABI.  ``self_attention`` and the tiny
-query-side layers (a few hundred rows) stay on library ops (launch-latency bound).
+Everything here runs forward AND backward on this package's hand-written sm_100a kernels through the C ABI:
+``linear`` / ``ffn`` / ``encoder_layer`` / ``mask_logits`` / ``conv1x1_nchw_to_cl`` / ``conv3x3_cl`` on the tcgen05
+split-precision GEMMs (bf16x3: K-major "NT" kernel and token-reduction "TN" kernel; 3xTF32 for the remaining
+mixed-major products), ``attn_mask_from_logits`` on the bit-packed mask kernels, ``masked_cross_attention`` on the
+fused attention forward and the two backward kernels that recompute the probabilities from the saved log-sum-exp,
+``add_layer_norm`` / ``group_norm_*`` / ``upsample2x_add_*`` on the row-wise and FPN-stage kernels.
+``grad_fanout`` / ``collect_mask_heads`` are autograd plumbing that lets the ten prediction heads share one batched
+backward.  ``self_attention`` over the few hundred queries and the query-side layers stay on library ops
+(launch-latency bound); ``conv2d_fp32`` pins the library convolution used for uncovered
+geometries to true fp32 in both directions.
 
 Inputs must be CUDA fp32 tensors; there is no CPU path.
 """
