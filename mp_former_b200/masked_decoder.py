@@ -294,6 +294,10 @@ class MultiScaleMaskedTransformerDecoder(_MaskedDecoderBase):
     def forward(self, x, mask_features, mask=None, dn_args=None):
         """ref decoder :427-523 (its ``dn_args`` branch calls the feature-DN ``prepare_for_dn``
         :369-419, which no MP-Former recipe uses)."""
+        with torch.autocast(device_type="cuda", enabled=False):
+            return self._forward([t.float() for t in x], mask_features.float(), mask, dn_args)
+
+    def _forward(self, x, mask_features, mask=None, dn_args=None):
         assert len(x) == self.num_feature_levels
         del mask
         if dn_args:
@@ -443,7 +447,14 @@ class MultiScaleMaskedTransformerDecoderMaskDN(_MaskedDecoderBase):
         return pm
 
     def forward(self, x, mask_features, mask=None, dn_args=None):
-        """ref decoder :1706-1857."""
+        """ref decoder :1706-1857.  The kernels compute in fp32 split precision whatever the trainer's autocast state
+        is (the reference runs this module in fp16 under AMP; its pixel decoder already forces fp32,
+        msdeformattn.py:314): autocast is switched off inside, so no library op of the path is re-cast behind the
+        custom kernels' backs."""
+        with torch.autocast(device_type="cuda", enabled=False):
+            return self._forward([t.float() for t in x], mask_features.float(), mask, dn_args)
+
+    def _forward(self, x, mask_features, mask=None, dn_args=None):
         assert len(x) == self.num_feature_levels
         del mask
         src, pos, size_list = self._memory(x)

@@ -183,3 +183,22 @@ def test_fused_encoder_layer_matches_the_module_path(monkeypatch):
     assert vals[-1] < 0.1, worst
     assert vals[int(0.9 * len(vals))] < 1e-2, worst
     assert vals[len(vals) // 2] < 5e-3, worst
+
+
+def test_decoder_under_autocast_matches_fp32_run():
+    """The trainer's AMP context (reference config SOLVER.AMP.ENABLED True) must not change the path: the modules
+    switch autocast off inside and compute in fp32 split precision."""
+    dec = build_decoder().to(DEV)
+    dec.load_state_dict(O.seeded_state_dict(decoder_template(), seed=51))
+    x, mf = cases.decoder_inputs()
+    dn_args = {"tgt": to_dev(cases.dn_targets()), "scalar": 1, "noise_scale": 0.0}
+    with torch.no_grad():
+        ref = dec(to_dev(x), mf.to(DEV), None, dn_args)
+        with torch.autocast(device_type="cuda", dtype=torch.float16):
+            got = dec([t.half() for t in to_dev(x)], mf.to(DEV).half(), None, dn_args)
+    assert got["pred_masks"].dtype == torch.float32
+    # inputs were rounded to fp16 on the way in: compare against the fp32 run on the same rounded inputs
+    with torch.no_grad():
+        ref16 = dec([t.half().float() for t in to_dev(x)], mf.to(DEV).half().float(), None, dn_args)
+    assert torch.equal(got["pred_logits"], ref16["pred_logits"]) and torch.equal(got["pred_masks"], ref16["pred_masks"])
+    assert ref["pred_masks"].shape == got["pred_masks"].shape
