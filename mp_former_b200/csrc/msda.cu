@@ -25,6 +25,8 @@
 //     gradcheck).
 #include "mpf_common.cuh"
 
+#include <cstdlib>
+
 namespace mpf {
 
 constexpr int kMaxTiledLevels = 8;
@@ -488,8 +490,8 @@ msda_enc_fwd_kernel(const float* __restrict__ value, const int64_t* __restrict__
   }
 }
 
-template <int LPI>
-__global__ void __launch_bounds__(kThreads, 3)
+template <int LPI, int OCC = 3>
+__global__ void __launch_bounds__(kThreads, OCC)
 msda_enc_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict__ value,
                     const int64_t* __restrict__ shapes, const int64_t* __restrict__ lstart,
                     const float* __restrict__ ow, const float* __restrict__ ref, long long ref_bstride, int S, int M,
@@ -870,7 +872,12 @@ int msda_enc_backward_f32(const float* grad_out, const float* value, const int64
   dim3 grid(t.num_chunks, M, B);
   switch (lpi) {
     case 4: msda_enc_bwd_kernel<4><<<grid, kThreads, 0, st>>>(grad_out, value, shapes, lstart, ow, ref, ref_bstride, S, M, L, Lq, gv, gow, t); break;
-    case 8: msda_enc_bwd_kernel<8><<<grid, kThreads, 0, st>>>(grad_out, value, shapes, lstart, ow, ref, ref_bstride, S, M, L, Lq, gv, gow, t); break;
+    case 8:
+      if (getenv("MPF_MSDA_BWD_OCC4") != nullptr)      // tuning aid: 64 registers (spilling ~300 B) at 4 CTAs per SM
+        msda_enc_bwd_kernel<8, 4><<<grid, kThreads, 0, st>>>(grad_out, value, shapes, lstart, ow, ref, ref_bstride, S, M, L, Lq, gv, gow, t);
+      else
+        msda_enc_bwd_kernel<8><<<grid, kThreads, 0, st>>>(grad_out, value, shapes, lstart, ow, ref, ref_bstride, S, M, L, Lq, gv, gow, t);
+      break;
     default: msda_enc_bwd_kernel<16><<<grid, kThreads, 0, st>>>(grad_out, value, shapes, lstart, ow, ref, ref_bstride, S, M, L, Lq, gv, gow, t); break;
   }
   count_launch();
