@@ -129,8 +129,8 @@ masked_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_c
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer (whole warp, one elected lane issues) =================
+    {
       constexpr uint32_t idesc_s = idesc_tf32(kXQ, kXK);   // S: 128 x 64
       constexpr uint32_t idesc_o = idesc_tf32(kXQ, kXD);   // O: 128 x 32
       const uint32_t q_hi = smem_u32(sQ), q_lo = q_hi + kQBytes;
@@ -145,11 +145,11 @@ masked_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_c
 #pragma unroll
         for (int k = 0; k < kXD / 8; ++k) {
           const uint32_t ko = k * 32;
-          mma_tf32_ss(d, smem_desc_sw128_kmajor(q_lo + ko), smem_desc_sw128_kmajor(k_hi + ko), idesc_s, k ? 1u : 0u);
-          mma_tf32_ss(d, smem_desc_sw128_kmajor(q_hi + ko), smem_desc_sw128_kmajor(k_lo + ko), idesc_s, 1u);
-          mma_tf32_ss(d, smem_desc_sw128_kmajor(q_hi + ko), smem_desc_sw128_kmajor(k_hi + ko), idesc_s, 1u);
+          mma_tf32_ss_elect(d, smem_desc_sw128_kmajor(q_lo + ko), smem_desc_sw128_kmajor(k_hi + ko), idesc_s, k ? 1u : 0u);
+          mma_tf32_ss_elect(d, smem_desc_sw128_kmajor(q_hi + ko), smem_desc_sw128_kmajor(k_lo + ko), idesc_s, 1u);
+          mma_tf32_ss_elect(d, smem_desc_sw128_kmajor(q_hi + ko), smem_desc_sw128_kmajor(k_hi + ko), idesc_s, 1u);
         }
-        mma_commit(&s_full[st]);
+        mma_commit_elect(&s_full[st]);
       };
       mbar_wait(q_full, 0);
       issue_s(0);
@@ -166,13 +166,13 @@ masked_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_c
         for (int k = 0; k < kXK / 8; ++k) {
           const uint32_t po = (k >> 2) * kPAtom + (k & 3) * 32;        // 32-key atoms of P
           const uint32_t vo = (k >> 2) * (kVBytes / 2) + (k & 3) * 32; // 32-key atoms of Vt
-          mma_tf32_ss(d, smem_desc_sw128_kmajor(p_lo + po), smem_desc_sw128_kmajor(v_hi + vo), idesc_o, k ? 1u : 0u);
-          mma_tf32_ss(d, smem_desc_sw128_kmajor(p_hi + po), smem_desc_sw128_kmajor(v_lo + vo), idesc_o, 1u);
-          mma_tf32_ss(d, smem_desc_sw128_kmajor(p_hi + po), smem_desc_sw128_kmajor(v_hi + vo), idesc_o, 1u);
+          mma_tf32_ss_elect(d, smem_desc_sw128_kmajor(p_lo + po), smem_desc_sw128_kmajor(v_hi + vo), idesc_o, k ? 1u : 0u);
+          mma_tf32_ss_elect(d, smem_desc_sw128_kmajor(p_hi + po), smem_desc_sw128_kmajor(v_lo + vo), idesc_o, 1u);
+          mma_tf32_ss_elect(d, smem_desc_sw128_kmajor(p_hi + po), smem_desc_sw128_kmajor(v_hi + vo), idesc_o, 1u);
         }
-        mma_commit(&o_full[st]);
-        mma_commit(p_empty);
-        mma_commit(&kv_empty[kvs]);
+        mma_commit_elect(&o_full[st]);
+        mma_commit_elect(p_empty);
+        mma_commit_elect(&kv_empty[kvs]);
       }
     }
   } else if (warp >= 4) {
