@@ -214,8 +214,11 @@ int mpf_gemm_bf16x3(const float* A, long long lda, long long a_batch_stride, con
 int mpf_gemm_bf16x3_tn(const float* A, long long lda, long long a_batch_stride, const float* B, long long ldb,
                        long long b_batch_stride, float* C, long long ldc, long long c_batch_stride, int batch, int M,
                        int N, int T, int k_splits, void* stream);
-/* Same product; accumulate != 0 adds it into C (TMA reduce-add, C must hold valid data) instead of overwriting: the
- * mask-feature gradient is the sum over the 10 prediction heads (ref decoder :1865 called at :1767,:1797). */
+/* Same product; accumulate != 0 adds it into C (TMA reduce-add, C must hold valid data -- e.g. zeros) instead of
+ * overwriting, and then C is [batch, M, N] for ANY k_splits: the K-splits of a batch entry add into the same slab
+ * (fp32 additions in arrival order, like the atomics of the MSDeformAttn backward).  Used for the weight gradients
+ * (no partial-slab reduction kernel) and for the mask-feature gradient summed over the prediction heads
+ * (ref decoder :1865 called at :1767,:1797). */
 int mpf_gemm_bf16x3_tn_ex(const float* A, long long lda, long long a_batch_stride, const float* B, long long ldb,
                           long long b_batch_stride, float* C, long long ldc, long long c_batch_stride, int batch, int M,
                           int N, int T, int k_splits, int accumulate, void* stream);

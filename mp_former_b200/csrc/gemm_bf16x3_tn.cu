@@ -345,7 +345,8 @@ gemm_bf16x3_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         fence_proxy_async_smem();
         epi_bar();
         if (issuer) {
-          if (g.accumulate) tma_reduce_add_3d(&tmC, buf, n0, m_t * kBM, slab);
+          // accumulate mode: all K-splits of a batch entry add into ONE output slab (zeroed or pre-filled by the caller)
+          if (g.accumulate) tma_reduce_add_3d(&tmC, buf, n0, m_t * kBM, slab / g.k_splits);
           else tma_store_3d(&tmC, buf, n0, m_t * kBM, slab);
           bulk_commit();
         }
@@ -505,7 +506,8 @@ static int gemm_bf16x3_tn_impl(const float* A, long long lda, long long a_batch_
     rc = make_tmap(&tb, B, N, T, batch, ldb, b_batch_stride, kBK, "B");
   }
   if (rc) return rc;
-  rc = make_tmap(&tc, C, N, M, static_cast<long long>(batch) * k_splits, ldc, c_batch_stride, kBM, "C");
+  rc = make_tmap(&tc, C, N, M, accumulate ? batch : static_cast<long long>(batch) * k_splits, ldc, c_batch_stride, kBM,
+                 "C");
   if (rc) return rc;
 
   static bool configured = false;

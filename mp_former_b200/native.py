@@ -29,6 +29,10 @@ def split_tf32(x):
 
 
 GEMM_MODE = os.environ.get("MPF_GEMM", "bf16x3")       # "bf16x3" (default) | "tf32x3"
+# split-K of the TN GEMM: partial slabs + a sum kernel (default, bit-reproducible); MPF_TN_REDUCE_ADD=1 lets the
+# splits add into one zeroed output through the TMA reduce-add epilogue instead -- measured no faster on the B200
+# (139.8 vs 140.4 ms per step on one box: the memsets and the L2 read-modify-write cost what the tiny sums cost)
+SPLITK_REDUCE_ADD = bool(os.environ.get("MPF_TN_REDUCE_ADD"))
 
 # Optional per-launch device timing of the GEMM kernels (bench.py's roofline leg): CUDA events on the launching
 # stream right around the C-ABI call, with the launch's algorithmic flops / bytes.  Off by default.
@@ -653,7 +657,8 @@ def gemm_tn(a, b, k_splits=1, accumulate_into=None):
     """C[i] = a[i]^T @ b[i] for a [batch, T, M], b [batch, T, N] (fp32, row-major; 2-D inputs = batch 1) on the
     bf16x3 TN kernel: both operands are split in-kernel, reduction over T, optional split-K (partials summed here).
     ``accumulate_into`` [batch, M, N] (contiguous fp32): the product is ADDED to it by the kernel's TMA reduce-add
-    epilogue and the same tensor is returned (no split-K in that mode)."""
+    epilogue and the same tensor is returned.  Split-K (``k_splits > 1``): partial slabs summed here (bit-reproducible); with
+    MPF_TN_REDUCE_ADD=1 the splits add into one zeroed output through the same epilogue instead."""
     a, b = _f32c(a, "a"), _f32c(b, "b")
     squeeze = a.dim() == 2
     if squeeze:
@@ -671,6 +676,13 @@ def gemm_tn(a, b, k_splits=1, accumulate_into=None):
     if N % 4:
         raise RuntimeError("gemm_tn: N must be a multiple of 4")
     k_splits = max(1, min(int(k_splits), (T + 31) // 32))
+    own = False
+    if accumulate_into is None and k_splits > 1 and SPLITK_REDUCE_ADD:
+        # split-K without partial slabs: the splits add into one zeroed output through the TMA reduce-add epilogue
+        accumulate_into = torch.zeros((batch, M, N), dtype=torch.float32, device=a.device)
+        own = True
+    elif accumulate_into is not None:
+        k_splits = 1
     if accumulate_into is not None:
         acc = accumulate_into
         if (acc.dtype != torch.float32 or not acc.is_contiguous() or acc.numel() != batch * M * N
@@ -681,9 +693,9 @@ def gemm_tn(a, b, k_splits=1, accumulate_into=None):
             rc = _lib.load().mpf_gemm_bf16x3_tn_ex(
                 a.data_ptr(), a.stride(1), a.stride(0) if batch > 1 else T * a.stride(1),
                 b.data_ptr(), b.stride(1), b.stride(0) if batch > 1 else T * b.stride(1),
-                acc.data_ptr(), N, M * N, batch, M, N, T, 1, 1, _stream())
+                acc.data_ptr(), N, M * N, batch, M, N, T, k_splits, 1, _stream())
         _lib.check(rc, "gemm_bf16x3_tn_ex")
-        return acc
+        return acc[0] if (own and squeeze) else acc
     out = torch.empty((batch * k_splits, M, N), dtype=torch.float32, device=a.device)
     with torch.cuda.device(a.device), _Timed("gemm_bf16x3_tn_kernel", 2.0 * batch * M * N * T,
                                              4.0 * batch * (T * M + T * N + k_splits * M * N)):
