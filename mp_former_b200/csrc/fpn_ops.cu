@@ -555,10 +555,9 @@ int mpf_upsample2x_add_nchw_bwd_f32(const float* g, int batch, int H, int W, int
               "upsample2x_add_bwd: needs even H, W %% 4 == 0 and C %% 32 == 0 (H=%d W=%d C=%d)", H, W, C);
   MPF_REQUIRE(aligned16(g_cur) && aligned16(g_prev), "upsample2x_add_bwd: 16-byte alignment");
   MPF_REQUIRE(batch <= 65535 && C / kBC <= 65535, "upsample2x_add_bwd: grid too large");
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured_on = 0;
+  if (first_use_on_this_device(configured_on)) {
     MPF_CUDA_OK(cudaFuncSetAttribute(upsample2x_add_nchw_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmem));
-    configured = true;
   }
   const int Hp = H / 2, Wp = W / 2;
   dim3 grid(static_cast<unsigned>((Wp + 31) / 32) * ((Hp + 1) / 2), C / kBC, batch);

@@ -760,10 +760,9 @@ static int gemm_bf16x3_impl(const float* A, long long lda, long long a_batch_str
   g.debug = 0;
   if (const char* dbg = getenv("MPF_GEMM_DEBUG")) g.debug = atoi(dbg);
 
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured_on = 0;
+  if (first_use_on_this_device(configured_on)) {
     MPF_CUDA_OK(cudaFuncSetAttribute(gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-    configured = true;
   }
   const long long tiles = static_cast<long long>(slabs) * g.tiles_m * g.tiles_n;
   const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());

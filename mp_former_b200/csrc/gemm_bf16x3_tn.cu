@@ -510,10 +510,9 @@ static int gemm_bf16x3_tn_impl(const float* A, long long lda, long long a_batch_
                  "C");
   if (rc) return rc;
 
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured_on = 0;
+  if (first_use_on_this_device(configured_on)) {
     MPF_CUDA_OK(cudaFuncSetAttribute(gemm_bf16x3_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-    configured = true;
   }
   const long long tiles = static_cast<long long>(batch) * k_splits * g.tiles_m * g.tiles_n;
   const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());

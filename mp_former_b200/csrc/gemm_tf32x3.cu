@@ -469,11 +469,10 @@ template <int BN, bool A_MN, bool B_MN, bool SPLIT_B>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tbh, const CUtensorMap& tbl, GemmArgs g,
                        cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured_on = 0;
+  if (first_use_on_this_device(configured_on)) {
     MPF_CUDA_OK(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, A_MN, B_MN, SPLIT_B>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    configured = true;
   }
   g.tiles_m = (g.M + kBM - 1) / kBM;
   g.tiles_n = (g.N + BN - 1) / BN;

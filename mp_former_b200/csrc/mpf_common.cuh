@@ -18,6 +18,17 @@ int finish_launch(const char* what);
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// True exactly once per (call site, device): function attributes such as the opt-in dynamic shared-memory size are
+// per device, so a process that drives several GPUs must set them on each (`seen`: one static mask per call site).
+inline bool first_use_on_this_device(unsigned long long& seen) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (seen & bit) return false;
+  seen |= bit;          // benign race: the attribute is set again at worst
+  return true;
+}
+
 }  // namespace mpf
 
 #define MPF_REQUIRE(cond, ...)        \

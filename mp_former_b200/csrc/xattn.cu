@@ -328,10 +328,9 @@ int mpf_masked_xattn_fwd_f32(const float* q_hi, const float* q_lo, const float* 
   if ((rc = make_tmap_f32_3d(&tkl, k_lo, E, HW, B, E, static_cast<long long>(HW) * E, kXD, kXK))) return rc;
   if ((rc = make_tmap_f32_3d(&tvh, vt_hi, HW, E, B, HW, static_cast<long long>(HW) * E, 32, kXD))) return rc;
   if ((rc = make_tmap_f32_3d(&tvl, vt_lo, HW, E, B, HW, static_cast<long long>(HW) * E, 32, kXD))) return rc;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured_on = 0;
+  if (first_use_on_this_device(configured_on)) {
     MPF_CUDA_OK(cudaFuncSetAttribute(masked_xattn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kXSmem));
-    configured = true;
   }
   XattnArgs g;
   g.bits = mask_bits; g.row_open = row_open; g.out = out; g.lse2 = lse2;

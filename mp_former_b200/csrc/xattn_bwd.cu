@@ -561,11 +561,10 @@ int mpf_masked_xattn_bwd_f32(const float* q_hi, const float* q_lo, const float* 
   if ((rc = make_tmap_f32_3d(&tv_l, v_lo, E, HW, B, E, ks, 32, xa::kK))) return rc;
   if ((rc = make_tmap_f32_3d(&tkt_h, kt_hi, HW, E, B, HW, ks, 32, 32))) return rc;
   if ((rc = make_tmap_f32_3d(&tkt_l, kt_lo, HW, E, B, HW, ks, 32, 32))) return rc;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured_on = 0;
+  if (first_use_on_this_device(configured_on)) {
     MPF_CUDA_OK(cudaFuncSetAttribute(masked_xattn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, xa::kSmem));
     MPF_CUDA_OK(cudaFuncSetAttribute(masked_xattn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, xk::kSmem));
-    configured = true;
   }
   XbwdArgs g;
   g.bits = mask_bits; g.row_open = row_open; g.lse2 = lse2; g.delta = delta; g.dq = dq; g.dk = dk; g.dv = dv;
