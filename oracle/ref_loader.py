@@ -170,6 +170,31 @@ def load_reference():
     return ns
 
 
+def _point_sample(input, point_coords, **kwargs):
+    """detectron2.projects.point_rend.point_features.point_sample (detectron2 is an unpinned "git master"
+    dependency of the reference, INSTALL.md:36-38, and is not vendored): a wrapper around F.grid_sample that takes
+    point coordinates in [0, 1] x [0, 1] ([N, P, 2]) instead of [-1, 1] grids -- restated from its published source."""
+    import torch.nn.functional as F
+    add_dim = False
+    if point_coords.dim() == 3:
+        add_dim = True
+        point_coords = point_coords.unsqueeze(2)
+    output = F.grid_sample(input, 2.0 * point_coords - 1.0, **kwargs)
+    if add_dim:
+        output = output.squeeze(3)
+    return output
+
+
+def load_matcher():
+    """The reference's HungarianMatcher (mask2former/modeling/matcher.py), imported unmodified; its only third-party
+    import is detectron2's ``point_sample`` (stand-in above).  Groundwork for SURVEY.md §8f rank 1."""
+    load_reference()
+    _mod("detectron2.projects")
+    _mod("detectron2.projects.point_rend")
+    _mod("detectron2.projects.point_rend.point_features", point_sample=_point_sample)
+    return importlib.import_module("mask2former.modeling.matcher")
+
+
 class cuda_is_identity:
     """Context manager: the reference's DN preparation hard-codes ``.cuda()`` / ``.to('cuda')``
     (reference mask2former_transformer_decoder.py:984-985,1029,1052).  To run it on CPU for golden

@@ -1,0 +1,39 @@
+"""CPU: the matcher restatement (oracle/matcher_oracle.py, groundwork for SURVEY.md §8f rank 1) against the golden
+assignments / cost terms produced by the UNMODIFIED reference matcher (tests/golden/make_golden_matcher.py)."""
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+from make_golden_matcher import inputs  # noqa: E402
+from oracle import matcher_oracle as MO  # noqa: E402
+
+
+def test_matcher_oracle_matches_reference_golden():
+    G = torch.load(os.path.join(HERE, "golden", "matcher.pt"), weights_only=False)
+    outputs, targets = inputs()
+    for case in G["cases"]:
+        wc, wm, wd = case["weights"]
+        torch.manual_seed(case["seed"])
+        idx, costs = MO.hungarian_match(outputs, targets, case["num_points"], wc, wm, wd)
+        assert len(idx) == len(case["indices"])
+        for (i, j), (gi, gj), C, t in zip(idx, case["indices"], costs, targets):
+            assert torch.equal(i, gi) and torch.equal(j, gj)
+            assert C.shape == (outputs["pred_logits"].shape[1], len(t["labels"]))
+            assert len(i) == min(C.shape)
+    g = torch.Generator().manual_seed(9)
+    a, t = torch.randn(6, 50, generator=g) * 2, (torch.rand(4, 50, generator=g) > 0.5).float()
+    assert torch.allclose(MO.batch_dice_cost(a, t), G["dice"], atol=1e-6)
+    assert torch.allclose(MO.batch_sigmoid_ce_cost(a, t), G["ce"], atol=1e-6)
+
+
+def test_point_sample_is_bilinear_at_unit_square_coordinates():
+    """The detectron2 helper restated in the oracle: pixel centres map to (i + 0.5) / size."""
+    m = torch.arange(12.0).view(1, 1, 3, 4)
+    xs = (torch.arange(4) + 0.5) / 4
+    ys = (torch.arange(3) + 0.5) / 3
+    pts = torch.stack(torch.meshgrid(xs, ys, indexing="xy"), -1).reshape(1, -1, 2)
+    got = MO.point_sample(m, pts).view(3, 4)
+    assert torch.allclose(got, m[0, 0], atol=1e-6)
