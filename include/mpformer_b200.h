@@ -308,6 +308,43 @@ int mpf_masked_xattn_bwd_f32(const float* q_hi, const float* q_lo, const float* 
                              int mask_words, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Hungarian matching on the device (the caller right after the prediction heads).
+ * ref: mask2former/modeling/matcher.py:97-157 (HungarianMatcher.memory_efficient_forward), :15-30 (batch_dice_loss),
+ *      :38-62 (batch_sigmoid_ce_loss); detectron2 point_sample (F.grid_sample at 2*c-1, bilinear, zeros padding,
+ *      align_corners=False); scipy.optimize.linear_sum_assignment (matcher.py:151).
+ *
+ * mpf_match_cost_f32: for every image b, query q and target j of that image
+ *     cost[Q*off[b] + q*n_b + j] = cost_mask * mean_p BCE(x_qp, t_jp) + cost_class * (-softmax(logits[b,q])[label_j])
+ *                                  + cost_dice * (1 - (2 sum_p sig(x_qp) t_jp + 1) / (sum_p sig(x_qp) + sum_p t_jp + 1))
+ *   with x_qp / t_jp the bilinear samples of pred_masks[b,q] / target mask j at point_coords[b,p] (one point set per
+ *   image shared by all its masks, matcher.py:124-137).  One row-major [Q, n_b] matrix per image, images back to back.
+ *     pred_logits   [B, Q, K+1] through (logits_img_stride, logits_q_stride), class dim contiguous
+ *     pred_masks    [B, Q, H, W] through (masks_img_stride, masks_q_stride), each H x W map contiguous
+ *     tgt_mask_ptrs [B] DEVICE array of device pointers; entry b -> [n_b, Hg, Wg] contiguous, uint8/bool (0/1) or,
+ *                   with tgt_is_f32 != 0, float32 (the reference converts with `.to(out_mask)`, matcher.py:117)
+ *     tgt_labels    [total_targets] int64, images back to back;  tgt_offsets [B+1] int32 prefix sums of n_b
+ *     point_coords  [B, P, 2] (x, y) in [0, 1], 8-byte aligned
+ *     workspace     >= mpf_match_cost_workspace_bytes(...) bytes (per-point-split partial sums; no atomics, so the
+ *                   result is run-to-run deterministic)
+ * mpf_lsap_f32: solves every image's [Q, n_b] assignment problem (one CTA each) with scipy's algorithm, scan order
+ *   and tie rule in float64, and writes the min(Q, n_b) pairs of image b at offset sum_{b'<b} min(Q, n_b') of
+ *   out_query / out_target (int64), ordered as scipy returns them (ascending query index).  *status (int32, zeroed by
+ *   the caller) is set to b+1 when image b's matrix is infeasible / contains NaN (scipy raises ValueError there) and
+ *   its pairs are written as -1.  max(Q, max_targets) <= 4266.
+ * ------------------------------------------------------------------------------------------- */
+long long mpf_match_cost_workspace_bytes(int batch, int num_queries, int total_targets, int max_targets,
+                                         int num_points);
+int mpf_match_cost_f32(const float* pred_logits, long long logits_img_stride, long long logits_q_stride,
+                       int num_classes_p1, const float* pred_masks, long long masks_img_stride,
+                       long long masks_q_stride, int H, int W, const void* const* tgt_mask_ptrs, int tgt_is_f32,
+                       int Hg, int Wg, const int64_t* tgt_labels, const int32_t* tgt_offsets, int total_targets,
+                       int max_targets, const float* point_coords, int batch, int num_queries, int num_points,
+                       float cost_class, float cost_mask, float cost_dice, void* workspace,
+                       long long workspace_bytes, float* cost, void* stream);
+int mpf_lsap_f32(const float* cost, const int32_t* tgt_offsets, int batch, int num_queries, int max_targets,
+                 int64_t* out_query, int64_t* out_target, int32_t* status, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * FPN stage of the pixel decoder (ref pixel_decoder/msdeformattn.py:343-351): the map changes layout twice around
  * the 3x3 convolution (library, NCHW); both crossings are fused into the elementwise work next to them.
  *   mpf_upsample2x_add_nchw_fwd_f32:  out[b,c,h,w] = cur[b,h,w,c] + bilinear_x2(prev)[b,h,w,c]

@@ -71,6 +71,11 @@ SIGNATURES = {
     "mpf_gt_mask_area_bits": (_c_int, [_c_vp] + [_c_int] * 5 + [_c_vp, _c_int, _c_vp]),
     "mpf_masked_xattn_fwd_f32": (_c_int, [_c_vp] * 10 + [_c_int] * 6 + [_c_vp]),
     "mpf_masked_xattn_bwd_f32": (_c_int, [_c_vp] * 21 + [_c_int] * 7 + [_c_vp]),
+    "mpf_match_cost_workspace_bytes": (_c_ll, [_c_int] * 5),
+    "mpf_match_cost_f32": (_c_int, [_c_vp, _c_ll, _c_ll, _c_int, _c_vp, _c_ll, _c_ll, _c_int, _c_int, _c_vp, _c_int,
+                                    _c_int, _c_int, _c_vp, _c_vp, _c_int, _c_int, _c_vp, _c_int, _c_int, _c_int,
+                                    ctypes.c_float, ctypes.c_float, ctypes.c_float, _c_vp, _c_ll, _c_vp, _c_vp]),
+    "mpf_lsap_f32": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp]),
 }
 
 _lib = None

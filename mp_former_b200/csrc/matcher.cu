@@ -1,0 +1,521 @@
+// Hungarian matching on the device (the step right after the decoder's prediction heads).
+//
+//   ref: mask2former/modeling/matcher.py:97-157 (HungarianMatcher.memory_efficient_forward), :15-62 (the two cost
+//        terms), detectron2 point_sample (= F.grid_sample at 2*c-1, bilinear, zeros padding, align_corners=False),
+//        scipy.optimize.linear_sum_assignment (matcher.py:151).
+//
+// The reference runs, per image and per prediction head, two grid_samples, two softplus maps, three einsums over
+// the 12544 sampled points, a device->host copy of the cost matrix (a stream sync) and a CPU solve: 16 x 10 syncs per
+// step at the bench geometry.  Here the whole batch is three launches with no host round trip:
+//
+//   match_cost_partial_kernel   grid (point splits, query tiles x target tiles, images).  A CTA owns 64 queries x
+//                               <=32 targets of one image and walks its share of the points in chunks of 128:
+//                               phase 1 samples the prediction logits (4 gathers per query and point; the corner
+//                               offsets and weights of a point are computed once per thread and reused for all its
+//                               queries) and the GT masks (uint8 or float) and leaves softplus(-x), softplus(x),
+//                               sigmoid(x) and t in shared memory, point-major with an odd row pitch so both the
+//                               phase-1 stores (lanes = points) and the phase-2 loads (lanes = queries) are
+//                               conflict-free; phase 2 is a 2x4 register tile per thread of the three point sums
+//                               sum pos*t, sum neg*(1-t), sum sig*t.  Partial sums per point split go to a workspace.
+//   match_cost_finish_kernel    one thread per (query, target): adds the splits in a fixed order (deterministic, no
+//                               atomics), forms the cross-entropy and dice costs, the class cost -softmax(logits)[label]
+//                               and the weighted total, written as one row-major [Q, n_b] matrix per image.
+//   lsap_kernel                 one CTA per image: shortest-augmenting-path LSAP in float64 with scipy's scan order and
+//                               tie rule (restated and pinned in oracle/lsap_oracle.py), the column scan parallel over
+//                               the CTA with an order-independent key, so the INDICES equal scipy's on equal costs.
+//
+// Bound: the gathers (Q*P*2 32-byte sectors per image and head out of a 26 MB logit map that was just written and is
+// L2-resident); arithmetic is ~1 GFLOP per head.
+#include "mpf_common.cuh"
+
+#include <math_constants.h>
+
+namespace mpf {
+
+constexpr int MC_PT = 128;       // points per chunk
+constexpr int MC_QT = 64;        // queries per CTA
+constexpr int MC_NT = 32;        // targets per CTA
+constexpr int MC_THREADS = 256;
+constexpr int MC_QS = MC_QT + 1; // shared-memory row pitches (odd: conflict-free both ways)
+constexpr int MC_TS = MC_NT + 1;
+constexpr size_t MC_SMEM = (3 * MC_PT * MC_QS + MC_PT * MC_TS) * sizeof(float);
+
+// Corner offsets (or -1 outside the map: zeros padding) and weights of one point on an H x W map.
+// Mirrors ATen's grid_sampler_2d (bilinear, zeros, align_corners=False) on grid = 2*c - 1:
+//   ix = ((gx + 1) * W - 1) / 2, nw = (x1 - ix) * (y1 - iy), ne = (ix - x0) * (y1 - iy), sw = ..., se = ...
+struct Corners {
+  int o[4];
+  float w[4];
+};
+
+__device__ __forceinline__ Corners point_corners(float cx, float cy, int H, int W) {
+  const float gx = __fsub_rn(__fmul_rn(2.0f, cx), 1.0f);
+  const float gy = __fsub_rn(__fmul_rn(2.0f, cy), 1.0f);
+  const float ix = __fsub_rn(__fmul_rn(__fadd_rn(gx, 1.0f), static_cast<float>(W)), 1.0f) * 0.5f;
+  const float iy = __fsub_rn(__fmul_rn(__fadd_rn(gy, 1.0f), static_cast<float>(H)), 1.0f) * 0.5f;
+  const float fx0 = floorf(ix), fy0 = floorf(iy);
+  const float fx1 = fx0 + 1.0f, fy1 = fy0 + 1.0f;
+  Corners c;
+  c.w[0] = __fmul_rn(fx1 - ix, fy1 - iy);   // nw
+  c.w[1] = __fmul_rn(ix - fx0, fy1 - iy);   // ne
+  c.w[2] = __fmul_rn(fx1 - ix, iy - fy0);   // sw
+  c.w[3] = __fmul_rn(ix - fx0, iy - fy0);   // se
+  // coordinates far outside the map (a caller's own point set) must not overflow the int conversion
+  const bool finite = (ix > -2.0f) && (iy > -2.0f) && (ix < static_cast<float>(W) + 1.0f) &&
+                      (iy < static_cast<float>(H) + 1.0f);
+  const int x0 = finite ? static_cast<int>(fx0) : -2, y0 = finite ? static_cast<int>(fy0) : -2;
+  const int x1 = x0 + 1, y1 = y0 + 1;
+  const bool vx0 = x0 >= 0 && x0 < W, vx1 = x1 >= 0 && x1 < W;
+  const bool vy0 = y0 >= 0 && y0 < H, vy1 = y1 >= 0 && y1 < H;
+  c.o[0] = (vx0 && vy0) ? y0 * W + x0 : -1;
+  c.o[1] = (vx1 && vy0) ? y0 * W + x1 : -1;
+  c.o[2] = (vx0 && vy1) ? y1 * W + x0 : -1;
+  c.o[3] = (vx1 && vy1) ? y1 * W + x1 : -1;
+  return c;
+}
+
+template <typename T>
+__device__ __forceinline__ float sample_map(const T* __restrict__ map, const Corners& c) {
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (c.o[k] >= 0) acc += static_cast<float>(__ldg(map + c.o[k])) * c.w[k];
+  return acc;
+}
+
+struct MatchCostArgs {
+  const float* pred_masks;        // [B, Q, H, W] through the two strides below
+  long long masks_img_stride, masks_q_stride;
+  const void* const* tgt_mask_ptrs;  // [B] device pointers, each [n_b, Hg, Wg] contiguous (uint8 0/1 or float)
+  const int* tgt_offsets;         // [B + 1] prefix sums of n_b
+  const float* point_coords;      // [B, P, 2] (x, y) in [0, 1]
+  float* part3;                   // [S, Q, ntot, 3]
+  float* part_sig;                // [S, B, Q]
+  float* part_t;                  // [S, ntot]
+  int B, Q, P, H, W, Hg, Wg, ntot, qtiles, nchunks;
+};
+
+template <typename TM>
+__global__ void __launch_bounds__(MC_THREADS) match_cost_partial_kernel(const MatchCostArgs a) {
+  extern __shared__ float smem[];
+  float* s_pos = smem;
+  float* s_neg = s_pos + MC_PT * MC_QS;
+  float* s_sig = s_neg + MC_PT * MC_QS;
+  float* s_t = s_sig + MC_PT * MC_QS;
+
+  const int b = blockIdx.z;
+  const int n0 = a.tgt_offsets[b];
+  const int nb = a.tgt_offsets[b + 1] - n0;
+  const int qt = blockIdx.y % a.qtiles, tt = blockIdx.y / a.qtiles;
+  const int j0 = tt * MC_NT;
+  if (j0 >= nb) return;                         // CTA-uniform (also images without targets)
+  const int q0 = qt * MC_QT;
+  const int nq = min(MC_QT, a.Q - q0), nj = min(MC_NT, nb - j0);
+  const int S = gridDim.x, s = blockIdx.x;
+  const int tid = threadIdx.x;
+
+  const float* pm = a.pred_masks + b * a.masks_img_stride + q0 * a.masks_q_stride;
+  const TM* tm = static_cast<const TM*>(a.tgt_mask_ptrs[b]) + static_cast<long long>(j0) * a.Hg * a.Wg;
+  const float* pc = a.point_coords + static_cast<long long>(b) * a.P * 2;
+
+  // phase 1 mapping: a thread owns one point of the chunk and every second query / target
+  const int p1 = tid & (MC_PT - 1), half = tid >> 7;
+  // phase 2 mapping: lanes = queries (lane, lane + 32), warp = four targets
+  const int lane = tid & 31, wj = tid >> 5;
+
+  float accP[2][4], accN[2][4], accD[2][4], sumS[2] = {0.f, 0.f}, sumT[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) accP[i][k] = accN[i][k] = accD[i][k] = 0.f;
+
+  for (int c = s; c < a.nchunks; c += S) {
+    const int pidx = c * MC_PT + p1;
+    const bool valid = pidx < a.P;
+    float cx = 0.f, cy = 0.f;
+    if (valid) {
+      const float2 xy = __ldg(reinterpret_cast<const float2*>(pc) + pidx);
+      cx = xy.x;
+      cy = xy.y;
+    }
+    {
+      const Corners cp = point_corners(cx, cy, a.H, a.W);
+      for (int qq = half; qq < MC_QT; qq += 2) {
+        float pos = 0.f, neg = 0.f, sig = 0.f;
+        if (valid && qq < nq) {
+          const float x = sample_map(pm + qq * a.masks_q_stride, cp);
+          // BCE-with-logits against 1 and against 0 (matcher.py:52-57): max(-+x, 0) + log1p(exp(-|x|))
+          const float sp = log1pf(expf(-fabsf(x)));
+          pos = fmaxf(-x, 0.f) + sp;
+          neg = fmaxf(x, 0.f) + sp;
+          sig = 1.0f / (1.0f + expf(-x));
+        }
+        s_pos[p1 * MC_QS + qq] = pos;
+        s_neg[p1 * MC_QS + qq] = neg;
+        s_sig[p1 * MC_QS + qq] = sig;
+      }
+    }
+    {
+      const Corners ct = point_corners(cx, cy, a.Hg, a.Wg);
+      for (int jj = half; jj < MC_NT; jj += 2) {
+        float t = 0.f;
+        if (valid && jj < nj) t = sample_map(tm + static_cast<long long>(jj) * a.Hg * a.Wg, ct);
+        s_t[p1 * MC_TS + jj] = t;
+      }
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int p = 0; p < MC_PT; ++p) {
+      const float ps[2] = {s_pos[p * MC_QS + lane], s_pos[p * MC_QS + lane + 32]};
+      const float ng[2] = {s_neg[p * MC_QS + lane], s_neg[p * MC_QS + lane + 32]};
+      const float sg[2] = {s_sig[p * MC_QS + lane], s_sig[p * MC_QS + lane + 32]};
+      float t[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) t[k] = s_t[p * MC_TS + wj * 4 + k];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        sumS[i] += sg[i];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          accP[i][k] += ps[i] * t[k];
+          accN[i][k] += ng[i] * (1.0f - t[k]);
+          accD[i][k] += sg[i] * t[k];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) sumT[k] += t[k];
+    }
+    __syncthreads();
+  }
+
+  // partial sums of this point split
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int ql = lane + 32 * i;
+    if (ql >= nq) continue;
+    const int q = q0 + ql;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int jl = wj * 4 + k;
+      if (jl >= nj) continue;
+      float* dst = a.part3 + ((static_cast<long long>(s) * a.Q + q) * a.ntot + n0 + j0 + jl) * 3;
+      dst[0] = accP[i][k];
+      dst[1] = accN[i][k];
+      dst[2] = accD[i][k];
+    }
+    if (tt == 0 && wj == 0) a.part_sig[(static_cast<long long>(s) * a.B + b) * a.Q + q] = sumS[i];
+  }
+  if (qt == 0 && lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int jl = wj * 4 + k;
+      if (jl < nj) a.part_t[static_cast<long long>(s) * a.ntot + n0 + j0 + jl] = sumT[k];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+match_cost_finish_kernel(const float* __restrict__ part3, const float* __restrict__ part_sig,
+                         const float* __restrict__ part_t, const float* __restrict__ logits,
+                         long long logits_img_stride, long long logits_q_stride, int K1,
+                         const long long* __restrict__ labels, const int* __restrict__ offsets, int B, int Q, int ntot,
+                         int S, int P, float w_class, float w_mask, float w_dice, float* __restrict__ cost) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<long long>(Q) * ntot) return;
+  const int q = static_cast<int>(idx / ntot), jg = static_cast<int>(idx - static_cast<long long>(q) * ntot);
+  int b = 0;
+  while (b + 1 < B && __ldg(offsets + b + 1) <= jg) ++b;
+  const int n0 = __ldg(offsets + b), nb = __ldg(offsets + b + 1) - n0;
+  float sp = 0.f, sn = 0.f, sd = 0.f, ss = 0.f, st = 0.f;
+  for (int s = 0; s < S; ++s) {
+    const float* p3 = part3 + ((static_cast<long long>(s) * Q + q) * ntot + jg) * 3;
+    sp += p3[0];
+    sn += p3[1];
+    sd += p3[2];
+    ss += part_sig[(static_cast<long long>(s) * B + b) * Q + q];
+    st += part_t[static_cast<long long>(s) * ntot + jg];
+  }
+  const float c_mask = (sp + sn) / static_cast<float>(P);                 // matcher.py:59-61
+  const float c_dice = 1.0f - (2.0f * sd + 1.0f) / (ss + st + 1.0f);      // matcher.py:26-29
+  // class cost: -softmax(logits[b, q])[label]   (matcher.py:107,113)
+  const float* row = logits + b * logits_img_stride + q * logits_q_stride;
+  const long long lab = __ldg(labels + jg);
+  float c_class;
+  if (lab < 0 || lab >= K1) {
+    c_class = CUDART_NAN_F;                                               // surfaces as "invalid" in the solver
+  } else {
+    float m = -CUDART_INF_F;
+    for (int k = 0; k < K1; ++k) m = fmaxf(m, __ldg(row + k));
+    float den = 0.f;
+    for (int k = 0; k < K1; ++k) den += expf(__ldg(row + k) - m);
+    c_class = -(expf(__ldg(row + lab) - m) / den);
+  }
+  cost[static_cast<long long>(Q) * n0 + static_cast<long long>(q) * nb + (jg - n0)] =
+      (w_mask * c_mask + w_class * c_class) + w_dice * c_dice;            // matcher.py:137-141
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Rectangular LSAP, one CTA per image.  Algorithm and tie rules: oracle/lsap_oracle.py (scipy's, restated).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int LSAP_THREADS = 128;
+
+struct ScanKey {       // minimum of (value, cls, ord) == the column scipy's sequential scan selects
+  double value;
+  int cls, ord, it;
+};
+
+__device__ __forceinline__ bool key_less(const ScanKey& x, const ScanKey& y) {
+  if (x.value != y.value) return x.value < y.value;
+  if (x.cls != y.cls) return x.cls < y.cls;
+  return x.ord < y.ord;
+}
+
+__device__ __forceinline__ ScanKey key_shfl_xor(const ScanKey& k, int m) {
+  ScanKey r;
+  r.value = __shfl_xor_sync(0xffffffffu, k.value, m);
+  r.cls = __shfl_xor_sync(0xffffffffu, k.cls, m);
+  r.ord = __shfl_xor_sync(0xffffffffu, k.ord, m);
+  r.it = __shfl_xor_sync(0xffffffffu, k.it, m);
+  return r;
+}
+
+__global__ void __launch_bounds__(LSAP_THREADS)
+lsap_kernel(const float* __restrict__ cost, const int* __restrict__ offsets, int Q, int dim,
+            long long* __restrict__ out_q, long long* __restrict__ out_t, int* __restrict__ status) {
+  extern __shared__ double lsap_smem[];
+  double* u = lsap_smem;            // [dim] rows
+  double* v = u + dim;              // [dim] cols
+  double* spc = v + dim;            // [dim] shortest path costs
+  int* path = reinterpret_cast<int*>(spc + dim);
+  int* col4row = path + dim;
+  int* row4col = col4row + dim;
+  int* remaining = row4col + dim;
+  int* SR = remaining + dim;
+  int* SC = SR + dim;
+  __shared__ ScanKey s_key[LSAP_THREADS / 32];
+  __shared__ int s_i, s_sink, s_num_remaining, s_fail;
+  __shared__ double s_min;
+
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int n0 = offsets[b], n = offsets[b + 1] - n0;
+  // matches of the images before this one
+  long long out0 = 0;
+  for (int bb = 0; bb < b; ++bb) out0 += min(Q, offsets[bb + 1] - offsets[bb]);
+  if (n <= 0) return;
+  const float* C = cost + static_cast<long long>(Q) * n0;    // [Q, n] row-major
+  const bool transposed = n < Q;                              // scipy: solve the transpose of a tall matrix
+  const int nr = transposed ? n : Q, nc = transposed ? Q : n;
+  const long long si = transposed ? 1 : n, sj = transposed ? n : 1;   // cost(i, j) = C[i * si + j * sj]
+
+  for (int k = tid; k < nr; k += LSAP_THREADS) { u[k] = 0.0; col4row[k] = -1; }
+  for (int k = tid; k < nc; k += LSAP_THREADS) { v[k] = 0.0; row4col[k] = -1; path[k] = -1; }
+  if (tid == 0) s_fail = 0;
+  __syncthreads();
+
+  for (int cur = 0; cur < nr; ++cur) {
+    for (int k = tid; k < nr; k += LSAP_THREADS) SR[k] = 0;
+    for (int k = tid; k < nc; k += LSAP_THREADS) { SC[k] = 0; spc[k] = CUDART_INF; remaining[k] = nc - k - 1; }
+    if (tid == 0) { s_i = cur; s_sink = -1; s_num_remaining = nc; s_min = 0.0; }
+    __syncthreads();
+    while (true) {
+      const int i = s_i, num_remaining = s_num_remaining;
+      const double min_val = s_min, ui = u[i];
+      ScanKey best;
+      best.value = CUDART_INF; best.cls = 2; best.ord = 0; best.it = -1;
+      for (int it = tid; it < num_remaining; it += LSAP_THREADS) {
+        const int j = remaining[it];
+        const double r = min_val + static_cast<double>(__ldg(C + i * si + j * sj)) - ui - v[j];
+        double d = spc[j];
+        if (r < d) { path[j] = i; spc[j] = r; d = r; }
+        if (d < CUDART_INF) {
+          ScanKey k;
+          k.value = d; k.it = it;
+          if (row4col[j] == -1) { k.cls = 0; k.ord = -it; } else { k.cls = 1; k.ord = it; }
+          if (best.it < 0 || key_less(k, best)) best = k;
+        }
+      }
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) {
+        const ScanKey o = key_shfl_xor(best, m);
+        if (o.it >= 0 && (best.it < 0 || key_less(o, best))) best = o;
+      }
+      if ((tid & 31) == 0) s_key[tid >> 5] = best;
+      __syncthreads();
+      if (tid == 0) {
+        ScanKey w = s_key[0];
+        for (int k = 1; k < LSAP_THREADS / 32; ++k) {
+          const ScanKey o = s_key[k];
+          if (o.it >= 0 && (w.it < 0 || key_less(o, w))) w = o;
+        }
+        SR[i] = 1;
+        if (w.it < 0) {                    // infeasible / NaN costs (scipy raises ValueError)
+          s_fail = 1;
+        } else {
+          s_min = w.value;
+          const int j = remaining[w.it];
+          if (row4col[j] == -1) s_sink = j; else s_i = row4col[j];
+          SC[j] = 1;
+          remaining[w.it] = remaining[num_remaining - 1];
+          s_num_remaining = num_remaining - 1;
+        }
+      }
+      __syncthreads();
+      if (s_fail || s_sink >= 0) break;
+    }
+    if (s_fail) break;
+    // dual variables
+    const double min_val = s_min;
+    for (int k = tid; k < nr; k += LSAP_THREADS)
+      if (SR[k] && k != cur) u[k] += min_val - spc[col4row[k]];
+    for (int k = tid; k < nc; k += LSAP_THREADS)
+      if (SC[k]) v[k] -= min_val - spc[k];
+    __syncthreads();
+    if (tid == 0) {
+      u[cur] += min_val;
+      int j = s_sink;
+      while (true) {                         // augment along the alternating path
+        const int i = path[j];
+        row4col[j] = i;
+        const int t = col4row[i];
+        col4row[i] = j;
+        j = t;
+        if (i == cur) break;
+      }
+    }
+    __syncthreads();
+  }
+
+  if (tid == 0) {
+    const int m = min(Q, n);
+    if (s_fail) {
+      for (int k = 0; k < m; ++k) { out_q[out0 + k] = -1; out_t[out0 + k] = -1; }
+      atomicExch(status, b + 1);
+    } else if (transposed) {                 // rows = targets, cols = queries: emit pairs in query order
+      int cnt = 0;
+      for (int q = 0; q < Q; ++q)
+        if (row4col[q] >= 0) { out_q[out0 + cnt] = q; out_t[out0 + cnt] = row4col[q]; ++cnt; }
+    } else {
+      for (int q = 0; q < Q; ++q) { out_q[out0 + q] = q; out_t[out0 + q] = col4row[q]; }
+    }
+  }
+}
+
+static int match_split(int B, int qtiles, int ttiles, int nchunks) {
+  // enough CTAs for ~2 waves of the 148 SMs (one 114 KB CTA per SM pair of slots), at most one chunk per split
+  const long long per_split = static_cast<long long>(B) * qtiles * ttiles;
+  long long s = (2 * 148 + per_split - 1) / per_split;
+  if (s < 1) s = 1;
+  if (s > nchunks) s = nchunks;
+  return static_cast<int>(s);
+}
+
+}  // namespace mpf
+
+extern "C" {
+
+long long mpf_match_cost_workspace_bytes(int batch, int num_queries, int total_targets, int max_targets,
+                                         int num_points) {
+  using namespace mpf;
+  if (batch <= 0 || num_queries <= 0 || total_targets < 0 || max_targets < 0 || num_points <= 0) return -1;
+  const int qtiles = (num_queries + MC_QT - 1) / MC_QT, ttiles = max(1, (max_targets + MC_NT - 1) / MC_NT);
+  const int nchunks = (num_points + MC_PT - 1) / MC_PT;
+  const long long S = match_split(batch, qtiles, ttiles, nchunks);
+  const long long floats = S * num_queries * total_targets * 3 + S * batch * num_queries + S * total_targets;
+  return (floats + 4) * static_cast<long long>(sizeof(float));
+}
+
+int mpf_match_cost_f32(const float* pred_logits, long long logits_img_stride, long long logits_q_stride,
+                       int num_classes_p1, const float* pred_masks, long long masks_img_stride,
+                       long long masks_q_stride, int H, int W, const void* const* tgt_mask_ptrs, int tgt_is_f32,
+                       int Hg, int Wg, const int64_t* tgt_labels, const int32_t* tgt_offsets, int total_targets,
+                       int max_targets, const float* point_coords, int batch, int num_queries, int num_points,
+                       float cost_class, float cost_mask, float cost_dice, void* workspace,
+                       long long workspace_bytes, float* cost, void* stream) {
+  using namespace mpf;
+  clear_error();
+  MPF_REQUIRE(batch > 0 && num_queries > 0 && num_points > 0 && H > 0 && W > 0 && Hg > 0 && Wg > 0 &&
+                  num_classes_p1 > 0,
+              "match_cost: sizes must be positive");
+  MPF_REQUIRE(total_targets >= 0 && max_targets >= 0 && max_targets <= total_targets,
+              "match_cost: bad target counts (total %d, max %d)", total_targets, max_targets);
+  if (total_targets == 0) return MPF_OK;       // nothing to match
+  MPF_REQUIRE(pred_logits && pred_masks && tgt_mask_ptrs && tgt_labels && tgt_offsets && point_coords && workspace &&
+                  cost,
+              "match_cost: null pointer argument");
+  MPF_REQUIRE(static_cast<long long>(H) * W < (1ll << 31) && static_cast<long long>(Hg) * Wg < (1ll << 31),
+              "match_cost: map too large");
+  MPF_REQUIRE(batch <= 65535, "match_cost: batch > 65535");
+  const long long need = mpf_match_cost_workspace_bytes(batch, num_queries, total_targets, max_targets, num_points);
+  MPF_REQUIRE(workspace_bytes >= need, "match_cost: workspace of %lld bytes, need %lld", workspace_bytes, need);
+  MPF_REQUIRE((reinterpret_cast<uintptr_t>(point_coords) & 7u) == 0, "match_cost: point_coords must be 8-byte aligned");
+
+  const int qtiles = (num_queries + MC_QT - 1) / MC_QT, ttiles = max(1, (max_targets + MC_NT - 1) / MC_NT);
+  const int nchunks = (num_points + MC_PT - 1) / MC_PT;
+  const int S = match_split(batch, qtiles, ttiles, nchunks);
+  MPF_REQUIRE(static_cast<long long>(qtiles) * ttiles <= 65535, "match_cost: too many query x target tiles");
+
+  MatchCostArgs a;
+  a.pred_masks = pred_masks;
+  a.masks_img_stride = masks_img_stride;
+  a.masks_q_stride = masks_q_stride;
+  a.tgt_mask_ptrs = tgt_mask_ptrs;
+  a.tgt_offsets = tgt_offsets;
+  a.point_coords = point_coords;
+  float* ws = static_cast<float*>(workspace);
+  a.part3 = ws;
+  a.part_sig = a.part3 + static_cast<long long>(S) * num_queries * total_targets * 3;
+  a.part_t = a.part_sig + static_cast<long long>(S) * batch * num_queries;
+  a.B = batch; a.Q = num_queries; a.P = num_points; a.H = H; a.W = W; a.Hg = Hg; a.Wg = Wg;
+  a.ntot = total_targets; a.qtiles = qtiles; a.nchunks = nchunks;
+
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const dim3 grid(S, qtiles * ttiles, batch);
+  static unsigned long long seen_u8 = 0, seen_f32 = 0;
+  if (tgt_is_f32) {
+    if (first_use_on_this_device(seen_f32))
+      MPF_CUDA_OK(cudaFuncSetAttribute(match_cost_partial_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(MC_SMEM)));
+    match_cost_partial_kernel<float><<<grid, MC_THREADS, MC_SMEM, st>>>(a);
+  } else {
+    if (first_use_on_this_device(seen_u8))
+      MPF_CUDA_OK(cudaFuncSetAttribute(match_cost_partial_kernel<uint8_t>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(MC_SMEM)));
+    match_cost_partial_kernel<uint8_t><<<grid, MC_THREADS, MC_SMEM, st>>>(a);
+  }
+  count_launch();
+  int rc = finish_launch("match_cost (partial sums)");
+  if (rc != MPF_OK) return rc;
+
+  const long long cells = static_cast<long long>(num_queries) * total_targets;
+  const long long blocks = (cells + 255) / 256;
+  MPF_REQUIRE(blocks < (1ll << 31), "match_cost: problem too large");
+  match_cost_finish_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+      a.part3, a.part_sig, a.part_t, pred_logits, logits_img_stride, logits_q_stride, num_classes_p1,
+      reinterpret_cast<const long long*>(tgt_labels), tgt_offsets, batch, num_queries, total_targets, S, num_points,
+      cost_class, cost_mask, cost_dice, cost);
+  count_launch();
+  return finish_launch("match_cost (finish)");
+}
+
+int mpf_lsap_f32(const float* cost, const int32_t* tgt_offsets, int batch, int num_queries, int max_targets,
+                 int64_t* out_query, int64_t* out_target, int32_t* status, void* stream) {
+  using namespace mpf;
+  clear_error();
+  MPF_REQUIRE(batch > 0 && num_queries > 0 && max_targets >= 0, "lsap: bad sizes");
+  if (max_targets == 0) return MPF_OK;
+  MPF_REQUIRE(cost && tgt_offsets && out_query && out_target && status, "lsap: null pointer argument");
+  const int dim = max(num_queries, max_targets);
+  const size_t smem = static_cast<size_t>(dim) * (3 * sizeof(double) + 6 * sizeof(int));
+  MPF_REQUIRE(smem <= 200 * 1024, "lsap: max(queries, targets) = %d exceeds the shared-memory solver's limit (4266)",
+              dim);
+  static unsigned long long seen = 0;
+  if (smem > 48 * 1024 && first_use_on_this_device(seen))
+    MPF_CUDA_OK(cudaFuncSetAttribute(lsap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  lsap_kernel<<<batch, LSAP_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+      cost, tgt_offsets, num_queries, dim, reinterpret_cast<long long*>(out_query),
+      reinterpret_cast<long long*>(out_target), status);
+  count_launch();
+  return finish_launch("lsap");
+}
+
+}  // extern "C"

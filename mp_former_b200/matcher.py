@@ -1,0 +1,166 @@
+"""Device-resident mirror of the reference's ``HungarianMatcher`` (mask2former/modeling/matcher.py:70-189): same
+constructor, same ``forward(outputs, targets)`` contract and result format, same consumption of the global random
+generator (one ``torch.rand(1, num_points, 2)`` per image, in image order, matcher.py:124) -- but the whole batch is
+matched in three kernel launches (native.match_cost + native.lsap) with ONE device->host copy of the finished index
+pairs, instead of, per image, two grid_samples, three einsums, a cost-matrix copy to the host (a stream sync) and a
+scipy solve.  With ``device_indices=True`` the pairs stay on the device and nothing synchronises at all (the number of
+pairs per image, min(Q, n_b), is known on the host from the target shapes).
+
+There is no CPU path: CUDA tensors only (the extension must be present; see mp_former_b200._lib)."""
+import torch
+from torch import nn
+
+from . import _lib, native
+
+
+class PackedTargets:
+    """The per-step, head-independent half of the matcher's inputs: label vector, per-image offsets and the device
+    table of mask pointers.  Built once per step and reused by the ten prediction heads' matchings."""
+
+    def __init__(self, targets, device):
+        masks = []
+        for t in targets:
+            m = t["masks"]
+            _lib.require_cuda(m, "targets[i]['masks']")
+            if m.dim() != 3:
+                raise RuntimeError("targets[i]['masks'] must be [n, H, W]")
+            if m.dtype == torch.bool:
+                m = m.contiguous().view(torch.uint8)
+            elif m.dtype == torch.uint8 or m.dtype == torch.float32:
+                m = m.contiguous()
+            else:                                   # the reference converts with `.to(out_mask)` (matcher.py:117)
+                m = m.to(torch.float32).contiguous()
+            masks.append(m)
+        kinds = {m.dtype for m in masks}
+        if len(kinds) > 1:
+            masks = [m.to(torch.float32) for m in masks]
+        self.masks = masks                          # keeps the storage behind the pointer table alive
+        self.is_f32 = bool(masks) and masks[0].dtype == torch.float32
+        self.counts = [int(m.shape[0]) for m in masks]
+        self.sizes = [tuple(m.shape[-2:]) for m in masks]
+        labels = [t["labels"].to(device=device, dtype=torch.int64) for t in targets]
+        for lab, n in zip(labels, self.counts):
+            if lab.numel() != n:
+                raise RuntimeError("targets[i]['labels'] and targets[i]['masks'] disagree on the number of instances")
+        self.labels = torch.cat(labels) if labels else torch.zeros(0, dtype=torch.int64, device=device)
+        self.device = device
+
+    def uniform(self):
+        return len(set(self.sizes)) <= 1
+
+    def tables(self, lo, hi):
+        """(ptrs int64 [hi-lo], offsets int32 [hi-lo+1], labels, counts) of images lo..hi-1."""
+        counts = self.counts[lo:hi]
+        offs = [0]
+        for n in counts:
+            offs.append(offs[-1] + n)
+        ptrs = torch.tensor([m.data_ptr() if m.shape[0] else 0 for m in self.masks[lo:hi]], dtype=torch.int64,
+                            device=self.device)
+        offsets = torch.tensor(offs, dtype=torch.int32, device=self.device)
+        first = sum(self.counts[:lo])
+        return ptrs, offsets, self.labels[first:first + offs[-1]], counts
+
+
+class HungarianMatcher(nn.Module):
+    """Assignment between the targets and the predictions of the network (ref matcher.py:70-189).
+
+    ``forward`` returns ``[(index_i, index_j)] * batch`` -- int64 tensors with ``len == min(num_queries, n_b)``,
+    ``index_i`` the selected predictions in ascending order, ``index_j`` the matched targets -- on the CPU like the
+    reference (matcher.py:153-156), or on the device with ``device_indices=True``."""
+
+    def __init__(self, cost_class: float = 1, cost_mask: float = 1, cost_dice: float = 1, num_points: int = 0,
+                 device_indices: bool = False):
+        super().__init__()
+        self.cost_class = cost_class
+        self.cost_mask = cost_mask
+        self.cost_dice = cost_dice
+        assert cost_class != 0 or cost_mask != 0 or cost_dice != 0, "all costs cant be 0"
+        self.num_points = num_points
+        self.device_indices = device_indices
+        self._packed_key = None
+        self._packed = None
+        self._tables = {}
+        self.last_status = None
+
+    # -- inputs shared by the heads of one step -------------------------------------------------------------------
+    def pack_targets(self, targets, device):
+        key = tuple((t["masks"].data_ptr(), tuple(t["masks"].shape), t["masks"].dtype, t["labels"].data_ptr())
+                    for t in targets)
+        if key != self._packed_key:
+            self._packed = PackedTargets(targets, device)
+            self._packed_key = key
+            self._tables = {}
+        return self._packed
+
+    def _tables_for(self, packed, lo, hi):
+        if (lo, hi) not in self._tables:
+            self._tables[(lo, hi)] = packed.tables(lo, hi)
+        return self._tables[(lo, hi)]
+
+    # -- the matching ------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def match_device(self, outputs, targets, point_coords=None):
+        """Returns (query_idx, target_idx, counts, cost, status): flat int64 device tensors holding the pairs of all
+        images back to back (min(Q, n_b) each), the host list n_b, the flat cost matrices and the solver status.
+        ``point_coords`` [B, P, 2] overrides the random points (tests)."""
+        logits, masks = outputs["pred_logits"], outputs["pred_masks"]
+        _lib.require_cuda(masks, "outputs['pred_masks']")
+        _lib.require_cuda(logits, "outputs['pred_logits']")
+        bs, num_queries = logits.shape[:2]
+        if len(targets) != bs:
+            raise RuntimeError(f"{len(targets)} targets for a batch of {bs}")
+        dev = masks.device
+        packed = self.pack_targets(targets, dev)
+        if point_coords is None:
+            # all masks of an image share one set of points; drawn per image like the reference (matcher.py:124)
+            point_coords = torch.cat([torch.rand(1, self.num_points, 2, device=dev) for _ in range(bs)])
+        logits = logits.float()                     # autocast heads: the costs are computed in fp32 (matcher.py:126-128)
+        masks = masks.float()
+        groups = [(0, bs)] if packed.uniform() else [(b, b + 1) for b in range(bs)]
+        qi, ti, costs, stats = [], [], [], []
+        for lo, hi in groups:
+            ptrs, offsets, labels, counts = self._tables_for(packed, lo, hi)
+            if sum(counts) == 0:
+                continue
+            hw = packed.sizes[lo]
+            cost = native.match_cost(logits[lo:hi], masks[lo:hi], ptrs, packed.is_f32, hw, labels, offsets, counts,
+                                     point_coords[lo:hi], self.cost_class, self.cost_mask, self.cost_dice)
+            q, t, status = native.lsap(cost, offsets, counts, num_queries)
+            qi.append(q), ti.append(t), costs.append(cost), stats.append(status)
+        if not qi:
+            z = torch.zeros(0, dtype=torch.int64, device=dev)
+            return z, z, packed.counts, torch.zeros(0, device=dev), torch.zeros(1, dtype=torch.int32, device=dev)
+        cat = (lambda xs: xs[0] if len(xs) == 1 else torch.cat(xs))
+        status = stats[0] if len(stats) == 1 else torch.stack(stats).max(0).values
+        self.last_status = status
+        return cat(qi), cat(ti), packed.counts, cat(costs), status
+
+    @torch.no_grad()
+    def memory_efficient_forward(self, outputs, targets):
+        num_queries = outputs["pred_logits"].shape[1]
+        q, t, counts, _, status = self.match_device(outputs, targets)
+        sizes = [min(num_queries, n) for n in counts]
+        if self.device_indices:
+            return list(zip(torch.split(q, sizes), torch.split(t, sizes)))
+        # ONE device->host copy for the batch (the reference: one per image, plus the solve on the host)
+        host = torch.cat([q, t, status.to(torch.int64)]).cpu()
+        m = q.numel()
+        if int(host[-1]) != 0:
+            raise ValueError(f"matrix of image {int(host[-1]) - 1} contains invalid numeric entries or is infeasible")
+        return list(zip(torch.split(host[:m], sizes), torch.split(host[m:2 * m], sizes)))
+
+    @torch.no_grad()
+    def forward(self, outputs, targets):
+        """outputs: {"pred_logits": [B, Q, K+1], "pred_masks": [B, Q, H, W]}; targets: list of B dicts with "labels"
+        [n_b] and "masks" [n_b, H_gt, W_gt] (ref matcher.py:159-179)."""
+        return self.memory_efficient_forward(outputs, targets)
+
+    def __repr__(self, _repr_indent=4):
+        head = "Matcher " + self.__class__.__name__
+        body = [
+            "cost_class: {}".format(self.cost_class),
+            "cost_mask: {}".format(self.cost_mask),
+            "cost_dice: {}".format(self.cost_dice),
+        ]
+        lines = [head] + [" " * _repr_indent + line for line in body]
+        return "\n".join(lines)

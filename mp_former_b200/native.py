@@ -755,3 +755,79 @@ def masked_xattn_bwd(q_hi, q_lo, k_hi, k_lo, kt_hi, kt_lo, v_hi, v_lo, d_o, bits
             B, Qt, qt_ld, HW, heads, E // heads, bits.shape[2], _stream())
     _lib.check(rc, "masked_xattn_bwd")
     return dq, dk, dv
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Hungarian matching on the device (ref mask2former/modeling/matcher.py:97-157)
+# ----------------------------------------------------------------------------------------------------------------
+def match_cost(pred_logits, pred_masks, tgt_mask_ptrs, tgt_is_f32, tgt_hw, tgt_labels, tgt_offsets, counts,
+               point_coords, cost_class, cost_mask, cost_dice):
+    """Cost matrices of a whole batch in one pass.  pred_logits [B, Q, K+1] f32, pred_masks [B, Q, H, W] f32 (may be
+    a query slice of a larger tensor), tgt_mask_ptrs int64 [B] (device pointers to each image's [n_b, Hg, Wg] masks),
+    tgt_labels int64 [ntot], tgt_offsets int32 [B+1], counts = the host list of n_b, point_coords [B, P, 2].
+    Returns a flat float tensor: image b's row-major [Q, n_b] matrix at Q * offsets[b]."""
+    for t, n in ((pred_logits, "pred_logits"), (pred_masks, "pred_masks"), (tgt_mask_ptrs, "tgt_mask_ptrs"),
+                 (tgt_labels, "tgt_labels"), (tgt_offsets, "tgt_offsets"), (point_coords, "point_coords")):
+        _lib.require_cuda(t, n)
+    if pred_logits.dtype != torch.float32 or pred_masks.dtype != torch.float32 or point_coords.dtype != torch.float32:
+        raise RuntimeError("match_cost: pred_logits, pred_masks and point_coords must be float32")
+    if pred_logits.dim() != 3 or pred_masks.dim() != 4 or pred_logits.shape[:2] != pred_masks.shape[:2]:
+        raise RuntimeError("match_cost: expected pred_logits [B, Q, K+1] and pred_masks [B, Q, H, W]")
+    B, Q, K1 = pred_logits.shape
+    H, W = pred_masks.shape[-2:]
+    if pred_masks.stride(-1) != 1 or pred_masks.stride(-2) != W:
+        pred_masks = pred_masks.contiguous()
+    if pred_logits.stride(-1) != 1:
+        pred_logits = pred_logits.contiguous()
+    point_coords = point_coords.contiguous()
+    if point_coords.shape[0] != B or point_coords.shape[-1] != 2 or point_coords.dim() != 3:
+        raise RuntimeError("match_cost: point_coords must be [B, P, 2]")
+    if tgt_mask_ptrs.dtype != torch.int64 or tgt_labels.dtype != torch.int64 or tgt_offsets.dtype != torch.int32:
+        raise RuntimeError("match_cost: tgt_mask_ptrs / tgt_labels must be int64 and tgt_offsets int32")
+    if len(counts) != B or tgt_offsets.numel() != B + 1 or tgt_mask_ptrs.numel() != B:
+        raise RuntimeError("match_cost: one target entry per image expected")
+    P = point_coords.shape[1]
+    ntot, nmax = int(sum(counts)), int(max(counts))
+    if tgt_labels.numel() != ntot:
+        raise RuntimeError("match_cost: tgt_labels does not hold sum(counts) labels")
+    cost = torch.empty(Q * ntot, dtype=torch.float32, device=pred_masks.device)
+    if ntot == 0:
+        return cost
+    lib = _lib.load()
+    ws_bytes = int(lib.mpf_match_cost_workspace_bytes(B, Q, ntot, nmax, P))
+    if ws_bytes < 0:
+        raise RuntimeError("match_cost: bad sizes")
+    ws = torch.empty((ws_bytes + 3) // 4, dtype=torch.float32, device=pred_masks.device)
+    with torch.cuda.device(pred_masks.device):
+        rc = lib.mpf_match_cost_f32(
+            pred_logits.data_ptr(), pred_logits.stride(0), pred_logits.stride(1), K1,
+            pred_masks.data_ptr(), pred_masks.stride(0), pred_masks.stride(1), H, W,
+            tgt_mask_ptrs.data_ptr(), int(bool(tgt_is_f32)), int(tgt_hw[0]), int(tgt_hw[1]),
+            tgt_labels.data_ptr(), tgt_offsets.data_ptr(), ntot, nmax, point_coords.data_ptr(), B, Q, P,
+            float(cost_class), float(cost_mask), float(cost_dice), ws.data_ptr(), ws.numel() * 4, cost.data_ptr(),
+            _stream())
+    _lib.check(rc, "match_cost")
+    return cost
+
+
+def lsap(cost, tgt_offsets, counts, num_queries):
+    """Solves every image's [Q, n_b] assignment problem on the device (scipy's algorithm and tie rule).
+    Returns (query_idx int64 [m], target_idx int64 [m], status int32 [1]) with m = sum_b min(Q, n_b); image b's pairs
+    start at sum_{b'<b} min(Q, n_b').  No host synchronisation."""
+    _lib.require_cuda(cost, "cost")
+    _lib.require_cuda(tgt_offsets, "tgt_offsets")
+    if cost.dtype != torch.float32 or tgt_offsets.dtype != torch.int32:
+        raise RuntimeError("lsap: cost must be float32 and tgt_offsets int32")
+    B, Q = len(counts), int(num_queries)
+    if tgt_offsets.numel() != B + 1 or cost.numel() != Q * int(sum(counts)) or not cost.is_contiguous():
+        raise RuntimeError("lsap: cost must hold one contiguous [Q, n_b] matrix per image")
+    m = int(sum(min(Q, int(n)) for n in counts))
+    out = torch.empty((2, m), dtype=torch.int64, device=cost.device)
+    status = torch.zeros(1, dtype=torch.int32, device=cost.device)
+    if m == 0:
+        return out[0], out[1], status
+    with torch.cuda.device(cost.device):
+        rc = _lib.load().mpf_lsap_f32(cost.data_ptr(), tgt_offsets.data_ptr(), B, Q, int(max(counts)),
+                                      out[0].data_ptr(), out[1].data_ptr(), status.data_ptr(), _stream())
+    _lib.check(rc, "lsap")
+    return out[0], out[1], status
