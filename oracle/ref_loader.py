@@ -195,6 +195,48 @@ def load_matcher():
     return importlib.import_module("mask2former.modeling.matcher")
 
 
+def _get_uncertain_point_coords_with_randomness(coarse_logits, uncertainty_func, num_points, oversample_ratio,
+                                                importance_sample_ratio):
+    """detectron2.projects.point_rend.point_features.get_uncertain_point_coords_with_randomness, restated from its
+    published source (PointRend, Kirillov et al. 2020, sec. 3.1): draw ``oversample_ratio * num_points`` uniform
+    points per mask, keep the ``importance_sample_ratio * num_points`` most uncertain ones (``torch.topk``) and fill up
+    with fresh uniform points.  RNG consumption: one ``torch.rand(R, kN, 2)`` then one ``torch.rand(R, N - bN, 2)``."""
+    assert oversample_ratio >= 1
+    assert 0 <= importance_sample_ratio <= 1
+    num_boxes = coarse_logits.shape[0]
+    num_sampled = int(num_points * oversample_ratio)
+    point_coords = torch.rand(num_boxes, num_sampled, 2, device=coarse_logits.device, dtype=coarse_logits.dtype)
+    point_logits = _point_sample(coarse_logits, point_coords, align_corners=False)
+    point_uncertainties = uncertainty_func(point_logits)
+    num_uncertain_points = int(importance_sample_ratio * num_points)
+    num_random_points = num_points - num_uncertain_points
+    idx = torch.topk(point_uncertainties[:, 0, :], k=num_uncertain_points, dim=1)[1]
+    shift = num_sampled * torch.arange(num_boxes, dtype=torch.long, device=coarse_logits.device)
+    idx = idx + shift[:, None]
+    point_coords = point_coords.view(-1, 2)[idx.view(-1), :].view(num_boxes, num_uncertain_points, 2)
+    if num_random_points > 0:
+        point_coords = torch.cat(
+            [point_coords, torch.rand(num_boxes, num_random_points, 2, device=coarse_logits.device)], dim=1)
+    return point_coords
+
+
+def load_criterion():
+    """The reference's SetCriterion (mask2former/modeling/criterion.py), imported unmodified.  Third-party stand-ins:
+    detectron2's ``get_world_size`` (-> torch.distributed's, 1 when not initialised), ``point_sample`` and
+    ``get_uncertain_point_coords_with_randomness`` (above)."""
+    load_matcher()
+    import torch.distributed as dist
+
+    def get_world_size():
+        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    _mod("detectron2.utils.comm", get_world_size=get_world_size)
+    pf = sys.modules["detectron2.projects.point_rend.point_features"]
+    pf.get_uncertain_point_coords_with_randomness = _get_uncertain_point_coords_with_randomness
+    _pkg("mask2former.utils", os.path.join(REFERENCE_ROOT, "mask2former", "utils"))
+    return importlib.import_module("mask2former.modeling.criterion")
+
+
 class cuda_is_identity:
     """Context manager: the reference's DN preparation hard-codes ``.cuda()`` / ``.to('cuda')``
     (reference mask2former_transformer_decoder.py:984-985,1029,1052).  To run it on CPU for golden
