@@ -345,6 +345,23 @@ int mpf_lsap_f32(const float* cost, const int32_t* tgt_offsets, int batch, int n
                  int64_t* out_query, int64_t* out_target, int32_t* status, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Point sampling of mask maps for the criterion.
+ * ref: mask2former/modeling/criterion.py:143-192 (SetCriterion.loss_masks), detectron2 point_sample
+ *      (F.grid_sample at 2*c-1, bilinear, zeros padding, align_corners=False) and its autograd backward.
+ *   mpf_point_sample_rows:         out[r, p] = bilinear(map_r, point_coords[r, p, :])   (neg_abs != 0: -|.|, the
+ *                                  uncertainty score of criterion.py:75-89)
+ *   mpf_point_sample_rows_bwd_f32: grad_map_r[corner] += w_corner * grad_out[r, p]  (fp32 atomics; the caller zeroes
+ *                                  the gradient maps; rows may alias the same map)
+ *     map_ptrs      [rows] DEVICE array of device pointers, each to one contiguous H x W map (uint8/bool 0/1, or
+ *                   float32 with maps_are_f32 != 0): rows are sampled where they live -- no gather, no conversion
+ *     point_coords  [rows, num_points, 2] (x, y) in [0, 1], 8-byte aligned;  out / grad_out [rows, num_points]
+ * ------------------------------------------------------------------------------------------- */
+int mpf_point_sample_rows(const void* const* map_ptrs, int maps_are_f32, int H, int W, const float* point_coords,
+                          int rows, int num_points, int neg_abs, float* out, void* stream);
+int mpf_point_sample_rows_bwd_f32(float* const* grad_map_ptrs, int H, int W, const float* point_coords, int rows,
+                                  int num_points, const float* grad_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * FPN stage of the pixel decoder (ref pixel_decoder/msdeformattn.py:343-351): the map changes layout twice around
  * the 3x3 convolution (library, NCHW); both crossings are fused into the elementwise work next to them.
  *   mpf_upsample2x_add_nchw_fwd_f32:  out[b,c,h,w] = cur[b,h,w,c] + bilinear_x2(prev)[b,h,w,c]

@@ -76,6 +76,8 @@ SIGNATURES = {
                                     _c_int, _c_int, _c_vp, _c_vp, _c_int, _c_int, _c_vp, _c_int, _c_int, _c_int,
                                     ctypes.c_float, ctypes.c_float, ctypes.c_float, _c_vp, _c_ll, _c_vp, _c_vp]),
     "mpf_lsap_f32": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp]),
+    "mpf_point_sample_rows": (_c_int, [_c_vp, _c_int, _c_int, _c_int, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
+    "mpf_point_sample_rows_bwd_f32": (_c_int, [_c_vp, _c_int, _c_int, _c_vp, _c_int, _c_int, _c_vp, _c_vp]),
 }
 
 _lib = None

@@ -831,3 +831,77 @@ def lsap(cost, tgt_offsets, counts, num_queries):
                                       out[0].data_ptr(), out[1].data_ptr(), status.data_ptr(), _stream())
     _lib.check(rc, "lsap")
     return out[0], out[1], status
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Point sampling for the criterion (ref mask2former/modeling/criterion.py:143-192)
+# ----------------------------------------------------------------------------------------------------------------
+def point_sample_rows(map_ptrs, maps_are_f32, hw, coords, neg_abs=False):
+    """out[r, p] = bilinear(map_r, coords[r, p]) with map_r the H x W map (uint8 or float32) at device address
+    map_ptrs[r] (int64 [R]); coords [R, P, 2] f32 in [0, 1].  No autograd (see PointSampleRows)."""
+    _lib.require_cuda(map_ptrs, "map_ptrs")
+    _lib.require_cuda(coords, "coords")
+    if map_ptrs.dtype != torch.int64 or coords.dtype != torch.float32 or coords.dim() != 3 or coords.shape[-1] != 2:
+        raise RuntimeError("point_sample_rows: map_ptrs int64 [R] and coords float32 [R, P, 2] expected")
+    coords = coords.contiguous()
+    R, P = coords.shape[:2]
+    if map_ptrs.numel() != R:
+        raise RuntimeError("point_sample_rows: one map pointer per row of coords expected")
+    out = torch.empty((R, P), dtype=torch.float32, device=coords.device)
+    with torch.cuda.device(coords.device):
+        rc = _lib.load().mpf_point_sample_rows(map_ptrs.data_ptr(), int(bool(maps_are_f32)), int(hw[0]), int(hw[1]),
+                                               coords.data_ptr(), R, P, int(bool(neg_abs)), out.data_ptr(), _stream())
+    _lib.check(rc, "point_sample_rows")
+    return out
+
+
+class PointSampleRows(torch.autograd.Function):
+    """Differentiable sampling of rows of a float32 tensor of maps: ``maps`` [..., H, W] (any leading dims, each map
+    contiguous), ``row_index`` int64 [R] = flat index of the map each row samples (rows may repeat a map).  Forward
+    reads the maps in place; backward returns a dense zero gradient with the samples' contributions added."""
+
+    @staticmethod
+    def forward(ctx, maps, row_index, coords):
+        _lib.require_cuda(maps, "maps")
+        if maps.dtype != torch.float32 or maps.dim() < 3:
+            raise RuntimeError("PointSampleRows: float32 maps [..., H, W] expected")
+        H, W = maps.shape[-2:]
+        if maps.stride(-1) != 1 or maps.stride(-2) != W:
+            raise RuntimeError("PointSampleRows: every H x W map must be contiguous")
+        lead = maps.shape[:-2]
+        # element offset of every map: flat index -> multi-index over the leading dims -> strides
+        offs = torch.zeros_like(row_index)
+        rem = row_index
+        for size, stride in zip(reversed(lead), reversed(maps.stride()[:-2])):
+            offs = offs + (rem % size) * stride
+            rem = rem // size
+        coords = coords.contiguous()
+        ctx.save_for_backward(row_index, coords)
+        ctx.maps_shape = tuple(maps.shape)
+        ptrs = maps.data_ptr() + 4 * offs
+        return point_sample_rows(ptrs, True, (H, W), coords)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        row_index, coords = ctx.saved_tensors
+        shape = ctx.maps_shape
+        H, W = shape[-2:]
+        grad = torch.zeros(shape, dtype=torch.float32, device=grad_out.device)       # contiguous: map i at i * H * W
+        ptrs = grad.data_ptr() + (4 * H * W) * row_index
+        point_sample_rows_bwd(ptrs, (H, W), coords, grad_out)
+        return grad, None, None
+
+
+def point_sample_rows_bwd(grad_map_ptrs, hw, coords, grad_out):
+    """grad_map_r[corner] += w_corner * grad_out[r, p] (fp32 atomics) for the zero-initialised H x W float32 maps at
+    device addresses grad_map_ptrs[r]."""
+    _lib.require_cuda(grad_out, "grad_out")
+    grad_out = grad_out.contiguous()
+    if grad_out.dtype != torch.float32 or grad_out.shape != coords.shape[:2] or not coords.is_contiguous():
+        raise RuntimeError("point_sample_rows_bwd: grad_out float32 [R, P] matching contiguous coords [R, P, 2] expected")
+    R, P = grad_out.shape
+    with torch.cuda.device(grad_out.device):
+        rc = _lib.load().mpf_point_sample_rows_bwd_f32(grad_map_ptrs.data_ptr(), int(hw[0]), int(hw[1]),
+                                                       coords.data_ptr(), R, P, grad_out.data_ptr(), _stream())
+    _lib.check(rc, "point_sample_rows_bwd")

@@ -1,0 +1,152 @@
+"""GPU parity of the criterion's device path (mp_former_b200/criterion.py, csrc/point_sample.cu)
+against the CPU/GPU-agnostic oracle (oracle/criterion_oracle.py, pinned to the unmodified reference by
+tests/golden/criterion.pt) run on the same device with the same seed (identical random-number consumption), and of the
+two sampling kernels against torch's grid_sample.  Tolerances: samples 1e-5 abs (fp32, same bilinear formula); losses
+1e-4 relative (sums over the sampled points in a different order); gradients 1e-4 relative + 1e-6 abs (fp32 atomics)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+from make_golden_criterion import CASES, CFG, inputs  # noqa: E402
+from oracle import criterion_oracle as CO  # noqa: E402
+from oracle import matcher_oracle as MO  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _to(x, dev="cuda"):
+    if isinstance(x, torch.Tensor):
+        return x.to(dev)
+    if isinstance(x, dict):
+        return {k: _to(v, dev) for k, v in x.items()}
+    if isinstance(x, list):
+        return [_to(v, dev) for v in x]
+    return x
+
+
+@pytest.mark.parametrize("as_float", [False, True])
+def test_point_sample_rows_equals_grid_sample(as_float):
+    from mp_former_b200 import native
+    g = torch.Generator().manual_seed(3)
+    maps = torch.rand(5, 40, 56, generator=g) > 0.5
+    maps = (maps.float() * torch.randn(5, 40, 56, generator=g)) if as_float else maps
+    rows = torch.tensor([4, 0, 0, 2, 3, 1, 4])
+    coords = torch.rand(len(rows), 333, 2, generator=g)
+    coords[0, :4] = torch.tensor([[0.0, 0.0], [1.0, 1.0], [0.0, 1.0], [0.5 / 56, 0.5 / 40]])
+    coords[1, 0] = torch.tensor([-0.3, 1.7])                       # outside the map: zeros
+    ref = MO.point_sample(maps.float()[rows][:, None], coords)[:, 0]
+    dm = maps.cuda() if as_float else maps.cuda().view(torch.uint8)
+    ptrs = dm.data_ptr() + rows.cuda() * (40 * 56 * dm.element_size())
+    got = native.point_sample_rows(ptrs, as_float, (40, 56), coords.cuda())
+    assert torch.allclose(got.cpu(), ref, atol=1e-5)
+    neg = native.point_sample_rows(ptrs, as_float, (40, 56), coords.cuda(), neg_abs=True)
+    assert torch.equal(neg, -got.abs())
+
+
+def test_point_sample_rows_autograd_on_a_strided_slice():
+    from mp_former_b200 import native
+    g = torch.Generator().manual_seed(4)
+    full = torch.randn(3, 9, 20, 28, generator=g)
+    rows = torch.tensor([0, 5, 5, 11, 17])                         # flat (b, q) over the [3, 6] slice, one repeated
+    coords = torch.rand(len(rows), 200, 2, generator=g)
+    w = torch.randn(len(rows), 200, generator=g)
+    a = full.clone().requires_grad_(True)
+    ref = MO.point_sample(a[:, 3:].reshape(18, 1, 20, 28)[rows], coords)[:, 0]
+    (ref * w).sum().backward()
+    b = full.cuda().requires_grad_(True)
+    got = native.PointSampleRows.apply(b[:, 3:], rows.cuda(), coords.cuda())
+    (got * w.cuda()).sum().backward()
+    assert torch.allclose(got.detach().cpu(), ref.detach(), atol=1e-5)
+    assert torch.allclose(b.grad.cpu(), a.grad, rtol=1e-4, atol=1e-6)
+    with pytest.raises(RuntimeError):
+        native.PointSampleRows.apply(full, rows, coords)           # CPU tensors: no fallback
+
+
+def _device_criterion(no_lb=False, device_indices=True):
+    from mp_former_b200.criterion import SetCriterion
+    from mp_former_b200.matcher import HungarianMatcher
+    m = HungarianMatcher(CFG["cost_class"], CFG["cost_mask"], CFG["cost_dice"], CFG["num_points"],
+                         device_indices=device_indices)
+    return SetCriterion(CFG["num_classes"], matcher=m, weight_dict={}, eos_coef=CFG["eos_coef"],
+                        losses=["labels", "masks"], num_points=CFG["num_points"],
+                        oversample_ratio=CFG["oversample_ratio"],
+                        importance_sample_ratio=CFG["importance_sample_ratio"], dn_no_lb=no_lb).cuda()
+
+
+def test_criterion_equals_oracle_on_device_all_cases():
+    for name, with_dn, training, no_lb, seed in CASES:
+        outputs, targets = inputs(with_dn=with_dn)
+        o, t = _to(outputs), _to(targets)
+        crit = _device_criterion(no_lb).train(training)
+        torch.manual_seed(seed)
+        got = crit(o, t)
+        torch.manual_seed(seed)
+        ref = CO.set_criterion(o, t, losses=["labels", "masks"], training=training, dn_no_lb=no_lb, **CFG)
+        assert sorted(got) == sorted(ref), (name, sorted(set(got) ^ set(ref)))
+        for k in ref:
+            assert torch.allclose(got[k], ref[k], rtol=1e-4, atol=1e-6), (name, k, got[k], ref[k])
+
+
+def test_criterion_gradients_equal_oracle_on_device():
+    outputs, targets = inputs(with_dn=True)
+    o, t = _to(outputs), _to(targets)
+    full = torch.cat([torch.zeros(2, 3, 24, 32, device="cuda"), o["pred_masks"]], 1)
+
+    def run(fn):
+        masks_leaf, logits_leaf = full.clone().requires_grad_(True), o["pred_logits"].clone().requires_grad_(True)
+        oo = dict(o)
+        oo["pred_masks"], oo["pred_logits"] = masks_leaf[:, 3:], logits_leaf
+        torch.manual_seed(5)
+        losses = fn(oo)
+        sum(v for k, v in sorted(losses.items()) if v.requires_grad).backward()
+        return masks_leaf.grad, logits_leaf.grad
+
+    crit = _device_criterion().train(True)
+    gm_a, gl_a = run(lambda oo: crit(oo, t))
+    gm_b, gl_b = run(lambda oo: CO.set_criterion(oo, t, losses=["labels", "masks"], training=True, **CFG))
+    assert torch.allclose(gm_a, gm_b, rtol=1e-4, atol=1e-6) and float(gm_b.abs().sum()) > 0
+    assert torch.allclose(gl_a, gl_b, rtol=1e-4, atol=1e-6)
+
+
+def test_criterion_bench_geometry_properties():
+    """4 images at the bench geometry (100 queries + 2 dn groups, 256x256 logits, 1024x1024 bool GT masks, 12544
+    points, 2 auxiliary layers): finite losses, every expected key, and mask-logit gradients only on matched / dn rows."""
+    from mp_former_b200.criterion import SetCriterion
+    from mp_former_b200.matcher import HungarianMatcher
+    g = torch.Generator(device="cuda").manual_seed(6)
+    B, Q, K, counts, groups = 4, 100, 80, [3, 11, 1, 20], 2
+    max_num = max(counts)
+
+    def head(q):
+        return {"pred_logits": torch.randn(B, q, K + 1, device="cuda", generator=g),
+                "pred_masks": (torch.randn(B, q, 256, 256, device="cuda", generator=g) * 3).requires_grad_(True)}
+
+    targets = []
+    for n in counts:
+        m = torch.rand(n, 32, 32, device="cuda", generator=g) > 0.7
+        targets.append({"labels": torch.randint(0, K, (n,), device="cuda", generator=g),
+                        "masks": m.repeat_interleave(32, 1).repeat_interleave(32, 2)})
+    out = head(Q)
+    out["aux_outputs"] = [head(Q) for _ in range(2)]
+    dn = head(groups * max_num)
+    dn["aux_outputs"] = [head(groups * max_num) for _ in range(2)]
+    dn["dn_args"] = {"pad_size": groups * max_num, "max_num": max_num}
+    out["dn_out"] = dn
+    crit = SetCriterion(K, matcher=HungarianMatcher(2.0, 5.0, 5.0, 12544, device_indices=True), weight_dict={},
+                        eos_coef=0.1, losses=["labels", "masks"], num_points=12544, oversample_ratio=3.0,
+                        importance_sample_ratio=0.75).cuda().train(True)
+    losses = crit(out, targets)
+    assert len(losses) == 18 and all(torch.isfinite(v) for v in losses.values())
+    sum(v for k, v in losses.items() if "mask" in k or "dice" in k).backward()
+    rows = out["pred_masks"].grad.abs().flatten(2).sum(-1) > 0
+    assert rows.sum(1).tolist() == counts
+    dn_rows = dn["pred_masks"].grad.abs().flatten(2).sum(-1) > 0
+    assert dn_rows.sum(1).tolist() == [groups * n for n in counts]
+    for b, n in enumerate(counts):                                 # group g's query g*max_num + j <- target j
+        expect = sorted(gq * max_num + j for gq in range(groups) for j in range(n))
+        assert dn_rows[b].nonzero().flatten().tolist() == expect
