@@ -354,6 +354,11 @@ def run_ours(a):
             t_hbm = r["bytes"] / (hbm * 1e9)
             t_tensor = 3.0 * r["flops"] / (tens * 1e12)
             common = {"kernel": f"{kind} ({what})", "traffic": None,
+                      "traffic_note": "a mix of shapes is timed here, so there is no single per-launch DRAM figure; "
+                                      "single-shape ncu --set full captures (dram read+write per launch): encoder "
+                                      "FFN1 1.70 GB (profiles/r1o_ncu_gemm_ffn1.txt), 3x3 convolution forward 2.11 GB "
+                                      "(profiles/r1x_ncu_conv_fwd.txt), TN weight gradient 1.80 GB "
+                                      "(profiles/r1o_ncu_gemm_tn.txt)",
                       "note": "fp32 operands, bf16x3 split arithmetic: 3 MMAs per product (tensor ceiling = peak/3 in "
                               "algorithmic flops); bound = the ceiling with the larger ideal time for the timed launches",
                       "tensor_TFLOPs_algorithmic": tf, "tensor_frac_algorithmic": tf / tens,
@@ -385,6 +390,11 @@ def run_ours(a):
                     "algorithmic_bytes_per_launch": alg, "avg_launch_ms": fwd_ms,
                     "launches_timed": len(prof["fwd_ms"]),
                     "share_of_step": fwd_ms * len(prof["fwd_ms"]) / n_prof / step_ms}
+            if B == 16 and a.height == 1024 and a.width == 1024:
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch at exactly this geometry, from the
+                # committed `ncu --set full` capture (a bench run cannot profile itself)
+                msda["traffic"] = 749.512192e6 + 334.541312e6
+                msda["traffic_source"] = "profiles/r1x_ncu_msda_enc_fwd.txt"
             if bwd_ms:
                 alg_b = (4 * (S * Mh * D * 2 + 3 * S * Mh * L * P) + 4 * (S * Mh * D + 3 * S * Mh * L * P)) * B
                 msda["backward"] = {"kernel": "msda_enc_bwd_kernel<8> (+ grad_value memset)", "avg_launch_ms": bwd_ms,

@@ -17,6 +17,8 @@ from .pixel_decoder import (MSDeformAttnPixelDecoder, MSDeformAttnTransformerEnc
                             ShapeSpec)
 from .masked_decoder import (MultiScaleMaskedTransformerDecoder,  # noqa: E402,F401
                              MultiScaleMaskedTransformerDecoderMaskDN)
+from .matcher import HungarianMatcher  # noqa: E402,F401
+from .criterion import SetCriterion  # noqa: E402,F401
 from .registry import (SEM_SEG_HEADS_REGISTRY, TRANSFORMER_DECODER_REGISTRY,  # noqa: E402,F401
                        build_pixel_decoder, build_transformer_decoder)
 
@@ -24,6 +26,7 @@ __all__ = [
     "MultiScaleDeformableAttention", "MSDeformAttn", "MSDeformAttnFunction", "PositionEmbeddingSine",
     "MSDeformAttnPixelDecoder", "MSDeformAttnTransformerEncoderOnly", "ShapeSpec",
     "MultiScaleMaskedTransformerDecoder", "MultiScaleMaskedTransformerDecoderMaskDN",
+    "HungarianMatcher", "SetCriterion",
     "SEM_SEG_HEADS_REGISTRY", "TRANSFORMER_DECODER_REGISTRY", "build_pixel_decoder",
     "build_transformer_decoder",
 ]

@@ -78,9 +78,10 @@ def dn_indices(targets, dn_args, device):
 
 def set_criterion(outputs, targets, *, num_classes, eos_coef, losses, num_points, oversample_ratio,
                   importance_sample_ratio, cost_class, cost_mask, cost_dice, training=True, dn_no_lb=False,
-                  world_size=1, matcher=None):
+                  world_size=1, global_num_masks=None, matcher=None):
     """``SetCriterion.forward`` (criterion.py:214-308).  ``matcher(outputs, targets) -> [(i, j)]`` defaults to the
-    matcher oracle with the given cost weights."""
+    matcher oracle with the given cost weights.  ``global_num_masks`` / ``world_size``: the all-reduced target count of a
+    data-parallel run (this restatement does not communicate)."""
     dev = outputs["pred_masks"].device
     if matcher is None:
         def matcher(o, t):
@@ -100,7 +101,9 @@ def set_criterion(outputs, targets, *, num_classes, eos_coef, losses, num_points
                 raise AssertionError(f"do you really want to compute {name} loss?")
         return d
 
-    num_masks = max(float(sum(len(t["labels"]) for t in targets)) / world_size, 1.0)
+    # criterion.py:228-240: the number of targets is summed over the ranks (all_reduce) and divided by the world size
+    total = float(sum(len(t["labels"]) for t in targets)) if global_num_masks is None else float(global_num_masks)
+    num_masks = max(total / world_size, 1.0)
     dn_out = outputs.get("dn_out")
     main = {k: v for k, v in outputs.items() if k not in ("aux_outputs", "dn_out")}
     out = all_losses(main, matcher(main, targets), num_masks)
