@@ -42,13 +42,18 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every launch eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--criterion", action="store_true",
+                    help="BASELINE config 3: SetCriterion + HungarianMatcher (device path, 12544 points, deep "
+                         "supervision + dn losses) instead of the linear pseudo-loss; not the default workload")
     return ap.parse_args()
 
 
 def workload_name(a):
     return (f"R50 feature maps {a.height}x{a.width} -> MSDeformAttnPixelDecoder(6 layers) + "
             f"MultiScaleMaskedTransformerDecoderMaskDN(9 layers, {a.queries} queries, "
-            f"{'DN points' if not a.no_dn else 'no DN'}), fwd+bwd, linear pseudo-loss")
+            f"{'DN points' if not a.no_dn else 'no DN'}), fwd+bwd, "
+            + ("SetCriterion + HungarianMatcher on the device (12544 points, 10 heads + dn)"
+               if getattr(a, "criterion", False) else "linear pseudo-loss"))
 
 
 def pseudo_loss(out):
@@ -208,6 +213,16 @@ def run_ours(a):
         dn_args = {"tgt": workload.synthetic_targets(B, a.height, a.width, seed=rank, device=dev),
                    "scalar": 1, "noise_scale": 0.0}
 
+    loss_of = pseudo_loss
+    if a.criterion:
+        targets = dn_args["tgt"] if dn_args is not None else workload.synthetic_targets(
+            B, a.height, a.width, seed=rank, device=dev)
+        criterion, weighted_sum = workload.build_criterion(device=dev)
+        criterion.train(True)
+
+        def loss_of(out):
+            return weighted_sum(criterion(out, targets))
+
     # Gradient all-reduce (the path's only collective): one flat NCCL all-reduce of the head's
     # gradients (~20 M parameters) after the backward, averaged over ranks like DistributedDataParallel.
     def allreduce_grads():
@@ -216,7 +231,7 @@ def run_ours(a):
     def eager_step(f):
         for p in params:
             p.grad = None
-        loss = pseudo_loss(head(f, dn_args))
+        loss = loss_of(head(f, dn_args))
         loss.backward()
         allreduce_grads()
         return loss
@@ -230,7 +245,7 @@ def run_ours(a):
     gs, graph_note = None, "disabled (--no-graph)"
     if not a.no_graph:
         try:
-            gs = graphs.GraphedStep(lambda inp: pseudo_loss(head(inp, dn_args)), feats, params, warmup=1)
+            gs = graphs.GraphedStep(lambda inp: loss_of(head(inp, dn_args)), feats, params, warmup=1)
             graph_note = "forward+loss+backward captured once, replayed per step"
         except Exception as e:  # noqa: BLE001
             gs, graph_note = None, f"capture failed, eager stepping: {type(e).__name__}: {str(e)[:160]}"

@@ -72,3 +72,31 @@ def synthetic_targets(batch, height=1024, width=1024, num_classes=80, seed=0, de
         boxes = torch.stack([cx / width, cy / height, 2 * rx / width, 2 * ry / height], -1)
         out.append({"labels": labels.to(device), "masks": masks.to(device), "boxes": boxes.to(device)})
     return out
+
+
+def build_criterion(num_classes=80, dec_layers=10, class_weight=2.0, mask_weight=5.0, dice_weight=5.0,
+                    no_object_weight=0.1, num_points=12544, oversample_ratio=3.0, importance_sample_ratio=0.75,
+                    device="cuda", device_indices=True):
+    """The criterion of the COCO-instance recipe as ``MaskFormer.from_config`` assembles it (ref
+    maskformer_model.py:105-146: weights 2 / 5 / 5, eos 0.1, 12544 points, oversampling 3, importance ratio 0.75,
+    deep supervision over ``dec_layers - 1`` auxiliary layers, dn losses weighted like the matching ones), on the
+    device matcher.  Returns (criterion, weighted_sum) with ``weighted_sum(losses)`` the scalar the trainer
+    back-propagates (maskformer_model.py:225-231)."""
+    from .criterion import SetCriterion
+    from .matcher import HungarianMatcher
+    matcher = HungarianMatcher(cost_class=class_weight, cost_mask=mask_weight, cost_dice=dice_weight,
+                               num_points=num_points, device_indices=device_indices)
+    weight_dict = {"loss_ce": class_weight, "loss_mask": mask_weight, "loss_dice": dice_weight}
+    weight_dict.update({k + "_dn": v for k, v in list(weight_dict.items())})
+    aux = {}
+    for i in range(dec_layers - 1):
+        aux.update({k + f"_{i}": v for k, v in weight_dict.items()})
+    weight_dict.update(aux)
+    crit = SetCriterion(num_classes, matcher=matcher, weight_dict=weight_dict, eos_coef=no_object_weight,
+                        losses=["labels", "masks"], num_points=num_points, oversample_ratio=oversample_ratio,
+                        importance_sample_ratio=importance_sample_ratio).to(device)
+
+    def weighted_sum(losses):
+        return sum(v * weight_dict[k] for k, v in losses.items() if k in weight_dict)
+
+    return crit, weighted_sum
