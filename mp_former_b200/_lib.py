@@ -78,6 +78,8 @@ SIGNATURES = {
     "mpf_lsap_f32": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp]),
     "mpf_point_sample_rows": (_c_int, [_c_vp, _c_int, _c_int, _c_int, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
     "mpf_point_sample_rows_bwd_f32": (_c_int, [_c_vp, _c_int, _c_int, _c_vp, _c_int, _c_int, _c_vp, _c_vp]),
+    "mpf_instance_masks_blocks": (_c_int, [_c_int, _c_int]),
+    "mpf_instance_masks_f32": (_c_int, [_c_vp, _c_ll, _c_int, _c_int, _c_vp] + [_c_int] * 7 + [_c_vp, _c_int, _c_vp, _c_vp]),
 }
 
 _lib = None

@@ -1,0 +1,65 @@
+"""Inference epilogue of the mask-classification model on the device: what the reference's
+``MaskFormer.forward`` does after the head in eval mode (mask2former/maskformer_model.py:232-279, :300-304, :365-401).
+
+``instance_inference`` takes the decoder's LOW-RESOLUTION mask logits: the resize to the padded input size, the crop
+and resize of detectron2's ``sem_seg_postprocess``, the gather of the top-k queries, the ``> 0`` threshold and the
+foreground-probability score are one kernel (``native.instance_masks``) that writes each binary mask once -- the
+reference materialises Q full-resolution fp32 maps per image (420 MB at 100 queries, 1024 x 1024) and re-reads them
+four times.  ``semantic_inference`` is the reference's arithmetic on library ops (resize, softmax, einsum).
+Panoptic inference (:306-363) is a host-side loop over segments with per-segment ``.item()`` reads; it stays with the
+stock model (out of this path).
+
+A maintainer's patch in the reference: in ``MaskFormer.forward`` drop the ``F.interpolate`` at :237-242 and call
+``instance_inference(mask_cls_result, low_res_mask_result, images.tensor.shape[-2:], image_size, (height, width),
+num_classes, test_topk_per_image)`` in place of :274-276."""
+import torch
+import torch.nn.functional as F
+
+from . import native
+
+
+class InstanceResult(dict):
+    """What the reference stores in a detectron2 ``Instances`` (:389-400): ``pred_masks`` [k, H, W], ``scores`` [k],
+    ``pred_classes`` [k], ``pred_boxes`` (zeros [k, 4], as in the reference, :392) and ``image_size``; attribute access
+    like ``Instances``."""
+
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError:
+            raise AttributeError(name) from None
+
+
+@torch.no_grad()
+def instance_inference(mask_cls, mask_pred, padded_size, image_size, out_size, num_classes, topk, thing_ids=None,
+                       mask_dtype=torch.float32):
+    """mask_cls [Q, K+1], mask_pred [Q, h, w] low-resolution logits of one image -> InstanceResult.
+    ``mask_dtype=torch.float32`` reproduces the reference's 0/1 float masks (:391); ``torch.uint8`` writes a quarter of
+    the bytes."""
+    scores = F.softmax(mask_cls.float(), dim=-1)[:, :-1]
+    k = min(int(topk), scores.numel())
+    s, idx = scores.flatten(0, 1).topk(k, sorted=False)
+    labels = idx % num_classes                      # == arange(K).repeat(Q)[idx]   (:370-373)
+    query = idx // num_classes
+    if thing_ids is not None:                       # panoptic models keep the "thing" classes only (:381-388)
+        keep = torch.isin(labels, torch.as_tensor(sorted(thing_ids), device=labels.device))
+        s, labels, query = s[keep], labels[keep], query[keep]
+    masks, sums = native.instance_masks(mask_pred.float(), query, padded_size, image_size, out_size, mask_dtype)
+    mask_scores = sums[:, 0] / (sums[:, 1] + 1e-6)  # average foreground probability (:397)
+    return InstanceResult(image_size=tuple(int(v) for v in out_size), pred_masks=masks, scores=s * mask_scores,
+                          pred_classes=labels, pred_boxes=torch.zeros(masks.shape[0], 4, device=masks.device))
+
+
+@torch.no_grad()
+def semantic_inference(mask_cls, mask_pred, padded_size, image_size, out_size, postprocess_before_inference=True):
+    """mask_cls [Q, K+1], mask_pred [Q, h, w] -> sem_seg [K, out_h, out_w]   (:236-243, :256-267, :300-304)."""
+    up = F.interpolate(mask_pred.float()[None], size=tuple(padded_size), mode="bilinear", align_corners=False)[0]
+
+    def post(x):
+        x = x[:, :image_size[0], :image_size[1]]
+        return F.interpolate(x[None], size=tuple(out_size), mode="bilinear", align_corners=False)[0]
+
+    cls = F.softmax(mask_cls.float(), dim=-1)[..., :-1]
+    if postprocess_before_inference:
+        return torch.einsum("qc,qhw->chw", cls, post(up).sigmoid())
+    return post(torch.einsum("qc,qhw->chw", cls, up.sigmoid()))

@@ -905,3 +905,36 @@ def point_sample_rows_bwd(grad_map_ptrs, hw, coords, grad_out):
         rc = _lib.load().mpf_point_sample_rows_bwd_f32(grad_map_ptrs.data_ptr(), int(hw[0]), int(hw[1]),
                                                        coords.data_ptr(), R, P, grad_out.data_ptr(), _stream())
     _lib.check(rc, "point_sample_rows_bwd")
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Instance-segmentation epilogue (ref mask2former/maskformer_model.py:236-260, 365-401)
+# ----------------------------------------------------------------------------------------------------------------
+def instance_masks(mask_logits, query_index, padded_size, image_size, out_size, mask_dtype=torch.uint8):
+    """mask_logits [Q, h, w] f32 (one image), query_index int64 [R] -> (masks [R, oh, ow] uint8 | float32 of 0/1,
+    sums [R, 2] = (sum of sigmoid over the foreground, foreground pixel count)).  Both bilinear resizes of the
+    reference (to the padded input size; after the crop to ``image_size``, to ``out_size``) are evaluated on the fly."""
+    _lib.require_cuda(mask_logits, "mask_logits")
+    _lib.require_cuda(query_index, "query_index")
+    if mask_logits.dtype != torch.float32 or mask_logits.dim() != 3 or query_index.dtype != torch.int64:
+        raise RuntimeError("instance_masks: mask_logits float32 [Q, h, w] and query_index int64 [R] expected")
+    if mask_dtype not in (torch.uint8, torch.float32):
+        raise RuntimeError("instance_masks: mask_dtype must be torch.uint8 or torch.float32")
+    Q, h, w = mask_logits.shape
+    if mask_logits.stride(-1) != 1 or mask_logits.stride(-2) != w:
+        mask_logits = mask_logits.contiguous()
+    R = int(query_index.numel())
+    oh, ow = int(out_size[0]), int(out_size[1])
+    lib = _lib.load()
+    blocks = int(lib.mpf_instance_masks_blocks(oh, ow))
+    if blocks <= 0:
+        raise RuntimeError("instance_masks: bad output size")
+    masks = torch.empty((R, oh, ow), dtype=mask_dtype, device=mask_logits.device)
+    partial = torch.empty((R, blocks, 2), dtype=torch.float32, device=mask_logits.device)
+    with torch.cuda.device(mask_logits.device):
+        rc = lib.mpf_instance_masks_f32(mask_logits.data_ptr(), mask_logits.stride(0), h, w, query_index.data_ptr(), R,
+                                        int(padded_size[0]), int(padded_size[1]), int(image_size[0]),
+                                        int(image_size[1]), oh, ow, masks.data_ptr(),
+                                        int(mask_dtype == torch.float32), partial.data_ptr(), _stream())
+    _lib.check(rc, "instance_masks")
+    return masks, partial.sum(1)

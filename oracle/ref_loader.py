@@ -237,6 +237,70 @@ def load_criterion():
     return importlib.import_module("mask2former.modeling.criterion")
 
 
+class _Instances:
+    """detectron2.structures.Instances stand-in: an attribute bag with the image size."""
+
+    def __init__(self, image_size, **kwargs):
+        self._image_size = tuple(image_size)
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+
+    @property
+    def image_size(self):
+        return self._image_size
+
+
+class _Boxes:
+    def __init__(self, tensor):
+        self.tensor = tensor
+
+
+class _ImageList:
+    """detectron2.structures.ImageList stand-in (published behaviour of ``from_tensors``): images are zero-padded at
+    the bottom/right to the largest height/width of the batch, rounded up to ``size_divisibility``."""
+
+    def __init__(self, tensor, image_sizes):
+        self.tensor, self.image_sizes = tensor, image_sizes
+
+    @staticmethod
+    def from_tensors(tensors, size_divisibility=0, pad_value=0.0):
+        sizes = [tuple(t.shape[-2:]) for t in tensors]
+        H, W = max(s[0] for s in sizes), max(s[1] for s in sizes)
+        if size_divisibility > 1:
+            H = (H + size_divisibility - 1) // size_divisibility * size_divisibility
+            W = (W + size_divisibility - 1) // size_divisibility * size_divisibility
+        out = tensors[0].new_full((len(tensors), tensors[0].shape[0], H, W), pad_value)
+        for i, t in enumerate(tensors):
+            out[i, :, :t.shape[-2], :t.shape[-1]] = t
+        return _ImageList(out, sizes)
+
+
+def _sem_seg_postprocess(result, img_size, output_height, output_width):
+    """detectron2.modeling.postprocessing.sem_seg_postprocess (published): crop the padding away, then resize to the
+    requested output resolution (bilinear, align_corners=False)."""
+    import torch.nn.functional as F
+    result = result[:, : img_size[0], : img_size[1]].expand(1, -1, -1, -1)
+    return F.interpolate(result, size=(output_height, output_width), mode="bilinear", align_corners=False)[0]
+
+
+def load_meta_arch():
+    """The reference's ``MaskFormer`` meta-architecture (mask2former/maskformer_model.py), imported unmodified, for
+    golden vectors of its inference epilogue (:232-279, :300-401).  Detectron2 stand-ins: Instances / Boxes /
+    ImageList / sem_seg_postprocess above; registries, ``retry_if_cuda_oom`` (identity) and builders (unused)."""
+    load_criterion()
+    reg = _Registry("META_ARCH")
+    dm = sys.modules["detectron2.modeling"]
+    dm.META_ARCH_REGISTRY = reg
+    dm.build_backbone = dm.build_sem_seg_head = lambda *a, **k: None
+    _mod("detectron2.data", MetadataCatalog=types.SimpleNamespace(get=lambda name: None))
+    _mod("detectron2.modeling.backbone", Backbone=nn.Module)
+    _mod("detectron2.modeling.postprocessing", sem_seg_postprocess=_sem_seg_postprocess)
+    _mod("detectron2.structures", Boxes=_Boxes, ImageList=_ImageList, Instances=_Instances, BitMasks=object)
+    _mod("detectron2.utils.memory", retry_if_cuda_oom=lambda f: f)
+    _pkg("mask2former.util", os.path.join(REFERENCE_ROOT, "mask2former", "util"))
+    return importlib.import_module("mask2former.maskformer_model")
+
+
 class cuda_is_identity:
     """Context manager: the reference's DN preparation hard-codes ``.cuda()`` / ``.to('cuda')``
     (reference mask2former_transformer_decoder.py:984-985,1029,1052).  To run it on CPU for golden

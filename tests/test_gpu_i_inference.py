@@ -1,0 +1,79 @@
+"""GPU parity of the instance-segmentation epilogue kernel (csrc/inference.cu, mp_former_b200/inference.py; SURVEY.md
+§8f rank 3) against the oracle (oracle/inference_oracle.py) and the golden outputs of the unmodified reference
+MaskFormer.forward (tests/golden/inference.pt).
+
+NOTE: this kernel was written after round 1's GPU budget was spent.  Its host logic and its resampling formula are
+pinned on the CPU (tests/test_inference_cpu.py); these tests have not run on a B200 yet and are therefore marked
+xfail(strict=False) -- they report XPASS once the kernel is confirmed and the marker is to be removed then.
+Tolerances: masks may differ from the CPU reference only where |logit| is within fp32 rounding of 0 (< 1e-4 of the
+pixels); scores 1e-4 relative."""
+import os
+import sys
+
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+sys.path.insert(0, HERE)
+from make_golden_inference import CFG, IMAGES, inputs  # noqa: E402
+from oracle import inference_oracle as IO  # noqa: E402
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="kernel written after the round-1 GPU budget was spent; "
+                                                     "first B200 run pending (CPU-pinned formula and host logic)")]
+
+
+@pytest.mark.parametrize("geom", [((16, 24), (64, 96), (64, 96), (64, 96)), ((16, 24), (64, 96), (50, 70), (75, 105)),
+                                  ((64, 64), (256, 256), (200, 256), (480, 613)), ((7, 9), (28, 36), (28, 33), (11, 17))])
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.float32])
+def test_instance_masks_kernel_equals_interpolate_chain(geom, dtype):
+    from mp_former_b200 import native
+    (h, w), padded, image, out = geom
+    g = torch.Generator().manual_seed(h + w)
+    full_q = torch.randn(11, h, w, generator=g) * 3
+    rows = torch.tensor([10, 0, 3, 3, 7])
+    ref = IO.full_resolution_masks(full_q, padded, image, out)[rows]
+    masks, sums = native.instance_masks(full_q.cuda(), rows.cuda(), padded, image, out, dtype)
+    assert masks.dtype == dtype and masks.shape == ref.shape
+    fg = ref > 0
+    assert ((masks.cpu() != 0) != fg).float().mean() < 1e-4
+    ref_sums = torch.stack([(ref.sigmoid() * fg).flatten(1).sum(1), fg.flatten(1).sum(1).float()], 1)
+    assert torch.allclose(sums.cpu(), ref_sums, rtol=1e-4, atol=1e-2)
+    again = native.instance_masks(full_q.cuda(), rows.cuda(), padded, image, out, dtype)
+    assert torch.equal(again[0], masks) and torch.equal(again[1], sums)         # deterministic (no atomics)
+
+
+def test_instance_inference_equals_reference_golden():
+    from mp_former_b200 import inference
+    from test_inference_cpu import _check_instances, _geometry
+    G = torch.load(os.path.join(HERE, "golden", "inference.pt"), weights_only=False)
+    outputs, _ = inputs()
+    for b in range(len(IMAGES)):
+        padded, image, out = _geometry(b)
+        r = inference.instance_inference(outputs["pred_logits"][b].cuda(), outputs["pred_masks"][b].cuda(), padded,
+                                         image, out, CFG["num_classes"], CFG["topk"])
+        _check_instances({k: r[k].cpu() for k in ("pred_masks", "scores", "pred_classes")}, G["instance"][b])
+
+
+def test_instance_inference_bench_geometry():
+    """100 queries, 256x256 logits -> 1024x1024 masks, top-100 of 100 x 80 class scores, strided query slice."""
+    from mp_former_b200 import inference
+    g = torch.Generator().manual_seed(12)
+    cls = torch.randn(100, 81, generator=g) * 2
+    logits = torch.randn(109, 256, 256, generator=g) * 3
+    r = inference.instance_inference(cls.cuda(), logits.cuda()[9:], (1024, 1024), (1024, 1024), (1024, 1024), 80, 100,
+                                     mask_dtype=torch.uint8)
+    full = IO.full_resolution_masks(logits[9:], (1024, 1024), (1024, 1024), (1024, 1024))
+    ref = IO.instance_inference(cls, full, 80, 100)
+    key = (lambda c, s: torch.argsort(c.double() * 10 + s.double()))
+    o, ro = key(r.pred_classes.cpu(), r.scores.cpu()), key(ref["pred_classes"], ref["scores"])
+    assert torch.equal(r.pred_classes.cpu()[o], ref["pred_classes"][ro])
+    assert torch.allclose(r.scores.cpu()[o], ref["scores"][ro], rtol=1e-4, atol=1e-6)
+    assert ((r.pred_masks.cpu()[o] != 0) != ref["pred_masks"][ro]).float().mean() < 1e-4
+
+
+def test_instance_masks_rejects_cpu_tensors():
+    from mp_former_b200 import native
+    with pytest.raises(RuntimeError):
+        native.instance_masks(torch.zeros(2, 4, 4), torch.zeros(1, dtype=torch.int64), (16, 16), (16, 16), (16, 16))

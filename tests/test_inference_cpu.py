@@ -1,0 +1,115 @@
+"""CPU: inference epilogue.
+  * the oracle (oracle/inference_oracle.py) against the outputs of the UNMODIFIED reference MaskFormer.forward in eval
+    mode (tests/golden/inference.pt);
+  * the host logic of mp_former_b200/inference.py against the same golden, with the one kernel it calls
+    (native.instance_masks) replaced -- in this test only -- by a torch emulation;
+  * the on-the-fly two-stage resampling formula the kernel implements (csrc/inference.cu: ATen's source index / weight
+    arithmetic, applied twice with a crop in between) against torch's F.interpolate chain."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+from make_golden_inference import CFG, IMAGES, inputs  # noqa: E402
+from oracle import inference_oracle as IO  # noqa: E402
+
+
+def _geometry(b):
+    d = CFG["size_divisibility"]
+    Hp = max((s[0] + d - 1) // d * d for s, _ in IMAGES)
+    Wp = max((s[1] + d - 1) // d * d for s, _ in IMAGES)
+    return (Hp, Wp), IMAGES[b][0], IMAGES[b][1]
+
+
+def _canon(res):
+    """rows in a canonical order (top-k is unsorted): by class, then score."""
+    key = res["pred_classes"].double() * 10 + res["scores"].double()
+    o = torch.argsort(key)
+    return res["pred_masks"][o], res["scores"][o], res["pred_classes"][o]
+
+
+def _check_instances(got, ref):
+    gm, gs, gc = _canon(got)
+    rm, rs, rc = _canon(ref)
+    assert torch.equal(gc, rc)
+    assert torch.allclose(gs, rs, rtol=1e-5, atol=1e-7)
+    assert torch.equal(gm.bool(), rm.bool())
+
+
+def test_inference_oracle_matches_reference_golden():
+    G = torch.load(os.path.join(HERE, "golden", "inference.pt"), weights_only=False)
+    outputs, _ = inputs()
+    for b in range(len(IMAGES)):
+        padded, image, out = _geometry(b)
+        full = IO.full_resolution_masks(outputs["pred_masks"][b], padded, image, out)
+        _check_instances(IO.instance_inference(outputs["pred_logits"][b], full, CFG["num_classes"], CFG["topk"]),
+                         G["instance"][b])
+        assert tuple(G["instance"][b]["image_size"]) == tuple(out)
+        assert torch.allclose(IO.semantic_inference(outputs["pred_logits"][b], full), G["semantic"][b]["sem_seg"],
+                              atol=1e-5)
+
+
+def _emu_instance_masks(mask_logits, query_index, padded_size, image_size, out_size, mask_dtype=torch.uint8):
+    full = IO.full_resolution_masks(mask_logits, padded_size, image_size, out_size)[query_index]
+    fg = full > 0
+    sums = torch.stack([(full.sigmoid() * fg).flatten(1).sum(1), fg.flatten(1).sum(1).float()], 1)
+    return fg.to(mask_dtype), sums
+
+
+def test_inference_host_logic_matches_reference_golden(monkeypatch):
+    from mp_former_b200 import inference, native
+    monkeypatch.setattr(native, "instance_masks", _emu_instance_masks)
+    G = torch.load(os.path.join(HERE, "golden", "inference.pt"), weights_only=False)
+    outputs, _ = inputs()
+    for b in range(len(IMAGES)):
+        padded, image, out = _geometry(b)
+        r = inference.instance_inference(outputs["pred_logits"][b], outputs["pred_masks"][b], padded, image, out,
+                                         CFG["num_classes"], CFG["topk"])
+        assert r.pred_masks.dtype == torch.float32 and r.image_size == tuple(out) and r.pred_boxes.shape == (CFG["topk"], 4)
+        _check_instances(r, G["instance"][b])
+        for before, name in ((True, "semantic"), (False, "semantic_after")):
+            s = inference.semantic_inference(outputs["pred_logits"][b], outputs["pred_masks"][b], padded, image, out,
+                                             postprocess_before_inference=before)
+            assert torch.allclose(s, G[name][b]["sem_seg"], atol=1e-5), name
+    # "thing" filter of panoptic models
+    r = inference.instance_inference(outputs["pred_logits"][0], outputs["pred_masks"][0], *_geometry(0),
+                                     CFG["num_classes"], CFG["topk"], thing_ids={0, 2, 3})
+    assert set(r.pred_classes.tolist()) <= {0, 2, 3} and r.pred_masks.shape[0] == r.scores.shape[0] <= CFG["topk"]
+    with pytest.raises(AttributeError):
+        r.no_such_field
+
+
+def _src(scale, n_out, n_in):
+    s = torch.tensor(scale, dtype=torch.float32) * (torch.arange(n_out, dtype=torch.float32) + 0.5) - 0.5
+    s = s.clamp(min=0)
+    i0 = s.to(torch.int64).clamp(max=n_in - 1)
+    i1 = i0 + (i0 < n_in - 1).to(torch.int64)
+    return i0, i1, s - i0.float()
+
+
+def _resize(x, n_out_h, n_out_w):
+    """ATen's upsample_bilinear2d(align_corners=False) arithmetic as csrc/inference.cu evaluates it."""
+    h, w = x.shape[-2:]
+    y0, y1, ly = _src(float(torch.tensor(h, dtype=torch.float32) / n_out_h), n_out_h, h)
+    x0, x1, lx = _src(float(torch.tensor(w, dtype=torch.float32) / n_out_w), n_out_w, w)
+    hy, hx = (1 - ly)[:, None], (1 - lx)[None, :]
+    ly, lx = ly[:, None], lx[None, :]
+    top = hx * x[..., y0[:, None], x0[None, :]] + lx * x[..., y0[:, None], x1[None, :]]
+    bot = hx * x[..., y1[:, None], x0[None, :]] + lx * x[..., y1[:, None], x1[None, :]]
+    return hy * top + ly * bot
+
+
+@pytest.mark.parametrize("geom", [((16, 24), (64, 96), (64, 96), (64, 96)), ((16, 24), (64, 96), (50, 70), (75, 105)),
+                                  ((64, 64), (256, 256), (200, 256), (480, 613)), ((7, 9), (28, 36), (28, 33), (11, 17))])
+def test_two_stage_resampling_formula_equals_interpolate_chain(geom):
+    (h, w), padded, image, out = geom
+    g = torch.Generator().manual_seed(h * w)
+    L = torch.randn(3, h, w, generator=g) * 3
+    ref = IO.full_resolution_masks(L, padded, image, out)
+    got = _resize(_resize(L, *padded)[:, :image[0], :image[1]], *out)
+    assert torch.allclose(got, ref, rtol=2e-6, atol=1e-5)      # a few fp32 ulps (values up to ~10)
+    assert ((got > 0) != (ref > 0)).float().mean() < 1e-4
