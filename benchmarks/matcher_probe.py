@@ -54,7 +54,8 @@ def main():
         targets.append({"labels": torch.randint(0, K, (n,), device=DEV, generator=g),
                         "masks": m.repeat_interleave(32, 1).repeat_interleave(32, 2)})
     coords = torch.rand(B, P, 2, device=DEV, generator=g)
-    m = HungarianMatcher(2.0, 5.0, 5.0, num_points=P, device_indices=True)
+    sort_points = os.environ.get("MPF_SORT_POINTS", "0") == "1"
+    m = HungarianMatcher(2.0, 5.0, 5.0, num_points=P, device_indices=True, sort_points=sort_points)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
     for _ in range(3):
         m.match_device(outputs, targets, point_coords=coords)
@@ -87,7 +88,7 @@ def main():
     print(json.dumps({"probe": "hungarian_matcher_one_head", "B": B, "Q": Q, "points": P, "targets_total": ntot,
                       "device_ms": ours_ms, "stock_torch_scipy_ms_wall": stock_ms, "speedup": stock_ms / ours_ms,
                       "same_assignment_as_stock": bool(same), "gather_sector_GBps": sector_bytes / ours_ms / 1e6,
-                      "host_syncs": {"device": 0, "stock": B}}))
+                      "host_syncs": {"device": 0, "stock": B}, "sort_points": sort_points}))
 
 
 if __name__ == "__main__":

@@ -37,3 +37,23 @@ def test_point_sample_is_bilinear_at_unit_square_coordinates():
     pts = torch.stack(torch.meshgrid(xs, ys, indexing="xy"), -1).reshape(1, -1, 2)
     got = MO.point_sample(m, pts).view(3, 4)
     assert torch.allclose(got, m[0, 0], atol=1e-6)
+
+
+def test_row_major_point_order_is_a_permutation_and_leaves_costs_unchanged():
+    """HungarianMatcher(sort_points=True) only reorders an image's points; the cost sums (hence the assignment) do not
+    depend on the order beyond fp32 rounding."""
+    from mp_former_b200.matcher import HungarianMatcher
+    outputs, targets = inputs()
+    g = torch.Generator().manual_seed(2)
+    coords = torch.rand(3, 500, 2, generator=g)
+    H, W = outputs["pred_masks"].shape[-2:]
+    srt = HungarianMatcher.row_major_order(coords, H, W)
+    key = (srt[..., 1] * H).floor() * W + (srt[..., 0] * W).floor()
+    assert bool((key[:, 1:] >= key[:, :-1]).all())
+    for b in range(3):
+        assert torch.equal(srt[b][srt[b][:, 0].argsort(stable=True)], coords[b][coords[b][:, 0].argsort(stable=True)])
+        a = MO.matching_cost(outputs["pred_logits"][b], outputs["pred_masks"][b], targets[b]["labels"],
+                             targets[b]["masks"], coords[b:b + 1], 2.0, 5.0, 5.0)
+        c = MO.matching_cost(outputs["pred_logits"][b], outputs["pred_masks"][b], targets[b]["labels"],
+                             targets[b]["masks"], srt[b:b + 1], 2.0, 5.0, 5.0)
+        assert torch.allclose(a, c, rtol=1e-5, atol=1e-5)
