@@ -6,8 +6,8 @@ and resize of detectron2's ``sem_seg_postprocess``, the gather of the top-k quer
 foreground-probability score are one kernel (``native.instance_masks``) that writes each binary mask once -- the
 reference materialises Q full-resolution fp32 maps per image (420 MB at 100 queries, 1024 x 1024) and re-reads them
 four times.  ``semantic_inference`` is the reference's arithmetic on library ops (resize, softmax, einsum).
-Panoptic inference (:306-363) is a host-side loop over segments with per-segment ``.item()`` reads; it stays with the
-stock model (out of this path).
+``panoptic_inference`` (:306-363) computes the per-query pixel counts the reference reads back one ``.item()`` at a
+time with two bincounts and a row sum, and synchronises once.
 
 A maintainer's patch in the reference: in ``MaskFormer.forward`` drop the ``F.interpolate`` at :237-242 and call
 ``instance_inference(mask_cls_result, low_res_mask_result, images.tensor.shape[-2:], image_size, (height, width),
@@ -63,3 +63,50 @@ def semantic_inference(mask_cls, mask_pred, padded_size, image_size, out_size, p
     if postprocess_before_inference:
         return torch.einsum("qc,qhw->chw", cls, post(up).sigmoid())
     return post(torch.einsum("qc,qhw->chw", cls, up.sigmoid()))
+
+
+@torch.no_grad()
+def panoptic_inference(mask_cls, mask_pred, num_classes, thing_ids, object_mask_threshold, overlap_threshold):
+    """mask_cls [Q, K+1], mask_pred [Q, H, W] full-resolution logits -> (panoptic_seg int32 [H, W], segments_info)
+    (ref maskformer_model.py:306-363).
+
+    The reference walks the kept queries one by one and reads three pixel counts per query back to the host
+    (``.item()`` at :331-336: up to 3 Q stream synchronisations per image).  Here the three counts of every kept query
+    come from two ``bincount``s and one row sum, ONE device->host copy brings (class, counts) of all kept queries, the
+    sequential part that is inherently host-side -- segment numbering with the merge of same-class "stuff" segments,
+    and ``segments_info``, a list of Python dicts -- runs on those few numbers, and one lookup-table gather paints the
+    segment ids."""
+    scores, labels = F.softmax(mask_cls.float(), dim=-1).max(-1)
+    keep = labels.ne(num_classes) & (scores > object_mask_threshold)
+    H, W = mask_pred.shape[-2:]
+    seg = torch.zeros((H, W), dtype=torch.int32, device=mask_pred.device)
+    kept = keep.nonzero().flatten()                 # (data-dependent size: the reference's boolean indexing, :311-315)
+    n = int(kept.numel())
+    if n == 0:
+        return seg, []
+    prob = mask_pred.float()[kept].sigmoid()
+    ids = (scores[kept].view(-1, 1, 1) * prob).argmax(0)                       # :326
+    fg = prob >= 0.5
+    sel = fg.gather(0, ids[None])[0]                                           # pixel claimed by its arg-max mask
+    flat = ids.flatten()
+    area = torch.bincount(flat, minlength=n)                                   # (ids == k).sum()            :331
+    inter = torch.bincount(flat[sel.flatten()], minlength=n)                   # ((ids == k) & fg_k).sum()   :335
+    original = fg.flatten(1).sum(1)                                            # (mask_k >= 0.5).sum()       :332
+    host = torch.stack([labels[kept], area, original, inter]).cpu().tolist()   # the one synchronisation
+    thing_ids = set(int(t) for t in thing_ids)
+    lut, info, stuff, current = [0] * n, [], {}, 0
+    for k, (c, a, o, i) in enumerate(zip(*host)):
+        if not (a > 0 and o > 0 and i > 0) or a / o < overlap_threshold:
+            continue
+        isthing = c in thing_ids
+        if not isthing:
+            if c in stuff:                          # merge stuff regions of one class (:341-344)
+                lut[k] = stuff[c]
+                continue
+            stuff[c] = current + 1
+        current += 1
+        lut[k] = current
+        info.append({"id": current, "isthing": bool(isthing), "category_id": int(c)})
+    lut_t = torch.tensor(lut, dtype=torch.int32, device=seg.device)
+    seg = torch.where(sel, lut_t[ids], seg)
+    return seg, info

@@ -35,3 +35,35 @@ def instance_inference(mask_cls, mask_pred_full, num_classes, topk, thing_ids=No
     fg = (m > 0).float()
     mask_scores = (m.sigmoid().flatten(1) * fg.flatten(1)).sum(1) / (fg.flatten(1).sum(1) + 1e-6)
     return {"pred_masks": fg.bool(), "scores": s * mask_scores, "pred_classes": labels, "query": query}
+
+
+def panoptic_inference(mask_cls, mask_pred_full, num_classes, thing_ids, object_mask_threshold, overlap_threshold):
+    """-> (panoptic_seg int32 [H, W], segments_info)   (:306-363, segment by segment like the reference)."""
+    scores, labels = F.softmax(mask_cls, dim=-1).max(-1)
+    prob = mask_pred_full.sigmoid()
+    keep = labels.ne(num_classes) & (scores > object_mask_threshold)
+    cur_scores, cur_classes, cur_masks = scores[keep], labels[keep], prob[keep]
+    seg = torch.zeros(prob.shape[-2:], dtype=torch.int32, device=prob.device)
+    info = []
+    if cur_masks.shape[0] == 0:
+        return seg, info
+    ids = (cur_scores.view(-1, 1, 1) * cur_masks).argmax(0)
+    stuff, current = {}, 0
+    for k in range(cur_classes.shape[0]):
+        c = int(cur_classes[k])
+        isthing = c in thing_ids
+        area = int((ids == k).sum())
+        original = int((cur_masks[k] >= 0.5).sum())
+        m = (ids == k) & (cur_masks[k] >= 0.5)
+        if area > 0 and original > 0 and int(m.sum()) > 0:
+            if area / original < overlap_threshold:
+                continue
+            if not isthing:
+                if c in stuff:
+                    seg[m] = stuff[c]
+                    continue
+                stuff[c] = current + 1
+            current += 1
+            seg[m] = current
+            info.append({"id": current, "isthing": bool(isthing), "category_id": c})
+    return seg, info

@@ -75,6 +75,11 @@ def test_inference_host_logic_matches_reference_golden(monkeypatch):
             s = inference.semantic_inference(outputs["pred_logits"][b], outputs["pred_masks"][b], padded, image, out,
                                              postprocess_before_inference=before)
             assert torch.allclose(s, G[name][b]["sem_seg"], atol=1e-5), name
+    for b in range(len(IMAGES)):                 # instances of a panoptic model: "thing" classes only (:381-388)
+        padded, image, out = _geometry(b)
+        r = inference.instance_inference(outputs["pred_logits"][b], outputs["pred_masks"][b], padded, image, out,
+                                         CFG["num_classes"], CFG["topk"], thing_ids=set(CFG["thing_ids"]))
+        _check_instances(r, G["panoptic"][b])
     # "thing" filter of panoptic models
     r = inference.instance_inference(outputs["pred_logits"][0], outputs["pred_masks"][0], *_geometry(0),
                                      CFG["num_classes"], CFG["topk"], thing_ids={0, 2, 3})
@@ -113,3 +118,26 @@ def test_two_stage_resampling_formula_equals_interpolate_chain(geom):
     got = _resize(_resize(L, *padded)[:, :image[0], :image[1]], *out)
     assert torch.allclose(got, ref, rtol=2e-6, atol=1e-5)      # a few fp32 ulps (values up to ~10)
     assert ((got > 0) != (ref > 0)).float().mean() < 1e-4
+
+
+@pytest.mark.parametrize("case", ["panoptic", "panoptic_structured"])
+def test_panoptic_inference_matches_reference_golden(case):
+    """Oracle (segment by segment) and the product's batched formulation (three counts per kept query from two
+    bincounts and a row sum, one host read) against the unmodified reference; library ops only, so it runs here."""
+    from make_golden_inference import panoptic_inputs
+    from mp_former_b200 import inference
+    G = torch.load(os.path.join(HERE, "golden", "inference.pt"), weights_only=False)
+    outputs, _ = panoptic_inputs() if case == "panoptic_structured" else inputs()
+    args = (CFG["num_classes"], set(CFG["thing_ids"]), CFG["object_mask_threshold"], CFG["overlap_threshold"])
+    n_seg = 0
+    for b in range(len(IMAGES)):
+        padded, image, out = _geometry(b)
+        full = IO.full_resolution_masks(outputs["pred_masks"][b], padded, image, out)
+        for fn in (IO.panoptic_inference, inference.panoptic_inference):
+            seg, info = fn(outputs["pred_logits"][b], full, *args)
+            assert info == G[case][b]["segments_info"], fn.__module__
+            assert seg.dtype == torch.int32 and torch.equal(seg, G[case][b]["panoptic_seg"]), fn.__module__
+        n_seg += len(info)
+    assert n_seg >= (5 if case == "panoptic_structured" else 1)
+    seg, info = inference.panoptic_inference(outputs["pred_logits"][0], full, CFG["num_classes"], set(), 2.0, 0.5)
+    assert info == [] and int(seg.abs().sum()) == 0                              # nothing above the score threshold
