@@ -14,38 +14,14 @@
 // per row as per-block partials (summed by the caller in a fixed order: deterministic, no atomics).
 // Bound: HBM write of the masks (topk * oh * ow bytes); one thread per output pixel, 16 cached gathers each.
 #include "mpf_common.cuh"
+#include "inference_math.cuh"
 
 namespace mpf {
 
-__device__ __forceinline__ void bilinear_src(float scale, int dst, int in_size, int& i0, int& i1, float& l1) {
-  float s = scale * (static_cast<float>(dst) + 0.5f) - 0.5f;
-  s = s < 0.f ? 0.f : s;
-  i0 = static_cast<int>(s);
-  if (i0 > in_size - 1) i0 = in_size - 1;
-  i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
-  l1 = s - static_cast<float>(i0);
-}
-
-// value of the stage-1 map (h x w logits -> Hp x Wp) at (y, x); products and sums separately rounded like ATen
-__device__ __forceinline__ float stage1_at(const float* __restrict__ L, int h, int w, float sh, float sw, int y, int x) {
-  int y0, y1, x0, x1;
-  float ly, lx;
-  bilinear_src(sh, y, h, y0, y1, ly);
-  bilinear_src(sw, x, w, x0, x1, lx);
-  const float hy = 1.f - ly, hx = 1.f - lx;
-  const float p00 = __ldg(L + y0 * w + x0), p01 = __ldg(L + y0 * w + x1);
-  const float p10 = __ldg(L + y1 * w + x0), p11 = __ldg(L + y1 * w + x1);
-  const float top = __fadd_rn(__fmul_rn(hx, p00), __fmul_rn(lx, p01));
-  const float bot = __fadd_rn(__fmul_rn(hx, p10), __fmul_rn(lx, p11));
-  return __fadd_rn(__fmul_rn(hy, top), __fmul_rn(ly, bot));
-}
-
 template <typename TO>
 __global__ void __launch_bounds__(256)
-instance_masks_kernel(const float* __restrict__ logits, long long q_stride, int h, int w,
-                      const long long* __restrict__ query_index, int Hp, int Wp, int ih, int iw, int oh, int ow,
-                      float s1h, float s1w, float s2h, float s2w, int identity2, TO* __restrict__ out,
-                      float* __restrict__ partial) {
+instance_masks_kernel(const float* __restrict__ logits, long long q_stride, const long long* __restrict__ query_index,
+                      const TwoStage ts, int oh, int ow, TO* __restrict__ out, float* __restrict__ partial) {
   const int r = blockIdx.y;
   const long long npix = static_cast<long long>(oh) * ow;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -53,21 +29,7 @@ instance_masks_kernel(const float* __restrict__ logits, long long q_stride, int 
   float fg = 0.f, prob = 0.f;
   if (idx < npix) {
     const int y = static_cast<int>(idx / ow), x = static_cast<int>(idx - static_cast<long long>(y) * ow);
-    float v;
-    if (identity2) {                 // output resolution == image size: the second resize is the identity
-      v = stage1_at(L, h, w, s1h, s1w, y, x);
-    } else {
-      int y0, y1, x0, x1;
-      float ly, lx;
-      bilinear_src(s2h, y, ih, y0, y1, ly);
-      bilinear_src(s2w, x, iw, x0, x1, lx);
-      const float hy = 1.f - ly, hx = 1.f - lx;
-      const float u00 = stage1_at(L, h, w, s1h, s1w, y0, x0), u01 = stage1_at(L, h, w, s1h, s1w, y0, x1);
-      const float u10 = stage1_at(L, h, w, s1h, s1w, y1, x0), u11 = stage1_at(L, h, w, s1h, s1w, y1, x1);
-      const float top = __fadd_rn(__fmul_rn(hx, u00), __fmul_rn(lx, u01));
-      const float bot = __fadd_rn(__fmul_rn(hx, u10), __fmul_rn(lx, u11));
-      v = __fadd_rn(__fmul_rn(hy, top), __fmul_rn(ly, bot));
-    }
+    const float v = two_stage_at(L, ts, y, x);
     const bool m = v > 0.f;                                        // maskformer_model.py:391
     out[static_cast<long long>(r) * npix + idx] = static_cast<TO>(m ? 1 : 0);
     if (m) {
@@ -122,23 +84,16 @@ int mpf_instance_masks_f32(const float* mask_logits, long long query_stride, int
   MPF_REQUIRE(rows <= 65535, "instance_masks: more than 65535 rows");
   const int blocks = mpf_instance_masks_blocks(out_h, out_w);
   MPF_REQUIRE(blocks > 0, "instance_masks: output too large");
-  // ATen: scale = (float)input_size / output_size  (area_pixel_compute_scale, align_corners=False)
-  const float s1h = static_cast<float>(h) / static_cast<float>(padded_h);
-  const float s1w = static_cast<float>(w) / static_cast<float>(padded_w);
-  const float s2h = static_cast<float>(image_h) / static_cast<float>(out_h);
-  const float s2w = static_cast<float>(image_w) / static_cast<float>(out_w);
-  const int identity2 = (image_h == out_h && image_w == out_w) ? 1 : 0;
+  const TwoStage ts = make_two_stage(h, w, padded_h, padded_w, image_h, image_w, out_h, out_w);
   const dim3 grid(blocks, rows);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long* qi = reinterpret_cast<const long long*>(query_index);
   if (out_is_f32)
-    instance_masks_kernel<float><<<grid, 256, 0, st>>>(mask_logits, query_stride, h, w, qi, padded_h, padded_w, image_h,
-                                                       image_w, out_h, out_w, s1h, s1w, s2h, s2w, identity2,
+    instance_masks_kernel<float><<<grid, 256, 0, st>>>(mask_logits, query_stride, qi, ts, out_h, out_w,
                                                        static_cast<float*>(out_masks), partial);
   else
-    instance_masks_kernel<uint8_t><<<grid, 256, 0, st>>>(mask_logits, query_stride, h, w, qi, padded_h, padded_w,
-                                                         image_h, image_w, out_h, out_w, s1h, s1w, s2h, s2w,
-                                                         identity2, static_cast<uint8_t*>(out_masks), partial);
+    instance_masks_kernel<uint8_t><<<grid, 256, 0, st>>>(mask_logits, query_stride, qi, ts, out_h, out_w,
+                                                         static_cast<uint8_t*>(out_masks), partial);
   count_launch();
   return finish_launch("instance_masks");
 }

@@ -141,3 +141,49 @@ def test_panoptic_inference_matches_reference_golden(case):
     assert n_seg >= (5 if case == "panoptic_structured" else 1)
     seg, info = inference.panoptic_inference(outputs["pred_logits"][0], full, CFG["num_classes"], set(), 2.0, 0.5)
     assert info == [] and int(seg.abs().sum()) == 0                              # nothing above the score threshold
+
+
+def _host_kernel_lib(tmp_path_factory=None):
+    """g++ build of tests/host_emul/inference_host.cpp: the kernel's own per-pixel header compiled for the host."""
+    import ctypes
+    import subprocess
+    root = os.path.dirname(HERE)
+    out_dir = os.path.join(root, "build", "host_emul")
+    os.makedirs(out_dir, exist_ok=True)
+    lib = os.path.join(out_dir, "libinference_host.so")
+    src = os.path.join(HERE, "host_emul", "inference_host.cpp")
+    hdr = os.path.join(root, "mp_former_b200", "csrc", "inference_math.cuh")
+    if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-D__host__=", "-D__device__=",
+                               "-D__forceinline__=inline", "-o", lib, src])
+    return ctypes.CDLL(lib)
+
+
+@pytest.mark.parametrize("geom", [((16, 24), (64, 96), (64, 96), (64, 96)), ((16, 24), (64, 96), (50, 70), (75, 105)),
+                                  ((64, 64), (256, 256), (200, 256), (480, 613)), ((7, 9), (28, 36), (28, 33), (11, 17)),
+                                  ((32, 32), (128, 128), (128, 128), (64, 64))])
+def test_kernel_pixel_arithmetic_on_host_equals_interpolate_chain(geom):
+    """The header the CUDA kernel includes (inference_math.cuh), compiled for the host: values within a few ulps of
+    torch's two interpolates with the crop in between, identical masks except where |logit| ~ 0, same score sums;
+    rows address a strided query slice through query_index like the kernel."""
+    import ctypes
+    lib = _host_kernel_lib()
+    (h, w), padded, image, out = geom
+    g = torch.Generator().manual_seed(h * 7 + w)
+    store = torch.randn(9, h * w + 5, generator=g) * 3              # q_stride > h*w
+    logits = store[:, :h * w].reshape(9, h, w)
+    rows = torch.tensor([8, 0, 3, 3, 5], dtype=torch.int64)
+    R, (oh, ow) = len(rows), out
+    masks = torch.zeros(R, oh, ow, dtype=torch.uint8)
+    values = torch.zeros(R, oh, ow)
+    sums = torch.zeros(R, 2, dtype=torch.float64)
+    vp = ctypes.c_void_p
+    lib.host_instance_masks(vp(store.data_ptr()), ctypes.c_longlong(store.stride(0)), h, w, vp(rows.data_ptr()), R,
+                            padded[0], padded[1], image[0], image[1], oh, ow, vp(masks.data_ptr()),
+                            vp(values.data_ptr()), vp(sums.data_ptr()))
+    ref = IO.full_resolution_masks(logits, padded, image, out)[rows]
+    assert torch.allclose(values, ref, rtol=2e-6, atol=1e-5)
+    fg = ref > 0
+    assert ((masks != 0) != fg).float().mean() < 1e-4
+    ref_sums = torch.stack([(ref.double().sigmoid() * fg).flatten(1).sum(1), fg.flatten(1).sum(1).double()], 1)
+    assert torch.allclose(sums, ref_sums, rtol=1e-4, atol=1e-2)
