@@ -20,7 +20,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import native
-from .matcher import PackedTargets
+from .matcher import PackedTargets, targets_key
 
 
 def _world_size():
@@ -99,8 +99,7 @@ class SetCriterion(nn.Module):
             return self._dn[key]
 
     def _step_state(self, targets, device):
-        key = tuple((t["masks"].data_ptr(), tuple(t["masks"].shape), t["masks"].dtype, t["labels"].data_ptr())
-                    for t in targets)
+        key = targets_key(targets)
         if key != self._step_key:
             packed = self.matcher.pack_targets(targets, device) if hasattr(self.matcher, "pack_targets") else None
             self._step = SetCriterion._Step(targets, device, packed)
@@ -180,7 +179,7 @@ class SetCriterion(nn.Module):
         "pred_masks", "aux_outputs", "dn_args": {"pad_size", "max_num"}}}; targets: list of {"labels", "masks"}
         (ref criterion.py:214-308).  Returns the dict of unweighted losses."""
         main = {k: v for k, v in outputs.items() if k != "aux_outputs" and k != "dn_out"}
-        dn_out = outputs["dn_out"]
+        dn_out = outputs.get("dn_out")
         dev = main["pred_masks"].device
         step = self._step_state(targets, dev)
         num_masks = float(step.total)

@@ -13,6 +13,13 @@ from torch import nn
 from . import _lib, native
 
 
+def targets_key(targets):
+    """Identity of a step's targets for the per-step caches: storage addresses, shapes, dtypes and the tensors'
+    in-place modification counters (the caches hold the tensors, so an address cannot be recycled under them)."""
+    return tuple((t["masks"].data_ptr(), tuple(t["masks"].shape), t["masks"].dtype, t["masks"]._version,
+                  t["labels"].data_ptr(), t["labels"]._version) for t in targets)
+
+
 class PackedTargets:
     """The per-step, head-independent half of the matcher's inputs: label vector, per-image offsets and the device
     table of mask pointers.  Built once per step and reused by the ten prediction heads' matchings."""
@@ -35,9 +42,11 @@ class PackedTargets:
         if len(kinds) > 1:
             masks = [m.to(torch.float32) for m in masks]
         self.masks = masks                          # keeps the storage behind the pointer table alive
+        self._mask_refs = [t["masks"] for t in targets]
         self.is_f32 = bool(masks) and masks[0].dtype == torch.float32
         self.counts = [int(m.shape[0]) for m in masks]
         self.sizes = [tuple(m.shape[-2:]) for m in masks]
+        self._label_refs = [t["labels"] for t in targets]      # pinned for the cache key's sake
         labels = [t["labels"].to(device=device, dtype=torch.int64) for t in targets]
         for lab, n in zip(labels, self.counts):
             if lab.numel() != n:
@@ -88,8 +97,7 @@ class HungarianMatcher(nn.Module):
 
     # -- inputs shared by the heads of one step -------------------------------------------------------------------
     def pack_targets(self, targets, device):
-        key = tuple((t["masks"].data_ptr(), tuple(t["masks"].shape), t["masks"].dtype, t["labels"].data_ptr())
-                    for t in targets)
+        key = targets_key(targets)
         if key != self._packed_key:
             self._packed = PackedTargets(targets, device)
             self._packed_key = key

@@ -868,6 +868,8 @@ class PointSampleRows(torch.autograd.Function):
         H, W = maps.shape[-2:]
         if maps.stride(-1) != 1 or maps.stride(-2) != W:
             raise RuntimeError("PointSampleRows: every H x W map must be contiguous")
+        if row_index.dtype != torch.int64 or row_index.dim() != 1 or row_index.device != maps.device:
+            raise RuntimeError("PointSampleRows: row_index must be an int64 vector on the maps' device")
         lead = maps.shape[:-2]
         # element offset of every map: flat index -> multi-index over the leading dims -> strides
         offs = torch.zeros_like(row_index)
