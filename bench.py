@@ -97,6 +97,37 @@ def cpu_port_step_fn(a):
     return fn, "1 image (same shapes/config) fwd+bwd per step through oracle/torch_oracle.py on host cores"
 
 
+def cpu_msda_baseline(a, reps=5):
+    """The reference's CPU MSDeformAttn path (``ms_deform_attn_core_pytorch``, ref ops/functions/ms_deform_attn_func.py:
+    52-72, restated in oracle/torch_oracle.py::msda_core_grid_sample) on the host cores: ONE image, one encoder layer's
+    call (S = Lq = all pixels of the three levels, M=8, D=32, L=3, P=4), 2 warm-up + ``reps`` timed calls (~2-4 s).
+    Reported next to the GPU kernel's number in `roofline_msda` (north_star: "next to the reference's CPU MSDeformAttn
+    path timed on the same box's host cores (core count stated) in the same run")."""
+    import torch
+    from oracle import torch_oracle as O
+    torch.set_num_threads(min(32, os.cpu_count() or 1))
+    shapes = [(a.height // s, a.width // s) for s in (8, 16, 32)]
+    S = sum(h * w for h, w in shapes)
+    M_, D, L, P = 8, 32, 3, 4
+    g = torch.Generator().manual_seed(3)
+    value = torch.rand(1, S, M_, D, generator=g) * 0.01                      # distributions of ref ops/test.py:36-39
+    loc = torch.rand(1, S, M_, L, P, 2, generator=g)
+    aw = torch.rand(1, S, M_, L, P, generator=g) + 1e-5
+    aw = aw / aw.sum(-1, keepdim=True).sum(-2, keepdim=True)
+    with torch.no_grad():
+        for _ in range(2):
+            O.msda_core_grid_sample(value, shapes, loc, aw)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            O.msda_core_grid_sample(value, shapes, loc, aw)
+        ms = (time.perf_counter() - t0) * 1e3 / reps
+    alg = 4 * (S * M_ * D + 2 * S * M_ * L * P + S * M_ * L * P + S * M_ * D)   # SURVEY.md §8d, per image and layer
+    return {"kernel": "ms_deform_attn_core_pytorch (reference CPU path, per-level F.grid_sample), forward",
+            "ms_per_image_per_layer": ms, "achieved": alg / (ms / 1e3) / 1e9, "unit": "GB/s (algorithmic bytes)",
+            "algorithmic_bytes": alg, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"1 image, S=Lq={S}, L=3, M=8, D=32, P=4, {reps} calls"}
+
+
 def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -433,6 +464,13 @@ def run_ours(a):
             dt = time.perf_counter() - t0
             cpu = {"value": n / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                    "sample": sample + f" ({n} steps, {dt:.1f}s)"}
+            if msda is not None:
+                try:
+                    msda["cpu_reference"] = cpu_msda_baseline(a)
+                    msda["cpu_reference"]["speedup_vs_cpu_per_image"] = (
+                        msda["cpu_reference"]["ms_per_image_per_layer"] / (msda["avg_launch_ms"] / B))
+                except Exception as e:  # noqa: BLE001  (a reporting extra must not cost the bench line)
+                    msda["cpu_reference"] = {"error": f"{type(e).__name__}: {str(e)[:120]}"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,

@@ -65,6 +65,28 @@ def msda_core(value, spatial_shapes, sampling_locations, attention_weights):
 # --------------------------------------------------------------------------------------------
 # a8: sine position embedding
 # --------------------------------------------------------------------------------------------
+def msda_core_grid_sample(value, spatial_shapes, sampling_locations, attention_weights):
+    """The reference's own CPU path, as it computes it (ref ops/functions/ms_deform_attn_func.py:52-72): per level one
+    ``F.grid_sample`` (bilinear, zeros padding, align_corners=False) of the level's [N*M, D, H, W] view at the grid
+    ``2 * loc - 1``, then the weighted sum over levels and points.  Same result as :func:`msda_core` (which restates
+    the CUDA kernel) up to fp32 rounding; kept separately because it is the arithmetic whose SPEED on the host cores
+    bench.py reports as the reference's CPU MSDeformAttn baseline."""
+    N, S, M, D = value.shape
+    _, Lq, _, L, P, _ = sampling_locations.shape
+    shapes = [(int(h), int(w)) for h, w in (spatial_shapes.tolist() if torch.is_tensor(spatial_shapes)
+                                             else spatial_shapes)]
+    grids = 2 * sampling_locations - 1
+    sampled, start = [], 0
+    for l, (H, W) in enumerate(shapes):
+        v = value[:, start:start + H * W].flatten(2).transpose(1, 2).reshape(N * M, D, H, W)
+        start += H * W
+        g = grids[:, :, :, l].transpose(1, 2).flatten(0, 1)                     # [N*M, Lq, P, 2]
+        sampled.append(F.grid_sample(v, g, mode="bilinear", padding_mode="zeros", align_corners=False))
+    w = attention_weights.transpose(1, 2).reshape(N * M, 1, Lq, L * P)
+    out = (torch.stack(sampled, dim=-2).flatten(-2) * w).sum(-1).view(N, M * D, Lq)
+    return out.transpose(1, 2).contiguous()
+
+
 def position_embedding_sine(B, H, W, num_pos_feats=128, temperature=10000, scale=2 * math.pi, device=None,
                             dtype=torch.float32):
     """ref: transformer_decoder/position_encoding.py:29-52 with mask=None, normalize=True."""
