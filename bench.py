@@ -52,7 +52,7 @@ def workload_name(a):
     return (f"R50 feature maps {a.height}x{a.width} -> MSDeformAttnPixelDecoder(6 layers) + "
             f"MultiScaleMaskedTransformerDecoderMaskDN(9 layers, {a.queries} queries, "
             f"{'DN points' if not a.no_dn else 'no DN'}), fwd+bwd, "
-            + ("SetCriterion + HungarianMatcher on the device (12544 points, 10 heads + dn)"
+            + ("SetCriterion + HungarianMatcher (recipe weights, 12544 points, 10 heads + dn)"
                if getattr(a, "criterion", False) else "linear pseudo-loss"))
 
 
@@ -84,10 +84,21 @@ def cpu_port_step_fn(a):
     dn = None if a.no_dn else {"tgt": workload.synthetic_targets(1, a.height, a.width), "scalar": 1,
                                "noise_scale": 0.0}
 
+    loss_of = pseudo_loss
+    if getattr(a, "criterion", False):       # same workload as the GPU arm's --criterion: the recipe's SetCriterion
+        from oracle import criterion_oracle as CO
+        targets = dn["tgt"] if dn is not None else workload.synthetic_targets(1, a.height, a.width)
+        _, weighted_sum = workload.build_criterion(device="cpu")
+
+        def loss_of(out):
+            return weighted_sum(CO.set_criterion(out, targets, num_classes=80, eos_coef=0.1, losses=["labels", "masks"],
+                                                 num_points=12544, oversample_ratio=3.0, importance_sample_ratio=0.75,
+                                                 cost_class=2.0, cost_mask=5.0, cost_dice=5.0, training=True))
+
     def fn():
         mf, _, ms = O.pixel_decoder_forward(psd, feats)
         out = O.decoder_forward(dsd, ms, mf, num_queries=a.queries, dn_args=dn, dn_label_noise_ratio=0.2)
-        loss = pseudo_loss(out)
+        loss = loss_of(out)
         loss.backward()
         for sd in (psd, dsd):
             for v in sd.values():
