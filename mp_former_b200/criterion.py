@@ -62,6 +62,9 @@ class SetCriterion(nn.Module):
                 offs.append(offs[-1] + n)
             self.offsets = torch.tensor(offs[:-1], dtype=torch.int64, device=device)
             self.total = offs[-1]
+            # device copy of the local target count, made once per step-state: the all-reduce below then needs no
+            # host->device upload per forward (and the forward stays CUDA-graph capturable)
+            self.total_dev = torch.tensor([float(self.total)], dtype=torch.float, device=device)
             if self.packed.uniform():
                 self.masks = self.packed.masks
             else:       # zero-padded to the largest map, top-left aligned (utils/misc.py:48-73); rare: the model pads
@@ -185,7 +188,7 @@ class SetCriterion(nn.Module):
         num_masks = float(step.total)
         ws = _world_size()
         if ws > 1:       # average number of masks across ranks, kept on the device (no .item() sync)
-            nm = torch.tensor([num_masks], dtype=torch.float, device=dev)
+            nm = step.total_dev.clone()
             dist.all_reduce(nm)
             num_masks = torch.clamp(nm / ws, min=1)[0]
         else:
