@@ -38,3 +38,15 @@ def test_lsap_oracle_empty_and_invalid():
         L.solve(np.array([[np.nan, 1.0]]))
     with pytest.raises(ValueError):
         L.solve(np.array([[np.inf, np.inf], [1.0, 2.0]]))
+
+
+def test_lsap_oracle_fuzz_small_integer_matrices():
+    """400 random small matrices with few distinct values (many optima): both selection rules return scipy's pairs."""
+    rng = np.random.default_rng(123)
+    for _ in range(400):
+        r, c = int(rng.integers(1, 9)), int(rng.integers(1, 9))
+        C = rng.integers(0, int(rng.integers(1, 4)) + 1, (r, c)).astype(np.float64)
+        ri, ci = linear_sum_assignment(C)
+        for rule in (False, True):
+            oi, oj = L.solve(C, parallel_rule=rule)
+            assert np.array_equal(ri, oi) and np.array_equal(ci, oj), (C, rule)
