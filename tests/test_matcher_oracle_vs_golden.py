@@ -48,7 +48,7 @@ def test_row_major_point_order_is_a_permutation_and_leaves_costs_unchanged():
     coords = torch.rand(3, 500, 2, generator=g)
     H, W = outputs["pred_masks"].shape[-2:]
     srt = HungarianMatcher.row_major_order(coords, H, W)
-    key = (srt[..., 1] * H).floor() * W + (srt[..., 0] * W).floor()
+    key = (srt[..., 1] * H - 0.5).floor().clamp(0, H - 1) * W + (srt[..., 0] * W - 0.5).floor().clamp(0, W - 1)
     assert bool((key[:, 1:] >= key[:, :-1]).all())
     for b in range(3):
         assert torch.equal(srt[b][srt[b][:, 0].argsort(stable=True)], coords[b][coords[b][:, 0].argsort(stable=True)])
