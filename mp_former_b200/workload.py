@@ -78,7 +78,7 @@ def build_criterion(num_classes=80, dec_layers=10, class_weight=2.0, mask_weight
                     no_object_weight=0.1, num_points=12544, oversample_ratio=3.0, importance_sample_ratio=0.75,
                     device="cuda", device_indices=True):
     """The criterion of the COCO-instance recipe as ``MaskFormer.from_config`` assembles it (ref
-    maskformer_model.py:105-146: weights 2 / 5 / 5, eos 0.1, 12544 points, oversampling 3, importance ratio 0.75,
+    maskformer_model.py:105-147: weights 2 / 5 / 5, eos 0.1, 12544 points, oversampling 3, importance ratio 0.75,
     deep supervision over ``dec_layers - 1`` auxiliary layers, dn losses weighted like the matching ones), on the
     device matcher.  Returns (criterion, weighted_sum) with ``weighted_sum(losses)`` the scalar the trainer
     back-propagates (maskformer_model.py:225-231)."""

@@ -41,7 +41,7 @@ def test_decoder_outputs_through_criterion_and_back(monkeypatch):
     assert out["dn_out"] is not None and out["dn_out"]["dn_args"]["pad_size"] > 0
     K, L = cases.DEC_CFG["num_classes"], cases.DEC_CFG["dec_layers"]
 
-    # the recipe's weight dict (maskformer_model.py:117-126), built by the bench helper, on a CPU-capable matcher
+    # the recipe's weight dict (maskformer_model.py:123-132), built by the bench helper, on a CPU-capable matcher
     crit_dev, weighted_sum = workload.build_criterion(num_classes=K, dec_layers=L + 1, num_points=PTS, device="cpu")
     crit = SetCriterion(K, matcher=_Matcher(), weight_dict=crit_dev.weight_dict, eos_coef=0.1,
                         losses=["labels", "masks"], num_points=PTS, oversample_ratio=3.0,
