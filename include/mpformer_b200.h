@@ -363,7 +363,7 @@ int mpf_point_sample_rows_bwd_f32(float* const* grad_map_ptrs, int H, int W, con
 
 /* ---------------------------------------------------------------------------------------------
  * Instance-segmentation epilogue.
- * ref: mask2former/maskformer_model.py:236-243 (F.interpolate of pred_masks to the padded image size), :256-260 +
+ * ref: mask2former/maskformer_model.py:239-244 (F.interpolate of pred_masks to the padded image size), :257-259 +
  *      detectron2 sem_seg_postprocess (crop to the image, resize to the output resolution), :365-401
  *      (instance_inference: top-k queries' maps, `> 0`, average foreground probability).
  * For row r and output pixel (y, x):  v = resize2(crop(resize1(mask_logits[query_index[r]])))[y, x]  with both
@@ -371,7 +371,7 @@ int mpf_point_sample_rows_bwd_f32(float* const* grad_map_ptrs, int H, int W, con
  *     out_masks[r, y, x] = v > 0   (uint8, or float32 0/1 with out_is_f32 != 0)
  *     partial[r, k, 0] = sum over block k's pixels of sigmoid(v) * [v > 0];   partial[r, k, 1] = sum of [v > 0]
  * with k < mpf_instance_masks_blocks(out_h, out_w); the caller adds the blocks (fixed order: deterministic) and forms
- * the mask score  sum0 / (sum1 + 1e-6)  (:397).
+ * the mask score  sum0 / (sum1 + 1e-6)  (:398).
  *   mask_logits [Q, h, w] of ONE image through query_stride (each map contiguous); query_index int64 [rows]
  * ------------------------------------------------------------------------------------------- */
 int mpf_instance_masks_blocks(int out_h, int out_w);

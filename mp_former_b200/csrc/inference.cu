@@ -1,7 +1,7 @@
 // Instance-segmentation epilogue: mask logits -> full-resolution binary masks + mask scores.
 //
-//   ref: mask2former/maskformer_model.py:236-243 (F.interpolate of pred_masks to the padded image size, bilinear,
-//        align_corners=False), :256-260 + detectron2 sem_seg_postprocess (crop to the image, bilinear resize to the
+//   ref: mask2former/maskformer_model.py:239-244 (F.interpolate of pred_masks to the padded image size, bilinear,
+//        align_corners=False), :257-259 + detectron2 sem_seg_postprocess (crop to the image, bilinear resize to the
 //        requested output resolution), :365-401 instance_inference (gather of the top-k queries' maps, `> 0`,
 //        average foreground probability).
 //
@@ -30,11 +30,11 @@ instance_masks_kernel(const float* __restrict__ logits, long long q_stride, cons
   if (idx < npix) {
     const int y = static_cast<int>(idx / ow), x = static_cast<int>(idx - static_cast<long long>(y) * ow);
     const float v = two_stage_at(L, ts, y, x);
-    const bool m = v > 0.f;                                        // maskformer_model.py:391
+    const bool m = v > 0.f;                                        // maskformer_model.py:392
     out[static_cast<long long>(r) * npix + idx] = static_cast<TO>(m ? 1 : 0);
     if (m) {
       fg = 1.f;
-      prob = 1.0f / (1.0f + expf(-v));                             // :397 (only foreground pixels contribute)
+      prob = 1.0f / (1.0f + expf(-v));                             // :398 (only foreground pixels contribute)
     }
   }
   // block sums -> partial[r, blockIdx.x, 0..1]

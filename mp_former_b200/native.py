@@ -910,7 +910,7 @@ def point_sample_rows_bwd(grad_map_ptrs, hw, coords, grad_out):
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# Instance-segmentation epilogue (ref mask2former/maskformer_model.py:236-260, 365-401)
+# Instance-segmentation epilogue (ref mask2former/maskformer_model.py:239-260, 365-401)
 # ----------------------------------------------------------------------------------------------------------------
 def instance_masks(mask_logits, query_index, padded_size, image_size, out_size, mask_dtype=torch.uint8):
     """mask_logits [Q, h, w] f32 (one image), query_index int64 [R] -> (masks [R, oh, ow] uint8 | float32 of 0/1,

@@ -2,10 +2,10 @@
 decoder's outputs at test time.  Not used by the product path or by bench.py.
 
 Follows mask2former/maskformer_model.py of the reference:
-  * :236-243  pred_masks resized to the padded input size (bilinear, align_corners=False)
+  * :239-244  pred_masks resized to the padded input size (bilinear, align_corners=False)
   * :247-260  per image: detectron2 ``sem_seg_postprocess`` (crop the padding away, resize to the requested output
               resolution; third-party, restated from its published source in oracle/ref_loader.py)
-  * :300-304  ``semantic_inference``; :365-401 ``instance_inference``
+  * :301-305  ``semantic_inference``; :365-401 ``instance_inference``
 Pinned by ``tests/golden/inference.pt``: the UNMODIFIED ``MaskFormer.forward`` in eval mode around a stand-in backbone /
 head (tests/golden/make_golden_inference.py)."""
 import torch
@@ -13,7 +13,7 @@ import torch.nn.functional as F
 
 
 def full_resolution_masks(mask_pred, padded_size, image_size, out_size):
-    """mask_pred [Q, h, w] -> [Q, out_h, out_w]  (:236-243, :256-259)."""
+    """mask_pred [Q, h, w] -> [Q, out_h, out_w]  (:239-244, :257-259)."""
     up = F.interpolate(mask_pred[None], size=tuple(padded_size), mode="bilinear", align_corners=False)[0]
     up = up[:, :image_size[0], :image_size[1]]
     return F.interpolate(up[None], size=tuple(out_size), mode="bilinear", align_corners=False)[0]
@@ -38,7 +38,7 @@ def instance_inference(mask_cls, mask_pred_full, num_classes, topk, thing_ids=No
 
 
 def panoptic_inference(mask_cls, mask_pred_full, num_classes, thing_ids, object_mask_threshold, overlap_threshold):
-    """-> (panoptic_seg int32 [H, W], segments_info)   (:306-363, segment by segment like the reference)."""
+    """-> (panoptic_seg int32 [H, W], segments_info)   (:307-363, segment by segment like the reference)."""
     scores, labels = F.softmax(mask_cls, dim=-1).max(-1)
     prob = mask_pred_full.sigmoid()
     keep = labels.ne(num_classes) & (scores > object_mask_threshold)

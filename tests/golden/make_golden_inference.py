@@ -1,5 +1,5 @@
 """Generates tests/golden/inference.pt by running the UNMODIFIED reference MaskFormer.forward in eval mode
-(mask2former/maskformer_model.py:232-279 and the *_inference methods :300-401) around a stand-in backbone / head that
+(mask2former/maskformer_model.py:232-279 and the *_inference methods :301-401) around a stand-in backbone / head that
 returns seeded ``pred_logits`` / ``pred_masks`` (authoring container only):
 
     python tests/golden/make_golden_inference.py
@@ -41,8 +41,8 @@ def inputs(seed=41, stride=4):
 
 def panoptic_inputs(seed=43, stride=4):
     """Structured predictions for the panoptic branch: elliptic blobs as mask logits, several queries of the same
-    "stuff" class (merged into one segment, :341-347), overlapping blobs (overlap-threshold rejections, :337-339),
-    no-object and low-confidence queries (:310-311)."""
+    "stuff" class (merged into one segment, :345-350), overlapping blobs (overlap-threshold rejections, :341-342),
+    no-object and low-confidence queries (:311)."""
     g = torch.Generator().manual_seed(seed)
     out, batched = inputs()
     B, Q, K = out["pred_logits"].shape[0], CFG["num_queries"], CFG["num_classes"]
