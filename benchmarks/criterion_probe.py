@@ -37,7 +37,7 @@ def timed(fn, reps=REPS, warm=2):
 
 def stock_loss_masks(pred_masks, targets, b, q, t, num_masks, num_points=12544, k=3.0, beta=0.75):
     """The reference's formulation of SetCriterion.loss_masks with library ops (timing comparator only; ref
-    criterion.py:143-192): gather of the matched prediction maps, float zero-padded copy of every GT mask of the batch,
+    criterion.py:141-191): gather of the matched prediction maps, float zero-padded copy of every GT mask of the batch,
     grid_sample at the candidate points, top-k, two more grid_samples, BCE + dice."""
     src = pred_masks[b, q][:, None]
     nmax = max(len(x["labels"]) for x in targets)

@@ -2,7 +2,7 @@
 12544 points, 1..20 instances per image): CUDA-event time of one head's matching (cost kernels + LSAP kernel, no host
 round trip) next to the reference's formulation run with stock PyTorch ops on the same GPU (per image: two
 grid_samples, the softplus/sigmoid maps, three einsums, the cost matrix copied to the host and scipy's solve --
-mask2former/modeling/matcher.py:97-157), wall-clock timed because it synchronises per image.  One JSON line."""
+mask2former/modeling/matcher.py:96-157), wall-clock timed because it synchronises per image.  One JSON line."""
 import json
 import os
 import statistics

@@ -309,7 +309,7 @@ int mpf_masked_xattn_bwd_f32(const float* q_hi, const float* q_lo, const float* 
 
 /* ---------------------------------------------------------------------------------------------
  * Hungarian matching on the device (the caller right after the prediction heads).
- * ref: mask2former/modeling/matcher.py:97-157 (HungarianMatcher.memory_efficient_forward), :15-30 (batch_dice_loss),
+ * ref: mask2former/modeling/matcher.py:96-157 (HungarianMatcher.memory_efficient_forward), :15-30 (batch_dice_loss),
  *      :38-62 (batch_sigmoid_ce_loss); detectron2 point_sample (F.grid_sample at 2*c-1, bilinear, zeros padding,
  *      align_corners=False); scipy.optimize.linear_sum_assignment (matcher.py:151).
  *
@@ -317,11 +317,11 @@ int mpf_masked_xattn_bwd_f32(const float* q_hi, const float* q_lo, const float* 
  *     cost[Q*off[b] + q*n_b + j] = cost_mask * mean_p BCE(x_qp, t_jp) + cost_class * (-softmax(logits[b,q])[label_j])
  *                                  + cost_dice * (1 - (2 sum_p sig(x_qp) t_jp + 1) / (sum_p sig(x_qp) + sum_p t_jp + 1))
  *   with x_qp / t_jp the bilinear samples of pred_masks[b,q] / target mask j at point_coords[b,p] (one point set per
- *   image shared by all its masks, matcher.py:124-137).  One row-major [Q, n_b] matrix per image, images back to back.
+ *   image shared by all its masks, matcher.py:118-132).  One row-major [Q, n_b] matrix per image, images back to back.
  *     pred_logits   [B, Q, K+1] through (logits_img_stride, logits_q_stride), class dim contiguous
  *     pred_masks    [B, Q, H, W] through (masks_img_stride, masks_q_stride), each H x W map contiguous
  *     tgt_mask_ptrs [B] DEVICE array of device pointers; entry b -> [n_b, Hg, Wg] contiguous, uint8/bool (0/1) or,
- *                   with tgt_is_f32 != 0, float32 (the reference converts with `.to(out_mask)`, matcher.py:117)
+ *                   with tgt_is_f32 != 0, float32 (the reference converts with `.to(out_mask)`, matcher.py:115)
  *     tgt_labels    [total_targets] int64, images back to back;  tgt_offsets [B+1] int32 prefix sums of n_b
  *     point_coords  [B, P, 2] (x, y) in [0, 1], 8-byte aligned
  *     workspace     >= mpf_match_cost_workspace_bytes(...) bytes (per-point-split partial sums; no atomics, so the
@@ -346,10 +346,10 @@ int mpf_lsap_f32(const float* cost, const int32_t* tgt_offsets, int batch, int n
 
 /* ---------------------------------------------------------------------------------------------
  * Point sampling of mask maps for the criterion.
- * ref: mask2former/modeling/criterion.py:143-192 (SetCriterion.loss_masks), detectron2 point_sample
+ * ref: mask2former/modeling/criterion.py:141-191 (SetCriterion.loss_masks), detectron2 point_sample
  *      (F.grid_sample at 2*c-1, bilinear, zeros padding, align_corners=False) and its autograd backward.
  *   mpf_point_sample_rows:         out[r, p] = bilinear(map_r, point_coords[r, p, :])   (neg_abs != 0: -|.|, the
- *                                  uncertainty score of criterion.py:75-89)
+ *                                  uncertainty score of criterion.py:73-87)
  *   mpf_point_sample_rows_bwd_f32: grad_map_r[corner] += w_corner * grad_out[r, p]  (fp32 atomics; the caller zeroes
  *                                  the gradient maps; rows may alias the same map)
  *     map_ptrs      [rows] DEVICE array of device pointers, each to one contiguous H x W map (uint8/bool 0/1, or

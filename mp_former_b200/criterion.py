@@ -1,4 +1,4 @@
-"""Mirror of the reference's ``SetCriterion`` (mask2former/modeling/criterion.py:92-323): same constructor, same
+"""Mirror of the reference's ``SetCriterion`` (mask2former/modeling/criterion.py:90-322): same constructor, same
 ``forward(outputs, targets)`` contract, same loss keys (``loss_ce / loss_mask / loss_dice`` + ``_dn`` + ``_{i}``
 suffixes), same consumption of the random generator -- arranged for the device:
 
@@ -6,9 +6,9 @@ suffixes), same consumption of the random generator -- arranged for the device:
     (``match_device``); any matcher with the reference's ``forward`` contract (list of CPU index pairs) works too;
   * predictions are point-sampled where the prediction heads wrote them and GT masks where the loader put them
     (``native.point_sample_rows`` through device pointer tables): no ``pred_masks[idx]`` gather, no float / zero-padded
-    copy of every GT mask of the batch per loss call (criterion.py:155-157; 1.3 GB at the bench geometry), and the
+    copy of every GT mask of the batch per loss call (criterion.py:152-155; 1.3 GB at the bench geometry), and the
     backward adds straight into a dense mask-logit gradient (``native.PointSampleRows``);
-  * the fixed assignment of the mask-piloted ("dn") queries (criterion.py:246-256) and the batch index vectors are
+  * the fixed assignment of the mask-piloted ("dn") queries (criterion.py:246-257) and the batch index vectors are
     built once per step on the host from the target counts instead of per image with ``.cuda()`` uploads;
   * ``num_masks`` is a host number (single process) or stays a device tensor after the all-reduce (no ``.item()``).
 
@@ -28,7 +28,7 @@ def _world_size():
 
 
 class SetCriterion(nn.Module):
-    """Loss of the mask-classification model (ref criterion.py:92-323): Hungarian assignment between ground truth and
+    """Loss of the mask-classification model (ref criterion.py:90-322): Hungarian assignment between ground truth and
     predictions, then classification and point-sampled mask losses for every matched pair, for the mask-piloted
     queries with their fixed assignment, and for every auxiliary decoder layer."""
 
@@ -125,7 +125,7 @@ class SetCriterion(nn.Module):
 
     # -- the two losses ---------------------------------------------------------------------------------------------
     def loss_labels(self, outputs, step, idx, num_masks):
-        """Classification loss (ref criterion.py:123-141): matched queries take their target's class, all others the
+        """Classification loss (ref criterion.py:123-139): matched queries take their target's class, all others the
         no-object class, which is down-weighted by ``eos_coef``."""
         b, q, t = idx
         logits = outputs["pred_logits"].float()
@@ -134,7 +134,7 @@ class SetCriterion(nn.Module):
         return {"loss_ce": F.cross_entropy(logits.transpose(1, 2), classes, self.empty_weight)}
 
     def loss_masks(self, outputs, step, idx, num_masks):
-        """Point-sampled binary cross-entropy and dice losses of the matched masks (ref criterion.py:143-192) with
+        """Point-sampled binary cross-entropy and dice losses of the matched masks (ref criterion.py:141-191) with
         PointRend's importance sampling of the points (detectron2 get_uncertain_point_coords_with_randomness)."""
         b, q, t = idx
         pm = outputs["pred_masks"].float()
@@ -151,7 +151,7 @@ class SetCriterion(nn.Module):
         with torch.no_grad():
             src_ptrs = pm.data_ptr() + 4 * (b * pm.stride(0) + q * pm.stride(1))
             cand = torch.rand(R, n_over, 2, device=pm.device, dtype=pm.dtype)
-            unc = native.point_sample_rows(src_ptrs, True, (H, W), cand, neg_abs=True)     # -|logit|, :75-89
+            unc = native.point_sample_rows(src_ptrs, True, (H, W), cand, neg_abs=True)     # -|logit|, :73-87
             top = unc.topk(n_unc, dim=1).indices
             coords = torch.gather(cand, 1, top.unsqueeze(-1).expand(-1, -1, 2))
             if n_rand > 0:
@@ -180,7 +180,7 @@ class SetCriterion(nn.Module):
     def forward(self, outputs, targets):
         """outputs: {"pred_logits", "pred_masks", optional "aux_outputs": [...], "dn_out": None | {"pred_logits",
         "pred_masks", "aux_outputs", "dn_args": {"pad_size", "max_num"}}}; targets: list of {"labels", "masks"}
-        (ref criterion.py:214-308).  Returns the dict of unweighted losses."""
+        (ref criterion.py:213-304).  Returns the dict of unweighted losses."""
         main = {k: v for k, v in outputs.items() if k != "aux_outputs" and k != "dn_out"}
         dn_out = outputs.get("dn_out")
         dev = main["pred_masks"].device

@@ -1,6 +1,6 @@
 // Hungarian matching on the device (the step right after the decoder's prediction heads).
 //
-//   ref: mask2former/modeling/matcher.py:97-157 (HungarianMatcher.memory_efficient_forward), :15-62 (the two cost
+//   ref: mask2former/modeling/matcher.py:96-157 (HungarianMatcher.memory_efficient_forward), :15-62 (the two cost
 //        terms), detectron2 point_sample (= F.grid_sample at 2*c-1, bilinear, zeros padding, align_corners=False),
 //        scipy.optimize.linear_sum_assignment (matcher.py:151).
 //
@@ -195,7 +195,7 @@ match_cost_finish_kernel(const float* __restrict__ part3, const float* __restric
   }
   const float c_mask = (sp + sn) / static_cast<float>(P);                 // matcher.py:59-61
   const float c_dice = 1.0f - (2.0f * sd + 1.0f) / (ss + st + 1.0f);      // matcher.py:26-29
-  // class cost: -softmax(logits[b, q])[label]   (matcher.py:107,113)
+  // class cost: -softmax(logits[b, q])[label]   (matcher.py:105,111)
   const float* row = logits + b * logits_img_stride + q * logits_q_stride;
   const long long lab = __ldg(labels + jg);
   float c_class;
@@ -209,7 +209,7 @@ match_cost_finish_kernel(const float* __restrict__ part3, const float* __restric
     c_class = -(expf(__ldg(row + lab) - m) / den);
   }
   cost[static_cast<long long>(Q) * n0 + static_cast<long long>(q) * nb + (jg - n0)] =
-      (w_mask * c_mask + w_class * c_class) + w_dice * c_dice;            // matcher.py:137-141
+      (w_mask * c_mask + w_class * c_class) + w_dice * c_dice;            // matcher.py:142-146
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -1,6 +1,6 @@
 // Point sampling of mask maps for the criterion ("criterion point sampling").
 //
-//   ref: mask2former/modeling/criterion.py:143-192 (SetCriterion.loss_masks: point_sample of the matched prediction
+//   ref: mask2former/modeling/criterion.py:141-191 (SetCriterion.loss_masks: point_sample of the matched prediction
 //        maps at 3 x 12544 candidate points for the uncertainty ranking, then of predictions and GT masks at the
 //        12544 chosen points), detectron2 point_sample (= F.grid_sample at 2*c-1, bilinear, zeros padding,
 //        align_corners=False) and its autograd backward.

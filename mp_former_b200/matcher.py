@@ -1,6 +1,6 @@
 """Device-resident mirror of the reference's ``HungarianMatcher`` (mask2former/modeling/matcher.py:70-189): same
 constructor, same ``forward(outputs, targets)`` contract and result format, same consumption of the global random
-generator (one ``torch.rand(1, num_points, 2)`` per image, in image order, matcher.py:124) -- but the whole batch is
+generator (one ``torch.rand(1, num_points, 2)`` per image, in image order, matcher.py:120) -- but the whole batch is
 matched in three kernel launches (native.match_cost + native.lsap) with ONE device->host copy of the finished index
 pairs, instead of, per image, two grid_samples, three einsums, a cost-matrix copy to the host (a stream sync) and a
 scipy solve.  With ``device_indices=True`` the pairs stay on the device and nothing synchronises at all (the number of
@@ -35,7 +35,7 @@ class PackedTargets:
                 m = m.contiguous().view(torch.uint8)
             elif m.dtype == torch.uint8 or m.dtype == torch.float32:
                 m = m.contiguous()
-            else:                                   # the reference converts with `.to(out_mask)` (matcher.py:117)
+            else:                                   # the reference converts with `.to(out_mask)` (matcher.py:115)
                 m = m.to(torch.float32).contiguous()
             masks.append(m)
         kinds = {m.dtype for m in masks}
@@ -135,11 +135,11 @@ class HungarianMatcher(nn.Module):
         dev = masks.device
         packed = self.pack_targets(targets, dev)
         if point_coords is None:
-            # all masks of an image share one set of points; drawn per image like the reference (matcher.py:124)
+            # all masks of an image share one set of points; drawn per image like the reference (matcher.py:120)
             point_coords = torch.cat([torch.rand(1, self.num_points, 2, device=dev) for _ in range(bs)])
         if self.sort_points:
             point_coords = self.row_major_order(point_coords, *masks.shape[-2:])
-        logits = logits.float()                     # autocast heads: the costs are computed in fp32 (matcher.py:126-128)
+        logits = logits.float()                     # autocast heads: the costs are computed in fp32 (matcher.py:134-136)
         masks = masks.float()
         groups = [(0, bs)] if packed.uniform() else [(b, b + 1) for b in range(bs)]
         qi, ti, costs, stats = [], [], [], []

@@ -758,7 +758,7 @@ def masked_xattn_bwd(q_hi, q_lo, k_hi, k_lo, kt_hi, kt_lo, v_hi, v_lo, d_o, bits
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# Hungarian matching on the device (ref mask2former/modeling/matcher.py:97-157)
+# Hungarian matching on the device (ref mask2former/modeling/matcher.py:96-157)
 # ----------------------------------------------------------------------------------------------------------------
 def match_cost(pred_logits, pred_masks, tgt_mask_ptrs, tgt_is_f32, tgt_hw, tgt_labels, tgt_offsets, counts,
                point_coords, cost_class, cost_mask, cost_dice):
@@ -834,7 +834,7 @@ def lsap(cost, tgt_offsets, counts, num_queries):
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# Point sampling for the criterion (ref mask2former/modeling/criterion.py:143-192)
+# Point sampling for the criterion (ref mask2former/modeling/criterion.py:141-191)
 # ----------------------------------------------------------------------------------------------------------------
 def point_sample_rows(map_ptrs, maps_are_f32, hw, coords, neg_abs=False):
     """out[r, p] = bilinear(map_r, coords[r, p]) with map_r the H x W map (uint8 or float32) at device address

@@ -2,10 +2,10 @@
 that consumes the decoder's outputs.  Not used by the product path or by bench.py's timed legs.
 
 Follows mask2former/modeling/criterion.py of the reference:
-  * ``dice_loss`` :21-41, ``sigmoid_ce_loss`` :49-67, ``calculate_uncertainty`` :75-89
-  * ``SetCriterion.loss_labels`` :123-141, ``loss_masks`` :143-192, permutation indices :194-204
-  * ``SetCriterion.forward`` :214-308 (main matching, num_masks normalisation, the mask-piloted "dn" losses with the
-    fixed GT assignment :243-262, the per-layer auxiliary losses :274-303, ``dn_no_lb`` :304-305)
+  * ``dice_loss`` :21-41, ``sigmoid_ce_loss`` :49-67, ``calculate_uncertainty`` :73-87
+  * ``SetCriterion.loss_labels`` :123-141, ``loss_masks`` :141-191, permutation indices :193-203
+  * ``SetCriterion.forward`` :213-304 (main matching, num_masks normalisation, the mask-piloted "dn" losses with the
+    fixed GT assignment :243-262, the per-layer auxiliary losses :276-299, ``dn_no_lb`` :300-301)
 and detectron2's ``get_uncertain_point_coords_with_randomness`` (PointRend importance sampling; third-party, unpinned
 "git master", INSTALL.md:36-38 -- restated from the published algorithm, see oracle/ref_loader.py).
 Random-number consumption (global generator of the masks' device) is the reference's, call for call, so that seeded
@@ -23,7 +23,7 @@ def uncertain_points(logits, num_points, oversample_ratio, importance_sample_rat
     R = logits.shape[0]
     n_over = int(num_points * oversample_ratio)
     cand = torch.rand(R, n_over, 2, device=logits.device, dtype=logits.dtype)
-    unc = -point_sample(logits, cand).abs()[:, 0]                       # criterion.py:75-89
+    unc = -point_sample(logits, cand).abs()[:, 0]                       # criterion.py:73-87
     n_unc = int(importance_sample_ratio * num_points)
     top = unc.topk(n_unc, dim=1).indices
     coords = torch.gather(cand, 1, top[..., None].expand(-1, -1, 2))
@@ -33,7 +33,7 @@ def uncertain_points(logits, num_points, oversample_ratio, importance_sample_rat
 
 
 def flat_indices(indices):
-    """[(src_b, tgt_b)] -> (batch index, src index, tgt index), images back to back (criterion.py:194-204)."""
+    """[(src_b, tgt_b)] -> (batch index, src index, tgt index), images back to back (criterion.py:193-203)."""
     b = torch.cat([torch.full_like(s, i) for i, (s, _) in enumerate(indices)])
     return b, torch.cat([s for s, _ in indices]), torch.cat([t for _, t in indices])
 
@@ -65,7 +65,7 @@ def loss_masks(outputs, targets, indices, num_masks, num_points, oversample_rati
 
 
 def dn_indices(targets, dn_args, device):
-    """Fixed assignment of the mask-piloted queries: group g's query g*max_num + j belongs to target j (:246-256)."""
+    """Fixed assignment of the mask-piloted queries: group g's query g*max_num + j belongs to target j (:246-257)."""
     scalar = dn_args["pad_size"] // dn_args["max_num"]
     out = []
     for tt in targets:
@@ -79,7 +79,7 @@ def dn_indices(targets, dn_args, device):
 def set_criterion(outputs, targets, *, num_classes, eos_coef, losses, num_points, oversample_ratio,
                   importance_sample_ratio, cost_class, cost_mask, cost_dice, training=True, dn_no_lb=False,
                   world_size=1, global_num_masks=None, matcher=None):
-    """``SetCriterion.forward`` (criterion.py:214-308).  ``matcher(outputs, targets) -> [(i, j)]`` defaults to the
+    """``SetCriterion.forward`` (criterion.py:213-304).  ``matcher(outputs, targets) -> [(i, j)]`` defaults to the
     matcher oracle with the given cost weights.  ``global_num_masks`` / ``world_size``: the all-reduced target count of a
     data-parallel run (this restatement does not communicate)."""
     dev = outputs["pred_masks"].device
@@ -101,7 +101,7 @@ def set_criterion(outputs, targets, *, num_classes, eos_coef, losses, num_points
                 raise AssertionError(f"do you really want to compute {name} loss?")
         return d
 
-    # criterion.py:228-240: the number of targets is summed over the ranks (all_reduce) and divided by the world size
+    # criterion.py:231-237: the number of targets is summed over the ranks (all_reduce) and divided by the world size
     total = float(sum(len(t["labels"]) for t in targets)) if global_num_masks is None else float(global_num_masks)
     num_masks = max(total / world_size, 1.0)
     dn_out = outputs.get("dn_out")

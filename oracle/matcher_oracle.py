@@ -5,7 +5,7 @@ product path or by bench.py.
 Restates mask2former/modeling/matcher.py of the reference:
   * ``batch_dice_loss``        matcher.py:15-30
   * ``batch_sigmoid_ce_loss``  matcher.py:38-62
-  * ``HungarianMatcher.memory_efficient_forward``  matcher.py:97-157 (one shared set of random points per image,
+  * ``HungarianMatcher.memory_efficient_forward``  matcher.py:96-157 (one shared set of random points per image,
     class cost = -softmax probability of the target class, LSAP by scipy)
 and the one third-party function on that path, detectron2's ``point_sample`` (unpinned "git master" dependency,
 INSTALL.md:36-38; not vendored): bilinear ``F.grid_sample`` at ``2 * coords - 1``, ``align_corners=False``.
@@ -39,7 +39,7 @@ def batch_sigmoid_ce_cost(inputs, targets):
 
 def matching_cost(pred_logits, pred_masks, labels, masks, point_coords, cost_class=1.0, cost_mask=1.0, cost_dice=1.0):
     """One image.  pred_logits [Q, K+1], pred_masks [Q, H, W], labels [n], masks [n, Hg, Wg] (bool / float),
-    point_coords [1, P, 2] -> cost matrix [Q, n]   (matcher.py:107-149)."""
+    point_coords [1, P, 2] -> cost matrix [Q, n]   (matcher.py:105-149)."""
     out_prob = pred_logits.softmax(-1)
     c_class = -out_prob[:, labels]
     out_mask = pred_masks[:, None]

@@ -1,6 +1,6 @@
 """N>1 path of the criterion on CPU: two gloo ranks, one image each with different numbers of targets; the device
 criterion's mask-count all-reduce (kept as a tensor, no .item()) must normalise both ranks' losses by the global
-average (ref criterion.py:228-240), checked against the oracle told the global count.  Kernels emulated in host memory
+average (ref criterion.py:231-237), checked against the oracle told the global count.  Kernels emulated in host memory
 as in tests/test_criterion_host_logic_cpu.py -- the collective / normalisation logic is under test, not the kernels."""
 import os
 import socket
