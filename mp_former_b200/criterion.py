@@ -1,6 +1,8 @@
 """Mirror of the reference's ``SetCriterion`` (mask2former/modeling/criterion.py:90-322): same constructor, same
 ``forward(outputs, targets)`` contract, same loss keys (``loss_ce / loss_mask / loss_dice`` + ``_dn`` + ``_{i}``
-suffixes), same consumption of the random generator -- arranged for the device:
+suffixes), same per-call consumption of the random generator (the candidate points of ``loss_masks`` and the matcher's
+points are drawn like the reference's; END-TO-END seed parity with the reference does not hold, because the DN
+preparation upstream draws differently -- see masked_decoder.prepare_for_dn_v5) -- arranged for the device:
 
   * the matcher's index pairs stay on the device when the matcher is ``mp_former_b200.matcher.HungarianMatcher``
     (``match_device``); any matcher with the reference's ``forward`` contract (list of CPU index pairs) works too;
@@ -50,6 +52,19 @@ class SetCriterion(nn.Module):
         assert oversample_ratio >= 1 and 0 <= importance_sample_ratio <= 1
         self._step_key = None
         self._step = None
+        self._status = None          # int32 [1] on the device: != 0 once a matching of this step has failed
+
+    def check_status(self):
+        """Raises the reference's error for a failed assignment (scipy's ``ValueError: matrix contains invalid numeric
+        entries`` / ``cost matrix is infeasible`` at matcher.py:153 -- NaN/-inf costs from diverged logits, or a label
+        outside [0, num_classes)).  The device matcher reports failure through a status word instead of a host round
+        trip per head, so the forward itself cannot raise: it poisons every loss of the step with NaN (nothing is
+        silently trained on a made-up assignment) and this method -- one 4-byte device read; call it wherever the
+        trainer already synchronises, e.g. next to the loss logging -- raises."""
+        st, self._status = self._status, None
+        if st is not None and int(st.item()) != 0:
+            raise ValueError(f"HungarianMatcher: cost matrix of image {int(st.item()) - 1} contains invalid numeric "
+                             "entries (NaN / -inf) or is infeasible")
 
     # -- per-step state shared by the 20 loss evaluations of one forward --------------------------------------------
     class _Step:
@@ -113,7 +128,9 @@ class SetCriterion(nn.Module):
     def _match(self, outputs, targets, step):
         """-> (batch index, query index, target index), int64 device vectors over all matched pairs."""
         if hasattr(self.matcher, "match_device"):
-            q, t, counts, _, _ = self.matcher.match_device(outputs, targets)
+            q, t, counts, _, status = self.matcher.match_device(outputs, targets)
+            # a failed solve returns in-range placeholder pairs (memory-safe) and a non-zero status
+            self._status = status if self._status is None else torch.maximum(self._status, status)
             nq = outputs["pred_logits"].shape[1]
             return step.batch_index([min(nq, n) for n in counts]), q, t
         indices = self.matcher(outputs, targets)
@@ -130,7 +147,9 @@ class SetCriterion(nn.Module):
         b, q, t = idx
         logits = outputs["pred_logits"].float()
         classes = torch.full(logits.shape[:2], self.num_classes, dtype=torch.int64, device=logits.device)
-        classes[b, q] = step.packed.labels[step.offsets[b] + t]
+        # (labels outside [0, num_classes) make the matcher fail -- status, NaN losses --; clamped so that the
+        # class-index gather of the cross-entropy kernel stays in range until check_status() raises)
+        classes[b, q] = step.packed.labels[step.offsets[b] + t].clamp(0, self.num_classes)
         return {"loss_ce": F.cross_entropy(logits.transpose(1, 2), classes, self.empty_weight)}
 
     def loss_masks(self, outputs, step, idx, num_masks):
@@ -185,6 +204,7 @@ class SetCriterion(nn.Module):
         dn_out = outputs.get("dn_out")
         dev = main["pred_masks"].device
         step = self._step_state(targets, dev)
+        self._status = None
         num_masks = float(step.total)
         ws = _world_size()
         if ws > 1:       # average number of masks across ranks, kept on the device (no .item() sync)
@@ -216,6 +236,9 @@ class SetCriterion(nn.Module):
                 losses.update(dn_losses(dn_out["aux_outputs"][i] if use_dn else None, f"_{i}"))
         if self.dn_no_lb:
             losses = {k: losses[k] for k in losses if not k.startswith("loss_ce_dn")}
+        if self._status is not None:        # failed assignment -> every loss NaN (see check_status)
+            poison = torch.where(self._status[0] == 0, 0.0, float("nan"))
+            losses = {k: v + poison for k, v in losses.items()}
         return losses
 
     def __repr__(self):

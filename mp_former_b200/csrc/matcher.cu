@@ -269,8 +269,20 @@ lsap_kernel(const float* __restrict__ cost, const int* __restrict__ offsets, int
   for (int k = tid; k < nc; k += LSAP_THREADS) { v[k] = 0.0; row4col[k] = -1; path[k] = -1; }
   if (tid == 0) s_fail = 0;
   __syncthreads();
+  // scipy's linear_sum_assignment rejects a matrix with ANY NaN or -inf entry ("matrix contains invalid numeric
+  // entries") before it solves; the augmenting-path search alone would only notice a row without a finite column.
+  {
+    int bad = 0;
+    const long long total = static_cast<long long>(Q) * n;
+    for (long long k = tid; k < total; k += LSAP_THREADS) {
+      const float c = __ldg(C + k);
+      bad |= (c != c) || (c == -CUDART_INF_F);
+    }
+    if (bad) s_fail = 1;
+  }
+  __syncthreads();
 
-  for (int cur = 0; cur < nr; ++cur) {
+  for (int cur = 0; cur < nr && !s_fail; ++cur) {
     for (int k = tid; k < nr; k += LSAP_THREADS) SR[k] = 0;
     for (int k = tid; k < nc; k += LSAP_THREADS) { SC[k] = 0; spc[k] = CUDART_INF; remaining[k] = nc - k - 1; }
     if (tid == 0) { s_i = cur; s_sink = -1; s_num_remaining = nc; s_min = 0.0; }
@@ -346,8 +358,11 @@ lsap_kernel(const float* __restrict__ cost, const int* __restrict__ offsets, int
   if (tid == 0) {
     const int m = min(Q, n);
     if (s_fail) {
-      for (int k = 0; k < m; ++k) { out_q[out0 + k] = -1; out_t[out0 + k] = -1; }
-      atomicExch(status, b + 1);
+      // failure is reported through ``status`` (the reference: scipy's ValueError); the pairs written here only have
+      // to be IN RANGE, so that a caller that consumes them before it looks at the status (the criterion gathers and
+      // scatters through them without a host round trip) cannot leave its buffers
+      for (int k = 0; k < m; ++k) { out_q[out0 + k] = k; out_t[out0 + k] = k; }
+      atomicMax(status, b + 1);
     } else if (transposed) {                 // rows = targets, cols = queries: emit pairs in query order
       int cnt = 0;
       for (int q = 0; q < Q; ++q)

@@ -250,11 +250,24 @@ class _MaskedDecoderBase(nn.Module):
         attn_mask = ops.attn_mask_from_logits(outputs_mask, attn_mask_target_size)
         return outputs_class, outputs_mask, attn_mask
 
+    # Parity instrumentation (tests / bench.py's parity block; None in production).  A dict with
+    #   "own":   list that receives, per cross-attention layer, the PackedMask this decoder derived itself
+    #            (after the mask-piloted rows were written);
+    #   "force": optional list of bool [B, Qt, hw] masks, one per layer, consumed INSTEAD of the decoder's own
+    #            (teacher forcing with the oracle's masks, so that one flipped bit of a logit that sits on the
+    #            threshold cannot compound over the following layers).
+    mask_debug = None
+
     def _decode(self, output, src, pos, size_list, mask_features, tgt_mask, heads0, dn_hook=None):
         outputs_class, outputs_mask, attn_mask = heads0
         predictions_class, predictions_mask = [outputs_class], [outputs_mask]
+        dbg = self.mask_debug
         for i in range(self.num_layers):
             li = i % self.num_feature_levels
+            if dbg is not None:
+                dbg["own"].append(attn_mask)
+                if dbg.get("force") is not None:
+                    attn_mask = ops.PackedMask.from_bool(dbg["force"][i].to(output.device))
             output = self.transformer_cross_attention_layers[i](
                 output, src[li], memory_mask=attn_mask, pos=pos[li], query_pos=None)
             output = self.transformer_self_attention_layers[i](output, tgt_mask=tgt_mask)

@@ -124,7 +124,9 @@ class HungarianMatcher(nn.Module):
     @torch.no_grad()
     def match_device(self, outputs, targets, point_coords=None):
         """Returns (query_idx, target_idx, counts, cost, status): flat int64 device tensors holding the pairs of all
-        images back to back (min(Q, n_b) each), the host list n_b, the flat cost matrices and the solver status.
+        images back to back (min(Q, n_b) each), the host list n_b, the flat cost matrices and the solver status
+        (int32 [1]: 0, or 1 + the index of an image whose cost matrix holds NaN / -inf or is infeasible -- where scipy
+        raises ValueError in the reference; that image's pairs are then the in-range placeholders (k, k)).
         ``point_coords`` [B, P, 2] overrides the random points (tests)."""
         logits, masks = outputs["pred_logits"], outputs["pred_masks"]
         _lib.require_cuda(masks, "outputs['pred_masks']")

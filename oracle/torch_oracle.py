@@ -254,12 +254,18 @@ def _dn_noise(masks, noise_scale, hw):
 
 
 def decoder_forward(sd, x, mask_features, *, num_queries, n_heads=8, dec_layers=9, num_classes=80,
-                    dn_args=None, dn_label_noise_ratio=-1.0, all_lys=True, prefix=""):
+                    dn_args=None, dn_label_noise_ratio=-1.0, all_lys=True, prefix="", trace=None):
     """``MultiScaleMaskedTransformerDecoderMaskDN.forward`` with ``dn_mode='points'``
     (ref decoder :1706-1857; prepare_for_normal :729-735; prepare_for_dn_v5 :968-1060;
     gen_mask_dn :1584-1622; postprocess_for_dn :1697-1703).  With ``dn_args=None`` this is also
     ``MultiScaleMaskedTransformerDecoder.forward`` (:427-523) up to the ``label_enc*0`` term.
-    ``input_proj`` is the identity (in_channels == hidden_dim, no enforce_input_project)."""
+    ``input_proj`` is the identity (in_channels == hidden_dim, no enforce_input_project).
+
+    ``trace`` (test aid, optional dict): receives ``"masks"`` -- per cross-attention layer the boolean attention mask
+    it consumed ([B, Qt, hw], head 0; the heads share it, ref :1875), after the mask-piloted rows were written and
+    before the all-masked-row rule of :1780 -- and ``"resized"``, the bilinearly resized mask logits those bits were
+    thresholded from ([B, Qt, hw], ref :1869), so that a test can teacher-force another implementation's layers with
+    these masks and check that any bit it would have computed differently sits on the threshold."""
     p = prefix
     B, C = x[0].shape[:2]
     size_list, src, pos = [], [], []
@@ -319,8 +325,14 @@ def decoder_forward(sd, x, mask_features, *, num_queries, n_heads=8, dec_layers=
             tgt_mask[single_pad * i:single_pad * (i + 1), :single_pad * i] = True
 
     pred_class, pred_mask = [outputs_class], [outputs_mask]
+    if trace is not None:
+        trace["masks"], trace["resized"] = [], []
+        resized = F.interpolate(outputs_mask, size=size_list[0], mode="bilinear", align_corners=False).flatten(2)
     for i in range(dec_layers):
         li = i % 3
+        if trace is not None:
+            trace["masks"].append(attn_mask.view(B, n_heads, -1, attn_mask.shape[-1])[:, 0].clone())
+            trace["resized"].append(resized.detach())
         attn_mask = attn_mask.clone()
         attn_mask[torch.where(attn_mask.sum(-1) == attn_mask.shape[-1])] = False      # ref :1780
         cp = f"{p}transformer_cross_attention_layers.{i}."
@@ -335,6 +347,8 @@ def decoder_forward(sd, x, mask_features, *, num_queries, n_heads=8, dec_layers=
         output = F.layer_norm(output + t2, (C,), sd[fp + "norm.weight"], sd[fp + "norm.bias"])
         level = (i + 1) % 3
         outputs_class, outputs_mask, attn_mask = prediction_heads(sd, p, output, mask_features, size_list[level], n_heads)
+        if trace is not None:
+            resized = F.interpolate(outputs_mask, size=size_list[level], mode="bilinear", align_corners=False).flatten(2)
         if dn_args is not None and (all_lys or i < 3):
             hw = size_list[level][0] * size_list[level][1]
             pm = torch.ones(B, dn_meta["pad_size"], hw, dtype=torch.bool, device=x[0].device)

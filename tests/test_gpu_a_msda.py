@@ -66,10 +66,10 @@ def test_reference_testpy_float_and_double_criteria():
             assert torch.allclose(got, ref, rtol=1e-2, atol=1e-3)
 
 
-@pytest.mark.parametrize("channels", [30, 32, 64, 71, 1025])
+@pytest.mark.parametrize("channels", [30, 32, 64, 71, 1025, 2048, 3096])
 def test_reference_gradcheck_channels(channels):
-    """ops/test.py:66-89 gradcheck in fp64 over the channel counts that select the reference's
-    different backward kernels (2048 / 3096 behave like 1025 here: one generic kernel)."""
+    """ops/test.py:66-89 gradcheck in fp64 over the reference's full list of channel counts (:88-89; they select
+    its different backward kernels -- here fp64 always runs the one generic kernel)."""
     N, M_, Lq, L, P = 1, 2, 2, 2, 2
     shapes = [(6, 4), (3, 2)]
     S = sum(h * w for h, w in shapes)

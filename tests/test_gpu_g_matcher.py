@@ -143,7 +143,24 @@ def test_lsap_kernel_batched_ragged_and_invalid():
     bad[:, 4] = np.nan          # a whole column invalid: no feasible complete assignment of the 7 targets
     qi, ti, status = native.lsap(torch.from_numpy(bad.reshape(-1)).cuda(),
                                  torch.tensor([0, 7], dtype=torch.int32, device="cuda"), [7], Q)
-    assert int(status.item()) == 1 and bool((qi == -1).all())
+    # failure is the status word; the pairs are in-range placeholders so that a consumer cannot leave its buffers
+    assert int(status.item()) == 1
+    assert torch.equal(qi.cpu(), torch.arange(7)) and torch.equal(ti.cpu(), torch.arange(7))
+    # scipy rejects ANY NaN / -inf entry, also one that a complete assignment could avoid
+    for val in (np.nan, -np.inf):
+        bad = mats[0].copy()
+        bad[3, 2] = val
+        with pytest.raises(ValueError):
+            linear_sum_assignment(bad)
+        _, _, status = native.lsap(torch.from_numpy(bad.reshape(-1)).cuda(),
+                                   torch.tensor([0, 7], dtype=torch.int32, device="cuda"), [7], Q)
+        assert int(status.item()) == 1
+    ok = mats[0].copy()
+    ok[3, 2] = np.inf           # +inf is a legal "forbidden pair" for scipy
+    qi, ti, status = native.lsap(torch.from_numpy(ok.reshape(-1)).cuda(),
+                                 torch.tensor([0, 7], dtype=torch.int32, device="cuda"), [7], Q)
+    ri, ci = linear_sum_assignment(ok)
+    assert int(status.item()) == 0 and np.array_equal(qi.cpu().numpy(), ri) and np.array_equal(ti.cpu().numpy(), ci)
 
 
 @pytest.mark.parametrize("tgt_float", [False, True])

