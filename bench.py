@@ -1,19 +1,23 @@
 #!/usr/bin/env python
 """bench.py -- img/s (forward+backward) of the MP-Former hot path on N B200s, one JSON line.
 
-A "step" is one forward+backward pass of the hot path (MSDeformAttn pixel decoder + masked-attention
-transformer decoder, MP-Former COCO-instance R50 head, DN/mask-piloted queries on) over one batch of
-synthetic 1024x1024 backbone features.  The backbone (upstream of the path) and the criterion
-(downstream) are outside the path: inputs are R50-shaped feature maps, the loss is a
-fixed linear functional of every prediction the head returns.
+A "step" is one training pass of the hot path -- MSDeformAttn pixel decoder + masked-attention transformer decoder with
+the mask-piloted (DN) query group, the recipe's SetCriterion + HungarianMatcher on top, backward to every parameter of
+the head, gradient all-reduce -- over one batch of synthetic backbone features (the backbone is upstream of the path).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]           our arm
-  python bench.py --impl reference [...]                          CPU port of the reference path
-  torchrun --nproc-per-node N bench.py --gpus N ...               one rank per GPU (weak scaling)
+  python bench.py [--gpus N] [--steps K] [--warmup W]     our arm; default preset = BASELINE configs[1]/[2]:
+                                                          R50, 1024x1024, GLOBAL batch 16 split over the N ranks
+  python bench.py --config {1,2,3,4,5}                    another BASELINE.json configuration (1 = MSDeformAttn alone)
+  python bench.py --weak                                  16 images per GPU instead of 16 in total (round-1 mode)
+  python bench.py --loss pseudo                           linear pseudo-loss instead of the criterion (round-1 mode)
+  python bench.py --impl reference [...]                  the reference's CPU path (oracle port) on the host cores
+  torchrun --nproc-per-node N bench.py --gpus N ...       one rank per GPU
 
 Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
+The reference arm imports nothing of the product package (oracle/ only).
 """
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -24,7 +28,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "images/sec fwd+bwd, MP-Former R50 head (MSDeformAttn pixel decoder + masked decoder), 1024x1024"
+METRIC = "images/sec fwd+bwd, MP-Former head (MSDeformAttn pixel decoder + masked decoder + criterion), synthetic"
 UNIT = "img/s"
 
 
@@ -34,26 +38,52 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=16, help="images per GPU (weak scaling)")
-    ap.add_argument("--height", type=int, default=1024)
-    ap.add_argument("--width", type=int, default=1024)
-    ap.add_argument("--queries", type=int, default=100)
+    ap.add_argument("--config", type=int, default=0, choices=[0, 1, 2, 3, 4, 5],
+                    help="BASELINE.json configs[i-1]; 0 (default) = 2 on one GPU / 3 on several (same head, global "
+                         "batch 16)")
+    ap.add_argument("--weak", action="store_true", help="weak scaling: the global batch of the preset PER GPU")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU (overrides the preset's split)")
+    ap.add_argument("--loss", default="criterion", choices=["criterion", "pseudo"])
     ap.add_argument("--no-dn", action="store_true", help="drop the mask-piloted (DN) query group")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every launch eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--criterion", action="store_true",
-                    help="BASELINE config 3: SetCriterion + HungarianMatcher (device path, 12544 points, deep "
-                         "supervision + dn losses) instead of the linear pseudo-loss; not the default workload")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-stock", action="store_true")
     return ap.parse_args()
 
 
-def workload_name(a):
-    return (f"R50 feature maps {a.height}x{a.width} -> MSDeformAttnPixelDecoder(6 layers) + "
-            f"MultiScaleMaskedTransformerDecoderMaskDN(9 layers, {a.queries} queries, "
-            f"{'DN points' if not a.no_dn else 'no DN'}), fwd+bwd, "
-            + ("SetCriterion + HungarianMatcher (recipe weights, 12544 points, 10 heads + dn)"
-               if getattr(a, "criterion", False) else "linear pseudo-loss"))
+def world_info():
+    return (int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")),
+            int(os.environ.get("LOCAL_RANK", "0")))
+
+
+def resolve(a, world):
+    """Preset -> workload description shared by both arms (identical `config` objects)."""
+    from oracle import synthetic as SY
+    idx = a.config if a.config else (2 if world == 1 else 3)
+    p = dict(SY.PRESETS[idx])
+    gb = p["global_batch"]
+    if a.batch:
+        per_gpu, scaling = a.batch, "weak"
+    elif a.weak:
+        per_gpu, scaling = gb, "weak"
+    else:
+        if gb % world:
+            raise SystemExit(f"global batch {gb} does not split over {world} ranks")
+        per_gpu, scaling = gb // world, "strong"
+    p.update(per_gpu=per_gpu, scaling=scaling, preset=idx)
+    loss = ("SetCriterion + HungarianMatcher (recipe weights 2/5/5, eos 0.1, 12544 points, 10 heads + dn)"
+            if a.loss == "criterion" else "linear pseudo-loss")
+    p["config"] = {
+        "workload": (f"{p['name']}: backbone maps -> MSDeformAttnPixelDecoder(6 layers) + "
+                     f"MultiScaleMaskedTransformerDecoderMaskDN(9 layers, {p['queries']} queries, "
+                     f"{'DN points' if not a.no_dn else 'no DN'}), fwd+bwd, {loss}"),
+        "preset": f"BASELINE.json configs[{idx - 1}]", "images_per_gpu": per_gpu, "global_batch": per_gpu * world,
+        "parallelism": f"dp{world}" if world > 1 else "single", "loss": a.loss,
+        "l2": "inputs + activations of a step (> 250 MB per image) exceed the 126 MB L2; no explicit flush",
+    }
+    return p
 
 
 def pseudo_loss(out):
@@ -69,35 +99,36 @@ def pseudo_loss(out):
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port of the reference's CPU path on the host cores
+# reference arm / cpu baseline: the oracle port of the reference's CPU path on the host cores.
+# Imports oracle/ only.
 # ------------------------------------------------------------------------------------------------
-def cpu_port_step_fn(a):
+def cpu_port_step_fn(a, p):
     """Returns (fn, sample_description): fn() runs ONE image fwd+bwd through the CPU oracle."""
     import torch
-    from mp_former_b200 import workload
+    from oracle import synthetic as SY
     from oracle import torch_oracle as O
     torch.set_num_threads(min(32, os.cpu_count() or 1))   # >32 threads slow the gather-heavy port down
-    pd, dec = workload.build_head(num_queries=a.queries, device="cpu")
-    psd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in pd.state_dict().items()}
-    dsd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in dec.state_dict().items()}
-    feats = workload.synthetic_features(1, a.height, a.width)
-    dn = None if a.no_dn else {"tgt": workload.synthetic_targets(1, a.height, a.width), "scalar": 1,
-                               "noise_scale": 0.0}
-
+    psd, dsd = SY.head_state_dicts(p["backbone"], p["queries"], p["classes"], seed=0)
+    psd = {k: v.requires_grad_(v.is_floating_point()) for k, v in psd.items()}
+    dsd = {k: v.requires_grad_(v.is_floating_point()) for k, v in dsd.items()}
+    feats = SY.features(1, p["height"], p["width"], p["backbone"])
+    tg = SY.targets(1, p["height"], p["width"], p["classes"])
+    dn = None if a.no_dn else {"tgt": tg, "scalar": 1, "noise_scale": 0.0}
     loss_of = pseudo_loss
-    if getattr(a, "criterion", False):       # same workload as the GPU arm's --criterion: the recipe's SetCriterion
+    if a.loss == "criterion":
         from oracle import criterion_oracle as CO
-        targets = dn["tgt"] if dn is not None else workload.synthetic_targets(1, a.height, a.width)
-        _, weighted_sum = workload.build_criterion(device="cpu")
+        wd = SY.recipe_weight_dict()
 
         def loss_of(out):
-            return weighted_sum(CO.set_criterion(out, targets, num_classes=80, eos_coef=0.1, losses=["labels", "masks"],
-                                                 num_points=12544, oversample_ratio=3.0, importance_sample_ratio=0.75,
-                                                 cost_class=2.0, cost_mask=5.0, cost_dice=5.0, training=True))
+            losses = CO.set_criterion(out, tg, num_classes=p["classes"], eos_coef=0.1, losses=["labels", "masks"],
+                                      num_points=12544, oversample_ratio=3.0, importance_sample_ratio=0.75,
+                                      cost_class=2.0, cost_mask=5.0, cost_dice=5.0, training=True)
+            return sum(v * wd[k] for k, v in losses.items() if k in wd)
 
     def fn():
         mf, _, ms = O.pixel_decoder_forward(psd, feats)
-        out = O.decoder_forward(dsd, ms, mf, num_queries=a.queries, dn_args=dn, dn_label_noise_ratio=0.2)
+        out = O.decoder_forward(dsd, ms, mf, num_queries=p["queries"], num_classes=p["classes"], dn_args=dn,
+                                dn_label_noise_ratio=0.2)
         loss = loss_of(out)
         loss.backward()
         for sd in (psd, dsd):
@@ -105,64 +136,96 @@ def cpu_port_step_fn(a):
                 v.grad = None
         return float(loss.detach())
 
-    return fn, "1 image (same shapes/config) fwd+bwd per step through oracle/torch_oracle.py on host cores"
+    return fn, "1 image of the same configuration fwd+bwd per step through oracle/torch_oracle.py (+ criterion_oracle.py)"
 
 
-def cpu_msda_baseline(a, reps=5):
+def config1_inputs(device="cpu"):
+    import torch
+    shapes = [(128, 128), (64, 64), (32, 32), (16, 16)]              # S = Lq = 21760 (BASELINE configs[0])
+    g = torch.Generator().manual_seed(3)
+    S = sum(h * w for h, w in shapes)
+    value = torch.rand(1, S, 8, 32, generator=g) * 0.01                # distributions of ref ops/test.py:36-39
+    loc = torch.rand(1, S, 8, 4, 4, 2, generator=g)
+    aw = torch.rand(1, S, 8, 4, 4, generator=g) + 1e-5
+    aw = aw / aw.sum(-1, keepdim=True).sum(-2, keepdim=True)
+    return shapes, value.to(device), loc.to(device), aw.to(device)
+
+
+def msda_alg_bytes(B, S, Lq, M, D, L, P, backward=False):
+    fwd = 4 * (S * M * D + 2 * Lq * M * L * P + Lq * M * L * P + Lq * M * D) * B
+    if not backward:
+        return fwd
+    return fwd + 4 * (S * M * D + 3 * Lq * M * L * P) * B
+
+
+def cpu_msda_baseline(shapes, reps=5, backward=False):
     """The reference's CPU MSDeformAttn path (``ms_deform_attn_core_pytorch``, ref ops/functions/ms_deform_attn_func.py:
-    52-72, restated in oracle/torch_oracle.py::msda_core_grid_sample) on the host cores: ONE image, one encoder layer's
-    call (S = Lq = all pixels of the three levels, M=8, D=32, L=3, P=4), 2 warm-up + ``reps`` timed calls (~2-4 s).
-    Reported next to the GPU kernel's number in `roofline_msda` (north_star: "next to the reference's CPU MSDeformAttn
-    path timed on the same box's host cores (core count stated) in the same run")."""
+    52-72, restated in oracle/torch_oracle.py::msda_core_grid_sample) on the host cores: ONE image, one call over
+    S = Lq = all pixels of ``shapes``, M=8, D=32, P=4."""
     import torch
     from oracle import torch_oracle as O
     torch.set_num_threads(min(32, os.cpu_count() or 1))
-    shapes = [(a.height // s, a.width // s) for s in (8, 16, 32)]
     S = sum(h * w for h, w in shapes)
-    M_, D, L, P = 8, 32, 3, 4
+    M_, D, L, P = 8, 32, len(shapes), 4
     g = torch.Generator().manual_seed(3)
-    value = torch.rand(1, S, M_, D, generator=g) * 0.01                      # distributions of ref ops/test.py:36-39
-    loc = torch.rand(1, S, M_, L, P, 2, generator=g)
+    value = (torch.rand(1, S, M_, D, generator=g) * 0.01).requires_grad_(backward)
+    loc = torch.rand(1, S, M_, L, P, 2, generator=g).requires_grad_(backward)
     aw = torch.rand(1, S, M_, L, P, generator=g) + 1e-5
-    aw = aw / aw.sum(-1, keepdim=True).sum(-2, keepdim=True)
-    with torch.no_grad():
+    aw = (aw / aw.sum(-1, keepdim=True).sum(-2, keepdim=True)).requires_grad_(backward)
+
+    def call():
+        y = O.msda_core_grid_sample(value, shapes, loc, aw)
+        if backward:
+            y.sum().backward()
+            value.grad = loc.grad = aw.grad = None
+    with torch.set_grad_enabled(backward):
         for _ in range(2):
-            O.msda_core_grid_sample(value, shapes, loc, aw)
+            call()
         t0 = time.perf_counter()
         for _ in range(reps):
-            O.msda_core_grid_sample(value, shapes, loc, aw)
+            call()
         ms = (time.perf_counter() - t0) * 1e3 / reps
-    alg = 4 * (S * M_ * D + 2 * S * M_ * L * P + S * M_ * L * P + S * M_ * D)   # SURVEY.md §8d, per image and layer
-    return {"kernel": "ms_deform_attn_core_pytorch (reference CPU path, per-level F.grid_sample), forward",
+    alg = msda_alg_bytes(1, S, S, M_, D, L, P, backward)
+    return {"kernel": "ms_deform_attn_core_pytorch (reference CPU path, per-level F.grid_sample), "
+                      + ("forward+backward" if backward else "forward"),
             "ms_per_image_per_layer": ms, "achieved": alg / (ms / 1e3) / 1e9, "unit": "GB/s (algorithmic bytes)",
             "algorithmic_bytes": alg, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"1 image, S=Lq={S}, L=3, M=8, D=32, P=4, {reps} calls"}
+            "sample": f"1 image, S=Lq={S}, L={L}, M=8, D=32, P=4, {reps} calls"}
 
 
 def run_reference_arm(a):
-    rank = int(os.environ.get("RANK", "0"))
+    world, rank, _ = world_info()
     if rank != 0:
         return
-    fn, sample = cpu_port_step_fn(a)
-    for _ in range(min(a.warmup, 1)):
-        fn()
-    steps = a.steps
-    t0 = time.perf_counter()
-    done = 0
-    for _ in range(steps):
-        fn()
-        done += 1
-        if time.perf_counter() - t0 > 240:      # keep the whole arm within minutes
-            break
-    dt = time.perf_counter() - t0
-    v = done / dt
     import torch
+    if a.config == 1:
+        shapes = config1_inputs()[0]
+        t0 = time.perf_counter()
+        r = cpu_msda_baseline(shapes, reps=max(1, a.steps), backward=True)
+        print(json.dumps({
+            "impl": "reference", "metric": "MSDeformAttn fwd+bwd, BASELINE configs[0] (B=1, L=4, S=Lq=21760), "
+            "algorithmic GB/s", "value": r["achieved"], "unit": "GB/s", "n_gpus": a.gpus, "steps": max(1, a.steps),
+            "warmup": 2, "ms_per_step": r["ms_per_image_per_layer"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": "config1 MSDeformAttn"},
+            "cpu_baseline": {"value": r["achieved"], "unit": "GB/s", "cores": r["cores"], "kind": "port",
+                             "sample": r["sample"]},
+            "e2e": {"value": r["achieved"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.perf_counter() - t0}), flush=True)
+        return
+    p = resolve(a, world)
+    fn, sample = cpu_port_step_fn(a, p)
+    for _ in range(a.warmup):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        fn()
+    dt = time.perf_counter() - t0
+    v = a.steps / dt
     cores = torch.get_num_threads()
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus,
-        "steps": done, "warmup": min(a.warmup, 1), "ms_per_step": dt / done * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "images_per_step": 1},
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True,
+        "scaling": p["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": p["config"],
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -183,7 +246,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.proc = None
@@ -200,14 +263,14 @@ class ClockSampler:
         self.f.close()
         sm, mx, reasons = [], [], set()
         for line in open(self.path):
-            p = [x.strip() for x in line.split(",")]
-            if len(p) < 9:
+            q = [x.strip() for x in line.split(",")]
+            if len(q) < 9:
                 continue
             try:
-                sm.append(float(p[1])); mx.append(float(p[2]))
+                sm.append(float(q[1])); mx.append(float(q[2]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), q[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
@@ -217,6 +280,155 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def peaks():
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    d = json.load(open(pk)) if os.path.exists(pk) else {}
+    src = "MEASURED_PEAKS.json" if d else "fallback of B200_PROFILING.md (6650 GB/s, 1400 TFLOP/s sustained)"
+    return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), src
+
+
+def run_config1(a):
+    """BASELINE configs[0] on the GPU: MSDeformAttn forward+backward at L=4, S=Lq=21760 through the reference's
+    extension-module API (mp_former_b200.MultiScaleDeformableAttention), checked against the CPU oracle in place."""
+    import torch
+    from mp_former_b200 import MultiScaleDeformableAttention as MSDA
+    from mp_former_b200 import _lib
+    from oracle import torch_oracle as O
+    dev = torch.device("cuda", 0)
+    shapes, value, loc, aw = config1_inputs(dev)
+    st = torch.as_tensor(shapes, dtype=torch.long, device=dev)
+    st._mpf_host_shapes = tuple(shapes)
+    lsi = torch.cat((st.new_zeros((1,)), st.prod(1).cumsum(0)[:-1]))
+    gy = torch.randn(1, value.shape[1], 256, device=dev)
+    ref = O.msda_core(value.cpu(), shapes, loc.cpu(), aw.cpu())
+    err = float((MSDA.ms_deform_attn_forward(value, st, lsi, loc, aw, 128).cpu() - ref).abs().max())
+    assert err < 1e-6, err
+
+    def step():
+        MSDA.ms_deform_attn_forward(value, st, lsi, loc, aw, 128)
+        MSDA.ms_deform_attn_backward(value, st, lsi, loc, aw, gy, 128)
+    for _ in range(max(a.warmup, 3)):
+        step()
+    sampler = ClockSampler(0, os.path.join(ROOT, "gpurun_out", "clocks_rank0.csv"))
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    sampler.start()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2: written between timed steps
+    l0 = _lib.launch_count()
+    ms = []
+    for _ in range(a.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(); step(); e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop()
+    hbm, _, src = peaks()
+    S = value.shape[1]
+    alg = msda_alg_bytes(1, S, S, 8, 32, 4, 4, True) + msda_alg_bytes(1, S, S, 8, 32, 4, 4, False)
+    t = statistics.mean(ms)
+    cpu = None if a.no_cpu_baseline else cpu_msda_baseline(shapes, reps=5, backward=True)
+    # e2e: host tensors in, host gradients out, through the same extension-module API
+    hv, hl, ha, hg = (x.cpu().pin_memory() for x in (value, loc, aw, gy))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(a.steps):
+        v, l, w, g = (x.to(dev, non_blocking=True) for x in (hv, hl, ha, hg))
+        y = MSDA.ms_deform_attn_forward(v, st, lsi, l, w, 128)
+        gv, gl, ga = MSDA.ms_deform_attn_backward(v, st, lsi, l, w, g, 128)
+        outs = [x.cpu() for x in (y, gv, gl, ga)]
+    e1.record()
+    torch.cuda.synchronize()
+    te = e0.elapsed_time(e1) / a.steps
+    h2d = sum(x.numel() * 4 for x in (hv, hl, ha, hg))
+    d2h = sum(x.numel() * 4 for x in outs)
+    print(json.dumps({
+        "metric": "MSDeformAttn fwd+bwd, BASELINE configs[0] (B=1, L=4, S=Lq=21760), algorithmic GB/s",
+        "value": alg / (t / 1e3) / 1e9, "unit": "GB/s", "n_gpus": 1, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": t, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": "config1 MSDeformAttn", "l2": "256 MB written between timed steps"},
+        "clocks": clocks, "gpu_launches": launches,
+        "e2e": {"value": alg / (te / 1e3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "roofline": {"bound": "hbm", "achieved": alg / (t / 1e3) / 1e9, "peak": hbm, "unit": "GB/s",
+                     "frac": alg / (t / 1e3) / 1e9 / hbm, "traffic": None, "peak_source": src,
+                     "kernel": "msda_fwd_vec_kernel<8> + msda_bwd_vec_kernel<8> (one image: 170 CTAs x 8 heads)",
+                     "parity_max_abs_err_vs_oracle": err},
+        "cpu_baseline": None if cpu is None else {"value": cpu["achieved"], "unit": "GB/s", "cores": cpu["cores"],
+                                                  "kind": "port", "sample": cpu["sample"]}}), flush=True)
+
+
+def stock_forward_block(pd, dec, p, feats, B):
+    """Forward only, eval, no DN: this package vs the STOCK CUDA path -- the reference's eager module code (the
+    oracle's restatement run on CUDA tensors: same library calls) with the UNMODIFIED reference MSDeformAttn CUDA
+    kernel (oracle/_ref/libmsda_stock.so, built from /root/reference's .cuh at build time) plugged in.  A second stock
+    variant runs the decoder under fp16 autocast, as the reference recipe trains it (SOLVER.AMP.ENABLED, pixel decoder
+    forced to fp32 at msdeformattn.py:314)."""
+    import torch
+    from oracle import torch_oracle as O
+    so = os.path.join(ROOT, "oracle", "_ref", "libmsda_stock.so")
+    if not os.path.exists(so):
+        return {"unavailable": "oracle/_ref/libmsda_stock.so not built"}
+    lib = ctypes.CDLL(so)
+    vp, i = ctypes.c_void_p, ctypes.c_int
+    lib.ref_msda_forward_f32.argtypes = [vp] * 5 + [i] * 7 + [vp, vp]
+
+    def stock_core(value, shapes, loc, aw):
+        N, S, Mh, D = value.shape
+        Lq, L, P = loc.shape[1], loc.shape[3], loc.shape[4]
+        st = torch.as_tensor(shapes, dtype=torch.long, device=value.device)
+        lsi = torch.cat((st.new_zeros((1,)), st.prod(1).cumsum(0)[:-1]))
+        out = torch.zeros(N, Lq, Mh * D, device=value.device)         # reference zero-fills (cuda.cu:59)
+        value, loc, aw = value.float().contiguous(), loc.float().contiguous(), aw.float().contiguous()
+        rc = lib.ref_msda_forward_f32(value.data_ptr(), st.data_ptr(), lsi.data_ptr(), loc.data_ptr(),
+                                      aw.data_ptr(), N, S, Mh, D, L, Lq, P, out.data_ptr(),
+                                      torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+        return out
+
+    def timeit(fn, reps):
+        fn()
+        ts = []
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts)
+
+    psd = {k: v.detach() for k, v in pd.state_dict().items()}
+    dsd = {k: v.detach() for k, v in dec.state_dict().items()}
+    was_training = pd.training, dec.training
+    pd.eval(), dec.eval()
+    orig = O.msda_core
+    O.msda_core = stock_core
+    try:
+        with torch.no_grad():
+            def ours():
+                mf, _, ms = pd.forward_features(feats)
+                return dec(ms, mf)
+
+            def stock(amp=False):
+                mf, _, ms = O.pixel_decoder_forward(psd, feats)
+                with torch.autocast("cuda", dtype=torch.float16, enabled=amp):
+                    return O.decoder_forward(dsd, ms, mf, num_queries=p["queries"], num_classes=p["classes"])
+            a_, b_ = ours(), stock()
+            r0 = ((a_["aux_outputs"][0]["pred_masks"] - b_["aux_outputs"][0]["pred_masks"]).abs()
+                  / b_["aux_outputs"][0]["pred_masks"].abs().clamp(min=1.0)).max().item()
+            del a_, b_
+            t_ours, t_stock, t_amp = timeit(ours, 5), timeit(stock, 3), timeit(lambda: stock(True), 3)
+    finally:
+        O.msda_core = orig
+        pd.train(was_training[0]), dec.train(was_training[1])
+    torch.cuda.empty_cache()
+    return {"what": "forward only (eval, no DN), TF32 off; stock = reference eager modules on CUDA + the unmodified "
+                    "reference MSDeformAttn CUDA kernel", "images": B, "ours_ms": t_ours, "stock_fp32_ms": t_stock,
+            "stock_decoder_fp16_amp_ms": t_amp, "speedup_vs_stock_fp32": t_stock / t_ours,
+            "speedup_vs_stock_decoder_fp16_amp": t_amp / t_ours, "head0_pred_masks_max_rel_diff": r0}
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -224,9 +436,7 @@ def run_ours(a):
     from mp_former_b200 import MultiScaleDeformableAttention as MSDA
     from mp_former_b200 import _lib, graphs, native, workload
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world, rank, local = world_info()
     assert torch.cuda.is_available(), "bench.py (our arm) needs a GPU; there is no CPU fallback"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -235,8 +445,10 @@ def run_ours(a):
     torch.backends.cuda.matmul.allow_tf32 = False          # fp32 path, like the reference's pixel decoder
     torch.backends.cudnn.allow_tf32 = False
 
-    B = a.batch
-    pd, dec = workload.build_head(num_queries=a.queries, device=dev, seed=0)
+    p = resolve(a, world)
+    B, H, W = p["per_gpu"], p["height"], p["width"]
+    pd, dec = workload.build_head(backbone=p["backbone"], num_queries=p["queries"], num_classes=p["classes"],
+                                  device=dev, seed=0)
 
     class Head(torch.nn.Module):
         def __init__(self):
@@ -248,18 +460,14 @@ def run_ours(a):
             return self.predictor(ms, mf, None, dn_args)
 
     head = Head()
-    params = [p for p in head.parameters()]
-    feats = workload.synthetic_features(B, a.height, a.width, seed=rank, device=dev)
-    dn_args = None
-    if not a.no_dn:
-        dn_args = {"tgt": workload.synthetic_targets(B, a.height, a.width, seed=rank, device=dev),
-                   "scalar": 1, "noise_scale": 0.0}
+    params = [q for q in head.parameters()]
+    feats = workload.synthetic_features(B, H, W, backbone=p["backbone"], seed=rank, device=dev)
+    targets = workload.synthetic_targets(B, H, W, num_classes=p["classes"], seed=rank, device=dev)
+    dn_args = None if a.no_dn else {"tgt": targets, "scalar": 1, "noise_scale": 0.0}
 
-    loss_of = pseudo_loss
-    if a.criterion:
-        targets = dn_args["tgt"] if dn_args is not None else workload.synthetic_targets(
-            B, a.height, a.width, seed=rank, device=dev)
-        criterion, weighted_sum = workload.build_criterion(device=dev)
+    loss_of, criterion = pseudo_loss, None
+    if a.loss == "criterion":
+        criterion, weighted_sum = workload.build_criterion(num_classes=p["classes"], device=dev)
         criterion.train(True)
 
         def loss_of(out):
@@ -271,8 +479,8 @@ def run_ours(a):
         graphs.allreduce_gradients(params, world)
 
     def eager_step(f):
-        for p in params:
-            p.grad = None
+        for q in params:
+            q.grad = None
         loss = loss_of(head(f, dn_args))
         loss.backward()
         allreduce_grads()
@@ -281,9 +489,11 @@ def run_ours(a):
     for _ in range(max(a.warmup, 3)):
         eager_step(feats)
     torch.cuda.synchronize()
+    if criterion is not None:
+        criterion.check_status()
 
-    # One CUDA graph for forward + loss + backward (mp_former_b200/graphs.py): ~2,600 launches per step would
-    # otherwise be issued from Python.  Falls back to eager stepping (and says so) if capture is refused.
+    # One CUDA graph for forward + loss + backward (mp_former_b200/graphs.py).  Falls back to eager stepping (and says
+    # so) if capture is refused.
     gs, graph_note = None, "disabled (--no-graph)"
     if not a.no_graph:
         try:
@@ -338,9 +548,8 @@ def run_ours(a):
     # ---- e2e: host (pinned) inputs, H2D inside the timed region, loss read back ---------------
     e2e = None
     if not a.no_e2e:
-        host = workload.synthetic_features(B, a.height, a.width, seed=rank, device="cpu", pin=True)
+        host = workload.synthetic_features(B, H, W, backbone=p["backbone"], seed=rank, device="cpu", pin=True)
         h2d = sum(t_.numel() * t_.element_size() for t_ in host.values())
-
         # Every step's inputs come from pinned host memory; the copy of step i+1 runs on a side stream while
         # step i computes (double buffering, as a data loader would), and each step's loss is read back.
         copy_stream = torch.cuda.Stream(device=dev)
@@ -390,16 +599,10 @@ def run_ours(a):
     gprof = native.profile_end()
 
     if rank == 0:
-        peaks = {}
-        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(pk):
-            peaks = json.load(open(pk))
-        hbm = peaks.get("hbm_gbs", 6650.0)
-        tens = peaks.get("bf16_tflops_sustained", 1400.0)          # kernels timed inside a long step
-        src = "MEASURED_PEAKS.json" if peaks else "fallback (6650 GB/s, 1400 TFLOP/s sustained)"
+        hbm, tens, src = peaks()
         step_ms = ms_total / a.steps
 
-        def gemm_roof(kind, what):
+        def gemm_roof(kind, what, mma_per_product=3.0):
             r = gprof.get(kind)
             if not r or r["ms"] <= 0:
                 return None
@@ -407,19 +610,13 @@ def run_ours(a):
             tf = r["flops"] / (r["ms"] / 1e3) / 1e12
             gb = r["bytes"] / (r["ms"] / 1e3) / 1e9
             # which ceiling binds this mix of shapes: time at HBM peak for the algorithmic bytes vs time at the
-            # tensor peak for the MMAs the split arithmetic issues (3 per product); the larger one is the roofline
+            # tensor peak for the MMAs the split arithmetic issues; the larger one is the roofline
             t_hbm = r["bytes"] / (hbm * 1e9)
-            t_tensor = 3.0 * r["flops"] / (tens * 1e12)
+            t_tensor = mma_per_product * r["flops"] / (tens * 1e12)
             common = {"kernel": f"{kind} ({what})", "traffic": None,
-                      "traffic_note": "a mix of shapes is timed here, so there is no single per-launch DRAM figure; "
-                                      "single-shape ncu --set full captures (dram read+write per launch): encoder "
-                                      "FFN1 1.70 GB (profiles/r1o_ncu_gemm_ffn1.txt), 3x3 convolution forward 2.11 GB "
-                                      "(profiles/r1x_ncu_conv_fwd.txt), TN weight gradient 1.80 GB "
-                                      "(profiles/r1o_ncu_gemm_tn.txt)",
-                      "note": "fp32 operands, bf16x3 split arithmetic: 3 MMAs per product (tensor ceiling = peak/3 in "
-                              "algorithmic flops); bound = the ceiling with the larger ideal time for the timed launches",
                       "tensor_TFLOPs_algorithmic": tf, "tensor_frac_algorithmic": tf / tens,
-                      "tensor_issue_frac": 3 * tf / tens, "achieved_hbm_GBs": gb, "hbm_frac": gb / hbm,
+                      "tensor_issue_frac": mma_per_product * tf / tens, "achieved_hbm_GBs": gb, "hbm_frac": gb / hbm,
+                      "frac_of_combined_roof": max(t_hbm, t_tensor) / (r["ms"] / 1e3),
                       "ideal_ms_hbm": t_hbm * 1e3 / n, "ideal_ms_tensor": t_tensor * 1e3 / n,
                       "algorithmic_flops_per_launch": r["flops"] / n, "algorithmic_bytes_per_launch": r["bytes"] / n,
                       "avg_launch_ms": r["ms"] / n, "launches_timed": n,
@@ -430,71 +627,93 @@ def run_ours(a):
             return {"bound": "tensor", "achieved": tf, "peak": tens, "unit": "TFLOP/s", "frac": tf / tens,
                     "peak_source": src + " bf16_tflops_sustained", **common}
 
-        # MSDeformAttn: algorithmic bytes per launch:
-        #   4 * (S*M*D + 2*Lq*M*L*P + Lq*M*L*P + Lq*M*D) per image
-        S = sum((a.height // s) * (a.width // s) for s in (32, 16, 8))
-        Mh, D, L, P = 8, 32, 3, 4
-        alg = 4 * (S * Mh * D + 2 * S * Mh * L * P + S * Mh * L * P + S * Mh * D) * B
+        # MSDeformAttn: algorithmic bytes per launch
+        S = sum((H // s) * (W // s) for s in (32, 16, 8))
+        alg = msda_alg_bytes(B, S, S, 8, 32, 3, 4)
         fwd_ms = statistics.mean(prof["fwd_ms"]) if prof["fwd_ms"] else None
         bwd_ms = statistics.mean(prof["bwd_ms"]) if prof["bwd_ms"] else None
         msda = None
         if fwd_ms:
             ach = alg / (fwd_ms / 1e3) / 1e9
             msda = {"kernel": "msda_enc_fwd_kernel<8> (MSDeformAttn forward, softmax+locations fused)",
-                    "bound": "hbm", "achieved": ach, "peak": hbm,
-                    "unit": "GB/s", "frac": ach / hbm, "traffic": None,
-                    "peak_source": src + " hbm_gbs",
-                    "algorithmic_bytes_per_launch": alg, "avg_launch_ms": fwd_ms,
+                    "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+                    "peak_source": src + " hbm_gbs", "algorithmic_bytes_per_launch": alg, "avg_launch_ms": fwd_ms,
                     "launches_timed": len(prof["fwd_ms"]),
                     "share_of_step": fwd_ms * len(prof["fwd_ms"]) / n_prof / step_ms}
-            if B == 16 and a.height == 1024 and a.width == 1024:
-                # dram__bytes_read.sum + dram__bytes_write.sum of one launch at exactly this geometry, from the
-                # committed `ncu --set full` capture (a bench run cannot profile itself)
-                msda["traffic"] = 749.512192e6 + 334.541312e6
-                msda["traffic_source"] = "profiles/r1x_ncu_msda_enc_fwd.txt"
             if bwd_ms:
-                alg_b = (4 * (S * Mh * D * 2 + 3 * S * Mh * L * P) + 4 * (S * Mh * D + 3 * S * Mh * L * P)) * B
+                alg_b = msda_alg_bytes(B, S, S, 8, 32, 3, 4, True)
                 msda["backward"] = {"kernel": "msda_enc_bwd_kernel<8> (+ grad_value memset)", "avg_launch_ms": bwd_ms,
                                     "achieved": alg_b / (bwd_ms / 1e3) / 1e9,
                                     "frac": alg_b / (bwd_ms / 1e3) / 1e9 / hbm,
                                     "algorithmic_bytes_per_launch": alg_b,
                                     "share_of_step": bwd_ms * len(prof["bwd_ms"]) / n_prof / step_ms}
-        # `roofline` = the dominant kernel of the step (largest share); the others ride along under their names
         gk = gemm_roof("gemm_bf16x3_kernel", "linears / 1x1 convs / mask logits / projections, fwd + input grads")
         gt = gemm_roof("gemm_bf16x3_tn_kernel", "weight gradients, dF of the mask logits")
+        xf = gemm_roof("masked_xattn_fwd", "fused masked cross-attention forward, 3xTF32", 6.0)
+        xb = gemm_roof("masked_xattn_bwd", "fused masked cross-attention backward (dQ + dK/dV kernels)", 6.0)
         cands = [r for r in (gk, gt, msda) if r]
-        roof = max(cands, key=lambda r: r["share_of_step"]) if cands else None
-        cpu = None
-        if not a.no_cpu_baseline and world == 1:
-            fn, sample = cpu_port_step_fn(a)
-            fn()
-            t0 = time.perf_counter()
-            n = 0
-            while n < 8 and time.perf_counter() - t0 < 15:     # bounded sample: ~15-20 s of host work
-                fn(); n += 1
-            dt = time.perf_counter() - t0
-            cpu = {"value": n / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                   "sample": sample + f" ({n} steps, {dt:.1f}s)"}
-            if msda is not None:
+        roof = dict(max(cands, key=lambda r: r["share_of_step"])) if cands else None
+        if roof is not None:
+            # the north-star kernels ride inside the headline object (the driver keeps `roofline` whole)
+            def brief(r):
+                return None if r is None else {k: r[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac",
+                                                                 "avg_launch_ms", "share_of_step") if k in r}
+            roof["north_star"] = {"msda_fwd": brief(msda), "msda_bwd": None if not msda else msda.get("backward"),
+                                  "xattn_fwd": brief(xf), "xattn_bwd": brief(xb)}
+        cpu = parity = stock = None
+        if world == 1:
+            if not a.no_cpu_baseline:
+                fn, sample = cpu_port_step_fn(a, p)
+                fn()
+                t0 = time.perf_counter()
+                n = 0
+                while n < 8 and time.perf_counter() - t0 < 15:     # bounded sample: ~15-25 s of host work
+                    fn(); n += 1
+                dt = time.perf_counter() - t0
+                cpu = {"value": n / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                       "sample": sample + f" ({n} steps, {dt:.1f}s)"}
+                if msda is not None:
+                    try:
+                        shapes = [(H // s, W // s) for s in (8, 16, 32)]
+                        msda["cpu_reference"] = cpu_msda_baseline(shapes)
+                        msda["cpu_reference"]["speedup_vs_cpu_per_image"] = (
+                            msda["cpu_reference"]["ms_per_image_per_layer"] / (msda["avg_launch_ms"] / B))
+                    except Exception as e:  # noqa: BLE001  (a reporting extra must not cost the bench line)
+                        msda["cpu_reference"] = {"error": f"{type(e).__name__}: {str(e)[:120]}"}
+            if not a.no_parity:
+                # one image of this configuration, product vs CPU oracle (tests/parity_full.py): arithmetic error with
+                # the oracle's attention masks teacher-forced, and the free-running mask-bit flip rate per layer
                 try:
-                    msda["cpu_reference"] = cpu_msda_baseline(a)
-                    msda["cpu_reference"]["speedup_vs_cpu_per_image"] = (
-                        msda["cpu_reference"]["ms_per_image_per_layer"] / (msda["avg_launch_ms"] / B))
-                except Exception as e:  # noqa: BLE001  (a reporting extra must not cost the bench line)
-                    msda["cpu_reference"] = {"error": f"{type(e).__name__}: {str(e)[:120]}"}
+                    sys.path.insert(0, os.path.join(ROOT, "tests"))
+                    import parity_full
+                    f1 = workload.synthetic_features(1, H, W, backbone=p["backbone"], seed=5)
+                    t1 = workload.synthetic_targets(1, H, W, num_classes=p["classes"], seed=5)
+                    r = parity_full.compare(pd, dec, f1, t1, dev, num_queries=p["queries"])
+                    parity = {"teacher_forced_max_rel_err": max(r["forced_max_rel_logits"], r["forced_max_rel_masks"]),
+                              "tolerance": 1e-3, "teacher_forced_flip_rate_max": max(r["forced_flip_rate"]),
+                              "teacher_forced_flip_max_dist_from_threshold": r["forced_flip_max_dist"],
+                              "mask_flip_rate": statistics.mean(r["free_flip_rate"]),
+                              "mask_flip_rate_per_layer": r["free_flip_rate"],
+                              "free_running_final_frac_above_1e-3": r["free_frac_above_1e-3_masks"]}
+                except Exception as e:  # noqa: BLE001
+                    parity = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+            if not a.no_stock:
+                try:
+                    stock = stock_forward_block(pd, dec, p, feats, B)
+                except Exception as e:  # noqa: BLE001
+                    stock = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+        cfg = dict(p["config"])
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(a), "images_per_gpu": B, "global_batch": B * world,
-                       "parallelism": f"dp{world}" if world > 1 else "single",
-                       "l2": "inputs+activations per step (>2 GB) exceed the 126 MB L2; no explicit flush",
-                       "native_ops": sorted(M.ops.NATIVE_OPS), "tf32": False,
-                       "arithmetic": "fp32 storage; GEMMs in bf16x3 split arithmetic (fp32 accumulate), attention "
-                                     "core in 3xTF32; no single-pass reduced precision",
-                       "cuda_graph": graph_note},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof,
-            "roofline_msda": msda, "roofline_gemm": gk, "roofline_gemm_tn": gt, "cpu_baseline": cpu,
+            "scaling": p["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "impl_notes": {"native_ops": sorted(M.ops.NATIVE_OPS), "tf32": False, "cuda_graph": graph_note,
+                           "arithmetic": "fp32 storage; GEMMs in bf16x3 split arithmetic (fp32 accumulate), attention "
+                                         "core in 3xTF32; no single-pass reduced precision"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+            "parity": parity, "vs_stock_cuda": stock,
+            "roofline_msda": msda, "roofline_gemm": gk, "roofline_gemm_tn": gt, "roofline_xattn_fwd": xf,
+            "roofline_xattn_bwd": xb,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -505,5 +724,8 @@ if __name__ == "__main__":
     args = parse()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.config == 1:
+        if world_info()[1] == 0:                      # one image, one GPU: the other ranks have nothing to do
+            run_config1(args)
     else:
         run_ours(args)

@@ -18,6 +18,11 @@ pd, dec = workload.build_head(device=DEV)
 feats = workload.synthetic_features(B, device=DEV)
 dn = {"tgt": workload.synthetic_targets(B, device=DEV), "scalar": 1, "noise_scale": 0.0}
 params = list(pd.parameters()) + list(dec.parameters())
+loss_of = pseudo_loss
+if os.environ.get("MPF_LOSS", "criterion") == "criterion":
+    criterion, weighted_sum = workload.build_criterion(device=DEV)
+    criterion.train(True)
+    loss_of = lambda out: weighted_sum(criterion(out, dn["tgt"]))  # noqa: E731
 
 
 def step():
@@ -28,7 +33,7 @@ def step():
     with record_function("FWD_decoder"):
         out = dec(ms, mf, None, dn)
     with record_function("LOSS"):
-        loss = pseudo_loss(out)
+        loss = loss_of(out)
     with record_function("BWD"):
         loss.backward()
 

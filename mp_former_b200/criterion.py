@@ -92,6 +92,7 @@ class SetCriterion(nn.Module):
                                           device=device)
             self._batch_index = {}
             self._dn = {}
+            self.num_masks = None
 
         def batch_index(self, sizes):
             key = tuple(sizes)
@@ -205,14 +206,19 @@ class SetCriterion(nn.Module):
         dev = main["pred_masks"].device
         step = self._step_state(targets, dev)
         self._status = None
-        num_masks = float(step.total)
-        ws = _world_size()
-        if ws > 1:       # average number of masks across ranks, kept on the device (no .item() sync)
-            nm = step.total_dev.clone()
-            dist.all_reduce(nm)
-            num_masks = torch.clamp(nm / ws, min=1)[0]
-        else:
-            num_masks = max(num_masks, 1.0)
+        if step.num_masks is None:
+            # average number of target masks across ranks (ref criterion.py:262-269).  It depends on the targets
+            # alone, so it is part of the per-step state: one all-reduce when a new batch of targets arrives, kept on
+            # the device (no .item() sync), and nothing to communicate when a step with the same targets is replayed
+            # from a CUDA graph.
+            ws = _world_size()
+            if ws > 1:
+                nm = step.total_dev.clone()
+                dist.all_reduce(nm)
+                step.num_masks = torch.clamp(nm / ws, min=1)[0]
+            else:
+                step.num_masks = max(float(step.total), 1.0)
+        num_masks = step.num_masks
 
         losses = self._all_losses(main, step, self._match(main, targets, step), num_masks)
 

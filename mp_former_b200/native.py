@@ -584,7 +584,9 @@ def masked_xattn_fwd(q_hi, q_lo, k_hi, k_lo, vt_hi, vt_lo, bits, row_open, heads
     bits = bits.contiguous()
     if row_open is not None:
         row_open = row_open.to(torch.uint8).contiguous()
-    with torch.cuda.device(q_hi.device):
+    # algorithmic: QK^T and PV (2 * Qt * HW * hd flop each per head); bytes: K, V^T hi+lo read once + mask bits
+    with torch.cuda.device(q_hi.device), _Timed("masked_xattn_fwd", 4.0 * B * Qt * HW * E,
+                                                4.0 * B * HW * E * 4 + B * Qt * HW / 8.0):
         rc = _lib.load().mpf_masked_xattn_fwd_f32(
             q_hi.data_ptr(), q_lo.data_ptr(), k_hi.data_ptr(), k_lo.data_ptr(), vt_hi.data_ptr(),
             vt_lo.data_ptr(), bits.data_ptr(), None if row_open is None else row_open.data_ptr(),
@@ -748,7 +750,9 @@ def masked_xattn_bwd(q_hi, q_lo, k_hi, k_lo, kt_hi, kt_lo, v_hi, v_lo, d_o, bits
             raise RuntimeError("masked_xattn_bwd: operands must be contiguous")
     bits = bits.contiguous()
     lse2, delta = lse2.contiguous(), delta.contiguous()
-    with torch.cuda.device(q_hi.device):
+    # algorithmic: S recomputed twice, dP, dQ, dK, dV (2 * Qt * HW * hd flop each per head)
+    with torch.cuda.device(q_hi.device), _Timed("masked_xattn_bwd", 12.0 * B * Qt * HW * E,
+                                                4.0 * B * HW * E * 8 + B * Qt * HW / 8.0):
         rc = _lib.load().mpf_masked_xattn_bwd_f32(
             *[t.data_ptr() for t in ts], bits.data_ptr(), None if ro is None else ro.data_ptr(),
             lse2.data_ptr(), delta.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),

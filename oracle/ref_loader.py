@@ -237,6 +237,27 @@ def load_criterion():
     return importlib.import_module("mask2former.modeling.criterion")
 
 
+def load_head():
+    """The reference's caller of the path, ``MaskFormerHead`` (mask2former/modeling/meta_arch/mask_former_head.py),
+    imported unmodified, together with its two builders (pixel_decoder/fpn.py:21-34, transformer_decoder/
+    maskformer_transformer_decoder.py:22-28) and their registries -- for the boundary tests."""
+    load_reference()
+    dl = sys.modules["detectron2.layers"]
+    if not hasattr(dl, "DeformConv"):
+        dl.DeformConv = object
+    base = os.path.join(REFERENCE_ROOT, "mask2former", "modeling")
+    _pkg("mask2former.modeling.meta_arch", os.path.join(base, "meta_arch"))
+    ns = types.SimpleNamespace()
+    head = importlib.import_module("mask2former.modeling.meta_arch.mask_former_head")
+    ns.MaskFormerHead = head.MaskFormerHead
+    ns.build_pixel_decoder = importlib.import_module("mask2former.modeling.pixel_decoder.fpn").build_pixel_decoder
+    td = importlib.import_module("mask2former.modeling.transformer_decoder.maskformer_transformer_decoder")
+    ns.build_transformer_decoder = td.build_transformer_decoder
+    ns.TRANSFORMER_DECODER_REGISTRY = td.TRANSFORMER_DECODER_REGISTRY
+    ns.SEM_SEG_HEADS_REGISTRY = sys.modules["detectron2.modeling"].SEM_SEG_HEADS_REGISTRY
+    return ns
+
+
 class _Instances:
     """detectron2.structures.Instances stand-in: an attribute bag with the image size."""
 
