@@ -223,7 +223,7 @@ class SetCriterion(nn.Module):
         losses = self._all_losses(main, step, self._match(main, targets, step), num_masks)
 
         use_dn = bool(self.training and dn_out)
-        zero = torch.as_tensor(0.0, device=dev)
+        zero = torch.zeros((), device=dev)           # (a fill kernel: capturable, unlike a host scalar upload)
         if use_dn:
             db, dq, dt, scalar = step.dn_indices(dn_out["dn_args"])
             dn_idx = (db, dq, dt)
