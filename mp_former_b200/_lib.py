@@ -32,6 +32,7 @@ SIGNATURES = {
     "mpf_msda_backward_f64": (_c_int, _MSDA_BWD),
     "mpf_msda_enc_forward_f32": (_c_int, [_c_vp] * 5 + [_c_ll] + [_c_int] * 7 + [_c_vp, _c_vp, _c_vp]),
     "mpf_msda_enc_backward_f32": (_c_int, [_c_vp] * 6 + [_c_ll] + [_c_int] * 7 + [_c_vp, _c_vp, _c_vp, _c_vp]),
+    "mpf_msda_set_staged": (_c_int, [_c_int]),
     "mpf_split_tf32": (_c_int, [_c_vp, _c_vp, _c_vp, ctypes.c_longlong, _c_vp]),
     "mpf_gemm_tf32x3": (_c_int, [_c_vp, ctypes.c_longlong, ctypes.c_longlong, _c_vp, _c_vp,
                                  ctypes.c_longlong, ctypes.c_longlong, _c_vp, _c_vp, ctypes.c_longlong,

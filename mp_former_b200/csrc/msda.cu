@@ -23,57 +23,11 @@
 //   * "generic" kernels (any D / L / P, float or double) keep one thread per output scalar and are
 //     used for shapes outside the fast path (e.g. the reference's test.py geometries, fp64
 //     gradcheck).
-#include "mpf_common.cuh"
+#include "msda_tiling.cuh"
 
 #include <cstdlib>
 
 namespace mpf {
-
-constexpr int kMaxTiledLevels = 8;
-constexpr int kChunkQ = 128;  // queries per work unit
-constexpr int kTileW = 16;
-constexpr int kTileH = 8;
-constexpr int kThreads = 256;
-
-struct MsdaTiling {
-  int mode;  // 0: linear chunks of kChunkQ queries; 1: 16x8 tiles per level (num_query == S)
-  int num_chunks;
-  int L;
-  int H[kMaxTiledLevels];
-  int W[kMaxTiledLevels];
-  int start[kMaxTiledLevels];
-  int tiles_x[kMaxTiledLevels];
-  int chunk_begin[kMaxTiledLevels + 1];
-};
-
-// chunk-local index j (0..127) -> query index, or -1 if the slot is padding.
-__device__ __forceinline__ int query_of(const MsdaTiling& t, int chunk, int j, int num_query) {
-  if (t.mode == 0) {
-    int q = chunk * kChunkQ + j;
-    return q < num_query ? q : -1;
-  }
-  int l = 0;
-#pragma unroll
-  for (int i = 1; i < kMaxTiledLevels; ++i)
-    if (i < t.L && chunk >= t.chunk_begin[i]) l = i;
-  int tt = chunk - t.chunk_begin[l];
-  int ty = tt / t.tiles_x[l];
-  int tx = tt - ty * t.tiles_x[l];
-  int y = ty * kTileH + j / kTileW;
-  int x = tx * kTileW + (j % kTileW);
-  if (y >= t.H[l] || x >= t.W[l]) return -1;
-  return t.start[l] + y * t.W[l] + x;
-}
-
-__device__ __forceinline__ float4 ldg4(const float* p) {
-  return __ldg(reinterpret_cast<const float4*>(p));
-}
-
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b),
-               "f"(c), "f"(d)
-               : "memory");
-}
 
 // ------------------------------------------------------------------------------------------------
 // Vectorised kernels: D = 4*LPI channels, P = 4 points, L <= 8 levels.
@@ -144,12 +98,7 @@ __device__ __forceinline__ void build_descriptors(int4* so, float4* sw, const My
         offs.y = (top && rgt) ? o1 + MD : -1;
         offs.z = (bot && lft) ? o1 + rs : -1;
         offs.w = (bot && rgt) ? o1 + rs + MD : -1;
-        if (kBackward) {
-          wv = make_float4(lh, lw, a, 0.f);
-        } else {
-          const float hh = 1.f - lh, hw = 1.f - lw;
-          wv = make_float4(hh * hw * a, hh * lw * a, lh * hw * a, lh * lw * a);
-        }
+        wv = make_float4(lh, lw, a, 0.f);        // forward and backward rebuild the four corner weights from these
       } else if (kBackward) {
         wv.z = a;
       }
@@ -197,15 +146,18 @@ msda_fwd_vec_kernel(const float* __restrict__ value, const int64_t* __restrict__
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
         const int4 o = so[j * kDescStride + p];
-        const float4 w = sw[j * kDescStride + p];
+        const float4 d = sw[j * kDescStride + p];          // (lh, lw, attention weight, -)
+        if ((o.x & o.y & o.z & o.w) < 0) continue;         // sample outside the gate: the reference adds nothing
+        const float hh = 1.f - d.x, hw = 1.f - d.y;
+        const float w1 = hh * hw, w2 = hh * d.y, w3 = d.x * hw, w4 = d.x * d.y;
         const float4 v1 = o.x >= 0 ? ldg4(vl + o.x) : z;
         const float4 v2 = o.y >= 0 ? ldg4(vl + o.y) : z;
         const float4 v3 = o.z >= 0 ? ldg4(vl + o.z) : z;
         const float4 v4 = o.w >= 0 ? ldg4(vl + o.w) : z;
-        acc[it].x += w.x * v1.x + w.y * v2.x + w.z * v3.x + w.w * v4.x;
-        acc[it].y += w.x * v1.y + w.y * v2.y + w.z * v3.y + w.w * v4.y;
-        acc[it].z += w.x * v1.z + w.y * v2.z + w.z * v3.z + w.w * v4.z;
-        acc[it].w += w.x * v1.w + w.y * v2.w + w.z * v3.w + w.w * v4.w;
+        acc[it].x = bilinear_acc(acc[it].x, d.z, w1, w2, w3, w4, v1.x, v2.x, v3.x, v4.x);
+        acc[it].y = bilinear_acc(acc[it].y, d.z, w1, w2, w3, w4, v1.y, v2.y, v3.y, v4.y);
+        acc[it].z = bilinear_acc(acc[it].z, d.z, w1, w2, w3, w4, v1.z, v2.z, v3.z, v4.z);
+        acc[it].w = bilinear_acc(acc[it].w, d.z, w1, w2, w3, w4, v1.w, v2.w, v3.w, v4.w);
       }
     }
   }
@@ -412,12 +364,7 @@ __device__ __forceinline__ void enc_build_descriptors(int4* so, float4* sw, cons
         offs.y = (top && rgt) ? o1 + MD : -1;
         offs.z = (bot && lft) ? o1 + rs : -1;
         offs.w = (bot && rgt) ? o1 + rs + MD : -1;
-        if (kBackward) {
-          wv = make_float4(lh, lw, a, 0.f);
-        } else {
-          const float hh = 1.f - lh, hw = 1.f - lw;
-          wv = make_float4(hh * hw * a, hh * lw * a, lh * hw * a, lh * lw * a);
-        }
+        wv = make_float4(lh, lw, a, 0.f);        // forward and backward rebuild the four corner weights from these
       } else if (kBackward) {
         wv.z = a;
       }
@@ -470,15 +417,18 @@ msda_enc_fwd_kernel(const float* __restrict__ value, const int64_t* __restrict__
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
         const int4 o = so[j * kDescStride + p];
-        const float4 w = sw[j * kDescStride + p];
+        const float4 d = sw[j * kDescStride + p];          // (lh, lw, attention weight, -)
+        if ((o.x & o.y & o.z & o.w) < 0) continue;         // sample outside the gate: the reference adds nothing
+        const float hh = 1.f - d.x, hw = 1.f - d.y;
+        const float w1 = hh * hw, w2 = hh * d.y, w3 = d.x * hw, w4 = d.x * d.y;
         const float4 v1 = o.x >= 0 ? ldg4(vl + o.x) : z;
         const float4 v2 = o.y >= 0 ? ldg4(vl + o.y) : z;
         const float4 v3 = o.z >= 0 ? ldg4(vl + o.z) : z;
         const float4 v4 = o.w >= 0 ? ldg4(vl + o.w) : z;
-        acc[it].x += w.x * v1.x + w.y * v2.x + w.z * v3.x + w.w * v4.x;
-        acc[it].y += w.x * v1.y + w.y * v2.y + w.z * v3.y + w.w * v4.y;
-        acc[it].z += w.x * v1.z + w.y * v2.z + w.z * v3.z + w.w * v4.z;
-        acc[it].w += w.x * v1.w + w.y * v2.w + w.z * v3.w + w.w * v4.w;
+        acc[it].x = bilinear_acc(acc[it].x, d.z, w1, w2, w3, w4, v1.x, v2.x, v3.x, v4.x);
+        acc[it].y = bilinear_acc(acc[it].y, d.z, w1, w2, w3, w4, v1.y, v2.y, v3.y, v4.y);
+        acc[it].z = bilinear_acc(acc[it].z, d.z, w1, w2, w3, w4, v1.z, v2.z, v3.z, v4.z);
+        acc[it].w = bilinear_acc(acc[it].w, d.z, w1, w2, w3, w4, v1.w, v2.w, v3.w, v4.w);
       }
     }
   }
@@ -734,37 +684,6 @@ static bool vec_path_ok(int D, int L, int P, int M, int B, int* lpi) {
   return true;
 }
 
-// shapes_host may be null (then linear chunking is used).
-static MsdaTiling make_tiling(const int64_t* shapes_host, int L, int S, int Lq) {
-  MsdaTiling t;
-  t.mode = 0;
-  t.L = L;
-  t.num_chunks = (Lq + kChunkQ - 1) / kChunkQ;
-  for (int i = 0; i < kMaxTiledLevels; ++i) t.H[i] = t.W[i] = t.start[i] = t.tiles_x[i] = 0;
-  for (int i = 0; i <= kMaxTiledLevels; ++i) t.chunk_begin[i] = 0;
-  if (shapes_host == nullptr || Lq != S || L > kMaxTiledLevels) return t;
-  long long total = 0;
-  int chunks = 0;
-  for (int l = 0; l < L; ++l) {
-    const long long H = shapes_host[2 * l], W = shapes_host[2 * l + 1];
-    if (H <= 0 || W <= 0 || H > (1 << 20) || W > (1 << 20)) return t;
-    t.H[l] = static_cast<int>(H);
-    t.W[l] = static_cast<int>(W);
-    t.start[l] = static_cast<int>(total);
-    t.tiles_x[l] = (t.W[l] + kTileW - 1) / kTileW;
-    t.chunk_begin[l] = chunks;
-    chunks += t.tiles_x[l] * ((t.H[l] + kTileH - 1) / kTileH);
-    total += H * W;
-  }
-  if (total != S) return t;  // host shapes do not describe this value tensor: stay linear
-  // Tiles waste slots when W < 16 or H < 8; fall back to linear if padding exceeds 2x.
-  if (static_cast<long long>(chunks) * kChunkQ > 2ll * S + kChunkQ) return t;
-  for (int l = L; l <= kMaxTiledLevels; ++l) t.chunk_begin[l] = chunks;
-  t.num_chunks = chunks;
-  t.mode = 1;
-  return t;
-}
-
 template <typename T>
 static int launch_fwd_generic(const T* value, const int64_t* shapes, const int64_t* lstart,
                               const T* loc, const T* aw, int B, int S, int M, int D, int L, int Lq,
@@ -835,6 +754,14 @@ int msda_backward_f32(const float* grad_out, const float* value, const int64_t* 
   return finish_launch("msda_bwd_vec");
 }
 
+// msda_staged.cu
+bool msda_staged_ok(const MsdaTiling& t, int D, int L, int P, int M, int B);
+int msda_enc_forward_staged(const float* value, const float* ow, const float* ref, long long ref_bstride, int B, int S,
+                            int M, int L, int Lq, float* out, const MsdaTiling& t, cudaStream_t st);
+int msda_enc_backward_staged(const float* grad_out, const float* value, const float* ow, const float* ref,
+                             long long ref_bstride, int B, int S, int M, int L, int Lq, float* gv, float* gow,
+                             const MsdaTiling& t, cudaStream_t st);
+
 static bool enc_path_ok(int D, int L, int P, int M, int B, int* lpi) {
   return vec_path_ok(D, L, P, M, B, lpi) && L * P <= kMaxLP;
 }
@@ -848,6 +775,8 @@ int msda_enc_forward_f32(const float* value, const int64_t* shapes, const int64_
     return MPF_ERR_UNSUPPORTED;
   }
   const MsdaTiling t = make_tiling(shapes_host, L, S, Lq);
+  if (msda_staged_ok(t, D, L, P, M, B))
+    return msda_enc_forward_staged(value, ow, ref, ref_bstride, B, S, M, L, Lq, out, t, st);
   dim3 grid(t.num_chunks, M, B);
   switch (lpi) {
     case 4: msda_enc_fwd_kernel<4><<<grid, kThreads, 0, st>>>(value, shapes, lstart, ow, ref, ref_bstride, S, M, L, Lq, out, t); break;
@@ -869,6 +798,8 @@ int msda_enc_backward_f32(const float* grad_out, const float* value, const int64
   }
   MPF_CUDA_OK(cudaMemsetAsync(gv, 0, static_cast<size_t>(B) * S * M * D * sizeof(float), st));
   const MsdaTiling t = make_tiling(shapes_host, L, S, Lq);
+  if (msda_staged_ok(t, D, L, P, M, B))
+    return msda_enc_backward_staged(grad_out, value, ow, ref, ref_bstride, B, S, M, L, Lq, gv, gow, t, st);
   dim3 grid(t.num_chunks, M, B);
   switch (lpi) {
     case 4: msda_enc_bwd_kernel<4><<<grid, kThreads, 0, st>>>(grad_out, value, shapes, lstart, ow, ref, ref_bstride, S, M, L, Lq, gv, gow, t); break;

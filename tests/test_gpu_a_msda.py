@@ -192,3 +192,55 @@ def test_encoder_fused_softmax_and_locations(geom):
     close(vd.grad.cpu(), v64.grad.float(), 1e-4)
     scale = o64.grad.abs().max().item()
     assert (od.grad.cpu().double() - o64.grad).abs().max().item() / scale < 2e-4
+
+
+@pytest.mark.parametrize("geom", [
+    dict(N=2, shapes=[(32, 32), (64, 64), (128, 128)], off=3.0),      # bench geometry, offsets of a few texels
+    dict(N=1, shapes=[(8, 8), (16, 16), (32, 32)], off=1.0),
+    dict(N=2, shapes=[(16, 16), (32, 32), (64, 64)], off=40.0),       # huge offsets: most samples leave their region
+    dict(N=1, shapes=[(20, 37), (10, 19)], off=2.0),                  # ragged tiles, two levels
+    dict(N=1, shapes=[(12, 16)], off=0.3),                            # one level
+])
+def test_staged_tile_kernels_equal_the_l1_gather_kernels(geom):
+    """csrc/msda_staged.cu (TMA-staged regions, LDS gathers, fixed-point shared-memory accumulation of grad_value) vs
+    csrc/msda.cu on identical inputs: forward bit for bit (same association), grad_offsets/logits to fp32 rounding,
+    grad_value within the fixed-point quantum (2^-21 of the tile's largest incoming gradient) + atomics order."""
+    from mp_former_b200 import _lib
+    g = torch.Generator().manual_seed(23)
+    M_, D, P, L = 8, 32, 4, len(geom["shapes"])
+    shapes = geom["shapes"]
+    S = sum(h * w for h, w in shapes)
+    N = geom["N"]
+    value = torch.randn(N, S, M_, D, generator=g).to(DEV)
+    # offsets in texels of each level, a directional bias per head like the module's initialisation
+    ang = torch.arange(M_) * (2 * torch.pi / M_)
+    bias = torch.stack([ang.cos(), ang.sin()], -1).view(1, 1, M_, 1, 1, 2) * torch.arange(1, P + 1).view(1, 1, 1, 1, P, 1)
+    off = (torch.randn(N, S, M_, L, P, 2, generator=g) * 0.5 + bias) * geom["off"]
+    ow = torch.cat([off.reshape(N, S, -1), torch.randn(N, S, M_ * L * P, generator=g)], -1).to(DEV)
+    pts = []
+    for h, w in shapes:
+        ys, xs = torch.meshgrid((torch.arange(h) + 0.5) / h, (torch.arange(w) + 0.5) / w, indexing="ij")
+        pts.append(torch.stack([xs.reshape(-1), ys.reshape(-1)], -1))
+    ref = torch.cat(pts)[None, :, None, :].expand(1, S, L, 2).contiguous().to(DEV)
+    gy = torch.randn(N, S, M_ * D, generator=g).to(DEV)
+    gy[:, : S // 3] *= 1e-3                                           # tiles with very different gradient scales
+    st, lsi = dev_shapes(shapes, True)
+    lib = _lib.load()
+    outs = {}
+    prev = lib.mpf_msda_set_staged(-1)
+    try:
+        for mode in (1, 0):
+            lib.mpf_msda_set_staged(mode)
+            y = MSDA.ms_deform_attn_enc_forward(value, st, lsi, ow, ref, P)
+            gv, gow = MSDA.ms_deform_attn_enc_backward(value, st, lsi, ow, ref, gy, P)
+            torch.cuda.synchronize()
+            outs[mode] = (y, gv, gow)
+    finally:
+        lib.mpf_msda_set_staged(prev)
+    (y1, gv1, go1), (y0, gv0, go0) = outs[1], outs[0]
+    assert torch.equal(y1, y0)
+    assert (go1 - go0).abs().max().item() <= 1e-5 * max(1.0, go0.abs().max().item())
+    assert (gv1 - gv0).abs().max().item() <= 2e-5 * gy.abs().max().item()
+    # and relative to each texel's own magnitude where the gradient is small (the 1e-3 part): quantum << value
+    small = gv0[:, : shapes[0][0] * shapes[0][1]].abs().max().item()
+    assert (gv1 - gv0)[:, : shapes[0][0] * shapes[0][1]].abs().max().item() <= 1e-3 * max(small, 1e-6) + 1e-5
