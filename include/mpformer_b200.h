@@ -94,13 +94,14 @@ int mpf_msda_enc_backward_f32(const float* grad_out, const float* value, const i
                               int num_point, float* grad_value, float* grad_offsets_logits,
                               const int64_t* spatial_shapes_host, void* stream);
 
-/* Selects the kernels behind mpf_msda_enc_*: 1 (default) = TMA-staged feature tiles in shared memory + on-chip
+/* Selects the kernels behind mpf_msda_enc_*: 1 = TMA-staged feature tiles in shared memory + on-chip
  * fixed-point accumulation of grad_value (csrc/msda_staged.cu) whenever the launch is the encoder's self-attention
  * over a pixel grid (num_query == spatial_size, host shapes given, 32 channels per head, 4 points, <= 4 levels);
- * 0 = always the L1-gather / per-corner global-reduction kernels (csrc/msda.cu).  enabled < 0 only queries.
+ * 0 (default: measured faster on the B200, profiles/r2e_msda_enc_probe.jsonl) = always the L1-gather / per-corner
+ * global-reduction kernels (csrc/msda.cu).  enabled < 0 only queries.
  * Returns the previous setting.  Results agree to fp32 rounding (forward: bit for bit).  Same semantics as the
  * reference op either way (ref ops/src/cuda/ms_deform_im2col_cuda.cuh:242-304, :92-164).  Process-wide; meant for
- * A/B measurements and tests (also: environment MPF_MSDA_STAGED=0 at load time). */
+ * A/B measurements and tests (also: environment MPF_MSDA_STAGED=1 at load time). */
 int mpf_msda_set_staged(int enabled);
 
 /* ---------------------------------------------------------------------------------------------

@@ -28,6 +28,17 @@
 //   * samples whose footprint leaves the region (huge offsets, or regions clipped by the shared-memory pool: coarse
 //     query tiles looking at the finest level) take the L1 gather / global reduction path of msda.cu, per sample.
 // Results do not depend on which path a sample takes beyond fp32 rounding of the gradient sums.
+//
+// MEASURED OUTCOME (round 2, B200, B=16 at 1024^2, profiles/r2e_*): correct on the first run (bit-identical forward,
+// memcheck clean) but NOT faster than msda.cu: forward 1.44 ms vs 0.99 ms, backward 3.3 ms vs 2.98 ms.  ncu
+// (r2e_ncu_msda_staged_fwd.txt): the LDS gathers cost what the micro-benchmark promised (150 M shared wavefronts =
+// 0.54 ms at peak) but the kernel issues 34.6 K warp instructions per CTA, more than half of them in phase A (the
+// per-sample softmax / location / bilinear setup that both designs need), and with 100 KB of shared memory only two
+// CTAs (16 warps) share an SM: issue slots 45 % busy, LSU 48 %, dominant stalls long-scoreboard (phase A's global
+// loads) and fixed-latency waits -- latency-bound, where the L1 kernels hide the same latencies with 32 warps per SM.
+// The op is bound by instruction issue + LSU together, not by where the texels live, so staging cannot buy the 2x the
+// LSU numbers alone suggest.  The kernels stay in the tree as an option (mpf_msda_set_staged / MPF_MSDA_STAGED=1) and
+// as the measured answer to BASELINE.json's "TMA staging of per-level feature tiles"; the default path is msda.cu.
 #include "msda_tiling.cuh"
 #include "sm100_ptx.cuh"
 
@@ -85,6 +96,7 @@ struct Ctx {
   int* s_bbox;         // [L][4]: min h, max h, min w, max w of the low corners
   uint64_t* bars;      // [L]
   float* s_misc;       // [0] = max |grad_out| bits (backward)
+  Region* s_reg;       // [L] regions, for the level loop of phase B
 };
 
 template <bool kBwd>
@@ -102,6 +114,7 @@ __device__ __forceinline__ Ctx<kBwd> carve(uint8_t* raw, int L) {
   c.bars = reinterpret_cast<uint64_t*>(p);
   c.s_bbox = reinterpret_cast<int*>(p + 64);
   c.s_misc = reinterpret_cast<float*>(p + 64 + 64);
+  c.s_reg = reinterpret_cast<Region*>(p + 64 + 64 + 16);
   return c;
 }
 
@@ -163,8 +176,13 @@ __device__ __forceinline__ void phase_a(const Ctx<kBwd>& c, const Maps& maps, co
         const float2 rf = __ldg(reinterpret_cast<const float2*>(ref_b + (static_cast<size_t>(q[k]) * L + l) * 2));
         t.a = v[l] / sum;
         // loc = ref + off / (W, H), then pixel = loc * size - 0.5: the reference's operation order
-        const float lx = rf.x + __fdiv_rn(off.x, static_cast<float>(W));
-        const float ly = rf.y + __fdiv_rn(off.y, static_cast<float>(H));
+        // (a power-of-two size divides exactly by multiplying with its reciprocal: same bits, ~60 instructions less)
+        const float ox = (W & (W - 1)) == 0 ? off.x * (1.f / static_cast<float>(W))
+                                            : __fdiv_rn(off.x, static_cast<float>(W));
+        const float oy = (H & (H - 1)) == 0 ? off.y * (1.f / static_cast<float>(H))
+                                            : __fdiv_rn(off.y, static_cast<float>(H));
+        const float lx = rf.x + ox;
+        const float ly = rf.y + oy;
         const float h_im = ly * H - 0.5f;
         const float w_im = lx * W - 0.5f;
         if ((h_im > -1.f) && (w_im > -1.f) && (h_im < H) && (w_im < W)) {
@@ -218,6 +236,7 @@ __device__ __forceinline__ void phase_a(const Ctx<kBwd>& c, const Maps& maps, co
     base += r.pitch * r.rows;
     left -= r.pitch * r.rows;
     reg[l] = r;
+    if (tid == 0 && l < L) c.s_reg[l] = r;
   }
   // TMA: warp 0 issues every box of every region; one barrier per level
   if (tid < 32) {
@@ -314,28 +333,29 @@ msda_enc_fwd_staged_kernel(const __grid_constant__ Maps maps, const float* __res
   float4 acc[ITERS];
 #pragma unroll
   for (int it = 0; it < ITERS; ++it) acc[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-  for (int l = 0; l < kMaxL; ++l) {
-    if (l < L) {
-      if (reg[l].rows > 0) mbar_wait(&c.bars[l], 0);
-      const float* vl = vimg + static_cast<size_t>(tiling.start[l]) * MD;
-      const int pitch = reg[l].pitch, W = tiling.W[l];
+  // (runtime loops over levels and points keep the kernel inside the instruction cache: fully unrolled, the two
+  // gather paths made 9 K instructions here and 28 K in the backward, and both ran slower than the L1 kernels)
+#pragma unroll 1
+  for (int l = 0; l < L; ++l) {
+    const Region r = c.s_reg[l];
+    if (r.rows > 0) mbar_wait(&c.bars[l], 0);
+    const float* vl = vimg + static_cast<size_t>(tiling.start[l]) * MD;
+    const int pitch = r.pitch, W = tiling.W[l];
+#pragma unroll 1
+    for (int p = 0; p < 4; ++p) {
 #pragma unroll
       for (int it = 0; it < ITERS; ++it) {
         const int j = it * SLOTS + slot;
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          const uint4 d = c.desc[j * ds + l * 4 + p];
-          if (d.x == 0u) continue;
-          const float lh = __uint_as_float(d.y), lw = __uint_as_float(d.z), a = __uint_as_float(d.w);
-          const float hh = 1.f - lh, hw = 1.f - lw;
-          const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
-          const Corners g = gather(d.x, c.pool, pitch, vl, MD, W, li);
-          acc[it].x = bilinear_acc(acc[it].x, a, w1, w2, w3, w4, g.v1.x, g.v2.x, g.v3.x, g.v4.x);
-          acc[it].y = bilinear_acc(acc[it].y, a, w1, w2, w3, w4, g.v1.y, g.v2.y, g.v3.y, g.v4.y);
-          acc[it].z = bilinear_acc(acc[it].z, a, w1, w2, w3, w4, g.v1.z, g.v2.z, g.v3.z, g.v4.z);
-          acc[it].w = bilinear_acc(acc[it].w, a, w1, w2, w3, w4, g.v1.w, g.v2.w, g.v3.w, g.v4.w);
-        }
+        const uint4 d = c.desc[j * ds + l * 4 + p];
+        if (d.x == 0u) continue;
+        const float lh = __uint_as_float(d.y), lw = __uint_as_float(d.z), a = __uint_as_float(d.w);
+        const float hh = 1.f - lh, hw = 1.f - lw;
+        const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+        const Corners g = gather(d.x, c.pool, pitch, vl, MD, W, li);
+        acc[it].x = bilinear_acc(acc[it].x, a, w1, w2, w3, w4, g.v1.x, g.v2.x, g.v3.x, g.v4.x);
+        acc[it].y = bilinear_acc(acc[it].y, a, w1, w2, w3, w4, g.v1.y, g.v2.y, g.v3.y, g.v4.y);
+        acc[it].z = bilinear_acc(acc[it].z, a, w1, w2, w3, w4, g.v1.z, g.v2.z, g.v3.z, g.v4.z);
+        acc[it].w = bilinear_acc(acc[it].w, a, w1, w2, w3, w4, g.v1.w, g.v2.w, g.v3.w, g.v4.w);
       }
     }
   }
@@ -419,14 +439,15 @@ msda_enc_bwd_staged_kernel(const __grid_constant__ Maps maps, const float* __res
 #pragma unroll
   for (int k = 0; k < 4; ++k) rot[k] = 4u * static_cast<uint32_t>(k ^ gi);
 
-#pragma unroll
-  for (int l = 0; l < kMaxL; ++l) {
-    if (l < L) {
-      if (reg[l].rows > 0) mbar_wait(&c.bars[l], 0);
+#pragma unroll 1
+  for (int l = 0; l < L; ++l) {
+    {
+      const Region rl = c.s_reg[l];
+      if (rl.rows > 0) mbar_wait(&c.bars[l], 0);
       const size_t loff = static_cast<size_t>(tiling.start[l]) * MD;
       const float* vl = vimg + loff;
       float* gvl = gvimg + loff;
-      const int pitch = reg[l].pitch, W = tiling.W[l];
+      const int pitch = rl.pitch, W = tiling.W[l];
 #pragma unroll
       for (int it = 0; it < ITERS; ++it) {
         const int j = it * SLOTS + slot;
@@ -436,7 +457,7 @@ msda_enc_bwd_staged_kernel(const __grid_constant__ Maps maps, const float* __res
         const float u0 = (gi & 1) ? s1 : s0, u1 = (gi & 1) ? s0 : s1, u2 = (gi & 1) ? s3 : s2, u3 = (gi & 1) ? s2 : s3;
         const float ts0 = (gi & 2) ? u2 : u0, ts1 = (gi & 2) ? u3 : u1, ts2 = (gi & 2) ? u0 : u2,
                     ts3 = (gi & 2) ? u1 : u3;
-#pragma unroll
+#pragma unroll 1
         for (int p = 0; p < 4; ++p) {
           const uint4 d = c.desc[j * ds + l * 4 + p];
           float gh = 0.f, gw = 0.f, ga = 0.f;
@@ -499,10 +520,10 @@ msda_enc_bwd_staged_kernel(const __grid_constant__ Maps maps, const float* __res
   }
   __syncthreads();
   // flush: every touched texel of every region, once (texels of the halo outside the map are skipped)
-#pragma unroll
-  for (int l = 0; l < kMaxL; ++l) {
-    if (l < L && reg[l].rows > 0) {
-      const Region r = reg[l];
+#pragma unroll 1
+  for (int l = 0; l < L; ++l) {
+    const Region r = c.s_reg[l];
+    if (r.rows > 0) {
       const int H = tiling.H[l], W = tiling.W[l];
       float* gvl = gvimg + static_cast<size_t>(tiling.start[l]) * MD;
       const int npx = r.pitch * r.rows;
@@ -586,7 +607,9 @@ static int make_maps(Maps* maps, const float* value, const MsdaTiling& t, int B,
 
 // True when the staged kernels cover this launch (encoder self-attention: queries == pixels with host shapes, D = 32,
 // P = 4, L <= 4).  MPF_MSDA_STAGED=0 keeps the L1-gather kernels of msda.cu (A/B measurements).
-static int g_staged = [] { const char* e = getenv("MPF_MSDA_STAGED"); return (e != nullptr && e[0] == '0') ? 0 : 1; }();
+// Default: OFF.  Measured on the B200 (profiles/r2e_msda_enc_probe.jsonl, B=16, 1024^2): staged forward 1.44 ms vs
+// 0.99 ms, staged backward 3.3 ms vs 2.98 ms -- see the note at the end of the header comment.
+static int g_staged = [] { const char* e = getenv("MPF_MSDA_STAGED"); return (e != nullptr && e[0] == '1') ? 1 : 0; }();
 
 bool msda_staged_ok(const MsdaTiling& t, int D, int L, int P, int M, int B) {
   if (!g_staged || t.mode != 1 || D != stg::kD || P != 4 || L > stg::kMaxL || M > 65535 || B > 65535) return false;

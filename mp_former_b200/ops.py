@@ -13,6 +13,8 @@ geometries to true fp32 in both directions.
 
 Inputs must be CUDA fp32 tensors; there is no CPU path.
 """
+import collections
+import logging
 import math
 import os
 
@@ -33,6 +35,29 @@ NATIVE_OPS = {"ms_deform_attn_forward", "ms_deform_attn_backward", "linear fwd+b
 MASK_LOGIT_THRESHOLD = float.fromhex("-0x1.7ffffep-23")
 
 LOG2E = 1.4426950408889634
+
+# ------------------------------------------------------------------------------------------------
+# route accounting: which implementation ran
+# ------------------------------------------------------------------------------------------------
+# Every op whose geometry may fall outside what the hand-written kernels cover records the route it took:
+# ROUTES["<op>:native"] / ROUTES["<op>:library"] count calls; the first library-route call of each (op, reason) is
+# logged once; MPF_STRICT_NATIVE=1 turns a library route into an error (CI for the bench geometries: nothing of the
+# recipe may leave the native path).  bench.py prints the counters as `impl_notes.routes`.
+ROUTES = collections.Counter()
+_ROUTE_SEEN = set()
+STRICT_NATIVE = bool(os.environ.get("MPF_STRICT_NATIVE"))
+
+
+def _route(op, native, why=""):
+    ROUTES[f"{op}:{'native' if native else 'library'}"] += 1
+    if not native:
+        if STRICT_NATIVE:
+            raise RuntimeError(f"mp_former_b200.ops.{op}: geometry outside the native kernels ({why}) and "
+                               "MPF_STRICT_NATIVE is set")
+        if (op, why) not in _ROUTE_SEEN:
+            _ROUTE_SEEN.add((op, why))
+            logging.getLogger("mp_former_b200").warning("%s: library (ATen / cuBLAS / cuDNN) route: %s", op, why)
+    return native
 
 
 def _cuda_only(t, name):
@@ -61,14 +86,15 @@ class _Linear(torch.autograd.Function):
             g2 = g2 * (y > 0)
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            if weight.shape[0] % 32 == 0:            # reduction dim of the input-gradient GEMM
+            if _route("linear.input_grad", weight.shape[0] % 32 == 0, f"out_features {weight.shape[0]} % 32 != 0"):
                 wt_hi, wt_lo = native.split_b(weight.t().contiguous())
                 gx = native.gemm(g2.contiguous(), wt_hi, wt_lo)
             else:
                 gx = g2 @ weight
             gx = gx.view(*gy.shape[:-1], weight.shape[1])
         if ctx.needs_input_grad[1]:
-            if g2.shape[1] % 4 == 0 and x2.shape[1] % 4 == 0:
+            if _route("linear.weight_grad", g2.shape[1] % 4 == 0 and x2.shape[1] % 4 == 0,
+                      f"features ({g2.shape[1]}, {x2.shape[1]}) not multiples of 4"):
                 gw = native.matmul_tn(g2.contiguous(), x2)      # dW = dY^T X on the tensor cores, no transposes
             else:
                 gw = g2.t() @ x2
@@ -82,7 +108,7 @@ def linear(x, weight, bias=None, relu=False):
     Replaces nn.Linear at ref ops/modules/ms_deform_attn.py:98,102-103,124 and
     pixel_decoder/msdeformattn.py:116-120."""
     _cuda_only(x, "x")
-    if x.shape[-1] % 32 != 0:
+    if not _route("linear", x.shape[-1] % 32 == 0, f"in_features {x.shape[-1]} % 32 != 0"):
         y = F.linear(x, weight, bias)
         return F.relu(y) if relu else y
     return _Linear.apply(x, weight, bias, relu)
@@ -130,7 +156,10 @@ class _ConvFp32(torch.autograd.Function):
 
 
 def conv2d_fp32(x, conv):
-    """``conv`` (an nn.Conv2d) applied to ``x`` with fp32 arithmetic forward and backward."""
+    """``conv`` (an nn.Conv2d) applied to ``x`` with fp32 arithmetic forward and backward (library convolution: the
+    route of layers the tensor-core kernels do not cover)."""
+    _cuda_only(x, "x")
+    _route("conv2d", False, f"{tuple(conv.weight.shape)} on {tuple(x.shape)}: cuDNN, TF32 off")
     if conv.padding_mode != "zeros" or isinstance(conv.padding, str):
         with fp32_math():
             return conv._conv_forward(x, conv.weight, conv.bias)
@@ -184,11 +213,11 @@ def conv1x1_nchw_to_cl(x, weight, bias=None):
     """1x1 convolution (ref pixel_decoder/msdeformattn.py:216-219 input projections, :262 lateral convs) of an
     NCHW-contiguous map; result: the same logical [B, Cout, H, W] in channels-last memory.  None when the geometry is
     not covered."""
-    if (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.is_contiguous() and native.GEMM_MODE == "bf16x3"
-            and (x.shape[2] * x.shape[3]) % 4 == 0 and x.shape[2] * x.shape[3] >= 128 and weight.shape[0] % 4 == 0
-            and x.shape[1] % 4 == 0):
-        return _Conv1x1NCHW.apply(x, weight, bias)
-    return None
+    ok = (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.is_contiguous() and native.GEMM_MODE == "bf16x3"
+          and (x.shape[2] * x.shape[3]) % 4 == 0 and x.shape[2] * x.shape[3] >= 128 and weight.shape[0] % 4 == 0
+          and x.shape[1] % 4 == 0)
+    ROUTES[f"conv1x1_nchw:{'tn_gemm' if ok else 'token_gemm'}"] += 1      # both native; the second copies the layout
+    return _Conv1x1NCHW.apply(x, weight, bias) if ok else None
 
 
 class _AddLayerNorm(torch.autograd.Function):
@@ -210,8 +239,9 @@ def add_layer_norm(x, r, norm):
     backward: the sum is never materialised (ref pixel_decoder/msdeformattn.py:125-126,129; decoder :52,:112,:169)."""
     _cuda_only(x, "x")
     C = x.shape[-1]
-    if C not in (128, 256, 512) or x.dtype != torch.float32 or tuple(norm.normalized_shape) != (C,) \
-            or norm.weight is None or norm.bias is None:
+    ok = (C in (128, 256, 512) and x.dtype == torch.float32 and tuple(norm.normalized_shape) == (C,)
+          and norm.weight is not None and norm.bias is not None)
+    if not _route("add_layer_norm", ok, f"width {C} / dtype {x.dtype} / affine"):
         return norm(x if r is None else x + r)
     return _AddLayerNorm.apply(x, r, norm.weight, norm.bias, norm.eps)
 
@@ -249,9 +279,9 @@ def group_norm_cl(x, gn, relu=False):
     """nn.GroupNorm (optionally followed by ReLU) on a logically-NCHW map held in channels-last memory, as two
     HBM passes forward / two backward (ref pixel_decoder/msdeformattn.py:216-219, :262-275).  Other layouts /
     group sizes go through the library GroupNorm."""
-    if (x.is_cuda and x.dim() == 4 and x.dtype == torch.float32 and gn.affine and not _NO_GN_KERNEL
-            and native.groupnorm_cl_ok(x.shape[1], gn.num_groups)
-            and x.permute(0, 2, 3, 1).is_contiguous()):
+    ok = (x.is_cuda and x.dim() == 4 and x.dtype == torch.float32 and gn.affine and not _NO_GN_KERNEL
+          and native.groupnorm_cl_ok(x.shape[1], gn.num_groups) and x.permute(0, 2, 3, 1).is_contiguous())
+    if _route("group_norm", ok, f"{tuple(x.shape)} groups {gn.num_groups} (layout / group size)"):
         return _GroupNormCL.apply(x, gn.weight, gn.bias, gn.eps, gn.num_groups, relu)
     y = gn(x)
     return F.relu(y) if relu else y
@@ -288,8 +318,9 @@ def group_norm_nchw_to_cl(x, gn, relu=False):
     if (x.is_cuda and x.dim() == 4 and x.dtype == torch.float32 and gn.affine and not _NO_GN_KERNEL
             and x.is_contiguous()
             and native.groupnorm_nchw2cl_ok(x.shape[1], gn.num_groups, x.shape[2] * x.shape[3])):
+        ROUTES["group_norm_nchw_to_cl:native"] += 1
         return _GroupNormNCHW2CL.apply(x, gn.weight, gn.bias, gn.eps, gn.num_groups, relu)
-    return None
+    return None          # (the caller continues with group_norm_cl, which records its own route)
 
 
 class _Upsample2xAddNCHW(torch.autograd.Function):
@@ -314,7 +345,9 @@ def upsample2x_add_to_nchw(cur, prev):
             and cur.shape[2] == 2 * prev.shape[2] and cur.shape[3] == 2 * prev.shape[3]
             and native.upsample2x_add_ok(cur.shape[2], cur.shape[3], cur.shape[1])
             and cur.permute(0, 2, 3, 1).is_contiguous() and prev.permute(0, 2, 3, 1).is_contiguous()):
+        ROUTES["upsample2x_add_to_nchw:native"] += 1
         return _Upsample2xAddNCHW.apply(cur, prev)
+    _route("upsample2x_add_to_nchw", False, f"{tuple(cur.shape)} <- {tuple(prev.shape)}")
     return None
 
 
@@ -340,8 +373,9 @@ def upsample2x_add_cl(cur, prev):
     if (cur.is_cuda and cur.dtype == torch.float32 and prev.dtype == torch.float32 and cur.dim() == 4
             and cur.shape[2] == 2 * prev.shape[2] and cur.shape[3] == 2 * prev.shape[3] and cur.shape[1] % 4 == 0
             and cur.permute(0, 2, 3, 1).is_contiguous() and prev.permute(0, 2, 3, 1).is_contiguous()):
+        ROUTES["upsample2x_add_cl:native"] += 1
         return _Upsample2xAddCL.apply(cur, prev)
-    return None
+    return None          # (the caller tries upsample2x_add_to_nchw next)
 
 
 class _Conv3x3CL(torch.autograd.Function):
@@ -389,7 +423,8 @@ def conv3x3_cl_supported(x, conv):
 def conv3x3_cl(x, conv):
     """``conv`` (nn.Conv2d, 3x3, stride 1, padding 1) on a logically-NCHW map in channels-last memory, result likewise.
     None when the layer / geometry is not covered (caller uses the library convolution)."""
-    if conv3x3_cl_supported(x, conv) and x.permute(0, 2, 3, 1).is_contiguous():
+    if _route("conv3x3", conv3x3_cl_supported(x, conv) and x.permute(0, 2, 3, 1).is_contiguous(),
+              f"{tuple(x.shape)} -> {conv.out_channels} (channels % 64 / layout)"):
         return _Conv3x3CL.apply(x, conv.weight, conv.bias)
     return None
 
@@ -428,7 +463,8 @@ def ffn(x, w1, b1, w2, b2):
     dropout 0)."""
     _cuda_only(x, "x")
     if x.shape[-1] % 32 or w1.shape[0] % 32 or w2.shape[0] % 4:
-        return linear(linear(x, w1, b1, relu=True), w2, b2)
+        return linear(linear(x, w1, b1, relu=True), w2, b2)          # (each linear records its own route)
+    ROUTES["ffn:native"] += 1
     return _FFN.apply(x, w1, b1, w2, b2)
 
 
@@ -641,7 +677,7 @@ class _MaskLogits(torch.autograd.Function):
         g2 = g.reshape(B, g.shape[1], H * W)
         ge = gf = None
         g2 = g2.contiguous()
-        ok = (H * W) % 4 == 0 and C % 4 == 0
+        ok = _route("mask_logits.backward", (H * W) % 4 == 0 and C % 4 == 0, f"H*W {H * W} or C {C} % 4 != 0")
         if ctx.needs_input_grad[0]:
             # dE[b] = dOut[b] (Q x HW) @ F[b] (HW x C): a small [Q x C] result reduced over H*W = 65536, so the
             # reduction is cut into K-splits across CTAs; F is consumed MN-major (no transpose)
@@ -943,6 +979,7 @@ def self_attention(qk_in, v_in, w_in, b_in, w_out, b_out, nhead, tgt_mask=None):
         q, k = qk[..., :E], qk[..., E:]
         v = linear(v_in, w_in[2 * E:], b_in[2 * E:])
     allowed = None if tgt_mask is None else ~tgt_mask
+    ROUTES["self_attention.core:library"] += 1      # [Q x Q] core: library SDPA (projections are native GEMMs)
     o = F.scaled_dot_product_attention(_split_heads(q, nhead), _split_heads(k, nhead),
                                        _split_heads(v, nhead), attn_mask=allowed)
     o = o.transpose(1, 2).reshape(qk_in.shape)

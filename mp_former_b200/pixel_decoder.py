@@ -50,7 +50,7 @@ class ConvNormAct(nn.Conv2d):
         self.activation = activation
 
     def forward(self, x):
-        x = ops.conv2d_fp32(x, self) if x.is_cuda else super().forward(x)
+        x = ops.conv2d_fp32(x, self)           # library convolution, fp32 pinned; CUDA only like every op of the path
         return self.norm_act(x)
 
     def norm_act(self, x):
@@ -71,7 +71,7 @@ def conv1x1_tokens(x, conv):
     tensor-core kernel: [B*H*W, Cin] x W[Cout, Cin]^T (+ bias).  Returns the map in the same form."""
     B, Cin, H, W = x.shape
     if Cin % 32 != 0 or conv.kernel_size != (1, 1) or conv.stride != (1, 1):
-        return ops.conv2d_fp32(x, conv) if x.is_cuda else F.conv2d(x, conv.weight, conv.bias)
+        return ops.conv2d_fp32(x, conv)
     if x.is_contiguous() and not x.permute(0, 2, 3, 1).is_contiguous():
         # NCHW backbone output: consumed as the MN-major operand of the token-reduction GEMM, no layout copy
         y = ops.conv1x1_nchw_to_cl(x, conv.weight, conv.bias)

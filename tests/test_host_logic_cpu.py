@@ -68,6 +68,7 @@ def install_cpu_ops(setattr_fn):
     setattr_fn(native, "gt_mask_area_bits", lambda masks, size: cpu_pack_bits(
         F.interpolate(masks.float().unsqueeze(1), size=size, mode="area").flatten(1) <= 1e-8))   # ref decoder :986
     setattr_fn(ops, "masked_cross_attention", xattn)
+    setattr_fn(ops, "conv2d_fp32", lambda x, conv: conv._conv_forward(x, conv.weight, conv.bias))
 
 
 @pytest.fixture()
