@@ -510,7 +510,7 @@ def run_ours(a):
         if f is not None:
             gs.load_inputs(f)
         loss = gs.replay()
-        allreduce_grads()
+        graphs.allreduce_gradients(params, world, flat=gs.flat_grad)
         return loss
 
     def sync():

@@ -104,6 +104,28 @@ int mpf_msda_enc_backward_f32(const float* grad_out, const float* value, const i
  * A/B measurements and tests (also: environment MPF_MSDA_STAGED=1 at load time). */
 int mpf_msda_set_staged(int enabled);
 
+/* Per-row top-k selection with payload gather: for every row r of scores [rows, n] (fp32, device) the k largest
+ * entries are selected and payload[r, i, 0:payload_width] of the selected i is written to out [rows, k,
+ * payload_width] in ascending order of i (deterministic; ties at the threshold go to the lower index).  Replaces
+ * torch.topk + gather in PointRend's importance sampling of the criterion -- ref mask2former/modeling/criterion.py:
+ * 165-172 (detectron2 get_uncertain_point_coords_with_randomness): only the SET of the k most uncertain points is
+ * needed, so a 4-pass radix select over keys held in shared memory replaces a full segmented sort.
+ * Limits: 0 < k <= n <= 49152, payload_width 1 or 2.  NaN scores rank above +inf (torch.topk's convention). */
+int mpf_topk_gather_rows_f32(const float* scores, int rows, int n, int k, const float* payload, int payload_width,
+                             float* out, void* stream);
+
+/* Self-attention core of the decoder's SelfAttentionLayer (ref transformer_decoder/
+ * mask2former_transformer_decoder.py:42-52; tgt_mask of the mask-piloted groups: decoder :1051-1059):
+ *   out[b, :, h] = softmax(q_h k_h^T / sqrt(head_dim) + mask) v_h   with q | k | v = qkv[b, :, 0:E | E:2E | 2E:3E]
+ * qkv [B, Qt, 3E] fp32 (the packed in-projection output), mask uint8 [Qt, Qt] or null (1 = not allowed, shared by
+ * images and heads), out [B, Qt, E], lse [B, heads, Qt] (natural-log log-sum-exp of the scaled scores, kept for the
+ * backward).  head_dim == 32, Qt <= 320.  The backward recomputes the probabilities from lse and writes every element
+ * of d_qkv [B, Qt, 3E] (no atomics: deterministic). */
+int mpf_self_attn_fwd_f32(const float* qkv, const uint8_t* mask, int B, int Qt, int heads, int head_dim, float* out,
+                          float* lse, void* stream);
+int mpf_self_attn_bwd_f32(const float* qkv, const uint8_t* mask, const float* d_out, const float* lse, int B, int Qt,
+                          int heads, int head_dim, float* d_qkv, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Multi-scale deformable attention, backward.
  * ref: .../src/ms_deform_attn.h:47-66 (ms_deform_attn_backward), .../cuda/ms_deform_attn_cuda.cu:88-158,
@@ -316,6 +338,26 @@ int mpf_masked_xattn_bwd_f32(const float* q_hi, const float* q_lo, const float* 
                              const uint8_t* row_open, const float* lse2, const float* delta, float* dq,
                              float* dk, float* dv, int B, int Qt, int qt_ld, int HW, int heads, int head_dim,
                              int mask_words, void* stream);
+
+/* Key-split variants of the two entry points above for small batches (B * heads CTAs do not fill 148 SMs, e.g. the
+ * 2 images per GPU of BASELINE configs[2]): the key tiles of every (query tile, head, image) are divided over
+ * `key_splits` CTAs.  Forward: each CTA leaves its unnormalised output and (max, sum) in ws_o [key_splits, B, Qt, E] /
+ * ws_ml [key_splits, B, heads, Qt, 2]; a log-sum-exp merge kernel writes out / lse2.  Backward: the dQ kernel writes
+ * partial sums to ws_dq [key_splits, B, Qt, E], added in a fixed order (deterministic); dK / dV are key-parallel
+ * already.  key_splits == 1 is exactly the unsplit kernel (workspaces may be null).  Same reference semantics:
+ * transformer_decoder/mask2former_transformer_decoder.py:100-112, :1780. */
+int mpf_masked_xattn_fwd_f32_ex(const float* q_hi, const float* q_lo, const float* k_hi, const float* k_lo,
+                                const float* vt_hi, const float* vt_lo, const uint32_t* mask_bits,
+                                const uint8_t* row_open, float* out, float* lse2, int B, int Qt, int HW, int heads,
+                                int head_dim, int mask_words, int key_splits, float* ws_o, float* ws_ml,
+                                void* stream);
+int mpf_masked_xattn_bwd_f32_ex(const float* q_hi, const float* q_lo, const float* qt_hi, const float* qt_lo,
+                                const float* k_hi, const float* k_lo, const float* kt_hi, const float* kt_lo,
+                                const float* v_hi, const float* v_lo, const float* do_hi, const float* do_lo,
+                                const float* dot_hi, const float* dot_lo, const uint32_t* mask_bits,
+                                const uint8_t* row_open, const float* lse2, const float* delta, float* dq, float* dk,
+                                float* dv, int B, int Qt, int qt_ld, int HW, int heads, int head_dim, int mask_words,
+                                int key_splits, float* ws_dq, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Hungarian matching on the device (the caller right after the prediction heads).

@@ -33,6 +33,9 @@ SIGNATURES = {
     "mpf_msda_enc_forward_f32": (_c_int, [_c_vp] * 5 + [_c_ll] + [_c_int] * 7 + [_c_vp, _c_vp, _c_vp]),
     "mpf_msda_enc_backward_f32": (_c_int, [_c_vp] * 6 + [_c_ll] + [_c_int] * 7 + [_c_vp, _c_vp, _c_vp, _c_vp]),
     "mpf_msda_set_staged": (_c_int, [_c_int]),
+    "mpf_self_attn_fwd_f32": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_vp]),
+    "mpf_self_attn_bwd_f32": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
+    "mpf_topk_gather_rows_f32": (_c_int, [_c_vp, _c_int, _c_int, _c_int, _c_vp, _c_int, _c_vp, _c_vp]),
     "mpf_split_tf32": (_c_int, [_c_vp, _c_vp, _c_vp, ctypes.c_longlong, _c_vp]),
     "mpf_gemm_tf32x3": (_c_int, [_c_vp, ctypes.c_longlong, ctypes.c_longlong, _c_vp, _c_vp,
                                  ctypes.c_longlong, ctypes.c_longlong, _c_vp, _c_vp, ctypes.c_longlong,
@@ -72,6 +75,8 @@ SIGNATURES = {
     "mpf_gt_mask_area_bits": (_c_int, [_c_vp] + [_c_int] * 5 + [_c_vp, _c_int, _c_vp]),
     "mpf_masked_xattn_fwd_f32": (_c_int, [_c_vp] * 10 + [_c_int] * 6 + [_c_vp]),
     "mpf_masked_xattn_bwd_f32": (_c_int, [_c_vp] * 21 + [_c_int] * 7 + [_c_vp]),
+    "mpf_masked_xattn_fwd_f32_ex": (_c_int, [_c_vp] * 10 + [_c_int] * 7 + [_c_vp] * 3),
+    "mpf_masked_xattn_bwd_f32_ex": (_c_int, [_c_vp] * 21 + [_c_int] * 8 + [_c_vp] * 2),
     "mpf_match_cost_workspace_bytes": (_c_ll, [_c_int] * 5),
     "mpf_match_cost_f32": (_c_int, [_c_vp, _c_ll, _c_ll, _c_int, _c_vp, _c_ll, _c_ll, _c_int, _c_int, _c_vp, _c_int,
                                     _c_int, _c_int, _c_vp, _c_vp, _c_int, _c_int, _c_vp, _c_int, _c_int, _c_int,

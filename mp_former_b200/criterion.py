@@ -172,8 +172,13 @@ class SetCriterion(nn.Module):
             src_ptrs = pm.data_ptr() + 4 * (b * pm.stride(0) + q * pm.stride(1))
             cand = torch.rand(R, n_over, 2, device=pm.device, dtype=pm.dtype)
             unc = native.point_sample_rows(src_ptrs, True, (H, W), cand, neg_abs=True)     # -|logit|, :73-87
-            top = unc.topk(n_unc, dim=1).indices
-            coords = torch.gather(cand, 1, top.unsqueeze(-1).expand(-1, -1, 2))
+            if n_over <= native.TOPK_GATHER_MAX_N:
+                # the SET of the n_unc most uncertain candidates (the losses are sums over the points): radix select
+                # in shared memory + ordered gather, one kernel instead of a segmented sort, top-k and a gather
+                coords = native.topk_gather_rows(unc, cand, n_unc)
+            else:
+                top = unc.topk(n_unc, dim=1).indices
+                coords = torch.gather(cand, 1, top.unsqueeze(-1).expand(-1, -1, 2))
             if n_rand > 0:
                 coords = torch.cat([coords, torch.rand(R, n_rand, 2, device=pm.device)], dim=1)
             coords = coords.contiguous()

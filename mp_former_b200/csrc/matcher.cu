@@ -33,7 +33,7 @@
 
 namespace mpf {
 
-constexpr int MC_PT = 128;       // points per chunk
+constexpr int MC_PT = 64;        // points per chunk (58 KB of shared memory per CTA: three CTAs per SM)
 constexpr int MC_QT = 64;        // queries per CTA
 constexpr int MC_NT = 32;        // targets per CTA
 constexpr int MC_THREADS = 256;
@@ -54,7 +54,7 @@ struct MatchCostArgs {
 };
 
 template <typename TM>
-__global__ void __launch_bounds__(MC_THREADS) match_cost_partial_kernel(const MatchCostArgs a) {
+__global__ void __launch_bounds__(MC_THREADS, 3) match_cost_partial_kernel(const MatchCostArgs a) {
   extern __shared__ float smem[];
   float* s_pos = smem;
   float* s_neg = s_pos + MC_PT * MC_QS;
@@ -76,8 +76,9 @@ __global__ void __launch_bounds__(MC_THREADS) match_cost_partial_kernel(const Ma
   const TM* tm = static_cast<const TM*>(a.tgt_mask_ptrs[b]) + static_cast<long long>(j0) * a.Hg * a.Wg;
   const float* pc = a.point_coords + static_cast<long long>(b) * a.P * 2;
 
-  // phase 1 mapping: a thread owns one point of the chunk and every second query / target
-  const int p1 = tid & (MC_PT - 1), half = tid >> 7;
+  // phase 1 mapping: a thread owns one point of the chunk and every fourth query / target
+  const int p1 = tid & (MC_PT - 1), part = tid / MC_PT;
+  constexpr int PARTS = MC_THREADS / MC_PT;
   // phase 2 mapping: lanes = queries (lane, lane + 32), warp = four targets
   const int lane = tid & 31, wj = tid >> 5;
 
@@ -97,29 +98,47 @@ __global__ void __launch_bounds__(MC_THREADS) match_cost_partial_kernel(const Ma
       cy = xy.y;
     }
     {
+      // The kernel is bound by the latency of these random gathers (ncu, profiles/r2b_ncu_match_cost.txt: 8 warps
+      // per SM, long-scoreboard stalls 4.3 per issue, issue slots 20 % busy): four queries' sixteen corner loads are
+      // put in flight before the first transcendental, and three CTAs share an SM.
       const Corners cp = point_corners(cx, cy, a.H, a.W);
-      for (int qq = half; qq < MC_QT; qq += 2) {
-        float pos = 0.f, neg = 0.f, sig = 0.f;
-        if (valid && qq < nq) {
-          const float x = sample_map(pm + qq * a.masks_q_stride, cp);
-          // BCE-with-logits against 1 and against 0 (matcher.py:52-57): max(-+x, 0) + log1p(exp(-|x|))
-          const float sp = log1pf(expf(-fabsf(x)));
-          pos = fmaxf(-x, 0.f) + sp;
-          neg = fmaxf(x, 0.f) + sp;
-          sig = 1.0f / (1.0f + expf(-x));
+#pragma unroll 1
+      for (int q4 = part; q4 < MC_QT; q4 += 4 * PARTS) {
+        float x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int qq = q4 + u * PARTS;
+          x[u] = (valid && qq < nq) ? sample_map(pm + qq * a.masks_q_stride, cp) : 0.f;
         }
-        s_pos[p1 * MC_QS + qq] = pos;
-        s_neg[p1 * MC_QS + qq] = neg;
-        s_sig[p1 * MC_QS + qq] = sig;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int qq = q4 + u * PARTS;
+          float pos = 0.f, neg = 0.f, sig = 0.f;
+          if (valid && qq < nq) {
+            // BCE-with-logits against 1 and against 0 (matcher.py:52-57): max(-+x, 0) + log1p(exp(-|x|))
+            const float sp = log1pf(expf(-fabsf(x[u])));
+            pos = fmaxf(-x[u], 0.f) + sp;
+            neg = fmaxf(x[u], 0.f) + sp;
+            sig = 1.0f / (1.0f + expf(-x[u]));
+          }
+          if (qq < MC_QT) {
+            s_pos[p1 * MC_QS + qq] = pos;
+            s_neg[p1 * MC_QS + qq] = neg;
+            s_sig[p1 * MC_QS + qq] = sig;
+          }
+        }
       }
     }
     {
       const Corners ct = point_corners(cx, cy, a.Hg, a.Wg);
-      for (int jj = half; jj < MC_NT; jj += 2) {
-        float t = 0.f;
-        if (valid && jj < nj) t = sample_map(tm + static_cast<long long>(jj) * a.Hg * a.Wg, ct);
-        s_t[p1 * MC_TS + jj] = t;
+      float t[MC_NT / PARTS];
+#pragma unroll
+      for (int u = 0; u < MC_NT / PARTS; ++u) {
+        const int jj = part + u * PARTS;
+        t[u] = (valid && jj < nj) ? sample_map(tm + static_cast<long long>(jj) * a.Hg * a.Wg, ct) : 0.f;
       }
+#pragma unroll
+      for (int u = 0; u < MC_NT / PARTS; ++u) s_t[p1 * MC_TS + part + u * PARTS] = t[u];
     }
     __syncthreads();
 #pragma unroll 4
@@ -374,9 +393,10 @@ lsap_kernel(const float* __restrict__ cost, const int* __restrict__ offsets, int
 }
 
 static int match_split(int B, int qtiles, int ttiles, int nchunks) {
-  // enough CTAs for ~2 waves of the 148 SMs (one 114 KB CTA per SM pair of slots), at most one chunk per split
+  // as many point splits as fill ONE wave of 148 SMs x 3 resident CTAs without spilling into a second, mostly
+  // empty one (round 1 launched 320 one-per-SM CTAs = 3 rounds for 2.16 rounds of work); at most one chunk per split
   const long long per_split = static_cast<long long>(B) * qtiles * ttiles;
-  long long s = (2 * 148 + per_split - 1) / per_split;
+  long long s = (3 * 148) / per_split;
   if (s < 1) s = 1;
   if (s > nchunks) s = nchunks;
   return static_cast<int>(s);

@@ -51,6 +51,12 @@ struct XattnArgs {
   float* out;                // [B, Qt, E]
   float* lse2;               // [B, heads, Qt]
   int B, Qt, HW, E, heads, words;
+  // key split (small batches: B * heads CTAs do not fill 148 SMs): blockIdx.x = q_tile * splits + split; a CTA walks
+  // the key tiles [split * tiles_per_split, ...) and, when splits > 1, leaves its UNNORMALISED output with the
+  // running maximum and sum in the workspace for xattn_merge_splits_kernel (log-sum-exp merge).
+  int splits, tiles_per_split;
+  float* part_o;             // [splits, B, Qt, E]
+  float* part_ml;            // [splits, B, heads, Qt, 2]  (m, l) in the log2 domain
 };
 
 __device__ __forceinline__ float rn_tf32x(float x) {
@@ -80,8 +86,10 @@ masked_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kXQ, head = blockIdx.y, b = blockIdx.z;
-  const int T = (g.HW + kXK - 1) / kXK;
+  const int split = blockIdx.x % g.splits;
+  const int q0 = (blockIdx.x / g.splits) * kXQ, head = blockIdx.y, b = blockIdx.z;
+  const int jb = split * g.tiles_per_split;                       // first key tile of this CTA
+  const int T = min((g.HW + kXK - 1) / kXK, jb + g.tiles_per_split) - jb;   // its number of key tiles (>= 1)
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmQh); prefetch_tmap(&tmQl); prefetch_tmap(&tmKh);
@@ -119,7 +127,7 @@ masked_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_c
         mbar_wait(&kv_empty[st], ph ^ 1);
         uint8_t* s = sKV + st * kKVStage;
         mbar_arrive_expect_tx(&kv_full[st], kKVStage);
-        const int key0 = j * kXK;
+        const int key0 = (jb + j) * kXK;
         tma_load_3d(s, &tmKh, &kv_full[st], head * kXD, key0, b);
         tma_load_3d(s + kKBytes, &tmKl, &kv_full[st], head * kXD, key0, b);
         tma_load_3d(s + 2 * kKBytes, &tmVh, &kv_full[st], key0, head * kXD, b);
@@ -227,9 +235,9 @@ masked_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_c
       if (lane == 0) mbar_arrive(&s_empty[st]);
 
       // mask word for keys [64j + 32h, 64j + 32h + 32): bit = 1 -> masked.  Keys >= HW are always masked.
-      const int key0 = j * kXK + 32 * h;
+      const int key0 = (jb + j) * kXK + 32 * h;
       uint32_t w0 = 0u;
-      if (!open) w0 = brow[2 * j + h];
+      if (!open) w0 = brow[2 * (jb + j) + h];
       if (key0 + 32 > g.HW) w0 |= (key0 >= g.HW) ? 0xFFFFFFFFu : (0xFFFFFFFFu << (g.HW - key0));
 
       float tmax = -INFINITY;
@@ -283,7 +291,7 @@ masked_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_c
     s_xch[T & 1][h][r] = l;
     asm volatile("bar.sync 1, 256;" ::: "memory");
     l += s_xch[T & 1][h ^ 1][r];
-    if (q_ok) {
+    if (q_ok && g.splits == 1) {
       const float inv = 1.f / l;
       float* dst = g.out + (static_cast<long long>(b) * g.Qt + q) * g.E + head * kXD + 16 * h;
 #pragma unroll
@@ -291,6 +299,19 @@ masked_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_c
         *reinterpret_cast<float4*>(dst + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
       if (g.lse2 != nullptr && h == 0)
         g.lse2[(static_cast<long long>(b) * g.heads + head) * g.Qt + q] = m + log2f(l);
+    } else if (q_ok) {
+      // partial result of this key range: o is relative to the running maximum m_o (== m unless the last tiles
+      // were fully masked, in which case o was not rescaled: bring it to m here)
+      const float fix = (m_o == -INFINITY || m_o == m) ? 1.f : exp2f(m_o - m);
+      float* dst = g.part_o + ((static_cast<long long>(split) * g.B + b) * g.Qt + q) * g.E + head * kXD + 16 * h;
+#pragma unroll
+      for (int i = 0; i < kXD / 2; i += 4)
+        *reinterpret_cast<float4*>(dst + i) = make_float4(o[i] * fix, o[i + 1] * fix, o[i + 2] * fix, o[i + 3] * fix);
+      if (h == 0) {
+        float* ml = g.part_ml + ((((static_cast<long long>(split) * g.B + b) * g.heads + head) * g.Qt + q) << 1);
+        ml[0] = m;
+        ml[1] = l;
+      }
     }
   }
 
@@ -302,14 +323,57 @@ masked_xattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_c
   }
 }
 
+// out[b, q, head*32 + d] = sum_s o_s * 2^(m_s - m*) / sum_s l_s * 2^(m_s - m*),  lse2 = m* + log2(sum ...): the
+// log-sum-exp merge of the key splits.  One warp per (image, query, head), lane = head-dim channel.
+__global__ void __launch_bounds__(256)
+xattn_merge_splits_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml, int splits, int B,
+                          int Qt, int heads, float* __restrict__ out, float* __restrict__ lse2) {
+  const long long wid = (blockIdx.x * 256ll + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= static_cast<long long>(B) * Qt * heads) return;
+  const int head = static_cast<int>(wid % heads);
+  const long long bq = wid / heads;                     // b * Qt + q
+  const int b = static_cast<int>(bq / Qt), q = static_cast<int>(bq - static_cast<long long>(b) * Qt);
+  const int E = heads * kXD;
+  float mstar = -INFINITY;
+  for (int s = 0; s < splits; ++s)
+    mstar = fmaxf(mstar, __ldg(part_ml + ((((static_cast<long long>(s) * B + b) * heads + head) * Qt + q) << 1)));
+  float acc = 0.f, lsum = 0.f;
+  for (int s = 0; s < splits; ++s) {
+    const float* ml = part_ml + ((((static_cast<long long>(s) * B + b) * heads + head) * Qt + q) << 1);
+    const float ms = __ldg(ml);
+    if (ms == -INFINITY) continue;                       // this key range was fully masked for the row
+    const float w = exp2f(ms - mstar);
+    lsum += __ldg(ml + 1) * w;
+    acc += __ldg(part_o + ((static_cast<long long>(s) * B + b) * Qt + q) * E + head * kXD + lane) * w;
+  }
+  out[(static_cast<long long>(b) * Qt + q) * E + head * kXD + lane] = acc / lsum;
+  if (lse2 != nullptr && lane == 0) lse2[(static_cast<long long>(b) * heads + head) * Qt + q] = mstar + log2f(lsum);
+}
+
 }  // namespace mpf
 
 extern "C" {
+
+int mpf_masked_xattn_fwd_f32_ex(const float* q_hi, const float* q_lo, const float* k_hi, const float* k_lo,
+                                const float* vt_hi, const float* vt_lo, const uint32_t* mask_bits,
+                                const uint8_t* row_open, float* out, float* lse2, int B, int Qt, int HW, int heads,
+                                int head_dim, int mask_words, int key_splits, float* ws_o, float* ws_ml,
+                                void* stream);
 
 int mpf_masked_xattn_fwd_f32(const float* q_hi, const float* q_lo, const float* k_hi, const float* k_lo,
                              const float* vt_hi, const float* vt_lo, const uint32_t* mask_bits,
                              const uint8_t* row_open, float* out, float* lse2, int B, int Qt, int HW,
                              int heads, int head_dim, int mask_words, void* stream) {
+  return mpf_masked_xattn_fwd_f32_ex(q_hi, q_lo, k_hi, k_lo, vt_hi, vt_lo, mask_bits, row_open, out, lse2, B, Qt, HW,
+                                     heads, head_dim, mask_words, 1, nullptr, nullptr, stream);
+}
+
+int mpf_masked_xattn_fwd_f32_ex(const float* q_hi, const float* q_lo, const float* k_hi, const float* k_lo,
+                                const float* vt_hi, const float* vt_lo, const uint32_t* mask_bits,
+                                const uint8_t* row_open, float* out, float* lse2, int B, int Qt, int HW, int heads,
+                                int head_dim, int mask_words, int key_splits, float* ws_o, float* ws_ml,
+                                void* stream) {
   using namespace mpf;
   clear_error();
   MPF_REQUIRE(q_hi && q_lo && k_hi && k_lo && vt_hi && vt_lo && mask_bits && out, "masked_xattn: null pointer");
@@ -319,6 +383,11 @@ int mpf_masked_xattn_fwd_f32(const float* q_hi, const float* q_lo, const float* 
   const int T = (HW + kXK - 1) / kXK;
   MPF_REQUIRE(mask_words >= 2 * T, "masked_xattn: mask_words (%d) must cover %d key tiles of 64", mask_words, T);
   MPF_REQUIRE(heads <= 65535 && B <= 65535, "masked_xattn: grid too large");
+  MPF_REQUIRE(key_splits >= 1 && key_splits <= T, "masked_xattn: key_splits (%d) must be in [1, %d key tiles]",
+              key_splits, T);
+  MPF_REQUIRE(key_splits == 1 || (ws_o && ws_ml), "masked_xattn: key_splits > 1 needs the two workspaces");
+  const int tiles_per_split = (T + key_splits - 1) / key_splits;
+  const int splits = (T + tiles_per_split - 1) / tiles_per_split;       // no empty split
   const int E = heads * head_dim;
   CUtensorMap tqh, tql, tkh, tkl, tvh, tvl;
   int rc;
@@ -335,11 +404,18 @@ int mpf_masked_xattn_fwd_f32(const float* q_hi, const float* q_lo, const float* 
   XattnArgs g;
   g.bits = mask_bits; g.row_open = row_open; g.out = out; g.lse2 = lse2;
   g.B = B; g.Qt = Qt; g.HW = HW; g.E = E; g.heads = heads; g.words = mask_words;
-  dim3 grid((Qt + kXQ - 1) / kXQ, heads, B);
-  masked_xattn_fwd_kernel<<<grid, kXThreads, kXSmem, static_cast<cudaStream_t>(stream)>>>(tqh, tql, tkh, tkl, tvh,
-                                                                                         tvl, g);
+  g.splits = splits; g.tiles_per_split = tiles_per_split; g.part_o = ws_o; g.part_ml = ws_ml;
+  dim3 grid(((Qt + kXQ - 1) / kXQ) * splits, heads, B);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  masked_xattn_fwd_kernel<<<grid, kXThreads, kXSmem, st>>>(tqh, tql, tkh, tkl, tvh, tvl, g);
   count_launch();
-  return finish_launch("masked_xattn_fwd");
+  rc = finish_launch("masked_xattn_fwd");
+  if (rc != MPF_OK || splits == 1) return rc;
+  const long long warps = static_cast<long long>(B) * Qt * heads;
+  xattn_merge_splits_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, st>>>(ws_o, ws_ml, splits, B, Qt,
+                                                                                             heads, out, lse2);
+  count_launch();
+  return finish_launch("masked_xattn_fwd (split merge)");
 }
 
 }  // extern "C"

@@ -91,6 +91,10 @@ struct XbwdArgs {
   float* dv;                // kernel B: [B, HW, E]
   int B, Qt, HW, E, heads, words;
   float inv_sqrt_d;
+  // kernel A key split (see XattnArgs in xattn.cu): partial dQ of key range `split` -> part_dq[split], summed by
+  // xattn_sum_splits_kernel in a fixed order (deterministic, unlike atomics)
+  int splits, tiles_per_split;
+  float* part_dq;           // [splits, B, Qt, E]
 };
 
 // ================================================================================================
@@ -135,8 +139,10 @@ masked_xattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kQ, head = blockIdx.y, b = blockIdx.z;
-  const int T = (g.HW + kK - 1) / kK;
+  const int split = blockIdx.x % g.splits;
+  const int q0 = (blockIdx.x / g.splits) * kQ, head = blockIdx.y, b = blockIdx.z;
+  const int jb = split * g.tiles_per_split;                                  // first key tile of this CTA
+  const int T = min((g.HW + kK - 1) / kK, jb + g.tiles_per_split) - jb;      // its number of key tiles (>= 1)
 
   if (warp == 0 && lane == 0) {
     mbar_init(qdo_full, 1);
@@ -169,7 +175,7 @@ masked_xattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
         mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
         uint8_t* s = sKV + st * kStage;
         mbar_arrive_expect_tx(&kv_full[st], kStage);
-        const int key0 = j * kK;
+        const int key0 = (jb + j) * kK;
         tma_load_3d(s, &tmKh, &kv_full[st], head * 32, key0, b);
         tma_load_3d(s + kKBytes, &tmKl, &kv_full[st], head * 32, key0, b);
         tma_load_3d(s + 2 * kKBytes, &tmVh, &kv_full[st], head * 32, key0, b);
@@ -237,9 +243,9 @@ masked_xattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
 
     for (int j = 0; j < T; ++j) {
       const int st = j & 1;
-      const int key0 = j * kK + 32 * h;
+      const int key0 = (jb + j) * kK + 32 * h;
       uint32_t w = 0u;
-      if (!open) w = brow[2 * j + h];
+      if (!open) w = brow[2 * (jb + j) + h];
       if (key0 + 32 > g.HW) w |= (key0 >= g.HW) ? 0xFFFFFFFFu : (0xFFFFFFFFu << (g.HW - key0));
       if (!q_ok) w = 0xFFFFFFFFu;                                  // padding rows contribute nothing
       mbar_wait(&sdp_full[st], (j >> 1) & 1);
@@ -272,7 +278,8 @@ masked_xattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
     tmem_ld_32x16(lane_addr + kTQ + 16 * h, v);
     tmem_ld_wait();
     if (q_ok) {
-      float* dst = g.dq + (static_cast<long long>(b) * g.Qt + q) * g.E + head * 32 + 16 * h;
+      float* base = g.splits == 1 ? g.dq : g.part_dq + static_cast<long long>(split) * g.B * g.Qt * g.E;
+      float* dst = base + (static_cast<long long>(b) * g.Qt + q) * g.E + head * 32 + 16 * h;
 #pragma unroll
       for (int i = 0; i < 16; i += 4)
         *reinterpret_cast<float4*>(dst + i) =
@@ -523,9 +530,30 @@ masked_xattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKh, const __gr
   }
 }
 
+// out[i] = sum_s part[s][i]: the key splits' partial dQ in a fixed order
+__global__ void __launch_bounds__(256)
+xattn_sum_splits_kernel(const float4* __restrict__ part, int splits, long long n4, float4* __restrict__ out) {
+  const long long i = blockIdx.x * 256ll + threadIdx.x;
+  if (i >= n4) return;
+  float4 a = __ldg(part + i);
+  for (int s = 1; s < splits; ++s) {
+    const float4 v = __ldg(part + s * n4 + i);
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  out[i] = a;
+}
+
 }  // namespace mpf
 
 extern "C" {
+
+int mpf_masked_xattn_bwd_f32_ex(const float* q_hi, const float* q_lo, const float* qt_hi, const float* qt_lo,
+                                const float* k_hi, const float* k_lo, const float* kt_hi, const float* kt_lo,
+                                const float* v_hi, const float* v_lo, const float* do_hi, const float* do_lo,
+                                const float* dot_hi, const float* dot_lo, const uint32_t* mask_bits,
+                                const uint8_t* row_open, const float* lse2, const float* delta, float* dq, float* dk,
+                                float* dv, int B, int Qt, int qt_ld, int HW, int heads, int head_dim, int mask_words,
+                                int key_splits, float* ws_dq, void* stream);
 
 int mpf_masked_xattn_bwd_f32(const float* q_hi, const float* q_lo, const float* qt_hi, const float* qt_lo,
                              const float* k_hi, const float* k_lo, const float* kt_hi, const float* kt_lo,
@@ -534,6 +562,18 @@ int mpf_masked_xattn_bwd_f32(const float* q_hi, const float* q_lo, const float* 
                              const uint8_t* row_open, const float* lse2, const float* delta, float* dq, float* dk,
                              float* dv, int B, int Qt, int qt_ld, int HW, int heads, int head_dim, int mask_words,
                              void* stream) {
+  return mpf_masked_xattn_bwd_f32_ex(q_hi, q_lo, qt_hi, qt_lo, k_hi, k_lo, kt_hi, kt_lo, v_hi, v_lo, do_hi, do_lo,
+                                     dot_hi, dot_lo, mask_bits, row_open, lse2, delta, dq, dk, dv, B, Qt, qt_ld, HW,
+                                     heads, head_dim, mask_words, 1, nullptr, stream);
+}
+
+int mpf_masked_xattn_bwd_f32_ex(const float* q_hi, const float* q_lo, const float* qt_hi, const float* qt_lo,
+                                const float* k_hi, const float* k_lo, const float* kt_hi, const float* kt_lo,
+                                const float* v_hi, const float* v_lo, const float* do_hi, const float* do_lo,
+                                const float* dot_hi, const float* dot_lo, const uint32_t* mask_bits,
+                                const uint8_t* row_open, const float* lse2, const float* delta, float* dq, float* dk,
+                                float* dv, int B, int Qt, int qt_ld, int HW, int heads, int head_dim, int mask_words,
+                                int key_splits, float* ws_dq, void* stream) {
   using namespace mpf;
   clear_error();
   MPF_REQUIRE(q_hi && q_lo && qt_hi && qt_lo && k_hi && k_lo && kt_hi && kt_lo && v_hi && v_lo && do_hi && do_lo &&
@@ -546,6 +586,12 @@ int mpf_masked_xattn_bwd_f32(const float* q_hi, const float* q_lo, const float* 
               HW, qt_ld, Qt);
   MPF_REQUIRE(mask_words >= 2 * ((HW + 63) / 64), "masked_xattn_bwd: mask_words too small");
   MPF_REQUIRE(heads <= 65535 && B <= 65535, "masked_xattn_bwd: grid too large");
+  const int Ta = (HW + xa::kK - 1) / xa::kK;
+  MPF_REQUIRE(key_splits >= 1 && key_splits <= Ta, "masked_xattn_bwd: key_splits (%d) must be in [1, %d key tiles]",
+              key_splits, Ta);
+  MPF_REQUIRE(key_splits == 1 || ws_dq, "masked_xattn_bwd: key_splits > 1 needs the dQ workspace");
+  const int tiles_per_split = (Ta + key_splits - 1) / key_splits;
+  const int splits = (Ta + tiles_per_split - 1) / tiles_per_split;
   const int E = heads * head_dim;
   const long long qs = static_cast<long long>(Qt) * E, ks = static_cast<long long>(HW) * E;
   CUtensorMap tq_h, tq_l, td_h, td_l, tk_h, tk_l, tv_h, tv_l, tkt_h, tkt_l;
@@ -570,12 +616,20 @@ int mpf_masked_xattn_bwd_f32(const float* q_hi, const float* q_lo, const float* 
   g.bits = mask_bits; g.row_open = row_open; g.lse2 = lse2; g.delta = delta; g.dq = dq; g.dk = dk; g.dv = dv;
   g.B = B; g.Qt = Qt; g.HW = HW; g.E = E; g.heads = heads; g.words = mask_words;
   g.inv_sqrt_d = 1.0f / sqrtf(static_cast<float>(head_dim));
+  g.splits = splits; g.tiles_per_split = tiles_per_split; g.part_dq = ws_dq;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  dim3 grid_a((Qt + xa::kQ - 1) / xa::kQ, heads, B);
+  dim3 grid_a(((Qt + xa::kQ - 1) / xa::kQ) * splits, heads, B);
   masked_xattn_bwd_dq_kernel<<<grid_a, xa::kThreads, xa::kSmem, st>>>(tq_h, tq_l, td_h, td_l, tk_h, tk_l, tv_h, tv_l,
                                                                       tkt_h, tkt_l, g);
   count_launch();
   if ((rc = finish_launch("masked_xattn_bwd_dq"))) return rc;
+  if (splits > 1) {
+    const long long n4 = static_cast<long long>(B) * Qt * E / 4;
+    xattn_sum_splits_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(ws_dq), splits, n4, reinterpret_cast<float4*>(dq));
+    count_launch();
+    if ((rc = finish_launch("masked_xattn_bwd_dq (split sum)"))) return rc;
+  }
   // ---- kernel B maps: K/V [128 x 32], Q/dO chunks [64 x 32], Q^T/dO^T atoms [32 d x 32 q]
   CUtensorMap bk_h, bk_l, bv_h, bv_l, bq_h, bq_l, bd_h, bd_l, bqt_h, bqt_l, bdt_h, bdt_l;
   if ((rc = make_tmap_f32_3d(&bk_h, k_hi, E, HW, B, E, ks, 32, xk::kKeys))) return rc;

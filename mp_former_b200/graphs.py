@@ -16,12 +16,17 @@ from . import _lib
 
 
 class GraphedStep:
-    def __init__(self, step_fn, example_inputs, params, warmup=3):
+    def __init__(self, step_fn, example_inputs, params, warmup=3, flat_grads=True):
         """``step_fn(inputs: dict[str, Tensor]) -> loss`` (scalar tensor); ``params``: parameters whose ``.grad`` the
-        step produces.  ``example_inputs`` fixes shapes / dtypes / device."""
+        step produces.  ``example_inputs`` fixes shapes / dtypes / device.
+
+        ``flat_grads``: the parameters' ``.grad`` tensors are views of ONE flat buffer (``self.flat_grad``) that the
+        captured step zeroes and accumulates into, so the data-parallel exchange is a single in-place all-reduce of
+        that buffer -- no flatten / unflatten copies around it (DistributedDataParallel's ``gradient_as_bucket_view``)."""
         self.params = [p for p in params if p.requires_grad]
         self.static_in = {k: v.detach().clone() for k, v in example_inputs.items()}
         dev = next(iter(self.static_in.values())).device
+        self.flat_grad = None
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):                       # warm-up off the default stream, as capture requires
@@ -33,9 +38,17 @@ class GraphedStep:
         torch.cuda.synchronize(dev)
         for p in self.params:
             p.grad = None
+        if flat_grads and self.params and all(p.dtype == self.params[0].dtype for p in self.params):
+            self.flat_grad = torch.zeros(sum(p.numel() for p in self.params), dtype=self.params[0].dtype, device=dev)
+            off = 0
+            for p in self.params:
+                p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+                off += p.numel()
         self.graph = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
         with torch.cuda.graph(self.graph):
+            if self.flat_grad is not None:
+                self.flat_grad.zero_()                       # AccumulateGrad then adds in place into the views
             self.static_loss = step_fn(self.static_in)
             self.static_loss.backward()
         self.launches_per_replay = _lib.launch_count() - n0     # kernels of this library inside the graph
@@ -55,12 +68,16 @@ class GraphedStep:
         return self.replay()
 
 
-def allreduce_gradients(params, world_size):
+def allreduce_gradients(params, world_size, flat=None):
     """Data-parallel gradient exchange of the path (its only collective): ONE flat all-reduce of all
     gradients, averaged over ranks like DistributedDataParallel.  Used after a graph replay, where DDP's autograd
-    hooks do not run."""
+    hooks do not run.  ``flat``: the buffer the gradients are views of (``GraphedStep.flat_grad``): reduced in place."""
     import torch.distributed as dist
     if world_size == 1:
+        return
+    if flat is not None:
+        dist.all_reduce(flat)
+        flat.div_(world_size)
         return
     grads = [p.grad for p in params if p.grad is not None]
     flat = torch._utils._flatten_dense_tensors(grads)

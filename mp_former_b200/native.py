@@ -569,6 +569,20 @@ def unpack_bits(bits, n):
     return b.flatten(-2)[..., :n]
 
 
+XATTN_KEY_SPLITS = int(os.environ.get("MPF_XATTN_KEY_SPLITS", "0"))     # 0 = automatic; A/B measurements
+
+
+def xattn_key_splits(B, Qt, HW, heads):
+    """How many CTAs share the key tiles of one (query tile, head, image): as many as it takes to give every one of the
+    148 SMs a CTA (the fused attention kernels keep ONE 190 KB CTA per SM), never more than there are 64-key tiles.
+    B = 16: 128 CTAs -> 1 (unsplit); B = 2 (BASELINE configs[2] per GPU): 16 CTAs -> 9."""
+    tiles = (HW + 63) // 64
+    if XATTN_KEY_SPLITS > 0:
+        return max(1, min(XATTN_KEY_SPLITS, tiles))
+    ctas = B * heads * ((Qt + 127) // 128)
+    return max(1, min(tiles, 148 // max(1, ctas)))
+
+
 def masked_xattn_fwd(q_hi, q_lo, k_hi, k_lo, vt_hi, vt_lo, bits, row_open, heads):
     """Fused masked cross-attention forward.  Returns (out [B,Qt,E], lse2 [B,heads,Qt])."""
     B, Qt, E = q_hi.shape
@@ -584,13 +598,19 @@ def masked_xattn_fwd(q_hi, q_lo, k_hi, k_lo, vt_hi, vt_lo, bits, row_open, heads
     bits = bits.contiguous()
     if row_open is not None:
         row_open = row_open.to(torch.uint8).contiguous()
+    splits = xattn_key_splits(B, Qt, HW, heads)
+    ws_o = ws_ml = None
+    if splits > 1:
+        ws_o = torch.empty((splits, B, Qt, E), dtype=torch.float32, device=q_hi.device)
+        ws_ml = torch.empty((splits, B, heads, Qt, 2), dtype=torch.float32, device=q_hi.device)
     # algorithmic: QK^T and PV (2 * Qt * HW * hd flop each per head); bytes: K, V^T hi+lo read once + mask bits
     with torch.cuda.device(q_hi.device), _Timed("masked_xattn_fwd", 4.0 * B * Qt * HW * E,
                                                 4.0 * B * HW * E * 4 + B * Qt * HW / 8.0):
-        rc = _lib.load().mpf_masked_xattn_fwd_f32(
+        rc = _lib.load().mpf_masked_xattn_fwd_f32_ex(
             q_hi.data_ptr(), q_lo.data_ptr(), k_hi.data_ptr(), k_lo.data_ptr(), vt_hi.data_ptr(),
             vt_lo.data_ptr(), bits.data_ptr(), None if row_open is None else row_open.data_ptr(),
-            out.data_ptr(), lse2.data_ptr(), B, Qt, HW, heads, E // heads, bits.shape[2], _stream())
+            out.data_ptr(), lse2.data_ptr(), B, Qt, HW, heads, E // heads, bits.shape[2], splits,
+            None if ws_o is None else ws_o.data_ptr(), None if ws_ml is None else ws_ml.data_ptr(), _stream())
     _lib.check(rc, "masked_xattn_fwd")
     return out, lse2
 
@@ -750,13 +770,16 @@ def masked_xattn_bwd(q_hi, q_lo, k_hi, k_lo, kt_hi, kt_lo, v_hi, v_lo, d_o, bits
             raise RuntimeError("masked_xattn_bwd: operands must be contiguous")
     bits = bits.contiguous()
     lse2, delta = lse2.contiguous(), delta.contiguous()
+    splits = xattn_key_splits(B, Qt, HW, heads)
+    ws_dq = torch.empty((splits, B, Qt, E), dtype=torch.float32, device=q_hi.device) if splits > 1 else None
     # algorithmic: S recomputed twice, dP, dQ, dK, dV (2 * Qt * HW * hd flop each per head)
     with torch.cuda.device(q_hi.device), _Timed("masked_xattn_bwd", 12.0 * B * Qt * HW * E,
                                                 4.0 * B * HW * E * 8 + B * Qt * HW / 8.0):
-        rc = _lib.load().mpf_masked_xattn_bwd_f32(
+        rc = _lib.load().mpf_masked_xattn_bwd_f32_ex(
             *[t.data_ptr() for t in ts], bits.data_ptr(), None if ro is None else ro.data_ptr(),
             lse2.data_ptr(), delta.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
-            B, Qt, qt_ld, HW, heads, E // heads, bits.shape[2], _stream())
+            B, Qt, qt_ld, HW, heads, E // heads, bits.shape[2], splits,
+            None if ws_dq is None else ws_dq.data_ptr(), _stream())
     _lib.check(rc, "masked_xattn_bwd")
     return dq, dk, dv
 
@@ -911,6 +934,62 @@ def point_sample_rows_bwd(grad_map_ptrs, hw, coords, grad_out):
         rc = _lib.load().mpf_point_sample_rows_bwd_f32(grad_map_ptrs.data_ptr(), int(hw[0]), int(hw[1]),
                                                        coords.data_ptr(), R, P, grad_out.data_ptr(), _stream())
     _lib.check(rc, "point_sample_rows_bwd")
+
+
+SELF_ATTN_MAX_Q = 320
+
+
+def self_attn_fwd(qkv, mask_u8, heads):
+    """qkv [B, Qt, 3E] f32, mask_u8 uint8 [Qt, Qt] or None (1 = not allowed) -> (out [B, Qt, E], lse [B, heads, Qt])."""
+    _f32c(qkv, "qkv")
+    B, Qt, E3 = qkv.shape
+    E = E3 // 3
+    if not qkv.is_contiguous() or E3 != 3 * E or E % heads or E // heads != 32 or Qt > SELF_ATTN_MAX_Q:
+        raise RuntimeError(f"self_attn: unsupported geometry {tuple(qkv.shape)}, {heads} heads")
+    if mask_u8 is not None and (mask_u8.dtype != torch.uint8 or mask_u8.shape != (Qt, Qt) or not mask_u8.is_contiguous()):
+        raise RuntimeError("self_attn: mask must be a contiguous uint8 [Qt, Qt] tensor")
+    out = torch.empty((B, Qt, E), dtype=torch.float32, device=qkv.device)
+    lse = torch.empty((B, heads, Qt), dtype=torch.float32, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        rc = _lib.load().mpf_self_attn_fwd_f32(qkv.data_ptr(), None if mask_u8 is None else mask_u8.data_ptr(), B, Qt,
+                                               heads, 32, out.data_ptr(), lse.data_ptr(), _stream())
+    _lib.check(rc, "self_attn_fwd")
+    return out, lse
+
+
+def self_attn_bwd(qkv, mask_u8, d_out, lse, heads):
+    """-> d_qkv [B, Qt, 3E]"""
+    _f32c(d_out, "d_out")
+    B, Qt, E3 = qkv.shape
+    d_out = d_out.contiguous()
+    d_qkv = torch.empty_like(qkv)
+    with torch.cuda.device(qkv.device):
+        rc = _lib.load().mpf_self_attn_bwd_f32(qkv.data_ptr(), None if mask_u8 is None else mask_u8.data_ptr(),
+                                               d_out.data_ptr(), lse.data_ptr(), B, Qt, heads, 32, d_qkv.data_ptr(),
+                                               _stream())
+    _lib.check(rc, "self_attn_bwd")
+    return d_qkv
+
+
+TOPK_GATHER_MAX_N = 49152
+
+
+def topk_gather_rows(scores, payload, k):
+    """scores [R, n] f32, payload [R, n, w] f32 (w = 1 or 2) -> payload rows of the k largest scores of every row,
+    [R, k, w], in ascending index order (ref criterion.py:165-172: the most uncertain candidate points)."""
+    _f32c(scores, "scores")
+    _f32c(payload, "payload")
+    R, n = scores.shape
+    w = payload.shape[-1]
+    if payload.shape != (R, n, w) or w not in (1, 2) or not 0 < k <= n <= TOPK_GATHER_MAX_N:
+        raise RuntimeError(f"topk_gather_rows: unsupported shapes {tuple(scores.shape)} / {tuple(payload.shape)}, k={k}")
+    scores, payload = scores.contiguous(), payload.contiguous()
+    out = torch.empty((R, k, w), dtype=torch.float32, device=scores.device)
+    with torch.cuda.device(scores.device):
+        rc = _lib.load().mpf_topk_gather_rows_f32(scores.data_ptr(), R, n, k, payload.data_ptr(), w, out.data_ptr(),
+                                                  _stream())
+    _lib.check(rc, "topk_gather_rows")
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -7,9 +7,10 @@ mixed-major products), ``attn_mask_from_logits`` on the bit-packed mask kernels,
 fused attention forward and the two backward kernels that recompute the probabilities from the saved log-sum-exp,
 ``add_layer_norm`` / ``group_norm_*`` / ``upsample2x_add_*`` on the row-wise and FPN-stage kernels.
 ``grad_fanout`` / ``collect_mask_heads`` are autograd plumbing that lets the ten prediction heads share one batched
-backward.  ``self_attention`` over the few hundred queries and the query-side layers stay on library ops
-(launch-latency bound); ``conv2d_fp32`` pins the library convolution used for uncovered
-geometries to true fp32 in both directions.
+backward.  ``self_attention`` over the few hundred queries runs its projections on the GEMMs and its [Q x Q] core on
+the fp32 kernels of csrc/self_attn.cu; ``conv2d_fp32`` pins the library convolution used for
+uncovered geometries to true fp32 in both directions.  Ops whose geometry may leave the native kernels record the
+route they took in ``ROUTES``.
 
 Inputs must be CUDA fp32 tensors; there is no CPU path.
 """
@@ -26,7 +27,9 @@ from . import _lib, native
 NATIVE_OPS = {"ms_deform_attn_forward", "ms_deform_attn_backward", "linear fwd+bwd (bf16x3 tcgen05 GEMM, TMA in/out)",
               "conv3x3 fwd+bwd (bf16x3 tcgen05 GEMM, taps as shifted TMA boxes)",
               "mask_logits fwd+bwd (bf16x3 / 3xTF32 tcgen05 GEMM)", "attn_mask_bits", "gt_mask_area_bits",
-              "masked_cross_attention fwd+bwd (tcgen05)"}
+              "masked_cross_attention fwd+bwd (tcgen05, key-split for small batches)",
+              "self_attention core fwd+bwd (fp32 CUDA cores)", "topk_gather_rows (radix select)",
+              "match_cost / lsap (Hungarian matcher)", "point_sample_rows fwd+bwd"}
 
 # fp32 ``sigmoid(x) < 0.5`` as evaluated by the reference (1/(1+exp(-x)) with a correctly rounded exp)
 # is EXACTLY ``x <= -0x1.7ffffep-23``: for -1.788e-7 < x < 0 the sigmoid rounds to 0.5 and the key stays
@@ -86,17 +89,28 @@ class _Linear(torch.autograd.Function):
             g2 = g2 * (y > 0)
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            if _route("linear.input_grad", weight.shape[0] % 32 == 0, f"out_features {weight.shape[0]} % 32 != 0"):
+            n_out = weight.shape[0]
+            if n_out % 32 == 0:
                 wt_hi, wt_lo = native.split_b(weight.t().contiguous())
                 gx = native.gemm(g2.contiguous(), wt_hi, wt_lo)
             else:
-                gx = g2 @ weight
+                # e.g. class_embed (81 outputs): the reduction dimension of the input-gradient GEMM is zero-padded to a
+                # multiple of 32 (exact) instead of leaving the path for a library matmul
+                pad = (-n_out) % 32
+                wt_hi, wt_lo = native.split_b(F.pad(weight, (0, 0, 0, pad)).t().contiguous())
+                gx = native.gemm(F.pad(g2, (0, pad)), wt_hi, wt_lo)
+            ROUTES["linear.input_grad:native"] += 1
             gx = gx.view(*gy.shape[:-1], weight.shape[1])
         if ctx.needs_input_grad[1]:
-            if _route("linear.weight_grad", g2.shape[1] % 4 == 0 and x2.shape[1] % 4 == 0,
-                      f"features ({g2.shape[1]}, {x2.shape[1]}) not multiples of 4"):
+            if g2.shape[1] % 4 == 0 and x2.shape[1] % 4 == 0:
                 gw = native.matmul_tn(g2.contiguous(), x2)      # dW = dY^T X on the tensor cores, no transposes
+                ROUTES["linear.weight_grad:native"] += 1
+            elif x2.shape[1] % 4 == 0:
+                pad = (-g2.shape[1]) % 4                         # zero columns of dY -> zero rows of dW, sliced away
+                gw = native.matmul_tn(F.pad(g2, (0, pad)), x2)[:g2.shape[1]]
+                ROUTES["linear.weight_grad:native"] += 1
             else:
+                _route("linear.weight_grad", False, f"in_features {x2.shape[1]} % 4 != 0")
                 gw = g2.t() @ x2
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = native.colsum(g2)
@@ -965,22 +979,54 @@ def masked_cross_attention(q_in, memory, pos, w_in, b_in, w_out, b_out, nhead, m
                                        w_out, b_out, nhead, bits, n_keys)
 
 
+class _SelfAttnCore(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, mask_u8, nhead):
+        out, lse = native.self_attn_fwd(qkv, mask_u8, nhead)
+        ctx.save_for_backward(qkv, lse)
+        ctx.mask_u8, ctx.nhead = mask_u8, nhead
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        qkv, lse = ctx.saved_tensors
+        return native.self_attn_bwd(qkv, ctx.mask_u8, g, lse, ctx.nhead), None, None
+
+
+_MASK_U8 = {}
+
+
+def _mask_u8(tgt_mask):
+    """bool [Q, Q] -> uint8 copy, cached per mask tensor (the decoder builds one tgt_mask per forward and hands it to
+    all nine layers)."""
+    key = (tgt_mask.data_ptr(), tuple(tgt_mask.shape), tgt_mask._version)
+    hit = _MASK_U8.get(key)
+    if hit is None or hit[0] is not tgt_mask:
+        _MASK_U8.clear()
+        hit = (tgt_mask, tgt_mask.to(torch.uint8).contiguous())
+        _MASK_U8[key] = hit
+    return hit[1]
+
+
 def self_attention(qk_in, v_in, w_in, b_in, w_out, b_out, nhead, tgt_mask=None):
     """nn.MultiheadAttention self-attention over the (few hundred) queries (ref decoder :42-52); tgt_mask
-    bool [Q,Q], True = not allowed (DN groups, ref decoder :1051-1059).  Projections on the tensor-core
-    GEMM; the [Q x Q] attention itself is a library SDPA call (launch-latency bound)."""
+    bool [Q,Q], True = not allowed (DN groups, ref decoder :1051-1059).  Projections on the tensor-core GEMM, the
+    [Q x Q] core on the fp32 kernels of csrc/self_attn.cu (head dim 32, Q <= 320; other geometries: library SDPA,
+    recorded in ROUTES)."""
     _cuda_only(qk_in, "tgt")
     E = qk_in.shape[-1]
     if qk_in is v_in:                                              # no query_pos: one GEMM for q, k and v
         qkv = linear(qk_in, w_in, b_in)
-        q, k, v = qkv[..., :E], qkv[..., E:2 * E], qkv[..., 2 * E:]
     else:
-        qk = linear(qk_in, w_in[:2 * E], b_in[:2 * E])             # q and k share the input
-        q, k = qk[..., :E], qk[..., E:]
-        v = linear(v_in, w_in[2 * E:], b_in[2 * E:])
-    allowed = None if tgt_mask is None else ~tgt_mask
-    ROUTES["self_attention.core:library"] += 1      # [Q x Q] core: library SDPA (projections are native GEMMs)
-    o = F.scaled_dot_product_attention(_split_heads(q, nhead), _split_heads(k, nhead),
-                                       _split_heads(v, nhead), attn_mask=allowed)
-    o = o.transpose(1, 2).reshape(qk_in.shape)
+        qkv = torch.cat([linear(qk_in, w_in[:2 * E], b_in[:2 * E]),      # q and k share the input
+                         linear(v_in, w_in[2 * E:], b_in[2 * E:])], -1)
+    if _route("self_attention.core", qkv.dim() == 3 and E // nhead == 32 and E % nhead == 0
+              and qkv.shape[1] <= native.SELF_ATTN_MAX_Q and qkv.dtype == torch.float32,
+              f"head_dim {E // nhead} / {qkv.shape[1]} queries"):
+        o = _SelfAttnCore.apply(qkv.contiguous(), None if tgt_mask is None else _mask_u8(tgt_mask), nhead)
+    else:
+        q, k, v = qkv[..., :E], qkv[..., E:2 * E], qkv[..., 2 * E:]
+        o = F.scaled_dot_product_attention(_split_heads(q, nhead), _split_heads(k, nhead), _split_heads(v, nhead),
+                                           attn_mask=None if tgt_mask is None else ~tgt_mask)
+        o = o.transpose(1, 2).reshape(qk_in.shape)
     return linear(o, w_out, b_out)

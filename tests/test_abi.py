@@ -47,8 +47,8 @@ def test_matcher_and_sampler_entry_points_validate_arguments_without_a_gpu():
     # workspace: S point splits x (3 sums per (query, target) + one per (image, query) + one per target)
     B, Q, ntot, nmax, P = 16, 100, 156, 20, 12544
     ws = lib.mpf_match_cost_workspace_bytes(B, Q, ntot, nmax, P)
-    qtiles, ttiles, nchunks = 2, 1, 98
-    S = min(nchunks, -(-2 * 148 // (B * qtiles * ttiles)))
+    qtiles, ttiles, nchunks = 2, 1, 196                       # 64 queries x 32 targets per CTA, chunks of 64 points
+    S = min(nchunks, max(1, 3 * 148 // (B * qtiles * ttiles)))  # one wave of 148 SMs x 3 resident CTAs
     assert ws == (S * Q * ntot * 3 + S * B * Q + S * ntot + 4) * 4
     assert lib.mpf_match_cost_workspace_bytes(0, Q, ntot, nmax, P) == -1
     args = [None, 0, 0, 81, None, 0, 0, 256, 256, None, 0, 1024, 1024, None, None, ntot, nmax, None, B, Q, P,

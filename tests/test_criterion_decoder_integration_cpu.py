@@ -33,6 +33,7 @@ def test_decoder_outputs_through_criterion_and_back(monkeypatch):
     install_cpu_ops(monkeypatch.setattr)
     monkeypatch.setattr(native, "point_sample_rows", T._emu_sample)
     monkeypatch.setattr(native, "point_sample_rows_bwd", T._emu_sample_bwd)
+    monkeypatch.setattr(native, "topk_gather_rows", T._emu_topk_gather)
     dec = build_decoder().train()
     x, mf = cases.decoder_inputs()
     targets = cases.dn_targets()

@@ -1,6 +1,6 @@
 """CPU: host logic of the device criterion (mp_former_b200/criterion.py) against the golden losses of the UNMODIFIED
-reference SetCriterion.  The two CUDA entry points it calls (native.point_sample_rows / point_sample_rows_bwd, which
-address maps through device-pointer tables) are replaced -- in this test only -- by an emulation that reads / updates
+reference SetCriterion.  The CUDA entry points it calls (native.point_sample_rows / point_sample_rows_bwd, which
+address maps through device-pointer tables, and native.topk_gather_rows) are replaced -- in this test only -- by an emulation that reads / updates
 the same addresses in host memory with torch's grid_sample, so that everything else (index bookkeeping, pointer
 arithmetic, random-number consumption, dn assignment, loss keys and normalisation) is exercised without a GPU.  The
 kernels themselves are covered by tests/test_gpu_h_criterion.py."""
@@ -41,6 +41,12 @@ def _emu_sample_bwd(grad_map_ptrs, hw, coords, grad_out):
         _host_map(p, True, H, W)[...] += z.grad[0, 0].numpy()
 
 
+def _emu_topk_gather(scores, payload, k):
+    """native.topk_gather_rows: payload rows of the k largest scores per row, ascending index order."""
+    idx = scores.topk(k, dim=1).indices.sort(dim=1).values
+    return torch.gather(payload, 1, idx.unsqueeze(-1).expand(-1, -1, payload.shape[-1]))
+
+
 class _OracleMatcher(torch.nn.Module):
     """Reference-contract matcher (list of CPU index pairs) for the host-logic test."""
 
@@ -61,6 +67,7 @@ def host_kernels(monkeypatch):
     monkeypatch.setattr(_lib, "require_cuda", lambda t, name: None)
     monkeypatch.setattr(native, "point_sample_rows", _emu_sample)
     monkeypatch.setattr(native, "point_sample_rows_bwd", _emu_sample_bwd)
+    monkeypatch.setattr(native, "topk_gather_rows", _emu_topk_gather)
 
 
 def _criterion(no_lb=False):

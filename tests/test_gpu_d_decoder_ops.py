@@ -105,6 +105,40 @@ def test_masked_cross_attention_forward_backward(B, Qt, HW):
     assert torch.equal(y2, y.detach())
 
 
+@pytest.mark.parametrize("B,Qt,HW,splits", [(2, 120, 4096, 1), (2, 120, 4096, 5), (2, 120, 4096, 64), (1, 130, 950, 3),
+                                            (2, 9, 16384, 9)])
+def test_masked_cross_attention_key_splits_agree(monkeypatch, B, Qt, HW, splits):
+    """The key-split path (small batches: every (query tile, head, image) spread over several CTAs, log-sum-exp merge
+    of the partial outputs, fixed-order sum of the partial dQ) against the unsplit kernels on identical inputs,
+    including rows whose open keys all fall into ONE split and splits that are fully masked for a row."""
+    E, nhead = 256, 8
+    g = torch.Generator(device=DEV).manual_seed(B * 77 + Qt + HW + splits)
+    rn = lambda *s, sc=1.0: torch.randn(*s, device=DEV, generator=g) * sc
+    q_in, memory, pos = rn(B, Qt, E), rn(B, HW, E), rn(1, HW, E)
+    w_in, b_in = rn(3 * E, E, sc=1 / 16), rn(3 * E, sc=0.1)
+    w_out, b_out = rn(E, E, sc=1 / 16), rn(E, sc=0.1)
+    mask = torch.rand(B, Qt, HW, device=DEV, generator=g) < 0.9
+    mask[0, 0] = True                                   # fully masked row
+    mask[0, 1] = True
+    mask[0, 1, HW - 3] = False                          # a single open key, in the last split
+    mask[0, 2] = True
+    mask[0, 2, : min(64, HW)] = False                   # open keys only in the first key tile
+    gy = rn(B, Qt, E)
+    res = {}
+    for tag, ks in (("unsplit", 1), ("split", splits)):
+        monkeypatch.setattr(native, "XATTN_KEY_SPLITS", ks)
+        leaves = [t.clone().requires_grad_(True) for t in (q_in, memory, w_in, b_in, w_out, b_out)]
+        y = ops.masked_cross_attention(leaves[0], leaves[1], pos, leaves[2], leaves[3], leaves[4], leaves[5], nhead,
+                                       ops.PackedMask.from_bool(mask))
+        y.backward(gy)
+        res[tag] = [y.detach()] + [t.grad for t in leaves]
+    for a, b_ in zip(res["split"], res["unsplit"]):
+        assert torch.isfinite(a).all()
+        # both paths sit ~1e-5 .. 4e-5 (relative to the largest entry) from the fp64 result: 3xTF32 products summed in
+        # a different order (benchmarks/debug_xattn_split.py prints both against fp64)
+        assert (a - b_).abs().max().item() <= 2e-4 * max(1.0, b_.abs().max().item())
+
+
 def test_linear_and_mask_logits_autograd():
     g = torch.Generator(device=DEV).manual_seed(3)
     x = torch.randn(2, 300, 256, device=DEV, generator=g, requires_grad=True)
@@ -459,3 +493,37 @@ def test_upsample2x_add_channels_last(B, C, H, W):
     (cr + F.interpolate(pr, size=(H, W), mode="bilinear", align_corners=False)).backward(gy.double())
     assert rel(cur.grad, cr.grad) < 1e-6
     assert rel(prev.grad, pr.grad) < 1e-5
+
+
+@pytest.mark.parametrize("B,Qt,with_mask", [(2, 120, True), (1, 100, False), (3, 7, True), (2, 320, True), (1, 33, False)])
+def test_self_attention_core_forward_backward(B, Qt, with_mask):
+    """csrc/self_attn.cu through ops.self_attention against nn.MultiheadAttention's arithmetic in fp64 (oracle mha),
+    with the block mask of the mask-piloted groups (ref decoder :1051-1059)."""
+    E, nhead = 256, 8
+    g = torch.Generator(device=DEV).manual_seed(B * 31 + Qt)
+    rn = lambda *s, sc=1.0: torch.randn(*s, device=DEV, generator=g) * sc
+    x = rn(B, Qt, E)
+    w_in, b_in, w_out, b_out = rn(3 * E, E, sc=1 / 16), rn(3 * E, sc=0.1), rn(E, E, sc=1 / 16), rn(E, sc=0.1)
+    mask = None
+    if with_mask:
+        pad = max(1, Qt // 6)
+        mask = torch.zeros(Qt, Qt, dtype=torch.bool, device=DEV)
+        mask[pad:, :pad] = True                                    # matching queries do not see the dn group
+        mask[: pad // 2, pad // 2:pad] = True
+    leaves = [t.clone().requires_grad_(True) for t in (x, w_in, b_in, w_out, b_out)]
+    before = dict(ops.ROUTES)
+    y = ops.self_attention(leaves[0], leaves[0], leaves[1], leaves[2], leaves[3], leaves[4], nhead, mask)
+    assert ops.ROUTES["self_attention.core:native"] == before.get("self_attention.core:native", 0) + 1
+    gy = rn(B, Qt, E)
+    y.backward(gy)
+    ref = [t.double().clone().requires_grad_(True) for t in (x, w_in, b_in, w_out, b_out)]
+    sd = {"in_proj_weight": ref[1], "in_proj_bias": ref[2], "out_proj.weight": ref[3], "out_proj.bias": ref[4]}
+    am = None if mask is None else mask[None].expand(B * nhead, -1, -1)
+    xr = ref[0].transpose(0, 1)
+    yr = O.mha(sd, "", xr, xr, xr, nhead, am).transpose(0, 1)
+    yr.backward(gy.double())
+    assert rel(y, yr) < TOL, rel(y, yr)
+    for name, a, b_ in zip(("x", "w_in", "b_in", "w_out", "b_out"), leaves, ref):
+        scale = b_.grad.abs().max().item()
+        err = (a.grad.double() - b_.grad).abs().max().item() / max(scale, 1e-6)
+        assert err < 2 * TOL, (name, err)

@@ -181,3 +181,29 @@ def test_criterion_failed_assignment_is_memory_safe_and_reported(fault):
     good = crit(o2, t2)
     assert all(bool(torch.isfinite(v)) for v in good.values())
     crit.check_status()
+
+
+@pytest.mark.parametrize("R,n,k,w", [(7, 37632, 9408, 2), (3, 1000, 1, 2), (2, 4096, 4096, 1), (5, 777, 300, 2),
+                                     (1, 49152, 12345, 1)])
+def test_topk_gather_rows_selects_the_same_set_as_torch_topk(R, n, k, w):
+    from mp_former_b200 import native
+    g = torch.Generator(device="cuda").manual_seed(R * 1000 + k)
+    scores = -torch.randn(R, n, device="cuda", generator=g).abs()          # the criterion's -|logit|
+    scores[0, : n // 7] = scores[0, 0]                                     # a block of exact ties (crosses the threshold
+    scores[-1, 5] = float("inf")                                           #  for some parameter sets), +inf and NaN
+    scores[-1, 9 % n] = float("nan")
+    payload = torch.randn(R, n, w, device="cuda", generator=g)
+    payload[..., 0] = torch.arange(n, device="cuda")                      # channel 0 carries the index (exact in fp32)
+    got = native.topk_gather_rows(scores, payload, k)
+    assert got.shape == (R, k, w)
+    ref_idx = scores.topk(k, dim=1).indices
+    for r in range(R):
+        sel_vals = torch.sort(torch.nan_to_num(scores[r][ref_idx[r]], nan=float("inf"))).values
+        idx = got[r, :, 0].long()
+        assert bool(((idx >= 0) & (idx < n)).all()), (r, idx[:8])
+        assert torch.equal(got[r], payload[r][idx])                        # whole payload rows were gathered
+        assert bool((idx[1:] > idx[:-1]).all()), (r, idx[:8])              # ascending index order, no duplicates
+        mine = torch.sort(torch.nan_to_num(scores[r][idx], nan=float("inf"))).values
+        assert torch.equal(mine, sel_vals), (r, mine[:4], sel_vals[:4])    # same multiset of scores as torch.topk
+    again = native.topk_gather_rows(scores, payload, k)
+    assert torch.equal(again, got)                                         # deterministic

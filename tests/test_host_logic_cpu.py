@@ -55,6 +55,14 @@ def install_cpu_ops(setattr_fn):
                   nhead, am)
         return y.transpose(0, 1)
 
+    def self_attn(qk_in, v_in, w_in, b_in, w_out, b_out, nhead, tgt_mask=None):
+        sd = {"in_proj_weight": w_in, "in_proj_bias": b_in, "out_proj.weight": w_out, "out_proj.bias": b_out}
+        B = qk_in.shape[0]
+        am = None if tgt_mask is None else tgt_mask[None].expand(B * nhead, -1, -1)
+        return O.mha(sd, "", qk_in.transpose(0, 1), qk_in.transpose(0, 1), v_in.transpose(0, 1), nhead,
+                     am).transpose(0, 1)
+
+    setattr_fn(ops, "self_attention", self_attn)
     setattr_fn(MSDA, "ms_deform_attn_forward", fwd)
     setattr_fn(MSDA, "enc_supported", lambda value, L, P: False)       # CPU: exercise the unfused module path
     setattr_fn(_lib, "require_cuda", lambda t, n: None)
