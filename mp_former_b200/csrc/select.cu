@@ -16,6 +16,7 @@ constexpr int kSelMaxN = 49152;                 // keys of one row in shared mem
 
 __device__ __forceinline__ unsigned sel_key(float f) {     // order-preserving: larger float <=> larger key
   const unsigned u = __float_as_uint(f);
+  if ((u & 0x7FFFFFFFu) > 0x7F800000u) return 0xFFFFFFFFu;            // NaN of either sign ranks first (torch.topk)
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 

@@ -78,7 +78,7 @@ class HungarianMatcher(nn.Module):
     reference (matcher.py:153-156), or on the device with ``device_indices=True``."""
 
     def __init__(self, cost_class: float = 1, cost_mask: float = 1, cost_dice: float = 1, num_points: int = 0,
-                 device_indices: bool = False, sort_points: bool = True):
+                 device_indices: bool = False, sort_points=None):
         super().__init__()
         self.cost_class = cost_class
         self.cost_mask = cost_mask
@@ -90,7 +90,9 @@ class HungarianMatcher(nn.Module):
         # map once, row by row, instead of pulling a 32-byte DRAM sector per corner (the 419 MB of mask logits of a
         # head do not fit the L2).  Measured on the B200 with the round-2 cost kernel (profiles/r2f_matcher_probe*.json,
         # 16 images x 100 queries x 12544 points): 0.77 ms per head with the sort (argsort included) vs 1.10 ms
-        # without; same assignments.  The cost sums do not depend on the order beyond fp32 rounding.
+        # without; same assignments.  The cost sums do not depend on the order beyond fp32 rounding.  None (default):
+        # sort when the maps of a head exceed the L2 (>= 8 images' worth of 100 x 256 x 256 logits); for a couple of
+        # images the argsort costs more than the gathers it tidies.
         self.sort_points = sort_points
         self._packed_key = None
         self._packed = None
@@ -141,7 +143,10 @@ class HungarianMatcher(nn.Module):
         if point_coords is None:
             # all masks of an image share one set of points; drawn per image like the reference (matcher.py:120)
             point_coords = torch.cat([torch.rand(1, self.num_points, 2, device=dev) for _ in range(bs)])
-        if self.sort_points:
+        sort = self.sort_points
+        if sort is None:
+            sort = masks.numel() * masks.element_size() >= (200 << 20)
+        if sort:
             point_coords = self.row_major_order(point_coords, *masks.shape[-2:])
         logits = logits.float()                     # autocast heads: the costs are computed in fp32 (matcher.py:134-136)
         masks = masks.float()

@@ -198,12 +198,13 @@ def test_topk_gather_rows_selects_the_same_set_as_torch_topk(R, n, k, w):
     assert got.shape == (R, k, w)
     ref_idx = scores.topk(k, dim=1).indices
     for r in range(R):
-        sel_vals = torch.sort(torch.nan_to_num(scores[r][ref_idx[r]], nan=float("inf"))).values
+        inf = float("inf")
+        sel_vals = torch.sort(torch.nan_to_num(scores[r][ref_idx[r]], nan=inf, posinf=inf)).values
         idx = got[r, :, 0].long()
         assert bool(((idx >= 0) & (idx < n)).all()), (r, idx[:8])
         assert torch.equal(got[r], payload[r][idx])                        # whole payload rows were gathered
         assert bool((idx[1:] > idx[:-1]).all()), (r, idx[:8])              # ascending index order, no duplicates
-        mine = torch.sort(torch.nan_to_num(scores[r][idx], nan=float("inf"))).values
+        mine = torch.sort(torch.nan_to_num(scores[r][idx], nan=inf, posinf=inf)).values
         assert torch.equal(mine, sel_vals), (r, mine[:4], sel_vals[:4])    # same multiset of scores as torch.topk
     again = native.topk_gather_rows(scores, payload, k)
     assert torch.equal(again, got)                                         # deterministic
