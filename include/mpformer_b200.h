@@ -102,6 +102,14 @@ int mpf_msda_enc_backward_f32(const float* grad_out, const float* value, const i
  * Returns the previous setting.  Results agree to fp32 rounding (forward: bit for bit).  Same semantics as the
  * reference op either way (ref ops/src/cuda/ms_deform_im2col_cuda.cuh:242-304, :92-164).  Process-wide; meant for
  * A/B measurements and tests (also: environment MPF_MSDA_STAGED=1 at load time). */
+/* CTA-pair mode of mpf_gemm_bf16x3 / mpf_gemm_bf16x3_relubits / mpf_conv3x3_cl_bf16x3 (tcgen05 cta_group::2: clusters of two
+ * CTAs execute one M = 256 UMMA, each staging half of the B tile): 0 (default) = never, 1 = when a launch has at least
+ * one full wave of 256-row pair tiles, 2 = whenever the problem has two M tiles (tests).  mode < 0 only queries.
+ * Returns the previous mode.  Results are identical in every mode (same products, same accumulation order per
+ * element); measured SLOWER than single CTAs with the 3-MMA split arithmetic, hence off by default.
+ * Also: environment MPF_GEMM_PAIR at load time. */
+int mpf_gemm_bf16x3_set_pair_mode(int mode);
+
 int mpf_msda_set_staged(int enabled);
 
 /* Per-row top-k selection with payload gather: for every row r of scores [rows, n] (fp32, device) the k largest

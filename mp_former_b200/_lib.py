@@ -33,6 +33,7 @@ SIGNATURES = {
     "mpf_msda_enc_forward_f32": (_c_int, [_c_vp] * 5 + [_c_ll] + [_c_int] * 7 + [_c_vp, _c_vp, _c_vp]),
     "mpf_msda_enc_backward_f32": (_c_int, [_c_vp] * 6 + [_c_ll] + [_c_int] * 7 + [_c_vp, _c_vp, _c_vp, _c_vp]),
     "mpf_msda_set_staged": (_c_int, [_c_int]),
+    "mpf_gemm_bf16x3_set_pair_mode": (_c_int, [_c_int]),
     "mpf_self_attn_fwd_f32": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_vp]),
     "mpf_self_attn_bwd_f32": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
     "mpf_topk_gather_rows_f32": (_c_int, [_c_vp, _c_int, _c_int, _c_int, _c_vp, _c_int, _c_vp, _c_vp]),

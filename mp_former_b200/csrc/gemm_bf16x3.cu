@@ -97,6 +97,60 @@ __device__ __forceinline__ void bulk_wait_read() {
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
+// ---- CTA-pair ("cta_group::2") primitives: two CTAs of a cluster on the two SMs of a TPC execute one UMMA with
+// M = 256 (each CTA holds 128 rows of A and of the accumulator, and HALF of the B tile), so a CTA moves half the B
+// bytes through its shared memory per MMA.  Only the leader (cluster rank 0) issues MMAs; barriers that both CTAs feed
+// live in the leader and are reached through the shared::cluster window (rank bit 24 cleared).
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the LEADER's copy of `bar` (works from both CTAs of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask)
+               : "memory");
+}
+// TMA load into THIS CTA's shared memory whose bytes are counted on the LEADER's barrier
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                 int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0),
+      "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void mma_bf16_ss_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of all prior MMAs of the issuing thread -> arrive on `bar` in BOTH CTAs of the pair
+__device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(static_cast<uint16_t>(3))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {   // one warp in EACH CTA
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate.  One thread issues.
 __device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                             uint32_t accumulate) {
@@ -140,10 +194,13 @@ __device__ __forceinline__ float rn_tf32(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
+// kPair: the CTA-pair variant (launched as clusters of two CTAs).  A pair walks "pair tiles" of 256 rows: rank r
+// loads / converts / drains M tile 2 * pair_m + r and loads the B rows [r * BN/2, (r + 1) * BN/2) of the N tile.
+template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
-                   const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmC,
-                   const __grid_constant__ CUtensorMap tmClo, const Args g) {
+gemm_bf16x3_kernel_t(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+                     const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmC,
+                     const __grid_constant__ CUtensorMap tmClo, const Args g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int S = g.stages;
@@ -154,12 +211,18 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint64_t* empty = bars + 2 * kMaxStages;       // [S] MMAs reading the stage retired
   uint64_t* tfull = bars + 3 * kMaxStages;       // [2] accumulator complete
   uint64_t* tempty = bars + 3 * kMaxStages + 2;  // [2] accumulator drained by the epilogue
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kMaxStages + 4);
+  uint64_t* fullA = bars + 3 * kMaxStages + 4;   // [S] pair mode: this CTA's raw A tile landed (full = B of both CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * kMaxStages + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int BN = g.bn;
-  const int b_bytes = BN * kBK * 2;              // one of B_hi / B_lo per stage
+  const int rank = kPair ? static_cast<int>(cluster_ctarank()) : 0;
+  const int b_rows = kPair ? BN / 2 : BN;        // B rows this CTA holds
+  const int b_bytes = b_rows * kBK * 2;          // one of B_hi / B_lo per stage
+  const int worker = kPair ? blockIdx.x >> 1 : blockIdx.x;        // index of this CTA (pair) in the persistent loop
+  const int workers = kPair ? gridDim.x >> 1 : gridDim.x;
+  const int tiles_m = kPair ? (g.tiles_m + 1) / 2 : g.tiles_m;     // pair tiles along M
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -168,22 +231,25 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     prefetch_tmap(&tmC);
     for (int s = 0; s < S; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&conv[s], 4);
+      mbar_init(&conv[s], kPair ? 8 : 4);          // pair mode: the converter warps of BOTH CTAs arrive at the leader
       mbar_init(&empty[s], 1);
+      mbar_init(&fullA[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 8);
+      mbar_init(&tempty[a], kPair ? 16 : 8);
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == 2) {
+    if (kPair) tmem_alloc_pair(tmem_slot, kTmemCols); else tmem_alloc(tmem_slot, kTmemCols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();   // barriers of BOTH CTAs exist before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_tiles = g.batch * g.k_splits * g.tiles_m * g.tiles_n;
+  const int num_tiles = g.batch * g.k_splits * tiles_m * g.tiles_n;
   const int kblocks = g.k_per_split / kBK;
 
   if (warp == 0) {
@@ -192,11 +258,11 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       const bool ldA = !(g.debug & 32), ldB = !(g.debug & 16);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < num_tiles; tile += workers) {
         const int n_t = tile % g.tiles_n;
         int rest = tile / g.tiles_n;
-        const int m_t = rest % g.tiles_m;
-        rest /= g.tiles_m;
+        const int m_t = (rest % tiles_m) * (kPair ? 2 : 1) + rank;
+        rest /= tiles_m;
         const int ks = rest % g.k_splits;
         const int b = rest / g.k_splits;
         const int kb0 = ks * kblocks;
@@ -205,21 +271,33 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const int kb = kb0 + kbi;
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * g.stage_bytes;
-          mbar_arrive_expect_tx(&full[stage], (ldA ? kRawABytes : 0) + (ldB ? 2 * b_bytes : 0));
+          if (kPair) {
+            // own A tile -> own barrier; the B halves of both CTAs are counted on the leader's `full`
+            mbar_arrive_expect_tx(&fullA[stage], kRawABytes);
+            if (rank == 0) mbar_arrive_expect_tx(&full[stage], 4 * b_bytes);
+          } else {
+            mbar_arrive_expect_tx(&full[stage], (ldA ? kRawABytes : 0) + (ldB ? 2 * b_bytes : 0));
+          }
+          uint64_t* const barA = kPair ? &fullA[stage] : &full[stage];
           if (ldA) {
             if (g.conv_wt) {
               const int y = m_t / g.conv_wt, x0 = (m_t - y * g.conv_wt) * kBM;
               const int tap = kb / g.conv_cb, c0 = (kb - tap * g.conv_cb) * kBK;
               const int ty = tap / 3;
-              tma_load_4d(st, &tmA, &full[stage], c0, x0 + (tap - 3 * ty) - 1, y + ty - 1, b);
+              tma_load_4d(st, &tmA, barA, c0, x0 + (tap - 3 * ty) - 1, y + ty - 1, b);
             } else {
-              tma_load_3d(st, &tmA, &full[stage], kb * kBK, m_t * kBM, b);
+              tma_load_3d(st, &tmA, barA, kb * kBK, m_t * kBM, b);
             }
           }
           if (ldB) {
             uint8_t* bs = st + kRawABytes + 2 * kOpABytes;
-            tma_load_3d(bs, &tmBhi, &full[stage], kb * kBK, n_t * BN, bb);
-            tma_load_3d(bs + b_bytes, &tmBlo, &full[stage], kb * kBK, n_t * BN, bb);
+            if (kPair) {
+              tma_load_3d_pair(bs, &tmBhi, &full[stage], kb * kBK, n_t * BN + rank * b_rows, bb);
+              tma_load_3d_pair(bs + b_bytes, &tmBlo, &full[stage], kb * kBK, n_t * BN + rank * b_rows, bb);
+            } else {
+              tma_load_3d(bs, &tmBhi, &full[stage], kb * kBK, n_t * BN, bb);
+              tma_load_3d(bs + b_bytes, &tmBlo, &full[stage], kb * kBK, n_t * BN, bb);
+            }
           }
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
@@ -227,13 +305,13 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      const uint32_t idesc = idesc_bf16(kBM, BN);
+    if (lane == 0 && rank == 0) {                  // pair mode: the leader issues for both CTAs
+      const uint32_t idesc = idesc_bf16(kPair ? 2 * kBM : kBM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < num_tiles; tile += workers) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
@@ -252,6 +330,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const uint64_t dal = smem_desc_sw64_kmajor(a_lo + k * 32);
             const uint64_t dbh = smem_desc_sw64_kmajor(b_hi + k * 32);
             const uint64_t dbl = smem_desc_sw64_kmajor(b_lo + k * 32);
+            if (kPair) {
+              mma_bf16_ss_pair(d_tmem, dal, dbh, idesc, (kb | k) ? 1u : 0u);
+              mma_bf16_ss_pair(d_tmem, dah, dbl, idesc, 1u);
+              mma_bf16_ss_pair(d_tmem, dah, dbh, idesc, 1u);
+              continue;
+            }
             if (g.debug & 8) {
               mma_bf16_ss(d_tmem, dah, dbh, idesc, (kb | k) ? 1u : 0u);
               continue;
@@ -260,8 +344,13 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             mma_bf16_ss(d_tmem, dah, dbl, idesc, 1u);
             mma_bf16_ss(d_tmem, dah, dbh, idesc, 1u);
           }
-          mma_commit(&empty[stage]);
-          if (kb == kblocks - 1) mma_commit(&tfull[acc]);
+          if (kPair) {
+            mma_commit_pair(&empty[stage]);          // frees the stage in BOTH CTAs
+            if (kb == kblocks - 1) mma_commit_pair(&tfull[acc]);
+          } else {
+            mma_commit(&empty[stage]);
+            if (kb == kblocks - 1) mma_commit(&tfull[acc]);
+          }
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
         acc ^= 1;
@@ -275,9 +364,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int osw = (r >> 1) & 3;          // SWIZZLE_64B:  16-byte chunk index ^ ((row / 2) % 4)
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = worker; tile < num_tiles; tile += workers) {
       for (int kb = 0; kb < kblocks; ++kb) {
-        mbar_wait(&full[stage], phase);
+        mbar_wait(kPair ? &fullA[stage] : &full[stage], phase);
         uint8_t* st = smem + stage * g.stage_bytes;
         if (!(g.debug & 4)) {
           const uint8_t* raw = st + r * 128;
@@ -303,7 +392,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           fence_proxy_async_smem();
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&conv[stage]);
+        if (lane == 0) {
+          if (kPair) mbar_arrive_leader(&conv[stage]); else mbar_arrive(&conv[stage]);
+        }
         if (++stage == S) { stage = 0; phase ^= 1; }
       }
     }
@@ -320,15 +411,15 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     int acc = 0;
     uint32_t acc_phase = 0;
     const int nchunks = BN / 32;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = worker; tile < num_tiles; tile += workers) {
       const int n_t = tile % g.tiles_n;
       int rest = tile / g.tiles_n;
-      const int m_t = rest % g.tiles_m;
-      const int slab = rest / g.tiles_m;            // = batch * k_splits + split: index of the output slab
+      const int m_t = (rest % tiles_m) * (kPair ? 2 : 1) + rank;
+      const int slab = rest / tiles_m;              // = batch * k_splits + split: index of the output slab
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const int row = m_t * kBM + trow;
-      const bool row_ok = row < g.M;
+      const bool row_ok = row < g.M && m_t < g.tiles_m;
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * 256);
       const float* grow = (g.gate != nullptr && row_ok) ? g.gate + static_cast<long long>(row) * g.gate_ld : nullptr;
       const float* rrow = nullptr;
@@ -342,7 +433,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       if (live <= eg) {                             // nothing to drain for this group: release the accumulator
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[acc]);
+        if (lane == 0) {
+          if (kPair) mbar_arrive_leader(&tempty[acc]); else mbar_arrive(&tempty[acc]);
+        }
       }
 #pragma unroll 1
       for (int c = eg; c < live; c += 2) {
@@ -353,7 +446,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (c == my_last) {                         // this group's part of the accumulator is read
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
+          if (lane == 0) {
+          if (kPair) mbar_arrive_leader(&tempty[acc]); else mbar_arrive(&tempty[acc]);
+        }
         }
         if (g.debug & 64) continue;
         float f[32];
@@ -485,10 +580,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();     // the peer may still be signalling this CTA's barriers
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (kPair) tmem_dealloc_pair(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -623,6 +718,15 @@ static int make_tmap_f32_4d(CUtensorMap* m, const float* base, long long d0, lon
   return MPF_OK;
 }
 
+// 0 (default): never use CTA pairs, 1: when a launch has at least one full wave of pair tiles, 2: whenever possible.
+// MEASURED (round 2, profiles/r2j_*): the pair kernel is bit-identical to the single-CTA kernel and SLOWER -- encoder
+// FFN1 0.73 vs 0.55 ms, FFN2 0.78 vs 0.51 ms, 3x3 convolution 4.07 vs 3.01 ms, whole step 162.1 vs 152.3 ms.  The
+// single-CTA main loop already runs at 77 % (K = 1024) to 90 % (K = 2304) of the sustained bf16 rate counting the three
+// MMAs per product, so shared-memory operand traffic was not the limiter round 1's analysis took it for; with
+// cta_group::2 every SM reads half of each B tile from its PEER's shared memory, three times per product in the split
+// arithmetic, and the leader's issue thread waits on cross-SM barriers.  Kept as an option and as a measured answer.
+static int g_pair_mode = [] { const char* e = getenv("MPF_GEMM_PAIR"); return e ? atoi(e) : 0; }();
+
 static int pick_bn(int N) {
   if (N <= 64) return 64;
   for (int bn = 256; bn >= 64; bn -= 32) {
@@ -636,6 +740,12 @@ static int pick_bn(int N) {
 }  // namespace mpf
 
 extern "C" {
+
+int mpf_gemm_bf16x3_set_pair_mode(int mode) {
+  const int prev = mpf::bf3::g_pair_mode;
+  if (mode >= 0 && mode <= 2) mpf::bf3::g_pair_mode = mode;
+  return prev;
+}
 
 int mpf_split_bf16(const float* x, uint16_t* hi, uint16_t* lo, long long n, void* stream) {
   mpf::clear_error();
@@ -693,7 +803,13 @@ static int gemm_bf16x3_impl(const float* A, long long lda, long long a_batch_str
   const int kblocks_total = (K + kBK - 1) / kBK;
   g.k_splits = k_splits;
   g.k_per_split = (kblocks_total + k_splits - 1) / k_splits * kBK;
-  g.stage_bytes = kRawABytes + 2 * kOpABytes + 2 * g.bn * kBK * 2;
+  // CTA-pair mode (cta_group::2): worth it when there is a full wave of 256-row pair tiles; each CTA then stages only
+  // half of the B tile.  MPF_GEMM_PAIR=0 disables it (A/B measurements).
+  const long long pair_tiles = static_cast<long long>(batch) * k_splits * ((g.tiles_m + 1) / 2) * g.tiles_n;
+  const bool pair = g_pair_mode != 0 && g.tiles_m >= 2 && sm_count() % 2 == 0 &&
+                    (g_pair_mode == 2 || pair_tiles >= sm_count() / 2);
+  const int b_rows = pair ? g.bn / 2 : g.bn;
+  g.stage_bytes = kRawABytes + 2 * kOpABytes + 2 * b_rows * kBK * 2;
   const int avail = kSmemBudget - 1024 - 2 * kStagingBytes - 512;
   g.stages = avail / g.stage_bytes;
   if (g.stages > kMaxStages) g.stages = kMaxStages;
@@ -715,10 +831,10 @@ static int gemm_bf16x3_impl(const float* A, long long lda, long long a_batch_str
   }
   if (rc) return rc;
   const long long nb = g.b_broadcast ? 1 : batch;
-  rc = make_tmap_3d(&tbh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B_hi, K, N, nb, ldb, b_batch_stride, kBK, g.bn,
+  rc = make_tmap_3d(&tbh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B_hi, K, N, nb, ldb, b_batch_stride, kBK, b_rows,
                     CU_TENSOR_MAP_SWIZZLE_64B, "B_hi");
   if (rc) return rc;
-  rc = make_tmap_3d(&tbl, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B_lo, K, N, nb, ldb, b_batch_stride, kBK, g.bn,
+  rc = make_tmap_3d(&tbl, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B_lo, K, N, nb, ldb, b_batch_stride, kBK, b_rows,
                     CU_TENSOR_MAP_SWIZZLE_64B, "B_lo");
   if (rc) return rc;
   if (conv_H > 0) {
@@ -762,11 +878,30 @@ static int gemm_bf16x3_impl(const float* A, long long lda, long long a_batch_str
 
   static unsigned long long configured_on = 0;
   if (first_use_on_this_device(configured_on)) {
-    MPF_CUDA_OK(cudaFuncSetAttribute(gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    MPF_CUDA_OK(cudaFuncSetAttribute(gemm_bf16x3_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    MPF_CUDA_OK(cudaFuncSetAttribute(gemm_bf16x3_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+  }
+  if (pair) {
+    const int clusters = static_cast<int>(pair_tiles < sm_count() / 2 ? pair_tiles : sm_count() / 2);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MPF_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel_t<true>, ta, tbh, tbl, tc, tcl, g));
+    count_launch();
+    return finish_launch("gemm_bf16x3 (CTA pairs)");
   }
   const long long tiles = static_cast<long long>(slabs) * g.tiles_m * g.tiles_n;
   const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
-  gemm_bf16x3_kernel<<<grid, kThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(ta, tbh, tbl, tc, tcl, g);
+  gemm_bf16x3_kernel_t<false><<<grid, kThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(ta, tbh, tbl, tc, tcl, g);
   count_launch();
   return finish_launch("gemm_bf16x3");
 }

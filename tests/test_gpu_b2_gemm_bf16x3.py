@@ -196,3 +196,62 @@ def test_relu_bit_mask_epilogues(M, N, K):
     gh_ref = (dy.double() @ w2.double().t()) * (y > 0)
     assert (gh.double() - gh_ref).abs().max().item() < TOL * max(1.0, gh_ref.abs().max().item())
     assert torch.equal(gh == 0, ~(y > 0) | (gh == 0))
+
+
+@pytest.fixture
+def pair_mode():
+    """Switches the K-major bf16x3 GEMM between single CTAs (0) and forced CTA pairs (2); restores the setting."""
+    from mp_former_b200 import _lib
+    lib = _lib.load()
+    prev = lib.mpf_gemm_bf16x3_set_pair_mode(-1)
+    yield lib.mpf_gemm_bf16x3_set_pair_mode
+    lib.mpf_gemm_bf16x3_set_pair_mode(prev)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 128, 256), (1000, 100, 256), (4096, 288, 256), (300, 1024, 256),
+                                   (777, 256, 1024), (65536, 100, 256), (21504, 768, 256), (43008, 256, 256),
+                                   (384, 256, 32)])
+def test_gemm_cta_pairs_equal_single_cta(pair_mode, M, N, K):
+    """tcgen05 cta_group::2 variant (clusters of two CTAs, M = 256 UMMA, half of the B tile per CTA) against the
+    single-CTA kernel: the same products accumulate in the same order per element, so the results are bit-identical --
+    with every epilogue variant (bias + ReLU, ReLU bits, gate bits, residual, transposed store, pre-split output), odd
+    numbers of M tiles (the phantom tile of the last pair) and ragged N."""
+    g = torch.Generator(device=DEV).manual_seed(M * 3 + N + K)
+    a = torch.randn(M, K, device=DEV, generator=g)
+    b = torch.randn(N, K, device=DEV, generator=g) / K ** 0.5
+    bias = torch.randn(N, device=DEV, generator=g)
+    resid = torch.randn(M, N, device=DEV, generator=g)
+    bh, bl = native.split_bf16(b)
+
+    def run():
+        out = [native.gemm(a, bh, bl, bias, relu=True), native.gemm(a, bh, bl, None, resid=resid, alpha=0.5)]
+        if M % 4 == 0:
+            out.append(native.gemm(a, bh, bl, None, transpose_c=True))
+        out += list(native.gemm(a, bh, bl, bias, split_out=True))
+        if N % 32 == 0:
+            y, bits = native.gemm_relu_bits(a, bh, bl, bias, relu_bits_out=True)
+            out += [y, bits, native.gemm_relu_bits(a, bh, bl, None, gate_bits=bits)]
+        return out
+
+    pair_mode(0)
+    single = run()
+    pair_mode(2)
+    paired = run()
+    torch.cuda.synchronize()
+    assert rel_err(single[0], ref64(a, b, bias, True)) < TOL
+    for s_, p_ in zip(single, paired):
+        assert torch.equal(s_, p_)
+
+
+def test_conv3x3_cta_pairs_equal_single_cta(pair_mode):
+    g = torch.Generator(device=DEV).manual_seed(11)
+    x = torch.randn(2, 40, 200, 64, device=DEV, generator=g)                      # channels-last [B, H, W, Cin]
+    w = torch.randn(128, 9 * 64, device=DEV, generator=g) / 24
+    bias = torch.randn(128, device=DEV, generator=g)
+    wh, wl = native.split_bf16(w)
+    pair_mode(0)
+    a = native.conv3x3_cl(x, wh, wl, bias)
+    pair_mode(2)
+    b = native.conv3x3_cl(x, wh, wl, bias)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
