@@ -709,6 +709,7 @@ def run_ours(a):
             "scaling": p["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
             "impl_notes": {"native_ops": sorted(M.ops.NATIVE_OPS), "tf32": False, "cuda_graph": graph_note,
                            "routes": dict(sorted(M.ops.ROUTES.items())),
+                           "criterion_path": getattr(criterion, "last_path", None) if a.loss == "criterion" else None,
                            "arithmetic": "fp32 storage; GEMMs in bf16x3 split arithmetic (fp32 accumulate), attention "
                                          "core in 3xTF32; no single-pass reduced precision"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,

@@ -122,6 +122,19 @@ int mpf_msda_set_staged(int enabled);
 int mpf_topk_gather_rows_f32(const float* scores, int rows, int n, int k, const float* payload, int payload_width,
                              float* out, void* stream);
 
+/* Point-sampled mask losses of the criterion for `rows` matched (prediction, target) pairs at once -- ref
+ * mask2former/modeling/criterion.py:25-43 (dice_loss) and :51-68 (sigmoid_ce_loss), called from loss_masks
+ * (criterion.py:188-189) once per prediction head; here the rows of all heads go through one launch:
+ *   bce[r]  = mean_p BCEWithLogits(x[r, p], y[r, p])
+ *   dice[r] = 1 - (2 sum_p s y + 1) / (sum_p s + sum_p y + 1),  s = sigmoid(x[r, p])
+ * x, y [rows, points] fp32 (device, contiguous); stats [rows, 2] keeps (numerator, denominator) of the dice ratio for
+ * the backward, which writes gx[r, p] = g_bce[r] * d bce[r]/dx + g_dice[r] * d dice[r]/dx (every element: no
+ * atomics, deterministic).  The division by num_masks and the sum over rows stay with the caller. */
+int mpf_mask_loss_rows_fwd_f32(const float* x, const float* y, int rows, int points, float* bce, float* dice,
+                               float* stats, void* stream);
+int mpf_mask_loss_rows_bwd_f32(const float* x, const float* y, const float* stats, const float* g_bce,
+                               const float* g_dice, int rows, int points, float* gx, void* stream);
+
 /* Self-attention core of the decoder's SelfAttentionLayer (ref transformer_decoder/
  * mask2former_transformer_decoder.py:42-52; tgt_mask of the mask-piloted groups: decoder :1051-1059):
  *   out[b, :, h] = softmax(q_h k_h^T / sqrt(head_dim) + mask) v_h   with q | k | v = qkv[b, :, 0:E | E:2E | 2E:3E]

@@ -37,6 +37,8 @@ SIGNATURES = {
     "mpf_self_attn_fwd_f32": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_vp]),
     "mpf_self_attn_bwd_f32": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
     "mpf_topk_gather_rows_f32": (_c_int, [_c_vp, _c_int, _c_int, _c_int, _c_vp, _c_int, _c_vp, _c_vp]),
+    "mpf_mask_loss_rows_fwd_f32": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp]),
+    "mpf_mask_loss_rows_bwd_f32": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_vp, _c_vp]),
     "mpf_split_tf32": (_c_int, [_c_vp, _c_vp, _c_vp, ctypes.c_longlong, _c_vp]),
     "mpf_gemm_tf32x3": (_c_int, [_c_vp, ctypes.c_longlong, ctypes.c_longlong, _c_vp, _c_vp,
                                  ctypes.c_longlong, ctypes.c_longlong, _c_vp, _c_vp, ctypes.c_longlong,

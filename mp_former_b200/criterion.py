@@ -14,7 +14,16 @@ preparation upstream draws differently -- see masked_decoder.prepare_for_dn_v5) 
     built once per step on the host from the target counts instead of per image with ``.cuda()`` uploads;
   * ``num_masks`` is a host number (single process) or stays a device tensor after the all-reduce (no ``.item()``).
 
-The loss arithmetic itself (cross-entropy, BCE, dice, top-k of the uncertainty scores) is library PyTorch.
+  * ALL prediction heads of a step (final + auxiliary layers, matching and mask-piloted queries: 20 loss evaluations
+    in the published recipe) are evaluated together (``_forward_heads``): the random numbers are drawn head by head
+    in the reference's order, everything else runs once over the rows of all heads -- one assignment launch, one
+    sampling launch per direction, one fused BCE + dice launch per direction (``native.MaskLossRows``,
+    csrc/mask_loss.cu), one cross-entropy over the concatenated class logits -- and the mask-logit gradients of all
+    heads land in ONE buffer (``native.PointSampleViews``) that the decoder's batched head backward consumes as is.
+    The head-by-head evaluation (``_forward_sequential``, the reference's loop) remains for inputs the joint path
+    does not cover (mixed target sizes, no targets at all, other ``losses`` lists).
+
+The cross-entropy is library PyTorch; the rest of the loss arithmetic are this package's kernels.
 There is no CPU path: CUDA tensors only."""
 import torch
 import torch.distributed as dist
@@ -23,6 +32,14 @@ from torch import nn
 
 from . import native
 from .matcher import PackedTargets, targets_key
+
+
+class LossDict(dict):
+    """The criterion's result: loss name -> scalar, like the reference's dict.  ``vectors`` additionally holds the
+    same values as a few stacked tensors ``[(names, values [n])]`` when the heads were evaluated together, so that the
+    trainer's weighted total (ref maskformer_model.py:225-231) is a handful of launches instead of one multiply and
+    one add per entry: see ``SetCriterion.weighted_total``."""
+    vectors = None
 
 
 def _world_size():
@@ -53,6 +70,10 @@ class SetCriterion(nn.Module):
         self._step_key = None
         self._step = None
         self._status = None          # int32 [1] on the device: != 0 once a matching of this step has failed
+        self.joint_heads = True      # evaluate all prediction heads together when the inputs allow (_forward_heads)
+        self.chunk_bytes = 96 << 20  # candidate points drawn / ranked per pass of the joint path (stays in the L2)
+        self._weights = {}
+        self.last_path = None        # "heads" | "sequential": which evaluation the last forward took
 
     def check_status(self):
         """Raises the reference's error for a failed assignment (scipy's ``ValueError: matrix contains invalid numeric
@@ -63,7 +84,8 @@ class SetCriterion(nn.Module):
         trainer already synchronises, e.g. next to the loss logging -- raises."""
         st, self._status = self._status, None
         if st is not None and int(st.item()) != 0:
-            raise ValueError(f"HungarianMatcher: cost matrix of image {int(st.item()) - 1} contains invalid numeric "
+            raise ValueError(f"HungarianMatcher: cost matrix of assignment problem {int(st.item()) - 1} (image, or "
+                             "head * batch + image when the heads are solved together) contains invalid numeric "
                              "entries (NaN / -inf) or is infeasible")
 
     # -- per-step state shared by the 20 loss evaluations of one forward --------------------------------------------
@@ -92,6 +114,7 @@ class SetCriterion(nn.Module):
                                           device=device)
             self._batch_index = {}
             self._dn = {}
+            self.joint = {}
             self.num_masks = None
 
         def batch_index(self, sizes):
@@ -224,33 +247,241 @@ class SetCriterion(nn.Module):
             else:
                 step.num_masks = max(float(step.total), 1.0)
         num_masks = step.num_masks
-
-        losses = self._all_losses(main, step, self._match(main, targets, step), num_masks)
-
         use_dn = bool(self.training and dn_out)
+        heads = [main] + list(outputs.get("aux_outputs", []))
+        dn_heads = None
+        if use_dn:
+            dn_heads = [{k: v for k, v in dn_out.items() if k != "aux_outputs"}]
+            dn_heads += list(dn_out["aux_outputs"])[:len(heads) - 1]
+        self.last_path = "heads" if self.joint_heads and self._joint_ok(heads, dn_heads, step) else "sequential"
+        if self.last_path == "heads":
+            losses = self._forward_heads(heads, dn_heads, dn_out, targets, step, num_masks)
+        else:
+            losses = self._forward_sequential(heads, dn_heads, dn_out, targets, step, num_masks)
+        if self.dn_no_lb:
+            for k in [k for k in losses if k.startswith("loss_ce_dn")]:
+                del losses[k]
+        return losses
+
+    def _forward_sequential(self, heads, dn_heads, dn_out, targets, step, num_masks):
+        """Head by head, as the reference loops (criterion.py:271-304)."""
+        dev = step.device
+        use_dn = dn_heads is not None
         zero = torch.zeros((), device=dev)           # (a fill kernel: capturable, unlike a host scalar upload)
         if use_dn:
             db, dq, dt, scalar = step.dn_indices(dn_out["dn_args"])
             dn_idx = (db, dq, dt)
-
-        def dn_losses(o, suffix):
+        losses = LossDict()
+        for e, head in enumerate(heads):
+            suffix = "" if e == 0 else f"_{e - 1}"
+            d = self._all_losses(head, step, self._match(head, targets, step), num_masks)
+            losses.update({k + suffix: v for k, v in d.items()})
             if use_dn:
-                d = self._all_losses(o, step, dn_idx, num_masks * scalar)
-                return {k + "_dn" + suffix: v for k, v in d.items()}
-            return {k + suffix: zero for k in ("loss_mask_dn", "loss_dice_dn", "loss_ce_dn")}
-
-        losses.update(dn_losses({k: v for k, v in dn_out.items() if k != "aux_outputs"} if use_dn else None, ""))
-        if "aux_outputs" in outputs:
-            for i, aux in enumerate(outputs["aux_outputs"]):
-                d = self._all_losses(aux, step, self._match(aux, targets, step), num_masks)
-                losses.update({k + f"_{i}": v for k, v in d.items()})
-                losses.update(dn_losses(dn_out["aux_outputs"][i] if use_dn else None, f"_{i}"))
-        if self.dn_no_lb:
-            losses = {k: losses[k] for k in losses if not k.startswith("loss_ce_dn")}
+                d = self._all_losses(dn_heads[e], step, dn_idx, num_masks * scalar)
+                losses.update({k + "_dn" + suffix: v for k, v in d.items()})
+            else:
+                losses.update({k + suffix: zero for k in ("loss_mask_dn", "loss_dice_dn", "loss_ce_dn")})
         if self._status is not None:        # failed assignment -> every loss NaN (see check_status)
             poison = torch.where(self._status[0] == 0, 0.0, float("nan"))
-            losses = {k: v + poison for k, v in losses.items()}
+            for k in losses:
+                losses[k] = losses[k] + poison
         return losses
+
+    # -- all heads together -----------------------------------------------------------------------------------------
+    def _joint_ok(self, heads, dn_heads, step):
+        """Whether ``_forward_heads`` covers these inputs; everything else takes the head-by-head path."""
+        if sorted(self.losses) != ["labels", "masks"] or not step.packed.uniform() or step.total == 0:
+            return False
+        if int(self.num_points * self.oversample_ratio) > native.TOPK_GATHER_MAX_N:
+            return False
+        if int(self.importance_sample_ratio * self.num_points) <= 0:
+            return False
+        m0, l0 = heads[0]["pred_masks"], heads[0]["pred_logits"]
+        if m0.dim() != 4 or m0.shape[1] == 0:
+            return False
+        H, W = m0.shape[-2:]
+        for group in ([heads, dn_heads] if dn_heads else [heads]):
+            g0 = group[0]
+            for o in group:
+                m, lg = o["pred_masks"], o["pred_logits"]
+                if m.dtype != torch.float32 or lg.dtype != l0.dtype or m.shape != g0["pred_masks"].shape or \
+                        lg.shape != g0["pred_logits"].shape or m.stride(-1) != 1 or m.stride(-2) != W or \
+                        m.stride(1) != H * W or tuple(m.shape[-2:]) != (H, W) or m.shape[0] != m0.shape[0]:
+                    return False
+        return dn_heads is None or len(dn_heads) == len(heads)
+
+    def _forward_heads(self, heads, dn_heads, dn_out, targets, step, num_masks):
+        """All loss evaluations of the step in one pass (see the module docstring).  Row layout: for head e = 0 (final),
+        1 .. (auxiliary 0 ..): its R_m matched pairs, then its R_d mask-piloted pairs -- the order in which the
+        reference draws their random points (criterion.py:271-304), so a seed gives the same points.  Column layout
+        of the concatenated class logits / mask-logit gradients: per head its Q matching queries, then its ``pad``
+        mask-piloted queries."""
+        dev = step.device
+        nE = len(heads)
+        use_dn = dn_heads is not None
+        m0 = heads[0]["pred_masks"]
+        B, Q, H, W = m0.shape
+        sizes_m = [min(Q, n) for n in step.counts]
+        R_m = sum(sizes_m)
+        scalar, R_d, pad = 1, 0, 0
+        if use_dn:
+            db, dq, dt, scalar = step.dn_indices(dn_out["dn_args"])
+            R_d, pad = int(db.numel()), dn_heads[0]["pred_masks"].shape[1]
+        per, width = R_m + R_d, Q + pad
+        total = nE * width
+        n_over = int(self.num_points * self.oversample_ratio)
+        n_unc = int(self.importance_sample_ratio * self.num_points)
+        n_rand = self.num_points - n_unc
+        P = self.num_points
+        device_matcher = hasattr(self.matcher, "match_device_heads")
+
+        # per-step tables that depend on the target counts and the head geometry only
+        key = ("heads", nE, Q, pad, scalar, R_d)
+        tab = step.joint.get(key)
+        if tab is None:
+            bm = step.batch_index(sizes_m)
+            b_per = torch.cat([bm, db]) if use_dn else bm
+            e_rows = torch.arange(nE, device=dev).repeat_interleave(per)
+            first = e_rows * width
+            if use_dn:       # the mask-piloted rows of every head start Q columns further
+                first = first + torch.cat([torch.zeros(R_m, dtype=torch.int64, device=dev),
+                                           torch.full((R_d,), Q, dtype=torch.int64, device=dev)]).repeat(nE)
+            b_all = b_per.repeat(nE)
+            tab = step.joint[key] = {"b_all": b_all, "slot0": b_all * total + first}
+        b_all = tab["b_all"]
+
+        maps, logit_list = [], []
+        for e in range(nE):
+            maps.append(heads[e]["pred_masks"])
+            logit_list.append(heads[e]["pred_logits"])
+            if use_dn:
+                maps.append(dn_heads[e]["pred_masks"])
+                logit_list.append(dn_heads[e]["pred_logits"])
+        s0_set = {m.stride(0) for m in maps}
+        s1 = H * W
+
+        R = nE * per
+        q_all = torch.empty(R, dtype=torch.int64, device=dev)
+        t_all = torch.empty(R, dtype=torch.int64, device=dev)
+        base = torch.empty(R, dtype=torch.int64, device=dev)
+        s0_rows = torch.empty(R, dtype=torch.int64, device=dev) if len(s0_set) > 1 else None
+        coords = torch.empty((R, P, 2), dtype=torch.float32, device=dev)
+        labels = torch.empty((R, P), dtype=torch.float32, device=dev)
+        q2, t2, base2 = q_all.view(nE, per), t_all.view(nE, per), base.view(nE, per)
+        if use_dn:
+            q2[:, R_m:] = dq
+            t2[:, R_m:] = dt
+        for e in range(nE):             # device addresses of the heads' maps: fills (kernel arguments; capturable)
+            base2[e, :R_m].fill_(maps[(2 if use_dn else 1) * e].data_ptr())
+            if use_dn:
+                base2[e, R_m:].fill_(maps[2 * e + 1].data_ptr())
+            if s0_rows is not None:
+                s0_rows.view(nE, per)[e, :R_m].fill_(maps[(2 if use_dn else 1) * e].stride(0))
+                if use_dn:
+                    s0_rows.view(nE, per)[e, R_m:].fill_(maps[2 * e + 1].stride(0))
+        s0 = s0_rows if s0_rows is not None else next(iter(s0_set))
+
+        heads_per_pass = max(1, min(nE, self.chunk_bytes // max(1, per * n_over * 12)))
+        with torch.no_grad():
+            for e0 in range(0, nE, heads_per_pass):
+                e1 = min(nE, e0 + heads_per_pass)
+                n = e1 - e0
+                r0, r1 = e0 * per, e1 * per
+                cand = torch.empty((n * per, n_over, 2), dtype=torch.float32, device=dev)
+                rnd = torch.empty((n * per, n_rand, 2), dtype=torch.float32, device=dev) if n_rand > 0 else None
+                pts, generic = [], []
+                # 1. the random numbers of these heads, in the reference's order (matcher.py:120; criterion.py:162,
+                #    get_uncertain_point_coords_with_randomness: candidates, then the purely random points)
+                for e in range(e0, e1):
+                    if device_matcher:
+                        pts.append(self.matcher.draw_points(B, dev))
+                    else:
+                        generic.append(self._match(heads[e], targets, step))
+                    lo = (e - e0) * per
+                    for a, b in ((lo, lo + R_m), (lo + R_m, lo + per)):
+                        if b > a:
+                            torch.rand(b - a, n_over, 2, out=cand[a:b])
+                            if rnd is not None:
+                                torch.rand(b - a, n_rand, 2, out=rnd[a:b])
+                # 2. assignment of these heads' matching queries
+                if device_matcher:
+                    qm, tm, status = self.matcher.match_device_heads(heads[e0:e1], targets, pts)
+                    self._status = status if self._status is None else torch.maximum(self._status, status)
+                    q2[e0:e1, :R_m] = qm.view(n, R_m)
+                    t2[e0:e1, :R_m] = tm.view(n, R_m)
+                else:
+                    for e, (_, qe, te) in zip(range(e0, e1), generic):
+                        q2[e, :R_m] = qe
+                        t2[e, :R_m] = te
+                # 3. importance sampling of the points: the n_unc most uncertain of the candidates + random ones
+                qs, ts, bs_ = q_all[r0:r1], t_all[r0:r1], b_all[r0:r1]
+                src = base[r0:r1] + 4 * (bs_ * (s0 if s0_rows is None else s0[r0:r1]) + qs * s1)
+                unc = native.point_sample_rows(src, True, (H, W), cand, neg_abs=True)
+                top = native.topk_gather_rows(unc, cand, n_unc)
+                if rnd is not None:
+                    torch.cat([top, rnd], dim=1, out=coords[r0:r1])
+                else:
+                    coords[r0:r1] = top
+                # 4. the targets at those points
+                tgt_ptrs = step.mask_ptrs[bs_] + ts * (step.hw[0] * step.hw[1] * step.elsize)
+                native.point_sample_rows(tgt_ptrs, step.packed.is_f32, step.hw, coords[r0:r1], out=labels[r0:r1])
+            src_all = base + 4 * (b_all * s0 + q_all * s1)
+            slot = tab["slot0"] + q_all
+            tgt_classes = step.packed.labels[step.offsets[b_all] + t_all].clamp(0, self.num_classes)
+
+        # mask losses of all rows
+        x = native.PointSampleViews.apply(coords, src_all, slot, *maps)
+        bce, dice = native.MaskLossRows.apply(x, labels)
+        bce, dice = bce.view(nE, per), dice.view(nE, per)
+        # classification loss of all heads (ref criterion.py:123-139): weighted mean per head = sum(w nll) / sum(w)
+        logits = torch.cat(logit_list, dim=1).float()                     # [B, total, K + 1]
+        classes = torch.full((B * total,), self.num_classes, dtype=torch.int64, device=dev)
+        classes[slot] = tgt_classes
+        nll = F.cross_entropy(logits.view(B * total, -1), classes, self.empty_weight, reduction="none")
+        nll = nll.view(B, nE, width)
+        wts = self.empty_weight[classes].view(B, nE, width)
+
+        vec = {"loss_ce": nll[:, :, :Q].sum((0, 2)) / wts[:, :, :Q].sum((0, 2)),
+               "loss_mask": bce[:, :R_m].sum(1) / num_masks, "loss_dice": dice[:, :R_m].sum(1) / num_masks}
+        if use_dn:
+            vec["loss_ce_dn"] = nll[:, :, Q:].sum((0, 2)) / wts[:, :, Q:].sum((0, 2))
+            vec["loss_mask_dn"] = bce[:, R_m:].sum(1) / (num_masks * scalar)
+            vec["loss_dice_dn"] = dice[:, R_m:].sum(1) / (num_masks * scalar)
+        else:
+            zeros = torch.zeros(nE, device=dev)
+            vec.update({k: zeros for k in ("loss_ce_dn", "loss_mask_dn", "loss_dice_dn")})
+        if self._status is not None:        # failed assignment -> every loss NaN (see check_status)
+            poison = torch.where(self._status[0] == 0, 0.0, float("nan"))
+            vec = {k: v + poison for k, v in vec.items()}
+        losses = LossDict()
+        losses.vectors = []
+        suffixes = [""] + [f"_{i}" for i in range(nE - 1)]
+        for k, v in vec.items():
+            if self.dn_no_lb and k == "loss_ce_dn":
+                continue
+            names = [k + sfx for sfx in suffixes]
+            losses.vectors.append((names, v))
+            losses.update(zip(names, v.unbind(0)))
+        return losses
+
+    def weighted_total(self, losses, weight_dict=None):
+        """sum_k weight_dict[k] * losses[k] over the losses that have a weight: the scalar the trainer back-propagates
+        (ref maskformer_model.py:225-231 followed by the trainer's ``sum(loss_dict.values())``).  With the stacked
+        values of the joint path this is one multiply-and-sum per loss kind instead of one multiply and one add per
+        entry (60 in the published recipe)."""
+        wd = self.weight_dict if weight_dict is None else weight_dict
+        vec = getattr(losses, "vectors", None)
+        if not vec:
+            return sum(v * wd[k] for k, v in losses.items() if k in wd)
+        total = None
+        for names, values in vec:
+            wkey = tuple(float(wd.get(k, 0.0)) for k in names)
+            w = self._weights.get((wkey, values.device))
+            if w is None:       # built on first use (eagerly, before any graph capture) and kept
+                w = self._weights[(wkey, values.device)] = torch.tensor(wkey, dtype=values.dtype, device=values.device)
+            term = torch.dot(values, w)
+            total = term if total is None else total + term
+        return total
 
     def __repr__(self):
         head = "Criterion " + self.__class__.__name__

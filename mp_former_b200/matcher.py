@@ -1,6 +1,7 @@
 """Device-resident mirror of the reference's ``HungarianMatcher`` (mask2former/modeling/matcher.py:70-189): same
 constructor, same ``forward(outputs, targets)`` contract and result format, same consumption of the global random
-generator (one ``torch.rand(1, num_points, 2)`` per image, in image order, matcher.py:120) -- but the whole batch is
+generator PER CALL (one ``torch.rand(1, num_points, 2)`` per image, in image order, matcher.py:120; end-to-end seed
+parity with a reference training run does not hold, see criterion.py) -- but the whole batch is
 matched in three kernel launches (native.match_cost + native.lsap) with ONE device->host copy of the finished index
 pairs, instead of, per image, two grid_samples, three einsums, a cost-matrix copy to the host (a stream sync) and a
 scipy solve.  With ``device_indices=True`` the pairs stay on the device and nothing synchronises at all (the number of
@@ -124,7 +125,58 @@ class HungarianMatcher(nn.Module):
         order = key.argsort(dim=1, stable=True)
         return torch.gather(point_coords, 1, order.unsqueeze(-1).expand(-1, -1, 2))
 
+    def draw_points(self, bs, device):
+        """The matcher's random points of one call: all masks of an image share one set, drawn per image like the
+        reference (``torch.rand(1, num_points, 2)`` inside the loop over the batch, matcher.py:120)."""
+        return torch.cat([torch.rand(1, self.num_points, 2, device=device) for _ in range(bs)])
+
     # -- the matching ------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def match_device_heads(self, heads, targets, point_coords):
+        """``match_device`` for SEVERAL prediction heads of one step (``heads``: list of outputs dicts over the same
+        batch and targets; ``point_coords``: their [B, P, 2] point sets, e.g. from ``draw_points``): the cost matrices
+        of all heads are solved by ONE launch of the assignment kernel (one CTA per (head, image) problem instead of
+        one launch of B CTAs per head).  Target maps of one size only (``PackedTargets.uniform()``).
+        Returns (query_idx, target_idx, status): the pairs of head 0's images, then head 1's, ...; status: 0, or
+        1 + (head * B + image) of a failed problem."""
+        bs, num_queries = heads[0]["pred_logits"].shape[:2]
+        if len(targets) != bs:
+            raise RuntimeError(f"{len(targets)} targets for a batch of {bs}")
+        dev = heads[0]["pred_masks"].device
+        packed = self.pack_targets(targets, dev)
+        if not packed.uniform():
+            raise RuntimeError("match_device_heads: target maps of one size expected")
+        ptrs, offsets, labels, counts = self._tables_for(packed, 0, bs)
+        ntot = sum(counts)
+        nh = len(heads)
+        if ntot == 0:
+            z = torch.zeros(0, dtype=torch.int64, device=dev)
+            return z, z, torch.zeros(1, dtype=torch.int32, device=dev)
+        costs = []
+        for o, pts in zip(heads, point_coords):
+            logits, masks = o["pred_logits"], o["pred_masks"]
+            _lib.require_cuda(masks, "outputs['pred_masks']")
+            _lib.require_cuda(logits, "outputs['pred_logits']")
+            sort = self.sort_points
+            if sort is None:
+                sort = masks.numel() * masks.element_size() >= (200 << 20)
+            if sort:
+                pts = self.row_major_order(pts, *masks.shape[-2:])
+            costs.append(native.match_cost(logits.float(), masks.float(), ptrs, packed.is_f32, packed.sizes[0], labels,
+                                           offsets, counts, pts, self.cost_class, self.cost_mask, self.cost_dice))
+        key = ("heads", nh)
+        if key not in self._tables:     # offsets of the nh * B problems in the concatenated cost buffer
+            offs, acc = [0], 0
+            for _ in range(nh):
+                for n in counts:
+                    acc += n
+                    offs.append(acc)
+            self._tables[key] = torch.tensor(offs, dtype=torch.int32, device=dev)
+        q, t, status = native.lsap(costs[0] if nh == 1 else torch.cat(costs), self._tables[key], list(counts) * nh,
+                                   num_queries)
+        self.last_status = status
+        return q, t, status
+
     @torch.no_grad()
     def match_device(self, outputs, targets, point_coords=None):
         """Returns (query_idx, target_idx, counts, cost, status): flat int64 device tensors holding the pairs of all
@@ -142,7 +194,7 @@ class HungarianMatcher(nn.Module):
         packed = self.pack_targets(targets, dev)
         if point_coords is None:
             # all masks of an image share one set of points; drawn per image like the reference (matcher.py:120)
-            point_coords = torch.cat([torch.rand(1, self.num_points, 2, device=dev) for _ in range(bs)])
+            point_coords = self.draw_points(bs, dev)
         sort = self.sort_points
         if sort is None:
             sort = masks.numel() * masks.element_size() >= (200 << 20)

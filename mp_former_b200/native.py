@@ -863,9 +863,10 @@ def lsap(cost, tgt_offsets, counts, num_queries):
 # ----------------------------------------------------------------------------------------------------------------
 # Point sampling for the criterion (ref mask2former/modeling/criterion.py:141-191)
 # ----------------------------------------------------------------------------------------------------------------
-def point_sample_rows(map_ptrs, maps_are_f32, hw, coords, neg_abs=False):
+def point_sample_rows(map_ptrs, maps_are_f32, hw, coords, neg_abs=False, out=None):
     """out[r, p] = bilinear(map_r, coords[r, p]) with map_r the H x W map (uint8 or float32) at device address
-    map_ptrs[r] (int64 [R]); coords [R, P, 2] f32 in [0, 1].  No autograd (see PointSampleRows)."""
+    map_ptrs[r] (int64 [R]); coords [R, P, 2] f32 in [0, 1].  No autograd (see PointSampleRows).  ``out``: optional
+    contiguous float32 [R, P] destination."""
     _lib.require_cuda(map_ptrs, "map_ptrs")
     _lib.require_cuda(coords, "coords")
     if map_ptrs.dtype != torch.int64 or coords.dtype != torch.float32 or coords.dim() != 3 or coords.shape[-1] != 2:
@@ -874,7 +875,10 @@ def point_sample_rows(map_ptrs, maps_are_f32, hw, coords, neg_abs=False):
     R, P = coords.shape[:2]
     if map_ptrs.numel() != R:
         raise RuntimeError("point_sample_rows: one map pointer per row of coords expected")
-    out = torch.empty((R, P), dtype=torch.float32, device=coords.device)
+    if out is None:
+        out = torch.empty((R, P), dtype=torch.float32, device=coords.device)
+    elif out.dtype != torch.float32 or tuple(out.shape) != (R, P) or not out.is_contiguous() or out.device != coords.device:
+        raise RuntimeError("point_sample_rows: out must be a contiguous float32 [R, P] tensor on the coords' device")
     with torch.cuda.device(coords.device):
         rc = _lib.load().mpf_point_sample_rows(map_ptrs.data_ptr(), int(bool(maps_are_f32)), int(hw[0]), int(hw[1]),
                                                coords.data_ptr(), R, P, int(bool(neg_abs)), out.data_ptr(), _stream())
@@ -934,6 +938,90 @@ def point_sample_rows_bwd(grad_map_ptrs, hw, coords, grad_out):
         rc = _lib.load().mpf_point_sample_rows_bwd_f32(grad_map_ptrs.data_ptr(), int(hw[0]), int(hw[1]),
                                                        coords.data_ptr(), R, P, grad_out.data_ptr(), _stream())
     _lib.check(rc, "point_sample_rows_bwd")
+
+
+class PointSampleViews(torch.autograd.Function):
+    """``PointSampleRows`` over SEVERAL map tensors at once (the mask logits of all prediction heads, each
+    ``[B, n_i, H, W]`` float32 with contiguous H x W maps).  Row r samples the map at device address ``src_ptrs[r]``,
+    which is map ``slot[r]`` of the virtual concatenation ``[B, sum n_i, H, W]`` of the tensors along dim 1 (flat
+    index ``b * sum n_i + first_i + q``; the caller derives both vectors from the same (tensor, b, q) triples -- see
+    ``view_tables``).  One forward launch for all rows; the backward allocates ONE zeroed buffer of that concatenated
+    shape, adds every row's contributions into it in one launch and returns its slices as the tensors' gradients -- a
+    consumer that needs them side by side (ops._HeadCollector) finds them already laid out."""
+
+    @staticmethod
+    def view_tables(maps):
+        """Per-tensor tables (base address, stride(0), stride(1) in bytes, first column of the concatenation) as int64
+        device vectors + the concatenated width; build once per step (host -> device uploads)."""
+        dev = maps[0].device
+        mk = (lambda v: torch.tensor(v, dtype=torch.int64, device=dev))
+        first, total = [], 0
+        for m in maps:
+            first.append(total)
+            total += m.shape[1]
+        return (mk([m.data_ptr() for m in maps]), mk([4 * m.stride(0) for m in maps]),
+                mk([4 * m.stride(1) for m in maps]), mk(first), total)
+
+    @staticmethod
+    def forward(ctx, coords, src_ptrs, slot, *maps):
+        B, _, H, W = maps[0].shape
+        for m in maps:
+            _lib.require_cuda(m, "maps")
+            if m.dtype != torch.float32 or m.dim() != 4 or m.shape[0] != B or tuple(m.shape[-2:]) != (H, W) or \
+                    m.stride(-1) != 1 or m.stride(-2) != W:
+                raise RuntimeError("PointSampleViews: float32 maps [B, n, H, W] of one size with contiguous H x W expected")
+        if src_ptrs.dtype != torch.int64 or slot.dtype != torch.int64 or src_ptrs.shape != slot.shape:
+            raise RuntimeError("PointSampleViews: src_ptrs / slot must be int64 vectors of one length")
+        coords = coords.contiguous()
+        ctx.save_for_backward(coords, slot)
+        ctx.geom = (B, H, W, [m.shape[1] for m in maps])
+        return point_sample_rows(src_ptrs, True, (H, W), coords)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        coords, slot = ctx.saved_tensors
+        B, H, W, sizes = ctx.geom
+        grad = torch.zeros((B, sum(sizes), H, W), dtype=torch.float32, device=grad_out.device)
+        point_sample_rows_bwd(grad.data_ptr() + (4 * H * W) * slot, (H, W), coords, grad_out)
+        return (None, None, None) + tuple(grad.split(sizes, dim=1))
+
+
+class MaskLossRows(torch.autograd.Function):
+    """(bce [R], dice [R]) of sampled logits x [R, P] against sampled targets y [R, P] (ref criterion.py:25-68; the
+    caller sums over rows and divides by num_masks): one launch forward, one backward (csrc/mask_loss.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, y):
+        _f32c(x, "x")
+        _f32c(y, "y")
+        if x.dim() != 2 or x.shape != y.shape:
+            raise RuntimeError("MaskLossRows: x and y must be [R, P] tensors of one shape")
+        x, y = x.contiguous(), y.contiguous()
+        R, P = x.shape
+        bce = torch.empty(R, dtype=torch.float32, device=x.device)
+        dice = torch.empty_like(bce)
+        stats = torch.empty((R, 2), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.load().mpf_mask_loss_rows_fwd_f32(x.data_ptr(), y.data_ptr(), R, P, bce.data_ptr(), dice.data_ptr(),
+                                                        stats.data_ptr(), _stream())
+        _lib.check(rc, "mask_loss_rows_fwd")
+        ctx.save_for_backward(x, y, stats)
+        return bce, dice
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_bce, g_dice):
+        x, y, stats = ctx.saved_tensors
+        R, P = x.shape
+        zero = (lambda g: torch.zeros(R, dtype=torch.float32, device=x.device) if g is None else g.contiguous())
+        g_bce, g_dice = zero(g_bce), zero(g_dice)
+        gx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            rc = _lib.load().mpf_mask_loss_rows_bwd_f32(x.data_ptr(), y.data_ptr(), stats.data_ptr(), g_bce.data_ptr(),
+                                                        g_dice.data_ptr(), R, P, gx.data_ptr(), _stream())
+        _lib.check(rc, "mask_loss_rows_bwd")
+        return gx, None
 
 
 SELF_ATTN_MAX_Q = 320

@@ -749,34 +749,92 @@ class _HeadCollector(torch.autograd.Function):
         return tuple(outs)
 
     @staticmethod
+    def _side_by_side(grads, sizes, B, H, W):
+        """The gradient pieces as ONE [B, T, H*W] tensor without copying, when they already are slices (along dim 1,
+        in any order) of one dense buffer that they tile completely -- what ``native.PointSampleViews`` (the
+        criterion's joint evaluation of all heads) hands back.  Returns (G2, first row of every piece) or None."""
+        if any(g is None for g in grads):
+            return None
+        T, HW = sum(sizes), H * W
+        store = grads[0].untyped_storage().data_ptr()
+        want = (T * HW, HW, W, 1)
+        for g, n in zip(grads, sizes):
+            if g.dtype != torch.float32 or g.untyped_storage().data_ptr() != store or tuple(g.shape) != (B, n, H, W) or \
+                    (n > 0 and g.stride() != want):
+                return None
+        base = min(g.storage_offset() for g in grads)
+        rows, covered = [], 0
+        for g, n in zip(grads, sizes):
+            d = g.storage_offset() - base
+            if d % HW or d // HW + n > T:
+                return None
+            rows.append(d // HW)
+            covered += n
+        order = sorted(range(len(rows)), key=lambda i: rows[i])
+        at = 0
+        for i in order:                       # the pieces must tile [0, T) exactly
+            if rows[i] != at:
+                return None
+            at += sizes[i]
+        return torch.as_strided(grads[order[0]], (B, T, HW), (T * HW, HW, 1), base), rows
+
+    @staticmethod
     def backward(ctx, *grads):
         sh, n_dn, nH = ctx.shared, ctx.n_dn, ctx.n_heads
         B, Qt, H, W = ctx.mshape
         dev = sh.tokens.device if sh.tokens is not None else next(g.device for g in grads if g is not None)
-        # ONE concatenation along the (head, query) axis: contiguous output, vectorised batched copy
         sizes = ([n_dn, Qt - n_dn] * nH) if n_dn > 0 else ([Qt] * nH)
-        pieces = [g.reshape(B, n, H * W) if g is not None else torch.zeros((B, n, H * W), dtype=torch.float32, device=dev)
-                  for g, n in zip(grads, sizes)]
-        G = torch.cat(pieces, 1).view(B, nH, Qt, H, W)
-        del pieces
         C = sh.tokens.shape[-1] if sh.tokens is not None else 0
-        if (sh.tokens is not None and len(sh.embeds) == nH and native.GEMM_MODE == "bf16x3" and (H * W) % 4 == 0
-                and C % 4 == 0):
-            G2 = G.view(B, nH * Qt, H * W)
-            E_all = torch.stack(sh.embeds, 1).view(B, nH * Qt, C)
+        batched = (sh.tokens is not None and len(sh.embeds) == nH and native.GEMM_MODE == "bf16x3" and (H * W) % 4 == 0
+                   and C % 4 == 0)
+        side = _HeadCollector._side_by_side(grads, sizes, B, H, W) if batched else None
+        ROUTES["mask_heads.backward:" + ("gradients_in_place" if side is not None else "gradients_concatenated")] += 1
+        if side is not None:
+            # no concatenation: the GEMMs read the buffer in place; its row order (any permutation of the pieces) is
+            # applied to the small operand E and undone on the small result dE
+            G2, rows = side
+            pieces_e, k = [], 0
+            for h in range(nH):
+                for n, lo in (((n_dn, 0), (Qt - n_dn, n_dn)) if n_dn > 0 else ((Qt, 0),)):
+                    pieces_e.append((rows[k], sh.embeds[h][:, lo:lo + n]))
+                    k += 1
+            E_all = torch.cat([e for _, e in sorted(pieces_e, key=lambda p: p[0])], 1)       # [B, T, C], buffer order
+        else:
+            # ONE concatenation along the (head, query) axis: contiguous output, vectorised batched copy
+            pieces = [g.reshape(B, n, H * W) if g is not None else
+                      torch.zeros((B, n, H * W), dtype=torch.float32, device=dev) for g, n in zip(grads, sizes)]
+            G = torch.cat(pieces, 1).view(B, nH, Qt, H, W)
+            del pieces
+            if batched:
+                G2 = G.view(B, nH * Qt, H * W)
+                E_all = torch.stack(sh.embeds, 1).view(B, nH * Qt, C)
+        if batched:
+            T = nH * Qt
             # dE: reduction over the H*W pixels -> mask_features is needed K-major: one transposing split per step
             # (instead of ten passes of the 3xTF32 mixed-major kernel), then the bf16x3 GEMM with split-K chosen so
             # that the tile count fills whole waves of the 148 SMs
-            tiles = ((nH * Qt + 127) // 128) * ((C + 255) // 256) * B
+            tiles = ((T + 127) // 128) * ((C + 255) // 256) * B
             max_splits = max(1, min(16, (H * W) // 2048))
             splits = min(range(1, max_splits + 1), key=lambda k: (-(-tiles * k // 148)) / (tiles * k / 148.0) + 0.01 * k)
             if (H * W) % 8 == 0:
                 ft_hi, ft_lo = native.transpose_split_bf16(sh.tokens)              # [B, C, HW]
-                sh.dE = native.gemm_bf16x3_splitk(G2, ft_hi, ft_lo, splits).view(B, nH, Qt, C)
+                dE = native.gemm_bf16x3_splitk(G2, ft_hi, ft_lo, splits)
                 del ft_hi, ft_lo
             else:
-                sh.dE = native.gemm_general(G2, sh.tokens, a_mn=False, b_mn=True, k_splits=splits).view(B, nH, Qt, C)
+                dE = native.gemm_general(G2, sh.tokens, a_mn=False, b_mn=True, k_splits=splits)
+            if side is not None:                 # back to (head, query) order
+                k, back = 0, []
+                for h in range(nH):
+                    for n in ((n_dn, Qt - n_dn) if n_dn > 0 else (Qt,)):
+                        back.append(dE[:, rows[k]:rows[k] + n])
+                        k += 1
+                dE = torch.cat(back, 1)
+            sh.dE = dE.view(B, nH, Qt, C)
             sh.buf = native.gemm_tn(G2, E_all)                                 # [B, HW, C]
+        if side is not None:
+            # the heads' own backward takes dE / dF from the shared state and ignores its incoming gradient
+            skip = torch.zeros(1, dtype=torch.float32, device=dev).expand(B, Qt, H, W)
+            return (None, None) + (skip,) * nH
         return (None, None) + tuple(G[:, h] for h in range(nH))
 
 

@@ -97,6 +97,6 @@ def build_criterion(num_classes=80, dec_layers=10, class_weight=2.0, mask_weight
                         importance_sample_ratio=importance_sample_ratio).to(device)
 
     def weighted_sum(losses):
-        return sum(v * weight_dict[k] for k, v in losses.items() if k in weight_dict)
+        return crit.weighted_total(losses, weight_dict)
 
     return crit, weighted_sum

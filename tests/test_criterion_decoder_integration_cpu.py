@@ -34,6 +34,7 @@ def test_decoder_outputs_through_criterion_and_back(monkeypatch):
     monkeypatch.setattr(native, "point_sample_rows", T._emu_sample)
     monkeypatch.setattr(native, "point_sample_rows_bwd", T._emu_sample_bwd)
     monkeypatch.setattr(native, "topk_gather_rows", T._emu_topk_gather)
+    monkeypatch.setattr(native, "MaskLossRows", T._EmuMaskLossRows)
     dec = build_decoder().train()
     x, mf = cases.decoder_inputs()
     targets = cases.dn_targets()

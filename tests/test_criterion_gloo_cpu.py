@@ -34,6 +34,7 @@ def _worker(rank, world, port, ret):
     native.point_sample_rows = T._emu_sample
     native.point_sample_rows_bwd = T._emu_sample_bwd
     native.topk_gather_rows = T._emu_topk_gather
+    native.MaskLossRows = T._EmuMaskLossRows
     outputs, targets = inputs(with_dn=True)                       # 2 images: 3 and 5 targets
 
     def shard(x):

@@ -24,12 +24,27 @@ def _host_map(ptr, is_f32, H, W):
     return np.ctypeslib.as_array((ct * (H * W)).from_address(int(ptr))).reshape(H, W)
 
 
-def _emu_sample(map_ptrs, maps_are_f32, hw, coords, neg_abs=False):
+def _emu_sample(map_ptrs, maps_are_f32, hw, coords, neg_abs=False, out=None):
     H, W = hw
     rows = [MO.point_sample(torch.from_numpy(_host_map(p, maps_are_f32, H, W).copy()).float()[None, None],
                             coords[r:r + 1])[0, 0] for r, p in enumerate(map_ptrs.tolist())]
-    out = torch.stack(rows)
-    return -out.abs() if neg_abs else out
+    res = torch.stack(rows)
+    res = -res.abs() if neg_abs else res
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+class _EmuMaskLossRows:
+    """native.MaskLossRows (csrc/mask_loss.cu): per-row BCE mean and dice term, as torch ops (ref criterion.py:25-68)."""
+
+    @staticmethod
+    def apply(x, y):
+        import torch.nn.functional as F
+        p = x.sigmoid()
+        dice = 1 - (2 * (p * y).sum(-1) + 1) / (p.sum(-1) + y.sum(-1) + 1)
+        return F.binary_cross_entropy_with_logits(x, y, reduction="none").mean(1), dice
 
 
 def _emu_sample_bwd(grad_map_ptrs, hw, coords, grad_out):
@@ -68,6 +83,7 @@ def host_kernels(monkeypatch):
     monkeypatch.setattr(native, "point_sample_rows", _emu_sample)
     monkeypatch.setattr(native, "point_sample_rows_bwd", _emu_sample_bwd)
     monkeypatch.setattr(native, "topk_gather_rows", _emu_topk_gather)
+    monkeypatch.setattr(native, "MaskLossRows", _EmuMaskLossRows)
 
 
 def _criterion(no_lb=False):
@@ -78,13 +94,18 @@ def _criterion(no_lb=False):
                         importance_sample_ratio=CFG["importance_sample_ratio"], dn_no_lb=no_lb)
 
 
-def test_criterion_host_logic_matches_reference_golden(host_kernels):
+@pytest.mark.parametrize("joint", [True, False])
+def test_criterion_host_logic_matches_reference_golden(host_kernels, joint):
+    """Both evaluation orders of the criterion -- all heads together (``_forward_heads``) and head by head -- against
+    the losses of the unmodified reference under the same seed (same random-number consumption)."""
     G = torch.load(os.path.join(HERE, "golden", "criterion.pt"), weights_only=False)
     for name, with_dn, training, no_lb, seed in CASES:
         outputs, targets = inputs(with_dn=with_dn)
         crit = _criterion(no_lb).train(training)
+        crit.joint_heads = joint
         torch.manual_seed(seed)
         got = crit(outputs, targets)
+        assert crit.last_path == ("heads" if joint else "sequential"), name
         ref = G[name]
         assert sorted(got) == sorted(ref), (name, sorted(set(got) ^ set(ref)))
         for k in ref:
@@ -92,7 +113,8 @@ def test_criterion_host_logic_matches_reference_golden(host_kernels):
     assert "num_points: 112" in repr(crit)
 
 
-def test_criterion_host_logic_gradients_match_oracle(host_kernels):
+@pytest.mark.parametrize("joint", [True, False])
+def test_criterion_host_logic_gradients_match_oracle(host_kernels, joint):
     """Gradients w.r.t. mask logits (a query slice of a larger tensor, like the decoder's [B, pad + Q, H, W]) and
     class logits, through the pointer-table backward, against autograd through the oracle."""
     outputs, targets = inputs(with_dn=True)
@@ -107,6 +129,7 @@ def test_criterion_host_logic_gradients_match_oracle(host_kernels):
         return {k: v.detach() for k, v in losses.items()}, masks_leaf.grad, logits_leaf.grad
 
     crit = _criterion().train(True)
+    crit.joint_heads = joint
     la, gm_a, gl_a = run(lambda o: crit(o, targets), full.clone().requires_grad_(True),
                          outputs["pred_logits"].clone().requires_grad_(True))
     lb, gm_b, gl_b = run(lambda o: CO.set_criterion(o, targets, losses=["labels", "masks"], training=True, **CFG),
@@ -116,6 +139,13 @@ def test_criterion_host_logic_gradients_match_oracle(host_kernels):
     assert torch.allclose(gm_a, gm_b, rtol=1e-4, atol=1e-7) and float(gm_b.abs().sum()) > 0
     assert torch.allclose(gl_a, gl_b, rtol=1e-5, atol=1e-7)
     assert float(gm_a[:, :3].abs().sum()) == 0.0
+    assert crit.last_path == ("heads" if joint else "sequential")
+    # the trainer's weighted total from the stacked values equals the entry-by-entry sum
+    torch.manual_seed(5)
+    losses = crit(outputs, targets)
+    wd = {k: 0.5 + 0.01 * i for i, k in enumerate(sorted(losses)) if "dice" not in k}
+    want = sum(v * wd[k] for k, v in losses.items() if k in wd)
+    assert torch.allclose(crit.weighted_total(losses, wd), want, rtol=1e-5)
 
 
 def test_criterion_mixed_target_sizes_and_empty_images(host_kernels):

@@ -99,6 +99,30 @@ def test_matcher_forward_contract_and_rng_consumption():
     assert "cost_class: 2.0" in repr(m)
 
 
+def test_match_device_heads_equals_head_by_head():
+    """Several prediction heads solved by one launch of the assignment kernel: the same pairs as one call per head
+    with the same points."""
+    from mp_former_b200.matcher import HungarianMatcher
+    outputs, targets = inputs()
+    o, t = _dev(outputs, targets)
+    g = torch.Generator(device="cuda").manual_seed(17)
+    heads = [o] + [{"pred_logits": torch.randn(o["pred_logits"].shape, device="cuda", generator=g),
+                    "pred_masks": torch.randn(o["pred_masks"].shape, device="cuda", generator=g) * 3} for _ in range(3)]
+    m = HungarianMatcher(2.0, 5.0, 5.0, num_points=300)
+    pts = [m.draw_points(len(t), "cuda") for _ in heads]
+    q, tt, status = m.match_device_heads(heads, t, pts)
+    assert int(status.item()) == 0
+    per_q, per_t = [], []
+    for h, p in zip(heads, pts):
+        qi, ti, _, _, st = m.match_device(h, t, point_coords=p)
+        assert int(st.item()) == 0
+        per_q.append(qi), per_t.append(ti)
+    assert torch.equal(q, torch.cat(per_q)) and torch.equal(tt, torch.cat(per_t))
+    heads[2]["pred_logits"][1, 0, 0] = float("nan")              # a failed problem is reported with its (head, image)
+    _, _, status = m.match_device_heads(heads, t, pts)
+    assert int(status.item()) == 1 + 2 * len(t) + 1
+
+
 def _lsap_cases():
     rng = np.random.default_rng(11)
     out = []

@@ -77,13 +77,18 @@ def _device_criterion(no_lb=False, device_indices=True):
                         importance_sample_ratio=CFG["importance_sample_ratio"], dn_no_lb=no_lb).cuda()
 
 
-def test_criterion_equals_oracle_on_device_all_cases():
+@pytest.mark.parametrize("joint", [True, False])
+def test_criterion_equals_oracle_on_device_all_cases(joint):
+    """All heads evaluated together (the default, ``SetCriterion._forward_heads``) and head by head: same losses as the
+    oracle under the same seed, i.e. the same random points."""
     for name, with_dn, training, no_lb, seed in CASES:
         outputs, targets = inputs(with_dn=with_dn)
         o, t = _to(outputs), _to(targets)
         crit = _device_criterion(no_lb).train(training)
+        crit.joint_heads = joint
         torch.manual_seed(seed)
         got = crit(o, t)
+        assert crit.last_path == ("heads" if joint else "sequential")
         torch.manual_seed(seed)
         ref = CO.set_criterion(o, t, losses=["labels", "masks"], training=training, dn_no_lb=no_lb, **CFG)
         assert sorted(got) == sorted(ref), (name, sorted(set(got) ^ set(ref)))
@@ -91,7 +96,8 @@ def test_criterion_equals_oracle_on_device_all_cases():
             assert torch.allclose(got[k], ref[k], rtol=1e-4, atol=1e-6), (name, k, got[k], ref[k])
 
 
-def test_criterion_gradients_equal_oracle_on_device():
+@pytest.mark.parametrize("joint", [True, False])
+def test_criterion_gradients_equal_oracle_on_device(joint):
     outputs, targets = inputs(with_dn=True)
     o, t = _to(outputs), _to(targets)
     full = torch.cat([torch.zeros(2, 3, 24, 32, device="cuda"), o["pred_masks"]], 1)
@@ -106,10 +112,38 @@ def test_criterion_gradients_equal_oracle_on_device():
         return masks_leaf.grad, logits_leaf.grad
 
     crit = _device_criterion().train(True)
+    crit.joint_heads = joint
     gm_a, gl_a = run(lambda oo: crit(oo, t))
     gm_b, gl_b = run(lambda oo: CO.set_criterion(oo, t, losses=["labels", "masks"], training=True, **CFG))
     assert torch.allclose(gm_a, gm_b, rtol=1e-4, atol=1e-6) and float(gm_b.abs().sum()) > 0
     assert torch.allclose(gl_a, gl_b, rtol=1e-4, atol=1e-6)
+    assert crit.last_path == ("heads" if joint else "sequential")
+
+
+def test_mask_loss_rows_kernel_equals_torch_losses():
+    """csrc/mask_loss.cu against the reference's formulas (criterion.py:25-68) in torch, values and gradients; fp32,
+    sums over 12544 points in a different order: 1e-5 relative."""
+    import torch.nn.functional as F
+    from mp_former_b200 import native
+    g = torch.Generator(device="cuda").manual_seed(8)
+    for R, P in ((37, 12544), (1, 1), (5, 255), (3, 1000)):
+        x0 = torch.randn(R, P, device="cuda", generator=g) * 4
+        x0[0, 0] = 60.0                                            # saturated logits stay finite
+        x0[-1, -1] = -60.0
+        y = (torch.rand(R, P, device="cuda", generator=g) > 0.6).float()
+        y[R // 2] = 0.0                                            # a target that misses every point
+        wb, wd = torch.randn(R, device="cuda", generator=g), torch.randn(R, device="cuda", generator=g)
+        xa, xb = x0.clone().requires_grad_(True), x0.clone().requires_grad_(True)
+        bce, dice = native.MaskLossRows.apply(xa, y)
+        p = xb.sigmoid()
+        ref_bce = F.binary_cross_entropy_with_logits(xb, y, reduction="none").mean(1)
+        ref_dice = 1 - (2 * (p * y).sum(-1) + 1) / (p.sum(-1) + y.sum(-1) + 1)
+        assert torch.allclose(bce, ref_bce, rtol=1e-5, atol=1e-7) and torch.allclose(dice, ref_dice, rtol=1e-5, atol=1e-7)
+        ((bce * wb).sum() + (dice * wd).sum()).backward()
+        ((ref_bce * wb).sum() + (ref_dice * wd).sum()).backward()
+        assert torch.allclose(xa.grad, xb.grad, rtol=1e-4, atol=1e-9), (xa.grad - xb.grad).abs().max()
+    with pytest.raises(RuntimeError):
+        native.MaskLossRows.apply(torch.zeros(2, 3), torch.zeros(2, 3))      # CPU tensors: no fallback
 
 
 def test_criterion_bench_geometry_properties():
@@ -140,6 +174,7 @@ def test_criterion_bench_geometry_properties():
                         eos_coef=0.1, losses=["labels", "masks"], num_points=12544, oversample_ratio=3.0,
                         importance_sample_ratio=0.75).cuda().train(True)
     losses = crit(out, targets)
+    assert crit.last_path == "heads"
     assert len(losses) == 18 and all(torch.isfinite(v) for v in losses.values())
     sum(v for k, v in losses.items() if "mask" in k or "dice" in k).backward()
     rows = out["pred_masks"].grad.abs().flatten(2).sum(-1) > 0
@@ -151,8 +186,9 @@ def test_criterion_bench_geometry_properties():
         assert dn_rows[b].nonzero().flatten().tolist() == expect
 
 
+@pytest.mark.parametrize("joint", [True, False])
 @pytest.mark.parametrize("fault", ["nan_logits", "label_out_of_range"])
-def test_criterion_failed_assignment_is_memory_safe_and_reported(fault):
+def test_criterion_failed_assignment_is_memory_safe_and_reported(fault, joint):
     """Diverged logits (NaN costs) or a label outside [0, num_classes): the reference gets scipy's ValueError (or a
     device assert).  Here the solve reports a status instead of a host round trip: the pairs stay in range (nothing
     is read or written outside the prediction / gradient buffers -- run under compute-sanitizer memcheck by
@@ -169,6 +205,7 @@ def test_criterion_failed_assignment_is_memory_safe_and_reported(fault):
     leaf = full.clone().requires_grad_(True)
     o["pred_masks"] = leaf[:, 3:]
     crit = _device_criterion().train(True)
+    crit.joint_heads = joint
     losses = crit(o, t)
     assert all(bool(torch.isnan(v)) for v in losses.values())
     sum(v for v in losses.values() if v.requires_grad).backward()
