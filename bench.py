@@ -602,6 +602,21 @@ def run_ours(a):
         hbm, tens, src = peaks()
         step_ms = ms_total / a.steps
 
+        def ncu_traffic(kernel):
+            """DRAM bytes per launch of `kernel` (dram__bytes_read.sum + dram__bytes_write.sum, mean over its launches
+            in one training step) from the committed ncu launch list of THIS workload (config 2, 16 images, criterion:
+            profiles/r2k_launch_summary_step_b16.txt, made by scripts/gpu_r2_call11.sh); None for other workloads --
+            ncu cannot run inside the timed bench."""
+            path = os.path.join(ROOT, "profiles", "r2k_launch_summary_step_b16.txt")
+            cfg_idx = a.config if a.config else (2 if world == 1 else 3)
+            if cfg_idx != 2 or B != 16 or a.loss != "criterion" or not os.path.exists(path):
+                return None
+            for ln in open(path):
+                f = ln.split()
+                if len(f) >= 7 and not ln.startswith("#") and kernel in " ".join(f[6:]):
+                    return (float(f[4]) + float(f[5])) * 1e6
+            return None
+
         def gemm_roof(kind, what, mma_per_product=3.0):
             r = gprof.get(kind)
             if not r or r["ms"] <= 0:
@@ -613,7 +628,7 @@ def run_ours(a):
             # tensor peak for the MMAs the split arithmetic issues; the larger one is the roofline
             t_hbm = r["bytes"] / (hbm * 1e9)
             t_tensor = mma_per_product * r["flops"] / (tens * 1e12)
-            common = {"kernel": f"{kind} ({what})", "traffic": None,
+            common = {"kernel": f"{kind} ({what})", "traffic": ncu_traffic(kind),
                       "tensor_TFLOPs_algorithmic": tf, "tensor_frac_algorithmic": tf / tens,
                       "tensor_issue_frac": mma_per_product * tf / tens, "achieved_hbm_GBs": gb, "hbm_frac": gb / hbm,
                       "frac_of_combined_roof": max(t_hbm, t_tensor) / (r["ms"] / 1e3),
@@ -636,7 +651,8 @@ def run_ours(a):
         if fwd_ms:
             ach = alg / (fwd_ms / 1e3) / 1e9
             msda = {"kernel": "msda_enc_fwd_kernel<8> (MSDeformAttn forward, softmax+locations fused)",
-                    "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+                    "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                    "traffic": ncu_traffic("msda_enc_fwd_kernel"),
                     "peak_source": src + " hbm_gbs", "algorithmic_bytes_per_launch": alg, "avg_launch_ms": fwd_ms,
                     "launches_timed": len(prof["fwd_ms"]),
                     "share_of_step": fwd_ms * len(prof["fwd_ms"]) / n_prof / step_ms}
@@ -646,6 +662,7 @@ def run_ours(a):
                                     "achieved": alg_b / (bwd_ms / 1e3) / 1e9,
                                     "frac": alg_b / (bwd_ms / 1e3) / 1e9 / hbm,
                                     "algorithmic_bytes_per_launch": alg_b,
+                                    "traffic": ncu_traffic("msda_enc_bwd_kernel"),
                                     "share_of_step": bwd_ms * len(prof["bwd_ms"]) / n_prof / step_ms}
         gk = gemm_roof("gemm_bf16x3_kernel", "linears / 1x1 convs / mask logits / projections, fwd + input grads")
         gt = gemm_roof("gemm_bf16x3_tn_kernel", "weight gradients, dF of the mask logits")

@@ -167,7 +167,7 @@ def main():
         del logits
     if "xattn" in which:
         E, heads, Qt = 256, 8, 120
-        for HW in (1024, 4096, 16384):
+        for HW in ([int(os.environ["MPF_HW"])] if os.environ.get("MPF_HW") else [1024, 4096, 16384]):
             q, k, vt = rn(B, Qt, E), rn(B, HW, E), rn(B, E, HW)
             qh, ql = native.split_tf32(q); kh, kl = native.split_tf32(k); vh, vl = native.split_tf32(vt)
             bits = native.pack_bool_bits(torch.rand(B, Qt, HW, device=DEV, generator=g) < 0.7)

@@ -59,6 +59,7 @@ struct Args {
   float alpha;
   int batch, M, N, K;
   int bn;                                     // N tile (multiple of 32, <= 256)
+  int sbufs;                                  // staging tiles per epilogue group (1 or 2)
   int tiles_m, tiles_n;
   int k_splits, k_per_split;
   int stages, stage_bytes;
@@ -204,8 +205,8 @@ gemm_bf16x3_kernel_t(const __grid_constant__ CUtensorMap tmA, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int S = g.stages;
-  uint8_t* staging = smem + S * g.stage_bytes;                 // 2 x 16 KiB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * kStagingBytes);
+  uint8_t* staging = smem + S * g.stage_bytes;                 // 2 groups x sbufs x 16 KiB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * g.sbufs * kStagingBytes);
   uint64_t* full = bars;                         // [S] TMA bytes landed
   uint64_t* conv = bars + kMaxStages;            // [S] A_hi / A_lo written
   uint64_t* empty = bars + 2 * kMaxStages;       // [S] MMAs reading the stage retired
@@ -290,7 +291,7 @@ gemm_bf16x3_kernel_t(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
           }
           if (ldB) {
-            uint8_t* bs = st + kRawABytes + 2 * kOpABytes;
+            uint8_t* bs = st + kRawABytes;
             if (kPair) {
               tma_load_3d_pair(bs, &tmBhi, &full[stage], kb * kBK, n_t * BN + rank * b_rows, bb);
               tma_load_3d_pair(bs + b_bytes, &tmBlo, &full[stage], kb * kBK, n_t * BN + rank * b_rows, bb);
@@ -320,7 +321,7 @@ gemm_bf16x3_kernel_t(const __grid_constant__ CUtensorMap tmA, const __grid_const
           mbar_wait(&conv[stage], phase);
           tc_fence_after();
           const uint32_t st = smem_u32(smem + stage * g.stage_bytes);
-          const uint32_t a_hi = st + kRawABytes;
+          const uint32_t a_hi = st;                  // converted IN PLACE over the raw fp32 tile
           const uint32_t a_lo = a_hi + kOpABytes;
           const uint32_t b_hi = a_lo + kOpABytes;
           const uint32_t b_lo = b_hi + b_bytes;
@@ -369,12 +370,17 @@ gemm_bf16x3_kernel_t(const __grid_constant__ CUtensorMap tmA, const __grid_const
         mbar_wait(kPair ? &fullA[stage] : &full[stage], phase);
         uint8_t* st = smem + stage * g.stage_bytes;
         if (!(g.debug & 4)) {
+          // The bf16 halves (2 x 8 KiB) replace the raw fp32 tile (16 KiB) IN PLACE: every thread reads its raw row
+          // into registers, the 128 converter threads meet at a named barrier, then the halves are written.  A
+          // stage is 48 KiB instead of 64 KiB at BN = 256, i.e. FOUR stages in flight instead of three: with three
+          // the main loop waited for loads (probe: 0.70 ms with two stages, 0.56 ms with three, profiles/r2m_*).
           const uint8_t* raw = st + r * 128;
-          uint8_t* ohi = st + kRawABytes + r * 64;
+          uint8_t* ohi = st + r * 64;
           uint8_t* olo = ohi + kOpABytes;
           float4 x[8];
 #pragma unroll
           for (int c = 0; c < 8; ++c) x[c] = *reinterpret_cast<const float4*>(raw + ((c ^ rsw) << 4));
+          epi_bar(3);
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
             const float4 u = x[2 * p], v = x[2 * p + 1];
@@ -407,7 +413,11 @@ gemm_bf16x3_kernel_t(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int trow = ew * 32 + lane;               // row of the tile this thread drains
     const bool issuer = (ew == 0 && lane == 0);
     const int bar_id = 1 + eg;
-    uint8_t* const sbuf = staging + eg * kStagingBytes;
+    // g.sbufs staging tiles per group, used in turn: with two, the TMA store of a chunk still reads its tile while
+    // the group fills the other one (the wait below then only covers the store before the previous one)
+    uint8_t* const sbuf0 = staging + eg * g.sbufs * kStagingBytes;
+    uint8_t* sbuf = sbuf0;
+    int scur = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     const int nchunks = BN / 32;
@@ -552,8 +562,15 @@ gemm_bf16x3_kernel_t(const __grid_constant__ CUtensorMap tmA, const __grid_const
             bulk_commit();
           }
         };
-        if (issuer) bulk_wait_read<0>();            // the previous store of this group has left the staging tile
-        epi_bar(bar_id);
+        auto next_tile = [&]() {                    // the store that last used this staging tile has read it
+          sbuf = sbuf0 + scur * kStagingBytes;
+          if (issuer) {
+            if (g.sbufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+          }
+          if (g.sbufs == 2) scur ^= 1;
+          epi_bar(bar_id);
+        };
+        next_tile();
         if (!g.split_out) {
           put(f);
           flush(&tmC);
@@ -567,8 +584,7 @@ gemm_bf16x3_kernel_t(const __grid_constant__ CUtensorMap tmA, const __grid_const
           }
           put(f);
           flush(&tmC);
-          if (issuer) bulk_wait_read<0>();
-          epi_bar(bar_id);
+          next_tile();
           put(lo);
           flush(&tmClo);
         }
@@ -727,6 +743,10 @@ static int make_tmap_f32_4d(CUtensorMap* m, const float* base, long long d0, lon
 // arithmetic, and the leader's issue thread waits on cross-SM barriers.  Kept as an option and as a measured answer.
 static int g_pair_mode = [] { const char* e = getenv("MPF_GEMM_PAIR"); return e ? atoi(e) : 0; }();
 
+// measurement knobs (environment, read once): staging tiles per epilogue group and a cap on the pipeline stages
+static int g_staging_tiles = [] { const char* e = getenv("MPF_GEMM_SBUFS"); return e && atoi(e) == 2 ? 2 : 1; }();
+static int g_max_stages = [] { const char* e = getenv("MPF_GEMM_STAGES"); return e ? atoi(e) : 0; }();
+
 static int pick_bn(int N) {
   if (N <= 64) return 64;
   for (int bn = 256; bn >= 64; bn -= 32) {
@@ -809,12 +829,18 @@ static int gemm_bf16x3_impl(const float* A, long long lda, long long a_batch_str
   const bool pair = g_pair_mode != 0 && g.tiles_m >= 2 && sm_count() % 2 == 0 &&
                     (g_pair_mode == 2 || pair_tiles >= sm_count() / 2);
   const int b_rows = pair ? g.bn / 2 : g.bn;
-  g.stage_bytes = kRawABytes + 2 * kOpABytes + 2 * b_rows * kBK * 2;
-  const int avail = kSmemBudget - 1024 - 2 * kStagingBytes - 512;
+  g.stage_bytes = kRawABytes + 2 * b_rows * kBK * 2;      // A: raw fp32, converted in place to bf16 hi | lo
+  g.sbufs = g_staging_tiles;
+  int avail = kSmemBudget - 1024 - 2 * g.sbufs * kStagingBytes - 512;
+  if (g.sbufs == 2 && avail / g.stage_bytes < 2) {       // not with this stage size: back to one staging tile per group
+    g.sbufs = 1;
+    avail = kSmemBudget - 1024 - 2 * kStagingBytes - 512;
+  }
   g.stages = avail / g.stage_bytes;
   if (g.stages > kMaxStages) g.stages = kMaxStages;
+  if (g_max_stages >= 2 && g.stages > g_max_stages) g.stages = g_max_stages;
   MPF_REQUIRE(g.stages >= 2, "gemm_bf16x3: not enough shared memory for two stages");
-  const int smem_bytes = g.stages * g.stage_bytes + 2 * kStagingBytes + 512 + 1024;
+  const int smem_bytes = g.stages * g.stage_bytes + 2 * g.sbufs * kStagingBytes + 512 + 1024;
   g.b_broadcast = (b_batch_stride == 0) ? 1 : 0;
   const int slabs = batch * k_splits;
 

@@ -257,7 +257,7 @@ __device__ __forceinline__ ScanKey key_shfl_xor(const ScanKey& k, int m) {
 }
 
 __global__ void __launch_bounds__(LSAP_THREADS)
-lsap_kernel(const float* __restrict__ cost, const int* __restrict__ offsets, int Q, int dim,
+lsap_kernel(const float* __restrict__ cost, const int* __restrict__ offsets, int Q, int dim, int cache_cost,
             long long* __restrict__ out_q, long long* __restrict__ out_t, int* __restrict__ status) {
   extern __shared__ double lsap_smem[];
   double* u = lsap_smem;            // [dim] rows
@@ -269,6 +269,7 @@ lsap_kernel(const float* __restrict__ cost, const int* __restrict__ offsets, int
   int* remaining = row4col + dim;
   int* SR = remaining + dim;
   int* SC = SR + dim;
+  float* c_smem = reinterpret_cast<float*>(SC + dim);          // [Q * n] when cache_cost
   __shared__ ScanKey s_key[LSAP_THREADS / 32];
   __shared__ int s_i, s_sink, s_num_remaining, s_fail;
   __shared__ double s_min;
@@ -279,7 +280,12 @@ lsap_kernel(const float* __restrict__ cost, const int* __restrict__ offsets, int
   long long out0 = 0;
   for (int bb = 0; bb < b; ++bb) out0 += min(Q, offsets[bb + 1] - offsets[bb]);
   if (n <= 0) return;
-  const float* C = cost + static_cast<long long>(Q) * n0;    // [Q, n] row-major
+  const float* Cg = cost + static_cast<long long>(Q) * n0;   // [Q, n] row-major
+  // The search below reads ONE cost entry per candidate column and step, each on the critical path of a serial
+  // algorithm: from global memory that is an L2 round trip per step (the solve of a 100 x 20 matrix took 150 us,
+  // scipy on a host core ~20 us).  The matrix (<= 40 KB for 100 queries x 100 targets) is therefore copied to shared
+  // memory by the validity pre-scan, which reads every entry anyway.
+  const float* C = cache_cost ? c_smem : Cg;
   const bool transposed = n < Q;                              // scipy: solve the transpose of a tall matrix
   const int nr = transposed ? n : Q, nc = transposed ? Q : n;
   const long long si = transposed ? 1 : n, sj = transposed ? n : 1;   // cost(i, j) = C[i * si + j * sj]
@@ -294,7 +300,8 @@ lsap_kernel(const float* __restrict__ cost, const int* __restrict__ offsets, int
     int bad = 0;
     const long long total = static_cast<long long>(Q) * n;
     for (long long k = tid; k < total; k += LSAP_THREADS) {
-      const float c = __ldg(C + k);
+      const float c = __ldg(Cg + k);
+      if (cache_cost) c_smem[k] = c;
       bad |= (c != c) || (c == -CUDART_INF_F);
     }
     if (bad) s_fail = 1;
@@ -313,7 +320,7 @@ lsap_kernel(const float* __restrict__ cost, const int* __restrict__ offsets, int
       best.value = CUDART_INF; best.cls = 2; best.ord = 0; best.it = -1;
       for (int it = tid; it < num_remaining; it += LSAP_THREADS) {
         const int j = remaining[it];
-        const double r = min_val + static_cast<double>(__ldg(C + i * si + j * sj)) - ui - v[j];
+        const double r = min_val + static_cast<double>(C[i * si + j * sj]) - ui - v[j];
         double d = spc[j];
         if (r < d) { path[j] = i; spc[j] = r; d = r; }
         if (d < CUDART_INF) {
@@ -498,14 +505,17 @@ int mpf_lsap_f32(const float* cost, const int32_t* tgt_offsets, int batch, int n
   if (max_targets == 0) return MPF_OK;
   MPF_REQUIRE(cost && tgt_offsets && out_query && out_target && status, "lsap: null pointer argument");
   const int dim = max(num_queries, max_targets);
-  const size_t smem = static_cast<size_t>(dim) * (3 * sizeof(double) + 6 * sizeof(int));
+  size_t smem = static_cast<size_t>(dim) * (3 * sizeof(double) + 6 * sizeof(int));
   MPF_REQUIRE(smem <= 200 * 1024, "lsap: max(queries, targets) = %d exceeds the shared-memory solver's limit (4266)",
               dim);
+  const size_t matrix = static_cast<size_t>(num_queries) * max_targets * sizeof(float);
+  const int cache_cost = smem + matrix <= 200 * 1024 ? 1 : 0;       // the largest image's matrix fits next to the state
+  if (cache_cost) smem += matrix;
   static unsigned long long seen = 0;
-  if (smem > 48 * 1024 && first_use_on_this_device(seen))
+  if (first_use_on_this_device(seen))
     MPF_CUDA_OK(cudaFuncSetAttribute(lsap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   lsap_kernel<<<batch, LSAP_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
-      cost, tgt_offsets, num_queries, dim, reinterpret_cast<long long*>(out_query),
+      cost, tgt_offsets, num_queries, dim, cache_cost, reinterpret_cast<long long*>(out_query),
       reinterpret_cast<long long*>(out_target), status);
   count_launch();
   return finish_launch("lsap");
