@@ -6,11 +6,14 @@
 // SWIZZLE_128B operand layout -- no transposed copies, no pre-split pass over HBM.
 //   D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (tcgen05.mma.kind::f16, fp32 accumulate in TMEM; ~2^-16 per product).
 //
-// Pipeline (one persistent CTA per SM, 16 warps), two decoupled rings so that raw loads run ahead of the MMAs:
-//   warp 0       TMA producer    raw ring: [32 tokens x 32 columns] fp32 boxes (SWIZZLE_128B), 4 for A, BN/32 for B
-//   warps 8-15   converters      raw ring -> operand ring (bf16 hi/lo, MN-major SW128: rows = token, 64 columns per
-//                                128-byte row, 4 KiB per 64-column group); frees the raw slot as soon as it is read
-//   warp 1       MMA issuer      2 k-steps x 3 MMAs (M=128, N=BN, K=16) per 32-token block; commit frees the operand slot
+// Pipeline (one persistent CTA per SM, 16 warps), ONE ring of slots that hold a 32-token block first raw, then split:
+//   warp 0       TMA producer    [32 tokens x 32 columns] fp32 boxes (SWIZZLE_128B), 4 for A, BN/32 for B, per slot
+//   warps 8-15   converters      read the raw boxes into registers, meet at a named barrier, write the bf16 hi/lo
+//                                halves IN PLACE (same bytes: MN-major SW128, rows = token, 64 columns per 128-byte
+//                                row, 4 KiB per 64-column group).  Round 2: with separate raw / operand rings only
+//                                two loads were in flight per SM and the main loop waited for them (~1200 cycles
+//                                per block against 768 of MMA); in place, 48 KiB slots give four blocks in flight.
+//   warp 1       MMA issuer      2 k-steps x 3 MMAs (M=128, N=BN, K=16) per 32-token block; commit frees the slot
 //   warps 4-7    epilogue        tcgen05.ld -> staging tile -> TMA store (split-K partial slabs, summed by the caller)
 //   warp 2       TMEM allocation
 #include "mpf_common.cuh"
@@ -37,14 +40,15 @@ constexpr int kThreads = 512;
 constexpr int kConvThreads = 256;
 constexpr int kSmemBudget = 232448;
 constexpr int kTmemCols = 512;
-constexpr int kRing = 2;                       // slots in each ring
+constexpr int kMaxRing = 6;                    // slots of the ring (as many as fit: 4 at BN = 256)
 
 struct Args {
   int batch, M, N, T;
   int bn;                                      // 64, 128, 192 or 256
   int tiles_m, tiles_n;
   int k_splits, k_per_split;                   // tokens per split (multiple of 32)
-  int raw_bytes, op_bytes;                     // per ring slot
+  int raw_bytes, op_bytes;                     // per ring slot (equal: the split halves replace the raw boxes)
+  int ring;                                    // slots
   int debug;
   int accumulate;                              // 1: C += product (TMA reduce-add store) instead of C = product
   // weight gradient of a 3x3 convolution over channels-last maps (conv_W > 0): the reduction index is the pixel
@@ -75,6 +79,7 @@ __device__ __forceinline__ void bulk_wait_read() {
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void conv_bar() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
 
 __device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                             uint32_t accumulate) {
@@ -129,17 +134,17 @@ gemm_bf16x3_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                       const __grid_constant__ CUtensorMap tmC, const Args g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int kRing = g.ring;
   uint8_t* raw_ring = smem;
-  uint8_t* op_ring = smem + kRing * g.raw_bytes;
-  uint8_t* staging = op_ring + kRing * g.op_bytes;             // 2 x 16 KiB
+  uint8_t* op_ring = smem;                                     // the same slots: converted in place
+  uint8_t* staging = smem + kRing * g.raw_bytes;               // 2 x 16 KiB
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * kStagingBytes);
-  uint64_t* raw_full = bars;                 // [kRing] TMA bytes landed
-  uint64_t* raw_empty = bars + kRing;        // [kRing] converters done reading (8 warps)
-  uint64_t* op_full = bars + 2 * kRing;      // [kRing] operand halves written (8 warps)
-  uint64_t* op_empty = bars + 3 * kRing;     // [kRing] MMAs reading the slot retired
-  uint64_t* tfull = bars + 4 * kRing;        // [2]
-  uint64_t* tempty = bars + 4 * kRing + 2;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * kRing + 4);
+  uint64_t* raw_full = bars;                 // [ring] TMA bytes landed
+  uint64_t* op_full = bars + kMaxRing;       // [ring] operand halves written (8 warps)
+  uint64_t* op_empty = bars + 2 * kMaxRing;  // [ring] MMAs reading the slot retired
+  uint64_t* tfull = bars + 3 * kMaxRing;     // [2]
+  uint64_t* tempty = bars + 3 * kMaxRing + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kMaxRing + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -154,7 +159,6 @@ gemm_bf16x3_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     prefetch_tmap(&tmC);
     for (int s = 0; s < kRing; ++s) {
       mbar_init(&raw_full[s], 1);
-      mbar_init(&raw_empty[s], kConvThreads / 32);
       mbar_init(&op_full[s], kConvThreads / 32);
       mbar_init(&op_empty[s], 1);
     }
@@ -187,7 +191,7 @@ gemm_bf16x3_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const int b = rest / g.k_splits;
         for (int kbi = 0; kbi < kblocks; ++kbi) {
           const int t0 = ks * g.k_per_split + kbi * kBK;
-          mbar_wait(&raw_empty[slot], phase ^ 1);
+          mbar_wait(&op_empty[slot], phase ^ 1);
           uint8_t* st = raw_ring + slot * g.raw_bytes;
           mbar_arrive_expect_tx(&raw_full[slot], (4 + b_boxes) * kBoxBytes);
           if (g.conv_ws) {
@@ -274,32 +278,40 @@ gemm_bf16x3_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(&raw_full[slot], phase);
-        mbar_wait(&op_empty[slot], phase ^ 1);
         if (!(g.debug & 4)) {
           const uint8_t* raw = raw_ring + slot * g.raw_bytes + k * 128;
           uint8_t* opa = op_ring + slot * g.op_bytes + k * 128;
           uint8_t* opb = opa + 2 * a_op_bytes;
-#pragma unroll 2
-          for (int box = par; box < n_boxes; box += 2) {
-            const uint8_t* rb = raw + box * kBoxBytes;
-            const float4 u = *reinterpret_cast<const float4*>(rb + (((2 * mc) ^ sw) << 4));
-            const float4 v = *reinterpret_cast<const float4*>(rb + (((2 * mc + 1) ^ sw) << 4));
-            uint4 h, l;
-            split8(u, v, h, l);
-            const bool is_a = box < 4;
-            const int bi = is_a ? box : box - 4;
-            uint8_t* dst = (is_a ? opa : opb) + (bi >> 1) * kGroupBytes + (((((bi & 1) << 2) + mc) ^ sw) << 4);
-            const int half_bytes = is_a ? a_op_bytes : b_op_bytes;
-            *reinterpret_cast<uint4*>(dst) = h;
-            *reinterpret_cast<uint4*>(dst + half_bytes) = l;
+          // raw boxes of this thread -> registers; all 256 converter threads; then the halves over the same bytes
+          float4 u[6], v[6];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            const int box = par + 2 * i;
+            if (box < n_boxes) {
+              const uint8_t* rb = raw + box * kBoxBytes;
+              u[i] = *reinterpret_cast<const float4*>(rb + (((2 * mc) ^ sw) << 4));
+              v[i] = *reinterpret_cast<const float4*>(rb + (((2 * mc + 1) ^ sw) << 4));
+            }
+          }
+          conv_bar();
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            const int box = par + 2 * i;
+            if (box < n_boxes) {
+              uint4 h, l;
+              split8(u[i], v[i], h, l);
+              const bool is_a = box < 4;
+              const int bi = is_a ? box : box - 4;
+              uint8_t* dst = (is_a ? opa : opb) + (bi >> 1) * kGroupBytes + (((((bi & 1) << 2) + mc) ^ sw) << 4);
+              const int half_bytes = is_a ? a_op_bytes : b_op_bytes;
+              *reinterpret_cast<uint4*>(dst) = h;
+              *reinterpret_cast<uint4*>(dst + half_bytes) = l;
+            }
           }
           fence_proxy_async_smem();
         }
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&op_full[slot]);
-          mbar_arrive(&raw_empty[slot]);
-        }
+        if (lane == 0) mbar_arrive(&op_full[slot]);
         if (++slot == kRing) { slot = 0; phase ^= 1; }
       }
     }
@@ -484,8 +496,15 @@ static int gemm_bf16x3_tn_impl(const float* A, long long lda, long long a_batch_
   g.k_per_split = (kblocks_total + k_splits - 1) / k_splits * kBK;
   g.raw_bytes = (4 + g.bn / 32) * kBoxBytes;
   g.op_bytes = 2 * (2 + g.bn / 64) * kGroupBytes;
-  const int smem_bytes = kRing * (g.raw_bytes + g.op_bytes) + 2 * kStagingBytes + 512 + 1024;
-  MPF_REQUIRE(smem_bytes <= kSmemBudget, "gemm_bf16x3_tn: shared-memory budget exceeded");
+  MPF_REQUIRE(g.raw_bytes == g.op_bytes, "gemm_bf16x3_tn: raw and split slot sizes differ");
+  g.ring = (kSmemBudget - 1024 - 512 - 2 * kStagingBytes) / g.raw_bytes;
+  if (g.ring > kMaxRing) g.ring = kMaxRing;
+  if (const char* e = getenv("MPF_GEMM_TN_RING")) {          // measurement knob
+    const int r = atoi(e);
+    if (r >= 2 && r < g.ring) g.ring = r;
+  }
+  MPF_REQUIRE(g.ring >= 2, "gemm_bf16x3_tn: shared-memory budget exceeded");
+  const int smem_bytes = g.ring * g.raw_bytes + 2 * kStagingBytes + 512 + 1024;
   MPF_REQUIRE(static_cast<long long>(batch) * k_splits * g.tiles_m * g.tiles_n < (1ll << 31), "gemm_bf16x3_tn: too many tiles");
   g.debug = 0;
   if (const char* dbg = getenv("MPF_GEMM_DEBUG")) g.debug = atoi(dbg);
