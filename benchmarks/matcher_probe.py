@@ -56,6 +56,7 @@ def main():
     coords = torch.rand(B, P, 2, device=DEV, generator=g)
     sort_points = os.environ.get("MPF_SORT_POINTS", "0") == "1"
     m = HungarianMatcher(2.0, 5.0, 5.0, num_points=P, device_indices=True, sort_points=sort_points)
+    m.stream_samples = os.environ.get("MPF_STREAM", "1") == "1"
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
     for _ in range(3):
         m.match_device(outputs, targets, point_coords=coords)
@@ -69,6 +70,14 @@ def main():
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(e))
     ours_ms = statistics.median(ts)
+    if os.environ.get("MPF_PROFILE"):
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            m.match_device(outputs, targets, point_coords=coords)
+            torch.cuda.synchronize()
+        for e in sorted(prof.key_averages(), key=lambda e: -e.self_device_time_total):
+            if e.self_device_time_total > 0:
+                print(f"# {e.self_device_time_total:9.1f} us  x{e.count:3d}  {e.key[:110]}")
     for _ in range(2):
         ref = stock_match(outputs, targets, coords, 2.0, 5.0, 5.0)
     ws = []
@@ -88,7 +97,7 @@ def main():
     print(json.dumps({"probe": "hungarian_matcher_one_head", "B": B, "Q": Q, "points": P, "targets_total": ntot,
                       "device_ms": ours_ms, "stock_torch_scipy_ms_wall": stock_ms, "speedup": stock_ms / ours_ms,
                       "same_assignment_as_stock": bool(same), "gather_sector_GBps": sector_bytes / ours_ms / 1e6,
-                      "host_syncs": {"device": 0, "stock": B}, "sort_points": sort_points}))
+                      "host_syncs": {"device": 0, "stock": B}, "sort_points": sort_points, "stream_samples": bool(sort_points and m.stream_samples)}))
 
 
 if __name__ == "__main__":

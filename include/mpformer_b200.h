@@ -414,6 +414,24 @@ int mpf_match_cost_f32(const float* pred_logits, long long logits_img_stride, lo
                        int max_targets, const float* point_coords, int batch, int num_queries, int num_points,
                        float cost_class, float cost_mask, float cost_dice, void* workspace,
                        long long workspace_bytes, float* cost, void* stream);
+/* The matcher's prediction samples through a STREAMING pass instead of gathers (same reference lines: the
+ * point_sample of out_mask at matcher.py:124-131): every [H, W] map maps[b, q] is read once, band by band, into shared
+ * memory and evaluated at the image's P shared points -> out [B, Q, P] (fp32).  point_coords [B, P, 2] should be
+ * ordered row-major by the top-left pixel of the bilinear footprint, with band_lo [B, n_bands + 1] (int32) holding
+ * the index of the first point of every band of band_rows rows (band_lo[b][n_bands] = P); points whose footprint
+ * lies outside their band are still sampled correctly (from global memory), only slower.  W % 4 == 0.
+ * mpf_match_cost_presampled_f32 is mpf_match_cost_f32 with those samples in place of (pred_masks, strides). */
+int mpf_sample_shared_points_f32(const float* maps, long long img_stride, long long q_stride, int H, int W,
+                                 const float* point_coords, const int32_t* band_lo, int n_bands, int band_rows,
+                                 int batch, int num_queries, int num_points, float* out, void* stream);
+int mpf_match_cost_presampled_f32(const float* pred_logits, long long logits_img_stride, long long logits_q_stride,
+                                  int num_classes_p1, const float* sampled, int H, int W,
+                                  const void* const* tgt_mask_ptrs, int tgt_is_f32, int Hg, int Wg,
+                                  const int64_t* tgt_labels, const int32_t* tgt_offsets, int total_targets,
+                                  int max_targets, const float* point_coords, int batch, int num_queries,
+                                  int num_points, float cost_class, float cost_mask, float cost_dice, void* workspace,
+                                  long long workspace_bytes, float* cost, void* stream);
+
 int mpf_lsap_f32(const float* cost, const int32_t* tgt_offsets, int batch, int num_queries, int max_targets,
                  int64_t* out_query, int64_t* out_target, int32_t* status, void* stream);
 

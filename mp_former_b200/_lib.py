@@ -84,6 +84,12 @@ SIGNATURES = {
     "mpf_match_cost_f32": (_c_int, [_c_vp, _c_ll, _c_ll, _c_int, _c_vp, _c_ll, _c_ll, _c_int, _c_int, _c_vp, _c_int,
                                     _c_int, _c_int, _c_vp, _c_vp, _c_int, _c_int, _c_vp, _c_int, _c_int, _c_int,
                                     ctypes.c_float, ctypes.c_float, ctypes.c_float, _c_vp, _c_ll, _c_vp, _c_vp]),
+    "mpf_sample_shared_points_f32": (_c_int, [_c_vp, _c_ll, _c_ll, _c_int, _c_int, _c_vp, _c_vp, _c_int, _c_int, _c_int,
+                                              _c_int, _c_int, _c_vp, _c_vp]),
+    "mpf_match_cost_presampled_f32": (_c_int, [_c_vp, _c_ll, _c_ll, _c_int, _c_vp, _c_int, _c_int, _c_vp, _c_int,
+                                               _c_int, _c_int, _c_vp, _c_vp, _c_int, _c_int, _c_vp, _c_int, _c_int,
+                                               _c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, _c_vp, _c_ll,
+                                               _c_vp, _c_vp]),
     "mpf_lsap_f32": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp]),
     "mpf_point_sample_rows": (_c_int, [_c_vp, _c_int, _c_int, _c_int, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
     "mpf_point_sample_rows_bwd_f32": (_c_int, [_c_vp, _c_int, _c_int, _c_vp, _c_int, _c_int, _c_vp, _c_vp]),

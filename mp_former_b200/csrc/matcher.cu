@@ -28,6 +28,7 @@
 // L2-resident); arithmetic is ~1 GFLOP per head.
 #include "mpf_common.cuh"
 #include "point_sample.cuh"
+#include "sm100_ptx.cuh"
 
 #include <math_constants.h>
 
@@ -47,6 +48,7 @@ struct MatchCostArgs {
   const void* const* tgt_mask_ptrs;  // [B] device pointers, each [n_b, Hg, Wg] contiguous (uint8 0/1 or float)
   const int* tgt_offsets;         // [B + 1] prefix sums of n_b
   const float* point_coords;      // [B, P, 2] (x, y) in [0, 1]
+  const float* sampled;           // optional [B, Q, P]: the prediction logits already sampled at the points
   float* part3;                   // [S, Q, ntot, 3]
   float* part_sig;                // [S, B, Q]
   float* part_t;                  // [S, ntot]
@@ -108,7 +110,10 @@ __global__ void __launch_bounds__(MC_THREADS, 3) match_cost_partial_kernel(const
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int qq = q4 + u * PARTS;
-          x[u] = (valid && qq < nq) ? sample_map(pm + qq * a.masks_q_stride, cp) : 0.f;
+          if (!(valid && qq < nq)) x[u] = 0.f;
+          else if (a.sampled != nullptr)
+            x[u] = __ldg(a.sampled + (static_cast<long long>(b) * a.Q + q0 + qq) * a.P + pidx);   // lanes = points: coalesced
+          else x[u] = sample_map(pm + qq * a.masks_q_stride, cp);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -188,6 +193,82 @@ __global__ void __launch_bounds__(MC_THREADS, 3) match_cost_partial_kernel(const
       const int jl = wj * 4 + k;
       if (jl < nj) a.part_t[static_cast<long long>(s) * a.ntot + n0 + j0 + jl] = sumT[k];
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Streaming sampler for the matcher's SHARED points: all Q maps of an image are sampled at the same P points
+// (matcher.py:120-131), and 12544 points with their 2x2 footprints touch most of a 256 x 256 map.  Gathering them
+// costs a 32-byte DRAM sector per corner once the logits of a head (419 MB at 16 images) exceed the L2 -- 661 MB of
+// sector traffic and, worse, the latency of dependent random loads (0.45 ms per head).  Here a CTA owns one map,
+// streams it through shared memory band by band with coalesced 16-byte loads (each byte read once: the map's own
+// size) and evaluates the points whose footprint starts in the band from shared memory.  The points arrive sorted
+// row-major (HungarianMatcher.row_major_order) with the first point of every band in band_lo; a point whose
+// footprint is not inside the staged band after all (a caller's own order, rounding at a band edge) is sampled from
+// global memory instead, so the result never depends on the order.
+//   grid (Q, B), 512 threads, shared memory (rows + 1) * W floats.   out [B, Q, P]
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kSspThreads = 512;
+
+__global__ void __launch_bounds__(kSspThreads)
+sample_shared_points_kernel(const float* __restrict__ maps, long long img_stride, long long q_stride, int H, int W,
+                            const float* __restrict__ coords, const int* __restrict__ band_lo, int n_bands, int rows,
+                            int P, int Q, float* __restrict__ out) {
+  extern __shared__ __align__(16) float s_band[];   // rows [r0, r0 + rows] of the map (one halo row below)
+  __shared__ uint64_t s_bar;
+  const int q = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const float* map = maps + b * img_stride + q * q_stride;
+  const float2* pc = reinterpret_cast<const float2*>(coords) + static_cast<long long>(b) * P;
+  float* dst = out + (static_cast<long long>(b) * Q + q) * P;
+  const int* lo = band_lo + b * (n_bands + 1);
+  if (tid == 0) {
+    ptx::mbar_init(&s_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  uint32_t phase = 0;
+  for (int k = 0; k < n_bands; ++k) {
+    const int p0 = lo[k], p1 = lo[k + 1];
+    if (p1 <= p0) continue;                       // CTA-uniform
+    const int r0 = k * rows;
+    const int nr = min(rows + 1, H - r0);         // rows present in the map (rows past its end are never addressed:
+                                                  // point_corners marks those corners invalid)
+    if (tid == 0) {
+      // the band is one contiguous piece of the map: a single bulk copy (TMA engine), completion on the mbarrier
+      const uint32_t bytes = static_cast<uint32_t>(nr) * W * 4u;
+      ptx::mbar_arrive_expect_tx(&s_bar, bytes);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       ptx::smem_u32(s_band)),
+                   "l"(map + static_cast<long long>(r0) * W), "r"(bytes), "r"(ptx::smem_u32(&s_bar))
+                   : "memory");
+    }
+    ptx::mbar_wait(&s_bar, phase);
+    phase ^= 1u;
+    const int base = r0 * W, limit = nr * W;
+    // two points per thread and iteration: both coordinate loads are in flight before either is used (the loop is
+    // otherwise one dependent L2 round trip per point: 282 us per head instead of the ~70 us the map read takes)
+    for (int p = p0 + tid; p < p1; p += 2 * kSspThreads) {
+      const int pb = p + kSspThreads;
+      const float2 xa = __ldg(pc + p);
+      const float2 xb = pb < p1 ? __ldg(pc + pb) : xa;
+      const Corners ca = point_corners(xa.x, xa.y, H, W), cb = point_corners(xb.x, xb.y, H, W);
+      float va[4], vb[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int oa = ca.o[j] - base, ob = cb.o[j] - base;
+        va[j] = ca.o[j] < 0 ? 0.f : ((oa >= 0 && oa < limit) ? s_band[oa] : __ldg(map + ca.o[j]));
+        vb[j] = cb.o[j] < 0 ? 0.f : ((ob >= 0 && ob < limit) ? s_band[ob] : __ldg(map + cb.o[j]));
+      }
+      float acca = 0.f, accb = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (ca.o[j] >= 0) acca += va[j] * ca.w[j];
+        if (cb.o[j] >= 0) accb += vb[j] * cb.w[j];
+      }
+      dst[p] = acca;
+      if (pb < p1) dst[pb] = accb;
+    }
+    __syncthreads();                              // all reads of the band done before the next copy lands in it
   }
 }
 
@@ -424,13 +505,38 @@ long long mpf_match_cost_workspace_bytes(int batch, int num_queries, int total_t
   return (floats + 4) * static_cast<long long>(sizeof(float));
 }
 
-int mpf_match_cost_f32(const float* pred_logits, long long logits_img_stride, long long logits_q_stride,
-                       int num_classes_p1, const float* pred_masks, long long masks_img_stride,
-                       long long masks_q_stride, int H, int W, const void* const* tgt_mask_ptrs, int tgt_is_f32,
-                       int Hg, int Wg, const int64_t* tgt_labels, const int32_t* tgt_offsets, int total_targets,
-                       int max_targets, const float* point_coords, int batch, int num_queries, int num_points,
-                       float cost_class, float cost_mask, float cost_dice, void* workspace,
-                       long long workspace_bytes, float* cost, void* stream) {
+int mpf_sample_shared_points_f32(const float* maps, long long img_stride, long long q_stride, int H, int W,
+                                 const float* point_coords, const int32_t* band_lo, int n_bands, int band_rows,
+                                 int batch, int num_queries, int num_points, float* out, void* stream) {
+  using namespace mpf;
+  clear_error();
+  MPF_REQUIRE(batch > 0 && num_queries > 0 && num_points > 0 && H > 0 && W > 0, "sample_shared_points: sizes must be positive");
+  MPF_REQUIRE(maps && point_coords && band_lo && out, "sample_shared_points: null pointer argument");
+  MPF_REQUIRE(W % 4 == 0 && aligned16(maps) && img_stride % 4 == 0 && q_stride % 4 == 0,
+              "sample_shared_points: W and the strides must be multiples of 4 and the maps 16-byte aligned");
+  MPF_REQUIRE(n_bands > 0 && band_rows > 0 && static_cast<long long>(n_bands) * band_rows >= H,
+              "sample_shared_points: the bands must cover the map (%d bands of %d rows, H = %d)", n_bands, band_rows, H);
+  MPF_REQUIRE(batch <= 65535, "sample_shared_points: batch > 65535");
+  MPF_REQUIRE((reinterpret_cast<uintptr_t>(point_coords) & 7u) == 0, "sample_shared_points: point_coords must be 8-byte aligned");
+  const size_t smem = static_cast<size_t>(band_rows + 1) * W * sizeof(float);
+  MPF_REQUIRE(smem <= 200 * 1024, "sample_shared_points: a band of %d rows x %d columns exceeds the shared memory", band_rows + 1, W);
+  static unsigned long long seen = 0;
+  if (first_use_on_this_device(seen))
+    MPF_CUDA_OK(cudaFuncSetAttribute(sample_shared_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  const dim3 grid(num_queries, batch);
+  sample_shared_points_kernel<<<grid, kSspThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      maps, img_stride, q_stride, H, W, point_coords, band_lo, n_bands, band_rows, num_points, num_queries, out);
+  count_launch();
+  return finish_launch("sample_shared_points");
+}
+
+static int match_cost_impl(const float* pred_logits, long long logits_img_stride, long long logits_q_stride,
+                           int num_classes_p1, const float* pred_masks, long long masks_img_stride,
+                           long long masks_q_stride, int H, int W, const void* const* tgt_mask_ptrs, int tgt_is_f32,
+                           int Hg, int Wg, const int64_t* tgt_labels, const int32_t* tgt_offsets, int total_targets,
+                           int max_targets, const float* point_coords, int batch, int num_queries, int num_points,
+                           float cost_class, float cost_mask, float cost_dice, void* workspace,
+                           long long workspace_bytes, float* cost, const float* sampled, void* stream) {
   using namespace mpf;
   clear_error();
   MPF_REQUIRE(batch > 0 && num_queries > 0 && num_points > 0 && H > 0 && W > 0 && Hg > 0 && Wg > 0 &&
@@ -439,8 +545,8 @@ int mpf_match_cost_f32(const float* pred_logits, long long logits_img_stride, lo
   MPF_REQUIRE(total_targets >= 0 && max_targets >= 0 && max_targets <= total_targets,
               "match_cost: bad target counts (total %d, max %d)", total_targets, max_targets);
   if (total_targets == 0) return MPF_OK;       // nothing to match
-  MPF_REQUIRE(pred_logits && pred_masks && tgt_mask_ptrs && tgt_labels && tgt_offsets && point_coords && workspace &&
-                  cost,
+  MPF_REQUIRE(pred_logits && (pred_masks || sampled) && tgt_mask_ptrs && tgt_labels && tgt_offsets && point_coords &&
+                  workspace && cost,
               "match_cost: null pointer argument");
   MPF_REQUIRE(static_cast<long long>(H) * W < (1ll << 31) && static_cast<long long>(Hg) * Wg < (1ll << 31),
               "match_cost: map too large");
@@ -461,6 +567,7 @@ int mpf_match_cost_f32(const float* pred_logits, long long logits_img_stride, lo
   a.tgt_mask_ptrs = tgt_mask_ptrs;
   a.tgt_offsets = tgt_offsets;
   a.point_coords = point_coords;
+  a.sampled = sampled;
   float* ws = static_cast<float*>(workspace);
   a.part3 = ws;
   a.part_sig = a.part3 + static_cast<long long>(S) * num_queries * total_targets * 3;
@@ -495,6 +602,33 @@ int mpf_match_cost_f32(const float* pred_logits, long long logits_img_stride, lo
       cost_class, cost_mask, cost_dice, cost);
   count_launch();
   return finish_launch("match_cost (finish)");
+}
+
+int mpf_match_cost_f32(const float* pred_logits, long long logits_img_stride, long long logits_q_stride,
+                       int num_classes_p1, const float* pred_masks, long long masks_img_stride,
+                       long long masks_q_stride, int H, int W, const void* const* tgt_mask_ptrs, int tgt_is_f32,
+                       int Hg, int Wg, const int64_t* tgt_labels, const int32_t* tgt_offsets, int total_targets,
+                       int max_targets, const float* point_coords, int batch, int num_queries, int num_points,
+                       float cost_class, float cost_mask, float cost_dice, void* workspace,
+                       long long workspace_bytes, float* cost, void* stream) {
+  return match_cost_impl(pred_logits, logits_img_stride, logits_q_stride, num_classes_p1, pred_masks, masks_img_stride,
+                         masks_q_stride, H, W, tgt_mask_ptrs, tgt_is_f32, Hg, Wg, tgt_labels, tgt_offsets,
+                         total_targets, max_targets, point_coords, batch, num_queries, num_points, cost_class,
+                         cost_mask, cost_dice, workspace, workspace_bytes, cost, nullptr, stream);
+}
+
+int mpf_match_cost_presampled_f32(const float* pred_logits, long long logits_img_stride, long long logits_q_stride,
+                                  int num_classes_p1, const float* sampled, int H, int W,
+                                  const void* const* tgt_mask_ptrs, int tgt_is_f32, int Hg, int Wg,
+                                  const int64_t* tgt_labels, const int32_t* tgt_offsets, int total_targets,
+                                  int max_targets, const float* point_coords, int batch, int num_queries,
+                                  int num_points, float cost_class, float cost_mask, float cost_dice, void* workspace,
+                                  long long workspace_bytes, float* cost, void* stream) {
+  MPF_REQUIRE(sampled != nullptr, "match_cost_presampled: null pointer argument");
+  return match_cost_impl(pred_logits, logits_img_stride, logits_q_stride, num_classes_p1, nullptr, 0, 0, H, W,
+                         tgt_mask_ptrs, tgt_is_f32, Hg, Wg, tgt_labels, tgt_offsets, total_targets, max_targets,
+                         point_coords, batch, num_queries, num_points, cost_class, cost_mask, cost_dice, workspace,
+                         workspace_bytes, cost, sampled, stream);
 }
 
 int mpf_lsap_f32(const float* cost, const int32_t* tgt_offsets, int batch, int num_queries, int max_targets,

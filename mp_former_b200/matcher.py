@@ -95,6 +95,13 @@ class HungarianMatcher(nn.Module):
         # sort when the maps of a head exceed the L2 (>= 8 images' worth of 100 x 256 x 256 logits); for a couple of
         # images the argsort costs more than the gathers it tidies.
         self.sort_points = sort_points
+        # With sorted points: sample the predictions by streaming every map once through shared memory
+        # (native.sample_shared_points) instead of gathering.  Measured on the B200 at 16 images x 100 queries x 12544
+        # points, cold L2 (profiles/r2q_matcher_probe_*.txt, r2r_*): the streamed sampler takes 0.18 ms and the cost
+        # kernel on its samples 0.30 ms, against 0.41 ms for the cost kernel gathering at the sorted points itself
+        # (1.03 ms unsorted) -- what remains of that kernel is the sampling of the GT masks and its reduction over the
+        # points, not the prediction gathers.  Off by default for that reason; kept as a tested option.
+        self.stream_samples = False
         self._packed_key = None
         self._packed = None
         self._tables = {}
@@ -115,15 +122,44 @@ class HungarianMatcher(nn.Module):
         return self._tables[(lo, hi)]
 
     @staticmethod
-    def row_major_order(point_coords, H, W):
+    def row_major_order(point_coords, H, W, band_rows=None):
         """point_coords [B, P, 2] (x, y) in [0, 1] -> the same points of every image, ordered row-major by the
         top-left pixel of their bilinear footprint on the H x W map (``floor(c * size - 0.5)``): the 32 points of a
         warp then touch 6.0 cache lines per gather instruction on average instead of 31.8 (12544 uniform points on a
-        256 x 256 fp32 map; ordering by the pixel containing the point gives 11.1, tiled orders 6.1-6.5)."""
+        256 x 256 fp32 map; ordering by the pixel containing the point gives 11.1, tiled orders 6.1-6.5).
+        With ``band_rows``: also returns int32 [B, n_bands + 1], the index of the first point of every band of
+        ``band_rows`` map rows (for ``native.sample_shared_points``)."""
         key = ((point_coords[..., 1] * H - 0.5).floor().clamp(0, H - 1) * W +
                (point_coords[..., 0] * W - 0.5).floor().clamp(0, W - 1))
-        order = key.argsort(dim=1, stable=True)
-        return torch.gather(point_coords, 1, order.unsqueeze(-1).expand(-1, -1, 2))
+        if band_rows is None:
+            order = key.argsort(dim=1, stable=True)
+            return torch.gather(point_coords, 1, order.unsqueeze(-1).expand(-1, -1, 2))
+        skey, order = key.sort(dim=1, stable=True)
+        n_bands = -(-H // band_rows)
+        edges = (torch.arange(n_bands + 1, device=key.device, dtype=key.dtype) * float(band_rows * W))
+        band_lo = torch.searchsorted(skey, edges.expand(key.shape[0], -1).contiguous()).to(torch.int32)
+        return torch.gather(point_coords, 1, order.unsqueeze(-1).expand(-1, -1, 2)), band_lo
+
+    def _head_cost(self, logits, masks, pts, ptrs, packed, hw, labels, offsets, counts):
+        """Cost matrices of one prediction head over a group of images (flat, see native.match_cost)."""
+        logits = logits.float()                     # autocast heads: the costs are computed in fp32 (matcher.py:134-136)
+        masks = masks.float()
+        sort = self.sort_points
+        if sort is None:
+            sort = masks.numel() * masks.element_size() >= (200 << 20)
+        sampled = None
+        if sort:
+            H, W = masks.shape[-2:]
+            if self.stream_samples and W % 4 == 0 and masks.stride(-1) == 1 and masks.stride(-2) == W and \
+                    masks.stride(0) % 4 == 0 and masks.stride(1) % 4 == 0 and masks.data_ptr() % 16 == 0:
+                # every map is streamed once through shared memory instead of being gathered from (see __init__)
+                rows, _ = native.shared_point_bands(H, W)
+                pts, band_lo = self.row_major_order(pts, H, W, band_rows=rows)
+                sampled = native.sample_shared_points(masks, pts, band_lo, rows)
+            else:
+                pts = self.row_major_order(pts, H, W)
+        return native.match_cost(logits, masks, ptrs, packed.is_f32, hw, labels, offsets, counts, pts,
+                                 self.cost_class, self.cost_mask, self.cost_dice, sampled=sampled)
 
     def draw_points(self, bs, device):
         """The matcher's random points of one call: all masks of an image share one set, drawn per image like the
@@ -157,13 +193,7 @@ class HungarianMatcher(nn.Module):
             logits, masks = o["pred_logits"], o["pred_masks"]
             _lib.require_cuda(masks, "outputs['pred_masks']")
             _lib.require_cuda(logits, "outputs['pred_logits']")
-            sort = self.sort_points
-            if sort is None:
-                sort = masks.numel() * masks.element_size() >= (200 << 20)
-            if sort:
-                pts = self.row_major_order(pts, *masks.shape[-2:])
-            costs.append(native.match_cost(logits.float(), masks.float(), ptrs, packed.is_f32, packed.sizes[0], labels,
-                                           offsets, counts, pts, self.cost_class, self.cost_mask, self.cost_dice))
+            costs.append(self._head_cost(logits, masks, pts, ptrs, packed, packed.sizes[0], labels, offsets, counts))
         key = ("heads", nh)
         if key not in self._tables:     # offsets of the nh * B problems in the concatenated cost buffer
             offs, acc = [0], 0
@@ -195,13 +225,6 @@ class HungarianMatcher(nn.Module):
         if point_coords is None:
             # all masks of an image share one set of points; drawn per image like the reference (matcher.py:120)
             point_coords = self.draw_points(bs, dev)
-        sort = self.sort_points
-        if sort is None:
-            sort = masks.numel() * masks.element_size() >= (200 << 20)
-        if sort:
-            point_coords = self.row_major_order(point_coords, *masks.shape[-2:])
-        logits = logits.float()                     # autocast heads: the costs are computed in fp32 (matcher.py:134-136)
-        masks = masks.float()
         groups = [(0, bs)] if packed.uniform() else [(b, b + 1) for b in range(bs)]
         qi, ti, costs, stats = [], [], [], []
         for lo, hi in groups:
@@ -209,8 +232,8 @@ class HungarianMatcher(nn.Module):
             if sum(counts) == 0:
                 continue
             hw = packed.sizes[lo]
-            cost = native.match_cost(logits[lo:hi], masks[lo:hi], ptrs, packed.is_f32, hw, labels, offsets, counts,
-                                     point_coords[lo:hi], self.cost_class, self.cost_mask, self.cost_dice)
+            cost = self._head_cost(logits[lo:hi], masks[lo:hi], point_coords[lo:hi], ptrs, packed, hw, labels, offsets,
+                                   counts)
             q, t, status = native.lsap(cost, offsets, counts, num_queries)
             qi.append(q), ti.append(t), costs.append(cost), stats.append(status)
         if not qi:

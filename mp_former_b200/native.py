@@ -787,11 +787,47 @@ def masked_xattn_bwd(q_hi, q_lo, k_hi, k_lo, kt_hi, kt_lo, v_hi, v_lo, d_o, bits
 # ----------------------------------------------------------------------------------------------------------------
 # Hungarian matching on the device (ref mask2former/modeling/matcher.py:96-157)
 # ----------------------------------------------------------------------------------------------------------------
+SHARED_POINT_BAND_BYTES = 96 << 10       # shared memory of one band of sample_shared_points (two CTAs per SM)
+
+
+def shared_point_bands(H, W):
+    """(rows per band, number of bands) of ``sample_shared_points`` for H x W maps."""
+    rows = max(1, min(H, SHARED_POINT_BAND_BYTES // (4 * W) - 1))
+    return rows, -(-H // rows)
+
+
+def sample_shared_points(pred_masks, point_coords, band_lo, band_rows):
+    """pred_masks [B, Q, H, W] f32 (each map contiguous, W % 4 == 0) sampled at the image's shared points
+    point_coords [B, P, 2] -> [B, Q, P], by streaming every map once through shared memory (csrc/matcher.cu
+    sample_shared_points_kernel).  ``band_lo`` int32 [B, n_bands + 1]: first point of every band of ``band_rows`` rows
+    in the row-major ordered point list."""
+    _f32c(pred_masks, "pred_masks")
+    _f32c(point_coords, "point_coords")
+    _lib.require_cuda(band_lo, "band_lo")
+    B, Q, H, W = pred_masks.shape
+    P = point_coords.shape[1]
+    n_bands = band_lo.shape[1] - 1
+    if pred_masks.stride(-1) != 1 or pred_masks.stride(-2) != W or W % 4 or band_lo.dtype != torch.int32 or \
+            band_lo.shape[0] != B or not band_lo.is_contiguous() or point_coords.shape != (B, P, 2):
+        raise RuntimeError("sample_shared_points: contiguous maps with W % 4 == 0, point_coords [B, P, 2] and int32 "
+                           "band_lo [B, n_bands + 1] expected")
+    point_coords = point_coords.contiguous()
+    out = torch.empty((B, Q, P), dtype=torch.float32, device=pred_masks.device)
+    with torch.cuda.device(pred_masks.device):
+        rc = _lib.load().mpf_sample_shared_points_f32(
+            pred_masks.data_ptr(), pred_masks.stride(0), pred_masks.stride(1), H, W, point_coords.data_ptr(),
+            band_lo.data_ptr(), n_bands, int(band_rows), B, Q, P, out.data_ptr(), _stream())
+    _lib.check(rc, "sample_shared_points")
+    return out
+
+
 def match_cost(pred_logits, pred_masks, tgt_mask_ptrs, tgt_is_f32, tgt_hw, tgt_labels, tgt_offsets, counts,
-               point_coords, cost_class, cost_mask, cost_dice):
+               point_coords, cost_class, cost_mask, cost_dice, sampled=None):
     """Cost matrices of a whole batch in one pass.  pred_logits [B, Q, K+1] f32, pred_masks [B, Q, H, W] f32 (may be
     a query slice of a larger tensor), tgt_mask_ptrs int64 [B] (device pointers to each image's [n_b, Hg, Wg] masks),
     tgt_labels int64 [ntot], tgt_offsets int32 [B+1], counts = the host list of n_b, point_coords [B, P, 2].
+    ``sampled`` [B, Q, P]: the prediction logits already sampled at the points (``sample_shared_points``); pred_masks
+    is then only consulted for its shape.
     Returns a flat float tensor: image b's row-major [Q, n_b] matrix at Q * offsets[b]."""
     for t, n in ((pred_logits, "pred_logits"), (pred_masks, "pred_masks"), (tgt_mask_ptrs, "tgt_mask_ptrs"),
                  (tgt_labels, "tgt_labels"), (tgt_offsets, "tgt_offsets"), (point_coords, "point_coords")):
@@ -826,13 +862,23 @@ def match_cost(pred_logits, pred_masks, tgt_mask_ptrs, tgt_is_f32, tgt_hw, tgt_l
         raise RuntimeError("match_cost: bad sizes")
     ws = torch.empty((ws_bytes + 3) // 4, dtype=torch.float32, device=pred_masks.device)
     with torch.cuda.device(pred_masks.device):
-        rc = lib.mpf_match_cost_f32(
-            pred_logits.data_ptr(), pred_logits.stride(0), pred_logits.stride(1), K1,
-            pred_masks.data_ptr(), pred_masks.stride(0), pred_masks.stride(1), H, W,
-            tgt_mask_ptrs.data_ptr(), int(bool(tgt_is_f32)), int(tgt_hw[0]), int(tgt_hw[1]),
-            tgt_labels.data_ptr(), tgt_offsets.data_ptr(), ntot, nmax, point_coords.data_ptr(), B, Q, P,
-            float(cost_class), float(cost_mask), float(cost_dice), ws.data_ptr(), ws.numel() * 4, cost.data_ptr(),
-            _stream())
+        if sampled is not None:
+            if sampled.dtype != torch.float32 or tuple(sampled.shape) != (B, Q, P) or not sampled.is_contiguous():
+                raise RuntimeError("match_cost: sampled must be a contiguous float32 [B, Q, P] tensor")
+            rc = lib.mpf_match_cost_presampled_f32(
+                pred_logits.data_ptr(), pred_logits.stride(0), pred_logits.stride(1), K1, sampled.data_ptr(), H, W,
+                tgt_mask_ptrs.data_ptr(), int(bool(tgt_is_f32)), int(tgt_hw[0]), int(tgt_hw[1]),
+                tgt_labels.data_ptr(), tgt_offsets.data_ptr(), ntot, nmax, point_coords.data_ptr(), B, Q, P,
+                float(cost_class), float(cost_mask), float(cost_dice), ws.data_ptr(), ws.numel() * 4, cost.data_ptr(),
+                _stream())
+        else:
+            rc = lib.mpf_match_cost_f32(
+                pred_logits.data_ptr(), pred_logits.stride(0), pred_logits.stride(1), K1,
+                pred_masks.data_ptr(), pred_masks.stride(0), pred_masks.stride(1), H, W,
+                tgt_mask_ptrs.data_ptr(), int(bool(tgt_is_f32)), int(tgt_hw[0]), int(tgt_hw[1]),
+                tgt_labels.data_ptr(), tgt_offsets.data_ptr(), ntot, nmax, point_coords.data_ptr(), B, Q, P,
+                float(cost_class), float(cost_mask), float(cost_dice), ws.data_ptr(), ws.numel() * 4, cost.data_ptr(),
+                _stream())
     _lib.check(rc, "match_cost")
     return cost
 

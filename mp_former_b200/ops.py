@@ -960,7 +960,8 @@ class _MaskedCrossAttention(torch.autograd.Function):
         o2 = o.reshape(B * Qt, E)
         g_wout = native.matmul_tn(gy2, o2)
         g_bout = gy2.sum(0)
-        go = (gy2 @ w_out).view(B, Qt, E)                                           # d(attention output)
+        wot_hi, wot_lo = native.split_b(w_out.t().contiguous())
+        go = native.gemm(gy2, wot_hi, wot_lo).view(B, Qt, E)                        # d(attention output)
         delta = (go.view(B, Qt, nhead, hd) * o.view(B, Qt, nhead, hd)).sum(-1).permute(0, 2, 1).contiguous()
         # operands the forward did not keep: V row-major and K^T (both pre-split by the GEMM epilogue)
         wq, wk, wv = w_in[:E], w_in[E:2 * E], w_in[2 * E:]
@@ -980,7 +981,10 @@ class _MaskedCrossAttention(torch.autograd.Function):
         g_wk = native.matmul_tn(dk2, mem2) + native.matmul_tn(dk.sum(0), pos2)
         g_win = torch.cat([native.matmul_tn(dq2, q_in.reshape(B * Qt, E)), g_wk, native.matmul_tn(dv2, mem2)], 0)
         g_bin = torch.cat([dq2.sum(0), native.colsum(dk2), native.colsum(dv2)], 0)
-        g_qin = (dq2 @ wq).view(B, Qt, E) if ctx.needs_input_grad[0] else None
+        g_qin = None
+        if ctx.needs_input_grad[0]:
+            wqt_hi, wqt_lo = native.split_b(wq.t().contiguous())
+            g_qin = native.gemm(dq2, wqt_hi, wqt_lo).view(B, Qt, E)
         g_mem = g_pos = None
         if ctx.needs_input_grad[1]:
             wkt_hi, wkt_lo = native.split_b(wk.t().contiguous())

@@ -50,7 +50,11 @@ def _split_costs(flat, Q, counts):
     return out
 
 
-def test_matcher_equals_reference_golden():
+@pytest.mark.parametrize("mode", ["gather", "sorted_gather", "sorted_streamed"])
+def test_matcher_equals_reference_golden(mode):
+    """The three ways the prediction logits are sampled -- gathered at the points as drawn, gathered at the row-major
+    ordered points, streamed through shared memory (native.sample_shared_points) -- against the costs and assignments
+    of the unmodified reference."""
     from mp_former_b200.matcher import HungarianMatcher
     G = torch.load(os.path.join(HERE, "golden", "matcher.pt"), weights_only=False)
     outputs, targets = inputs()
@@ -59,7 +63,9 @@ def test_matcher_equals_reference_golden():
     for case in G["cases"]:
         wc, wm, wd = case["weights"]
         coords = _reference_points(case["seed"], len(targets), case["num_points"])
-        m = HungarianMatcher(cost_class=wc, cost_mask=wm, cost_dice=wd, num_points=case["num_points"])
+        m = HungarianMatcher(cost_class=wc, cost_mask=wm, cost_dice=wd, num_points=case["num_points"],
+                             sort_points=mode != "gather")
+        m.stream_samples = mode == "sorted_streamed"
         qi, ti, counts, cost, status = m.match_device(o, t, point_coords=coords.cuda())
         assert int(status.item()) == 0
         ref_costs = _oracle_costs(outputs, targets, coords, (wc, wm, wd))
@@ -97,6 +103,36 @@ def test_matcher_forward_contract_and_rng_consumption():
     for (i, j), (di, dj) in zip(res, resd):
         assert di.is_cuda and torch.equal(di.cpu(), i) and torch.equal(dj.cpu(), j)
     assert "cost_class: 2.0" in repr(m)
+
+
+@pytest.mark.parametrize("H,W,Q,P,sort", [(256, 256, 5, 12544, True), (100, 36, 3, 777, True), (100, 32, 4, 300, False),
+                                          (300, 128, 2, 5000, True)])
+def test_sample_shared_points_equals_gathered_samples(H, W, Q, P, sort):
+    """Streaming sampler against the gather kernel (same bilinear formula: 1e-6), for points in row-major order with
+    the band table (the fast path), for maps whose height is not a multiple of the band, and for UNSORTED points with
+    a band table that does not describe them (every footprint outside its band falls back to global memory)."""
+    from mp_former_b200 import native
+    from mp_former_b200.matcher import HungarianMatcher
+    g = torch.Generator(device="cuda").manual_seed(H * 7 + P)
+    B = 3
+    full = torch.randn(B, Q + 2, H, W, device="cuda", generator=g)
+    maps = full[:, 2:]                                             # a query slice of a larger tensor
+    pts = torch.rand(B, P, 2, device="cuda", generator=g)
+    pts[0, :8] = torch.tensor([[0.0, 0.0], [1.0, 1.0], [0.0, 1.0], [1.0, 0.0], [0.5, 0.0], [0.5, 1.0], [0.0, 0.5],
+                               [1.0, 0.5]], device="cuda")       # footprints hanging over every edge
+    rows, n_bands = native.shared_point_bands(H, W)
+    rows = min(rows, 37) if H > 37 else rows                       # several bands also on small maps
+    n_bands = -(-H // rows)
+    if sort:
+        pts, band_lo = HungarianMatcher.row_major_order(pts, H, W, band_rows=rows)
+        assert band_lo.shape == (B, n_bands + 1) and int(band_lo[0, 0]) == 0 and int(band_lo[0, -1]) == P
+    else:
+        band_lo = torch.tensor([[0] + [P] * n_bands] * B, dtype=torch.int32, device="cuda")   # "everything in band 0"
+    got = native.sample_shared_points(maps, pts, band_lo, rows)
+    ptrs = (maps.data_ptr() + 4 * (torch.arange(B, device="cuda").view(B, 1) * maps.stride(0) +
+                                   torch.arange(Q, device="cuda").view(1, Q) * maps.stride(1))).reshape(-1)
+    ref = native.point_sample_rows(ptrs, True, (H, W), pts.repeat_interleave(Q, 0)).view(B, Q, P)
+    assert torch.allclose(got, ref, rtol=0, atol=1e-6), (got - ref).abs().max()
 
 
 def test_match_device_heads_equals_head_by_head():
