@@ -146,6 +146,9 @@ __global__ void __launch_bounds__(MC_THREADS, 3) match_cost_partial_kernel(const
       for (int u = 0; u < MC_NT / PARTS; ++u) s_t[p1 * MC_TS + part + u * PARTS] = t[u];
     }
     __syncthreads();
+    // a warp owns four targets: with fewer targets in the tile (COCO averages 7 instances per image against the
+    // tile's 32) the warps past the last one have nothing to add and leave the issue slots to the others
+    if (wj * 4 < nj) {
 #pragma unroll 4
     for (int p = 0; p < MC_PT; ++p) {
       const float ps[2] = {s_pos[p * MC_QS + lane], s_pos[p * MC_QS + lane + 32]};
@@ -166,6 +169,7 @@ __global__ void __launch_bounds__(MC_THREADS, 3) match_cost_partial_kernel(const
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) sumT[k] += t[k];
+    }
     }
     __syncthreads();
   }
