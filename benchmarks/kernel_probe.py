@@ -101,6 +101,22 @@ def main():
         emit(f"gemm_{native.GEMM_MODE}_tn ffn.d_w1 (token reduction, split-K) [1024 x 256] over M={m}", ms, 4 * (m * 1024 + m * 256),
              3 * 2.0 * m * 1024 * 256)
         del a, hid
+    if "gemm_small" in which:
+        # decoder-side products (few M tiles): B * Qt query rows, and the K / V projections of one memory level
+        Qt = 220
+        for (m, n, k, tag) in ((B * Qt, 256, 256, "decoder linear (queries)"), (B * Qt, 2048, 256, "decoder ffn.linear1"),
+                               (B * Qt, 256, 2048, "decoder ffn.linear2"), (B * 1024, 256, 256, "K/V projection HW=1024"),
+                               (B * 4096, 256, 256, "K/V projection HW=4096"), (B * 16384, 256, 256, "K/V projection HW=16384")):
+            a, w, bias = rn(m, k), rn(n, k) / 16, rn(n)
+            wh, wl = native.split_b(w)
+            ms = timeit(lambda: native.gemm(a, wh, wl, bias))
+            emit(f"gemm_{native.GEMM_MODE} {tag} M={m} N={n} K={k}", ms, 4 * (m * k + m * n) + 4 * n * k, 3 * 2.0 * m * n * k)
+            gy = rn(m, n)
+            ms = timeit(lambda: native.matmul_tn(gy, a))
+            emit(f"gemm_{native.GEMM_MODE}_tn weight grad of {tag} [{n} x {k}] over T={m}", ms, 4 * (m * n + m * k), 3 * 2.0 * m * n * k)
+            ms = timeit(lambda: native.split_b(w))
+            emit(f"split_bf16 weight [{n} x {k}]", ms, 8 * n * k)
+            del a, gy
     if "masklogits" in which:
         Q, C, HW = 120, 256, 65536
         e, f = rn(B, Q, C), rn(B, HW, C)
