@@ -233,6 +233,20 @@ def gemm(a, b_hi, b_lo, bias=None, relu=False, transpose_c=False, split_out=Fals
     if b_hi.dtype == torch.bfloat16:
         if b_hi.dim() == 3 and b_hi.shape[0] > 1 and b_hi.stride(0) == 0:     # expanded shared weight
             b_hi, b_lo = b_hi[:1], b_lo[:1]
+        batch, M, K = a.shape
+        N = b_hi.shape[1]
+        tiles = batch * ((M + 127) // 128) * ((N + 255) // 256)
+        if (K >= 1024 and tiles * 4 <= 148 and not (relu or transpose_c or split_out) and resid is None
+                and alpha == 1.0 and b_hi.shape[0] == batch and N % 4 == 0):
+            # a long reduction over a handful of output tiles (the decoder's second FFN product: 440 - 3520 query rows,
+            # K = 2048): every CTA would walk 64 k-blocks back to back on 4 - 28 SMs (51 us measured).  The reduction
+            # is cut across CTAs instead; the partial slabs are small.
+            splits = max(2, min(K // 256, 148 // tiles))
+            out = gemm_bf16x3_splitk(a, b_hi.contiguous(), b_lo.contiguous(), splits)
+            if bias is not None:
+                out = out + bias
+            out = out.reshape(batch, M, N)
+            return out[0] if squeeze else out
         out, out_lo = _gemm_bf16x3(a, b_hi.contiguous(), b_lo.contiguous(), bias, relu, transpose_c, split_out,
                                    resid, resid_rows, resid_cols, alpha)
         if squeeze:
