@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--no-dn", action="store_true", help="drop the mask-piloted (DN) query group")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-weight-cache", action="store_true", help="split every weight operand where it is used")
     ap.add_argument("--no-graph", action="store_true", help="issue every launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-stock", action="store_true")
@@ -478,10 +479,19 @@ def run_ours(a):
     def allreduce_grads():
         graphs.allreduce_gradients(params, world)
 
+    # Split weight operands of the step refreshed by one launch at its start (native.WeightOperandCache) instead of a
+    # split + transposing copy per use (--no-weight-cache: the per-use path).
+    wcache = None if a.no_weight_cache else native.set_weight_cache(native.WeightOperandCache(params))
+
+    def forward_loss(f):
+        if wcache is not None:
+            wcache.begin_step()
+        return loss_of(head(f, dn_args))
+
     def eager_step(f):
         for q in params:
             q.grad = None
-        loss = loss_of(head(f, dn_args))
+        loss = forward_loss(f)
         loss.backward()
         allreduce_grads()
         return loss
@@ -497,7 +507,7 @@ def run_ours(a):
     gs, graph_note = None, "disabled (--no-graph)"
     if not a.no_graph:
         try:
-            gs = graphs.GraphedStep(lambda inp: loss_of(head(inp, dn_args)), feats, params, warmup=1)
+            gs = graphs.GraphedStep(forward_loss, feats, params, warmup=2)
             graph_note = "forward+loss+backward captured once, replayed per step"
         except Exception as e:  # noqa: BLE001
             gs, graph_note = None, f"capture failed, eager stepping: {type(e).__name__}: {str(e)[:160]}"
@@ -727,6 +737,8 @@ def run_ours(a):
             "impl_notes": {"native_ops": sorted(M.ops.NATIVE_OPS), "tf32": False, "cuda_graph": graph_note,
                            "routes": dict(sorted(M.ops.ROUTES.items())),
                            "criterion_path": getattr(criterion, "last_path", None) if a.loss == "criterion" else None,
+                           "weight_operand_cache": None if wcache is None else {
+                               "operands": len(wcache.entries), "hits": wcache.hits, "misses": wcache.misses},
                            "arithmetic": "fp32 storage; GEMMs in bf16x3 split arithmetic (fp32 accumulate), attention "
                                          "core in 3xTF32; no single-pass reduced precision"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,

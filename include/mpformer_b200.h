@@ -241,6 +241,15 @@ int mpf_gemm_tf32x3_general(const float* A, int a_mn_major, long long lda, long 
  * Requirements: A/B/C 16-byte aligned; lda, ldc, batch strides multiples of 4 elements; ldb multiple of 8.
  * ------------------------------------------------------------------------------------------- */
 int mpf_split_bf16(const float* x, uint16_t* hi, uint16_t* lo, long long n, void* stream);
+
+/* All weight operands of a step in one launch: `table` (device) holds n_entries records
+ *   { const float* src; bf16* hi; bf16* lo; int32 rows, cols; int64 ld; int32 transposed; int32 tile0; }   (48 bytes)
+ * -- source [rows, cols] fp32 with row stride ld; destination halves [rows, cols] or, transposed, [cols, rows]
+ * (contiguous bf16); tile0 = index of the record's first 32 x 32 tile in the grid of total_tiles tiles (records sorted by
+ * tile0).  Replaces one mpf_split_bf16 (plus a transposing copy for the input-gradient operand) per use of every
+ * nn.Linear weight of the path: ref pixel_decoder/msdeformattn.py:116-131, transformer_decoder/
+ * mask2former_transformer_decoder.py:19-180 (the weights of self-attention, cross-attention, FFN and the heads). */
+int mpf_split_weights_f32(const void* table, int n_entries, int total_tiles, void* stream);
 /* C = A B^T (+ bias, + full residual, ReLU) for one [M, K] x [N, K] product with the ReLU pattern kept as ONE BIT per
  * element: relu_bits_out (with relu != 0) receives word [n / 32][m] whose bit n % 32 says C[m][n] > 0; gate_bits zeroes
  * the elements of C whose bit is clear (the backward of Linear -> ReLU -> Linear reads 1/32 of the bytes of the

@@ -51,6 +51,7 @@ SIGNATURES = {
                                          ctypes.c_float,
                                          _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp]),
     "mpf_split_bf16": (_c_int, [_c_vp, _c_vp, _c_vp, _c_ll, _c_vp]),
+    "mpf_split_weights_f32": (_c_int, [_c_vp, _c_int, _c_int, _c_vp]),
     "mpf_gemm_bf16x3": (_c_int, [_c_vp, _c_ll, _c_ll, _c_vp, _c_vp, _c_ll, _c_ll, _c_vp, _c_vp, _c_vp, _c_ll, _c_ll,
                                  _c_vp, _c_ll, _c_int, _c_int, _c_vp, _c_ll, ctypes.c_float,
                                  _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp]),

@@ -276,26 +276,38 @@ sample_shared_points_kernel(const float* __restrict__ maps, long long img_stride
   }
 }
 
+// One WARP per (query, target) cell: the lanes share the point splits (up to 111 of them when a couple of images
+// leave the partial kernel with many splits: a single thread walking them took 54 us per launch at two images) and
+// the K + 1 classes of the soft-max; fixed lane-strided order + xor-shuffle tree -> deterministic.
 __global__ void __launch_bounds__(256)
 match_cost_finish_kernel(const float* __restrict__ part3, const float* __restrict__ part_sig,
                          const float* __restrict__ part_t, const float* __restrict__ logits,
                          long long logits_img_stride, long long logits_q_stride, int K1,
                          const long long* __restrict__ labels, const int* __restrict__ offsets, int B, int Q, int ntot,
                          int S, int P, float w_class, float w_mask, float w_dice, float* __restrict__ cost) {
-  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (idx >= static_cast<long long>(Q) * ntot) return;
+  const long long idx = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (idx >= static_cast<long long>(Q) * ntot) return;          // warp-uniform
   const int q = static_cast<int>(idx / ntot), jg = static_cast<int>(idx - static_cast<long long>(q) * ntot);
   int b = 0;
   while (b + 1 < B && __ldg(offsets + b + 1) <= jg) ++b;
   const int n0 = __ldg(offsets + b), nb = __ldg(offsets + b + 1) - n0;
   float sp = 0.f, sn = 0.f, sd = 0.f, ss = 0.f, st = 0.f;
-  for (int s = 0; s < S; ++s) {
+  for (int s = lane; s < S; s += 32) {
     const float* p3 = part3 + ((static_cast<long long>(s) * Q + q) * ntot + jg) * 3;
     sp += p3[0];
     sn += p3[1];
     sd += p3[2];
     ss += part_sig[(static_cast<long long>(s) * B + b) * Q + q];
     st += part_t[static_cast<long long>(s) * ntot + jg];
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    sp += __shfl_xor_sync(0xffffffffu, sp, d);
+    sn += __shfl_xor_sync(0xffffffffu, sn, d);
+    sd += __shfl_xor_sync(0xffffffffu, sd, d);
+    ss += __shfl_xor_sync(0xffffffffu, ss, d);
+    st += __shfl_xor_sync(0xffffffffu, st, d);
   }
   const float c_mask = (sp + sn) / static_cast<float>(P);                 // matcher.py:59-61
   const float c_dice = 1.0f - (2.0f * sd + 1.0f) / (ss + st + 1.0f);      // matcher.py:26-29
@@ -307,13 +319,18 @@ match_cost_finish_kernel(const float* __restrict__ part3, const float* __restric
     c_class = CUDART_NAN_F;                                               // surfaces as "invalid" in the solver
   } else {
     float m = -CUDART_INF_F;
-    for (int k = 0; k < K1; ++k) m = fmaxf(m, __ldg(row + k));
+    for (int k = lane; k < K1; k += 32) m = fmaxf(m, __ldg(row + k));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
     float den = 0.f;
-    for (int k = 0; k < K1; ++k) den += expf(__ldg(row + k) - m);
+    for (int k = lane; k < K1; k += 32) den += expf(__ldg(row + k) - m);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) den += __shfl_xor_sync(0xffffffffu, den, d);
     c_class = -(expf(__ldg(row + lab) - m) / den);
   }
-  cost[static_cast<long long>(Q) * n0 + static_cast<long long>(q) * nb + (jg - n0)] =
-      (w_mask * c_mask + w_class * c_class) + w_dice * c_dice;            // matcher.py:142-146
+  if (lane == 0)
+    cost[static_cast<long long>(Q) * n0 + static_cast<long long>(q) * nb + (jg - n0)] =
+        (w_mask * c_mask + w_class * c_class) + w_dice * c_dice;          // matcher.py:142-146
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -598,7 +615,7 @@ static int match_cost_impl(const float* pred_logits, long long logits_img_stride
   if (rc != MPF_OK) return rc;
 
   const long long cells = static_cast<long long>(num_queries) * total_targets;
-  const long long blocks = (cells + 255) / 256;
+  const long long blocks = (cells + 7) / 8;          // a warp per cell, eight cells per CTA
   MPF_REQUIRE(blocks < (1ll << 31), "match_cost: problem too large");
   match_cost_finish_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(
       a.part3, a.part_sig, a.part_t, pred_logits, logits_img_stride, logits_q_stride, num_classes_p1,

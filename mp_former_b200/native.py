@@ -87,13 +87,124 @@ def split_bf16(x):
     return hi, lo
 
 
+class WeightOperandCache:
+    """The split weight operands of a training step, refreshed by ONE launch (csrc/weights.cu) instead of a split
+    (and, for the input-gradient operand, a transposing copy) per use: ~300 launches per step of this head.
+
+        cache = native.WeightOperandCache(model.parameters()); native.set_weight_cache(cache)
+        for every step:  cache.begin_step();  loss = ...;  loss.backward();  optimizer.step()
+
+    ``split_b(w)`` / ``split_bt(w)`` (the operand of ``w`` / of ``w.t()``) look the request up by address, shape and
+    strides -- ``w`` may be a row slice of a registered parameter, e.g. the q / k / v blocks of a packed in-projection.
+    A request seen for the first time is served the slow way and recorded; the next ``begin_step`` outside a graph
+    capture builds the arena and the device table for everything recorded.  An entry is only used while the
+    parameter's version counter equals the one it was filled at (an optimizer step without a following ``begin_step``
+    falls back to the slow way instead of serving stale halves), and inside a CUDA-graph capture only if ``begin_step``
+    was captured too (the replayed graph then refreshes the arena itself)."""
+
+    def __init__(self, params):
+        self.params = {}                 # storage address -> parameter (version counter shared by its views)
+        for p in params:
+            if p.dtype == torch.float32 and p.is_cuda:
+                self.params[p.untyped_storage().data_ptr()] = p
+        self.entries = {}                # key -> [hi, lo, param, filled version]
+        self.pending = {}                # key -> (geometry, param) recorded since the last build
+        self.table = None
+        self.total_tiles = 0
+        self._keep = []                  # every arena / table ever built: a captured graph may still use an older one
+        self._fresh_in_capture = False
+        self.hits = self.misses = 0
+
+    @staticmethod
+    def _key(w, transposed):
+        return (w.data_ptr(), tuple(w.shape), tuple(w.stride()), bool(transposed))
+
+    def lookup(self, w, transposed):
+        """-> (hi, lo) or None; records unknown requests on registered parameters."""
+        if w.dim() != 2 or w.dtype != torch.float32 or w.stride(1) != 1 or not w.is_cuda:
+            return None
+        p = self.params.get(w.untyped_storage().data_ptr())
+        if p is None:
+            return None
+        capturing = torch.cuda.is_current_stream_capturing()
+        if not capturing:
+            self._fresh_in_capture = False
+        key = self._key(w, transposed)
+        ent = self.entries.get(key)
+        if ent is not None and ent[3] == p._version and (not capturing or self._fresh_in_capture):
+            self.hits += 1
+            return ent[0], ent[1]
+        self.misses += 1
+        if ent is None and key not in self.pending:
+            self.pending[key] = (w.data_ptr(), w.shape[0], w.shape[1], w.stride(0), bool(transposed), p)
+        return None
+
+    def _build(self):
+        geoms = [(k, (e[4], e[5], e[6], e[7], k[3], e[2])) for k, e in self.entries.items()]
+        geoms += [(k, (g[0], g[1], g[2], g[3], g[4], g[5])) for k, g in self.pending.items()]
+        self.pending = {}
+        dev = next(iter(self.params.values())).device
+        total = sum(g[1] * g[2] for _, g in geoms)
+        arena = torch.empty(2 * total, dtype=torch.bfloat16, device=dev)
+        words, tile0, off = [], 0, 0
+        self.entries = {}
+        for key, (ptr, rows, cols, ld, transposed, p) in geoms:
+            n = rows * cols
+            shape = (cols, rows) if transposed else (rows, cols)
+            hi, lo = arena[off:off + n].view(shape), arena[off + n:off + 2 * n].view(shape)
+            off += 2 * n
+            words += [ptr, hi.data_ptr(), lo.data_ptr(), rows | (cols << 32), ld, int(transposed) | (tile0 << 32)]
+            tile0 += ((rows + 31) // 32) * ((cols + 31) // 32)
+            self.entries[key] = [hi, lo, p, -1, ptr, rows, cols, ld]
+        self.table = torch.tensor(words, dtype=torch.int64, device=dev)
+        self.total_tiles = tile0
+        self._keep += [arena, self.table]
+
+    def begin_step(self):
+        """Refreshes every recorded operand from the current weights (one launch); call before the forward."""
+        capturing = torch.cuda.is_current_stream_capturing()
+        if self.pending and not capturing:          # (the table upload is a host -> device copy: never inside a capture)
+            self._build()
+        if not self.entries:
+            return
+        with torch.cuda.device(self.table.device):
+            rc = _lib.load().mpf_split_weights_f32(self.table.data_ptr(), len(self.entries), self.total_tiles, _stream())
+        _lib.check(rc, "split_weights")
+        for ent in self.entries.values():
+            ent[3] = ent[2]._version
+        self._fresh_in_capture = capturing
+
+
+_WEIGHT_CACHE = None
+
+
+def set_weight_cache(cache):
+    """Installs (or, with None, removes) the process-wide ``WeightOperandCache`` consulted by split_b / split_bt."""
+    global _WEIGHT_CACHE
+    _WEIGHT_CACHE = cache
+    return cache
+
+
 def split_b(w):
     """Pre-split the B operand ([..., N, K], K contiguous) of ``gemm`` / ``gemm_general``: bf16 halves for the
     bf16x3 kernel when its TMA constraints hold (K % 8 == 0, N % 4 == 0), TF32 halves for the 3xTF32 kernel
     otherwise (or when MPF_GEMM=tf32x3)."""
     if GEMM_MODE == "bf16x3" and w.shape[-1] % 8 == 0 and w.shape[-2] % 4 == 0:
+        if _WEIGHT_CACHE is not None:
+            hit = _WEIGHT_CACHE.lookup(w, False)
+            if hit is not None:
+                return hit
         return split_bf16(w)
     return split_tf32(w)
+
+
+def split_bt(w):
+    """``split_b(w.t().contiguous())`` -- the operand of the input-gradient product dx = dy W for a weight W [N, K]."""
+    if GEMM_MODE == "bf16x3" and w.dim() == 2 and w.shape[0] % 8 == 0 and w.shape[1] % 4 == 0 and _WEIGHT_CACHE is not None:
+        hit = _WEIGHT_CACHE.lookup(w, True)
+        if hit is not None:
+            return hit
+    return split_b(w.t().contiguous())
 
 
 def transpose_split_bf16(x):

@@ -91,7 +91,7 @@ class _Linear(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             n_out = weight.shape[0]
             if n_out % 32 == 0:
-                wt_hi, wt_lo = native.split_b(weight.t().contiguous())
+                wt_hi, wt_lo = native.split_bt(weight)
                 gx = native.gemm(g2.contiguous(), wt_hi, wt_lo)
             else:
                 # e.g. class_embed (81 outputs): the reduction dimension of the input-gradient GEMM is zero-padded to a
@@ -210,7 +210,7 @@ class _Conv1x1NCHW(torch.autograd.Function):
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             # dX[b] (Cin x HW) = W^T dY[b]^T: token GEMM with a transposed store -> NCHW directly
-            wt_hi, wt_lo = native.split_b(weight.view(Cout, Cin).t().contiguous())
+            wt_hi, wt_lo = native.split_bt(weight.view(Cout, Cin))
             gx = native.gemm(g3, wt_hi[None].expand(B, -1, -1), wt_lo[None].expand(B, -1, -1), transpose_c=True)
             gx = gx.view(B, Cin, *ctx.hw)
         if ctx.needs_input_grad[1]:
@@ -461,11 +461,11 @@ class _FFN(torch.autograd.Function):
     def backward(ctx, gy):
         x2, w1, w2, hidden = ctx.saved_tensors
         g2 = gy.reshape(-1, gy.shape[-1]).contiguous()
-        w2t_hi, w2t_lo = native.split_b(w2.t().contiguous())
+        w2t_hi, w2t_lo = native.split_bt(w2)
         gh = native.gemm_general(g2, w2t_hi, b_lo=w2t_lo, gate=hidden)       # d(hidden) with the ReLU mask applied
         gw2 = native.matmul_tn(g2, hidden)
         gb2 = native.colsum(g2)
-        w1t_hi, w1t_lo = native.split_b(w1.t().contiguous())
+        w1t_hi, w1t_lo = native.split_bt(w1)
         gx = native.gemm(gh, w1t_hi, w1t_lo).view(*gy.shape[:-1], w1.shape[1]) if ctx.needs_input_grad[0] else None
         gw1 = native.matmul_tn(gh, x2)
         gb1 = native.colsum(gh)
@@ -543,7 +543,7 @@ class _EncoderLayer(torch.autograd.Function):
         B, S, C, M, P, host_shapes, n_off = ctx.geom
 
         def t_halves(w):
-            return native.split_b(w.t().contiguous())
+            return native.split_bt(w)
 
         # FFN block
         dsum2, dg2, db2, gb2 = native.add_layernorm_bwd(g_out.reshape(B * S, C), src1, y, g2, mean2, rstd2,
@@ -960,7 +960,7 @@ class _MaskedCrossAttention(torch.autograd.Function):
         o2 = o.reshape(B * Qt, E)
         g_wout = native.matmul_tn(gy2, o2)
         g_bout = gy2.sum(0)
-        wot_hi, wot_lo = native.split_b(w_out.t().contiguous())
+        wot_hi, wot_lo = native.split_bt(w_out)
         go = native.gemm(gy2, wot_hi, wot_lo).view(B, Qt, E)                        # d(attention output)
         delta = (go.view(B, Qt, nhead, hd) * o.view(B, Qt, nhead, hd)).sum(-1).permute(0, 2, 1).contiguous()
         # operands the forward did not keep: V row-major and K^T (both pre-split by the GEMM epilogue)
@@ -983,12 +983,12 @@ class _MaskedCrossAttention(torch.autograd.Function):
         g_bin = torch.cat([dq2.sum(0), native.colsum(dk2), native.colsum(dv2)], 0)
         g_qin = None
         if ctx.needs_input_grad[0]:
-            wqt_hi, wqt_lo = native.split_b(wq.t().contiguous())
+            wqt_hi, wqt_lo = native.split_bt(wq)
             g_qin = native.gemm(dq2, wqt_hi, wqt_lo).view(B, Qt, E)
         g_mem = g_pos = None
         if ctx.needs_input_grad[1]:
-            wkt_hi, wkt_lo = native.split_b(wk.t().contiguous())
-            wvt_hi, wvt_lo = native.split_b(wv.t().contiguous())
+            wkt_hi, wkt_lo = native.split_bt(wk)
+            wvt_hi, wvt_lo = native.split_bt(wv)
             # dK Wk + dV Wv: the second GEMM adds the first one's result in its epilogue (no separate full-size add)
             g_mem = native.gemm(dv2, wvt_hi, wvt_lo, resid=native.gemm(dk2, wkt_hi, wkt_lo)).view(B, HW, E)
         if ctx.needs_input_grad[2]:

@@ -50,3 +50,78 @@ def test_graphed_step_matches_eager_step():
                 continue
             scale = max(1e-6, r.abs().max().item())
             assert (p.grad - r).abs().max().item() / scale < 5e-4      # fp32 atomics: summation order differs run to run
+
+
+def test_weight_operand_cache_equals_per_use_splits_and_follows_weight_updates():
+    """native.WeightOperandCache (one launch refreshing every split weight operand of the step): same step as with a
+    split per use; entries are bypassed after an in-place weight update until ``begin_step`` refreshes them; and a
+    captured graph that contains ``begin_step`` follows weight updates on replay."""
+    from mp_former_b200 import native
+    pd = build_pixel_decoder().to(DEV)
+    pd.load_state_dict(O.seeded_state_dict(pixel_decoder_template(), seed=41))
+    dec = build_decoder(dn_label_noise_ratio=-1.0).to(DEV)
+    dec.load_state_dict(O.seeded_state_dict(decoder_template(), seed=51))
+    feats = {k: v.to(DEV) for k, v in cases.pixel_decoder_features().items()}
+    dn = {"tgt": [{k: v.to(DEV) for k, v in t.items()} for t in cases.dn_targets()], "scalar": 1, "noise_scale": 0.0}
+    params = list(pd.parameters()) + list(dec.parameters())
+
+    def step_fn(inp):
+        mf, _, ms = pd.forward_features(inp)
+        out = dec(ms, mf, None, dn)
+        return out["pred_masks"].square().mean() + out["pred_logits"].square().mean() + \
+            out["dn_out"]["pred_masks"].square().mean()
+
+    def run(begin=None):
+        for p in params:
+            p.grad = None
+        if begin is not None:
+            begin()
+        loss = step_fn(feats)
+        loss.backward()
+        return loss.item(), [None if p.grad is None else p.grad.clone() for p in params]
+
+    def same(a, b):
+        assert abs(a[0] - b[0]) <= 1e-6 * max(1.0, abs(b[0]))
+        for x, y in zip(a[1], b[1]):
+            if y is not None:
+                assert (x - y).abs().max().item() <= 5e-4 * max(1e-6, y.abs().max().item())
+
+    ref = run()
+    cache = native.set_weight_cache(native.WeightOperandCache(params))
+    try:
+        same(run(cache.begin_step), ref)                         # first step: everything recorded, served per use
+        assert cache.hits == 0 and cache.pending
+        same(run(cache.begin_step), ref)                         # second step: arena built, operands come from it
+        assert cache.hits > 50 and not cache.pending and len(cache.entries) > 50
+        with torch.no_grad():
+            for p in params:
+                p.mul_(1.01)
+        native.set_weight_cache(None)
+        ref2 = run()
+        native.set_weight_cache(cache)
+        hits = cache.hits
+        same(run(), ref2)                                        # stale entries are bypassed without begin_step
+        assert cache.hits == hits
+        same(run(cache.begin_step), ref2)                        # ... and used again after it
+        assert cache.hits > hits
+        # inside a CUDA graph: begin_step is captured, so the replay refreshes the arena from the current weights
+        gs = graphs.GraphedStep(lambda inp: (cache.begin_step(), step_fn(inp))[1], feats, params, warmup=2)
+        gs(feats)
+        torch.cuda.synchronize()
+        same((gs.static_loss.item(), [p.grad for p in params]), ref2)
+        with torch.no_grad():
+            for p in params:
+                p.div_(1.01)
+        gs(feats)
+        torch.cuda.synchronize()
+        got = (gs.static_loss.item(), [None if p.grad is None else p.grad.clone() for p in params])
+        native.set_weight_cache(None)
+        for p in params:
+            p.grad = None
+        ref3 = run()
+        assert abs(got[0] - ref3[0]) <= 1e-5 * max(1.0, abs(ref3[0]))
+        for x, y in zip(got[1], ref3[1]):
+            if y is not None:
+                assert (x - y).abs().max().item() <= 5e-4 * max(1e-6, y.abs().max().item())
+    finally:
+        native.set_weight_cache(None)
