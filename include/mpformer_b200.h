@@ -284,6 +284,16 @@ int mpf_gemm_bf16x3_tn(const float* A, long long lda, long long a_batch_stride, 
 int mpf_gemm_bf16x3_tn_ex(const float* A, long long lda, long long a_batch_stride, const float* B, long long ldb,
                           long long b_batch_stride, float* C, long long ldc, long long c_batch_stride, int batch, int M,
                           int N, int T, int k_splits, int accumulate, void* stream);
+/* mpf_gemm_bf16x3_tn with the column sums of A over each slab's tokens written to colsum (slab s at colsum +
+ * s * colsum_slab_stride floats, M values; e.g. right behind slab s of C so that one reduction sums both): the bias
+ * gradient sum_t dY[t, :] that accompanies every weight gradient dW = dY^T X of an nn.Linear (autograd of F.linear at
+ * ref pixel_decoder/msdeformattn.py:116-131 and decoder :19-180), taken from the registers of the converter warps
+ * instead of a second pass over dY. */
+int mpf_gemm_bf16x3_tn_colsum(const float* A, long long lda, long long a_batch_stride, const float* B, long long ldb,
+                              long long b_batch_stride, float* C, long long ldc, long long c_batch_stride, int batch,
+                              int M, int N, int T, int k_splits, float* colsum, long long colsum_slab_stride,
+                              void* stream);
+
 
 /* ---------------------------------------------------------------------------------------------
  * Row-wise kernels of the encoder / decoder layers.

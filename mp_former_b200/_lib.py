@@ -60,6 +60,8 @@ SIGNATURES = {
     "mpf_transpose_split_bf16": (_c_int, [_c_vp] * 3 + [_c_int, _c_ll, _c_int, _c_vp]),
     "mpf_gemm_bf16x3_tn": (_c_int, [_c_vp, _c_ll, _c_ll, _c_vp, _c_ll, _c_ll, _c_vp, _c_ll, _c_ll] + [_c_int] * 5 + [_c_vp]),
     "mpf_gemm_bf16x3_tn_ex": (_c_int, [_c_vp, _c_ll, _c_ll, _c_vp, _c_ll, _c_ll, _c_vp, _c_ll, _c_ll] + [_c_int] * 6 + [_c_vp]),
+    "mpf_gemm_bf16x3_tn_colsum": (_c_int, [_c_vp, _c_ll, _c_ll, _c_vp, _c_ll, _c_ll, _c_vp, _c_ll, _c_ll] + [_c_int] * 5
+                                  + [_c_vp, _c_ll, _c_vp]),
     "mpf_add_layernorm_partials": (_c_int, [_c_ll]),
     "mpf_add_layernorm_fwd_f32": (_c_int, [_c_vp] * 4 + [ctypes.c_float, _c_ll, _c_int] + [_c_vp] * 4),
     "mpf_add_layernorm_bwd_f32": (_c_int, [_c_vp] * 6 + [_c_ll, _c_int] + [_c_vp] * 3),

@@ -51,6 +51,9 @@ struct Args {
   int ring;                                    // slots
   int debug;
   int accumulate;                              // 1: C += product (TMA reduce-add store) instead of C = product
+  long long colsum_ld;                         // slab stride of colsum (floats)
+  float* colsum;                               // optional [slabs, M]: column sums of A over the slab's tokens (the bias
+                                               // gradient that goes with a weight gradient), written by the converters
   // weight gradient of a 3x3 convolution over channels-last maps (conv_W > 0): the reduction index is the pixel
   // (b, y, x), A = dY tokens [T, Cout]; B is the INPUT map [batch, H, W, Cin] behind a 4-D tensor map and the N tile
   // selects (tap, channel range): the tap only shifts the 32-pixel box, pixels outside the map read as zero.
@@ -276,6 +279,16 @@ gemm_bf16x3_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     int slot = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      // column sums of A (= dY^T 1, the bias gradient next to the weight gradient dY^T X): every converter thread
+      // already holds its raw A values in registers; it adds them up over the tile's token blocks (its token row k,
+      // its 8 columns of the boxes par and par + 2) and the warp folds the 32 token rows once per tile.  Only the
+      // first N tile of an M tile does it.
+      const bool do_cs = g.colsum != nullptr && (tile % g.tiles_n) == 0;
+      float cs[2][8];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cs[i][j] = 0.f;
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(&raw_full[slot], phase);
         if (!(g.debug & 4)) {
@@ -291,6 +304,13 @@ gemm_bf16x3_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
               const uint8_t* rb = raw + box * kBoxBytes;
               u[i] = *reinterpret_cast<const float4*>(rb + (((2 * mc) ^ sw) << 4));
               v[i] = *reinterpret_cast<const float4*>(rb + (((2 * mc + 1) ^ sw) << 4));
+            }
+          }
+          if (do_cs) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {                        // boxes par, par + 2: the A boxes of this thread
+              cs[i][0] += u[i].x; cs[i][1] += u[i].y; cs[i][2] += u[i].z; cs[i][3] += u[i].w;
+              cs[i][4] += v[i].x; cs[i][5] += v[i].y; cs[i][6] += v[i].z; cs[i][7] += v[i].w;
             }
           }
           conv_bar();
@@ -313,6 +333,20 @@ gemm_bf16x3_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive(&op_full[slot]);
         if (++slot == kRing) { slot = 0; phase ^= 1; }
+      }
+      if (do_cs) {
+        const int rest = tile / g.tiles_n;
+        const int m_t = rest % g.tiles_m, slab = rest / g.tiles_m;
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float x = cs[i][j];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+            const int col = m_t * kBM + (par + 2 * i) * 32 + mc * 8 + j;
+            if (lane == 0 && col < g.M) g.colsum[static_cast<long long>(slab) * g.colsum_ld + col] = x;
+          }
       }
     }
   } else if (warp >= 4) {
@@ -467,7 +501,7 @@ extern "C" {
 static int gemm_bf16x3_tn_impl(const float* A, long long lda, long long a_batch_stride, const float* B, long long ldb,
                                long long b_batch_stride, float* C, long long ldc, long long c_batch_stride, int batch,
                                int M, int N, int T, int k_splits, int accumulate, int conv_B, int conv_H, int conv_W,
-                               int conv_C, void* stream) {
+                               int conv_C, float* colsum, long long colsum_ld, void* stream) {
   using namespace mpf;
   using namespace mpf::bf3tn;
   clear_error();
@@ -509,6 +543,9 @@ static int gemm_bf16x3_tn_impl(const float* A, long long lda, long long a_batch_
   g.debug = 0;
   if (const char* dbg = getenv("MPF_GEMM_DEBUG")) g.debug = atoi(dbg);
   g.accumulate = accumulate ? 1 : 0;
+  MPF_REQUIRE(colsum == nullptr || (!accumulate && conv_H == 0), "gemm_bf16x3_tn: column sums need plain slabs");
+  g.colsum = colsum;
+  g.colsum_ld = colsum_ld;
 
   CUtensorMap ta, tb, tc;
   int rc = make_tmap(&ta, A, M, T, batch, lda, a_batch_stride, kBK, "A");
@@ -544,7 +581,16 @@ int mpf_gemm_bf16x3_tn_ex(const float* A, long long lda, long long a_batch_strid
                           long long b_batch_stride, float* C, long long ldc, long long c_batch_stride, int batch, int M,
                           int N, int T, int k_splits, int accumulate, void* stream) {
   return gemm_bf16x3_tn_impl(A, lda, a_batch_stride, B, ldb, b_batch_stride, C, ldc, c_batch_stride, batch, M, N, T,
-                             k_splits, accumulate, 0, 0, 0, 0, stream);
+                             k_splits, accumulate, 0, 0, 0, 0, nullptr, 0, stream);
+}
+
+int mpf_gemm_bf16x3_tn_colsum(const float* A, long long lda, long long a_batch_stride, const float* B, long long ldb,
+                              long long b_batch_stride, float* C, long long ldc, long long c_batch_stride, int batch,
+                              int M, int N, int T, int k_splits, float* colsum, long long colsum_slab_stride,
+                              void* stream) {
+  MPF_REQUIRE(colsum != nullptr && colsum_slab_stride >= M, "gemm_bf16x3_tn_colsum: bad column-sum output");
+  return gemm_bf16x3_tn_impl(A, lda, a_batch_stride, B, ldb, b_batch_stride, C, ldc, c_batch_stride, batch, M, N, T,
+                             k_splits, 0, 0, 0, 0, 0, colsum, colsum_slab_stride, stream);
 }
 
 int mpf_conv3x3_cl_wgrad_bf16x3(const float* dy, const float* x, float* dw, int batch, int H, int W, int Cin, int Cout,
@@ -559,7 +605,7 @@ int mpf_conv3x3_cl_wgrad_bf16x3(const float* dy, const float* x, float* dw, int 
   MPF_REQUIRE(T < (1ll << 31), "conv3x3_cl_wgrad: too many pixels");
   const int N = 9 * Cin;
   return gemm_bf16x3_tn_impl(dy, Cout, 0, x, N, 0, dw, N, static_cast<long long>(Cout) * N, 1, Cout, N,
-                             static_cast<int>(T), k_splits, 0, batch, H, W, Cin, stream);
+                             static_cast<int>(T), k_splits, 0, batch, H, W, Cin, nullptr, 0, stream);
 }
 
 int mpf_gemm_bf16x3_tn(const float* A, long long lda, long long a_batch_stride, const float* B, long long ldb,

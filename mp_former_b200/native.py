@@ -800,7 +800,7 @@ def gemm_general(a, b, a_mn=False, b_mn=False, b_lo=None, bias=None, relu=False,
     return out[0] if squeeze else out
 
 
-def gemm_tn(a, b, k_splits=1, accumulate_into=None):
+def gemm_tn(a, b, k_splits=1, accumulate_into=None, colsum=False):
     """C[i] = a[i]^T @ b[i] for a [batch, T, M], b [batch, T, N] (fp32, row-major; 2-D inputs = batch 1) on the
     bf16x3 TN kernel: both operands are split in-kernel, reduction over T, optional split-K (partials summed here).
     ``accumulate_into`` [batch, M, N] (contiguous fp32): the product is ADDED to it by the kernel's TMA reduce-add
@@ -843,6 +843,23 @@ def gemm_tn(a, b, k_splits=1, accumulate_into=None):
                 acc.data_ptr(), N, M * N, batch, M, N, T, k_splits, 1, _stream())
         _lib.check(rc, "gemm_bf16x3_tn_ex")
         return acc[0] if (own and squeeze) else acc
+    if colsum:
+        # ``colsum=True``: also returns the column sums of ``a`` over T ([batch, M]: the bias gradient that goes with
+        # the weight gradient), accumulated by the kernel's converter warps from the values they already hold
+        # (each slab of C is followed by its column sums, so that ONE reduction over the splits sums both)
+        slab = M * N + M
+        buf = torch.empty((batch * k_splits, slab), dtype=torch.float32, device=a.device)
+        with torch.cuda.device(a.device), _Timed("gemm_bf16x3_tn_kernel", 2.0 * batch * M * N * T,
+                                                 4.0 * batch * (T * M + T * N + k_splits * M * N)):
+            rc = _lib.load().mpf_gemm_bf16x3_tn_colsum(
+                a.data_ptr(), a.stride(1), a.stride(0) if batch > 1 else T * a.stride(1),
+                b.data_ptr(), b.stride(1), b.stride(0) if batch > 1 else T * b.stride(1),
+                buf.data_ptr(), N, slab, batch, M, N, T, k_splits, buf.data_ptr() + 4 * M * N, slab, _stream())
+        _lib.check(rc, "gemm_bf16x3_tn_colsum")
+        if k_splits > 1:
+            buf = buf.view(batch, k_splits, slab).sum(1)
+        out, cs = buf[:, :M * N].view(batch, M, N), buf[:, M * N:]
+        return (out[0], cs[0]) if squeeze else (out, cs)
     out = torch.empty((batch * k_splits, M, N), dtype=torch.float32, device=a.device)
     with torch.cuda.device(a.device), _Timed("gemm_bf16x3_tn_kernel", 2.0 * batch * M * N * T,
                                              4.0 * batch * (T * M + T * N + k_splits * M * N)):
@@ -856,16 +873,19 @@ def gemm_tn(a, b, k_splits=1, accumulate_into=None):
     return out[0] if squeeze else out
 
 
-def matmul_tn(x, y, target_tiles=296):
+def matmul_tn(x, y, target_tiles=296, with_colsum=False):
     """x^T @ y for x [T, M], y [T, N] (reduction over the long token dimension T), e.g. the weight gradient
     dW = dY^T X of an nn.Linear: both operands are consumed MN-major straight from their row-major
-    storage; T is cut into K-splits handled by different CTAs whose partial products are summed."""
+    storage; T is cut into K-splits handled by different CTAs whose partial products are summed.
+    ``with_colsum``: returns (x^T @ y, x.sum(0)) -- weight and bias gradient of the layer from one pass over dY."""
     T, M = x.shape
     N = y.shape[1]
     if GEMM_MODE == "bf16x3" and N % 4 == 0 and M % 4 == 0:
         tiles = ((M + 127) // 128) * ((N + 255) // 256)
         splits = max(1, min(148, target_tiles // max(1, tiles), (T + 1023) // 1024))
-        return gemm_tn(x, y, k_splits=splits)
+        return gemm_tn(x, y, k_splits=splits, colsum=with_colsum)
+    if with_colsum:
+        return matmul_tn(x, y, target_tiles), colsum(x)
     tiles = ((M + 127) // 128) * ((N + 127) // 128)
     splits = max(1, min(64, target_tiles // max(1, tiles), (T + 1023) // 1024))
     return gemm_general(x, y, a_mn=True, b_mn=True, k_splits=splits)

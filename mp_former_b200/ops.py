@@ -103,7 +103,10 @@ class _Linear(torch.autograd.Function):
             gx = gx.view(*gy.shape[:-1], weight.shape[1])
         if ctx.needs_input_grad[1]:
             if g2.shape[1] % 4 == 0 and x2.shape[1] % 4 == 0:
-                gw = native.matmul_tn(g2.contiguous(), x2)      # dW = dY^T X on the tensor cores, no transposes
+                if ctx.has_bias and ctx.needs_input_grad[2]:    # dW = dY^T X and db = dY^T 1 from one pass over dY
+                    gw, gb = native.matmul_tn(g2.contiguous(), x2, with_colsum=True)
+                else:
+                    gw = native.matmul_tn(g2.contiguous(), x2)  # dW = dY^T X on the tensor cores, no transposes
                 ROUTES["linear.weight_grad:native"] += 1
             elif x2.shape[1] % 4 == 0:
                 pad = (-g2.shape[1]) % 4                         # zero columns of dY -> zero rows of dW, sliced away
@@ -112,7 +115,7 @@ class _Linear(torch.autograd.Function):
             else:
                 _route("linear.weight_grad", False, f"in_features {x2.shape[1]} % 4 != 0")
                 gw = g2.t() @ x2
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+        if gb is None and ctx.has_bias and ctx.needs_input_grad[2]:
             gb = native.colsum(g2)
         return gx, gw, gb, None
 
@@ -463,12 +466,10 @@ class _FFN(torch.autograd.Function):
         g2 = gy.reshape(-1, gy.shape[-1]).contiguous()
         w2t_hi, w2t_lo = native.split_bt(w2)
         gh = native.gemm_general(g2, w2t_hi, b_lo=w2t_lo, gate=hidden)       # d(hidden) with the ReLU mask applied
-        gw2 = native.matmul_tn(g2, hidden)
-        gb2 = native.colsum(g2)
+        gw2, gb2 = native.matmul_tn(g2, hidden, with_colsum=True)
         w1t_hi, w1t_lo = native.split_bt(w1)
         gx = native.gemm(gh, w1t_hi, w1t_lo).view(*gy.shape[:-1], w1.shape[1]) if ctx.needs_input_grad[0] else None
-        gw1 = native.matmul_tn(gh, x2)
-        gb1 = native.colsum(gh)
+        gw1, gb1 = native.matmul_tn(gh, x2, with_colsum=True)
         return gx, gw1, gb1, gw2, gb2
 
 
@@ -556,8 +557,7 @@ class _EncoderLayer(torch.autograd.Function):
         gw2 = native.matmul_tn(dsum2, hidden)
         w1t_hi, w1t_lo = t_halves(w1)
         g_src1 = native.gemm(gh, w1t_hi, w1t_lo, resid=dsum2)                        # + the residual branch
-        gw1 = native.matmul_tn(gh, src1)
-        gb1 = native.colsum(gh)
+        gw1, gb1 = native.matmul_tn(gh, src1, with_colsum=True)      # weight and bias gradient from one pass over gh
         del gh
         # attention block
         dsum1, dg1, db1, gbo = native.add_layernorm_bwd(g_src1, x2, proj, g1, mean1, rstd1, with_colsum=True)
@@ -571,11 +571,10 @@ class _EncoderLayer(torch.autograd.Function):
         wowt_hi, wowt_lo = t_halves(wow)
         g_src = native.gemm(gv2, wvt_hi, wvt_lo, resid=dsum1)                        # residual + value branch
         g_src = native.gemm(gow2, wowt_hi, wowt_lo, resid=g_src)                     # + query branch
-        gwv = native.matmul_tn(gv2, x2)
-        gbv = native.colsum(gv2)
+        gwv, gbv = native.matmul_tn(gv2, x2, with_colsum=True)
         gow_b = g_ow.view(B, S, -1).sum(0)                                           # [S, M*L*P*3]
-        gwow = native.matmul_tn(gow2, x2) + native.matmul_tn(gow_b, pos2)
-        gbow = native.colsum(gow2)
+        gwow, gbow = native.matmul_tn(gow2, x2, with_colsum=True)
+        gwow = gwow + native.matmul_tn(gow_b, pos2)
         g_pos = native.gemm(gow_b, wowt_hi, wowt_lo).view(1, S, C) if ctx.needs_input_grad[1] else None
         return (g_src.view(B, S, C), g_pos, None, None, None, None, None,
                 gwv, gbv, gwow[:n_off], gbow[:n_off], gwow[n_off:], gbow[n_off:], gwo, gbo, dg1, db1, None,
@@ -958,8 +957,7 @@ class _MaskedCrossAttention(torch.autograd.Function):
         hd = E // nhead
         gy2 = gy.reshape(B * Qt, E).contiguous()
         o2 = o.reshape(B * Qt, E)
-        g_wout = native.matmul_tn(gy2, o2)
-        g_bout = gy2.sum(0)
+        g_wout, g_bout = native.matmul_tn(gy2, o2, with_colsum=True)
         wot_hi, wot_lo = native.split_bt(w_out)
         go = native.gemm(gy2, wot_hi, wot_lo).view(B, Qt, E)                        # d(attention output)
         delta = (go.view(B, Qt, nhead, hd) * o.view(B, Qt, nhead, hd)).sum(-1).permute(0, 2, 1).contiguous()
@@ -978,9 +976,12 @@ class _MaskedCrossAttention(torch.autograd.Function):
         dq2, dk2, dv2 = dq.view(B * Qt, E), dk.view(B * HW, E), dv.view(B * HW, E)
         mem2 = memory.reshape(B * HW, E)
         # in-projection weight gradients: dW = dY^T X on the tensor cores (keys see memory + pos)
-        g_wk = native.matmul_tn(dk2, mem2) + native.matmul_tn(dk.sum(0), pos2)
-        g_win = torch.cat([native.matmul_tn(dq2, q_in.reshape(B * Qt, E)), g_wk, native.matmul_tn(dv2, mem2)], 0)
-        g_bin = torch.cat([dq2.sum(0), native.colsum(dk2), native.colsum(dv2)], 0)
+        g_wk, g_bk = native.matmul_tn(dk2, mem2, with_colsum=True)
+        g_wk = g_wk + native.matmul_tn(dk.sum(0), pos2)
+        g_wq, g_bq = native.matmul_tn(dq2, q_in.reshape(B * Qt, E), with_colsum=True)
+        g_wv, g_bv = native.matmul_tn(dv2, mem2, with_colsum=True)
+        g_win = torch.cat([g_wq, g_wk, g_wv], 0)
+        g_bin = torch.cat([g_bq, g_bk, g_bv], 0)
         g_qin = None
         if ctx.needs_input_grad[0]:
             wqt_hi, wqt_lo = native.split_bt(wq)

@@ -129,6 +129,28 @@ def test_gemm_tn_matches_fp64(T, M, N, batch, splits):
         assert (y2.double() - r[0]).abs().max().item() / T ** 0.5 < TOL
 
 
+@pytest.mark.parametrize("T,M,N,batch,splits", [(1024, 128, 256, 1, 1), (43008, 288, 256, 1, 42), (1004, 256, 1024, 1, 3),
+                                                (120, 4096, 256, 2, 1), (344, 100, 64, 3, 2), (440, 2048, 256, 1, 1),
+                                                (3520, 256, 2048, 1, 4), (33, 84, 256, 1, 1)])
+def test_gemm_tn_with_column_sums_matches_fp64(T, M, N, batch, splits):
+    """Weight gradient dW = dY^T X and bias gradient db = dY^T 1 from ONE pass over dY (the converter warps of the TN
+    kernel add up the A values they already hold): product as in the plain kernel, column sums exact to fp32 rounding
+    of a T-term sum; ragged T / M tails, several N tiles (only the first one writes the sums), split-K, batches."""
+    g = torch.Generator(device=DEV).manual_seed(T + M + N + batch)
+    a = torch.randn(batch, T, M, device=DEV, generator=g)
+    b = torch.randn(batch, T, N, device=DEV, generator=g)
+    y, cs = native.gemm_tn(a, b, k_splits=splits, colsum=True)
+    r = a.double().transpose(1, 2) @ b.double()
+    assert y.shape == (batch, M, N) and cs.shape == (batch, M)
+    assert (y.double() - r).abs().max().item() / T ** 0.5 < TOL
+    assert torch.equal(y, native.gemm_tn(a, b, k_splits=splits))          # the product itself is unchanged
+    assert (cs.double() - a.double().sum(1)).abs().max().item() / T ** 0.5 < 2e-6
+    if batch == 1:
+        y2, c2 = native.matmul_tn(a[0], b[0], with_colsum=True)
+        assert (y2.double() - r[0]).abs().max().item() / T ** 0.5 < TOL
+        assert (c2.double() - a[0].double().sum(0)).abs().max().item() / T ** 0.5 < 2e-6
+
+
 @pytest.mark.parametrize("T,M,N,batch", [(120, 4096, 256, 2), (100, 1000, 64, 3), (37, 300, 128, 1)])
 def test_gemm_tn_accumulate_into(T, M, N, batch):
     """TMA reduce-add epilogue: C += A^T B (sum over the prediction heads of the mask-feature gradient, ragged M tail
