@@ -746,6 +746,7 @@ static int g_pair_mode = [] { const char* e = getenv("MPF_GEMM_PAIR"); return e 
 // measurement knobs (environment, read once): staging tiles per epilogue group and a cap on the pipeline stages
 static int g_staging_tiles = [] { const char* e = getenv("MPF_GEMM_SBUFS"); return e && atoi(e) == 2 ? 2 : 1; }();
 static int g_max_stages = [] { const char* e = getenv("MPF_GEMM_STAGES"); return e ? atoi(e) : 0; }();
+static int g_small_bn = [] { const char* e = getenv("MPF_GEMM_SMALL_BN"); return e ? atoi(e) : 1; }();
 
 static int pick_bn(int N) {
   if (N <= 64) return 64;
@@ -818,6 +819,15 @@ static int gemm_bf16x3_impl(const float* A, long long lda, long long a_batch_str
     if (f >= 32 && f <= 256 && f % 32 == 0) g.bn = f;
   }
   g.tiles_m = conv_H > 0 ? conv_H * ((conv_W + kBM - 1) / kBM) : (M + kBM - 1) / kBM;
+  // A product with a handful of output tiles (the decoder's linears on B * 120 query rows: 4 - 28 M tiles) leaves most
+  // SMs idle while each busy one drains an epilogue of BN / 32 chunks after a short main loop: narrower N tiles spread
+  // the same work over four times as many CTAs (the A tile is converted once per N tile, which is cheap at this size).
+  if (g_small_bn && !getenv("MPF_GEMM_BN") && N % 64 == 0 && N >= 128 &&
+      static_cast<long long>(batch) * k_splits * g.tiles_m * ((N + g.bn - 1) / g.bn) * 4 <= sm_count()) {
+    g.bn = 64;
+    // (MPF_GEMM_SMALL_BN=2, measurement knob: a second tier of 32-column tiles when even those leave 3/4 of the SMs idle)
+    if (g_small_bn >= 2 && static_cast<long long>(batch) * k_splits * g.tiles_m * (N / 64) * 4 <= sm_count()) g.bn = 32;
+  }
   g.tiles_n = (N + g.bn - 1) / g.bn;
   MPF_REQUIRE(static_cast<long long>(batch) * k_splits * g.tiles_m * g.tiles_n < (1ll << 31), "gemm_bf16x3: too many tiles");
   const int kblocks_total = (K + kBK - 1) / kBK;
