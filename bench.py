@@ -615,9 +615,9 @@ def run_ours(a):
         def ncu_traffic(kernel):
             """DRAM bytes per launch of `kernel` (dram__bytes_read.sum + dram__bytes_write.sum, mean over its launches
             in one training step) from the committed ncu launch list of THIS workload (config 2, 16 images, criterion:
-            profiles/r2x_launch_summary_step_b16.txt, made by scripts/gpu_r2_final1.sh); None for other workloads --
+            profiles/r2E_launch_summary_step_b16.txt, made by scripts/gpu_r2_final1.sh); None for other workloads --
             ncu cannot run inside the timed bench."""
-            path = os.path.join(ROOT, "profiles", "r2x_launch_summary_step_b16.txt")
+            path = os.path.join(ROOT, "profiles", "r2E_launch_summary_step_b16.txt")
             cfg_idx = a.config if a.config else (2 if world == 1 else 3)
             if cfg_idx != 2 or B != 16 or a.loss != "criterion" or not os.path.exists(path):
                 return None

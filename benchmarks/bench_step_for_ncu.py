@@ -9,7 +9,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from mp_former_b200 import workload  # noqa: E402
+from mp_former_b200 import native, workload  # noqa: E402
 
 DEV = "cuda:0"
 B = int(os.environ.get("MPF_B", "16"))
@@ -22,11 +22,13 @@ dn = {"tgt": targets, "scalar": 1, "noise_scale": 0.0}
 criterion, weighted_sum = workload.build_criterion(device=DEV)
 criterion.train(True)
 params = list(pd.parameters()) + list(dec.parameters())
+wcache = native.set_weight_cache(native.WeightOperandCache(params))
 
 
 def step():
     for p in params:
         p.grad = None
+    wcache.begin_step()
     mf, _, ms = pd.forward_features(feats)
     loss = weighted_sum(criterion(dec(ms, mf, None, dn), targets))
     loss.backward()
