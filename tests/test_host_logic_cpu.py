@@ -248,3 +248,40 @@ def test_grad_fanout_and_head_collector_fall_back_to_plain_autograd_sums():
         assert sh is None and al[0] is mf
         d2, m2 = ops.collect_mask_heads([masks[0].detach()], 0, None)
         assert d2 is None and m2[0].shape == (B, Qt, H, W)
+
+
+def test_head_collector_recognises_gradients_that_tile_one_buffer():
+    """ops._HeadCollector._side_by_side: the per-head mask-logit gradients handed back by the criterion's joint
+    evaluation (slices of ONE buffer along dim 1, in the criterion's head order, not the decoder's) are used in place;
+    anything else (separate tensors, a hole, a wrong stride, a missing piece) falls back to the concatenation."""
+    from mp_former_b200 import ops
+    B, H, W = 2, 3, 4
+    sizes = [2, 5, 2, 5, 2, 5]                                  # three heads: dn part, matching part
+    buf = torch.arange(B * sum(sizes) * H * W, dtype=torch.float32).view(B, sum(sizes), H, W)
+    pieces = list(buf.split(sizes, dim=1))
+    # the criterion orders the heads (final, aux 0, aux 1) and each head (matching, dn); the collector (aux 0, aux 1,
+    # final) x (dn, matching): a permutation of the same slices
+    order = [3, 2, 5, 4, 1, 0]
+    grads = [pieces[i] for i in order]
+    got = ops._HeadCollector._side_by_side(grads, [sizes[i] for i in order], B, H, W)
+    assert got is not None
+    G2, rows = got
+    assert G2.data_ptr() == buf.data_ptr() and G2.shape == (B, sum(sizes), H * W)
+    assert torch.equal(G2, buf.view(B, sum(sizes), H * W))
+    starts = [0, 2, 7, 9, 14, 16]
+    assert rows == [starts[i] for i in order]
+    for g, r, n in zip(grads, rows, [sizes[i] for i in order]):
+        assert torch.equal(G2[:, r:r + n].reshape(B, n, H, W), g)
+    # a view into the middle of a larger allocation works too (storage offset)
+    big = torch.zeros(5 + buf.numel())
+    inner = big[5:].view_as(buf)
+    got = ops._HeadCollector._side_by_side(list(inner.split(sizes, dim=1)), sizes, B, H, W)
+    assert got is not None and got[0].data_ptr() == inner.data_ptr()
+    # fallbacks
+    f = ops._HeadCollector._side_by_side
+    assert f([p.clone() for p in pieces], sizes, B, H, W) is None                       # separate tensors
+    assert f(pieces[:5] + [None], sizes, B, H, W) is None                               # a head without gradient
+    assert f(pieces[:4] + [pieces[5], pieces[5]], sizes[:4] + [5, 5], B, H, W) is None  # a hole / an overlap
+    wide = torch.zeros(B, sum(sizes) + 1, H, W)
+    assert f(list(wide[:, :sum(sizes)].split(sizes, dim=1)), sizes, B, H, W) is None    # stride of a wider buffer
+    assert f([p.double() for p in pieces], sizes, B, H, W) is None                      # dtype
