@@ -106,7 +106,12 @@ class WeightOperandCache:
         self.params = {}                 # storage address -> parameter (version counter shared by its views)
         for p in params:
             if p.dtype == torch.float32 and p.is_cuda:
-                self.params[p.untyped_storage().data_ptr()] = p
+                key = p.untyped_storage().data_ptr()
+                if key in self.params and self.params[key] is not p:
+                    # (the staleness check reads ONE version counter per storage: parameters that are separate
+                    # tensors over one flat buffer would be checked against each other's counters)
+                    raise ValueError("WeightOperandCache: parameters must own their storage (two of them share one)")
+                self.params[key] = p
         self.entries = {}                # key -> [hi, lo, param, filled version]
         self.pending = {}                # key -> (geometry, param) recorded since the last build
         self.table = None
