@@ -125,3 +125,49 @@ def test_weight_operand_cache_equals_per_use_splits_and_follows_weight_updates()
                 assert (x - y).abs().max().item() <= 5e-4 * max(1e-6, y.abs().max().item())
     finally:
         native.set_weight_cache(None)
+
+
+def test_head_gradients_read_in_place_equal_the_concatenated_route():
+    """Decoder -> criterion -> backward with the criterion's two evaluation orders: all heads in one pass hands the
+    heads' mask-logit gradients back as slices of ONE buffer, which the decoder's batched head backward reads in place
+    (in the criterion's head order: the small operands are permuted instead); head by head they arrive as separate
+    tensors and are concatenated.  Same loss, same gradients of every decoder parameter and of mask_features."""
+    from mp_former_b200 import ops, workload
+    dec = build_decoder(dn_label_noise_ratio=-1.0).to(DEV).train()
+    dec.load_state_dict(O.seeded_state_dict(decoder_template(), seed=51))
+    x, mf0 = cases.decoder_inputs()
+    x = [t.to(DEV) for t in x]
+    targets = [{k: v.to(DEV) for k, v in t.items()} for t in cases.dn_targets()]
+    K, L = cases.DEC_CFG["num_classes"], cases.DEC_CFG["dec_layers"]
+    crit, weighted_sum = workload.build_criterion(num_classes=K, dec_layers=L + 1, num_points=112, device=DEV)
+    crit.train(True)
+    params = [p for p in dec.parameters() if p.requires_grad]
+
+    def run(joint):
+        for p in params:
+            p.grad = None
+        mf = mf0.to(DEV).requires_grad_(True)
+        crit.joint_heads = joint
+        torch.manual_seed(3)
+        out = dec(x, mf, None, {"tgt": targets, "scalar": 2, "noise_scale": 0.0})
+        loss = weighted_sum(crit(out, targets))
+        loss.backward()
+        crit.check_status()
+        return loss.item(), [mf.grad.clone()] + [None if p.grad is None else p.grad.clone() for p in params]
+
+    key_in, key_cat = "mask_heads.backward:gradients_in_place", "mask_heads.backward:gradients_concatenated"
+    n_in, n_cat = ops.ROUTES[key_in], ops.ROUTES[key_cat]
+    la, ga = run(True)
+    if ops.ROUTES[key_in] != n_in + 1:
+        pytest.skip("the batched head backward did not take the in-place route at this geometry")
+    lb, gb = run(False)
+    assert crit.last_path == "sequential" and ops.ROUTES[key_cat] == n_cat + 1
+    assert abs(la - lb) <= 1e-5 * max(1.0, abs(lb))
+    checked = 0
+    for a, b in zip(ga, gb):
+        assert (a is None) == (b is None)
+        if b is None:
+            continue
+        assert (a - b).abs().max().item() <= 1e-3 * max(1e-6, b.abs().max().item())
+        checked += 1
+    assert checked > 20 and float(gb[0].abs().sum()) > 0
