@@ -57,3 +57,30 @@ def test_row_major_point_order_is_a_permutation_and_leaves_costs_unchanged():
         c = MO.matching_cost(outputs["pred_logits"][b], outputs["pred_masks"][b], targets[b]["labels"],
                              targets[b]["masks"], srt[b:b + 1], 2.0, 5.0, 5.0)
         assert torch.allclose(a, c, rtol=1e-5, atol=1e-5)
+
+
+def test_row_major_order_band_table_for_the_streamed_sampler():
+    """``row_major_order(..., band_rows=r)``: the same ordering plus, per image, the index of the first point of every
+    band of r map rows (what native.sample_shared_points walks): bands are contiguous, cover all points, and every
+    point of band k has its footprint's top row in [k r, (k + 1) r) -- points above the map join band 0."""
+    from mp_former_b200 import native
+    from mp_former_b200.matcher import HungarianMatcher
+    g = torch.Generator().manual_seed(9)
+    for H, W, rows in ((256, 256, 95), (100, 36, 37), (24, 32, 24), (7, 8, 2)):
+        coords = torch.rand(3, 777, 2, generator=g)
+        coords[0, :4] = torch.tensor([[0.0, 0.0], [1.0, 1.0], [0.5, 0.0], [0.5, 1.0]])
+        srt, band_lo = HungarianMatcher.row_major_order(coords, H, W, band_rows=rows)
+        assert torch.equal(srt, HungarianMatcher.row_major_order(coords, H, W))
+        n_bands = -(-H // rows)
+        assert band_lo.dtype == torch.int32 and band_lo.shape == (3, n_bands + 1)
+        assert bool((band_lo[:, 0] == 0).all()) and bool((band_lo[:, -1] == 777).all())
+        assert bool((band_lo[:, 1:] >= band_lo[:, :-1]).all())
+        y0 = (srt[..., 1] * H - 0.5).floor().clamp(0, H - 1)
+        for b in range(3):
+            for k in range(n_bands):
+                lo, hi = int(band_lo[b, k]), int(band_lo[b, k + 1])
+                if hi > lo:
+                    assert float(y0[b, lo:hi].min()) >= k * rows and float(y0[b, lo:hi].max()) < (k + 1) * rows
+    r, n = native.shared_point_bands(256, 256)
+    assert (r + 1) * 256 * 4 <= native.SHARED_POINT_BAND_BYTES and r * n >= 256 and r * (n - 1) < 256
+    assert native.shared_point_bands(8, 8) == (8, 1)
